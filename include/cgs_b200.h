@@ -1,0 +1,151 @@
+/*
+ * cgs_b200.h -- C ABI of the B200-native collapsed-Gibbs LDA hot path.
+ *
+ * pycisTopic has no C FFI on this path: run_cgs_model drives the third-party `lda`
+ * package through its Python object protocol (reference src/pycisTopic/lda_models.py:248-287)
+ * and, beneath that, the Cython entry points `lda._lda._sample_topics(WS, DS, ZS, nzw, ndz,
+ * nz, alpha, eta, rands)` and `lda._lda._loglikelihood(nzw, ndz, nz, nd, alpha, eta)`
+ * (SURVEY.md section 8b.2).  This header is the device-resident equivalent a maintainer
+ * would bind instead (ctypes stub in INTEGRATION.md).  Plain pointers and sizes only.
+ *
+ * Conventions: every function returns 0 on success, non-zero on failure; the message is
+ * available from cgs_last_error() (thread-local).  The caller owns every host buffer; a
+ * handle owns its device state.  One corpus is bound to one CUDA device; any number of
+ * models (one per n_topics value) may share a corpus.  Functions are asynchronous on the
+ * model's stream unless they return data to the host.
+ *
+ * Layouts handed back to the host are the REFERENCE's: nzw (K x W), ndz (D x K), nz (K),
+ * int32 row-major; topic_word (K x W) and doc_topic (D x K) float64 (lda_models.py:292-293,
+ * :345-357).  On the device n_wk is kept region-major (W x Kp, Kp = K rounded up to 4) so
+ * that the sampler reads one contiguous row per token.
+ */
+#ifndef CGS_B200_H
+#define CGS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cgs_corpus cgs_corpus;
+typedef struct cgs_model cgs_model;
+
+/* ---- library ------------------------------------------------------------------------ */
+const char *cgs_last_error(void);
+int cgs_version(void);
+int cgs_device_count(int *count);
+int cgs_max_topics(void);
+
+/* ---- corpus: token-list construction on device (replaces lda_models.py:151 +
+ *      lda.utils.matrix_to_lists) -------------------------------------- */
+
+/* Build from the reference's CistopicObject.binary_matrix layout: CSR with n_regions rows
+ * and n_cells columns (host pointers; indptr int64[n_regions+1], indices int32[nnz] = cell
+ * ids).  The transpose to cell-major token order (cell ascending, region ascending) runs on
+ * the device.  Only cells in [cell_begin, cell_end) are kept (AD-LDA shard; pass 0, n_cells
+ * for everything).  Duplicate (region, cell) entries collapse to one token (binary data). */
+int cgs_corpus_from_regions_by_cells(cgs_corpus **out, int device,
+                                     const int64_t *indptr, const int32_t *indices,
+                                     int32_t n_regions, int32_t n_cells, int64_t nnz,
+                                     int32_t cell_begin, int32_t cell_end);
+
+/* Build from the layout run_cgs_model receives (lda_models.py:179): CSR with n_cells rows and
+ * n_regions columns; indices need not be sorted (they are canonicalised on the device). */
+int cgs_corpus_from_cells_by_regions(cgs_corpus **out, int device,
+                                     const int64_t *indptr, const int32_t *indices,
+                                     int32_t n_cells, int32_t n_regions, int64_t nnz,
+                                     int32_t cell_begin, int32_t cell_end);
+
+/* Same as cgs_corpus_from_cells_by_regions but the two arrays are DEVICE pointers on
+ * `device` (already canonical: sorted, unique); used by the benchmark for resident inputs. */
+int cgs_corpus_from_device_tokens(cgs_corpus **out, int device,
+                                  const int64_t *d_cell_ptr, const int32_t *d_tok_region,
+                                  int32_t n_cells, int32_t n_regions, int64_t n_tokens,
+                                  int64_t global_token_offset);
+
+int cgs_corpus_destroy(cgs_corpus *c);
+int cgs_corpus_dims(const cgs_corpus *c, int32_t *n_cells, int32_t *n_regions, int64_t *n_tokens);
+/* Token lists in the `lda` package's form: WS[i] = region id, DS[i] = cell id (local to the
+ * shard), int32[n_tokens] each; either pointer may be NULL. */
+int cgs_corpus_export_tokens(const cgs_corpus *c, int32_t *WS, int32_t *DS);
+/* Global index of this shard's first token (z initialisation is i mod K over GLOBAL i). */
+int cgs_corpus_set_token_offset(cgs_corpus *c, int64_t global_token_offset);
+
+/* ---- model: one lda.LDA instance (lda_models.py:248-287) ----------------------------- */
+
+/* alpha, eta are the values the sampler uses (already divided by K where the caller asked
+ * for *_by_topic, lda_models.py:247-282).  Fails for alpha <= 0 or eta <= 0 (lda raises
+ * ValueError).  `stream` is a cudaStream_t to launch on, or NULL for a private stream. */
+int cgs_model_create(cgs_model **out, cgs_corpus *corpus, int32_t n_topics,
+                     double alpha, double eta, uint64_t seed, void *stream);
+int cgs_model_destroy(cgs_model *m);
+int cgs_model_set_stream(cgs_model *m, void *stream);
+int cgs_model_sync(cgs_model *m);
+
+/* lda.LDA._initialize: z_i = i mod K, rebuild n_wk / n_dk / n_k (bit-exact). */
+int cgs_model_init(cgs_model *m);
+/* Replace the assignments by a host vector (int32[n_tokens], values in [0, K)) and rebuild
+ * the three count tables from it (bit-exact bookkeeping tests). */
+int cgs_model_set_z(cgs_model *m, const int32_t *z);
+int cgs_model_get_z(cgs_model *m, int32_t *z);
+
+/* n_sweeps collapsed-Gibbs sweeps over every token of the corpus (replaces
+ * lda._lda._sample_topics).  Asynchronous. */
+int cgs_model_sweep(cgs_model *m, int32_t n_sweeps);
+/* Kernel launches issued by this model so far (for bench.py's gpu_launches). */
+int cgs_model_launch_count(const cgs_model *m, int64_t *count);
+/* Number of sweeps done so far. */
+int cgs_model_sweeps_done(const cgs_model *m, int64_t *count);
+
+/* lda._lda._loglikelihood with the model's alpha, eta.  For an AD-LDA shard
+ * `partial` selects what is summed: 0 = everything, 1 = only the cell-side terms (n_dk, nd),
+ * 2 = only the region-side terms (n_wk, n_k). */
+int cgs_model_loglik(cgs_model *m, int partial, double *ll);
+
+/* Reference-layout exports (host pointers, any may be NULL). */
+int cgs_model_export_counts(cgs_model *m, int32_t *nzw, int32_t *ndz, int32_t *nz);
+int cgs_model_export_distributions(cgs_model *m, double *topic_word, double *doc_topic);
+/* DataFrame-ready layouts: topic_region (W x K) and cell_topic (K x D) float64
+ * (lda_models.py:348-357 build these by transposing; the device writes them directly). */
+int cgs_model_export_frames(cgs_model *m, double *topic_region, double *cell_topic);
+
+/* ---- AD-LDA exchange step ------------------------------------- */
+/* Device buffers a host framework may wrap (torch via __cuda_array_interface__) to run the
+ * collective: 0 = n_wk (int32, W*Kp), 1 = n_wk snapshot taken at the last exchange,
+ * 2 = delta buffer (int32, W*Kp), 3 = n_k (int32, Kp), 4 = n_dk (int32, D*Kp),
+ * 5 = z (uint16, n_tokens), 6 = token regions (int32, n_tokens), 7 = cell_ptr (int64, D+1). */
+int cgs_model_device_buffer(cgs_model *m, int which, void **ptr, size_t *bytes);
+int cgs_model_padded_topics(const cgs_model *m, int32_t *kp);
+/* delta = n_wk - snapshot (the local changes since the last exchange). */
+int cgs_model_delta_compute(cgs_model *m);
+/* n_wk = snapshot + delta (delta now holds the sum over ranks), snapshot = n_wk,
+ * n_k = column sums of n_wk. */
+int cgs_model_delta_apply(cgs_model *m);
+/* snapshot = n_wk (call once after init / set_z). */
+int cgs_model_snapshot(cgs_model *m);
+/* Peer-memory exchange: every rank passes the device pointers of ALL ranks' delta buffers
+ * (peer-mapped, n_ranks entries, own rank included) and ONE kernel reduces them and applies
+ * the result to the local n_wk / n_k.  The caller provides the cross-rank barrier before
+ * (all deltas computed) and after (all reads done). */
+int cgs_model_delta_apply_peers(cgs_model *m, void *const *peer_delta, int32_t n_ranks);
+
+/* ---- imputation (replaces the fp32 chunk product of diff_features.py:443-464) --------- */
+/* out[r, c] = trunc_int32( (sum_k topic_region[r, k] * cell_topic[k, c]) * scale ) when
+ * as_int32 != 0, else the fp32 product (times scale if scale != 1).  All pointers are HOST
+ * pointers; topic_region is n_regions x n_topics, cell_topic is n_topics x n_cells, both
+ * fp32 row-major.  row_nonzero[r] (uint8, may be NULL) flags rows with any non-zero entry. */
+int cgs_impute_chunk(int device, const float *topic_region, const float *cell_topic,
+                     int32_t n_regions, int32_t n_topics, int32_t n_cells,
+                     float scale, int as_int32, void *out, uint8_t *row_nonzero);
+/* Device-resident variant used by the benchmark (all pointers on `device`). */
+int cgs_impute_chunk_device(int device, const float *d_topic_region, const float *d_cell_topic,
+                            int32_t n_regions, int32_t n_topics, int32_t n_cells,
+                            float scale, int as_int32, void *d_out, uint8_t *d_row_nonzero,
+                            void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CGS_B200_H */

@@ -1,0 +1,72 @@
+"""Load the reference's OWN functions for this path straight from the read-only tree.
+
+TEST INFRASTRUCTURE ONLY.  ``pycisTopic`` cannot be imported here (its first third-party
+imports fail), but the functions of interest are plain NumPy/``math`` code, so their
+``FunctionDef`` nodes are extracted with ``ast`` and executed unmodified:
+
+* ``utils.loglikelihood``            /root/reference/src/pycisTopic/utils.py:129-160
+* ``utils.subset_list`` / ``non_zero_rows``                          utils.py:113-126
+* ``calculate_imputed_accessibility`` (nested)   diff_features.py:398-492
+* ``calculate_normalized_scores`` (nested)       diff_features.py:540-548
+
+Used in THIS container to generate ``tests/golden/*.npz`` (``tests/golden/make_golden.py``);
+the GPU box has no /root/reference, so tests there read the committed fixtures.
+"""
+from __future__ import annotations
+
+import ast
+import logging
+import math
+import os
+import typing
+
+import numpy as np
+import scipy.sparse as sparse
+
+REFERENCE_ROOT = os.environ.get("PYCISTOPIC_REFERENCE", "/root/reference")
+
+
+def available() -> bool:
+    return os.path.exists(os.path.join(REFERENCE_ROOT, "src", "pycisTopic", "utils.py"))
+
+
+def _find(tree, name):
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef) and node.name == name:
+            return node
+    raise KeyError(name)
+
+
+def _load(relpath, names, extra=None):
+    path = os.path.join(REFERENCE_ROOT, "src", "pycisTopic", relpath)
+    with open(path) as f:
+        tree = ast.parse(f.read())
+    ns = {"math": math, "np": np, "sparse": sparse, "typing": typing, "Union": typing.Union,
+          "Sequence": typing.Sequence, "log": logging.getLogger("reference")}
+    if extra:
+        ns.update(extra)
+    for name in names:
+        node = _find(tree, name)
+        node.decorator_list = []
+        node.returns = None
+        for a in node.args.args + node.args.kwonlyargs:
+            a.annotation = None
+        mod = ast.Module(body=[node], type_ignores=[])
+        ast.fix_missing_locations(mod)
+        exec(compile(mod, path, "exec"), ns)
+    return ns
+
+
+def reference_loglikelihood():
+    return _load("utils.py", ["loglikelihood"])["loglikelihood"]
+
+
+def reference_calculate_imputed_accessibility():
+    ns = _load("utils.py", ["subset_list", "non_zero_rows"])
+    ns = _load("diff_features.py", ["calculate_imputed_accessibility"],
+               extra={"subset_list": ns["subset_list"], "non_zero_rows": ns["non_zero_rows"]})
+    return ns["calculate_imputed_accessibility"]
+
+
+def reference_calculate_normalized_scores():
+    return _load("diff_features.py", ["calculate_normalized_scores"])["calculate_normalized_scores"]

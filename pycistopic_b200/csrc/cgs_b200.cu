@@ -1,0 +1,801 @@
+// cgs_b200.cu -- C ABI (include/cgs_b200.h) over the sm_100a kernels.
+#include "../../include/cgs_b200.h"
+
+#include <algorithm>
+#include <numeric>
+#include <vector>
+
+#include "common.cuh"
+#include "corpus_kernels.cuh"
+#include "impute_kernels.cuh"
+#include "sampler_kernels.cuh"
+#include "stats_kernels.cuh"
+
+namespace cgs {
+thread_local std::string g_last_error;
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+template <typename T>
+static int dmalloc(T **p, size_t n) {
+    *p = nullptr;
+    if (n == 0) n = 1;
+    CGS_CUDA(cudaMalloc((void **)p, n * sizeof(T)));
+    return 0;
+}
+}  // namespace cgs
+
+using namespace cgs;
+
+struct cgs_corpus {
+    int device = 0;
+    int num_sms = kNumSMsFallback;
+    int32_t n_cells = 0, n_regions = 0;
+    int64_t n_tokens = 0;
+    int64_t token_offset = 0;
+    int64_t *d_cell_ptr = nullptr;    // D+1
+    int32_t *d_tok_region = nullptr;  // N
+    int32_t *d_cell_order = nullptr;  // D, longest cell first
+    bool owns_tokens = true;
+    int n_models = 0;
+};
+
+struct cgs_model {
+    cgs_corpus *corpus = nullptr;
+    int32_t K = 0, Kp = 0;
+    double alpha = 0, eta = 0;
+    uint64_t seed = 0;
+    cudaStream_t stream = nullptr;
+    bool owns_stream = false;
+    uint16_t *d_z = nullptr;
+    int32_t *d_nwk = nullptr, *d_ndk = nullptr, *d_nk = nullptr;
+    int32_t *d_snap = nullptr, *d_delta = nullptr;  // AD-LDA, allocated on first use
+    int32_t *d_work = nullptr;                      // work-queue counters, one per sweep slot
+    double *d_partials = nullptr;                   // reduction scratch
+    int *d_flag = nullptr;
+    int64_t launches = 0;
+    int64_t sweeps = 0;
+    int tpt = 1, ch = 1;
+    int sweep_blocks = 0;
+};
+
+namespace cgs {
+
+static constexpr int kWorkSlots = 1024;
+static constexpr int kPartialBlocks = 1184;  // 148 SMs x 8
+
+static int query_sms(int device, int *sms) {
+    CGS_CUDA(cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, device));
+    if (*sms <= 0) *sms = kNumSMsFallback;
+    return 0;
+}
+
+// Orders cells longest-first on the host (D counts only) and uploads the schedule.
+static int build_cell_order(cgs_corpus *c) {
+    std::vector<int64_t> ptr((size_t)c->n_cells + 1);
+    CGS_CUDA(cudaMemcpy(ptr.data(), c->d_cell_ptr, sizeof(int64_t) * ptr.size(), cudaMemcpyDeviceToHost));
+    std::vector<int32_t> order((size_t)c->n_cells);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+        return (ptr[a + 1] - ptr[a]) > (ptr[b + 1] - ptr[b]);
+    });
+    CGS_TRY(dmalloc(&c->d_cell_order, order.size()));
+    CGS_CUDA(cudaMemcpy(c->d_cell_order, order.data(), sizeof(int32_t) * order.size(), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// Steps (4)-(5) of the construction: canonicalise every cell's segment and, if duplicates were
+// dropped, compact.  d_tmp holds the unsorted region ids, d_raw_ptr the segment offsets.
+static int canonicalise(cgs_corpus *c, int32_t *d_tmp, int64_t *d_raw_ptr, int64_t raw_total) {
+    const int32_t D = c->n_cells;
+    int32_t *d_sorted = nullptr;
+    unsigned long long *d_uniq = nullptr;
+    int *d_flag = nullptr;
+    CGS_TRY(dmalloc(&d_sorted, (size_t)raw_total));
+    CGS_TRY(dmalloc(&d_uniq, (size_t)D));
+    CGS_TRY(dmalloc(&d_flag, 1));
+    CGS_CUDA(cudaMemset(d_flag, 0, sizeof(int)));
+
+    int max_smem = 0;
+    CGS_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
+    int64_t words_needed = ((int64_t)c->n_regions + 31) / 32;
+    int64_t words_cap = (max_smem - 1024) / 4;
+    int32_t words = (int32_t)std::max<int64_t>(1, std::min(words_needed, words_cap));
+    size_t smem = (size_t)words * 4;
+    CGS_CUDA(cudaFuncSetAttribute(bitmap_sort_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int blocks = std::max(1, std::min(D, c->num_sms * (smem > 100 * 1024 ? 1 : 2)));
+    bitmap_sort_cells_kernel<<<blocks, 512, smem>>>(d_tmp, d_raw_ptr, D, c->n_regions, words, d_sorted, d_uniq, d_flag);
+    CGS_CUDA(cudaGetLastError());
+    int flag = 0;
+    CGS_CUDA(cudaMemcpy(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost));
+    if (flag) {
+        cudaFree(d_sorted); cudaFree(d_uniq); cudaFree(d_flag);
+        CGS_FAIL("matrix index out of range while building the token list");
+    }
+    CGS_TRY(dmalloc(&c->d_cell_ptr, (size_t)D + 1));
+    exclusive_scan_i64_kernel<<<1, 1024>>>(d_uniq, c->d_cell_ptr, D);
+    CGS_CUDA(cudaGetLastError());
+    int64_t total = 0;
+    CGS_CUDA(cudaMemcpy(&total, c->d_cell_ptr + D, sizeof(int64_t), cudaMemcpyDeviceToHost));
+    c->n_tokens = total;
+    if (total == raw_total) {
+        c->d_tok_region = d_sorted;
+    } else {
+        CGS_TRY(dmalloc(&c->d_tok_region, (size_t)total));
+        compact_cells_kernel<<<std::max(1, std::min(D, c->num_sms * 8)), 256>>>(d_sorted, d_raw_ptr, c->d_cell_ptr, D,
+                                                                               c->d_tok_region);
+        CGS_CUDA(cudaGetLastError());
+        CGS_CUDA(cudaDeviceSynchronize());
+        cudaFree(d_sorted);
+    }
+    cudaFree(d_uniq);
+    cudaFree(d_flag);
+    return build_cell_order(c);
+}
+
+static int corpus_common_init(cgs_corpus *c, int device) {
+    c->device = device;
+    CGS_TRY(query_sms(device, &c->num_sms));
+    return 0;
+}
+
+}  // namespace cgs
+
+// =============================================================================================
+extern "C" {
+
+const char *cgs_last_error(void) { return g_last_error.c_str(); }
+int cgs_version(void) { return 100; }
+int cgs_max_topics(void) { return kMaxTopics; }
+
+int cgs_device_count(int *count) {
+    if (!count) CGS_FAIL("count is NULL");
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) {
+        *count = 0;
+        CGS_FAIL(std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+    }
+    return 0;
+}
+
+int cgs_corpus_from_regions_by_cells(cgs_corpus **out, int device, const int64_t *indptr, const int32_t *indices,
+                                     int32_t n_regions, int32_t n_cells, int64_t nnz, int32_t cell_begin,
+                                     int32_t cell_end) {
+    if (!out || !indptr || (!indices && nnz > 0)) CGS_FAIL("NULL argument");
+    if (n_regions <= 0 || n_cells <= 0) CGS_FAIL("empty matrix");
+    if (cell_begin < 0 || cell_end > n_cells || cell_begin >= cell_end) CGS_FAIL("bad cell range");
+    if (indptr[n_regions] != nnz) CGS_FAIL("indptr[n_regions] != nnz");
+    DeviceGuard g(device);
+    if (!g.ok) CGS_FAIL("cannot select CUDA device");
+    cgs_corpus *c = new cgs_corpus();
+    *out = nullptr;
+    int rc = [&]() -> int {
+        CGS_TRY(corpus_common_init(c, device));
+        c->n_cells = cell_end - cell_begin;
+        c->n_regions = n_regions;
+        const int32_t D = c->n_cells;
+        int64_t *d_row_ptr = nullptr;
+        int32_t *d_idx = nullptr;
+        unsigned long long *d_count = nullptr, *d_fill = nullptr;
+        int64_t *d_raw_ptr = nullptr;
+        CGS_TRY(dmalloc(&d_row_ptr, (size_t)n_regions + 1));
+        CGS_TRY(dmalloc(&d_idx, (size_t)nnz));
+        CGS_TRY(dmalloc(&d_count, (size_t)D));
+        CGS_TRY(dmalloc(&d_fill, (size_t)D));
+        CGS_TRY(dmalloc(&d_raw_ptr, (size_t)D + 1));
+        CGS_CUDA(cudaMemcpy(d_row_ptr, indptr, sizeof(int64_t) * ((size_t)n_regions + 1), cudaMemcpyHostToDevice));
+        CGS_CUDA(cudaMemcpy(d_idx, indices, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice));
+        CGS_CUDA(cudaMemset(d_count, 0, sizeof(unsigned long long) * (size_t)D));
+        CGS_CUDA(cudaMemset(d_fill, 0, sizeof(unsigned long long) * (size_t)D));
+        const int blocks = c->num_sms * 8;
+        count_cells_kernel<<<blocks, 256>>>(d_idx, nnz, cell_begin, cell_end, d_count);
+        CGS_CUDA(cudaGetLastError());
+        exclusive_scan_i64_kernel<<<1, 1024>>>(d_count, d_raw_ptr, D);
+        CGS_CUDA(cudaGetLastError());
+        int64_t raw_total = 0;
+        CGS_CUDA(cudaMemcpy(&raw_total, d_raw_ptr + D, sizeof(int64_t), cudaMemcpyDeviceToHost));
+        int32_t *d_tmp = nullptr;
+        CGS_TRY(dmalloc(&d_tmp, (size_t)raw_total));
+        scatter_rows_kernel<<<blocks, 256>>>(d_row_ptr, d_idx, n_regions, cell_begin, cell_end, d_raw_ptr, d_fill, d_tmp);
+        CGS_CUDA(cudaGetLastError());
+        CGS_CUDA(cudaDeviceSynchronize());
+        cudaFree(d_row_ptr); cudaFree(d_idx); cudaFree(d_count); cudaFree(d_fill);
+        int r = canonicalise(c, d_tmp, d_raw_ptr, raw_total);
+        cudaFree(d_tmp); cudaFree(d_raw_ptr);
+        return r;
+    }();
+    if (rc != 0) { cgs_corpus_destroy(c); return rc; }
+    *out = c;
+    return 0;
+}
+
+int cgs_corpus_from_cells_by_regions(cgs_corpus **out, int device, const int64_t *indptr, const int32_t *indices,
+                                     int32_t n_cells, int32_t n_regions, int64_t nnz, int32_t cell_begin,
+                                     int32_t cell_end) {
+    if (!out || !indptr || (!indices && nnz > 0)) CGS_FAIL("NULL argument");
+    if (n_regions <= 0 || n_cells <= 0) CGS_FAIL("empty matrix");
+    if (cell_begin < 0 || cell_end > n_cells || cell_begin >= cell_end) CGS_FAIL("bad cell range");
+    if (indptr[n_cells] != nnz) CGS_FAIL("indptr[n_cells] != nnz");
+    DeviceGuard g(device);
+    if (!g.ok) CGS_FAIL("cannot select CUDA device");
+    cgs_corpus *c = new cgs_corpus();
+    *out = nullptr;
+    int rc = [&]() -> int {
+        CGS_TRY(corpus_common_init(c, device));
+        c->n_cells = cell_end - cell_begin;
+        c->n_regions = n_regions;
+        const int32_t D = c->n_cells;
+        const int64_t t0 = indptr[cell_begin], t1 = indptr[cell_end];
+        const int64_t raw_total = t1 - t0;
+        std::vector<int64_t> local_ptr((size_t)D + 1);
+        for (int32_t d = 0; d <= D; ++d) local_ptr[d] = indptr[cell_begin + d] - t0;
+        int64_t *d_raw_ptr = nullptr;
+        int32_t *d_tmp = nullptr;
+        CGS_TRY(dmalloc(&d_raw_ptr, (size_t)D + 1));
+        CGS_TRY(dmalloc(&d_tmp, (size_t)raw_total));
+        CGS_CUDA(cudaMemcpy(d_raw_ptr, local_ptr.data(), sizeof(int64_t) * local_ptr.size(), cudaMemcpyHostToDevice));
+        CGS_CUDA(cudaMemcpy(d_tmp, indices + t0, sizeof(int32_t) * (size_t)raw_total, cudaMemcpyHostToDevice));
+        int r = canonicalise(c, d_tmp, d_raw_ptr, raw_total);
+        cudaFree(d_tmp); cudaFree(d_raw_ptr);
+        return r;
+    }();
+    if (rc != 0) { cgs_corpus_destroy(c); return rc; }
+    *out = c;
+    return 0;
+}
+
+int cgs_corpus_from_device_tokens(cgs_corpus **out, int device, const int64_t *d_cell_ptr, const int32_t *d_tok_region,
+                                  int32_t n_cells, int32_t n_regions, int64_t n_tokens, int64_t global_token_offset) {
+    if (!out || !d_cell_ptr || !d_tok_region) CGS_FAIL("NULL argument");
+    if (n_regions <= 0 || n_cells <= 0) CGS_FAIL("empty matrix");
+    DeviceGuard g(device);
+    if (!g.ok) CGS_FAIL("cannot select CUDA device");
+    cgs_corpus *c = new cgs_corpus();
+    *out = nullptr;
+    int rc = [&]() -> int {
+        CGS_TRY(corpus_common_init(c, device));
+        c->n_cells = n_cells;
+        c->n_regions = n_regions;
+        c->n_tokens = n_tokens;
+        c->token_offset = global_token_offset;
+        c->owns_tokens = false;
+        c->d_cell_ptr = const_cast<int64_t *>(d_cell_ptr);
+        c->d_tok_region = const_cast<int32_t *>(d_tok_region);
+        return build_cell_order(c);
+    }();
+    if (rc != 0) { cgs_corpus_destroy(c); return rc; }
+    *out = c;
+    return 0;
+}
+
+int cgs_corpus_destroy(cgs_corpus *c) {
+    if (!c) return 0;
+    if (c->n_models > 0) CGS_FAIL("corpus still has live models");
+    DeviceGuard g(c->device);
+    if (c->owns_tokens) {
+        if (c->d_cell_ptr) cudaFree(c->d_cell_ptr);
+        if (c->d_tok_region) cudaFree(c->d_tok_region);
+    }
+    if (c->d_cell_order) cudaFree(c->d_cell_order);
+    delete c;
+    return 0;
+}
+
+int cgs_corpus_dims(const cgs_corpus *c, int32_t *n_cells, int32_t *n_regions, int64_t *n_tokens) {
+    if (!c) CGS_FAIL("NULL corpus");
+    if (n_cells) *n_cells = c->n_cells;
+    if (n_regions) *n_regions = c->n_regions;
+    if (n_tokens) *n_tokens = c->n_tokens;
+    return 0;
+}
+
+int cgs_corpus_set_token_offset(cgs_corpus *c, int64_t off) {
+    if (!c) CGS_FAIL("NULL corpus");
+    c->token_offset = off;
+    return 0;
+}
+
+int cgs_corpus_export_tokens(const cgs_corpus *c, int32_t *WS, int32_t *DS) {
+    if (!c) CGS_FAIL("NULL corpus");
+    DeviceGuard g(c->device);
+    CGS_CUDA(cudaDeviceSynchronize());
+    if (WS)
+        CGS_CUDA(cudaMemcpy(WS, c->d_tok_region, sizeof(int32_t) * (size_t)c->n_tokens, cudaMemcpyDeviceToHost));
+    if (DS) {
+        int32_t *d_ds = nullptr;
+        CGS_TRY(dmalloc(&d_ds, (size_t)c->n_tokens));
+        expand_cells_kernel<<<std::max(1, std::min(c->n_cells, c->num_sms * 8)), 256>>>(c->d_cell_ptr, c->n_cells, d_ds);
+        CGS_CUDA(cudaGetLastError());
+        CGS_CUDA(cudaMemcpy(DS, d_ds, sizeof(int32_t) * (size_t)c->n_tokens, cudaMemcpyDeviceToHost));
+        cudaFree(d_ds);
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+static void pick_sweep_shape(int32_t Kp, int *tpt, int *ch) {
+    const int chunks = Kp / 4;
+    // fewest lanes per token that still fit the row in <= 4 chunks per lane
+    int t = 1;
+    while (t * 4 < chunks) t <<= 1;
+    *tpt = t;
+    *ch = (chunks + t - 1) / t;
+}
+
+int cgs_model_create(cgs_model **out, cgs_corpus *corpus, int32_t n_topics, double alpha, double eta, uint64_t seed,
+                     void *stream) {
+    if (!out || !corpus) CGS_FAIL("NULL argument");
+    if (n_topics < 1) CGS_FAIL("n_topics must be >= 1");
+    if (n_topics > kMaxTopics) CGS_FAIL("n_topics exceeds cgs_max_topics()");
+    if (!(alpha > 0) || !(eta > 0)) CGS_FAIL("alpha and eta must be greater than zero");
+    DeviceGuard g(corpus->device);
+    if (!g.ok) CGS_FAIL("cannot select CUDA device");
+    cgs_model *m = new cgs_model();
+    *out = nullptr;
+    m->corpus = corpus;
+    corpus->n_models++;
+    int rc = [&]() -> int {
+        m->K = n_topics;
+        m->Kp = (n_topics + 3) & ~3;
+        m->alpha = alpha;
+        m->eta = eta;
+        m->seed = seed;
+        pick_sweep_shape(m->Kp, &m->tpt, &m->ch);
+        if (stream) {
+            m->stream = (cudaStream_t)stream;
+        } else {
+            CGS_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+            m->owns_stream = true;
+        }
+        const size_t W = (size_t)corpus->n_regions, D = (size_t)corpus->n_cells, Kp = (size_t)m->Kp;
+        CGS_TRY(dmalloc(&m->d_z, (size_t)corpus->n_tokens));
+        CGS_TRY(dmalloc(&m->d_nwk, W * Kp));
+        CGS_TRY(dmalloc(&m->d_ndk, D * Kp));
+        CGS_TRY(dmalloc(&m->d_nk, Kp));
+        CGS_TRY(dmalloc(&m->d_work, (size_t)kWorkSlots));
+        CGS_TRY(dmalloc(&m->d_partials, (size_t)kPartialBlocks * 2 + 8));
+        CGS_TRY(dmalloc(&m->d_flag, 1));
+        CGS_CUDA(cudaMemsetAsync(m->d_nwk, 0, sizeof(int32_t) * W * Kp, m->stream));
+        CGS_CUDA(cudaMemsetAsync(m->d_ndk, 0, sizeof(int32_t) * D * Kp, m->stream));
+        CGS_CUDA(cudaMemsetAsync(m->d_nk, 0, sizeof(int32_t) * Kp, m->stream));
+        CGS_CUDA(cudaMemsetAsync(m->d_z, 0, sizeof(uint16_t) * (size_t)corpus->n_tokens, m->stream));
+        m->sweep_blocks = 0;
+        return 0;
+    }();
+    if (rc != 0) { cgs_model_destroy(m); return rc; }
+    *out = m;
+    return 0;
+}
+
+int cgs_model_destroy(cgs_model *m) {
+    if (!m) return 0;
+    DeviceGuard g(m->corpus->device);
+    if (m->stream) cudaStreamSynchronize(m->stream);
+    cudaFree(m->d_z); cudaFree(m->d_nwk); cudaFree(m->d_ndk); cudaFree(m->d_nk);
+    cudaFree(m->d_snap); cudaFree(m->d_delta); cudaFree(m->d_work); cudaFree(m->d_partials); cudaFree(m->d_flag);
+    if (m->owns_stream && m->stream) cudaStreamDestroy(m->stream);
+    m->corpus->n_models--;
+    delete m;
+    return 0;
+}
+
+int cgs_model_set_stream(cgs_model *m, void *stream) {
+    if (!m) CGS_FAIL("NULL model");
+    DeviceGuard g(m->corpus->device);
+    CGS_CUDA(cudaStreamSynchronize(m->stream));
+    if (m->owns_stream) { cudaStreamDestroy(m->stream); m->owns_stream = false; }
+    if (stream) {
+        m->stream = (cudaStream_t)stream;
+    } else {
+        CGS_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+        m->owns_stream = true;
+    }
+    return 0;
+}
+
+int cgs_model_sync(cgs_model *m) {
+    if (!m) CGS_FAIL("NULL model");
+    DeviceGuard g(m->corpus->device);
+    CGS_CUDA(cudaStreamSynchronize(m->stream));
+    return 0;
+}
+
+static int rebuild_counts(cgs_model *m) {
+    cgs_corpus *c = m->corpus;
+    const size_t W = (size_t)c->n_regions, D = (size_t)c->n_cells, Kp = (size_t)m->Kp;
+    CGS_CUDA(cudaMemsetAsync(m->d_nwk, 0, sizeof(int32_t) * W * Kp, m->stream));
+    CGS_CUDA(cudaMemsetAsync(m->d_ndk, 0, sizeof(int32_t) * D * Kp, m->stream));
+    CGS_CUDA(cudaMemsetAsync(m->d_nk, 0, sizeof(int32_t) * Kp, m->stream));
+    const int blocks = std::max(1, std::min(c->n_cells, c->num_sms * 8));
+    count_kernel<<<blocks, 256, sizeof(int) * Kp, m->stream>>>(c->d_cell_ptr, c->d_tok_region, m->d_z, c->n_cells, m->K,
+                                                              m->Kp, m->d_nwk, m->d_ndk, m->d_nk);
+    CGS_CUDA(cudaGetLastError());
+    m->launches += 1;
+    return 0;
+}
+
+int cgs_model_init(cgs_model *m) {
+    if (!m) CGS_FAIL("NULL model");
+    cgs_corpus *c = m->corpus;
+    DeviceGuard g(c->device);
+    init_z_kernel<<<c->num_sms * 8, 256, 0, m->stream>>>(m->d_z, c->n_tokens, c->token_offset, m->K);
+    CGS_CUDA(cudaGetLastError());
+    m->launches += 1;
+    m->sweeps = 0;
+    return rebuild_counts(m);
+}
+
+int cgs_model_set_z(cgs_model *m, const int32_t *z) {
+    if (!m || !z) CGS_FAIL("NULL argument");
+    cgs_corpus *c = m->corpus;
+    DeviceGuard g(c->device);
+    int32_t *d_tmp = nullptr;
+    CGS_TRY(dmalloc(&d_tmp, (size_t)c->n_tokens));
+    CGS_CUDA(cudaMemcpyAsync(d_tmp, z, sizeof(int32_t) * (size_t)c->n_tokens, cudaMemcpyHostToDevice, m->stream));
+    CGS_CUDA(cudaMemsetAsync(m->d_flag, 0, sizeof(int), m->stream));
+    z_from_i32_kernel<<<c->num_sms * 8, 256, 0, m->stream>>>(d_tmp, m->d_z, c->n_tokens, m->K, m->d_flag);
+    CGS_CUDA(cudaGetLastError());
+    m->launches += 1;
+    int flag = 0;
+    CGS_CUDA(cudaMemcpyAsync(&flag, m->d_flag, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    CGS_CUDA(cudaStreamSynchronize(m->stream));
+    cudaFree(d_tmp);
+    if (flag) CGS_FAIL("z contains a topic outside [0, n_topics)");
+    return rebuild_counts(m);
+}
+
+int cgs_model_get_z(cgs_model *m, int32_t *z) {
+    if (!m || !z) CGS_FAIL("NULL argument");
+    cgs_corpus *c = m->corpus;
+    DeviceGuard g(c->device);
+    int32_t *d_tmp = nullptr;
+    CGS_TRY(dmalloc(&d_tmp, (size_t)c->n_tokens));
+    z_to_i32_kernel<<<c->num_sms * 8, 256, 0, m->stream>>>(m->d_z, d_tmp, c->n_tokens);
+    CGS_CUDA(cudaGetLastError());
+    m->launches += 1;
+    CGS_CUDA(cudaMemcpyAsync(z, d_tmp, sizeof(int32_t) * (size_t)c->n_tokens, cudaMemcpyDeviceToHost, m->stream));
+    CGS_CUDA(cudaStreamSynchronize(m->stream));
+    cudaFree(d_tmp);
+    return 0;
+}
+
+}  // extern "C"
+
+// ---- sweep dispatch --------------------------------------------------------------------------
+template <int TPT, int CH>
+static int launch_sweep(cgs_model *m, const SweepParams &p, int *blocks_cache) {
+    if (*blocks_cache == 0) {
+        int per_sm = 0;
+        CGS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep_kernel<TPT, CH>, kSweepThreads, 0));
+        if (per_sm < 1) per_sm = 1;
+        *blocks_cache = m->corpus->num_sms * per_sm;
+    }
+    const int blocks = std::max(1, std::min(*blocks_cache, m->corpus->n_cells));
+    sweep_kernel<TPT, CH><<<blocks, kSweepThreads, 0, m->stream>>>(p);
+    CGS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <int TPT>
+static int dispatch_ch(cgs_model *m, const SweepParams &p, int *bc) {
+    switch (m->ch) {
+        case 1: return launch_sweep<TPT, 1>(m, p, bc);
+        case 2: return launch_sweep<TPT, 2>(m, p, bc);
+        case 3: return launch_sweep<TPT, 3>(m, p, bc);
+        case 4: return launch_sweep<TPT, 4>(m, p, bc);
+    }
+    CGS_FAIL("unsupported chunk count");
+}
+
+static int dispatch_sweep(cgs_model *m, const SweepParams &p) {
+    int *bc = &m->sweep_blocks;
+    switch (m->tpt) {
+        case 1: return dispatch_ch<1>(m, p, bc);
+        case 2: return dispatch_ch<2>(m, p, bc);
+        case 4: return dispatch_ch<4>(m, p, bc);
+        case 8: return dispatch_ch<8>(m, p, bc);
+        case 16: return dispatch_ch<16>(m, p, bc);
+        case 32: return dispatch_ch<32>(m, p, bc);
+    }
+    CGS_FAIL("unsupported lanes-per-token");
+}
+
+extern "C" {
+
+int cgs_model_sweep(cgs_model *m, int32_t n_sweeps) {
+    if (!m) CGS_FAIL("NULL model");
+    if (n_sweeps < 0) CGS_FAIL("n_sweeps < 0");
+    cgs_corpus *c = m->corpus;
+    DeviceGuard g(c->device);
+    SweepParams p;
+    p.cell_ptr = c->d_cell_ptr;
+    p.tok_region = c->d_tok_region;
+    p.z = m->d_z;
+    p.n_wk = m->d_nwk;
+    p.n_dk = m->d_ndk;
+    p.n_k = m->d_nk;
+    p.cell_order = c->d_cell_order;
+    p.n_cells = c->n_cells;
+    p.K = m->K;
+    p.Kp = m->Kp;
+    p.alpha = (float)m->alpha;
+    p.eta = (float)m->eta;
+    p.etaW = (float)(m->eta * (double)c->n_regions);
+    p.seed_lo = (uint32_t)m->seed;
+    p.seed_hi = (uint32_t)(m->seed >> 32);
+    p.token_offset = c->token_offset;
+    for (int32_t s = 0; s < n_sweeps; ++s) {
+        const int slot = (int)(m->sweeps % kWorkSlots);
+        if (slot == 0) {
+            // a fresh bank of queue counters (stream-ordered after every sweep that used the last one)
+            CGS_CUDA(cudaMemsetAsync(m->d_work, 0, sizeof(int32_t) * kWorkSlots, m->stream));
+        }
+        p.work_counter = m->d_work + slot;
+        p.sweep = (uint32_t)m->sweeps;
+        CGS_TRY(dispatch_sweep(m, p));
+        m->launches += 1;
+        m->sweeps += 1;
+    }
+    return 0;
+}
+
+int cgs_model_launch_count(const cgs_model *m, int64_t *count) {
+    if (!m || !count) CGS_FAIL("NULL argument");
+    *count = m->launches;
+    return 0;
+}
+
+int cgs_model_sweeps_done(const cgs_model *m, int64_t *count) {
+    if (!m || !count) CGS_FAIL("NULL argument");
+    *count = m->sweeps;
+    return 0;
+}
+
+// ---- log-likelihood ---------------------------------------------------------------------------
+int cgs_model_loglik(cgs_model *m, int partial, double *ll) {
+    if (!m || !ll) CGS_FAIL("NULL argument");
+    if (partial < 0 || partial > 2) CGS_FAIL("partial must be 0, 1 or 2");
+    cgs_corpus *c = m->corpus;
+    DeviceGuard g(c->device);
+    const int64_t W = c->n_regions, D = c->n_cells;
+    const int32_t Kp = m->Kp;
+    double *part = m->d_partials;                    // [0, B): region side, [B, 2B): cell side
+    double *res = m->d_partials + 2 * kPartialBlocks;  // 4 scalars
+    CGS_CUDA(cudaMemsetAsync(res, 0, sizeof(double) * 4, m->stream));
+    const int B = kPartialBlocks;
+    if (partial == 0 || partial == 2) {
+        lgamma_sum_kernel<<<B, kReduceThreads, 0, m->stream>>>(m->d_nwk, W * Kp, m->eta, part);
+        final_sum_kernel<<<1, kReduceThreads, 0, m->stream>>>(part, B, res + 0);
+        topic_norm_sum_kernel<<<1, kReduceThreads, 0, m->stream>>>(m->d_nk, m->K, m->eta * (double)W, res + 1);
+        m->launches += 3;
+    }
+    if (partial == 0 || partial == 1) {
+        lgamma_sum_kernel<<<B, kReduceThreads, 0, m->stream>>>(m->d_ndk, D * Kp, m->alpha, part + B);
+        final_sum_kernel<<<1, kReduceThreads, 0, m->stream>>>(part + B, B, res + 2);
+        const int cb = (int)std::max<int64_t>(1, std::min<int64_t>(B, ceil_div(D, kReduceThreads)));
+        cell_norm_sum_kernel<<<cb, kReduceThreads, 0, m->stream>>>(c->d_cell_ptr, c->n_cells, m->alpha * m->K, part);
+        final_sum_kernel<<<1, kReduceThreads, 0, m->stream>>>(part, cb, res + 3);
+        m->launches += 4;
+    }
+    CGS_CUDA(cudaGetLastError());
+    double h[4];
+    CGS_CUDA(cudaMemcpyAsync(h, res, sizeof(double) * 4, cudaMemcpyDeviceToHost, m->stream));
+    CGS_CUDA(cudaStreamSynchronize(m->stream));
+    *ll = h[0] + h[1] + h[2] + h[3];
+    return 0;
+}
+
+// ---- exports ----------------------------------------------------------------------------------
+int cgs_model_export_counts(cgs_model *m, int32_t *nzw, int32_t *ndz, int32_t *nz) {
+    if (!m) CGS_FAIL("NULL model");
+    cgs_corpus *c = m->corpus;
+    DeviceGuard g(c->device);
+    const int64_t W = c->n_regions, D = c->n_cells;
+    const int32_t K = m->K, Kp = m->Kp;
+    if (nzw) {
+        int32_t *d_t = nullptr;
+        CGS_TRY(dmalloc(&d_t, (size_t)W * K));
+        dim3 grid((unsigned)ceil_div(W, 32), (unsigned)ceil_div(K, 32)), block(32, 8);
+        transpose_counts_kernel<<<grid, block, 0, m->stream>>>(m->d_nwk, W, K, Kp, d_t);
+        CGS_CUDA(cudaGetLastError());
+        m->launches += 1;
+        CGS_CUDA(cudaMemcpyAsync(nzw, d_t, sizeof(int32_t) * (size_t)W * K, cudaMemcpyDeviceToHost, m->stream));
+        CGS_CUDA(cudaStreamSynchronize(m->stream));
+        cudaFree(d_t);
+    }
+    if (ndz) {
+        int32_t *d_t = nullptr;
+        CGS_TRY(dmalloc(&d_t, (size_t)D * K));
+        unpad_counts_kernel<<<c->num_sms * 8, 256, 0, m->stream>>>(m->d_ndk, D, K, Kp, d_t);
+        CGS_CUDA(cudaGetLastError());
+        m->launches += 1;
+        CGS_CUDA(cudaMemcpyAsync(ndz, d_t, sizeof(int32_t) * (size_t)D * K, cudaMemcpyDeviceToHost, m->stream));
+        CGS_CUDA(cudaStreamSynchronize(m->stream));
+        cudaFree(d_t);
+    }
+    if (nz) {
+        CGS_CUDA(cudaMemcpyAsync(nz, m->d_nk, sizeof(int32_t) * (size_t)K, cudaMemcpyDeviceToHost, m->stream));
+        CGS_CUDA(cudaStreamSynchronize(m->stream));
+    }
+    return 0;
+}
+
+static int export_dist(cgs_model *m, double *topic_side, int topic_transposed, double *cell_side, int cell_transposed) {
+    cgs_corpus *c = m->corpus;
+    const int64_t W = c->n_regions, D = c->n_cells;
+    const int32_t K = m->K, Kp = m->Kp;
+    dim3 block(32, 8);
+    if (topic_side) {
+        double *d_t = nullptr;
+        CGS_TRY(dmalloc(&d_t, (size_t)W * K));
+        dim3 grid((unsigned)ceil_div(W, 32), (unsigned)ceil_div(K, 32));
+        topic_word_kernel<<<grid, block, 0, m->stream>>>(m->d_nwk, m->d_nk, W, K, Kp, m->eta, topic_transposed, d_t);
+        CGS_CUDA(cudaGetLastError());
+        m->launches += 1;
+        CGS_CUDA(cudaMemcpyAsync(topic_side, d_t, sizeof(double) * (size_t)W * K, cudaMemcpyDeviceToHost, m->stream));
+        CGS_CUDA(cudaStreamSynchronize(m->stream));
+        cudaFree(d_t);
+    }
+    if (cell_side) {
+        double *d_t = nullptr;
+        CGS_TRY(dmalloc(&d_t, (size_t)D * K));
+        dim3 grid((unsigned)ceil_div(D, 32), (unsigned)ceil_div(K, 32));
+        doc_topic_kernel<<<grid, block, 0, m->stream>>>(m->d_ndk, c->d_cell_ptr, D, K, Kp, m->alpha, cell_transposed, d_t);
+        CGS_CUDA(cudaGetLastError());
+        m->launches += 1;
+        CGS_CUDA(cudaMemcpyAsync(cell_side, d_t, sizeof(double) * (size_t)D * K, cudaMemcpyDeviceToHost, m->stream));
+        CGS_CUDA(cudaStreamSynchronize(m->stream));
+        cudaFree(d_t);
+    }
+    return 0;
+}
+
+int cgs_model_export_distributions(cgs_model *m, double *topic_word, double *doc_topic) {
+    if (!m) CGS_FAIL("NULL model");
+    DeviceGuard g(m->corpus->device);
+    return export_dist(m, topic_word, 1, doc_topic, 0);
+}
+
+int cgs_model_export_frames(cgs_model *m, double *topic_region, double *cell_topic) {
+    if (!m) CGS_FAIL("NULL model");
+    DeviceGuard g(m->corpus->device);
+    return export_dist(m, topic_region, 0, cell_topic, 1);
+}
+
+// ---- AD-LDA exchange ---------------------------------------------------------------------------
+static int ensure_exchange_buffers(cgs_model *m) {
+    const size_t n = (size_t)m->corpus->n_regions * (size_t)m->Kp;
+    if (!m->d_snap) CGS_TRY(dmalloc(&m->d_snap, n));
+    if (!m->d_delta) CGS_TRY(dmalloc(&m->d_delta, n));
+    return 0;
+}
+
+int cgs_model_device_buffer(cgs_model *m, int which, void **ptr, size_t *bytes) {
+    if (!m || !ptr || !bytes) CGS_FAIL("NULL argument");
+    cgs_corpus *c = m->corpus;
+    DeviceGuard g(c->device);
+    const size_t WK = (size_t)c->n_regions * (size_t)m->Kp;
+    switch (which) {
+        case 0: *ptr = m->d_nwk; *bytes = WK * 4; return 0;
+        case 1: CGS_TRY(ensure_exchange_buffers(m)); *ptr = m->d_snap; *bytes = WK * 4; return 0;
+        case 2: CGS_TRY(ensure_exchange_buffers(m)); *ptr = m->d_delta; *bytes = WK * 4; return 0;
+        case 3: *ptr = m->d_nk; *bytes = (size_t)m->Kp * 4; return 0;
+        case 4: *ptr = m->d_ndk; *bytes = (size_t)c->n_cells * (size_t)m->Kp * 4; return 0;
+        case 5: *ptr = m->d_z; *bytes = (size_t)c->n_tokens * 2; return 0;
+        case 6: *ptr = c->d_tok_region; *bytes = (size_t)c->n_tokens * 4; return 0;
+        case 7: *ptr = c->d_cell_ptr; *bytes = ((size_t)c->n_cells + 1) * 8; return 0;
+    }
+    CGS_FAIL("unknown buffer id");
+}
+
+int cgs_model_padded_topics(const cgs_model *m, int32_t *kp) {
+    if (!m || !kp) CGS_FAIL("NULL argument");
+    *kp = m->Kp;
+    return 0;
+}
+
+int cgs_model_snapshot(cgs_model *m) {
+    if (!m) CGS_FAIL("NULL model");
+    DeviceGuard g(m->corpus->device);
+    CGS_TRY(ensure_exchange_buffers(m));
+    const size_t n = (size_t)m->corpus->n_regions * (size_t)m->Kp;
+    CGS_CUDA(cudaMemcpyAsync(m->d_snap, m->d_nwk, n * 4, cudaMemcpyDeviceToDevice, m->stream));
+    return 0;
+}
+
+int cgs_model_delta_compute(cgs_model *m) {
+    if (!m) CGS_FAIL("NULL model");
+    DeviceGuard g(m->corpus->device);
+    CGS_TRY(ensure_exchange_buffers(m));
+    const int64_t n4 = (int64_t)m->corpus->n_regions * m->Kp / 4;
+    delta_compute_kernel<<<m->corpus->num_sms * 8, 256, 0, m->stream>>>((const int4 *)m->d_nwk, (const int4 *)m->d_snap,
+                                                                       (int4 *)m->d_delta, n4);
+    CGS_CUDA(cudaGetLastError());
+    m->launches += 1;
+    return 0;
+}
+
+static int delta_apply_common(cgs_model *m, const PeerPtrs &peers, int n_ranks) {
+    const int64_t n4 = (int64_t)m->corpus->n_regions * m->Kp / 4;
+    CGS_CUDA(cudaMemsetAsync(m->d_nk, 0, sizeof(int32_t) * (size_t)m->Kp, m->stream));
+    delta_apply_kernel<<<m->corpus->num_sms * 4, 256, sizeof(int) * (size_t)m->Kp, m->stream>>>(
+        (int4 *)m->d_nwk, (int4 *)m->d_snap, peers, n_ranks, n4, m->Kp / 4, m->d_nk);
+    CGS_CUDA(cudaGetLastError());
+    m->launches += 1;
+    return 0;
+}
+
+int cgs_model_delta_apply(cgs_model *m) {
+    if (!m) CGS_FAIL("NULL model");
+    DeviceGuard g(m->corpus->device);
+    CGS_TRY(ensure_exchange_buffers(m));
+    PeerPtrs peers;
+    memset(&peers, 0, sizeof peers);
+    peers.p[0] = (const int4 *)m->d_delta;
+    return delta_apply_common(m, peers, 1);
+}
+
+int cgs_model_delta_apply_peers(cgs_model *m, void *const *peer_delta, int32_t n_ranks) {
+    if (!m || !peer_delta) CGS_FAIL("NULL argument");
+    if (n_ranks < 1 || n_ranks > kMaxPeers) CGS_FAIL("n_ranks out of range");
+    DeviceGuard g(m->corpus->device);
+    CGS_TRY(ensure_exchange_buffers(m));
+    PeerPtrs peers;
+    memset(&peers, 0, sizeof peers);
+    for (int r = 0; r < n_ranks; ++r) {
+        if (!peer_delta[r]) CGS_FAIL("NULL peer pointer");
+        peers.p[r] = (const int4 *)peer_delta[r];
+    }
+    return delta_apply_common(m, peers, n_ranks);
+}
+
+// ---- imputation --------------------------------------------------------------------------------
+int cgs_impute_chunk_device(int device, const float *d_topic_region, const float *d_cell_topic, int32_t n_regions,
+                            int32_t n_topics, int32_t n_cells, float scale, int as_int32, void *d_out,
+                            uint8_t *d_row_nonzero, void *stream) {
+    if (!d_topic_region || !d_cell_topic || !d_out) CGS_FAIL("NULL argument");
+    if (n_regions <= 0 || n_topics <= 0 || n_cells <= 0) CGS_FAIL("empty operand");
+    DeviceGuard g(device);
+    if (!g.ok) CGS_FAIL("cannot select CUDA device");
+    return impute_launch(device, d_topic_region, d_cell_topic, n_regions, n_topics, n_cells, scale, as_int32, d_out,
+                         d_row_nonzero, (cudaStream_t)stream);
+}
+
+int cgs_impute_chunk(int device, const float *topic_region, const float *cell_topic, int32_t n_regions,
+                     int32_t n_topics, int32_t n_cells, float scale, int as_int32, void *out, uint8_t *row_nonzero) {
+    if (!topic_region || !cell_topic || !out) CGS_FAIL("NULL argument");
+    if (n_regions <= 0 || n_topics <= 0 || n_cells <= 0) CGS_FAIL("empty operand");
+    DeviceGuard g(device);
+    if (!g.ok) CGS_FAIL("cannot select CUDA device");
+    float *d_a = nullptr, *d_b = nullptr;
+    void *d_o = nullptr;
+    uint8_t *d_f = nullptr;
+    const size_t na = (size_t)n_regions * n_topics, nb = (size_t)n_topics * n_cells, no = (size_t)n_regions * n_cells;
+    int rc = [&]() -> int {
+        CGS_TRY(dmalloc(&d_a, na));
+        CGS_TRY(dmalloc(&d_b, nb));
+        CGS_CUDA(cudaMalloc(&d_o, no * 4));
+        CGS_TRY(dmalloc(&d_f, (size_t)n_regions));
+        CGS_CUDA(cudaMemcpy(d_a, topic_region, na * 4, cudaMemcpyHostToDevice));
+        CGS_CUDA(cudaMemcpy(d_b, cell_topic, nb * 4, cudaMemcpyHostToDevice));
+        CGS_TRY(impute_launch(device, d_a, d_b, n_regions, n_topics, n_cells, scale, as_int32, d_o, d_f, nullptr));
+        CGS_CUDA(cudaDeviceSynchronize());
+        CGS_CUDA(cudaMemcpy(out, d_o, no * 4, cudaMemcpyDeviceToHost));
+        if (row_nonzero) CGS_CUDA(cudaMemcpy(row_nonzero, d_f, (size_t)n_regions, cudaMemcpyDeviceToHost));
+        return 0;
+    }();
+    cudaFree(d_a); cudaFree(d_b); cudaFree(d_o); cudaFree(d_f);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,321 @@
+"""``lda.LDA``-protocol front end of the device sampler.
+
+pycisTopic's ``run_cgs_model`` builds ``lda.LDA(n_topics, n_iter, random_state, alpha, eta,
+refresh)``, calls ``.fit(X)`` and reads ``topic_word_``, ``doc_topic_``, ``nzw_``, ``ndz_``,
+``nz_`` (reference src/pycisTopic/lda_models.py:248-287, :292-305, :345-357).  This module
+provides the same object protocol on top of the C ABI (``include/cgs_b200.h``); every count
+and every sweep lives on the GPU.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+import logging
+
+import numpy as np
+import scipy.sparse as sparse
+
+from . import _lib
+from ._lib import c_f64p, c_i32p, c_i64p, c_vp, check, ptr
+
+logger = logging.getLogger("lda")
+
+
+def _as_binary_csr(X, what):
+    """Canonical int32/int64 CSR arrays of a binary matrix; rejects what `lda` would reject."""
+    if not sparse.issparse(X):
+        X = sparse.csr_matrix(np.asarray(X))
+    X = X.tocsr()
+    if not np.issubdtype(X.dtype, np.integer) and not np.issubdtype(X.dtype, np.bool_):
+        # lda.utils.matrix_to_lists: "expected sparse matrix with integer values, found float values"
+        if X.nnz and not np.all(np.equal(np.mod(X.data, 1), 0)):
+            raise ValueError("expected sparse matrix with integer values, found float values")
+    if X.nnz and X.data.max() > 1:
+        raise ValueError(
+            f"{what} must be binary (0/1), as CistopicObject.binary_matrix is; found a value of {X.data.max()}"
+        )
+    if X.nnz and X.data.min() < 1:
+        X = X.copy()
+        X.eliminate_zeros()
+    indptr = np.ascontiguousarray(X.indptr, dtype=np.int64)
+    indices = np.ascontiguousarray(X.indices, dtype=np.int32)
+    return X.shape, indptr, indices
+
+
+class Corpus:
+    """Device-resident token list of one binary accessibility matrix (one GPU).
+
+    Built either from the reference's ``binary_matrix`` layout (regions x cells; the transpose
+    of lda_models.py:151 happens on the device) or from the cells x regions CSR that
+    ``run_cgs_model`` receives.  ``cell_range`` keeps a contiguous shard of cells (AD-LDA).
+    """
+
+    def __init__(self, handle, device):
+        self._h = handle
+        self.device = device
+        L = _lib.load()
+        d, w, n = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int64()
+        check(L.cgs_corpus_dims(self._h, ctypes.byref(d), ctypes.byref(w), ctypes.byref(n)))
+        self.n_cells, self.n_regions, self.n_tokens = d.value, w.value, n.value
+
+    @classmethod
+    def from_regions_by_cells(cls, binary_matrix, device=0, cell_range=None):
+        _lib.require_device()
+        (W, D), indptr, indices = _as_binary_csr(binary_matrix, "binary_matrix")
+        cb, ce = cell_range if cell_range is not None else (0, D)
+        h = c_vp()
+        check(_lib.load().cgs_corpus_from_regions_by_cells(ctypes.byref(h), device, ptr(indptr, c_i64p),
+                                                          ptr(indices, c_i32p), W, D, len(indices), cb, ce))
+        return cls(h, device)
+
+    @classmethod
+    def from_cells_by_regions(cls, X, device=0, cell_range=None):
+        _lib.require_device()
+        (D, W), indptr, indices = _as_binary_csr(X, "X")
+        cb, ce = cell_range if cell_range is not None else (0, D)
+        h = c_vp()
+        check(_lib.load().cgs_corpus_from_cells_by_regions(ctypes.byref(h), device, ptr(indptr, c_i64p),
+                                                          ptr(indices, c_i32p), D, W, len(indices), cb, ce))
+        return cls(h, device)
+
+    @classmethod
+    def from_device_tokens(cls, cell_ptr_addr, tok_region_addr, n_cells, n_regions, n_tokens, device=0,
+                           token_offset=0, keepalive=None):
+        """Wrap canonical token arrays already resident on ``device`` (raw device addresses)."""
+        _lib.require_device()
+        h = c_vp()
+        check(_lib.load().cgs_corpus_from_device_tokens(ctypes.byref(h), device, c_vp(cell_ptr_addr),
+                                                       c_vp(tok_region_addr), n_cells, n_regions, n_tokens,
+                                                       token_offset))
+        obj = cls(h, device)
+        obj._keepalive = keepalive
+        return obj
+
+    def set_token_offset(self, offset: int):
+        check(_lib.load().cgs_corpus_set_token_offset(self._h, int(offset)))
+
+    def token_lists(self):
+        """(WS, DS) exactly as ``lda.utils.matrix_to_lists`` returns them."""
+        WS = np.empty(self.n_tokens, np.int32)
+        DS = np.empty(self.n_tokens, np.int32)
+        check(_lib.load().cgs_corpus_export_tokens(self._h, ptr(WS, c_i32p), ptr(DS, c_i32p)))
+        return WS, DS
+
+    def close(self):
+        if self._h is not None:
+            check(_lib.load().cgs_corpus_destroy(self._h))
+            self._h = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) is not None and _lib._lib is not None:
+                _lib._lib.cgs_corpus_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+class DeviceModel:
+    """One collapsed-Gibbs chain on a :class:`Corpus` (thin wrapper over ``cgs_model_*``)."""
+
+    def __init__(self, corpus: Corpus, n_topics: int, alpha: float, eta: float, seed: int = 0, stream=None):
+        if alpha <= 0 or eta <= 0:
+            raise ValueError("alpha and eta must be greater than zero")
+        self.corpus = corpus
+        self.n_topics = int(n_topics)
+        self.alpha = float(alpha)
+        self.eta = float(eta)
+        h = c_vp()
+        check(_lib.load().cgs_model_create(ctypes.byref(h), corpus._h, self.n_topics, self.alpha, self.eta,
+                                          int(seed) & 0xFFFFFFFFFFFFFFFF, c_vp(stream) if stream else None))
+        self._h = h
+
+    # -- state ---------------------------------------------------------------------------
+    def init(self):
+        check(_lib.load().cgs_model_init(self._h))
+
+    def set_z(self, z):
+        z = np.ascontiguousarray(z, dtype=np.int32)
+        if z.shape[0] != self.corpus.n_tokens:
+            raise ValueError("z has the wrong length")
+        check(_lib.load().cgs_model_set_z(self._h, ptr(z, c_i32p)))
+
+    def get_z(self):
+        z = np.empty(self.corpus.n_tokens, np.int32)
+        check(_lib.load().cgs_model_get_z(self._h, ptr(z, c_i32p)))
+        return z
+
+    def set_stream(self, stream):
+        check(_lib.load().cgs_model_set_stream(self._h, c_vp(stream) if stream else None))
+
+    def sync(self):
+        check(_lib.load().cgs_model_sync(self._h))
+
+    # -- hot path ------------------------------------------------------------------------
+    def sweep(self, n_sweeps: int = 1):
+        check(_lib.load().cgs_model_sweep(self._h, int(n_sweeps)))
+
+    def loglikelihood(self, partial: int = 0) -> float:
+        ll = ctypes.c_double()
+        check(_lib.load().cgs_model_loglik(self._h, partial, ctypes.byref(ll)))
+        return ll.value
+
+    @property
+    def launch_count(self) -> int:
+        n = ctypes.c_int64()
+        check(_lib.load().cgs_model_launch_count(self._h, ctypes.byref(n)))
+        return n.value
+
+    @property
+    def sweeps_done(self) -> int:
+        n = ctypes.c_int64()
+        check(_lib.load().cgs_model_sweeps_done(self._h, ctypes.byref(n)))
+        return n.value
+
+    # -- exports -------------------------------------------------------------------------
+    def counts(self, nzw=True, ndz=True, nz=True):
+        K, W, D = self.n_topics, self.corpus.n_regions, self.corpus.n_cells
+        a = np.empty((K, W), np.int32) if nzw else None
+        b = np.empty((D, K), np.int32) if ndz else None
+        c = np.empty(K, np.int32) if nz else None
+        check(_lib.load().cgs_model_export_counts(self._h, ptr(a, c_i32p) if nzw else None,
+                                                 ptr(b, c_i32p) if ndz else None, ptr(c, c_i32p) if nz else None))
+        return a, b, c
+
+    def distributions(self, topic_word=True, doc_topic=True):
+        K, W, D = self.n_topics, self.corpus.n_regions, self.corpus.n_cells
+        a = np.empty((K, W), np.float64) if topic_word else None
+        b = np.empty((D, K), np.float64) if doc_topic else None
+        check(_lib.load().cgs_model_export_distributions(self._h, ptr(a, c_f64p) if topic_word else None,
+                                                        ptr(b, c_f64p) if doc_topic else None))
+        return a, b
+
+    def frames(self, topic_region=True, cell_topic=True):
+        """(topic_region W x K, cell_topic K x D) float64: the DataFrame layouts of lda_models.py:348-357."""
+        K, W, D = self.n_topics, self.corpus.n_regions, self.corpus.n_cells
+        a = np.empty((W, K), np.float64) if topic_region else None
+        b = np.empty((K, D), np.float64) if cell_topic else None
+        check(_lib.load().cgs_model_export_frames(self._h, ptr(a, c_f64p) if topic_region else None,
+                                                 ptr(b, c_f64p) if cell_topic else None))
+        return a, b
+
+    # -- AD-LDA exchange -------------------------------------------------------------------
+    @property
+    def padded_topics(self) -> int:
+        kp = ctypes.c_int32()
+        check(_lib.load().cgs_model_padded_topics(self._h, ctypes.byref(kp)))
+        return kp.value
+
+    _BUF = {"n_wk": (0, "<i4"), "snapshot": (1, "<i4"), "delta": (2, "<i4"), "n_k": (3, "<i4"),
+            "n_dk": (4, "<i4"), "z": (5, "<u2"), "tok_region": (6, "<i4"), "cell_ptr": (7, "<i8")}
+
+    def device_buffer(self, name: str):
+        """(address, nbytes, zero-copy view with ``__cuda_array_interface__``) of a handle-owned buffer."""
+        which, typestr = self._BUF[name]
+        p, n = c_vp(), ctypes.c_size_t()
+        check(_lib.load().cgs_model_device_buffer(self._h, which, ctypes.byref(p), ctypes.byref(n)))
+        itemsize = int(typestr[2:])
+        return p.value, n.value, _lib.DeviceArrayView(p.value, (n.value // itemsize,), typestr, owner=self)
+
+    def snapshot(self):
+        check(_lib.load().cgs_model_snapshot(self._h))
+
+    def delta_compute(self):
+        check(_lib.load().cgs_model_delta_compute(self._h))
+
+    def delta_apply(self):
+        check(_lib.load().cgs_model_delta_apply(self._h))
+
+    def delta_apply_peers(self, addresses):
+        arr = (c_vp * len(addresses))(*[c_vp(a) for a in addresses])
+        check(_lib.load().cgs_model_delta_apply_peers(self._h, arr, len(addresses)))
+
+    def close(self):
+        if self._h is not None:
+            check(_lib.load().cgs_model_destroy(self._h))
+            self._h = None
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) is not None and _lib._lib is not None:
+                _lib._lib.cgs_model_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
+class LDA:
+    """Drop-in for ``lda.LDA`` as pycisTopic uses it (lda_models.py:248-287).
+
+    Parameters follow the ``lda`` package.  ``fit`` accepts the cells x regions binary CSR that
+    ``run_cgs_model`` passes; the sweeps run on ``device``.  After ``fit``:
+    ``topic_word_``/``components_`` (K x W), ``doc_topic_`` (D x K), ``nzw_``, ``ndz_``, ``nz_``
+    and ``loglikelihoods_`` (the true Griffiths-Steyvers log-likelihood every ``refresh``
+    sweeps, starting with sweep 0, as the package logs it).
+    """
+
+    def __init__(self, n_topics, n_iter=2000, alpha=0.1, eta=0.01, random_state=None, refresh=10,
+                 device=0, corpus: Corpus | None = None, lazy_exports=False):
+        self.n_topics = n_topics
+        self.n_iter = n_iter
+        self.alpha = alpha
+        self.eta = eta
+        self.random_state = random_state
+        self.refresh = refresh
+        self.device = device
+        self._corpus = corpus
+        self._lazy = lazy_exports
+        if alpha <= 0 or eta <= 0:
+            raise ValueError("alpha and eta must be greater than zero")
+        if random_state is None:
+            self._seed = int(np.random.SeedSequence().generate_state(1, np.uint64)[0])
+        elif isinstance(random_state, (int, np.integer)):
+            self._seed = int(random_state)
+        else:  # numpy RandomState, as lda.utils.check_random_state accepts
+            self._seed = int(random_state.randint(0, 2 ** 31 - 1))
+
+    def fit(self, X, y=None):
+        self._fit(X)
+        return self
+
+    def fit_transform(self, X, y=None):
+        self._fit(X)
+        return self.doc_topic_
+
+    def _fit(self, X):
+        own_corpus = False
+        corpus = self._corpus
+        if corpus is None:
+            corpus = Corpus.from_cells_by_regions(X, device=self.device)
+            own_corpus = True
+        model = DeviceModel(corpus, self.n_topics, self.alpha, self.eta, seed=self._seed)
+        try:
+            model.init()
+            self.loglikelihoods_ = []
+            done = 0
+            refresh = max(1, int(self.refresh))
+            while done < self.n_iter:
+                if done % refresh == 0:
+                    ll = model.loglikelihood()
+                    logger.info("<%d> log likelihood: %.0f", done, ll)
+                    self.loglikelihoods_.append(ll)
+                step = min(refresh - done % refresh, self.n_iter - done)
+                model.sweep(step)
+                done += step
+            ll = model.loglikelihood()
+            logger.info("<%d> log likelihood: %.0f", self.n_iter - 1, ll)
+            self.final_loglikelihood_ = ll
+            self.nzw_, self.ndz_, self.nz_ = model.counts()
+            self.components_, self.doc_topic_ = model.distributions()
+            self.topic_word_ = self.components_
+            # DataFrame-ready layouts straight from the device (no host transpose)
+            self.topic_region_, self.cell_topic_ = model.frames()
+            self.launch_count_ = model.launch_count
+        finally:
+            model.close()
+            if own_corpus:
+                corpus.close()
+        return self
+
+    def loglikelihood(self):
+        """True log-likelihood of the fitted counts (lda.LDA.loglikelihood)."""
+        return self.final_loglikelihood_

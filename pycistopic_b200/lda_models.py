@@ -1,0 +1,368 @@
+"""Drop-in mirror of ``pycisTopic.lda_models`` for the collapsed-Gibbs path.
+
+Same public names, argument meaning and result layout as the reference
+(src/pycisTopic/lda_models.py): :class:`CistopicLDAModel` (:31-96), :func:`run_cgs_models`
+(:99-175), :func:`run_cgs_model` (:178-396), :func:`evaluate_models` (:1048-1270),
+:func:`load_cisTopic_model` (:1273-1289).  What changed is underneath: the token list is built
+on the GPU, the sweeps run in hand-written sm_100a kernels behind the C ABI, and the
+``n_topics`` models are spread over the visible GPUs (one model per GPU at a time, longest
+first) instead of over Ray worker processes.  Ray-only keyword arguments (``_temp_dir`` ...)
+are accepted and ignored; ``n_cpu`` is accepted and ignored.
+"""
+from __future__ import annotations
+
+import logging
+import os
+import pickle
+import sys
+import threading
+import time
+import warnings
+
+import numpy as np
+import pandas as pd
+from scipy import sparse
+
+from . import _lib
+from . import metrics as _metrics
+from .lda import LDA, Corpus
+
+__all__ = ["CistopicLDAModel", "run_cgs_models", "run_cgs_model", "evaluate_models", "load_cisTopic_model"]
+
+
+class CistopicLDAModel:
+    """cisTopic LDA model container -- attribute-for-attribute the reference class
+    (lda_models.py:31-96): ``metrics``, ``coherence``, ``marg_topic``, ``topic_ass``,
+    ``cell_topic`` (topics x cells), ``cell_topic_harmony``, ``topic_region`` (regions x topics),
+    ``parameters``, ``n_cells``, ``n_regions``, ``n_topic``."""
+
+    def __init__(self, metrics, coherence, marg_topic, topic_ass, cell_topic, topic_region, parameters):
+        self.metrics = metrics
+        self.coherence = coherence
+        self.marg_topic = marg_topic
+        self.topic_ass = topic_ass
+        self.cell_topic = cell_topic
+        self.cell_topic_harmony = []
+        self.topic_region = topic_region
+        self.parameters = parameters
+        self.n_cells = cell_topic.shape[1]
+        self.n_regions = topic_region.shape[0]
+        self.n_topic = cell_topic.shape[0]
+
+    def __str__(self):
+        return (f"CistopicLDAModel with {self.n_topic} topics and n_cells × n_regions = "
+                f"{self.n_cells} × {self.n_regions}")
+
+
+def _logger():
+    level = logging.INFO
+    log_format = "%(asctime)s %(name)-12s %(levelname)-8s %(message)s"
+    handlers = [logging.StreamHandler(stream=sys.stdout)]
+    logging.basicConfig(level=level, format=log_format, handlers=handlers)
+    return logging.getLogger("cisTopic")
+
+
+def model_cost(n_topics: int) -> float:
+    """Relative cost of one sweep: algorithmic bytes per token-update, 4K + 28."""
+    return 4.0 * n_topics + 28.0
+
+
+def schedule_models(n_topics, n_workers):
+    """Longest-processing-time assignment of models to workers.  Returns a list (per worker) of
+    indices into ``n_topics``; deterministic."""
+    order = sorted(range(len(n_topics)), key=lambda i: (-model_cost(n_topics[i]), i))
+    loads = [0.0] * n_workers
+    plan = [[] for _ in range(n_workers)]
+    for i in order:
+        w = min(range(n_workers), key=lambda j: (loads[j], j))
+        plan[w].append(i)
+        loads[w] += model_cost(n_topics[i])
+    return plan
+
+
+def run_cgs_models(
+    cistopic_obj,
+    n_topics,
+    n_cpu=1,
+    n_iter=150,
+    random_state=555,
+    alpha=50,
+    alpha_by_topic=True,
+    eta=0.1,
+    eta_by_topic=False,
+    top_topics_coh=5,
+    save_path=None,
+    **kwargs,
+):
+    """Run LDA with collapsed Gibbs sampling for every value in ``n_topics``.
+
+    Signature and return value of the reference (lda_models.py:99-175): a list of
+    :class:`CistopicLDAModel` in the order of ``n_topics``.  ``n_cpu`` and Ray keyword
+    arguments are ignored; ``devices=[...]`` (keyword-only extra) restricts the GPUs used.
+    """
+    devices = kwargs.pop("devices", None)
+    n_gpu = _lib.require_device()
+    if devices is None:
+        devices = list(range(n_gpu))
+    region_names = cistopic_obj.region_names
+    cell_names = cistopic_obj.cell_names
+    binary_matrix = cistopic_obj.binary_matrix  # regions x cells; transposed on the device
+    devices = devices[: max(1, min(len(devices), len(n_topics)))]
+    plan = schedule_models(list(n_topics), len(devices))
+    results = [None] * len(n_topics)
+    errors = []
+
+    def worker(dev, idxs):
+        try:
+            corpus = Corpus.from_regions_by_cells(binary_matrix, device=dev)
+            try:
+                for i in idxs:
+                    results[i] = _run_cgs_model_on_corpus(
+                        corpus, binary_matrix, n_topics[i], cell_names, region_names, n_iter, random_state,
+                        alpha, alpha_by_topic, eta, eta_by_topic, top_topics_coh, save_path)
+            finally:
+                corpus.close()
+        except BaseException as e:  # propagate to the caller like ray.get would
+            errors.append(e)
+
+    if len(devices) == 1:
+        worker(devices[0], plan[0])
+    else:
+        threads = [threading.Thread(target=worker, args=(d, p)) for d, p in zip(devices, plan) if p]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+    if errors:
+        raise errors[0]
+    return results
+
+
+def run_cgs_model(
+    binary_matrix,
+    n_topics,
+    cell_names,
+    region_names,
+    n_iter=150,
+    random_state=555,
+    alpha=50,
+    alpha_by_topic=True,
+    eta=0.1,
+    eta_by_topic=False,
+    top_topics_coh=5,
+    save_path=None,
+    device=0,
+):
+    """One model (lda_models.py:178-396).  ``binary_matrix`` is cells x regions, as there."""
+    X = sparse.csr_matrix(binary_matrix)
+    corpus = Corpus.from_cells_by_regions(X, device=device)
+    try:
+        return _run_cgs_model_on_corpus(corpus, sparse.csr_matrix(X.T), n_topics, cell_names, region_names, n_iter,
+                                        random_state, alpha, alpha_by_topic, eta, eta_by_topic, top_topics_coh,
+                                        save_path)
+    finally:
+        corpus.close()
+
+
+def _run_cgs_model_on_corpus(corpus, regions_by_cells, n_topics, cell_names, region_names, n_iter, random_state,
+                             alpha, alpha_by_topic, eta, eta_by_topic, top_topics_coh, save_path):
+    log = _logger()
+    lda_log = logging.getLogger("lda")
+    lda_log.addHandler(logging.NullHandler())
+    lda_log.propagate = False
+    warnings.filterwarnings("ignore")
+
+    # hyper-parameter scaling of lda_models.py:247-282
+    model = LDA(
+        n_topics=n_topics,
+        n_iter=n_iter,
+        random_state=random_state,
+        alpha=alpha / n_topics if alpha_by_topic else alpha,
+        eta=eta / n_topics if eta_by_topic else eta,
+        refresh=n_iter,
+        device=corpus.device,
+        corpus=corpus,
+    )
+    log.info(f"Running model with {n_topics} topics")
+    start_time = time.time()
+    model.fit(None)
+    end_time = time.time() - start_time
+
+    return build_cistopic_model(model, regions_by_cells, n_topics, cell_names, region_names, n_iter, random_state,
+                                alpha, alpha_by_topic, eta, eta_by_topic, top_topics_coh, end_time, save_path, log)
+
+
+def build_cistopic_model(model, regions_by_cells, n_topics, cell_names, region_names, n_iter, random_state, alpha,
+                         alpha_by_topic, eta, eta_by_topic, top_topics_coh, end_time, save_path=None, log=None):
+    """Metric block and DataFrame packing of lda_models.py:291-388 from a fitted LDA-protocol
+    object (needs topic_word_, doc_topic_, nzw_, ndz_, nz_)."""
+    M = sparse.csr_matrix(regions_by_cells)
+    doc_lengths = np.asarray(M.sum(axis=0)).ravel().astype(float)  # tokens per cell
+    arun_2010 = _metrics.metric_arun_2010(model.topic_word_, model.doc_topic_, doc_lengths)
+    cao_juan_2009 = _metrics.metric_cao_juan_2009(model.topic_word_)
+    mimno_2011 = _metrics.metric_coherence_mimno_2011(model.topic_word_, M, top_n=20, eps=1e-12, normalize=True)
+    ll = _metrics.loglikelihood_compat(model.nzw_, model.ndz_, alpha, eta)
+
+    if len(mimno_2011) <= top_topics_coh:
+        model_coh = np.mean(mimno_2011)
+    else:
+        model_coh = np.mean(mimno_2011[np.argpartition(mimno_2011, -top_topics_coh)[-top_topics_coh:]])
+    metrics = pd.DataFrame(
+        [arun_2010, cao_juan_2009, model_coh, ll],
+        index=["Arun_2010", "Cao_Juan_2009", "Mimno_2011", "loglikelihood"],
+        columns=["Metric"],
+    ).transpose()
+    topics = np.arange(1, n_topics + 1)
+    coherence = pd.DataFrame({"Topic": topics.astype(np.float64), "Mimno_2011": np.asarray(mimno_2011, np.float64)})
+    marg = _metrics.marginal_topic_distrib(model.doc_topic_, doc_lengths)
+    marg_topic = pd.DataFrame({"Topic": topics.astype(np.float64), "Marg_Topic": np.asarray(marg, np.float64)})
+    topic_ass = pd.DataFrame({"Topic": topics.astype(np.int64), "Assignments": np.asarray(model.nz_, np.int64)})
+    topic_names = ["Topic" + str(i) for i in range(1, n_topics + 1)]
+    cell_topic_arr = getattr(model, "cell_topic_", None)
+    if cell_topic_arr is None:
+        cell_topic_arr = np.ascontiguousarray(model.doc_topic_.T)
+    topic_region_arr = getattr(model, "topic_region_", None)
+    if topic_region_arr is None:
+        topic_region_arr = np.ascontiguousarray(model.topic_word_.T)
+    cell_topic = pd.DataFrame(cell_topic_arr, index=topic_names, columns=cell_names)
+    topic_region = pd.DataFrame(topic_region_arr, index=region_names, columns=topic_names)
+    parameters = pd.DataFrame(
+        ["lda", n_topics, n_iter, random_state, alpha, alpha_by_topic, eta, eta_by_topic, top_topics_coh, end_time],
+        index=["package", "n_topics", "n_iter", "random_state", "alpha", "alpha_by_topic", "eta", "eta_by_topic",
+               "top_topics_coh", "time"],
+        columns=["Parameter"],
+    )
+    out = CistopicLDAModel(metrics, coherence, marg_topic, topic_ass, cell_topic, topic_region, parameters)
+    # extras (not in the reference): the true Griffiths-Steyvers log-likelihood of the final state
+    out.loglikelihood_true = getattr(model, "final_loglikelihood_", None)
+    if log is not None:
+        log.info(f"Model with {n_topics} topics done!")
+    if isinstance(save_path, str):
+        if log is not None:
+            log.info(f"Saving model with {n_topics} topics at {save_path}")
+        if not os.path.exists(save_path):
+            os.mkdir(save_path)
+        with open(os.path.join(save_path, f"Topic{n_topics}.pkl"), "wb") as f:
+            pickle.dump(out, f)
+    return out
+
+
+def _rescale(values):
+    values = np.asarray(values, dtype=float)
+    return (values - values.min()) / (values.max() - values.min())
+
+
+def evaluate_models(
+    models,
+    select_model=None,
+    return_model=True,
+    metrics=["Minmo_2011", "loglikelihood", "Cao_Juan_2009", "Arun_2010"],
+    min_topics_coh=5,
+    plot=True,
+    figsize=(6.4, 4.8),
+    plot_metrics=False,
+    save=None,
+):
+    """Model selection on the four quality metrics (lda_models.py:1048-1270).
+
+    Behaviour kept from the reference: models are sorted by ``n_topic``; every metric is
+    min-max rescaled (Arun and Cao-Juan negated first); the coherence -- spelled
+    ``"Minmo_2011"`` in ``metrics``, as in the reference -- only uses models with at least
+    ``min_topics_coh`` topics and, when present, restricts the other metrics to the same
+    models; the best model maximises the sum.  Plotting needs matplotlib and is skipped
+    (with a log line) when it is not installed.
+    """
+    models = [models[i] for i in np.argsort([m.n_topic for m in models])]
+    all_topics = sorted([models[x].n_topic for x in range(0, len(models))])
+    metrics_dict = {}
+    curves = []  # (x, y, label) for the combined plot
+    raw = {}
+    use_coh = "Minmo_2011" in metrics
+    if use_coh:
+        in_index = [i for i in range(len(all_topics)) if all_topics[i] >= min_topics_coh]
+
+    def pick(values):
+        return np.array([values[i] for i in in_index]) if use_coh else values
+
+    if "Arun_2010" in metrics:
+        arun = [m.metrics.loc["Metric", "Arun_2010"] for m in models]
+        raw["Arun_2010"] = (all_topics, arun, "Arun_2010 - Minimize")
+        res = _rescale([-x for x in arun])
+        metrics_dict["Arun_2010"] = pick(res)
+        curves.append((all_topics, res, "Inv_Arun_2010"))
+    if "Cao_Juan_2009" in metrics:
+        cao = [m.metrics.loc["Metric", "Cao_Juan_2009"] for m in models]
+        raw["Cao_Juan_2009"] = (all_topics, cao, "Cao_Juan_2009 - Minimize")
+        res = _rescale([-x for x in cao])
+        metrics_dict["Cao_Juan_2009"] = pick(res)
+        curves.append((all_topics, res, "Inv_Cao_Juan_2009"))
+    if use_coh:
+        mimno = [models[i].metrics.loc["Metric", "Mimno_2011"] for i in in_index]
+        mimno_topics = [all_topics[i] for i in in_index]
+        raw["Minmo_2011"] = (mimno_topics, mimno, "Mimno_2011 - Maximize")
+        res = _rescale(mimno)
+        metrics_dict["Minmo_2011"] = np.array(res)
+        curves.append((mimno_topics, res, "Mimno_2011"))
+    if "loglikelihood" in metrics:
+        ll = [m.metrics.loc["Metric", "loglikelihood"] for m in models]
+        raw["loglikelihood"] = (all_topics, ll, "Loglikelihood - Maximize")
+        res = _rescale(ll)
+        metrics_dict["loglikelihood"] = pick(res)
+        curves.append((all_topics, res, "Loglikelihood"))
+
+    if select_model is None:
+        combined_metric = sum(metrics_dict.values())
+        pool = mimno_topics if use_coh else all_topics
+        best_model = pool[combined_metric.tolist().index(max(combined_metric))]
+    else:
+        combined_metric = None
+        best_model = select_model
+
+    if plot or save is not None or plot_metrics:
+        try:
+            import matplotlib.backends.backend_pdf
+            import matplotlib.pyplot as plt
+        except ImportError:
+            logging.getLogger("cisTopic").info("matplotlib is not installed: evaluate_models skips plotting")
+        else:
+            fig = plt.figure(figsize=figsize)
+            for x, y, label in curves:
+                plt.plot(x, y, linestyle="--", marker="o", label=label)
+            plt.axvline(best_model, linestyle="--", color="grey")
+            plt.xlabel("Number of topics\nOptimal number of topics: " + str(best_model))
+            plt.ylabel("Rescaled metric")
+            plt.legend(bbox_to_anchor=(1.04, 1), loc="upper left")
+            pdf = None
+            if save is not None:
+                pdf = matplotlib.backends.backend_pdf.PdfPages(save)
+                pdf.savefig(fig, bbox_inches="tight")
+            if plot is True:
+                plt.show()
+            else:
+                plt.close(fig)
+            if plot_metrics:
+                for name in ("Arun_2010", "Cao_Juan_2009", "Minmo_2011", "loglikelihood"):
+                    if name in raw:
+                        x, y, title = raw[name]
+                        fig = plt.figure()
+                        plt.plot(x, y, linestyle="--", marker="o")
+                        plt.axvline(best_model, linestyle="--", color="grey")
+                        plt.title(title)
+                        if pdf is not None:
+                            pdf.savefig(fig)
+                        plt.show()
+            if pdf is not None:
+                pdf.close()
+
+    if return_model:
+        return models[all_topics.index(best_model)]
+
+
+def load_cisTopic_model(path_to_cisTopic_model_matrices):
+    """Feather-matrix loader of lda_models.py:1273-1289."""
+    cell_topic = pd.read_feather(path_to_cisTopic_model_matrices + "cell_topic.feather")
+    cell_topic.index = ["Topic" + str(x) for x in range(1, cell_topic.shape[0] + 1)]
+    topic_region = pd.read_feather(path_to_cisTopic_model_matrices + "topic_region.feather")
+    topic_region.index = ["Topic" + str(x) for x in range(1, topic_region.shape[0] + 1)]
+    topic_region = topic_region.T
+    return CistopicLDAModel(None, None, None, None, cell_topic, topic_region, None)

@@ -1,0 +1,235 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle.
+
+Integer/index work is bit-exact; the stochastic sampler is compared through the true
+log-likelihood trace and the Mimno coherence within 1 % (BASELINE.json north_star).
+"""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from oracle import lda_oracle as lo
+from pycistopic_b200.synth import make_binary_matrix
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def small():
+    m, cells, regions = make_binary_matrix(n_cells=300, n_regions=5000, density=0.04, n_true_topics=6, seed=11)
+    return m, cells, regions
+
+
+@pytest.fixture(scope="module")
+def c1():
+    return make_binary_matrix("C1")
+
+
+def _corpus_pair(m):
+    from pycistopic_b200 import Corpus
+    X = sp.csr_matrix(m.T)
+    X.sort_indices()
+    return Corpus.from_regions_by_cells(m), X
+
+
+# ---- token-list construction (bit-exact) -------------------------------------------------------
+def test_tokens_from_regions_by_cells_bit_exact(small):
+    m, _, _ = small
+    corpus, X = _corpus_pair(m)
+    WS, DS = corpus.token_lists()
+    oWS, oDS = lo.matrix_to_lists(X)
+    assert corpus.n_tokens == len(oWS) == m.nnz
+    assert np.array_equal(WS, oWS)
+    assert np.array_equal(DS, oDS)
+    corpus.close()
+
+
+def test_tokens_from_cells_by_regions_unsorted_and_duplicates():
+    from pycistopic_b200 import Corpus
+    rng = np.random.default_rng(3)
+    D, W = 37, 1000
+    rows, cols = [], []
+    for d in range(D):
+        n = int(rng.integers(0, 60)) if d != 5 else 0  # one empty cell
+        c = rng.choice(W, size=n, replace=False)
+        rng.shuffle(c)
+        rows += [d] * n
+        cols += list(c)
+    # duplicates: repeat some entries (binary data: they must collapse)
+    rows += rows[:25]
+    cols += cols[:25]
+    indptr = np.concatenate([[0], np.cumsum(np.bincount(rows, minlength=D))]).astype(np.int64)
+    order = np.argsort(rows, kind="stable")
+    indices = np.asarray(cols, np.int32)[order]
+    X = sp.csr_matrix((np.ones(len(indices), np.int32), indices, indptr), shape=(D, W))  # not canonical
+    corpus = Corpus.from_cells_by_regions(X)
+    WS, DS = corpus.token_lists()
+    Xc = sp.csr_matrix((X.toarray() > 0).astype(np.int32))
+    oWS, oDS = lo.matrix_to_lists(Xc)
+    assert np.array_equal(WS, oWS) and np.array_equal(DS, oDS)
+    corpus.close()
+
+
+def test_cell_shard_matches_slice(small):
+    from pycistopic_b200 import Corpus
+    m, _, _ = small
+    X = sp.csr_matrix(m.T)
+    lo_, hi_ = 50, 211
+    corpus = Corpus.from_regions_by_cells(m, cell_range=(lo_, hi_))
+    WS, DS = corpus.token_lists()
+    oWS, oDS = lo.matrix_to_lists(X[lo_:hi_])
+    assert np.array_equal(WS, oWS) and np.array_equal(DS, oDS)
+    corpus.close()
+
+
+def test_bitmap_windows_large_region_axis():
+    """More regions than one shared-memory bitmap window holds (> 1.8 M)."""
+    from pycistopic_b200 import Corpus
+    rng = np.random.default_rng(5)
+    D, W = 12, 4_000_000
+    rows = np.repeat(np.arange(D), 500)
+    cols = np.concatenate([rng.choice(W, 500, replace=False) for _ in range(D)])
+    cols[:3] = [0, W - 1, 1_900_000]
+    X = sp.csr_matrix((np.ones(len(rows), np.int32), (rows, cols)), shape=(D, W))
+    X.sum_duplicates()
+    X.data[:] = 1
+    corpus = Corpus.from_cells_by_regions(X)
+    WS, DS = corpus.token_lists()
+    oWS, oDS = lo.matrix_to_lists(X)
+    assert np.array_equal(WS, oWS) and np.array_equal(DS, oDS)
+    corpus.close()
+
+
+# ---- count bookkeeping (bit-exact) ---------------------------------------------------------------
+@pytest.mark.parametrize("K", [2, 5, 10, 16, 33, 50, 100, 130, 300])
+def test_init_counts_bit_exact(small, K):
+    from pycistopic_b200 import DeviceModel
+    m, _, _ = small
+    corpus, X = _corpus_pair(m)
+    model = DeviceModel(corpus, K, 50.0 / K, 0.1, seed=1)
+    model.init()
+    nzw, ndz, nz = model.counts()
+    o = lo.OracleLDA(K, n_iter=0, alpha=50.0 / K, eta=0.1, random_state=1, keep_z=True)
+    o._initialize(X)
+    assert np.array_equal(model.get_z(), o.ZS)
+    assert np.array_equal(nzw, o.nzw_) and np.array_equal(ndz, o.ndz_) and np.array_equal(nz, o.nz_)
+    ll = model.loglikelihood()
+    assert ll == pytest.approx(o.loglikelihood(), rel=1e-10)
+    model.close()
+    corpus.close()
+
+
+@pytest.mark.parametrize("K", [3, 20, 64])
+def test_supplied_z_counts_bit_exact(small, K):
+    from pycistopic_b200 import DeviceModel
+    m, _, _ = small
+    corpus, X = _corpus_pair(m)
+    WS, DS = lo.matrix_to_lists(X)
+    rng = np.random.default_rng(K)
+    z = rng.integers(0, K, size=len(WS)).astype(np.int32)
+    model = DeviceModel(corpus, K, 0.5, 0.1, seed=1)
+    model.set_z(z)
+    nzw, ndz, nz = model.counts()
+    onzw, ondz, onz = lo.counts_from_z(WS, DS, z, X.shape[0], X.shape[1], K)
+    assert np.array_equal(model.get_z(), z)
+    assert np.array_equal(nzw, onzw) and np.array_equal(ndz, ondz) and np.array_equal(nz, onz)
+    assert model.loglikelihood() == pytest.approx(lo.loglikelihood_true(onzw, ondz, onz, 0.5, 0.1), rel=1e-10)
+    # normalised outputs (lda final normalisation) to fp64 round-off
+    tw, dt = model.distributions()
+    otw = (onzw + 0.1) / (onzw + 0.1).sum(axis=1, keepdims=True)
+    odt = (ondz + 0.5) / (ondz + 0.5).sum(axis=1, keepdims=True)
+    np.testing.assert_allclose(tw, otw, rtol=1e-12)
+    np.testing.assert_allclose(dt, odt, rtol=1e-12)
+    tr, ct = model.frames()
+    np.testing.assert_array_equal(tr, tw.T)
+    np.testing.assert_array_equal(ct, dt.T)
+    with pytest.raises(RuntimeError):
+        bad = z.copy()
+        bad[0] = K
+        model.set_z(bad)
+    model.close()
+    corpus.close()
+
+
+@pytest.mark.parametrize("K", [2, 7, 16, 24, 50, 100, 200, 500])
+def test_sweep_keeps_counts_consistent(small, K):
+    """After any number of sweeps the three tables are exactly the histograms of z."""
+    from pycistopic_b200 import DeviceModel
+    m, _, _ = small
+    corpus, X = _corpus_pair(m)
+    WS, DS = lo.matrix_to_lists(X)
+    model = DeviceModel(corpus, K, 50.0 / K, 0.1, seed=42)
+    model.init()
+    ll0 = model.loglikelihood()
+    model.sweep(7)
+    z = model.get_z()
+    assert z.min() >= 0 and z.max() < K
+    nzw, ndz, nz = model.counts()
+    onzw, ondz, onz = lo.counts_from_z(WS, DS, z, X.shape[0], X.shape[1], K)
+    assert np.array_equal(nzw, onzw) and np.array_equal(ndz, ondz) and np.array_equal(nz, onz)
+    assert nz.sum() == len(WS)
+    assert model.loglikelihood() > ll0
+    assert not np.array_equal(z, np.arange(len(WS)) % K)
+    model.close()
+    corpus.close()
+
+
+# ---- sampler: statistical parity with the sequential oracle ---------------------------------------
+@pytest.mark.parametrize("K", [2, 5, 10])
+def test_loglik_trace_within_1pct_c1(c1, K):
+    """Config C1 (BASELINE.json configs[0]): per-iteration true log-likelihood within 1 % of the
+    oracle (the `lda` restatement run with refresh=1), final coherence within 1 %."""
+    from pycistopic_b200 import LDA
+    from pycistopic_b200 import metrics as pm
+    m, _, _ = c1
+    X = sp.csr_matrix(m.T)
+    n_iter, alpha, eta = 150, 50.0 / K, 0.1
+    o = lo.OracleLDA(K, n_iter=n_iter, alpha=alpha, eta=eta, random_state=555, refresh=1).fit(X)
+    g = LDA(K, n_iter=n_iter, alpha=alpha, eta=eta, random_state=555, refresh=1).fit(X)
+    ot = np.array(o.loglikelihoods_ + [o.final_loglikelihood_])
+    gt = np.array(g.loglikelihoods_ + [g.final_loglikelihood_])
+    assert len(ot) == len(gt) == n_iter + 1
+    rel = np.abs(gt - ot) / np.abs(ot)
+    assert gt[0] == pytest.approx(ot[0], rel=1e-10)  # identical initial state
+    assert rel.max() < 0.01, f"trace deviates {rel.max():.3%} at sweep {rel.argmax()}"
+    # coherence (mean of the top-5 topics, lda_models.py:308-328) within 1 %
+    oc = lo.metric_coherence_mimno_2011(o.topic_word_, X)
+    gc = pm.metric_coherence_mimno_2011(g.topic_word_, m)
+    top = lambda c: np.mean(c) if len(c) <= 5 else np.mean(np.sort(c)[-5:])
+    assert top(gc) == pytest.approx(top(oc), rel=0.01)
+
+
+def test_loglik_trace_larger_k(small):
+    from pycistopic_b200 import LDA
+    m, _, _ = small
+    X = sp.csr_matrix(m.T)
+    for K in (40, 100):
+        o = lo.OracleLDA(K, n_iter=60, alpha=50.0 / K, eta=0.1, random_state=555, refresh=5).fit(X)
+        g = LDA(K, n_iter=60, alpha=50.0 / K, eta=0.1, random_state=555, refresh=5).fit(X)
+        ot = np.array(o.loglikelihoods_ + [o.final_loglikelihood_])
+        gt = np.array(g.loglikelihoods_ + [g.final_loglikelihood_])
+        rel = np.abs(gt - ot) / np.abs(ot)
+        assert rel.max() < 0.01, f"K={K}: trace deviates {rel.max():.3%}"
+
+
+# ---- imputation -----------------------------------------------------------------------------------
+def test_impute_chunk_matches_fp64_product():
+    from pycistopic_b200.diff_features import calculate_imputed_accessibility
+    rng = np.random.default_rng(0)
+    R, K, C = 1000, 37, 333
+    a = rng.dirichlet(np.full(R, 0.1), size=K).T.astype(np.float32)  # each topic sums to 1 over regions
+    b = rng.dirichlet(np.full(K, 0.5), size=C).T.astype(np.float32)
+    names = [f"r{i}" for i in range(R)]
+    out, kept = calculate_imputed_accessibility(a, b, names, 1.0, 256)  # float path: no scaling
+    ref = a.astype(np.float64) @ b.astype(np.float64)
+    nz = ref.any(axis=1)
+    assert kept == [n for n, k in zip(names, nz) if k]
+    np.testing.assert_allclose(out, ref[nz], rtol=1e-5, atol=1e-12)
+    out_i, kept_i = calculate_imputed_accessibility(a, b, names, 10 ** 6, 300)
+    ref_i = (ref * 1e6)
+    keep = np.trunc(ref_i).any(axis=1)
+    # truncation can flip by one at integer boundaries between summation orders
+    full = np.zeros((R, C), np.int64)
+    full[[names.index(n) for n in kept_i]] = out_i
+    assert np.abs(full - np.trunc(ref_i)).max() <= 1
+    assert out_i.dtype == np.int32 and (set(kept_i) ^ set(np.array(names)[keep])) <= set(
+        np.array(names)[np.abs(ref_i).max(axis=1) < 2])
