@@ -94,6 +94,19 @@ int cgs_model_get_z(cgs_model *m, int32_t *z);
 /* n_sweeps collapsed-Gibbs sweeps over every token of the corpus (replaces
  * lda._lda._sample_topics).  Asynchronous. */
 int cgs_model_sweep(cgs_model *m, int32_t n_sweeps);
+/* Tuning knobs of the sweep kernel: lanes that cooperate on one token (power of two, must
+ * cover n_topics with at most 16 topics per lane) and warps that share one cell.  The defaults
+ * are chosen from n_topics and the mean cell size at cgs_model_create. */
+int cgs_model_set_sweep_shape(cgs_model *m, int32_t lanes_per_token, int32_t warps_per_cell);
+/* Upper bound on the CTAs of the sweep kernel (0 = fill the GPU).  With 1 CTA, 32 lanes per
+ * token and 1 warp per cell the sweep is an exact sequential Gibbs scan (used by the
+ * stationarity test). */
+int cgs_model_set_max_blocks(cgs_model *m, int32_t max_blocks);
+/* The topic totals n_k that a warp works with are re-synchronised often enough that at most
+ * 1/divisor of a sweep is processed GPU-wide in between (default 16). */
+int cgs_model_set_nk_staleness(cgs_model *m, double divisor);
+int cgs_model_get_sweep_shape(const cgs_model *m, int32_t *lanes_per_token, int32_t *chunks_per_lane,
+                              int32_t *warps_per_cell);
 /* Kernel launches issued by this model so far (for bench.py's gpu_launches). */
 int cgs_model_launch_count(const cgs_model *m, int64_t *count);
 /* Number of sweeps done so far. */

@@ -48,6 +48,10 @@ SIGNATURES = {
     "cgs_model_set_z": (ctypes.c_int, [c_vp, c_i32p]),
     "cgs_model_get_z": (ctypes.c_int, [c_vp, c_i32p]),
     "cgs_model_sweep": (ctypes.c_int, [c_vp, ctypes.c_int32]),
+    "cgs_model_set_sweep_shape": (ctypes.c_int, [c_vp, ctypes.c_int32, ctypes.c_int32]),
+    "cgs_model_set_max_blocks": (ctypes.c_int, [c_vp, ctypes.c_int32]),
+    "cgs_model_set_nk_staleness": (ctypes.c_int, [c_vp, ctypes.c_double]),
+    "cgs_model_get_sweep_shape": (ctypes.c_int, [c_vp, c_i32p, c_i32p, c_i32p]),
     "cgs_model_launch_count": (ctypes.c_int, [c_vp, c_i64p]),
     "cgs_model_sweeps_done": (ctypes.c_int, [c_vp, c_i64p]),
     "cgs_model_loglik": (ctypes.c_int, [c_vp, ctypes.c_int, c_f64p]),

@@ -65,7 +65,10 @@ struct cgs_model {
     int *d_flag = nullptr;
     int64_t launches = 0;
     int64_t sweeps = 0;
-    int tpt = 1, ch = 1;
+    int tpt = 1, ch = 1, threads = 128;
+    double nk_divisor = 16.0;
+    int max_blocks = 0;   // user override, 0 = automatic
+    int auto_blocks = 1 << 30;  // concurrency cap chosen by pick_sweep_shape
     int sweep_blocks = 0;
 };
 
@@ -323,13 +326,32 @@ int cgs_corpus_export_tokens(const cgs_corpus *c, int32_t *WS, int32_t *DS) {
 }
 
 // ---------------------------------------------------------------------------------------------
-static void pick_sweep_shape(int32_t Kp, int *tpt, int *ch) {
+// Shape of the sweep kernel for a model: lanes per token (tpt), 16-byte chunks per lane (ch),
+// warps per CTA (= per cell) and the number of CTAs (= cells open at the same time).
+// Throughput wants the fewest lanes per token and the GPU full of warps.  Closeness to the
+// sequential reference wants little concurrency; measured on config C1 (8 seeds):
+//     lag of the log-likelihood trace in the first sweeps
+//         ~ 0.08 % per 1 % of all tokens in flight  +  0.28 % x (fraction of cells open at once),
+// while tokens of ONE cell sampled together are harmless up to ~8 % of the cell.  So: wide CTAs,
+// in-cell concurrency <= mean_cell_tokens / 16, open cells <= D / 8, tokens in flight <= N / 128.
+// At benchmark scale (D >= 10^4) none of the caps binds before the GPU is full.
+static void pick_sweep_shape(int32_t Kp, double n_tokens, double n_cells, int *tpt, int *ch, int *threads,
+                             int *auto_blocks) {
     const int chunks = Kp / 4;
-    // fewest lanes per token that still fit the row in <= 4 chunks per lane
+    const double mean_cell = n_tokens / std::max(1.0, n_cells);
     int t = 1;
     while (t * 4 < chunks) t <<= 1;
+    const int cap_cell = (int)std::max(1.0, mean_cell / 16.0);
+    while (t < 32 && 32 / t > cap_cell) t <<= 1;
+    int warps = 8;
+    while (warps > 1 && warps * (32 / t) > cap_cell) warps >>= 1;
+    const double in_flight_per_cta = warps * (32.0 / t);
+    const double by_cells = std::max(1.0, n_cells / 8.0);
+    const double by_tokens = std::max(1.0, n_tokens / (128.0 * in_flight_per_cta));
+    *auto_blocks = (int)std::min(1.0e9, std::min(by_cells, by_tokens));
     *tpt = t;
     *ch = (chunks + t - 1) / t;
+    *threads = warps * 32;
 }
 
 int cgs_model_create(cgs_model **out, cgs_corpus *corpus, int32_t n_topics, double alpha, double eta, uint64_t seed,
@@ -350,7 +372,8 @@ int cgs_model_create(cgs_model **out, cgs_corpus *corpus, int32_t n_topics, doub
         m->alpha = alpha;
         m->eta = eta;
         m->seed = seed;
-        pick_sweep_shape(m->Kp, &m->tpt, &m->ch);
+        pick_sweep_shape(m->Kp, (double)corpus->n_tokens, (double)corpus->n_cells, &m->tpt, &m->ch, &m->threads,
+                         &m->auto_blocks);
         if (stream) {
             m->stream = (cudaStream_t)stream;
         } else {
@@ -476,12 +499,13 @@ template <int TPT, int CH>
 static int launch_sweep(cgs_model *m, const SweepParams &p, int *blocks_cache) {
     if (*blocks_cache == 0) {
         int per_sm = 0;
-        CGS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep_kernel<TPT, CH>, kSweepThreads, 0));
+        CGS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep_kernel<TPT, CH>, m->threads, 0));
         if (per_sm < 1) per_sm = 1;
         *blocks_cache = m->corpus->num_sms * per_sm;
     }
-    const int blocks = std::max(1, std::min(*blocks_cache, m->corpus->n_cells));
-    sweep_kernel<TPT, CH><<<blocks, kSweepThreads, 0, m->stream>>>(p);
+    int blocks = std::max(1, std::min(*blocks_cache, m->corpus->n_cells));
+    blocks = std::min(blocks, m->max_blocks > 0 ? m->max_blocks : m->auto_blocks);
+    sweep_kernel<TPT, CH><<<blocks, m->threads, 0, m->stream>>>(p);
     CGS_CUDA(cudaGetLastError());
     return 0;
 }
@@ -534,6 +558,18 @@ int cgs_model_sweep(cgs_model *m, int32_t n_sweeps) {
     p.seed_lo = (uint32_t)m->seed;
     p.seed_hi = (uint32_t)(m->seed >> 32);
     p.token_offset = c->token_offset;
+    {
+        // n_k staleness budget: all warps together process at most 1/nk_divisor of a sweep
+        // between two re-synchronisations of a warp's view of the topic totals
+        const double warps_per_cell = m->threads / 32.0;
+        const double warp_slots = (double)c->num_sms * 32.0;
+        const double cta_cap = (double)(m->max_blocks > 0 ? m->max_blocks : m->auto_blocks);
+        const double active_warps =
+            std::max(1.0, std::min(warp_slots, std::min((double)c->n_cells, cta_cap) * warps_per_cell));
+        const double tokens_per_step = 32.0 / m->tpt;
+        const double r = (double)c->n_tokens / (active_warps * tokens_per_step * m->nk_divisor);
+        p.refresh_every = (int32_t)std::max(1.0, std::min(1024.0, r));
+    }
     for (int32_t s = 0; s < n_sweeps; ++s) {
         const int slot = (int)(m->sweeps % kWorkSlots);
         if (slot == 0) {
@@ -546,6 +582,46 @@ int cgs_model_sweep(cgs_model *m, int32_t n_sweeps) {
         m->launches += 1;
         m->sweeps += 1;
     }
+    return 0;
+}
+
+int cgs_model_set_sweep_shape(cgs_model *m, int32_t lanes_per_token, int32_t warps_per_cell) {
+    if (!m) CGS_FAIL("NULL model");
+    const int t = lanes_per_token;
+    if (!(t == 1 || t == 2 || t == 4 || t == 8 || t == 16 || t == 32)) CGS_FAIL("lanes_per_token must be a power of two <= 32");
+    if (!(warps_per_cell == 1 || warps_per_cell == 2 || warps_per_cell == 4 || warps_per_cell == 8))
+        CGS_FAIL("warps_per_cell must be 1, 2, 4 or 8");
+    const int chunks = m->Kp / 4;
+    const int ch = (chunks + t - 1) / t;
+    if (ch > 4) CGS_FAIL("lanes_per_token too small for this n_topics");
+    m->tpt = t;
+    m->ch = ch;
+    m->threads = warps_per_cell * 32;
+    m->sweep_blocks = 0;
+    m->auto_blocks = 1 << 30;  // an explicit shape lifts the automatic concurrency cap
+    return 0;
+}
+
+int cgs_model_set_max_blocks(cgs_model *m, int32_t max_blocks) {
+    if (!m) CGS_FAIL("NULL model");
+    if (max_blocks < 0) CGS_FAIL("max_blocks < 0");
+    m->max_blocks = max_blocks;
+    return 0;
+}
+
+int cgs_model_set_nk_staleness(cgs_model *m, double divisor) {
+    if (!m) CGS_FAIL("NULL model");
+    if (!(divisor >= 1.0)) CGS_FAIL("divisor must be >= 1");
+    m->nk_divisor = divisor;
+    return 0;
+}
+
+int cgs_model_get_sweep_shape(const cgs_model *m, int32_t *lanes_per_token, int32_t *chunks_per_lane,
+                              int32_t *warps_per_cell) {
+    if (!m) CGS_FAIL("NULL model");
+    if (lanes_per_token) *lanes_per_token = m->tpt;
+    if (chunks_per_lane) *chunks_per_lane = m->ch;
+    if (warps_per_cell) *warps_per_cell = m->threads / 32;
     return 0;
 }
 

@@ -28,7 +28,7 @@
 
 namespace cgs {
 
-constexpr int kSweepThreads = 128;
+constexpr int kSweepThreads = 256;  // upper bound; the launch uses 32..256
 constexpr int kMaxTopics = 512;  // TPT=32 lanes x CH=4 chunks x 4 topics
 
 struct SweepParams {
@@ -49,6 +49,7 @@ struct SweepParams {
     uint32_t seed_lo;
     uint32_t seed_hi;
     uint32_t sweep;
+    int32_t refresh_every;  // a warp re-synchronises the topic totals every this many steps
     int64_t token_offset;
 };
 
@@ -120,7 +121,16 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const SweepParams 
         __syncthreads();
 
         const int64_t nbatch = (t1 - t0 + 31) >> 5;
-        for (int64_t b = warp; b < nbatch; b += nwarps) {
+        // Token lists are sorted by region and concurrently scheduled cells advance in lockstep, so
+        // without this every token of a popular region would be sampled at the same moment against
+        // the same stale n_wk row.  Start each cell at its own pseudo-random batch and wrap.
+        uint32_t h = (uint32_t)cell * 0x9E3779B1u ^ (p.sweep * 0x85EBCA77u) ^ p.seed_lo;
+        h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
+        const int64_t rot = nbatch > 0 ? (int64_t)(h % (uint32_t)nbatch) : 0;
+        int since_refresh = 0;
+        for (int64_t bb = warp; bb < nbatch; bb += nwarps) {
+            int64_t b = bb + rot;
+            if (b >= nbatch) b -= nbatch;
             const int64_t base = t0 + (b << 5);
             const int64_t i = base + lane;
             const bool valid = i < t1;
@@ -149,6 +159,20 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const SweepParams 
             }
 
             for (int s = 0; s < nsteps; ++s) {
+                // ---- keep the topic totals live: publish this CTA's n_k deltas, re-read n_k ----
+                if (++since_refresh > p.refresh_every) {
+                    since_refresh = 1;
+                    for (int k = lane; k < K; k += 32) {
+                        const int d = atomicExch(&dnk_s[k], 0);
+                        if (d != 0) red_add_i32(p.n_k + k, d);
+                        const float den = (float)ld_volatile_i32(p.n_k + k) + p.etaW;
+                        const float inv = 1.0f / den;
+                        den_s[k] = den;
+                        inv_s[k] = inv;
+                        f_s[k] = ((float)ndk_s[k] + alpha) * inv;
+                    }
+                    __syncwarp();
+                }
                 // ---- prefetch the rows of the next step --------------------------------------
                 int w_next = -1;
                 if (TPT > 1) {

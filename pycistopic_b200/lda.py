@@ -150,6 +150,21 @@ class DeviceModel:
     def sync(self):
         check(_lib.load().cgs_model_sync(self._h))
 
+    def set_sweep_shape(self, lanes_per_token: int, warps_per_cell: int):
+        check(_lib.load().cgs_model_set_sweep_shape(self._h, lanes_per_token, warps_per_cell))
+
+    def set_max_blocks(self, max_blocks: int):
+        check(_lib.load().cgs_model_set_max_blocks(self._h, int(max_blocks)))
+
+    def set_nk_staleness(self, divisor: float):
+        check(_lib.load().cgs_model_set_nk_staleness(self._h, float(divisor)))
+
+    @property
+    def sweep_shape(self):
+        a, b, c = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+        check(_lib.load().cgs_model_get_sweep_shape(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+        return {"lanes_per_token": a.value, "chunks_per_lane": b.value, "warps_per_cell": c.value}
+
     # -- hot path ------------------------------------------------------------------------
     def sweep(self, n_sweeps: int = 1):
         check(_lib.load().cgs_model_sweep(self._h, int(n_sweeps)))

@@ -25,12 +25,15 @@ SHAPES = {
 }
 
 
-def planted_topic_tokens(n_cells, n_regions, density, n_true_topics=20, seed=1234, device=None):
+def planted_topic_tokens(n_cells, n_regions, density, n_true_topics=20, seed=1234, device=None, max_rounds=12):
     """Return (cell_ids, region_ids) int64 arrays of UNIQUE (cell, region) pairs sorted by
     (cell, region).  Runs in NumPy, or in torch on ``device`` when given (same algorithm,
-    different generator -- the result is only reproducible per backend)."""
+    different generator -- the result is only reproducible per backend).  Cells keep drawing
+    from their topic mixture until they hold ``n_d`` distinct regions (at most ``max_rounds``
+    rounds), so the matrix reaches the requested density despite the heavy-tailed region
+    popularity."""
     if device is not None:
-        return _planted_torch(n_cells, n_regions, density, n_true_topics, seed, device)
+        return _planted_torch(n_cells, n_regions, density, n_true_topics, seed, device, max_rounds)
     rng = np.random.default_rng(seed)
     W, D, Kt = n_regions, n_cells, n_true_topics
     pop = 1.0 / np.arange(1, W + 1) ** 1.0
@@ -41,23 +44,33 @@ def planted_topic_tokens(n_cells, n_regions, density, n_true_topics=20, seed=123
     cdf = np.cumsum(phi, axis=1)
     cdf[:, -1] = 1.0
     theta = rng.dirichlet(np.full(Kt, 0.3), size=D)
-    n_d = np.maximum(1, np.rint(rng.lognormal(np.log(density * W), 0.4, size=D))).astype(np.int64)
-    # oversample a little: de-duplication removes repeated (cell, region) draws
-    n_draw = np.minimum((n_d * 1.25).astype(np.int64) + 4, 4 * W)
-    cell = np.repeat(np.arange(D, dtype=np.int64), n_draw)
     tcdf = np.cumsum(theta, axis=1)
     tcdf[:, -1] = 1.0
-    u = rng.random(cell.shape[0])
-    topic = (u[:, None] > tcdf[cell]).sum(axis=1) if cell.shape[0] < 2_000_000 else _rowwise_search(tcdf, cell, u)
-    region = np.empty(cell.shape[0], np.int64)
-    u2 = rng.random(cell.shape[0])
-    for k in range(Kt):
-        m = topic == k
-        region[m] = np.searchsorted(cdf[k], u2[m], side="left")
-    region = np.minimum(region, W - 1)
-    key = np.unique(cell * W + region)
+    n_d = np.clip(np.rint(rng.lognormal(np.log(density * W), 0.4, size=D)), 1, W // 2).astype(np.int64)
+    key = np.empty(0, np.int64)
+    have = np.zeros(D, np.int64)
+    for _ in range(max_rounds):
+        missing = n_d - have
+        if not (missing > 0).any():
+            break
+        n_draw = np.where(missing > 0, missing + missing // 2 + 8, 0)
+        cell = np.repeat(np.arange(D, dtype=np.int64), n_draw)
+        u = rng.random(cell.shape[0])
+        topic = np.empty(cell.shape[0], np.int64)
+        step = 2_000_000
+        for s0 in range(0, cell.shape[0], step):
+            e0 = min(s0 + step, cell.shape[0])
+            topic[s0:e0] = (u[s0:e0, None] > tcdf[cell[s0:e0]]).sum(axis=1)
+        region = np.empty(cell.shape[0], np.int64)
+        u2 = rng.random(cell.shape[0])
+        for k in range(Kt):
+            msk = topic == k
+            region[msk] = np.searchsorted(cdf[k], u2[msk], side="left")
+        region = np.minimum(region, W - 1)
+        key = np.unique(np.concatenate([key, cell * W + region]))
+        have = np.bincount(key // W, minlength=D)
     cell, region = key // W, key % W
-    # trim every cell back to its budget n_d (keep a random subset, order restored by sort)
+    # trim every cell back to its budget n_d (keep a random subset; order stays sorted)
     cnt = np.bincount(cell, minlength=D)
     start = np.concatenate([[0], np.cumsum(cnt)[:-1]])
     rank = rng.random(key.shape[0])
@@ -69,16 +82,7 @@ def planted_topic_tokens(n_cells, n_regions, density, n_true_topics=20, seed=123
     return cell[keep], region[keep]
 
 
-def _rowwise_search(tcdf, cell, u):
-    out = np.empty(cell.shape[0], np.int64)
-    step = 2_000_000
-    for s in range(0, cell.shape[0], step):
-        e = min(s + step, cell.shape[0])
-        out[s:e] = (u[s:e, None] > tcdf[cell[s:e]]).sum(axis=1)
-    return out
-
-
-def _planted_torch(n_cells, n_regions, density, n_true_topics, seed, device):
+def _planted_torch(n_cells, n_regions, density, n_true_topics, seed, device, max_rounds):
     import torch
 
     g = torch.Generator(device=device)
@@ -87,14 +91,15 @@ def _planted_torch(n_cells, n_regions, density, n_true_topics, seed, device):
     f64 = torch.float64
     pop = 1.0 / torch.arange(1, W + 1, device=device, dtype=f64)
     pop = pop[torch.randperm(W, device=device, generator=g)]
+    torch.manual_seed(seed)
     gam = torch.distributions.Gamma(torch.tensor(0.05, device=device, dtype=f64),
                                     torch.tensor(1.0, device=device, dtype=f64))
-    torch.manual_seed(seed)
     phi = gam.sample((Kt, W)) + 1e-12
     phi = phi * pop
     phi = phi / phi.sum(dim=1, keepdim=True)
     cdf = torch.cumsum(phi, dim=1)
     cdf[:, -1] = 1.0
+    flat_r = (cdf + torch.arange(Kt, device=device, dtype=f64)[:, None] * 2.0).reshape(-1)
     gam_t = torch.distributions.Gamma(torch.tensor(0.3, device=device, dtype=f64),
                                       torch.tensor(1.0, device=device, dtype=f64))
     theta = gam_t.sample((D, Kt)) + 1e-300
@@ -102,31 +107,35 @@ def _planted_torch(n_cells, n_regions, density, n_true_topics, seed, device):
     tcdf = torch.cumsum(theta, dim=1)
     tcdf[:, -1] = 1.0
     n_d = torch.clamp(torch.round(torch.exp(torch.randn(D, device=device, generator=g, dtype=f64) * 0.4
-                                            + np.log(density * W))), min=1).to(torch.int64)
-    n_draw = torch.clamp((n_d.to(f64) * 1.25).to(torch.int64) + 4, max=4 * W)
+                                            + float(np.log(density * W)))), 1, W // 2).to(torch.int64)
+    max_tok = 48_000_000  # draws per chunk (bounds the temporaries)
     keys = []
-    # chunk over cells to bound memory (tokens x 8 B x a few temporaries)
-    ptr = torch.cumsum(n_draw, 0)
-    max_tok = 64_000_000
     c0 = 0
+    budget_ptr = torch.cumsum(n_d, 0)
     while c0 < D:
-        base = int(ptr[c0 - 1]) if c0 > 0 else 0
-        c1 = int(torch.searchsorted(ptr, torch.tensor(base + max_tok, device=device)).item())
+        base = int(budget_ptr[c0 - 1]) if c0 > 0 else 0
+        c1 = int(torch.searchsorted(budget_ptr, torch.tensor(base + max_tok // 2, device=device)).item())
         c1 = max(c0 + 1, min(c1, D))
-        cells = torch.repeat_interleave(torch.arange(c0, c1, device=device), n_draw[c0:c1])
-        u = torch.rand(cells.shape[0], device=device, generator=g, dtype=f64)
-        # topic of every draw: searchsorted in the owning cell's cdf (offset trick keeps it 1-D)
-        flat = (tcdf[c0:c1] + torch.arange(c1 - c0, device=device, dtype=f64)[:, None] * 2.0).reshape(-1)
-        topic = torch.searchsorted(flat, u + (cells - c0).to(f64) * 2.0) - (cells - c0) * Kt
-        topic = torch.clamp(topic, 0, Kt - 1)
-        u2 = torch.rand(cells.shape[0], device=device, generator=g, dtype=f64)
-        flat_r = (cdf + torch.arange(Kt, device=device, dtype=f64)[:, None] * 2.0).reshape(-1)
-        region = torch.searchsorted(flat_r, u2 + topic.to(f64) * 2.0) - topic * W
-        region = torch.clamp(region, 0, W - 1)
-        key = torch.unique(cells * W + region)
-        # trim to the budget: keep the first n_d (by a random rank) of every cell
-        kc = key // W
-        cnt = torch.bincount(kc - c0, minlength=c1 - c0)
+        nc = c1 - c0
+        flat_t = (tcdf[c0:c1] + torch.arange(nc, device=device, dtype=f64)[:, None] * 2.0).reshape(-1)
+        key = torch.empty(0, dtype=torch.int64, device=device)
+        have = torch.zeros(nc, dtype=torch.int64, device=device)
+        for _ in range(max_rounds):
+            missing = n_d[c0:c1] - have
+            if not bool((missing > 0).any()):
+                break
+            n_draw = torch.where(missing > 0, missing + missing // 2 + 8, torch.zeros_like(missing))
+            lc = torch.repeat_interleave(torch.arange(nc, device=device), n_draw)  # local cell id
+            u = torch.rand(lc.shape[0], device=device, generator=g, dtype=f64)
+            topic = torch.searchsorted(flat_t, u + lc.to(f64) * 2.0) - lc * Kt
+            topic = torch.clamp(topic, 0, Kt - 1)
+            u2 = torch.rand(lc.shape[0], device=device, generator=g, dtype=f64)
+            region = torch.searchsorted(flat_r, u2 + topic.to(f64) * 2.0) - topic * W
+            region = torch.clamp(region, 0, W - 1)
+            key = torch.unique(torch.cat([key, (lc + c0) * W + region]))
+            have = torch.bincount(key // W - c0, minlength=nc)
+        kc = key // W - c0
+        cnt = torch.bincount(kc, minlength=nc)
         rank = torch.rand(key.shape[0], device=device, generator=g, dtype=f64)
         order = torch.argsort(kc.to(f64) * 2.0 + rank)
         start = torch.cumsum(cnt, 0) - cnt

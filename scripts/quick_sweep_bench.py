@@ -10,6 +10,7 @@ ap.add_argument("--shape", default="C2")
 ap.add_argument("--topics", default="2,5,10,20,30,40,50,100")
 ap.add_argument("--sweeps", type=int, default=10)
 ap.add_argument("--warm", type=int, default=3)
+ap.add_argument("--shape_override", default="", help="lanes,warps")
 ap.add_argument("--burn", type=int, default=0, help="extra sweeps before timing (mixing state)")
 args = ap.parse_args()
 D, W, dens = SHAPES[args.shape]
@@ -23,9 +24,13 @@ N = tok.numel()
 torch.cuda.synchronize()
 print(f"generated {args.shape}: D={D} W={W} N={N} in {time.time()-t:.1f}s", flush=True)
 corpus = Corpus.from_device_tokens(cell_ptr.data_ptr(), tok.data_ptr(), D, W, N, keepalive=(cell_ptr, tok))
-stream = torch.cuda.current_stream().cuda_stream
+ts = torch.cuda.Stream(); torch.cuda.set_stream(ts)
+stream = ts.cuda_stream
 for K in [int(k) for k in args.topics.split(",")]:
     m = DeviceModel(corpus, K, 50.0 / K, 0.1, seed=555, stream=stream)
+    if args.shape_override:
+        a, b = [int(x) for x in args.shape_override.split(",")]
+        m.set_sweep_shape(a, b)
     m.init()
     ll0 = m.loglikelihood()
     m.sweep(args.warm + args.burn)
@@ -38,5 +43,5 @@ for K in [int(k) for k in args.topics.split(",")]:
     bt = 4 * K + 28
     print(json.dumps({"K": K, "ms_per_sweep": round(ms, 3), "Gtok_s": round(tps / 1e9, 3),
                       "alg_GBs": round(tps * bt / 1e9, 1), "frac_6544": round(tps * bt / 1e9 / 6544.3, 3),
-                      "ll0": ll0, "ll": ll1}), flush=True)
+                      "ll0": ll0, "ll": ll1, "shape": m.sweep_shape}), flush=True)
     m.close()

@@ -191,22 +191,80 @@ def test_loglik_trace_within_1pct_c1(c1, K):
     rel = np.abs(gt - ot) / np.abs(ot)
     assert gt[0] == pytest.approx(ot[0], rel=1e-10)  # identical initial state
     assert rel.max() < 0.01, f"trace deviates {rel.max():.3%} at sweep {rel.argmax()}"
-    # coherence (mean of the top-5 topics, lda_models.py:308-328) within 1 %
-    oc = lo.metric_coherence_mimno_2011(o.topic_word_, X)
-    gc = pm.metric_coherence_mimno_2011(g.topic_word_, m)
+
+
+def test_metrics_identical_on_identical_assignments(c1):
+    """Function-level parity of everything downstream of the sampler: load the ORACLE's final z
+    into the device model; counts are then bit-identical and every metric of run_cgs_model
+    (lda_models.py:291-305) must agree to fp64 round-off."""
+    from pycistopic_b200 import Corpus, DeviceModel
+    from pycistopic_b200 import metrics as pm
+    m, _, _ = c1
+    X = sp.csr_matrix(m.T)
+    K, alpha, eta = 10, 5.0, 0.1
+    o = lo.OracleLDA(K, n_iter=25, alpha=alpha, eta=eta, random_state=555, refresh=25, keep_z=True).fit(X)
+    corpus = Corpus.from_regions_by_cells(m)
+    model = DeviceModel(corpus, K, alpha, eta, seed=555)
+    model.set_z(o.ZS)
+    nzw, ndz, nz = model.counts()
+    assert np.array_equal(nzw, o.nzw_) and np.array_equal(ndz, o.ndz_) and np.array_equal(nz, o.nz_)
+    assert model.loglikelihood() == pytest.approx(o.final_loglikelihood_, rel=1e-12)
+    tw, dt = model.distributions()
+    np.testing.assert_allclose(tw, o.topic_word_, rtol=1e-12)
+    np.testing.assert_allclose(dt, o.doc_topic_, rtol=1e-12)
+    doc_len = np.asarray(X.sum(axis=1)).astype(float)
+    assert pm.metric_arun_2010(tw, dt, doc_len) == pytest.approx(lo.metric_arun_2010(o.topic_word_, o.doc_topic_, doc_len), rel=1e-9)
+    assert pm.metric_cao_juan_2009(tw) == pytest.approx(lo.metric_cao_juan_2009(o.topic_word_), rel=1e-10)
+    np.testing.assert_allclose(pm.metric_coherence_mimno_2011(tw, m), lo.metric_coherence_mimno_2011(o.topic_word_, X),
+                               rtol=1e-10)
+    np.testing.assert_allclose(pm.marginal_topic_distrib(dt, doc_len), lo.marginal_topic_distrib(o.doc_topic_, doc_len),
+                               rtol=1e-12)
+    model.close()
+    corpus.close()
+
+
+def test_coherence_distribution_matches_oracle(c1):
+    """The Mimno coherence of ONE chain varies by ~ +-15 % between seeds of the sequential
+    reference itself (measured: DESIGN.md), so a 1 % single-chain comparison is meaningless.
+    Instead the mean over seeds of the model coherence (mean of the top-5 topics,
+    lda_models.py:308-328) must agree within 2.5 pooled standard errors (or 1 %)."""
+    from pycistopic_b200 import LDA
+    from pycistopic_b200 import metrics as pm
+    m, _, _ = c1
+    X = sp.csr_matrix(m.T)
+    K, alpha, eta, n_iter = 10, 5.0, 0.1, 100
     top = lambda c: np.mean(c) if len(c) <= 5 else np.mean(np.sort(c)[-5:])
-    assert top(gc) == pytest.approx(top(oc), rel=0.01)
+    seeds = [555, 1, 2, 3, 4, 5]
+    oc, gc, oll, gll = [], [], [], []
+    for s in seeds:
+        o = lo.OracleLDA(K, n_iter=n_iter, alpha=alpha, eta=eta, random_state=s, refresh=n_iter).fit(X)
+        g = LDA(K, n_iter=n_iter, alpha=alpha, eta=eta, random_state=s, refresh=n_iter).fit(X)
+        oc.append(top(lo.metric_coherence_mimno_2011(o.topic_word_, X)))
+        gc.append(top(pm.metric_coherence_mimno_2011(g.topic_word_, m)))
+        oll.append(o.final_loglikelihood_)
+        gll.append(g.final_loglikelihood_)
+    oc, gc = np.array(oc), np.array(gc)
+    se = np.sqrt(oc.var(ddof=1) / len(oc) + gc.var(ddof=1) / len(gc))
+    assert abs(gc.mean() - oc.mean()) <= max(0.01 * abs(oc.mean()), 2.5 * se), (oc, gc)
+    assert np.mean(gll) == pytest.approx(np.mean(oll), rel=0.005)
 
 
 def test_loglik_trace_larger_k(small):
+    """Wider sweep shapes (K = 40: 4 lanes per token, K = 100: 8) on a tiny corpus (210 tokens per
+    cell).  One chain of the sequential oracle differs from another by ~0.7 % here, so the traces
+    are averaged over 4 seeds on both sides before the 1 % comparison."""
     from pycistopic_b200 import LDA
     m, _, _ = small
     X = sp.csr_matrix(m.T)
+    seeds = [555, 1, 2, 3]
     for K in (40, 100):
-        o = lo.OracleLDA(K, n_iter=60, alpha=50.0 / K, eta=0.1, random_state=555, refresh=5).fit(X)
-        g = LDA(K, n_iter=60, alpha=50.0 / K, eta=0.1, random_state=555, refresh=5).fit(X)
-        ot = np.array(o.loglikelihoods_ + [o.final_loglikelihood_])
-        gt = np.array(g.loglikelihoods_ + [g.final_loglikelihood_])
+        ot, gt = [], []
+        for s in seeds:
+            o = lo.OracleLDA(K, n_iter=60, alpha=50.0 / K, eta=0.1, random_state=s, refresh=5).fit(X)
+            g = LDA(K, n_iter=60, alpha=50.0 / K, eta=0.1, random_state=s, refresh=5).fit(X)
+            ot.append(o.loglikelihoods_ + [o.final_loglikelihood_])
+            gt.append(g.loglikelihoods_ + [g.final_loglikelihood_])
+        ot, gt = np.mean(ot, axis=0), np.mean(gt, axis=0)
         rel = np.abs(gt - ot) / np.abs(ot)
         assert rel.max() < 0.01, f"K={K}: trace deviates {rel.max():.3%}"
 
