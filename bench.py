@@ -1,0 +1,467 @@
+#!/usr/bin/env python
+"""Benchmark of the collapsed-Gibbs hot path (BASELINE.json metric: Gibbs tokens/s per sweep).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # CPU oracle port on the host cores
+
+Workload (BASELINE.json configs[1], "C2"): synthetic 10x-PBMC-shaped binary matrix, 10 000 cells
+x 200 000 regions at 3 % density (planted-topic generator, seed 1234), the n_topics sweep
+[2, 5, 10, ..., 50] (11 models), alpha = 50 / K, eta = 0.1, seed 555.  One STEP = one collapsed
+Gibbs sweep of every model.  With N > 1 GPUs the models are spread over the ranks
+longest-first (one model per GPU at a time, no collective on the data path), so the run is a
+strong-scaling one; `value` is the whole-job token-update rate.
+
+Prints ONE JSON line (rank 0).  See DESIGN.md section "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+N_TOPICS = [2, 5, 10, 15, 20, 25, 30, 35, 40, 45, 50]
+ALPHA, ETA, MODEL_SEED, DATA_SEED = 50.0, 0.1, 555, 1234
+WORKLOAD = "C2"
+E2E_SWEEPS = 10
+BURN_IN = 20  # sweeps before any timing, so the chains are past the z = i mod K transient
+
+
+def b_tok(k: int) -> float:
+    """Algorithmic bytes per token-update (SURVEY.md 8d / DESIGN.md): 4K + 28."""
+    return 4.0 * k + 28.0
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md recipe): nvidia-smi in the background during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu_index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic workload
+# ------------------------------------------------------------------------------------------------
+def make_workload_on_device(device):
+    """cell_ptr int64[D+1], tok_region int32[N] (canonical, cell-major) resident on `device`."""
+    import torch
+
+    from pycistopic_b200.synth import SHAPES, planted_topic_tokens
+    D, W, density = SHAPES[WORKLOAD]
+    cell, region = planted_topic_tokens(D, W, density, seed=DATA_SEED, device=device)
+    cnt = torch.bincount(cell, minlength=D)
+    cell_ptr = torch.zeros(D + 1, dtype=torch.int64, device=device)
+    cell_ptr[1:] = torch.cumsum(cnt, 0)
+    tok = region.to(torch.int32).contiguous()
+    del cell, region
+    return D, W, cell_ptr, tok
+
+
+def host_sample(cell_ptr_h, tok_h, n_cells_sample):
+    """First n cells of the workload as oracle token lists (WS, DS)."""
+    n_tok = int(cell_ptr_h[n_cells_sample])
+    WS = np.ascontiguousarray(tok_h[:n_tok], dtype=np.int32)
+    DS = np.repeat(np.arange(n_cells_sample, dtype=np.int32), np.diff(cell_ptr_h[: n_cells_sample + 1])).astype(np.int32)
+    return WS, DS
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port (oracle/cgs_oracle.c), one thread per model like the reference's
+# one-model-per-CPU fan-out (lda_models.py:122-123, :154-174)
+# ------------------------------------------------------------------------------------------------
+class CpuModels:
+    def __init__(self, WS, DS, n_cells, n_regions, topics):
+        from oracle import lda_oracle as lo
+        self.lo = lo
+        self.L = lo.lib()
+        self.WS, self.DS = WS, DS
+        self.W, self.D = n_regions, n_cells
+        self.models = []
+        rng = np.random.RandomState(MODEL_SEED)
+        self.rands = rng.rand(1024 ** 2 // 8)
+        for K in topics:
+            ZS = np.empty(len(WS), np.int32)
+            nzw = np.zeros((K, n_regions), np.int32)
+            ndz = np.zeros((n_cells, K), np.int32)
+            nz = np.zeros(K, np.int32)
+            self.L.oracle_initialize(lo._p(WS, lo._i32p), lo._p(DS, lo._i32p), lo._p(ZS, lo._i32p), len(WS), K,
+                                     n_regions, lo._p(nzw, lo._i32p), lo._p(ndz, lo._i32p), lo._p(nz, lo._i32p))
+            self.models.append((K, ZS, nzw, ndz, nz))
+        self.cores = max(1, min(len(topics), os.cpu_count() or 1))
+
+    def _sweep_one(self, mdl, n_sweeps):
+        lo = self.lo
+        K, ZS, nzw, ndz, nz = mdl
+        rc = self.L.oracle_run_sweeps(lo._p(self.WS, lo._i32p), lo._p(self.DS, lo._i32p), lo._p(ZS, lo._i32p),
+                                      len(self.WS), K, self.W, lo._p(nzw, lo._i32p), lo._p(ndz, lo._i32p),
+                                      lo._p(nz, lo._i32p), ALPHA / K, ETA, lo._p(self.rands, lo._f64p),
+                                      len(self.rands), n_sweeps)
+        if rc != 0:
+            raise MemoryError("oracle sweep failed")
+
+    def step(self, n_sweeps=1):
+        """One sweep of every model; models run concurrently on `cores` threads (ctypes drops the GIL)."""
+        from concurrent.futures import ThreadPoolExecutor
+        # longest first so the thread pool packs well
+        order = sorted(self.models, key=lambda m: -m[0])
+        with ThreadPoolExecutor(self.cores) as ex:
+            list(ex.map(lambda m: self._sweep_one(m, n_sweeps), order))
+
+    @property
+    def tokens_per_step(self):
+        return len(self.WS) * len(self.models)
+
+
+def cpu_model_name():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm
+# ------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    D, W, density = __import__("pycistopic_b200.synth", fromlist=["SHAPES"]).SHAPES[WORKLOAD]
+    sample_cells = args.cpu_sample_cells
+    try:
+        import torch
+        have_cuda = torch.cuda.is_available()
+    except Exception:
+        have_cuda = False
+    if have_cuda:
+        import torch
+        dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+        _, _, cell_ptr, tok = make_workload_on_device(dev)
+        cell_ptr_h = cell_ptr.cpu().numpy()
+        n_tok = int(cell_ptr_h[sample_cells])
+        tok_h = tok[:n_tok].cpu().numpy()
+        n_total = int(cell_ptr_h[-1])
+        del cell_ptr, tok
+        torch.cuda.empty_cache()
+        data = "synthetic (same device-generated matrix as the CUDA arm, first %d cells)" % sample_cells
+    else:
+        from pycistopic_b200.synth import planted_topic_tokens
+        cell, region = planted_topic_tokens(sample_cells, W, density, seed=DATA_SEED)
+        cell_ptr_h = np.concatenate([[0], np.cumsum(np.bincount(cell, minlength=sample_cells))]).astype(np.int64)
+        tok_h = region.astype(np.int32)
+        n_total = None
+        data = "synthetic (NumPy generator, %d cells of the same shape)" % sample_cells
+    WS, DS = host_sample(cell_ptr_h, tok_h, sample_cells)
+    cpu = CpuModels(WS, DS, sample_cells, W, N_TOPICS)
+    for _ in range(args.warmup):
+        cpu.step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu.step()
+    dt = time.perf_counter() - t0
+    value = cpu.tokens_per_step * args.steps / dt
+    sample = (f"one sweep of all {len(N_TOPICS)} models over the first {sample_cells} of {D} cells "
+              f"({len(WS)} tokens{'' if n_total is None else ' of %d' % n_total}); one thread per model")
+    line = {
+        "impl": "reference", "metric": "gibbs_tokens_per_s_per_sweep", "value": value, "unit": "tokens/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64 arithmetic on int32 counts",
+        "data": data,
+        "config": {"workload": f"{WORKLOAD}: {D} cells x {W} regions, density {density}, n_topics sweep {N_TOPICS}, "
+                               f"alpha={ALPHA}/K, eta={ETA}", "n_topics": N_TOPICS, "sampled_cells": sample_cells},
+        "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": cpu.cores, "kind": "port", "sample": sample,
+                         "cpu": cpu_model_name(), "host_cores": os.cpu_count()},
+        "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+# CUDA arm
+# ------------------------------------------------------------------------------------------------
+def run_cuda(args):
+    import torch
+    import torch.distributed as dist
+
+    from pycistopic_b200 import Corpus, DeviceModel, _lib
+    from pycistopic_b200.lda_models import schedule_models
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    _lib.require_device()
+
+    D, W, cell_ptr, tok = make_workload_on_device(dev)
+    N = tok.numel()
+    torch.cuda.synchronize()
+
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    corpus = Corpus.from_device_tokens(cell_ptr.data_ptr(), tok.data_ptr(), D, W, N, device=local_rank,
+                                       keepalive=(cell_ptr, tok))
+    plan = schedule_models(N_TOPICS, world)
+    my_topics = [N_TOPICS[i] for i in plan[rank]]
+    models = []
+    for K in my_topics:
+        m = DeviceModel(corpus, K, ALPHA / K, ETA, seed=MODEL_SEED, stream=stream.cuda_stream)
+        m.init()
+        m.sweep(BURN_IN)
+        models.append(m)
+    torch.cuda.synchronize()
+
+    def one_step(events=None):
+        for j, m in enumerate(models):
+            if events is not None:
+                events[j][0].record(stream)
+            m.sweep(1)
+            if events is not None:
+                events[j][1].record(stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(max(args.warmup, 0)):
+        one_step()
+    torch.cuda.synchronize()
+    barrier()
+    launches0 = sum(m.launch_count for m in models)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    per_model_events = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                         for _ in models] for _ in range(args.steps)]
+    e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    barrier()
+    e_start.record(stream)
+    for s in range(args.steps):
+        one_step(per_model_events[s])
+    e_stop.record(stream)
+    torch.cuda.synchronize()
+    barrier()
+    clock_info = clocks.stop() if rank == 0 else None
+    elapsed_ms = e_start.elapsed_time(e_stop)
+    launches = sum(m.launch_count for m in models) - launches0
+    per_model_ms = {K: statistics.mean(per_model_events[s][j][0].elapsed_time(per_model_events[s][j][1])
+                                       for s in range(args.steps)) for j, K in enumerate(my_topics)}
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (per_model_ms, launches))
+        per_model_ms = {k: v for g in gathered for k, v in g[0].items()}
+        launches = sum(g[1] for g in gathered)
+    total_tokens = float(N) * len(N_TOPICS) * args.steps
+    value = total_tokens / (elapsed_ms * 1e-3)
+
+    # ---- roofline of the dominant kernel: the K = 50 sweep ------------------------------------
+    k_dom = max(per_model_ms, key=lambda k: per_model_ms[k])
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        with open(peaks_path) as f:
+            peak, peak_src = float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    else:
+        peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+    achieved = b_tok(k_dom) * N / (per_model_ms[k_dom] * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "sweep_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            with open(tpath) as f:
+                traffic = json.load(f).get(f"K{k_dom}", {}).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": f"sweep_kernel (K={k_dom})", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": b_tok(k_dom) * N, "ms_per_launch": per_model_ms[k_dom],
+                "per_model": {str(k): {"ms": round(v, 4), "gtok_s": round(N / v / 1e6, 3),
+                                       "frac": round(b_tok(k) * N / (v * 1e-3) / 1e9 / peak, 4)}
+                              for k, v in sorted(per_model_ms.items())}}
+
+    # ---- end to end through the C ABI with HOST buffers (rank-local share of the models) ------
+    e2e = None
+    if not args.no_e2e:
+        cell_ptr_h = torch.empty(D + 1, dtype=torch.int64, pin_memory=True)
+        tok_h = torch.empty(N, dtype=torch.int32, pin_memory=True)
+        cell_ptr_h.copy_(cell_ptr)
+        tok_h.copy_(tok)
+        torch.cuda.synchronize()
+        indptr_np, indices_np = cell_ptr_h.numpy(), tok_h.numpy()
+        out_bufs = {K: (torch.empty((K, W), dtype=torch.int32, pin_memory=True).numpy(),
+                        torch.empty((D, K), dtype=torch.int32, pin_memory=True).numpy(),
+                        np.empty(K, np.int32)) for K in my_topics}
+        L = _lib.load()
+
+        def e2e_step():
+            h = ctypes.c_void_p()
+            _lib.check(L.cgs_corpus_from_cells_by_regions(ctypes.byref(h), local_rank, _lib.ptr(indptr_np, _lib.c_i64p),
+                                                          _lib.ptr(indices_np, _lib.c_i32p), D, W, N, 0, D))
+            for K in my_topics:
+                mh = ctypes.c_void_p()
+                _lib.check(L.cgs_model_create(ctypes.byref(mh), h, K, ALPHA / K, ETA, MODEL_SEED, None))
+                _lib.check(L.cgs_model_init(mh))
+                _lib.check(L.cgs_model_sweep(mh, E2E_SWEEPS))
+                a, b, c = out_bufs[K]
+                _lib.check(L.cgs_model_export_counts(mh, _lib.ptr(a, _lib.c_i32p), _lib.ptr(b, _lib.c_i32p),
+                                                     _lib.ptr(c, _lib.c_i32p)))
+                _lib.check(L.cgs_model_destroy(mh))
+            _lib.check(L.cgs_corpus_destroy(h))
+
+        e2e_step()  # warm-up
+        torch.cuda.synchronize()
+        barrier()
+        n_e2e = max(1, min(args.steps, 3))
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        h2d = (D + 1) * 8 + N * 4
+        d2h = sum((K * W + D * K + K) * 4 for K in my_topics)
+        if world > 1:
+            t = torch.tensor([float(h2d), float(d2h)], device=dev, dtype=torch.float64)
+            dist.all_reduce(t)
+            h2d, d2h = int(t[0].item()), int(t[1].item())
+        e2e = {"value": float(N) * len(N_TOPICS) * E2E_SWEEPS * n_e2e / dt, "unit": "tokens/s",
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": n_e2e, "ms_per_step": dt / n_e2e * 1e3,
+               "what": f"host CSR -> cgs_corpus_from_cells_by_regions -> per model: create, init, {E2E_SWEEPS} sweeps, "
+                       f"cgs_model_export_counts to host (all {len(N_TOPICS)} models); wall clock incl. every copy"}
+
+    # ---- CPU baseline on the host cores (rank 0, N = 1 only) -------------------------------------
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        sc = args.cpu_sample_cells
+        cp = cell_ptr[: sc + 1].cpu().numpy()
+        WS, DS = host_sample(cp, tok[: int(cp[-1])].cpu().numpy(), sc)
+        cpu = CpuModels(WS, DS, sc, W, N_TOPICS)
+        cpu.step()
+        t0 = time.perf_counter()
+        n_cpu_steps = 2
+        for _ in range(n_cpu_steps):
+            cpu.step()
+        dt = time.perf_counter() - t0
+        cpu_baseline = {"value": cpu.tokens_per_step * n_cpu_steps / dt, "unit": "tokens/s", "cores": cpu.cores,
+                        "kind": "port",
+                        "sample": f"{n_cpu_steps} sweeps of all {len(N_TOPICS)} models over the first {sc} of {D} cells "
+                                  f"({len(WS)} of {N} tokens), oracle/cgs_oracle.c, one thread per model",
+                        "cpu": cpu_model_name(), "host_cores": os.cpu_count(), "seconds": dt}
+
+    if rank == 0:
+        line = {
+            "metric": "gibbs_tokens_per_s_per_sweep", "value": value, "unit": "tokens/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "int32 counts, fp32 conditional, u16 topics", "data": "synthetic",
+            "config": {"workload": f"{WORKLOAD}: {D} cells x {W} regions, {N} tokens (density {N / (D * W):.4f}), "
+                                   f"n_topics sweep {N_TOPICS}, alpha={ALPHA}/K, eta={ETA}, one step = one Gibbs sweep "
+                                   f"of all {len(N_TOPICS)} models",
+                       "n_topics": N_TOPICS, "tokens": N, "cells": D, "regions": W,
+                       "sharding": "one model per GPU, longest first" if world > 1 else "all models on one GPU",
+                       "plan": {str(r): [N_TOPICS[i] for i in plan[r]] for r in range(world)},
+                       "burn_in_sweeps": BURN_IN, "e2e_sweeps_per_call": E2E_SWEEPS,
+                       "l2": "inputs larger than L2: every model streams 6 B/token of tokens+topics "
+                             f"({6 * N / 1e6:.0f} MB) per sweep and the step cycles through {len(my_topics)} models"},
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clock_info,
+        }
+        print(json.dumps(line), flush=True)
+    for m in models:
+        m.close()
+    corpus.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--cpu-sample-cells", type=int, default=500)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_cuda(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

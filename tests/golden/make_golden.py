@@ -1,0 +1,111 @@
+"""Generates tests/golden/*.npz by executing the REFERENCE's own functions (AST-extracted from
+/root/reference, see oracle/ref_functions.py) and the CPU oracle on small seeded inputs.
+Run in the authoring container (needs /root/reference):   python tests/golden/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+import scipy.sparse as sp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from oracle import lda_oracle as lo  # noqa: E402
+from oracle import ref_functions as rf  # noqa: E402
+
+
+def golden_loglikelihood():
+    """utils.loglikelihood (utils.py:129-160) on random count tables, incl. empty rows/topics."""
+    f = rf.reference_loglikelihood()
+    rng = np.random.default_rng(20261019)
+    out = {}
+    cases = [(3, 7, 5, 50.0, 0.1), (10, 40, 12, 50.0, 0.1), (5, 30, 9, 0.7, 0.02), (2, 11, 4, 25.0, 0.1),
+             (6, 25, 8, 50.0, 0.1)]
+    for i, (K, W, D, alpha, eta) in enumerate(cases):
+        nzw = rng.integers(0, 6, (K, W)) * (rng.random((K, W)) < 0.5)
+        ndz = rng.integers(0, 5, (D, K)) * (rng.random((D, K)) < 0.6)
+        if i == 2:
+            nzw[-1] = 0  # empty last topic
+        if i == 3:
+            ndz[-1] = 0  # empty last cell
+        if i == 4:
+            nzw[:] = 0
+            nzw[1, 3] = 4  # a single non-empty topic followed by empty ones
+        out[f"nzw{i}"], out[f"ndz{i}"] = nzw.astype(np.int32), ndz.astype(np.int32)
+        out[f"par{i}"] = np.array([alpha, eta])
+        out[f"ll{i}"] = np.array(f(nzw, ndz, alpha, eta))
+    out["n"] = np.array(len(cases))
+    np.savez(os.path.join(HERE, "loglikelihood_compat.npz"), **out)
+
+
+def golden_impute():
+    """calculate_imputed_accessibility (diff_features.py:398-492) and calculate_normalized_scores (:540-548)."""
+    f = rf.reference_calculate_imputed_accessibility()
+    g = rf.reference_calculate_normalized_scores()
+    rng = np.random.default_rng(4321)
+    out = {}
+    cases = [(257, 10, 33, 10 ** 6, 64), (1000, 37, 129, 10 ** 6, 300), (500, 100, 64, 10 ** 6, 20000),
+             (300, 5, 50, 1, 100), (300, 5, 50, 1e6, 100), (640, 16, 256, 10 ** 4, 128)]
+    for i, (R, K, C, scale, chunk) in enumerate(cases):
+        a = rng.dirichlet(np.full(R, 0.1), size=K).T.astype(np.float32)  # every topic sums to 1 over regions
+        b = rng.dirichlet(np.full(K, 50.0 / K), size=C).T.astype(np.float32)  # every cell sums to 1 over topics
+        if i == 1:
+            a[10:20] = 0  # all-zero regions must be dropped
+        names = [f"chr1:{j * 500}-{j * 500 + 500}" for j in range(R)]
+        m, kept = f(a, b, names, scale, chunk)
+        out[f"a{i}"], out[f"b{i}"] = a, b
+        out[f"scale{i}"] = np.array(scale, dtype=object if False else np.float64)
+        out[f"scale_is_int{i}"] = np.array(isinstance(scale, int))
+        out[f"chunk{i}"] = np.array(chunk)
+        out[f"out{i}"] = m
+        out[f"kept{i}"] = np.array([names.index(k) for k in kept], np.int64)
+        if i in (0, 5):
+            out[f"norm{i}"] = g(m.astype(np.float64) if m.dtype != np.float64 else m, 10 ** 4)
+    out["n"] = np.array(len(cases))
+    np.savez_compressed(os.path.join(HERE, "impute.npz"), **out)
+
+
+def golden_oracle_kat():
+    """Known-answer vectors frozen from the CPU oracle (pins the oracle against regressions;
+    parity with the real `lda` package stays UNPINNED, see oracle/lda_oracle.py)."""
+    X = sp.csr_matrix(np.array([[1, 1, 0, 1, 0, 1],
+                                [0, 1, 1, 0, 1, 0],
+                                [1, 0, 1, 1, 1, 1],
+                                [0, 1, 0, 1, 0, 1]], dtype=np.int32))
+    K, alpha, eta, seed = 2, 0.5, 0.1, 7
+    o = lo.OracleLDA(K, n_iter=0, alpha=alpha, eta=eta, random_state=seed, keep_z=True)
+    o._initialize(X)
+    rs = np.random.RandomState(seed)
+    rands = o._rands.copy()
+    zs, lls = [o.ZS.copy()], [o.loglikelihood()]
+    for _ in range(3):
+        rs.shuffle(rands)
+        o._sample_topics(rands)
+        zs.append(o.ZS.copy())
+        lls.append(o.loglikelihood())
+    out = {"X": X.toarray(), "K": np.array(K), "alpha": np.array(alpha), "eta": np.array(eta), "seed": np.array(seed),
+           "WS": o.WS, "DS": o.DS, "z": np.array(zs), "ll": np.array(lls), "nzw": o.nzw_, "ndz": o.ndz_, "nz": o.nz_}
+    # a C1-like small trace
+    from pycistopic_b200.synth import make_binary_matrix
+    m, _, _ = make_binary_matrix(n_cells=60, n_regions=800, density=0.05, n_true_topics=4, seed=3)
+    Xs = sp.csr_matrix(m.T)
+    o2 = lo.OracleLDA(5, n_iter=20, alpha=10.0, eta=0.1, random_state=555, refresh=1).fit(Xs)
+    out["trace_X_indptr"], out["trace_X_indices"] = Xs.indptr, Xs.indices
+    out["trace_shape"] = np.array(Xs.shape)
+    out["trace_ll"] = np.array(o2.loglikelihoods_ + [o2.final_loglikelihood_])
+    out["trace_nz"] = o2.nz_
+    out["trace_mimno"] = lo.metric_coherence_mimno_2011(o2.topic_word_, Xs)
+    out["trace_arun"] = np.array(lo.metric_arun_2010(o2.topic_word_, o2.doc_topic_,
+                                                      np.asarray(Xs.sum(axis=1)).astype(float)))
+    out["trace_cao"] = np.array(lo.metric_cao_juan_2009(o2.topic_word_))
+    np.savez_compressed(os.path.join(HERE, "oracle_kat.npz"), **out)
+
+
+if __name__ == "__main__":
+    if not rf.available():
+        sys.exit("the reference tree is not available: cannot regenerate the golden fixtures")
+    golden_loglikelihood()
+    golden_impute()
+    golden_oracle_kat()
+    print("golden fixtures written to", HERE)

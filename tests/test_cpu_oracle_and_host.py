@@ -1,0 +1,280 @@
+"""CPU tests (no GPU): the oracle against golden vectors and against independent restatements,
+the host-side logic (metrics, DataFrame packing, model selection, scheduling), and that the
+C-ABI library loads and exports every symbol include/cgs_b200.h declares."""
+import ctypes
+import os
+import pickle
+import re
+
+import numpy as np
+import pandas as pd
+import pytest
+import scipy.sparse as sp
+
+from oracle import lda_oracle as lo
+from oracle import ref_functions as rf
+from pycistopic_b200 import _lib, lda_models
+from pycistopic_b200 import metrics as pm
+from pycistopic_b200.synth import SyntheticCistopicObject, make_binary_matrix
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+# ---- C ABI ------------------------------------------------------------------------------------
+def test_abi_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "cgs_b200.h")).read()
+    declared = set(re.findall(r"\b(cgs_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 30
+    L = _lib.load()
+    for name in declared:
+        assert hasattr(L, name), f"{name} is declared in include/cgs_b200.h but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert L.cgs_version() >= 100 and L.cgs_max_topics() == 512
+
+
+def test_no_cpu_fallback_without_device():
+    n = ctypes.c_int(0)
+    rc = _lib.load().cgs_device_count(ctypes.byref(n))
+    if rc == 0 and n.value > 0:
+        pytest.skip("a GPU is visible")
+    m, cells, regions = make_binary_matrix(n_cells=20, n_regions=100, density=0.1, n_true_topics=2, seed=1)
+    with pytest.raises(RuntimeError):
+        lda_models.run_cgs_models(SyntheticCistopicObject(m, cells, regions), n_topics=[2], n_iter=2)
+    from pycistopic_b200 import LDA
+    with pytest.raises(RuntimeError):
+        LDA(2, n_iter=1).fit(sp.csr_matrix(m.T))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "pycistopic_b200")
+    for f in os.listdir(pkg):
+        if f.endswith(".py"):
+            src = open(os.path.join(pkg, f)).read()
+            assert "oracle" not in src.replace("# oracle", ""), f"{f} mentions the oracle"
+
+
+# ---- oracle vs golden / independent restatements -------------------------------------------------
+def test_oracle_known_answer_vectors():
+    g = np.load(os.path.join(GOLD, "oracle_kat.npz"))
+    X = sp.csr_matrix(g["X"])
+    K, alpha, eta, seed = int(g["K"]), float(g["alpha"]), float(g["eta"]), int(g["seed"])
+    o = lo.OracleLDA(K, n_iter=0, alpha=alpha, eta=eta, random_state=seed, keep_z=True)
+    o._initialize(X)
+    assert np.array_equal(o.WS, g["WS"]) and np.array_equal(o.DS, g["DS"])
+    rs = np.random.RandomState(seed)
+    rands = o._rands.copy()
+    assert np.array_equal(o.ZS, g["z"][0])
+    for it in range(3):
+        rs.shuffle(rands)
+        o._sample_topics(rands)
+        assert np.array_equal(o.ZS, g["z"][it + 1])
+        assert o.loglikelihood() == pytest.approx(float(g["ll"][it + 1]), rel=1e-13)
+    assert np.array_equal(o.nzw_, g["nzw"]) and np.array_equal(o.ndz_, g["ndz"]) and np.array_equal(o.nz_, g["nz"])
+    Xs = sp.csr_matrix((np.ones(len(g["trace_X_indices"]), np.int32), g["trace_X_indices"], g["trace_X_indptr"]),
+                       shape=tuple(g["trace_shape"]))
+    o2 = lo.OracleLDA(5, n_iter=20, alpha=10.0, eta=0.1, random_state=555, refresh=1).fit(Xs)
+    np.testing.assert_allclose(o2.loglikelihoods_ + [o2.final_loglikelihood_], g["trace_ll"], rtol=1e-13)
+    assert np.array_equal(o2.nz_, g["trace_nz"])
+    np.testing.assert_allclose(lo.metric_coherence_mimno_2011(o2.topic_word_, Xs), g["trace_mimno"], rtol=1e-12)
+
+
+def _py_sample_topics(WS, DS, ZS, nzw, ndz, nz, alpha, eta, rands):
+    """Line-by-line Python restatement of lda._lda._sample_topics."""
+    K, W = nzw.shape
+    eta_sum = eta * W
+    for i in range(len(WS)):
+        w, d, z = WS[i], DS[i], ZS[i]
+        nzw[z, w] -= 1; ndz[d, z] -= 1; nz[z] -= 1
+        dist = np.cumsum((nzw[:, w] + eta) / (nz + eta_sum) * (ndz[d] + alpha))
+        r = rands[i % len(rands)] * dist[-1]
+        z_new = int(np.searchsorted(dist, r, side="left"))
+        ZS[i] = z_new
+        nzw[z_new, w] += 1; ndz[d, z_new] += 1; nz[z_new] += 1
+
+
+def test_oracle_c_matches_python_restatement():
+    rng = np.random.default_rng(0)
+    X = sp.csr_matrix((rng.random((15, 40)) < 0.2).astype(np.int32))
+    K, alpha, eta, seed = 4, 0.8, 0.05, 3
+    o = lo.OracleLDA(K, n_iter=0, alpha=alpha, eta=eta, random_state=seed, keep_z=True)
+    o._initialize(X)
+    WS, DS = lo.matrix_to_lists_py(X)
+    assert np.array_equal(WS, o.WS) and np.array_equal(DS, o.DS)
+    ZS = np.arange(len(WS)) % K
+    nzw = np.zeros((K, X.shape[1]), np.int64); ndz = np.zeros((X.shape[0], K), np.int64); nz = np.zeros(K, np.int64)
+    np.add.at(nzw, (ZS, WS), 1); np.add.at(ndz, (DS, ZS), 1); np.add.at(nz, ZS, 1)
+    assert np.array_equal(nzw, o.nzw_) and np.array_equal(ndz, o.ndz_)
+    rs = np.random.RandomState(seed)
+    rands = o._rands.copy()
+    for _ in range(4):
+        rs.shuffle(rands)
+        o._sample_topics(rands)
+        _py_sample_topics(WS, DS, ZS, nzw, ndz, nz, alpha, eta, rands)
+        assert np.array_equal(ZS, o.ZS)
+    assert np.array_equal(nzw, o.nzw_) and np.array_equal(ndz, o.ndz_) and np.array_equal(nz, o.nz_)
+    assert lo.loglikelihood_true(nzw, ndz, nz, alpha, eta) == pytest.approx(
+        lo.loglikelihood_true_py(nzw, ndz, nz, alpha, eta), rel=1e-12)
+    # count matrices (not binary) expand into repeated tokens
+    Xc = sp.csr_matrix(np.array([[2, 0, 1], [0, 3, 0]], dtype=np.int32))
+    WS2, DS2 = lo.matrix_to_lists(Xc)
+    assert WS2.tolist() == [0, 0, 2, 1, 1, 1] and DS2.tolist() == [0, 0, 0, 1, 1, 1]
+    with pytest.raises(ValueError):
+        lo.matrix_to_lists(sp.csr_matrix(np.array([[0.5, 0.0]])))
+    with pytest.raises(ValueError):
+        lo.OracleLDA(2, alpha=0.0)
+
+
+def test_oracle_adlda_single_part_equals_sequential():
+    m, _, _ = make_binary_matrix(n_cells=40, n_regions=300, density=0.08, n_true_topics=3, seed=5)
+    X = sp.csr_matrix(m.T)
+    a = lo.OracleLDA(4, n_iter=5, alpha=1.0, eta=0.1, random_state=9, refresh=1).fit(X)
+    b = lo.OracleLDA(4, n_iter=5, alpha=1.0, eta=0.1, random_state=9, refresh=1, n_parts=1).fit(X)
+    assert np.array_equal(a.nzw_, b.nzw_)
+    c = lo.OracleLDA(4, n_iter=5, alpha=1.0, eta=0.1, random_state=9, refresh=1, n_parts=3).fit(X)
+    assert c.nz_.sum() == a.nz_.sum() == X.nnz and np.array_equal(c.nzw_.sum(axis=1), c.nz_)
+    ptr = lo.balanced_cell_partition(np.concatenate([[0], np.cumsum(np.diff(X.indptr))]), 3)
+    assert ptr[0] == 0 and ptr[-1] == X.shape[0] and np.all(np.diff(ptr) > 0)
+
+
+# ---- functions that live in the reference tree: golden fixtures ------------------------------------
+def test_loglikelihood_compat_matches_reference_golden():
+    g = np.load(os.path.join(GOLD, "loglikelihood_compat.npz"))
+    for i in range(int(g["n"])):
+        alpha, eta = g[f"par{i}"]
+        got = pm.loglikelihood_compat(g[f"nzw{i}"], g[f"ndz{i}"], float(alpha), float(eta))
+        assert got == pytest.approx(float(g[f"ll{i}"]), rel=1e-12, abs=1e-9)
+
+
+@pytest.mark.skipif(not rf.available(), reason="/root/reference not present")
+def test_loglikelihood_compat_matches_live_reference():
+    f = rf.reference_loglikelihood()
+    rng = np.random.default_rng(1)
+    for _ in range(20):
+        K, W, D = rng.integers(1, 8), rng.integers(2, 30), rng.integers(1, 12)
+        nzw = rng.integers(0, 4, (K, W)) * (rng.random((K, W)) < 0.4)
+        ndz = rng.integers(0, 4, (D, K)) * (rng.random((D, K)) < 0.5)
+        alpha, eta = float(rng.uniform(0.05, 60)), float(rng.uniform(0.01, 1))
+        assert pm.loglikelihood_compat(nzw, ndz, alpha, eta) == pytest.approx(f(nzw, ndz, alpha, eta), rel=1e-11, abs=1e-8)
+
+
+def test_normalize_scores_matches_reference_golden():
+    from pycistopic_b200.diff_features import CistopicImputedFeatures, normalize_scores
+    g = np.load(os.path.join(GOLD, "impute.npz"))
+    for i in (0, 5):
+        out = g[f"out{i}"]
+        obj = CistopicImputedFeatures(out, [str(j) for j in range(out.shape[0])], [str(j) for j in range(out.shape[1])], "p")
+        res = normalize_scores(obj, scale_factor=10 ** 4)
+        np.testing.assert_allclose(res.mtx, g[f"norm{i}"], rtol=1e-12)
+        df = normalize_scores(pd.DataFrame(out.astype(np.float64)), scale_factor=10 ** 4)
+        np.testing.assert_allclose(df.to_numpy(), g[f"norm{i}"], rtol=1e-12)
+
+
+# ---- metrics: product implementation vs oracle restatement -----------------------------------------
+@pytest.fixture(scope="module")
+def fitted():
+    m, cells, regions = make_binary_matrix(n_cells=80, n_regions=1200, density=0.05, n_true_topics=4, seed=21)
+    X = sp.csr_matrix(m.T)
+    o = lo.OracleLDA(7, n_iter=30, alpha=50 / 7, eta=0.1, random_state=555, refresh=30).fit(X)
+    return m, cells, regions, X, o
+
+
+def test_metrics_match_oracle_restatements(fitted):
+    m, _, _, X, o = fitted
+    doc_len = np.asarray(X.sum(axis=1)).astype(float)
+    assert pm.metric_arun_2010(o.topic_word_, o.doc_topic_, doc_len) == pytest.approx(
+        lo.metric_arun_2010(o.topic_word_, o.doc_topic_, doc_len), rel=1e-9)
+    assert pm.metric_cao_juan_2009(o.topic_word_) == pytest.approx(lo.metric_cao_juan_2009(o.topic_word_), rel=1e-11)
+    np.testing.assert_allclose(pm.metric_coherence_mimno_2011(o.topic_word_, m),
+                               lo.metric_coherence_mimno_2011(o.topic_word_, X), rtol=1e-11)
+    np.testing.assert_allclose(pm.marginal_topic_distrib(o.doc_topic_, doc_len),
+                               lo.marginal_topic_distrib(o.doc_topic_, doc_len), rtol=1e-12)
+    with pytest.raises(ValueError):
+        pm.metric_coherence_mimno_2011(o.topic_word_[:, :10], m[:10], top_n=20)
+
+
+def test_model_packing_layout(fitted, tmp_path):
+    """CistopicLDAModel layout of lda_models.py:307-388."""
+    m, cells, regions, X, o = fitted
+    K = 7
+    model = lda_models.build_cistopic_model(o, m, K, cells, regions, 30, 555, 50, True, 0.1, False, 5, 1.25,
+                                            save_path=str(tmp_path / "models"))
+    assert list(model.metrics.columns) == ["Arun_2010", "Cao_Juan_2009", "Mimno_2011", "loglikelihood"]
+    assert list(model.metrics.index) == ["Metric"] and model.metrics.shape == (1, 4)
+    assert list(model.coherence.columns) == ["Topic", "Mimno_2011"] and model.coherence.shape == (K, 2)
+    assert model.coherence["Topic"].tolist() == list(range(1, K + 1))
+    assert list(model.marg_topic.columns) == ["Topic", "Marg_Topic"]
+    assert model.marg_topic["Marg_Topic"].sum() == pytest.approx(1.0)
+    assert list(model.topic_ass.columns) == ["Topic", "Assignments"]
+    assert model.topic_ass["Assignments"].tolist() == o.nz_.tolist()
+    assert model.cell_topic.shape == (K, len(cells)) and list(model.cell_topic.index) == [f"Topic{i}" for i in range(1, K + 1)]
+    assert list(model.cell_topic.columns) == cells
+    assert model.topic_region.shape == (len(regions), K) and list(model.topic_region.index) == regions
+    np.testing.assert_allclose(model.cell_topic.to_numpy(), o.doc_topic_.T)
+    np.testing.assert_allclose(model.topic_region.to_numpy(), o.topic_word_.T)
+    assert list(model.parameters.index) == ["package", "n_topics", "n_iter", "random_state", "alpha", "alpha_by_topic",
+                                            "eta", "eta_by_topic", "top_topics_coh", "time"]
+    assert model.parameters.loc["package", "Parameter"] == "lda" and model.parameters.loc["alpha", "Parameter"] == 50
+    assert model.cell_topic_harmony == [] and (model.n_cells, model.n_regions, model.n_topic) == (len(cells), len(regions), K)
+    assert str(model).startswith("CistopicLDAModel with 7 topics")
+    # metrics: the buggy-compatible loglikelihood is called with the RAW alpha/eta (lda_models.py:305)
+    assert model.metrics.loc["Metric", "loglikelihood"] == pytest.approx(pm.loglikelihood_compat(o.nzw_, o.ndz_, 50, 0.1))
+    mim = lo.metric_coherence_mimno_2011(o.topic_word_, X)
+    assert model.metrics.loc["Metric", "Mimno_2011"] == pytest.approx(np.mean(np.sort(mim)[-5:]))
+    with open(tmp_path / "models" / "Topic7.pkl", "rb") as f:
+        again = pickle.load(f)
+    assert again.n_topic == K and again.topic_region.equals(model.topic_region)
+    obj = SyntheticCistopicObject(m, cells, regions)
+    obj.add_LDA_model(model)
+    assert obj.selected_model is model
+
+
+def _fake_model(k, arun, cao, mimno, ll):
+    metrics = pd.DataFrame([arun, cao, mimno, ll], index=["Arun_2010", "Cao_Juan_2009", "Mimno_2011", "loglikelihood"],
+                           columns=["Metric"]).transpose()
+    ct = pd.DataFrame(np.zeros((k, 3)))
+    tr = pd.DataFrame(np.zeros((4, k)))
+    return lda_models.CistopicLDAModel(metrics, None, None, None, ct, tr, None)
+
+
+def test_evaluate_models_selection():
+    """Model selection arithmetic of lda_models.py:1109-1216, checked against a direct computation."""
+    ks = [2, 5, 10, 15, 20]
+    arun = [9.0, 7.0, 4.0, 5.0, 6.0]
+    cao = [0.5, 0.3, 0.2, 0.25, 0.4]
+    mim = [-0.2, -0.5, -0.3, -0.35, -0.6]
+    ll = [-100.0, -80.0, -60.0, -65.0, -90.0]
+    models = [_fake_model(k, a, c, m, l) for k, a, c, m, l in zip(ks, arun, cao, mim, ll)]
+    shuffled = [models[i] for i in (3, 0, 4, 1, 2)]
+    best = lda_models.evaluate_models(shuffled, plot=False)
+    resc = lambda v: (np.array(v) - min(v)) / (max(v) - min(v))
+    idx = [i for i, k in enumerate(ks) if k >= 5]
+    comb = (resc([-x for x in arun])[idx] + resc([-x for x in cao])[idx] + resc([mim[i] for i in idx]) + resc(ll)[idx])
+    assert best.n_topic == ks[idx[int(np.argmax(comb))]] == 10
+    assert lda_models.evaluate_models(shuffled, select_model=15, plot=False).n_topic == 15
+    assert lda_models.evaluate_models(shuffled, plot=False, return_model=False) is None
+    only = lda_models.evaluate_models(shuffled, metrics=["loglikelihood", "Arun_2010"], plot=False)
+    assert only.n_topic == 10
+    best2 = lda_models.evaluate_models(shuffled, metrics=["Cao_Juan_2009"], plot=False)
+    assert best2.n_topic == 10
+
+
+def test_schedule_models_lpt():
+    topics = [2, 5, 10, 15, 20, 25, 30, 35, 40, 45, 50]
+    for n in (1, 2, 4, 8):
+        plan = lda_models.schedule_models(topics, n)
+        assert sorted(i for p in plan for i in p) == list(range(len(topics)))
+        loads = [sum(lda_models.model_cost(topics[i]) for i in p) for p in plan]
+        total = sum(lda_models.model_cost(k) for k in topics)
+        assert max(loads) <= max(total / n * 4 / 3 + 1e-9, lda_models.model_cost(50))
+    assert lda_models.schedule_models(topics, 1) == [sorted(range(len(topics)), key=lambda i: -topics[i])]
+
+
+def test_synthetic_shapes_and_duck_object():
+    m, cells, regions = make_binary_matrix(n_cells=50, n_regions=2000, density=0.03, n_true_topics=5, seed=2)
+    assert m.dtype == np.int32 and m.max() == 1 and m.shape == (len(regions), len(cells))
+    assert m.has_sorted_indices
+    dens = m.nnz / (2000 * 50)  # against the nominal shape (empty regions are dropped)
+    assert 0.02 < dens < 0.05
+    m2, _, _ = make_binary_matrix(n_cells=50, n_regions=2000, density=0.03, n_true_topics=5, seed=2)
+    assert (m != m2).nnz == 0
