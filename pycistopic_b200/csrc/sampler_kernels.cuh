@@ -78,8 +78,18 @@ __device__ __forceinline__ int log2_tpt() {
     return TPT == 1 ? 0 : TPT == 2 ? 1 : TPT == 4 ? 2 : TPT == 8 ? 3 : TPT == 16 ? 4 : 5;
 }
 
+// (c + oc) mod CH for c, oc in [0, CH)
+template <int CH>
+__device__ __forceinline__ int rot_chunk(int c, int oc) {
+    if (CH == 1) return 0;
+    if (CH == 2) return (c + oc) & 1;
+    if (CH == 4) return (c + oc) & 3;
+    const int t = c + oc;
+    return t >= CH ? t - CH : t;
+}
+
 template <int TPT, int CH>
-__global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const SweepParams p) {
+__global__ void __launch_bounds__(kSweepThreads, (CH <= 2 ? 4 : 3)) sweep_kernel(const SweepParams p) {
     constexpr int KS = TPT * CH * 4;  // topic slots covered by one token group
     constexpr unsigned FULL = 0xffffffffu;
     __shared__ __align__(16) float f_s[KS];    // (n_dk + alpha) / (n_k + eta W)
@@ -148,14 +158,21 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const SweepParams 
             const int rem = (int)min((int64_t)32, t1 - base);
             const int nsteps = rem < TPT ? rem : TPT;
 
+            // Chunk order is rotated per token so that the chunk holding the token's own topic is
+            // always register chunk 0 of its lane: the own-token exclusion then patches 4 slots
+            // instead of all CH*4 (any fixed order of the topics gives the same distribution).
             int4 rcur[CH], rnext[CH];
             int w_cur = __shfl_sync(FULL, w_j, gbase);
+            int zo_cur = __shfl_sync(FULL, zo_j, gbase);
+            {
+                const int oc = (zo_cur >> 2) >> log2_tpt<TPT>();
 #pragma unroll
-            for (int c = 0; c < CH; ++c) {
-                const int chunk = sub + TPT * c;
-                rcur[c] = make_int4(0, 0, 0, 0);
-                if (w_cur >= 0 && chunk * 4 < Kp)
-                    rcur[c] = ld_row_chunk(p.n_wk + (int64_t)w_cur * Kp + chunk * 4);
+                for (int c = 0; c < CH; ++c) {
+                    const int chunk = sub + TPT * rot_chunk<CH>(c, oc);
+                    rcur[c] = make_int4(0, 0, 0, 0);
+                    if (w_cur >= 0 && chunk * 4 < Kp)
+                        rcur[c] = ld_row_chunk(p.n_wk + (int64_t)w_cur * Kp + chunk * 4);
+                }
             }
 
             for (int s = 0; s < nsteps; ++s) {
@@ -166,7 +183,7 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const SweepParams 
                         const int d = atomicExch(&dnk_s[k], 0);
                         if (d != 0) red_add_i32(p.n_k + k, d);
                         const float den = (float)ld_volatile_i32(p.n_k + k) + p.etaW;
-                        const float inv = 1.0f / den;
+                        const float inv = __frcp_rn(den);
                         den_s[k] = den;
                         inv_s[k] = inv;
                         f_s[k] = ((float)ndk_s[k] + alpha) * inv;
@@ -174,44 +191,48 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const SweepParams 
                     __syncwarp();
                 }
                 // ---- prefetch the rows of the next step --------------------------------------
-                int w_next = -1;
+                int w_next = -1, zo_next = 0;
                 if (TPT > 1) {
                     const int src = gbase + ((s + 1) & (TPT - 1));
                     w_next = __shfl_sync(FULL, w_j, src);
+                    zo_next = __shfl_sync(FULL, zo_j, src);
                     if (s + 1 >= nsteps) w_next = -1;
+                    const int ocn = (zo_next >> 2) >> log2_tpt<TPT>();
 #pragma unroll
                     for (int c = 0; c < CH; ++c) {
-                        const int chunk = sub + TPT * c;
+                        const int chunk = sub + TPT * rot_chunk<CH>(c, ocn);
                         rnext[c] = make_int4(0, 0, 0, 0);
                         if (w_next >= 0 && chunk * 4 < Kp)
                             rnext[c] = ld_row_chunk(p.n_wk + (int64_t)w_next * Kp + chunk * 4);
                     }
                 }
                 const int w = w_cur;
-                const int zo = (TPT > 1) ? __shfl_sync(FULL, zo_j, gbase + s) : zo_j;
+                const int zo = zo_cur;
                 const float u = (TPT > 1) ? __shfl_sync(FULL, u_j, gbase + s) : u_j;
 
-                // ---- own-token exclusion: slot of z_old in this lane (or -1) ------------------
+                // ---- own-token exclusion: component of z_old in chunk 0 of its lane (or -1) -----
                 const int ochunk = zo >> 2;
-                const int osub = ochunk & (TPT - 1);
                 const int oc = ochunk >> log2_tpt<TPT>();
-                const int hit = (sub == osub) ? (oc * 4 + (zo & 3)) : -1;
-                const float fpp = ((float)(ndk_s[zo] - 1) + alpha) / (den_s[zo] - 1.0f);
+                const int hitq = (sub == (ochunk & (TPT - 1))) ? (zo & 3) : -1;
+                const float fpp = __fdividef((float)(ndk_s[zo] - 1) + alpha, den_s[zo] - 1.0f);
 
                 // ---- running sum of p(k) over this lane's slots -------------------------------
                 float cum[CH * 4];
                 float acc = 0.0f;
 #pragma unroll
                 for (int c = 0; c < CH; ++c) {
-                    const float4 fv = *reinterpret_cast<const float4 *>(&f_s[(sub + TPT * c) * 4]);
-                    const int nn[4] = {rcur[c].x, rcur[c].y, rcur[c].z, rcur[c].w};
-                    const float ff[4] = {fv.x, fv.y, fv.z, fv.w};
+                    const int chunk = sub + TPT * rot_chunk<CH>(c, oc);
+                    const float4 fv = *reinterpret_cast<const float4 *>(&f_s[chunk * 4]);
+                    int nn[4] = {rcur[c].x, rcur[c].y, rcur[c].z, rcur[c].w};
+                    float ff[4] = {fv.x, fv.y, fv.z, fv.w};
+                    if (c == 0) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (hitq == q) { nn[q] -= 1; ff[q] = fpp; }
+                    }
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        int n = nn[q];
-                        float fq = ff[q];
-                        if (hit == c * 4 + q) { n -= 1; fq = fpp; }
-                        acc = fmaf((float)n + eta, fq, acc);
+                        acc = fmaf((float)nn[q] + eta, ff[q], acc);
                         cum[c * 4 + q] = acc;
                     }
                 }
@@ -226,12 +247,11 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const SweepParams 
                     }
                 }
                 const float total = (TPT > 1) ? __shfl_sync(FULL, incl, TPT - 1, TPT) : incl;
-                const float excl = incl - acc;
-                const float thr = u * total;
+                const float tloc = u * total - (incl - acc);  // threshold relative to this lane
                 int cnt = 0;
 #pragma unroll
-                for (int j = 0; j < CH * 4; ++j) cnt += ((excl + cum[j]) <= thr) ? 1 : 0;
-                const int cand = (sub + TPT * (cnt >> 2)) * 4 + (cnt & 3);
+                for (int j = 0; j < CH * 4; ++j) cnt += (cum[j] <= tloc) ? 1 : 0;
+                const int cand = (sub + TPT * rot_chunk<CH>(cnt >> 2, oc)) * 4 + (cnt & 3);
                 int zn;
                 if (TPT > 1) {
                     const unsigned bal = __ballot_sync(FULL, cnt < CH * 4);
@@ -259,6 +279,7 @@ __global__ void __launch_bounds__(kSweepThreads) sweep_kernel(const SweepParams 
                 }
                 if (TPT > 1) {
                     w_cur = w_next;
+                    zo_cur = zo_next;
 #pragma unroll
                     for (int c = 0; c < CH; ++c) rcur[c] = rnext[c];
                 }
