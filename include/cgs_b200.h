@@ -94,6 +94,10 @@ int cgs_model_get_z(cgs_model *m, int32_t *z);
 /* n_sweeps collapsed-Gibbs sweeps over every token of the corpus (replaces
  * lda._lda._sample_topics).  Asynchronous. */
 int cgs_model_sweep(cgs_model *m, int32_t n_sweeps);
+/* One PART of a sweep: the cells at queue positions part, part + n_parts, ... (the queue is
+ * longest-first, so the parts are token-balanced).  Calling it for part = 0 .. n_parts-1 is one
+ * sweep; AD-LDA uses it to exchange n_wk deltas several times per sweep. */
+int cgs_model_sweep_part(cgs_model *m, int32_t part, int32_t n_parts);
 /* Tuning knobs of the sweep kernel: lanes that cooperate on one token (power of two, must
  * cover n_topics with at most 16 topics per lane) and warps that share one cell.  The defaults
  * are chosen from n_topics and the mean cell size at cgs_model_create. */
@@ -143,6 +147,12 @@ int cgs_model_snapshot(cgs_model *m);
  * the result to the local n_wk / n_k.  The caller provides the cross-rank barrier before
  * (all deltas computed) and after (all reads done). */
 int cgs_model_delta_apply_peers(cgs_model *m, void *const *peer_delta, int32_t n_ranks);
+
+/* CUDA IPC plumbing so that ranks (one process per GPU) can map each other's delta buffers:
+ * export a 64-byte handle of a cgs-owned device buffer, open a peer's handle, close it. */
+int cgs_ipc_export(void *device_ptr, void *handle_out_64_bytes);
+int cgs_ipc_open(int device, const void *handle_64_bytes, void **device_ptr);
+int cgs_ipc_close(int device, void *device_ptr);
 
 /* ---- imputation (replaces the fp32 chunk product of diff_features.py:443-464) --------- */
 /* out[r, c] = trunc_int32( (sum_k topic_region[r, k] * cell_topic[k, c]) * scale ) when

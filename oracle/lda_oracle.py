@@ -157,7 +157,7 @@ class OracleLDA:
     """
 
     def __init__(self, n_topics, n_iter=2000, alpha=0.1, eta=0.01, random_state=None, refresh=10,
-                 n_parts=1, keep_z=False):
+                 n_parts=1, keep_z=False, part_ptr=None):
         if alpha <= 0 or eta <= 0:
             raise ValueError("alpha and eta must be greater than zero")
         self.n_topics = n_topics
@@ -168,6 +168,7 @@ class OracleLDA:
         self.refresh = refresh
         self.n_parts = n_parts
         self.keep_z = keep_z
+        self.part_ptr = part_ptr
         rng = np.random.RandomState(random_state)
         self._rands = rng.rand(1024 ** 2 // 8)
 
@@ -212,7 +213,8 @@ class OracleLDA:
         if self.n_parts > 1:
             cnt = np.bincount(self.DS, minlength=X.shape[0]).astype(np.int64)
             self._cell_ptr = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
-            self._part_ptr = balanced_cell_partition(self._cell_ptr, self.n_parts).astype(np.int32)
+            pp = self.part_ptr if self.part_ptr is not None else balanced_cell_partition(self._cell_ptr, self.n_parts)
+            self._part_ptr = np.ascontiguousarray(pp, dtype=np.int32)
         random_state = np.random.RandomState(self.random_state)
         rands = self._rands.copy()
         for it in range(self.n_iter):

@@ -48,6 +48,7 @@ SIGNATURES = {
     "cgs_model_set_z": (ctypes.c_int, [c_vp, c_i32p]),
     "cgs_model_get_z": (ctypes.c_int, [c_vp, c_i32p]),
     "cgs_model_sweep": (ctypes.c_int, [c_vp, ctypes.c_int32]),
+    "cgs_model_sweep_part": (ctypes.c_int, [c_vp, ctypes.c_int32, ctypes.c_int32]),
     "cgs_model_set_sweep_shape": (ctypes.c_int, [c_vp, ctypes.c_int32, ctypes.c_int32]),
     "cgs_model_set_max_blocks": (ctypes.c_int, [c_vp, ctypes.c_int32]),
     "cgs_model_set_nk_staleness": (ctypes.c_int, [c_vp, ctypes.c_double]),
@@ -65,6 +66,9 @@ SIGNATURES = {
     "cgs_model_delta_apply": (ctypes.c_int, [c_vp]),
     "cgs_model_snapshot": (ctypes.c_int, [c_vp]),
     "cgs_model_delta_apply_peers": (ctypes.c_int, [c_vp, ctypes.POINTER(c_vp), ctypes.c_int32]),
+    "cgs_ipc_export": (ctypes.c_int, [c_vp, c_vp]),
+    "cgs_ipc_open": (ctypes.c_int, [ctypes.c_int, c_vp, ctypes.POINTER(c_vp)]),
+    "cgs_ipc_close": (ctypes.c_int, [ctypes.c_int, c_vp]),
     "cgs_impute_chunk": (ctypes.c_int, [ctypes.c_int, c_f32p, c_f32p, ctypes.c_int32, ctypes.c_int32,
                                         ctypes.c_int32, ctypes.c_float, ctypes.c_int, c_vp, c_u8p]),
     "cgs_impute_chunk_device": (ctypes.c_int, [ctypes.c_int, c_vp, c_vp, ctypes.c_int32, ctypes.c_int32,

@@ -1,0 +1,230 @@
+"""One large model sharded by cells over several GPUs (AD-LDA).
+
+One process per GPU (``torchrun``); ``torch.distributed`` is the plumbing.  Cells are split into
+contiguous, token-balanced ranges; every rank keeps its token/topic shard and its ``n_dk`` rows
+private, and a full replica of ``n_wk`` / ``n_k``.  After every sweep (or every 1/``sync_per_sweep``
+of a sweep) the ranks exchange their ``n_wk`` deltas:
+
+* ``exchange="nccl"``: ``delta = n_wk - snapshot`` (kernel) -> ``all_reduce(delta)`` (NCCL over
+  NVLink) -> ``n_wk = snapshot + delta; snapshot = n_wk; n_k = colsum`` (one kernel);
+* ``exchange="peer"``: every rank maps the other ranks' delta buffers (CUDA IPC) and ONE kernel
+  reads them over NVLink, reduces, applies and rebuilds ``n_k``; NCCL only provides the two
+  stream-ordered barriers around it.
+
+The reference has no equivalent (its multi-core analogue is Mallet's per-iteration merge of
+per-thread count copies, lda_models.py:572-573).  The orchestration below is independent of the
+device: tests drive it with a CPU shard backend under ``gloo``.
+"""
+from __future__ import annotations
+
+import numpy as np
+import scipy.sparse as sparse
+
+
+def balanced_cell_partition(tokens_per_cell, n_parts):
+    """Contiguous cell ranges with nearly equal token counts; returns int64[n_parts + 1]."""
+    cell_ptr = np.concatenate([[0], np.cumsum(np.asarray(tokens_per_cell, dtype=np.int64))])
+    D = len(cell_ptr) - 1
+    N = int(cell_ptr[-1])
+    targets = np.arange(1, n_parts, dtype=np.float64) * N / n_parts
+    cuts = np.clip(np.searchsorted(cell_ptr, targets, side="left"), 0, D)
+    ptr = np.concatenate([[0], cuts, [D]]).astype(np.int64)
+    # every part needs at least one cell
+    for i in range(1, len(ptr)):
+        if ptr[i] <= ptr[i - 1]:
+            ptr[i] = min(D, ptr[i - 1] + 1)
+    for i in range(len(ptr) - 2, -1, -1):
+        if ptr[i] >= ptr[i + 1]:
+            ptr[i] = max(0, ptr[i + 1] - 1)
+    return ptr, cell_ptr
+
+
+class GpuShard:
+    """Shard backend on one GPU: a :class:`DeviceModel` over this rank's cells."""
+
+    def __init__(self, binary_matrix, cell_range, token_offset, n_topics, alpha, eta, seed, device, exchange):
+        import torch
+
+        from .lda import Corpus, DeviceModel
+        self.torch = torch
+        self.device = device
+        torch.cuda.set_device(device)
+        self.stream = torch.cuda.Stream(device=device)
+        torch.cuda.set_stream(self.stream)
+        self.corpus = Corpus.from_regions_by_cells(binary_matrix, device=device, cell_range=cell_range)
+        self.corpus.set_token_offset(token_offset)
+        self.model = DeviceModel(self.corpus, n_topics, alpha, eta, seed=seed, stream=self.stream.cuda_stream)
+        self.exchange = exchange
+        self._delta_t = None
+        self._peers = None
+        self._token = None
+
+    def init(self):
+        self.model.init()
+
+    def sweep_part(self, part, n_parts):
+        self.model.sweep_part(part, n_parts)
+
+    def delta_compute(self):
+        self.model.delta_compute()
+
+    def delta_tensor(self):
+        if self._delta_t is None:
+            _, _, view = self.model.device_buffer("delta")
+            self._delta_t = self.torch.as_tensor(view, device=self.torch.device("cuda", self.device))
+        return self._delta_t
+
+    def delta_apply(self):
+        self.model.delta_apply()
+
+    # -- peer-memory exchange -------------------------------------------------------------
+    def ipc_handle(self) -> bytes:
+        import ctypes
+
+        from . import _lib
+        addr, _, _ = self.model.device_buffer("delta")
+        buf = ctypes.create_string_buffer(64)
+        _lib.check(_lib.load().cgs_ipc_export(ctypes.c_void_p(addr), buf))
+        return buf.raw
+
+    def open_peers(self, handles, rank):
+        import ctypes
+
+        from . import _lib
+        addrs = []
+        for r, h in enumerate(handles):
+            if r == rank:
+                addrs.append(self.model.device_buffer("delta")[0])
+            else:
+                p = ctypes.c_void_p()
+                _lib.check(_lib.load().cgs_ipc_open(self.device, ctypes.create_string_buffer(h, 64), ctypes.byref(p)))
+                addrs.append(p.value)
+        self._peers = addrs
+
+    def delta_apply_peers(self):
+        self.model.delta_apply_peers(self._peers)
+
+    def barrier_token(self):
+        if self._token is None:
+            self._token = self.torch.zeros(1, dtype=self.torch.int32, device=self.torch.device("cuda", self.device))
+        return self._token
+
+    # -- results --------------------------------------------------------------------------
+    def loglik_cells(self):
+        return self.model.loglikelihood(1)
+
+    def loglik_regions(self):
+        return self.model.loglikelihood(2)
+
+    def export(self):
+        return self.model.counts()
+
+    def sync(self):
+        self.model.sync()
+
+    def close(self):
+        import ctypes
+
+        from . import _lib
+        if self._peers is not None:
+            own = self.model.device_buffer("delta")[0]
+            for a in self._peers:
+                if a != own:
+                    _lib.load().cgs_ipc_close(self.device, ctypes.c_void_p(a))
+        self.model.close()
+        self.corpus.close()
+
+
+class AdLdaResult:
+    """LDA-protocol result (lda_models.py:292-305, :345-357 read these attributes)."""
+
+
+def fit_adlda(binary_matrix, n_topics, n_iter=150, alpha=0.1, eta=0.01, random_state=555, refresh=None,
+              sync_per_sweep=1, exchange="nccl", shard_factory=None, device=None, on_sweep=None):
+    """Fit ONE model with the cells of ``binary_matrix`` (scipy CSR, regions x cells -- the
+    layout of ``CistopicObject.binary_matrix``) sharded over the ranks of the default process
+    group.  ``alpha`` / ``eta`` are the values the sampler uses.  Returns, on every rank, an object
+    with ``nzw_``, ``ndz_``, ``nz_``, ``topic_word_``, ``doc_topic_``, ``loglikelihoods_``,
+    ``final_loglikelihood_`` (full matrices, gathered)."""
+    import torch.distributed as dist
+
+    distributed = dist.is_available() and dist.is_initialized()
+    world = dist.get_world_size() if distributed else 1
+    rank = dist.get_rank() if distributed else 0
+    if exchange not in ("nccl", "peer"):
+        raise ValueError("exchange must be 'nccl' or 'peer'")
+    if sync_per_sweep < 1:
+        raise ValueError("sync_per_sweep must be >= 1")
+    M = sparse.csr_matrix(binary_matrix)
+    W, D = M.shape
+    if world > D:
+        raise ValueError("more ranks than cells")
+    tokens_per_cell = np.bincount(M.indices, minlength=D)
+    part_ptr, cell_ptr = balanced_cell_partition(tokens_per_cell, world)
+    cb, ce = int(part_ptr[rank]), int(part_ptr[rank + 1])
+    token_offset = int(cell_ptr[cb])
+    if shard_factory is None:
+        if device is None:
+            import os
+            device = int(os.environ.get("LOCAL_RANK", "0"))
+
+        def shard_factory(*a):
+            return GpuShard(*a, device=device, exchange=exchange)
+    shard = shard_factory(M, (cb, ce), token_offset, n_topics, alpha, eta, random_state)
+    use_peer = exchange == "peer" and world > 1 and hasattr(shard, "ipc_handle")
+    try:
+        shard.init()
+        if use_peer:
+            handles = [None] * world
+            dist.all_gather_object(handles, shard.ipc_handle())
+            shard.open_peers(handles, rank)
+
+        def exchange_step():
+            shard.delta_compute()
+            if world == 1:
+                shard.delta_apply()
+            elif use_peer:
+                dist.all_reduce(shard.barrier_token())   # every rank's delta is complete
+                shard.delta_apply_peers()
+                dist.all_reduce(shard.barrier_token())   # every rank has read every delta
+            else:
+                dist.all_reduce(shard.delta_tensor())
+                shard.delta_apply()
+
+        def loglik():
+            cells = shard.loglik_cells()
+            if world > 1:
+                parts = [None] * world
+                dist.all_gather_object(parts, cells)
+                cells = float(np.sum(parts))
+            return cells + shard.loglik_regions()
+
+        exchange_step()  # local init counts -> global n_wk / n_k on every rank
+        res = AdLdaResult()
+        res.loglikelihoods_ = []
+        refresh = n_iter if refresh is None else max(1, int(refresh))
+        for it in range(n_iter):
+            if it % refresh == 0:
+                res.loglikelihoods_.append(loglik())
+            for part in range(sync_per_sweep):
+                shard.sweep_part(part, sync_per_sweep)
+                exchange_step()
+            if on_sweep is not None:
+                on_sweep(it, shard)
+        res.final_loglikelihood_ = loglik()
+        nzw, ndz_local, nz = shard.export()
+        if world > 1:
+            shards = [None] * world
+            dist.all_gather_object(shards, ndz_local)
+            ndz = np.concatenate(shards, axis=0)
+        else:
+            ndz = ndz_local
+        res.nzw_, res.ndz_, res.nz_ = nzw, ndz, nz
+        res.components_ = (nzw + eta) / (nz[:, None] + eta * W)
+        res.topic_word_ = res.components_
+        nd = tokens_per_cell.astype(np.float64)
+        res.doc_topic_ = (ndz + alpha) / (nd[:, None] + alpha * n_topics)
+        res.part_ptr_ = part_ptr
+        return res
+    finally:
+        shard.close()

@@ -65,6 +65,7 @@ struct cgs_model {
     int *d_flag = nullptr;
     int64_t launches = 0;
     int64_t sweeps = 0;
+    int64_t work_slot = 0;
     int tpt = 1, ch = 1, threads = 128;
     double nk_divisor = 16.0;
     int max_blocks = 0;   // user override, 0 = automatic
@@ -536,9 +537,21 @@ static int dispatch_sweep(cgs_model *m, const SweepParams &p) {
 
 extern "C" {
 
+static int sweep_impl(cgs_model *m, int32_t n_sweeps, int32_t part, int32_t n_parts);
+
 int cgs_model_sweep(cgs_model *m, int32_t n_sweeps) {
     if (!m) CGS_FAIL("NULL model");
     if (n_sweeps < 0) CGS_FAIL("n_sweeps < 0");
+    return sweep_impl(m, n_sweeps, 0, 1);
+}
+
+int cgs_model_sweep_part(cgs_model *m, int32_t part, int32_t n_parts) {
+    if (!m) CGS_FAIL("NULL model");
+    if (n_parts < 1 || part < 0 || part >= n_parts) CGS_FAIL("bad part / n_parts");
+    return sweep_impl(m, 1, part, n_parts);
+}
+
+static int sweep_impl(cgs_model *m, int32_t n_sweeps, int32_t part, int32_t n_parts) {
     cgs_corpus *c = m->corpus;
     DeviceGuard g(c->device);
     SweepParams p;
@@ -570,17 +583,20 @@ int cgs_model_sweep(cgs_model *m, int32_t n_sweeps) {
         const double r = (double)c->n_tokens / (active_warps * tokens_per_step * m->nk_divisor);
         p.refresh_every = (int32_t)std::max(1.0, std::min(1024.0, r));
     }
+    p.part = part;
+    p.n_parts = n_parts;
     for (int32_t s = 0; s < n_sweeps; ++s) {
-        const int slot = (int)(m->sweeps % kWorkSlots);
+        const int slot = (int)(m->work_slot % kWorkSlots);
         if (slot == 0) {
-            // a fresh bank of queue counters (stream-ordered after every sweep that used the last one)
+            // a fresh bank of queue counters (stream-ordered after every launch that used the last one)
             CGS_CUDA(cudaMemsetAsync(m->d_work, 0, sizeof(int32_t) * kWorkSlots, m->stream));
         }
+        m->work_slot += 1;
         p.work_counter = m->d_work + slot;
-        p.sweep = (uint32_t)m->sweeps;
+        p.sweep = (uint32_t)m->sweeps;  // all parts of one sweep share the Philox sweep index
         CGS_TRY(dispatch_sweep(m, p));
         m->launches += 1;
-        m->sweeps += 1;
+        if (part == n_parts - 1) m->sweeps += 1;
     }
     return 0;
 }
@@ -751,8 +767,14 @@ int cgs_model_export_frames(cgs_model *m, double *topic_region, double *cell_top
 // ---- AD-LDA exchange ---------------------------------------------------------------------------
 static int ensure_exchange_buffers(cgs_model *m) {
     const size_t n = (size_t)m->corpus->n_regions * (size_t)m->Kp;
-    if (!m->d_snap) CGS_TRY(dmalloc(&m->d_snap, n));
-    if (!m->d_delta) CGS_TRY(dmalloc(&m->d_delta, n));
+    if (!m->d_snap) {
+        CGS_TRY(dmalloc(&m->d_snap, n));
+        CGS_CUDA(cudaMemsetAsync(m->d_snap, 0, n * sizeof(int32_t), m->stream));
+    }
+    if (!m->d_delta) {
+        CGS_TRY(dmalloc(&m->d_delta, n));
+        CGS_CUDA(cudaMemsetAsync(m->d_delta, 0, n * sizeof(int32_t), m->stream));
+    }
     return 0;
 }
 
@@ -833,6 +855,34 @@ int cgs_model_delta_apply_peers(cgs_model *m, void *const *peer_delta, int32_t n
         peers.p[r] = (const int4 *)peer_delta[r];
     }
     return delta_apply_common(m, peers, n_ranks);
+}
+
+// ---- CUDA IPC helpers for the peer-memory exchange (one process per GPU) -------------------------
+int cgs_ipc_export(void *device_ptr, void *handle_out_64_bytes) {
+    if (!device_ptr || !handle_out_64_bytes) CGS_FAIL("NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaIpcMemHandle_t h;
+    CGS_CUDA(cudaIpcGetMemHandle(&h, device_ptr));
+    memcpy(handle_out_64_bytes, &h, sizeof h);
+    return 0;
+}
+
+int cgs_ipc_open(int device, const void *handle_64_bytes, void **device_ptr) {
+    if (!handle_64_bytes || !device_ptr) CGS_FAIL("NULL argument");
+    DeviceGuard g(device);
+    if (!g.ok) CGS_FAIL("cannot select CUDA device");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle_64_bytes, sizeof h);
+    CGS_CUDA(cudaIpcOpenMemHandle(device_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+
+int cgs_ipc_close(int device, void *device_ptr) {
+    if (!device_ptr) return 0;
+    DeviceGuard g(device);
+    if (!g.ok) CGS_FAIL("cannot select CUDA device");
+    CGS_CUDA(cudaIpcCloseMemHandle(device_ptr));
+    return 0;
 }
 
 // ---- imputation --------------------------------------------------------------------------------

@@ -50,6 +50,8 @@ struct SweepParams {
     uint32_t seed_hi;
     uint32_t sweep;
     int32_t refresh_every;  // a warp re-synchronises the topic totals every this many steps
+    int32_t part;           // this launch handles queue slots part, part + n_parts, ... (sub-sweep)
+    int32_t n_parts;
     int64_t token_offset;
 };
 
@@ -111,7 +113,7 @@ __global__ void __launch_bounds__(kSweepThreads, (CH <= 2 ? 4 : 3)) sweep_kernel
     for (;;) {
         if (tid == 0) cell_slot_s = atomicAdd(p.work_counter, 1);
         __syncthreads();
-        const int slot = cell_slot_s;
+        const int slot = cell_slot_s * p.n_parts + p.part;
         if (slot >= p.n_cells) break;
         const int cell = p.cell_order[slot];
         const int64_t t0 = p.cell_ptr[cell], t1 = p.cell_ptr[cell + 1];

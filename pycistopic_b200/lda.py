@@ -169,6 +169,9 @@ class DeviceModel:
     def sweep(self, n_sweeps: int = 1):
         check(_lib.load().cgs_model_sweep(self._h, int(n_sweeps)))
 
+    def sweep_part(self, part: int, n_parts: int):
+        check(_lib.load().cgs_model_sweep_part(self._h, int(part), int(n_parts)))
+
     def loglikelihood(self, partial: int = 0) -> float:
         ll = ctypes.c_double()
         check(_lib.load().cgs_model_loglik(self._h, partial, ctypes.byref(ll)))
