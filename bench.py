@@ -240,6 +240,83 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------
+# AD-LDA leg (BASELINE.json configs[2]): ONE 60-topic model on the C3 shape, cells sharded over the
+# ranks, n_wk deltas exchanged once per sweep.  Strong scaling: the matrix is fixed, N ranks split it.
+# ------------------------------------------------------------------------------------------------
+ADLDA_SHAPE, ADLDA_K = "C3", 60
+
+
+def run_adlda_leg(args, dev, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    from pycistopic_b200 import Corpus
+    from pycistopic_b200.adlda import Exchanger, GpuShard, balanced_cell_partition
+    from pycistopic_b200.synth import SHAPES, planted_topic_tokens
+
+    D, W, density = SHAPES[ADLDA_SHAPE]
+    cell, region = planted_topic_tokens(D, W, density, seed=DATA_SEED, device=dev)
+    cnt = torch.bincount(cell, minlength=D)
+    del cell
+    part_ptr, cell_ptr_h = balanced_cell_partition(cnt.cpu().numpy(), world)
+    cb, ce = int(part_ptr[rank]), int(part_ptr[rank + 1])
+    t0, t1 = int(cell_ptr_h[cb]), int(cell_ptr_h[ce])
+    N_total = int(cell_ptr_h[-1])
+    tok = region[t0:t1].to(torch.int32).contiguous()
+    del region
+    cp = torch.tensor(cell_ptr_h[cb:ce + 1] - t0, dtype=torch.int64, device=dev)
+    torch.cuda.empty_cache()
+    out = {}
+    for exchange in (["nccl", "peer"] if world > 1 else ["nccl"]):
+        corpus = Corpus.from_device_tokens(cp.data_ptr(), tok.data_ptr(), ce - cb, W, t1 - t0, device=local_rank,
+                                           token_offset=t0, keepalive=(cp, tok))
+        shard = GpuShard(None, (cb, ce), t0, ADLDA_K, ALPHA / ADLDA_K, ETA, MODEL_SEED, device=local_rank,
+                         exchange=exchange, corpus=corpus)
+        shard.init()
+        ex = Exchanger(shard, exchange)
+        ex.step()
+        stream = shard.stream
+
+        def sweep():
+            shard.sweep_part(0, 1)
+            ex.step()
+
+        for _ in range(5 + max(args.warmup, 3)):
+            sweep()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        n = max(3, args.steps)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+        e0.record(stream)
+        for i in range(n):
+            ev[i][0].record(stream)
+            shard.sweep_part(0, 1)
+            ev[i][1].record(stream)
+            ex.step()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        sample_ms = statistics.mean(a.elapsed_time(b) for a, b in ev)
+        if world > 1:
+            t = torch.tensor([ms, sample_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms, sample_ms = float(t[0].item()), float(t[1].item())
+        ll = shard.loglik_cells()
+        out[exchange] = {"tokens_per_s": N_total / (ms * 1e-3), "ms_per_sweep": ms, "ms_sampling": sample_ms,
+                         "ms_exchange": ms - sample_ms}
+        shard.close()
+        _ = ll
+    peak = 6544.3
+    best = max(out.values(), key=lambda v: v["tokens_per_s"])
+    return {"workload": f"{ADLDA_SHAPE}: {D} cells x {W} regions, {N_total} tokens, one K={ADLDA_K} model, cells sharded "
+                        f"over {world} GPU(s), one n_wk exchange per sweep ({4 * W * ((ADLDA_K + 3) // 4 * 4) / 1e6:.0f} MB)",
+            "scaling": "strong", "value": best["tokens_per_s"], "unit": "tokens/s", "per_exchange": out,
+            "frac_of_hbm_roofline_per_gpu": b_tok(ADLDA_K) * best["tokens_per_s"] / world / 1e9 / peak}
+
+
+# ------------------------------------------------------------------------------------------------
 # CUDA arm
 # ------------------------------------------------------------------------------------------------
 def run_cuda(args):
@@ -420,6 +497,19 @@ def run_cuda(args):
                                   f"({len(WS)} of {N} tokens), oracle/cgs_oracle.c, one thread per model",
                         "cpu": cpu_model_name(), "host_cores": os.cpu_count(), "seconds": dt}
 
+    # ---- AD-LDA leg (C3, one model sharded by cells) --------------------------------------------
+    for m in models:
+        m.close()
+    models = []
+    corpus.close()
+    corpus._keepalive = None
+    del cell_ptr, tok
+    torch.cuda.empty_cache()
+    adlda = None
+    if not args.no_adlda:
+        torch.cuda.set_stream(torch.cuda.default_stream(dev))
+        adlda = run_adlda_leg(args, dev, rank, world, local_rank)
+
     if rank == 0:
         line = {
             "metric": "gibbs_tokens_per_s_per_sweep", "value": value, "unit": "tokens/s", "n_gpus": world,
@@ -436,12 +526,9 @@ def run_cuda(args):
                        "l2": "inputs larger than L2: every model streams 6 B/token of tokens+topics "
                              f"({6 * N / 1e6:.0f} MB) per sweep and the step cycles through {len(my_topics)} models"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clock_info,
+            "clocks": clock_info, "adlda": adlda,
         }
         print(json.dumps(line), flush=True)
-    for m in models:
-        m.close()
-    corpus.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -457,6 +544,7 @@ def main():
     ap.add_argument("--cpu-sample-cells", type=int, default=500)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-adlda", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

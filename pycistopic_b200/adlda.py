@@ -42,7 +42,8 @@ def balanced_cell_partition(tokens_per_cell, n_parts):
 class GpuShard:
     """Shard backend on one GPU: a :class:`DeviceModel` over this rank's cells."""
 
-    def __init__(self, binary_matrix, cell_range, token_offset, n_topics, alpha, eta, seed, device, exchange):
+    def __init__(self, binary_matrix, cell_range, token_offset, n_topics, alpha, eta, seed, device, exchange,
+                 corpus=None):
         import torch
 
         from .lda import Corpus, DeviceModel
@@ -51,8 +52,10 @@ class GpuShard:
         torch.cuda.set_device(device)
         self.stream = torch.cuda.Stream(device=device)
         torch.cuda.set_stream(self.stream)
-        self.corpus = Corpus.from_regions_by_cells(binary_matrix, device=device, cell_range=cell_range)
-        self.corpus.set_token_offset(token_offset)
+        if corpus is None:
+            corpus = Corpus.from_regions_by_cells(binary_matrix, device=device, cell_range=cell_range)
+            corpus.set_token_offset(token_offset)
+        self.corpus = corpus
         self.model = DeviceModel(self.corpus, n_topics, alpha, eta, seed=seed, stream=self.stream.cuda_stream)
         self.exchange = exchange
         self._delta_t = None
@@ -135,6 +138,36 @@ class GpuShard:
         self.corpus.close()
 
 
+class Exchanger:
+    """The per-sweep n_wk exchange of one shard (see the module docstring)."""
+
+    def __init__(self, shard, exchange="nccl"):
+        import torch.distributed as dist
+        self.dist = dist
+        self.shard = shard
+        distributed = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size() if distributed else 1
+        self.rank = dist.get_rank() if distributed else 0
+        self.use_peer = exchange == "peer" and self.world > 1 and hasattr(shard, "ipc_handle")
+        if self.use_peer:
+            handles = [None] * self.world
+            dist.all_gather_object(handles, shard.ipc_handle())
+            shard.open_peers(handles, self.rank)
+
+    def step(self):
+        shard, dist = self.shard, self.dist
+        shard.delta_compute()
+        if self.world == 1:
+            shard.delta_apply()
+        elif self.use_peer:
+            dist.all_reduce(shard.barrier_token())   # every rank's delta is complete
+            shard.delta_apply_peers()
+            dist.all_reduce(shard.barrier_token())   # every rank has read every delta
+        else:
+            dist.all_reduce(shard.delta_tensor())
+            shard.delta_apply()
+
+
 class AdLdaResult:
     """LDA-protocol result (lda_models.py:292-305, :345-357 read these attributes)."""
 
@@ -171,25 +204,10 @@ def fit_adlda(binary_matrix, n_topics, n_iter=150, alpha=0.1, eta=0.01, random_s
         def shard_factory(*a):
             return GpuShard(*a, device=device, exchange=exchange)
     shard = shard_factory(M, (cb, ce), token_offset, n_topics, alpha, eta, random_state)
-    use_peer = exchange == "peer" and world > 1 and hasattr(shard, "ipc_handle")
     try:
         shard.init()
-        if use_peer:
-            handles = [None] * world
-            dist.all_gather_object(handles, shard.ipc_handle())
-            shard.open_peers(handles, rank)
-
-        def exchange_step():
-            shard.delta_compute()
-            if world == 1:
-                shard.delta_apply()
-            elif use_peer:
-                dist.all_reduce(shard.barrier_token())   # every rank's delta is complete
-                shard.delta_apply_peers()
-                dist.all_reduce(shard.barrier_token())   # every rank has read every delta
-            else:
-                dist.all_reduce(shard.delta_tensor())
-                shard.delta_apply()
+        exchanger = Exchanger(shard, exchange)
+        exchange_step = exchanger.step
 
         def loglik():
             cells = shard.loglik_cells()
