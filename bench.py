@@ -419,7 +419,8 @@ def run_cuda(args):
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": f"sweep_kernel (K={k_dom})", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch (ncu --set full, "
+                "profiles/sweep_traffic.json)", "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": b_tok(k_dom) * N, "ms_per_launch": per_model_ms[k_dom],
                 "per_model": {str(k): {"ms": round(v, 4), "gtok_s": round(N / v / 1e6, 3),
                                        "frac": round(b_tok(k) * N / (v * 1e-3) / 1e9 / peak, 4)}
