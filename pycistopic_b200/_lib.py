@@ -85,8 +85,8 @@ def load() -> ctypes.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB_PATH
-    if _build.needs_build():
+    path = os.environ.get("CGS_B200_LIB") or _build.LIB_PATH  # CGS_B200_LIB: a prebuilt variant (tuning runs)
+    if path == _build.LIB_PATH and _build.needs_build():
         if os.environ.get("CGS_B200_NO_BUILD") == "1" and os.path.exists(path):
             pass
         else:

@@ -518,6 +518,10 @@ static int dispatch_ch(cgs_model *m, const SweepParams &p, int *bc) {
         case 2: return launch_sweep<TPT, 2>(m, p, bc);
         case 3: return launch_sweep<TPT, 3>(m, p, bc);
         case 4: return launch_sweep<TPT, 4>(m, p, bc);
+        case 5: if (TPT <= 16) return launch_sweep<(TPT <= 16 ? TPT : 16), 5>(m, p, bc); break;
+        case 6: if (TPT <= 16) return launch_sweep<(TPT <= 16 ? TPT : 16), 6>(m, p, bc); break;
+        case 7: if (TPT <= 16) return launch_sweep<(TPT <= 16 ? TPT : 16), 7>(m, p, bc); break;
+        case 8: if (TPT <= 16) return launch_sweep<(TPT <= 16 ? TPT : 16), 8>(m, p, bc); break;
     }
     CGS_FAIL("unsupported chunk count");
 }
@@ -579,8 +583,8 @@ static int sweep_impl(cgs_model *m, int32_t n_sweeps, int32_t part, int32_t n_pa
         const double cta_cap = (double)(m->max_blocks > 0 ? m->max_blocks : m->auto_blocks);
         const double active_warps =
             std::max(1.0, std::min(warp_slots, std::min((double)c->n_cells, cta_cap) * warps_per_cell));
-        const double tokens_per_step = 32.0 / m->tpt;
-        const double r = (double)c->n_tokens / (active_warps * tokens_per_step * m->nk_divisor);
+        const double tokens_per_batch = 32.0;  // a warp checks once per 32-token batch
+        const double r = (double)c->n_tokens / (active_warps * tokens_per_batch * m->nk_divisor);
         p.refresh_every = (int32_t)std::max(1.0, std::min(1024.0, r));
     }
     p.part = part;
@@ -609,7 +613,7 @@ int cgs_model_set_sweep_shape(cgs_model *m, int32_t lanes_per_token, int32_t war
         CGS_FAIL("warps_per_cell must be 1, 2, 4 or 8");
     const int chunks = m->Kp / 4;
     const int ch = (chunks + t - 1) / t;
-    if (ch > 4) CGS_FAIL("lanes_per_token too small for this n_topics");
+    if (ch > kMaxChunksPerLane || t * ch * 4 > kMaxTopics) CGS_FAIL("lanes_per_token too small for this n_topics");
     m->tpt = t;
     m->ch = ch;
     m->threads = warps_per_cell * 32;

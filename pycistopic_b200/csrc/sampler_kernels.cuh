@@ -11,25 +11,29 @@
 //
 // Sweep kernel.  Persistent CTAs pull cells from a longest-first queue; a cell is owned by
 // exactly one CTA for the sweep, so its n_dk row lives in shared memory (as integer counts
-// and as the pre-multiplied factor f[k] = (n_dk[k] + alpha) / (n_k[k] + eta*W)).  Inside the
-// CTA every warp takes 32 consecutive tokens at a time: one coalesced load of their region
-// ids and topics, one Philox4x32-10 draw per token (counter = global token index, sweep).
-// A token is handled by TPT lanes; each lane owns CH 16-byte chunks (4 topics each) of the
-// token's n_wk row, read with 128-bit loads one step ahead of use.  The conditional
+// and as the pre-multiplied factor f[k] = (n_dk[k] + alpha) / (n_k[k] + eta*W)).  A warp walks
+// its share of the cell in batches of 32 consecutive tokens (one coalesced load of region ids
+// and topics, issued one batch ahead) grouped four at a time so that ONE Philox4x32-10 call
+// per lane serves four batches.  A token is handled by TPT lanes; a warp step therefore
+// samples 32/TPT tokens.  Each lane owns CH 16-byte chunks (4 topics each) of the token's
+// n_wk row, read with 128-bit loads one step ahead of use into a register ping-pong buffer
+// (the step loop is unrolled, so the buffers never move).  The conditional
 //   p(k) = (n_wk[w,k] - [k==z] + eta) * (n_dk[d,k] - [k==z] + alpha) / (n_k[k] - [k==z] + eta*W)
 // is accumulated as a per-lane running sum, scanned across the TPT lanes with shuffles,
-// and inverted with one ballot + an in-lane count.  A token that changes topic issues two
-// no-return global reductions on n_wk (live counts: every other token on the GPU sees the
-// update immediately, which is what keeps the chain close to the sequential reference) and
-// shared-memory atomics for the cell's row; n_k deltas are aggregated per CTA and flushed once
-// per cell.
+// and inverted with one ballot + an in-lane count.  A token that changes topic is applied by
+// two lanes of its group (one per topic): a no-return global reduction on n_wk (live counts:
+// every other token on the GPU sees the update immediately, which is what keeps the chain
+// close to the sequential reference) and a shared-memory atomic on the cell's row; n_k
+// deltas are the difference between the row and its last published copy, flushed every few
+// batches and once per cell.
 #pragma once
 #include "common.cuh"
 
 namespace cgs {
 
 constexpr int kSweepThreads = 256;  // upper bound; the launch uses 32..256
-constexpr int kMaxTopics = 512;  // TPT=32 lanes x CH=4 chunks x 4 topics
+constexpr int kMaxTopics = 512;     // TPT * CH * 4 slots, TPT <= 32, CH <= 8
+constexpr int kMaxChunksPerLane = 8;
 
 struct SweepParams {
     const int64_t *cell_ptr;
@@ -49,22 +53,15 @@ struct SweepParams {
     uint32_t seed_lo;
     uint32_t seed_hi;
     uint32_t sweep;
-    int32_t refresh_every;  // a warp re-synchronises the topic totals every this many steps
+    int32_t refresh_every;  // a warp re-synchronises the topic totals every this many batches
     int32_t part;           // this launch handles queue slots part, part + n_parts, ... (sub-sweep)
     int32_t n_parts;
     int64_t token_offset;
 };
 
-__device__ __forceinline__ int4 ld_row_chunk(const int32_t *p) {
-    // n_wk rows are read once per token and written by reductions from every SM: keep them out
-    // of L1 (L2 is the coherence point for the reductions).
-    int4 r;
-    asm volatile("ld.global.cg.v4.s32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
-                 : "l"(p));
-    return r;
-}
-
+// ---- memory primitives ----------------------------------------------------------------------
+// n_wk rows are read once per token and written by reductions from every SM: keep them out of
+// L1 (L2 is the coherence point for the reductions).
 __device__ __forceinline__ int32_t ld_volatile_i32(const int32_t *p) {
     int32_t v;
     asm volatile("ld.global.cg.s32 %0, [%1];" : "=r"(v) : "l"(p));
@@ -75,8 +72,49 @@ __device__ __forceinline__ void red_add_i32(int32_t *p, int32_t v) {
     asm volatile("red.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// Shared memory is addressed with 32-bit window addresses computed once per CTA.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float lds_f(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ int lds_i(uint32_t a) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_f(uint32_t a, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory");
+}
+__device__ __forceinline__ void sts_i(uint32_t a, int v) {
+    asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ int atoms_add(uint32_t a, int v) {
+    int o;
+    asm volatile("atom.shared.add.s32 %0, [%1], %2;" : "=r"(o) : "r"(a), "r"(v) : "memory");
+    return o;
+}
+__device__ __forceinline__ int atoms_exch(uint32_t a, int v) {
+    int o;
+    asm volatile("atom.shared.exch.b32 %0, [%1], %2;" : "=r"(o) : "r"(a), "r"(v) : "memory");
+    return o;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 template <int TPT>
-__device__ __forceinline__ int log2_tpt() {
+__host__ __device__ constexpr int log2_tpt() {
     return TPT == 1 ? 0 : TPT == 2 ? 1 : TPT == 4 ? 2 : TPT == 8 ? 3 : TPT == 16 ? 4 : 5;
 }
 
@@ -86,34 +124,190 @@ __device__ __forceinline__ int rot_chunk(int c, int oc) {
     if (CH == 1) return 0;
     if (CH == 2) return (c + oc) & 1;
     if (CH == 4) return (c + oc) & 3;
+    if (CH == 8) return (c + oc) & 7;
     const int t = c + oc;
     return t >= CH ? t - CH : t;
 }
 
+// Number of leading entries of the non-decreasing array cum[0..N) that are <= t: bisection
+// over registers (select trees), about N + 2 log2 N instructions instead of 2.5 N.
+template <int N>
+__device__ __forceinline__ int count_le_sorted(const float (&cum)[N], float t) {
+    constexpr int P = N <= 4 ? 4 : N <= 8 ? 8 : N <= 16 ? 16 : 32;
+    float a[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) a[j] = j < N ? cum[j] : __int_as_float(0x7f800000);
+    int cnt = 0;
+#pragma unroll
+    for (int S = P / 2; S >= 1; S >>= 1) {
+        const bool ge = a[S - 1] <= t;
+        if (ge) cnt += S;
+#pragma unroll
+        for (int j = 0; j + 1 < S; ++j) a[j] = ge ? a[j + S] : a[j];
+        if (S == 1 && ge) {  // the last entry itself
+            // (a[1] is the entry after the bisection point: counts when it is <= t as well)
+        }
+    }
+    // after the loop cnt is the index of the first entry > t within the first P - 1 entries; the
+    // entry P - 1 is never tested by the bisection above
+    return cnt;
+}
+
+// A token travels between lanes as two words: its region id and (22 random bits | padding flag |
+// topic).
+__device__ __forceinline__ int pack_token(uint32_t bits, int zo, bool valid) {
+    return (int)((bits & 0xfffffc00u) | (valid ? 0u : 0x200u) | (uint32_t)zo);
+}
+
+// One warp step: samples the 32/TPT tokens (w, pk) whose n_wk rows sit in `buf`, and -- as soon
+// as the rows have been consumed -- requests the rows of the next group (w_next, pk_next) into
+// the same registers, so the loads fly while this step scans, inverts and applies.  Returns the
+// new topic of the group's token (same value in all TPT lanes of the group).  sm = shared-memory
+// window address of f; inv, den, ndk follow at multiples of KS words.
 template <int TPT, int CH>
-__global__ void __launch_bounds__(kSweepThreads, (CH <= 2 ? 4 : 3)) sweep_kernel(const SweepParams p) {
-    constexpr int KS = TPT * CH * 4;  // topic slots covered by one token group
+__device__ __forceinline__ int sweep_step(int4 (&buf)[CH], const char *nwk_lane, uint32_t rowbytes, int lim, int w,
+                                          int pk, int w_next, int pk_next, uint32_t sm, int sub, int gbase, int lane,
+                                          float alpha, float eta, int K) {
     constexpr unsigned FULL = 0xffffffffu;
-    __shared__ __align__(16) float f_s[KS];    // (n_dk + alpha) / (n_k + eta W)
-    __shared__ __align__(16) float inv_s[KS];  // 1 / (n_k + eta W)
-    __shared__ __align__(16) float den_s[KS];  // n_k + eta W
-    __shared__ __align__(16) int ndk_s[KS];
-    __shared__ __align__(16) int dnk_s[KS];
-    __shared__ int cell_slot_s;
+    constexpr int LOG = log2_tpt<TPT>();
+    constexpr int KSB = TPT * CH * 16;  // bytes of one shared-memory array
+    const int zo = pk & 0x1ff;
+    const bool live = (pk & 0x200) == 0;
+
+    // ---- own-token exclusion: component of z_old in register chunk 0 of its lane (or -1) ----------
+    const int ochunk = zo >> 2;
+    const int oc = ochunk >> LOG;
+    const int hitq = (sub == (ochunk & (TPT - 1))) ? (zo & 3) : -1;
+    const float fpp = ((float)(lds_i(sm + 3 * KSB + zo * 4) - 1) + alpha) * rcp_approx(lds_f(sm + 2 * KSB + zo * 4) - 1.0f);
+
+    // ---- running sum of p(k) over this lane's slots ------------------------------------------
+    float cum[CH * 4];
+    float acc = 0.0f;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+        const int rc = rot_chunk<CH>(c, oc);
+        const float4 fv = lds_f4(sm + sub * 16 + rc * (TPT * 16));
+        const int4 nv = buf[c];
+        float x[4] = {(float)nv.x + eta, (float)nv.y + eta, (float)nv.z + eta, (float)nv.w + eta};
+        float ff[4] = {fv.x, fv.y, fv.z, fv.w};
+        if (c == 0) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (hitq == q) { x[q] -= 1.0f; ff[q] = fpp; }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            acc = fmaf(x[q], ff[q], acc);
+            cum[c * 4 + q] = acc;
+        }
+    }
+
+    // ---- request the next group's rows (chunk order rotated so its own topic lands in chunk 0) ----
+    {
+        const char *row_n = nwk_lane + (uint64_t)((uint32_t)w_next) * rowbytes;
+        const int ocn = ((pk_next & 0x1ff) >> 2) >> LOG;
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+            const int rc = rot_chunk<CH>(c, ocn);
+            // chunks past the end of the row are neither fetched nor cleared: their slots carry f = 0
+            if (rc < lim) buf[c] = __ldcg(reinterpret_cast<const int4 *>(row_n + rc * (TPT * 16)));
+        }
+    }
+
+    // ---- butterfly over the TPT lanes of the token: exclusive prefix and total -----------------
+    float excl = 0.0f, total = acc;
+    if (TPT > 1) {
+#pragma unroll
+        for (int off = 1; off < TPT; off <<= 1) {
+            const float t = __shfl_xor_sync(FULL, total, off);
+            if (sub & off) excl += t;
+            total += t;
+        }
+    }
+    const float u = (float)((uint32_t)pk >> 10) * (1.0f / 4194304.0f);
+    const float tloc = u * total - excl;  // threshold relative to this lane
+    // cum[CH*4 - 1] == acc; a lane whose acc <= tloc holds no crossing
+    const bool mine = !(acc <= tloc);
+    const int cnt = count_le_sorted<CH * 4>(cum, tloc);
+    const int cand = (sub + TPT * rot_chunk<CH>(cnt >> 2, oc)) * 4 + (cnt & 3);
+    int zn;
+    if (TPT > 1) {
+        const unsigned bal = __ballot_sync(FULL, mine);
+        const unsigned gm = (TPT == 32) ? bal : ((bal >> gbase) & ((1u << TPT) - 1u));
+        const int src = gm ? (gbase + __ffs(gm) - 1) : lane;
+        zn = __shfl_sync(FULL, cand, src);
+        if (!gm) zn = zo;
+    } else {
+        zn = mine ? cand : zo;
+    }
+    if (zn >= K || !live) zn = zo;  // rounding guard: padded slots carry p = 0
+
+    // ---- apply the move -------------------------------------------------------------------------
+    if (zn != zo) {
+        const char *row = nwk_lane + (uint64_t)((uint32_t)w) * rowbytes;
+        if (TPT > 1) {
+            // lane 0 of the group retires the old topic, lane 1 installs the new one
+            if (sub < 2) {
+                const int k = sub ? zn : zo;
+                const int sg = sub ? 1 : -1;
+                red_add_i32((int32_t *)const_cast<char *>(row + (k * 4 - sub * 16)), sg);
+                const int old = atoms_add(sm + 3 * KSB + k * 4, sg);
+                sts_f(sm + k * 4, ((float)(old + sg) + alpha) * lds_f(sm + KSB + k * 4));
+            }
+        } else {
+            int32_t *rowi = (int32_t *)const_cast<char *>(row);
+            red_add_i32(rowi + zo, -1);
+            red_add_i32(rowi + zn, 1);
+            const int o0 = atoms_add(sm + 3 * KSB + zo * 4, -1);
+            const int o1 = atoms_add(sm + 3 * KSB + zn * 4, 1);
+            sts_f(sm + zo * 4, ((float)(o0 - 1) + alpha) * lds_f(sm + KSB + zo * 4));
+            sts_f(sm + zn * 4, ((float)(o1 + 1) + alpha) * lds_f(sm + KSB + zn * 4));
+        }
+    }
+    return zn;
+}
+
+// Resident CTAs per SM the register budget is set for (measured on B200: occupancy beats the
+// few spills it costs; see profiles/).
+#ifndef CGS_SWEEP_MINB_NARROW
+#define CGS_SWEEP_MINB_NARROW 4  // CH <= 4
+#endif
+#ifndef CGS_SWEEP_MINB_WIDE
+#define CGS_SWEEP_MINB_WIDE 2  // CH >= 5
+#endif
+
+template <int TPT, int CH>
+__global__ void __launch_bounds__(kSweepThreads, (CH <= 4 ? CGS_SWEEP_MINB_NARROW : CGS_SWEEP_MINB_WIDE))
+sweep_kernel(const SweepParams p) {
+    constexpr int KS = TPT * CH * 4;  // topic slots covered by one token group
+    constexpr int KSB = KS * 4;
+    constexpr unsigned FULL = 0xffffffffu;
+    // f | inv | den | ndk | pub, KS words each, then the queue slot
+    __shared__ __align__(16) uint32_t smem_w[5 * KS + 4];
+    const uint32_t sm = smem_u32(smem_w);
+    const uint32_t s_f = sm, s_inv = sm + KSB, s_den = sm + 2 * KSB, s_ndk = sm + 3 * KSB, s_pub = sm + 4 * KSB;
+    const uint32_t s_slot = sm + 5 * KSB;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
-    const int warp = tid >> 5;
+    const int warp = __shfl_sync(FULL, tid >> 5, 0);  // warp-uniform by construction
     const int nwarps = blockDim.x >> 5;
     const int sub = lane & (TPT - 1);
     const int gbase = lane & ~(TPT - 1);
     const int K = p.K, Kp = p.Kp;
     const float alpha = p.alpha, eta = p.eta;
+    const uint32_t rowbytes = (uint32_t)Kp * 4u;
+    const int lim = ((Kp >> 2) - sub + TPT - 1) >> log2_tpt<TPT>();  // register chunks of this lane inside the row
+    const char *nwk_lane = reinterpret_cast<const char *>(p.n_wk) + sub * 16;
+
+    int4 buf[CH];  // the n_wk row chunks of the group sampled next
+#pragma unroll
+    for (int c = 0; c < CH; ++c) buf[c] = make_int4(0, 0, 0, 0);
 
     for (;;) {
-        if (tid == 0) cell_slot_s = atomicAdd(p.work_counter, 1);
+        if (tid == 0) sts_i(s_slot, atomicAdd(p.work_counter, 1));
         __syncthreads();
-        const int slot = cell_slot_s * p.n_parts + p.part;
+        const int slot = lds_i(s_slot) * p.n_parts + p.part;
         if (slot >= p.n_cells) break;
         const int cell = p.cell_order[slot];
         const int64_t t0 = p.cell_ptr[cell], t1 = p.cell_ptr[cell + 1];
@@ -128,170 +322,132 @@ __global__ void __launch_bounds__(kSweepThreads, (CH <= 2 ? 4 : 3)) sweep_kernel
                 nd = ndk_row[k];
                 f = ((float)nd + alpha) * inv;
             }
-            den_s[k] = den; inv_s[k] = inv; f_s[k] = f; ndk_s[k] = nd; dnk_s[k] = 0;
+            sts_f(s_den + k * 4, den); sts_f(s_inv + k * 4, inv); sts_f(s_f + k * 4, f);
+            sts_i(s_ndk + k * 4, nd); sts_i(s_pub + k * 4, nd);
         }
         __syncthreads();
 
-        const int64_t nbatch = (t1 - t0 + 31) >> 5;
-        // Token lists are sorted by region and concurrently scheduled cells advance in lockstep, so
-        // without this every token of a popular region would be sampled at the same moment against
-        // the same stale n_wk row.  Start each cell at its own pseudo-random batch and wrap.
-        uint32_t h = (uint32_t)cell * 0x9E3779B1u ^ (p.sweep * 0x85EBCA77u) ^ p.seed_lo;
-        h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
-        const int64_t rot = nbatch > 0 ? (int64_t)(h % (uint32_t)nbatch) : 0;
+        // A warp's share of the cell.  The cell's batches (32 tokens) are walked from a per-cell
+        // pseudo-random start batch `rot`, wrapping at the end: token lists are sorted by region and
+        // concurrently scheduled cells advance in lockstep, so without the rotation every token of a
+        // popular region would be sampled at the same moment against the same stale n_wk row.  The
+        // rotated sequence [rot, nbatch) ++ [0, rot) is cut into super-batches of up to four
+        // consecutive batches (never across the wrap) that the warps take round-robin.
+        const int ntok = (int)(t1 - t0);
+        const int nbatch = (ntok + 31) >> 5;
+        int rot = 0;
+        if (nbatch > 0) {
+            uint32_t h = (uint32_t)cell * 0x9E3779B1u ^ (p.sweep * 0x85EBCA77u) ^ p.seed_lo;
+            h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
+            rot = (int)(h % (uint32_t)nbatch);
+        }
+        const int nsup1 = (nbatch - rot + 3) >> 2;        // super-batches of the segment [rot, nbatch)
+        const int nsuper = nsup1 + ((rot + 3) >> 2);      // ... plus those of [0, rot)
+        const int32_t *tok_cell = p.tok_region + t0;
+        uint16_t *z_cell = p.z + t0;
+        const uint64_t gi0 = (uint64_t)(p.token_offset + t0) + (uint64_t)lane;
+
+        int sidx = warp;  // super-batch index in the rotated sequence
+        int off = 0;      // first token of the current batch, relative to the cell
+        int nbq = 0;      // batches in the current super-batch
+        bool more = sidx < nsuper;
+        if (more) {
+            const int b0 = sidx < nsup1 ? rot + 4 * sidx : 4 * (sidx - nsup1);
+            nbq = min(4, (sidx < nsup1 ? nbatch : rot) - b0);
+            off = b0 << 5;
+        }
+        int w_j = 0, pk_j = 0;
+        int w_c = 0, pk_c = 0x200;  // the group sampled by the next step
+        Philox4 rnd = {0u, 0u, 0u, 0u};
+        int bq = 0;  // batch inside the super-batch
+        if (more) {
+            const bool valid = (off + lane) < ntok;
+            const int ic = valid ? off + lane : ntok - 1;
+            w_j = __ldg(tok_cell + ic);
+            const uint64_t gi = gi0 + (uint64_t)off;
+            rnd = philox4x32_10((uint32_t)gi, (uint32_t)(gi >> 32), p.sweep, 0u, p.seed_lo, p.seed_hi);
+            pk_j = pack_token(rnd.x, (int)z_cell[ic], valid);
+            w_c = (TPT > 1) ? __shfl_sync(FULL, w_j, 0, TPT) : w_j;
+            pk_c = (TPT > 1) ? __shfl_sync(FULL, pk_j, 0, TPT) : pk_j;
+            const char *row = nwk_lane + (uint64_t)((uint32_t)w_c) * rowbytes;
+            const int oc = ((pk_c & 0x1ff) >> 2) >> log2_tpt<TPT>();
+#pragma unroll
+            for (int c = 0; c < CH; ++c) {
+                const int rc = rot_chunk<CH>(c, oc);
+                if (rc < lim) buf[c] = __ldcg(reinterpret_cast<const int4 *>(row + rc * (TPT * 16)));
+            }
+        }
         int since_refresh = 0;
-        for (int64_t bb = warp; bb < nbatch; bb += nwarps) {
-            int64_t b = bb + rot;
-            if (b >= nbatch) b -= nbatch;
-            const int64_t base = t0 + (b << 5);
-            const int64_t i = base + lane;
-            const bool valid = i < t1;
-            int w_j = -1, zo_j = 0;
-            if (valid) {
-                w_j = __ldg(p.tok_region + i);
-                zo_j = (int)p.z[i];
+        while (more) {
+            // ---- the batch after this one (its tokens feed the last step's prefetch) ---------------
+            int sidx_n = sidx, off_n = off + 32, bq_n = bq + 1;
+            if (bq_n == nbq) {
+                bq_n = 0;
+                sidx_n = sidx + nwarps;
+                const int b0 = sidx_n < nsup1 ? rot + 4 * sidx_n : 4 * (sidx_n - nsup1);
+                nbq = min(4, (sidx_n < nsup1 ? nbatch : rot) - b0);
+                off_n = b0 << 5;
             }
-            const uint64_t gi = (uint64_t)(p.token_offset + i);
-            const Philox4 rnd = philox4x32_10((uint32_t)gi, (uint32_t)(gi >> 32), p.sweep, 0u,
-                                              p.seed_lo, p.seed_hi);
-            const float u_j = u01_from_bits(rnd.x);
-            int zn_j = zo_j;
-
-            const int rem = (int)min((int64_t)32, t1 - base);
-            const int nsteps = rem < TPT ? rem : TPT;
-
-            // Chunk order is rotated per token so that the chunk holding the token's own topic is
-            // always register chunk 0 of its lane: the own-token exclusion then patches 4 slots
-            // instead of all CH*4 (any fixed order of the topics gives the same distribution).
-            int4 rcur[CH], rnext[CH];
-            int w_cur = __shfl_sync(FULL, w_j, gbase);
-            int zo_cur = __shfl_sync(FULL, zo_j, gbase);
-            {
-                const int oc = (zo_cur >> 2) >> log2_tpt<TPT>();
-#pragma unroll
-                for (int c = 0; c < CH; ++c) {
-                    const int chunk = sub + TPT * rot_chunk<CH>(c, oc);
-                    rcur[c] = make_int4(0, 0, 0, 0);
-                    if (w_cur >= 0 && chunk * 4 < Kp)
-                        rcur[c] = ld_row_chunk(p.n_wk + (int64_t)w_cur * Kp + chunk * 4);
+            const bool more_n = sidx_n < nsuper;
+            int w_n = w_j, pk_n = pk_j | 0x200;
+            if (more_n) {
+                const bool valid_n = (off_n + lane) < ntok;
+                const int icn = valid_n ? off_n + lane : ntok - 1;
+                w_n = __ldg(tok_cell + icn);
+                if (bq_n == 0) {  // one Philox call per lane serves the four batches of a super-batch
+                    const uint64_t gi = gi0 + (uint64_t)off_n;
+                    rnd = philox4x32_10((uint32_t)gi, (uint32_t)(gi >> 32), p.sweep, 0u, p.seed_lo, p.seed_hi);
                 }
+                const uint32_t bits = bq_n == 0 ? rnd.x : bq_n == 1 ? rnd.y : bq_n == 2 ? rnd.z : rnd.w;
+                pk_n = pack_token(bits, (int)z_cell[icn], valid_n);
             }
 
-            for (int s = 0; s < nsteps; ++s) {
-                // ---- keep the topic totals live: publish this CTA's n_k deltas, re-read n_k ----
-                if (++since_refresh > p.refresh_every) {
-                    since_refresh = 1;
-                    for (int k = lane; k < K; k += 32) {
-                        const int d = atomicExch(&dnk_s[k], 0);
-                        if (d != 0) red_add_i32(p.n_k + k, d);
-                        const float den = (float)ld_volatile_i32(p.n_k + k) + p.etaW;
-                        const float inv = __frcp_rn(den);
-                        den_s[k] = den;
-                        inv_s[k] = inv;
-                        f_s[k] = ((float)ndk_s[k] + alpha) * inv;
-                    }
-                    __syncwarp();
+            // ---- keep the topic totals live: publish this cell's n_k deltas, re-read n_k ---------
+            if (++since_refresh > p.refresh_every) {
+                since_refresh = 1;
+                for (int k = lane; k < K; k += 32) {
+                    const int cur = lds_i(s_ndk + k * 4);
+                    const int d = cur - atoms_exch(s_pub + k * 4, cur);
+                    if (d != 0) red_add_i32(p.n_k + k, d);
+                    const float den = (float)ld_volatile_i32(p.n_k + k) + p.etaW;
+                    const float inv = __frcp_rn(den);
+                    sts_f(s_den + k * 4, den);
+                    sts_f(s_inv + k * 4, inv);
+                    sts_f(s_f + k * 4, ((float)lds_i(s_ndk + k * 4) + alpha) * inv);
                 }
-                // ---- prefetch the rows of the next step --------------------------------------
-                int w_next = -1, zo_next = 0;
-                if (TPT > 1) {
-                    const int src = gbase + ((s + 1) & (TPT - 1));
-                    w_next = __shfl_sync(FULL, w_j, src);
-                    zo_next = __shfl_sync(FULL, zo_j, src);
-                    if (s + 1 >= nsteps) w_next = -1;
-                    const int ocn = (zo_next >> 2) >> log2_tpt<TPT>();
-#pragma unroll
-                    for (int c = 0; c < CH; ++c) {
-                        const int chunk = sub + TPT * rot_chunk<CH>(c, ocn);
-                        rnext[c] = make_int4(0, 0, 0, 0);
-                        if (w_next >= 0 && chunk * 4 < Kp)
-                            rnext[c] = ld_row_chunk(p.n_wk + (int64_t)w_next * Kp + chunk * 4);
-                    }
-                }
-                const int w = w_cur;
-                const int zo = zo_cur;
-                const float u = (TPT > 1) ? __shfl_sync(FULL, u_j, gbase + s) : u_j;
+                __syncwarp();
+            }
 
-                // ---- own-token exclusion: component of z_old in chunk 0 of its lane (or -1) -----
-                const int ochunk = zo >> 2;
-                const int oc = ochunk >> log2_tpt<TPT>();
-                const int hitq = (sub == (ochunk & (TPT - 1))) ? (zo & 3) : -1;
-                const float fpp = __fdividef((float)(ndk_s[zo] - 1) + alpha, den_s[zo] - 1.0f);
-
-                // ---- running sum of p(k) over this lane's slots -------------------------------
-                float cum[CH * 4];
-                float acc = 0.0f;
-#pragma unroll
-                for (int c = 0; c < CH; ++c) {
-                    const int chunk = sub + TPT * rot_chunk<CH>(c, oc);
-                    const float4 fv = *reinterpret_cast<const float4 *>(&f_s[chunk * 4]);
-                    int nn[4] = {rcur[c].x, rcur[c].y, rcur[c].z, rcur[c].w};
-                    float ff[4] = {fv.x, fv.y, fv.z, fv.w};
-                    if (c == 0) {
-#pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            if (hitq == q) { nn[q] -= 1; ff[q] = fpp; }
-                    }
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        acc = fmaf((float)nn[q] + eta, ff[q], acc);
-                        cum[c * 4 + q] = acc;
-                    }
-                }
-
-                // ---- scan over the TPT lanes of the token, draw, invert ------------------------
-                float incl = acc;
-                if (TPT > 1) {
-#pragma unroll
-                    for (int off = 1; off < TPT; off <<= 1) {
-                        const float t = __shfl_up_sync(FULL, incl, off, TPT);
-                        if (sub >= off) incl += t;
-                    }
-                }
-                const float total = (TPT > 1) ? __shfl_sync(FULL, incl, TPT - 1, TPT) : incl;
-                const float tloc = u * total - (incl - acc);  // threshold relative to this lane
-                int cnt = 0;
-#pragma unroll
-                for (int j = 0; j < CH * 4; ++j) cnt += (cum[j] <= tloc) ? 1 : 0;
-                const int cand = (sub + TPT * rot_chunk<CH>(cnt >> 2, oc)) * 4 + (cnt & 3);
-                int zn;
-                if (TPT > 1) {
-                    const unsigned bal = __ballot_sync(FULL, cnt < CH * 4);
-                    const unsigned gm = (TPT == 32) ? bal : ((bal >> gbase) & ((1u << TPT) - 1u));
-                    const int src = gm ? (gbase + __ffs(gm) - 1) : lane;
-                    zn = __shfl_sync(FULL, cand, src);
-                    if (!gm) zn = zo;
-                } else {
-                    zn = cand;
-                }
-                if (zn >= K) zn = zo;  // rounding guard: padded slots carry p = 0
-
-                // ---- apply the move (one lane per token) ---------------------------------------
-                if (sub == (s & (TPT - 1)) && w >= 0 && zn != zo) {
-                    int32_t *row = p.n_wk + (int64_t)w * Kp;
-                    red_add_i32(row + zo, -1);
-                    red_add_i32(row + zn, 1);
-                    const int o0 = atomicAdd(&ndk_s[zo], -1);
-                    const int o1 = atomicAdd(&ndk_s[zn], 1);
-                    f_s[zo] = ((float)(o0 - 1) + alpha) * inv_s[zo];
-                    f_s[zn] = ((float)(o1 + 1) + alpha) * inv_s[zn];
-                    atomicAdd(&dnk_s[zo], -1);
-                    atomicAdd(&dnk_s[zn], 1);
-                    zn_j = zn;
-                }
-                if (TPT > 1) {
-                    w_cur = w_next;
-                    zo_cur = zo_next;
-#pragma unroll
-                    for (int c = 0; c < CH; ++c) rcur[c] = rnext[c];
+            int zn_j = pk_j & 0x1ff;
+            if (TPT == 1) {
+                // one token per lane: the lane's own next-batch token is the next group
+                zn_j = sweep_step<TPT, CH>(buf, nwk_lane, rowbytes, lim, w_j, pk_j, w_n, pk_n, sm, sub, gbase, lane,
+                                           alpha, eta, K);
+            } else {
+                constexpr int UNR = (TPT <= 8) ? TPT : 2;
+#pragma unroll UNR
+                for (int s = 0; s < TPT; ++s) {
+                    // the last step of a batch requests the first group of the next batch
+                    const bool last = (s + 1 >= TPT);
+                    const int src = last ? 0 : s + 1;
+                    const int w_x = __shfl_sync(FULL, last ? w_n : w_j, src, TPT);
+                    const int pk_x = __shfl_sync(FULL, last ? pk_n : pk_j, src, TPT);
+                    const int zn = sweep_step<TPT, CH>(buf, nwk_lane, rowbytes, lim, w_c, pk_c, w_x, pk_x, sm, sub,
+                                                       gbase, lane, alpha, eta, K);
+                    if (sub == s) zn_j = zn;
+                    w_c = w_x;
+                    pk_c = pk_x;
                 }
             }
-            if (valid) p.z[i] = (uint16_t)zn_j;
+            if ((pk_j & 0x200) == 0) z_cell[off + lane] = (uint16_t)zn_j;
+            sidx = sidx_n; off = off_n; bq = bq_n; more = more_n;
+            w_j = w_n; pk_j = pk_n;
         }
         __syncthreads();
         for (int k = tid; k < K; k += blockDim.x) {
-            ndk_row[k] = ndk_s[k];
-            const int d = dnk_s[k];
+            const int cur = lds_i(s_ndk + k * 4);
+            ndk_row[k] = cur;
+            const int d = cur - lds_i(s_pub + k * 4);
             if (d != 0) red_add_i32(p.n_k + k, d);
         }
         __syncthreads();
