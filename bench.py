@@ -440,22 +440,31 @@ def run_cuda(args):
                         np.empty(K, np.int32)) for K in my_topics}
         L = _lib.load()
 
+        stage_ms = {}
+
+        def timed(name, rc_fn):
+            t = time.perf_counter()
+            _lib.check(rc_fn())
+            stage_ms[name] = stage_ms.get(name, 0.0) + (time.perf_counter() - t) * 1e3
+
         def e2e_step():
             h = ctypes.c_void_p()
-            _lib.check(L.cgs_corpus_from_cells_by_regions(ctypes.byref(h), local_rank, _lib.ptr(indptr_np, _lib.c_i64p),
-                                                          _lib.ptr(indices_np, _lib.c_i32p), D, W, N, 0, D))
+            timed("corpus_from_cells_by_regions", lambda: L.cgs_corpus_from_cells_by_regions(
+                ctypes.byref(h), local_rank, _lib.ptr(indptr_np, _lib.c_i64p), _lib.ptr(indices_np, _lib.c_i32p),
+                D, W, N, 0, D))
             for K in my_topics:
                 mh = ctypes.c_void_p()
-                _lib.check(L.cgs_model_create(ctypes.byref(mh), h, K, ALPHA / K, ETA, MODEL_SEED, None))
-                _lib.check(L.cgs_model_init(mh))
-                _lib.check(L.cgs_model_sweep(mh, E2E_SWEEPS))
+                timed("model_create", lambda: L.cgs_model_create(ctypes.byref(mh), h, K, ALPHA / K, ETA, MODEL_SEED, None))
+                timed("model_init", lambda: L.cgs_model_init(mh))
+                timed("model_sweep(launch)", lambda: L.cgs_model_sweep(mh, E2E_SWEEPS))
                 a, b, c = out_bufs[K]
-                _lib.check(L.cgs_model_export_counts(mh, _lib.ptr(a, _lib.c_i32p), _lib.ptr(b, _lib.c_i32p),
-                                                     _lib.ptr(c, _lib.c_i32p)))
-                _lib.check(L.cgs_model_destroy(mh))
-            _lib.check(L.cgs_corpus_destroy(h))
+                timed("export_counts(waits for the sweeps)", lambda: L.cgs_model_export_counts(
+                    mh, _lib.ptr(a, _lib.c_i32p), _lib.ptr(b, _lib.c_i32p), _lib.ptr(c, _lib.c_i32p)))
+                timed("model_destroy", lambda: L.cgs_model_destroy(mh))
+            timed("corpus_destroy", lambda: L.cgs_corpus_destroy(h))
 
         e2e_step()  # warm-up
+        stage_ms.clear()
         torch.cuda.synchronize()
         barrier()
         n_e2e = max(1, min(args.steps, 3))
@@ -476,6 +485,7 @@ def run_cuda(args):
             h2d, d2h = int(t[0].item()), int(t[1].item())
         e2e = {"value": float(N) * len(N_TOPICS) * E2E_SWEEPS * n_e2e / dt, "unit": "tokens/s",
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": n_e2e, "ms_per_step": dt / n_e2e * 1e3,
+               "host_ms_per_step_by_call": {k: round(v / n_e2e, 2) for k, v in stage_ms.items()},
                "what": f"host CSR -> cgs_corpus_from_cells_by_regions -> per model: create, init, {E2E_SWEEPS} sweeps, "
                        f"cgs_model_export_counts to host (all {len(N_TOPICS)} models); wall clock incl. every copy"}
 

@@ -168,6 +168,23 @@ int cgs_impute_chunk_device(int device, const float *d_topic_region, const float
                             float scale, int as_int32, void *d_out, uint8_t *d_row_nonzero,
                             void *stream);
 
+/* impute_accessibility multiplies EVERY chunk of topic_region with the same cell_topic
+ * (diff_features.py:443-456): a plan holds the cell operand on the device in the layout the
+ * tensor-core kernel reads (cells x topics, TF32 hi/lo split), prepared once.
+ * cell_topic is n_topics x n_cells fp32 row-major, host or device memory. */
+typedef struct cgs_impute_plan cgs_impute_plan;
+int cgs_impute_plan_create(cgs_impute_plan **out, int device, const float *cell_topic,
+                           int cell_topic_on_device, int32_t n_topics, int32_t n_cells, void *stream);
+int cgs_impute_plan_destroy(cgs_impute_plan *plan);
+/* One chunk of regions against the plan; host pointers (copies included) ... */
+int cgs_impute_plan_chunk(cgs_impute_plan *plan, const float *topic_region, int32_t n_regions,
+                          float scale, int as_int32, void *out, uint8_t *row_nonzero);
+/* ... or device pointers, asynchronous on `stream`. */
+int cgs_impute_plan_chunk_device(cgs_impute_plan *plan, const float *d_topic_region, int32_t n_regions,
+                                 float scale, int as_int32, void *d_out, uint8_t *d_row_nonzero,
+                                 void *stream);
+int cgs_impute_plan_launch_count(const cgs_impute_plan *plan, int64_t *launches);
+
 #ifdef __cplusplus
 }
 #endif

@@ -73,6 +73,13 @@ SIGNATURES = {
                                         ctypes.c_int32, ctypes.c_float, ctypes.c_int, c_vp, c_u8p]),
     "cgs_impute_chunk_device": (ctypes.c_int, [ctypes.c_int, c_vp, c_vp, ctypes.c_int32, ctypes.c_int32,
                                                ctypes.c_int32, ctypes.c_float, ctypes.c_int, c_vp, c_vp, c_vp]),
+    "cgs_impute_plan_create": (ctypes.c_int, [ctypes.POINTER(c_vp), ctypes.c_int, c_vp, ctypes.c_int,
+                                              ctypes.c_int32, ctypes.c_int32, c_vp]),
+    "cgs_impute_plan_destroy": (ctypes.c_int, [c_vp]),
+    "cgs_impute_plan_chunk": (ctypes.c_int, [c_vp, c_f32p, ctypes.c_int32, ctypes.c_float, ctypes.c_int, c_vp, c_u8p]),
+    "cgs_impute_plan_chunk_device": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int32, ctypes.c_float, ctypes.c_int,
+                                                    c_vp, c_vp, c_vp]),
+    "cgs_impute_plan_launch_count": (ctypes.c_int, [c_vp, c_i64p]),
 }
 
 

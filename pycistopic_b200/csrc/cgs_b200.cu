@@ -1,7 +1,10 @@
 // cgs_b200.cu -- C ABI (include/cgs_b200.h) over the sm_100a kernels.
 #include "../../include/cgs_b200.h"
 
+#include <stdlib.h>
+
 #include <algorithm>
+#include <chrono>
 #include <numeric>
 #include <vector>
 
@@ -26,11 +29,53 @@ struct DeviceGuard {
     }
 };
 
+// Device buffers come from the device's stream-ordered pool (cudaMallocAsync): creating and
+// destroying models inside a topic sweep then costs microseconds instead of the device-wide
+// synchronisation of cudaMalloc / cudaFree.  `stream` is the stream that first uses the buffer
+// (dmalloc) or last used it (dfree).  Buffers that are exported over CUDA IPC (AD-LDA deltas)
+// use dmalloc_ipc: legacy IPC handles only exist for cudaMalloc memory.
 template <typename T>
-static int dmalloc(T **p, size_t n) {
+static int dmalloc(T **p, size_t n, cudaStream_t stream) {
+    *p = nullptr;
+    if (n == 0) n = 1;
+    CGS_CUDA(cudaMallocAsync((void **)p, n * sizeof(T), stream));
+    return 0;
+}
+
+template <typename T>
+static void dfree(T *p, cudaStream_t stream) {
+    if (p) cudaFreeAsync((void *)p, stream);
+}
+
+template <typename T>
+static int dmalloc_ipc(T **p, size_t n) {
     *p = nullptr;
     if (n == 0) n = 1;
     CGS_CUDA(cudaMalloc((void **)p, n * sizeof(T)));
+    return 0;
+}
+
+// CGS_B200_TIMING=1 prints host wall-clock of the construction stages to stderr (diagnostics only).
+struct StageTimer {
+    bool on;
+    std::chrono::steady_clock::time_point t;
+    StageTimer() : on(getenv("CGS_B200_TIMING") != nullptr), t(std::chrono::steady_clock::now()) {}
+    void lap(const char *what) {
+        if (!on) return;
+        cudaDeviceSynchronize();
+        auto n = std::chrono::steady_clock::now();
+        fprintf(stderr, "[cgs timing] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+        t = n;
+    }
+};
+
+// Keep freed blocks in the pool (the default threshold of 0 returns them to the driver at every
+// synchronisation, which is what made cudaFree expensive in the first place).
+static int configure_pool(int device) {
+    cudaMemPool_t pool;
+    CGS_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t keep = UINT64_MAX;
+    CGS_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
     return 0;
 }
 }  // namespace cgs
@@ -93,8 +138,10 @@ static int build_cell_order(cgs_corpus *c) {
     std::stable_sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
         return (ptr[a + 1] - ptr[a]) > (ptr[b + 1] - ptr[b]);
     });
-    CGS_TRY(dmalloc(&c->d_cell_order, order.size()));
+    CGS_TRY(dmalloc(&c->d_cell_order, order.size(), 0));
     CGS_CUDA(cudaMemcpy(c->d_cell_order, order.data(), sizeof(int32_t) * order.size(), cudaMemcpyHostToDevice));
+    // models run on non-blocking streams: everything the corpus owns must have landed before they start
+    CGS_CUDA(cudaStreamSynchronize(0));
     return 0;
 }
 
@@ -105,9 +152,9 @@ static int canonicalise(cgs_corpus *c, int32_t *d_tmp, int64_t *d_raw_ptr, int64
     int32_t *d_sorted = nullptr;
     unsigned long long *d_uniq = nullptr;
     int *d_flag = nullptr;
-    CGS_TRY(dmalloc(&d_sorted, (size_t)raw_total));
-    CGS_TRY(dmalloc(&d_uniq, (size_t)D));
-    CGS_TRY(dmalloc(&d_flag, 1));
+    CGS_TRY(dmalloc(&d_sorted, (size_t)raw_total, 0));
+    CGS_TRY(dmalloc(&d_uniq, (size_t)D, 0));
+    CGS_TRY(dmalloc(&d_flag, 1, 0));
     CGS_CUDA(cudaMemset(d_flag, 0, sizeof(int)));
 
     int max_smem = 0;
@@ -118,15 +165,17 @@ static int canonicalise(cgs_corpus *c, int32_t *d_tmp, int64_t *d_raw_ptr, int64
     size_t smem = (size_t)words * 4;
     CGS_CUDA(cudaFuncSetAttribute(bitmap_sort_cells_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int blocks = std::max(1, std::min(D, c->num_sms * (smem > 100 * 1024 ? 1 : 2)));
+    StageTimer tm;
     bitmap_sort_cells_kernel<<<blocks, 512, smem>>>(d_tmp, d_raw_ptr, D, c->n_regions, words, d_sorted, d_uniq, d_flag);
     CGS_CUDA(cudaGetLastError());
+    tm.lap("  bitmap_sort_cells");
     int flag = 0;
     CGS_CUDA(cudaMemcpy(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost));
     if (flag) {
-        cudaFree(d_sorted); cudaFree(d_uniq); cudaFree(d_flag);
+        dfree(d_sorted, 0); dfree(d_uniq, 0); dfree(d_flag, 0);
         CGS_FAIL("matrix index out of range while building the token list");
     }
-    CGS_TRY(dmalloc(&c->d_cell_ptr, (size_t)D + 1));
+    CGS_TRY(dmalloc(&c->d_cell_ptr, (size_t)D + 1, 0));
     exclusive_scan_i64_kernel<<<1, 1024>>>(d_uniq, c->d_cell_ptr, D);
     CGS_CUDA(cudaGetLastError());
     int64_t total = 0;
@@ -135,21 +184,25 @@ static int canonicalise(cgs_corpus *c, int32_t *d_tmp, int64_t *d_raw_ptr, int64
     if (total == raw_total) {
         c->d_tok_region = d_sorted;
     } else {
-        CGS_TRY(dmalloc(&c->d_tok_region, (size_t)total));
+        CGS_TRY(dmalloc(&c->d_tok_region, (size_t)total, 0));
         compact_cells_kernel<<<std::max(1, std::min(D, c->num_sms * 8)), 256>>>(d_sorted, d_raw_ptr, c->d_cell_ptr, D,
                                                                                c->d_tok_region);
         CGS_CUDA(cudaGetLastError());
         CGS_CUDA(cudaDeviceSynchronize());
-        cudaFree(d_sorted);
+        dfree(d_sorted, 0);
     }
-    cudaFree(d_uniq);
-    cudaFree(d_flag);
-    return build_cell_order(c);
+    dfree(d_uniq, 0);
+    dfree(d_flag, 0);
+    tm.lap("  scan + compact");
+    int rc = build_cell_order(c);
+    tm.lap("  build_cell_order");
+    return rc;
 }
 
 static int corpus_common_init(cgs_corpus *c, int device) {
     c->device = device;
     CGS_TRY(query_sms(device, &c->num_sms));
+    CGS_TRY(configure_pool(device));
     return 0;
 }
 
@@ -192,11 +245,11 @@ int cgs_corpus_from_regions_by_cells(cgs_corpus **out, int device, const int64_t
         int32_t *d_idx = nullptr;
         unsigned long long *d_count = nullptr, *d_fill = nullptr;
         int64_t *d_raw_ptr = nullptr;
-        CGS_TRY(dmalloc(&d_row_ptr, (size_t)n_regions + 1));
-        CGS_TRY(dmalloc(&d_idx, (size_t)nnz));
-        CGS_TRY(dmalloc(&d_count, (size_t)D));
-        CGS_TRY(dmalloc(&d_fill, (size_t)D));
-        CGS_TRY(dmalloc(&d_raw_ptr, (size_t)D + 1));
+        CGS_TRY(dmalloc(&d_row_ptr, (size_t)n_regions + 1, 0));
+        CGS_TRY(dmalloc(&d_idx, (size_t)nnz, 0));
+        CGS_TRY(dmalloc(&d_count, (size_t)D, 0));
+        CGS_TRY(dmalloc(&d_fill, (size_t)D, 0));
+        CGS_TRY(dmalloc(&d_raw_ptr, (size_t)D + 1, 0));
         CGS_CUDA(cudaMemcpy(d_row_ptr, indptr, sizeof(int64_t) * ((size_t)n_regions + 1), cudaMemcpyHostToDevice));
         CGS_CUDA(cudaMemcpy(d_idx, indices, sizeof(int32_t) * (size_t)nnz, cudaMemcpyHostToDevice));
         CGS_CUDA(cudaMemset(d_count, 0, sizeof(unsigned long long) * (size_t)D));
@@ -209,13 +262,13 @@ int cgs_corpus_from_regions_by_cells(cgs_corpus **out, int device, const int64_t
         int64_t raw_total = 0;
         CGS_CUDA(cudaMemcpy(&raw_total, d_raw_ptr + D, sizeof(int64_t), cudaMemcpyDeviceToHost));
         int32_t *d_tmp = nullptr;
-        CGS_TRY(dmalloc(&d_tmp, (size_t)raw_total));
+        CGS_TRY(dmalloc(&d_tmp, (size_t)raw_total, 0));
         scatter_rows_kernel<<<blocks, 256>>>(d_row_ptr, d_idx, n_regions, cell_begin, cell_end, d_raw_ptr, d_fill, d_tmp);
         CGS_CUDA(cudaGetLastError());
         CGS_CUDA(cudaDeviceSynchronize());
-        cudaFree(d_row_ptr); cudaFree(d_idx); cudaFree(d_count); cudaFree(d_fill);
+        dfree(d_row_ptr, 0); dfree(d_idx, 0); dfree(d_count, 0); dfree(d_fill, 0);
         int r = canonicalise(c, d_tmp, d_raw_ptr, raw_total);
-        cudaFree(d_tmp); cudaFree(d_raw_ptr);
+        dfree(d_tmp, 0); dfree(d_raw_ptr, 0);
         return r;
     }();
     if (rc != 0) { cgs_corpus_destroy(c); return rc; }
@@ -245,12 +298,15 @@ int cgs_corpus_from_cells_by_regions(cgs_corpus **out, int device, const int64_t
         for (int32_t d = 0; d <= D; ++d) local_ptr[d] = indptr[cell_begin + d] - t0;
         int64_t *d_raw_ptr = nullptr;
         int32_t *d_tmp = nullptr;
-        CGS_TRY(dmalloc(&d_raw_ptr, (size_t)D + 1));
-        CGS_TRY(dmalloc(&d_tmp, (size_t)raw_total));
+        CGS_TRY(dmalloc(&d_raw_ptr, (size_t)D + 1, 0));
+        CGS_TRY(dmalloc(&d_tmp, (size_t)raw_total, 0));
+        StageTimer tm;
         CGS_CUDA(cudaMemcpy(d_raw_ptr, local_ptr.data(), sizeof(int64_t) * local_ptr.size(), cudaMemcpyHostToDevice));
         CGS_CUDA(cudaMemcpy(d_tmp, indices + t0, sizeof(int32_t) * (size_t)raw_total, cudaMemcpyHostToDevice));
+        tm.lap("H2D indices");
         int r = canonicalise(c, d_tmp, d_raw_ptr, raw_total);
-        cudaFree(d_tmp); cudaFree(d_raw_ptr);
+        tm.lap("canonicalise + cell order");
+        dfree(d_tmp, 0); dfree(d_raw_ptr, 0);
         return r;
     }();
     if (rc != 0) { cgs_corpus_destroy(c); return rc; }
@@ -287,10 +343,10 @@ int cgs_corpus_destroy(cgs_corpus *c) {
     if (c->n_models > 0) CGS_FAIL("corpus still has live models");
     DeviceGuard g(c->device);
     if (c->owns_tokens) {
-        if (c->d_cell_ptr) cudaFree(c->d_cell_ptr);
-        if (c->d_tok_region) cudaFree(c->d_tok_region);
+        if (c->d_cell_ptr) dfree(c->d_cell_ptr, 0);
+        if (c->d_tok_region) dfree(c->d_tok_region, 0);
     }
-    if (c->d_cell_order) cudaFree(c->d_cell_order);
+    if (c->d_cell_order) dfree(c->d_cell_order, 0);
     delete c;
     return 0;
 }
@@ -317,11 +373,11 @@ int cgs_corpus_export_tokens(const cgs_corpus *c, int32_t *WS, int32_t *DS) {
         CGS_CUDA(cudaMemcpy(WS, c->d_tok_region, sizeof(int32_t) * (size_t)c->n_tokens, cudaMemcpyDeviceToHost));
     if (DS) {
         int32_t *d_ds = nullptr;
-        CGS_TRY(dmalloc(&d_ds, (size_t)c->n_tokens));
+        CGS_TRY(dmalloc(&d_ds, (size_t)c->n_tokens, 0));
         expand_cells_kernel<<<std::max(1, std::min(c->n_cells, c->num_sms * 8)), 256>>>(c->d_cell_ptr, c->n_cells, d_ds);
         CGS_CUDA(cudaGetLastError());
         CGS_CUDA(cudaMemcpy(DS, d_ds, sizeof(int32_t) * (size_t)c->n_tokens, cudaMemcpyDeviceToHost));
-        cudaFree(d_ds);
+        dfree(d_ds, 0);
     }
     return 0;
 }
@@ -333,16 +389,23 @@ int cgs_corpus_export_tokens(const cgs_corpus *c, int32_t *WS, int32_t *DS) {
 // sequential reference wants little concurrency; measured on config C1 (8 seeds):
 //     lag of the log-likelihood trace in the first sweeps
 //         ~ 0.08 % per 1 % of all tokens in flight  +  0.28 % x (fraction of cells open at once),
-// while tokens of ONE cell sampled together are harmless up to ~8 % of the cell.  So: wide CTAs,
-// in-cell concurrency <= mean_cell_tokens / 16, open cells <= D / 8, tokens in flight <= N / 128.
+// while tokens of ONE cell sampled together are harmless up to ~8 % of the cell at K = 10 but not at
+// K = 40 on short cells (see cap_cell below).  So: wide CTAs, in-cell concurrency <=
+// mean_cell_tokens / 64, open cells <= D / 8, tokens in flight <= N / 128.
 // At benchmark scale (D >= 10^4) none of the caps binds before the GPU is full.
 static void pick_sweep_shape(int32_t Kp, double n_tokens, double n_cells, int *tpt, int *ch, int *threads,
                              int *auto_blocks) {
     const int chunks = Kp / 4;
     const double mean_cell = n_tokens / std::max(1.0, n_cells);
+    // fewest lanes per token with at most 4 chunks per lane, but two lanes as soon as there are two
+    // chunks: one lane per token makes every row load and every count update an uncoalesced 32-address
+    // access (measured on C2: K = 10 takes 0.93 ms per sweep with 2 lanes, 1.13 ms with 1)
     int t = 1;
     while (t * 4 < chunks) t <<= 1;
-    const int cap_cell = (int)std::max(1.0, mean_cell / 16.0);
+    if (chunks >= 2 && t < 2) t = 2;
+    // K = 40 on 210-token cells: 8 tokens of a cell per step lag the trace by 0.4 % even with ONE cell
+    // open, 1-2 tokens per step by 0.1 % (profiles/r1_trace_small40_concurrency.txt)
+    const int cap_cell = (int)std::max(1.0, mean_cell / 64.0);
     while (t < 32 && 32 / t > cap_cell) t <<= 1;
     int warps = 8;
     while (warps > 1 && warps * (32 / t) > cap_cell) warps >>= 1;
@@ -382,13 +445,13 @@ int cgs_model_create(cgs_model **out, cgs_corpus *corpus, int32_t n_topics, doub
             m->owns_stream = true;
         }
         const size_t W = (size_t)corpus->n_regions, D = (size_t)corpus->n_cells, Kp = (size_t)m->Kp;
-        CGS_TRY(dmalloc(&m->d_z, (size_t)corpus->n_tokens));
-        CGS_TRY(dmalloc(&m->d_nwk, W * Kp));
-        CGS_TRY(dmalloc(&m->d_ndk, D * Kp));
-        CGS_TRY(dmalloc(&m->d_nk, Kp));
-        CGS_TRY(dmalloc(&m->d_work, (size_t)kWorkSlots));
-        CGS_TRY(dmalloc(&m->d_partials, (size_t)kPartialBlocks * 2 + 8));
-        CGS_TRY(dmalloc(&m->d_flag, 1));
+        CGS_TRY(dmalloc(&m->d_z, (size_t)corpus->n_tokens, m->stream));
+        CGS_TRY(dmalloc(&m->d_nwk, W * Kp, m->stream));
+        CGS_TRY(dmalloc(&m->d_ndk, D * Kp, m->stream));
+        CGS_TRY(dmalloc(&m->d_nk, Kp, m->stream));
+        CGS_TRY(dmalloc(&m->d_work, (size_t)kWorkSlots, m->stream));
+        CGS_TRY(dmalloc(&m->d_partials, (size_t)kPartialBlocks * 2 + 8, m->stream));
+        CGS_TRY(dmalloc(&m->d_flag, 1, m->stream));
         CGS_CUDA(cudaMemsetAsync(m->d_nwk, 0, sizeof(int32_t) * W * Kp, m->stream));
         CGS_CUDA(cudaMemsetAsync(m->d_ndk, 0, sizeof(int32_t) * D * Kp, m->stream));
         CGS_CUDA(cudaMemsetAsync(m->d_nk, 0, sizeof(int32_t) * Kp, m->stream));
@@ -405,8 +468,8 @@ int cgs_model_destroy(cgs_model *m) {
     if (!m) return 0;
     DeviceGuard g(m->corpus->device);
     if (m->stream) cudaStreamSynchronize(m->stream);
-    cudaFree(m->d_z); cudaFree(m->d_nwk); cudaFree(m->d_ndk); cudaFree(m->d_nk);
-    cudaFree(m->d_snap); cudaFree(m->d_delta); cudaFree(m->d_work); cudaFree(m->d_partials); cudaFree(m->d_flag);
+    dfree(m->d_z, m->stream); dfree(m->d_nwk, m->stream); dfree(m->d_ndk, m->stream); dfree(m->d_nk, m->stream);
+    cudaFree(m->d_snap); cudaFree(m->d_delta); dfree(m->d_work, m->stream); dfree(m->d_partials, m->stream); dfree(m->d_flag, m->stream);
     if (m->owns_stream && m->stream) cudaStreamDestroy(m->stream);
     m->corpus->n_models--;
     delete m;
@@ -464,7 +527,7 @@ int cgs_model_set_z(cgs_model *m, const int32_t *z) {
     cgs_corpus *c = m->corpus;
     DeviceGuard g(c->device);
     int32_t *d_tmp = nullptr;
-    CGS_TRY(dmalloc(&d_tmp, (size_t)c->n_tokens));
+    CGS_TRY(dmalloc(&d_tmp, (size_t)c->n_tokens, m->stream));
     CGS_CUDA(cudaMemcpyAsync(d_tmp, z, sizeof(int32_t) * (size_t)c->n_tokens, cudaMemcpyHostToDevice, m->stream));
     CGS_CUDA(cudaMemsetAsync(m->d_flag, 0, sizeof(int), m->stream));
     z_from_i32_kernel<<<c->num_sms * 8, 256, 0, m->stream>>>(d_tmp, m->d_z, c->n_tokens, m->K, m->d_flag);
@@ -473,7 +536,7 @@ int cgs_model_set_z(cgs_model *m, const int32_t *z) {
     int flag = 0;
     CGS_CUDA(cudaMemcpyAsync(&flag, m->d_flag, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
     CGS_CUDA(cudaStreamSynchronize(m->stream));
-    cudaFree(d_tmp);
+    dfree(d_tmp, m->stream);
     if (flag) CGS_FAIL("z contains a topic outside [0, n_topics)");
     return rebuild_counts(m);
 }
@@ -483,13 +546,13 @@ int cgs_model_get_z(cgs_model *m, int32_t *z) {
     cgs_corpus *c = m->corpus;
     DeviceGuard g(c->device);
     int32_t *d_tmp = nullptr;
-    CGS_TRY(dmalloc(&d_tmp, (size_t)c->n_tokens));
+    CGS_TRY(dmalloc(&d_tmp, (size_t)c->n_tokens, m->stream));
     z_to_i32_kernel<<<c->num_sms * 8, 256, 0, m->stream>>>(m->d_z, d_tmp, c->n_tokens);
     CGS_CUDA(cudaGetLastError());
     m->launches += 1;
     CGS_CUDA(cudaMemcpyAsync(z, d_tmp, sizeof(int32_t) * (size_t)c->n_tokens, cudaMemcpyDeviceToHost, m->stream));
     CGS_CUDA(cudaStreamSynchronize(m->stream));
-    cudaFree(d_tmp);
+    dfree(d_tmp, m->stream);
     return 0;
 }
 
@@ -700,24 +763,24 @@ int cgs_model_export_counts(cgs_model *m, int32_t *nzw, int32_t *ndz, int32_t *n
     const int32_t K = m->K, Kp = m->Kp;
     if (nzw) {
         int32_t *d_t = nullptr;
-        CGS_TRY(dmalloc(&d_t, (size_t)W * K));
+        CGS_TRY(dmalloc(&d_t, (size_t)W * K, m->stream));
         dim3 grid((unsigned)ceil_div(W, 32), (unsigned)ceil_div(K, 32)), block(32, 8);
         transpose_counts_kernel<<<grid, block, 0, m->stream>>>(m->d_nwk, W, K, Kp, d_t);
         CGS_CUDA(cudaGetLastError());
         m->launches += 1;
         CGS_CUDA(cudaMemcpyAsync(nzw, d_t, sizeof(int32_t) * (size_t)W * K, cudaMemcpyDeviceToHost, m->stream));
         CGS_CUDA(cudaStreamSynchronize(m->stream));
-        cudaFree(d_t);
+        dfree(d_t, m->stream);
     }
     if (ndz) {
         int32_t *d_t = nullptr;
-        CGS_TRY(dmalloc(&d_t, (size_t)D * K));
+        CGS_TRY(dmalloc(&d_t, (size_t)D * K, m->stream));
         unpad_counts_kernel<<<c->num_sms * 8, 256, 0, m->stream>>>(m->d_ndk, D, K, Kp, d_t);
         CGS_CUDA(cudaGetLastError());
         m->launches += 1;
         CGS_CUDA(cudaMemcpyAsync(ndz, d_t, sizeof(int32_t) * (size_t)D * K, cudaMemcpyDeviceToHost, m->stream));
         CGS_CUDA(cudaStreamSynchronize(m->stream));
-        cudaFree(d_t);
+        dfree(d_t, m->stream);
     }
     if (nz) {
         CGS_CUDA(cudaMemcpyAsync(nz, m->d_nk, sizeof(int32_t) * (size_t)K, cudaMemcpyDeviceToHost, m->stream));
@@ -733,25 +796,25 @@ static int export_dist(cgs_model *m, double *topic_side, int topic_transposed, d
     dim3 block(32, 8);
     if (topic_side) {
         double *d_t = nullptr;
-        CGS_TRY(dmalloc(&d_t, (size_t)W * K));
+        CGS_TRY(dmalloc(&d_t, (size_t)W * K, m->stream));
         dim3 grid((unsigned)ceil_div(W, 32), (unsigned)ceil_div(K, 32));
         topic_word_kernel<<<grid, block, 0, m->stream>>>(m->d_nwk, m->d_nk, W, K, Kp, m->eta, topic_transposed, d_t);
         CGS_CUDA(cudaGetLastError());
         m->launches += 1;
         CGS_CUDA(cudaMemcpyAsync(topic_side, d_t, sizeof(double) * (size_t)W * K, cudaMemcpyDeviceToHost, m->stream));
         CGS_CUDA(cudaStreamSynchronize(m->stream));
-        cudaFree(d_t);
+        dfree(d_t, m->stream);
     }
     if (cell_side) {
         double *d_t = nullptr;
-        CGS_TRY(dmalloc(&d_t, (size_t)D * K));
+        CGS_TRY(dmalloc(&d_t, (size_t)D * K, m->stream));
         dim3 grid((unsigned)ceil_div(D, 32), (unsigned)ceil_div(K, 32));
         doc_topic_kernel<<<grid, block, 0, m->stream>>>(m->d_ndk, c->d_cell_ptr, D, K, Kp, m->alpha, cell_transposed, d_t);
         CGS_CUDA(cudaGetLastError());
         m->launches += 1;
         CGS_CUDA(cudaMemcpyAsync(cell_side, d_t, sizeof(double) * (size_t)D * K, cudaMemcpyDeviceToHost, m->stream));
         CGS_CUDA(cudaStreamSynchronize(m->stream));
-        cudaFree(d_t);
+        dfree(d_t, m->stream);
     }
     return 0;
 }
@@ -772,11 +835,11 @@ int cgs_model_export_frames(cgs_model *m, double *topic_region, double *cell_top
 static int ensure_exchange_buffers(cgs_model *m) {
     const size_t n = (size_t)m->corpus->n_regions * (size_t)m->Kp;
     if (!m->d_snap) {
-        CGS_TRY(dmalloc(&m->d_snap, n));
+        CGS_TRY(dmalloc_ipc(&m->d_snap, n));
         CGS_CUDA(cudaMemsetAsync(m->d_snap, 0, n * sizeof(int32_t), m->stream));
     }
     if (!m->d_delta) {
-        CGS_TRY(dmalloc(&m->d_delta, n));
+        CGS_TRY(dmalloc_ipc(&m->d_delta, n));
         CGS_CUDA(cudaMemsetAsync(m->d_delta, 0, n * sizeof(int32_t), m->stream));
     }
     return 0;
@@ -890,41 +953,158 @@ int cgs_ipc_close(int device, void *device_ptr) {
 }
 
 // ---- imputation --------------------------------------------------------------------------------
+}  // extern "C"
+
+struct cgs_impute_plan {
+    int device = 0;
+    int num_sms = kNumSMsFallback;
+    int32_t K = 0, Kp = 0, C = 0;
+    float *d_cells_raw = nullptr;           // K x C copy of cell_topic (cross-check path only)
+    float *d_b_hi = nullptr, *d_b_lo = nullptr;  // C x Kp, TF32 split, K-major
+    int64_t launches = 0;
+};
+
+namespace cgs {
+static bool impute_use_simt() {
+    const char *e = getenv("CGS_IMPUTE_SIMT");
+    return e && e[0] == '1';
+}
+
+// Splits the region operand, runs the tensor-core kernel against the plan's cell operand.
+static int impute_run(cgs_impute_plan *p, const float *d_A, int32_t R, float scale, int as_int32, void *d_out,
+                      uint8_t *d_row_nonzero, cudaStream_t stream) {
+    if (impute_use_simt()) {
+        CGS_TRY(impute_simt_launch(d_A, p->d_cells_raw, R, p->K, p->C, scale, as_int32, d_out, d_row_nonzero, stream));
+        p->launches += 1;
+        return 0;
+    }
+    float *d_a_hi = nullptr, *d_a_lo = nullptr;
+    const size_t n = (size_t)R * p->Kp;
+    CGS_TRY(dmalloc(&d_a_hi, n, stream));
+    CGS_TRY(dmalloc(&d_a_lo, n, stream));
+    int rc = [&]() -> int {
+        CGS_TRY(impute_prepare_regions(d_A, R, p->K, p->Kp, d_a_hi, d_a_lo, p->num_sms, stream));
+        CGS_TRY(impute_umma_launch(d_a_hi, d_a_lo, p->d_b_hi, p->d_b_lo, R, p->K, p->Kp, p->C, scale, as_int32, d_out,
+                                   d_row_nonzero, p->num_sms, stream));
+        p->launches += 2;
+        return 0;
+    }();
+    dfree(d_a_hi, stream);
+    dfree(d_a_lo, stream);
+    return rc;
+}
+}  // namespace cgs
+
+extern "C" {
+
+int cgs_impute_plan_create(cgs_impute_plan **out, int device, const float *cell_topic, int cell_topic_on_device,
+                           int32_t n_topics, int32_t n_cells, void *stream_) {
+    if (!out || !cell_topic) CGS_FAIL("NULL argument");
+    if (n_topics <= 0 || n_cells <= 0) CGS_FAIL("empty operand");
+    DeviceGuard g(device);
+    if (!g.ok) CGS_FAIL("cannot select CUDA device");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    cgs_impute_plan *p = new cgs_impute_plan();
+    *out = nullptr;
+    int rc = [&]() -> int {
+        p->device = device;
+        CGS_TRY(query_sms(device, &p->num_sms));
+        CGS_TRY(configure_pool(device));
+        p->K = n_topics;
+        p->Kp = impute_padded_k(n_topics);
+        p->C = n_cells;
+        const size_t nb = (size_t)n_topics * n_cells;
+        CGS_TRY(dmalloc(&p->d_cells_raw, nb, stream));
+        CGS_CUDA(cudaMemcpyAsync(p->d_cells_raw, cell_topic, nb * 4,
+                                 cell_topic_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, stream));
+        CGS_TRY(dmalloc(&p->d_b_hi, (size_t)n_cells * p->Kp, stream));
+        CGS_TRY(dmalloc(&p->d_b_lo, (size_t)n_cells * p->Kp, stream));
+        CGS_TRY(impute_prepare_cells(p->d_cells_raw, p->K, p->C, p->Kp, p->d_b_hi, p->d_b_lo, stream));
+        p->launches += 1;
+        if (!impute_use_simt()) {  // the raw copy only serves the cross-check kernel
+            dfree(p->d_cells_raw, stream);
+            p->d_cells_raw = nullptr;
+        }
+        CGS_CUDA(cudaStreamSynchronize(stream));  // later chunks may run on other streams
+        return 0;
+    }();
+    if (rc != 0) { cgs_impute_plan_destroy(p); return rc; }
+    *out = p;
+    return 0;
+}
+
+int cgs_impute_plan_destroy(cgs_impute_plan *p) {
+    if (!p) return 0;
+    DeviceGuard g(p->device);
+    cudaDeviceSynchronize();
+    dfree(p->d_cells_raw, 0); dfree(p->d_b_hi, 0); dfree(p->d_b_lo, 0);
+    delete p;
+    return 0;
+}
+
+int cgs_impute_plan_launch_count(const cgs_impute_plan *p, int64_t *launches) {
+    if (!p || !launches) CGS_FAIL("NULL argument");
+    *launches = p->launches;
+    return 0;
+}
+
+int cgs_impute_plan_chunk_device(cgs_impute_plan *p, const float *d_topic_region, int32_t n_regions, float scale,
+                                 int as_int32, void *d_out, uint8_t *d_row_nonzero, void *stream) {
+    if (!p || !d_topic_region || !d_out) CGS_FAIL("NULL argument");
+    if (n_regions <= 0) CGS_FAIL("empty operand");
+    DeviceGuard g(p->device);
+    if (!g.ok) CGS_FAIL("cannot select CUDA device");
+    return impute_run(p, d_topic_region, n_regions, scale, as_int32, d_out, d_row_nonzero, (cudaStream_t)stream);
+}
+
+int cgs_impute_plan_chunk(cgs_impute_plan *p, const float *topic_region, int32_t n_regions, float scale, int as_int32,
+                          void *out, uint8_t *row_nonzero) {
+    if (!p || !topic_region || !out) CGS_FAIL("NULL argument");
+    if (n_regions <= 0) CGS_FAIL("empty operand");
+    DeviceGuard g(p->device);
+    if (!g.ok) CGS_FAIL("cannot select CUDA device");
+    float *d_a = nullptr;
+    uint8_t *d_o = nullptr, *d_f = nullptr;
+    const size_t na = (size_t)n_regions * p->K, no = (size_t)n_regions * p->C;
+    int rc = [&]() -> int {
+        CGS_TRY(dmalloc(&d_a, na, 0));
+        CGS_TRY(dmalloc(&d_o, no * 4, 0));
+        CGS_TRY(dmalloc(&d_f, (size_t)n_regions, 0));
+        CGS_CUDA(cudaMemcpyAsync(d_a, topic_region, na * 4, cudaMemcpyHostToDevice, 0));
+        CGS_TRY(impute_run(p, d_a, n_regions, scale, as_int32, d_o, d_f, 0));
+        CGS_CUDA(cudaMemcpyAsync(out, d_o, no * 4, cudaMemcpyDeviceToHost, 0));
+        if (row_nonzero) CGS_CUDA(cudaMemcpyAsync(row_nonzero, d_f, (size_t)n_regions, cudaMemcpyDeviceToHost, 0));
+        CGS_CUDA(cudaStreamSynchronize(0));
+        return 0;
+    }();
+    dfree(d_a, 0); dfree(d_o, 0); dfree(d_f, 0);
+    return rc;
+}
+
 int cgs_impute_chunk_device(int device, const float *d_topic_region, const float *d_cell_topic, int32_t n_regions,
                             int32_t n_topics, int32_t n_cells, float scale, int as_int32, void *d_out,
                             uint8_t *d_row_nonzero, void *stream) {
     if (!d_topic_region || !d_cell_topic || !d_out) CGS_FAIL("NULL argument");
     if (n_regions <= 0 || n_topics <= 0 || n_cells <= 0) CGS_FAIL("empty operand");
-    DeviceGuard g(device);
-    if (!g.ok) CGS_FAIL("cannot select CUDA device");
-    return impute_launch(device, d_topic_region, d_cell_topic, n_regions, n_topics, n_cells, scale, as_int32, d_out,
-                         d_row_nonzero, (cudaStream_t)stream);
+    cgs_impute_plan *p = nullptr;
+    CGS_TRY(cgs_impute_plan_create(&p, device, d_cell_topic, 1, n_topics, n_cells, stream));
+    int rc = cgs_impute_plan_chunk_device(p, d_topic_region, n_regions, scale, as_int32, d_out, d_row_nonzero, stream);
+    if (rc == 0) {
+        DeviceGuard g(device);
+        cudaStreamSynchronize((cudaStream_t)stream);
+    }
+    cgs_impute_plan_destroy(p);
+    return rc;
 }
 
 int cgs_impute_chunk(int device, const float *topic_region, const float *cell_topic, int32_t n_regions,
                      int32_t n_topics, int32_t n_cells, float scale, int as_int32, void *out, uint8_t *row_nonzero) {
     if (!topic_region || !cell_topic || !out) CGS_FAIL("NULL argument");
     if (n_regions <= 0 || n_topics <= 0 || n_cells <= 0) CGS_FAIL("empty operand");
-    DeviceGuard g(device);
-    if (!g.ok) CGS_FAIL("cannot select CUDA device");
-    float *d_a = nullptr, *d_b = nullptr;
-    void *d_o = nullptr;
-    uint8_t *d_f = nullptr;
-    const size_t na = (size_t)n_regions * n_topics, nb = (size_t)n_topics * n_cells, no = (size_t)n_regions * n_cells;
-    int rc = [&]() -> int {
-        CGS_TRY(dmalloc(&d_a, na));
-        CGS_TRY(dmalloc(&d_b, nb));
-        CGS_CUDA(cudaMalloc(&d_o, no * 4));
-        CGS_TRY(dmalloc(&d_f, (size_t)n_regions));
-        CGS_CUDA(cudaMemcpy(d_a, topic_region, na * 4, cudaMemcpyHostToDevice));
-        CGS_CUDA(cudaMemcpy(d_b, cell_topic, nb * 4, cudaMemcpyHostToDevice));
-        CGS_TRY(impute_launch(device, d_a, d_b, n_regions, n_topics, n_cells, scale, as_int32, d_o, d_f, nullptr));
-        CGS_CUDA(cudaDeviceSynchronize());
-        CGS_CUDA(cudaMemcpy(out, d_o, no * 4, cudaMemcpyDeviceToHost));
-        if (row_nonzero) CGS_CUDA(cudaMemcpy(row_nonzero, d_f, (size_t)n_regions, cudaMemcpyDeviceToHost));
-        return 0;
-    }();
-    cudaFree(d_a); cudaFree(d_b); cudaFree(d_o); cudaFree(d_f);
+    cgs_impute_plan *p = nullptr;
+    CGS_TRY(cgs_impute_plan_create(&p, device, cell_topic, 0, n_topics, n_cells, nullptr));
+    int rc = cgs_impute_plan_chunk(p, topic_region, n_regions, scale, as_int32, out, row_nonzero);
+    cgs_impute_plan_destroy(p);
     return rc;
 }
 

@@ -4,7 +4,8 @@
 
 The chunk product ``topic_region[chunk] @ cell_topic`` (:443-456), the ``* scale_factor`` /
 ``astype(int32)`` epilogue (:458-464) and the all-zero-row filter (:468-486) run on the GPU
-through ``cgs_impute_chunk``; the return value has the reference's layout (a DENSE ndarray in
+through ``cgs_impute_plan_*`` (tcgen05 tensor-core kernel; the cell operand is prepared on the device
+once and reused by every chunk); the return value has the reference's layout (a DENSE ndarray in
 ``mtx``, the kept region names, the cell names).
 """
 from __future__ import annotations
@@ -62,22 +63,27 @@ def calculate_imputed_accessibility(topic_region, cell_topic, region_names, scal
     region_names_to_keep = []
     output_chunk_end = 0
     scale = float(np.float32(scale_factor)) if as_int else 1.0
-    for input_chunk_start in range(0, R, chunk_size):
-        input_chunk_end = input_chunk_start + chunk_size
-        output_chunk_start = output_chunk_end
-        if log is not None:
-            log.info(f"Impute region accessibility for regions {input_chunk_start}-{input_chunk_end}")
-        a = topic_region[input_chunk_start:input_chunk_end]
-        n = a.shape[0]
-        chunk = np.empty((n, C), dtype=out_dtype)
-        flags = np.empty(n, dtype=np.uint8)
-        check(L.cgs_impute_chunk(device, ptr(a, c_f32p), ptr(cell_topic, c_f32p), n, K, C, scale, int(as_int),
-                                 chunk.ctypes.data_as(c_vp), ptr(flags, c_u8p)))
-        keep = np.flatnonzero(flags)
-        names_chunk = region_names[input_chunk_start:input_chunk_end]
-        region_names_to_keep.extend([names_chunk[i] for i in keep])
-        output_chunk_end = output_chunk_start + len(keep)
-        imputed_acc[output_chunk_start:output_chunk_end, :] = chunk[keep]
+    plan = c_vp()
+    check(L.cgs_impute_plan_create(ctypes.byref(plan), device, ptr(cell_topic, c_f32p), 0, K, C, None))
+    try:
+        for input_chunk_start in range(0, R, chunk_size):
+            input_chunk_end = input_chunk_start + chunk_size
+            output_chunk_start = output_chunk_end
+            if log is not None:
+                log.info(f"Impute region accessibility for regions {input_chunk_start}-{input_chunk_end}")
+            a = topic_region[input_chunk_start:input_chunk_end]
+            n = a.shape[0]
+            chunk = np.empty((n, C), dtype=out_dtype)
+            flags = np.empty(n, dtype=np.uint8)
+            check(L.cgs_impute_plan_chunk(plan, ptr(a, c_f32p), n, scale, int(as_int), chunk.ctypes.data_as(c_vp),
+                                          ptr(flags, c_u8p)))
+            keep = np.flatnonzero(flags)
+            names_chunk = region_names[input_chunk_start:input_chunk_end]
+            region_names_to_keep.extend([names_chunk[i] for i in keep])
+            output_chunk_end = output_chunk_start + len(keep)
+            imputed_acc[output_chunk_start:output_chunk_end, :] = chunk[keep]
+    finally:
+        check(L.cgs_impute_plan_destroy(plan))
     imputed_acc = imputed_acc[0:output_chunk_end]
     return imputed_acc, region_names_to_keep
 
