@@ -557,6 +557,13 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-adlda", action="store_true")
     args = ap.parse_args()
+    # The contract is ONE JSON line on stdout.  Libraries underneath (NCCL prints its version banner
+    # there) write to file descriptor 1 directly, so that descriptor is pointed at stderr while the
+    # benchmark runs and the JSON line goes to the real stdout.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w", buffering=1)
     if args.impl == "reference":
         return run_reference(args)
     return run_cuda(args)
