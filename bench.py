@@ -254,23 +254,43 @@ def run_adlda_leg(args, dev, rank, world, local_rank):
     from pycistopic_b200.adlda import Exchanger, GpuShard, balanced_cell_partition
     from pycistopic_b200.synth import SHAPES, planted_topic_tokens
 
-    D, W, density = SHAPES[ADLDA_SHAPE]
-    cell, region = planted_topic_tokens(D, W, density, seed=DATA_SEED, device=dev)
-    cnt = torch.bincount(cell, minlength=D)
-    del cell
-    part_ptr, cell_ptr_h = balanced_cell_partition(cnt.cpu().numpy(), world)
-    cb, ce = int(part_ptr[rank]), int(part_ptr[rank + 1])
-    t0, t1 = int(cell_ptr_h[cb]), int(cell_ptr_h[ce])
-    N_total = int(cell_ptr_h[-1])
-    tok = region[t0:t1].to(torch.int32).contiguous()
-    del region
-    cp = torch.tensor(cell_ptr_h[cb:ce + 1] - t0, dtype=torch.int64, device=dev)
+    shape, K_adlda = args.adlda_shape, (ADLDA_K if args.adlda_shape != "C4" else 100)
+    D, W, density = SHAPES[shape]
+    if shape == "C4" or args.adlda_rank_local_data:
+        # atlas scale: every rank draws only its own cells (equal cell counts; the budgets are i.i.d.)
+        cb, ce = D * rank // world, D * (rank + 1) // world
+        cell, region = planted_topic_tokens(D, W, density, seed=DATA_SEED, device=dev, cell_range=(cb, ce))
+        cnt = torch.bincount(cell - cb, minlength=ce - cb)
+        del cell
+        n_local = int(cnt.sum().item())
+        sizes = torch.zeros(world, dtype=torch.int64, device=dev)
+        sizes[rank] = n_local
+        if world > 1:
+            dist.all_reduce(sizes)
+        t0 = int(sizes[:rank].sum().item())
+        t1 = t0 + n_local
+        N_total = int(sizes.sum().item())
+        tok = region.to(torch.int32).contiguous()
+        del region
+        cp = torch.zeros(ce - cb + 1, dtype=torch.int64, device=dev)
+        cp[1:] = torch.cumsum(cnt, 0)
+    else:
+        cell, region = planted_topic_tokens(D, W, density, seed=DATA_SEED, device=dev)
+        cnt = torch.bincount(cell, minlength=D)
+        del cell
+        part_ptr, cell_ptr_h = balanced_cell_partition(cnt.cpu().numpy(), world)
+        cb, ce = int(part_ptr[rank]), int(part_ptr[rank + 1])
+        t0, t1 = int(cell_ptr_h[cb]), int(cell_ptr_h[ce])
+        N_total = int(cell_ptr_h[-1])
+        tok = region[t0:t1].to(torch.int32).contiguous()
+        del region
+        cp = torch.tensor(cell_ptr_h[cb:ce + 1] - t0, dtype=torch.int64, device=dev)
     torch.cuda.empty_cache()
     out = {}
     for exchange in (["nccl", "peer"] if world > 1 else ["nccl"]):
         corpus = Corpus.from_device_tokens(cp.data_ptr(), tok.data_ptr(), ce - cb, W, t1 - t0, device=local_rank,
                                            token_offset=t0, keepalive=(cp, tok))
-        shard = GpuShard(None, (cb, ce), t0, ADLDA_K, ALPHA / ADLDA_K, ETA, MODEL_SEED, device=local_rank,
+        shard = GpuShard(None, (cb, ce), t0, K_adlda, ALPHA / K_adlda, ETA, MODEL_SEED, device=local_rank,
                          exchange=exchange, corpus=corpus)
         shard.init()
         ex = Exchanger(shard, exchange)
@@ -310,10 +330,10 @@ def run_adlda_leg(args, dev, rank, world, local_rank):
         _ = ll
     peak = 6544.3
     best = max(out.values(), key=lambda v: v["tokens_per_s"])
-    return {"workload": f"{ADLDA_SHAPE}: {D} cells x {W} regions, {N_total} tokens, one K={ADLDA_K} model, cells sharded "
-                        f"over {world} GPU(s), one n_wk exchange per sweep ({4 * W * ((ADLDA_K + 3) // 4 * 4) / 1e6:.0f} MB)",
+    return {"workload": f"{shape}: {D} cells x {W} regions, {N_total} tokens, one K={K_adlda} model, cells sharded "
+                        f"over {world} GPU(s), one n_wk exchange per sweep ({4 * W * ((K_adlda + 3) // 4 * 4) / 1e6:.0f} MB)",
             "scaling": "strong", "value": best["tokens_per_s"], "unit": "tokens/s", "per_exchange": out,
-            "frac_of_hbm_roofline_per_gpu": b_tok(ADLDA_K) * best["tokens_per_s"] / world / 1e9 / peak}
+            "frac_of_hbm_roofline_per_gpu": b_tok(K_adlda) * best["tokens_per_s"] / world / 1e9 / peak}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -335,6 +355,15 @@ def run_cuda(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     _lib.require_device()
+
+    if args.adlda_only:
+        adlda = run_adlda_leg(args, dev, rank, world, local_rank)
+        if rank == 0:
+            print(json.dumps({"metric": "gibbs_tokens_per_s_per_sweep", "n_gpus": world, "adlda": adlda}), flush=True)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
 
     D, W, cell_ptr, tok = make_workload_on_device(dev)
     N = tok.numel()
@@ -556,6 +585,11 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-adlda", action="store_true")
+    ap.add_argument("--adlda-shape", default=ADLDA_SHAPE, choices=["C1", "C2", "C3", "C4", "T"],
+                    help="matrix of the single-model AD-LDA leg (C3 = BASELINE configs[2], C4 = configs[3], K = 100)")
+    ap.add_argument("--adlda-rank-local-data", action="store_true",
+                    help="every rank draws only its own cells (always on for C4)")
+    ap.add_argument("--adlda-only", action="store_true", help="skip the model-sweep legs (used for the C4 run)")
     args = ap.parse_args()
     # The contract is ONE JSON line on stdout.  Libraries underneath (NCCL prints its version banner
     # there) write to file descriptor 1 directly, so that descriptor is pointed at stderr while the

@@ -25,7 +25,8 @@ SHAPES = {
 }
 
 
-def planted_topic_tokens(n_cells, n_regions, density, n_true_topics=20, seed=1234, device=None, max_rounds=12):
+def planted_topic_tokens(n_cells, n_regions, density, n_true_topics=20, seed=1234, device=None, max_rounds=12,
+                         cell_range=None):
     """Return (cell_ids, region_ids) int64 arrays of UNIQUE (cell, region) pairs sorted by
     (cell, region).  Runs in NumPy, or in torch on ``device`` when given (same algorithm,
     different generator -- the result is only reproducible per backend).  Cells keep drawing
@@ -33,7 +34,9 @@ def planted_topic_tokens(n_cells, n_regions, density, n_true_topics=20, seed=123
     rounds), so the matrix reaches the requested density despite the heavy-tailed region
     popularity."""
     if device is not None:
-        return _planted_torch(n_cells, n_regions, density, n_true_topics, seed, device, max_rounds)
+        return _planted_torch(n_cells, n_regions, density, n_true_topics, seed, device, max_rounds, cell_range)
+    if cell_range is not None:
+        raise ValueError("cell_range needs the torch backend (device=...)")
     rng = np.random.default_rng(seed)
     W, D, Kt = n_regions, n_cells, n_true_topics
     pop = 1.0 / np.arange(1, W + 1) ** 1.0
@@ -82,7 +85,9 @@ def planted_topic_tokens(n_cells, n_regions, density, n_true_topics=20, seed=123
     return cell[keep], region[keep]
 
 
-def _planted_torch(n_cells, n_regions, density, n_true_topics, seed, device, max_rounds):
+def _planted_torch(n_cells, n_regions, density, n_true_topics, seed, device, max_rounds, cell_range=None):
+    """``cell_range=(c0, c1)`` draws only those cells (same topics and budgets as the full matrix, its own
+    random stream): lets every rank of a sharded run generate its own cells of an atlas-scale matrix."""
     import torch
 
     g = torch.Generator(device=device)
@@ -111,11 +116,15 @@ def _planted_torch(n_cells, n_regions, density, n_true_topics, seed, device, max
     max_tok = 48_000_000  # draws per chunk (bounds the temporaries)
     keys = []
     c0 = 0
+    c_end = D
+    if cell_range is not None:
+        c0, c_end = int(cell_range[0]), int(cell_range[1])
+        g.manual_seed(seed + 7919 * (c0 + 1))
     budget_ptr = torch.cumsum(n_d, 0)
-    while c0 < D:
+    while c0 < c_end:
         base = int(budget_ptr[c0 - 1]) if c0 > 0 else 0
         c1 = int(torch.searchsorted(budget_ptr, torch.tensor(base + max_tok // 2, device=device)).item())
-        c1 = max(c0 + 1, min(c1, D))
+        c1 = max(c0 + 1, min(c1, c_end))
         nc = c1 - c0
         flat_t = (tcdf[c0:c1] + torch.arange(nc, device=device, dtype=f64)[:, None] * 2.0).reshape(-1)
         key = torch.empty(0, dtype=torch.int64, device=device)
