@@ -37,6 +37,13 @@ E2E_SWEEPS = 10
 BURN_IN = 20  # sweeps before any timing, so the chains are past the z = i mod K transient
 
 
+def workload_text(D, W, N):
+    """The `config.workload` string shared by both arms (N = tokens of the full matrix, None if unknown)."""
+    tok = "" if N is None else f", {N} tokens (density {N / D / W:.4f})"
+    return (f"{WORKLOAD}: {D} cells x {W} regions{tok}, n_topics sweep {N_TOPICS}, alpha={ALPHA}/K, eta={ETA}, "
+            f"one step = one Gibbs sweep of all {len(N_TOPICS)} models")
+
+
 def b_tok(k: int) -> float:
     """Algorithmic bytes per token-update (SURVEY.md 8d / DESIGN.md): 4K + 28."""
     return 4.0 * k + 28.0
@@ -228,8 +235,8 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64 arithmetic on int32 counts",
         "data": data,
-        "config": {"workload": f"{WORKLOAD}: {D} cells x {W} regions, density {density}, n_topics sweep {N_TOPICS}, "
-                               f"alpha={ALPHA}/K, eta={ETA}", "n_topics": N_TOPICS, "sampled_cells": sample_cells},
+        "config": {"workload": workload_text(D, W, n_total), "n_topics": N_TOPICS, "tokens": n_total, "cells": D,
+                   "regions": W, "sampled_cells": sample_cells},
         "cpu_baseline": {"value": value, "unit": "tokens/s", "cores": cpu.cores, "kind": "port", "sample": sample,
                          "cpu": cpu_model_name(), "host_cores": os.cpu_count()},
         "e2e": {"value": value, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -334,6 +341,61 @@ def run_adlda_leg(args, dev, rank, world, local_rank):
                         f"over {world} GPU(s), one n_wk exchange per sweep ({4 * W * ((K_adlda + 3) // 4 * 4) / 1e6:.0f} MB)",
             "scaling": "strong", "value": best["tokens_per_s"], "unit": "tokens/s", "per_exchange": out,
             "frac_of_hbm_roofline_per_gpu": b_tok(K_adlda) * best["tokens_per_s"] / world / 1e9 / peak}
+
+
+# ------------------------------------------------------------------------------------------------
+# Imputation leg (BASELINE.json configs[4], one chunk_size = 20 000 chunk of it): tcgen05 3xTF32 product
+# with the fused scale / truncate / row-flag epilogue, operands and result resident on the device.
+# ------------------------------------------------------------------------------------------------
+IMPUTE_R, IMPUTE_K, IMPUTE_C = 20_000, 100, 200_000
+
+
+def run_impute_leg(args, dev, local_rank, hbm_peak):
+    import torch
+
+    from pycistopic_b200 import _lib
+    L = _lib.load()
+    R, K, C = IMPUTE_R, IMPUTE_K, IMPUTE_C
+    g = torch.Generator(device=dev)
+    g.manual_seed(4321)
+    A = torch.rand(R, K, device=dev, generator=g)
+    A /= A.sum(0, keepdim=True)
+    B = torch.rand(K, C, device=dev, generator=g)
+    B /= B.sum(0, keepdim=True)
+    out = torch.empty(R, C, dtype=torch.int32, device=dev)
+    flags = torch.empty(R, dtype=torch.uint8, device=dev)
+    plan = ctypes.c_void_p()
+    _lib.check(L.cgs_impute_plan_create(ctypes.byref(plan), local_rank, B.data_ptr(), 1, K, C, None))
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def run():
+        _lib.check(L.cgs_impute_plan_chunk_device(plan, A.data_ptr(), R, 1e6, 1, out.data_ptr(), flags.data_ptr(), stream))
+
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    n = max(3, min(args.steps, 10))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    rows = torch.randint(0, R, (8,), device=dev)
+    ref = torch.trunc((A[rows].double() @ B.double()) * 1e6)
+    max_diff = float((out[rows].double() - ref).abs().max().item())
+    launches = ctypes.c_int64()
+    _lib.check(L.cgs_impute_plan_launch_count(plan, ctypes.byref(launches)))
+    _lib.check(L.cgs_impute_plan_destroy(plan))
+    del out
+    torch.cuda.empty_cache()
+    gbs = 4.0 * R * C / (ms * 1e-3) / 1e9
+    return {"workload": f"impute_accessibility chunk: {R} regions x {K} topics x {C} cells -> int32 (x 1e6, truncated), "
+                        "device resident, split of the region operand + tensor-core kernel per chunk",
+            "ms_per_chunk": ms, "bound": "hbm (4 R C output bytes)", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+            "frac": gbs / hbm_peak, "tflops_2RCK": 2.0 * R * C * K / (ms * 1e-3) / 1e12,
+            "max_abs_diff_vs_fp64_on_8_rows": max_diff, "kernel": "impute_umma_kernel (tcgen05.mma kind::tf32, 3xTF32)"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -545,9 +607,12 @@ def run_cuda(args):
     corpus._keepalive = None
     del cell_ptr, tok
     torch.cuda.empty_cache()
+    torch.cuda.set_stream(torch.cuda.default_stream(dev))
+    impute = None
+    if rank == 0 and not args.no_impute:
+        impute = run_impute_leg(args, dev, local_rank, peak)
     adlda = None
     if not args.no_adlda:
-        torch.cuda.set_stream(torch.cuda.default_stream(dev))
         adlda = run_adlda_leg(args, dev, rank, world, local_rank)
 
     if rank == 0:
@@ -556,9 +621,7 @@ def run_cuda(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "int32 counts, fp32 conditional, u16 topics", "data": "synthetic",
-            "config": {"workload": f"{WORKLOAD}: {D} cells x {W} regions, {N} tokens (density {N / (D * W):.4f}), "
-                                   f"n_topics sweep {N_TOPICS}, alpha={ALPHA}/K, eta={ETA}, one step = one Gibbs sweep "
-                                   f"of all {len(N_TOPICS)} models",
+            "config": {"workload": workload_text(D, W, N),
                        "n_topics": N_TOPICS, "tokens": N, "cells": D, "regions": W,
                        "sharding": "one model per GPU, longest first" if world > 1 else "all models on one GPU",
                        "plan": {str(r): [N_TOPICS[i] for i in plan[r]] for r in range(world)},
@@ -566,7 +629,7 @@ def run_cuda(args):
                        "l2": "inputs larger than L2: every model streams 6 B/token of tokens+topics "
                              f"({6 * N / 1e6:.0f} MB) per sweep and the step cycles through {len(my_topics)} models"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clock_info, "adlda": adlda,
+            "clocks": clock_info, "adlda": adlda, "impute": impute,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -585,6 +648,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-adlda", action="store_true")
+    ap.add_argument("--no-impute", action="store_true")
     ap.add_argument("--adlda-shape", default=ADLDA_SHAPE, choices=["C1", "C2", "C3", "C4", "T"],
                     help="matrix of the single-model AD-LDA leg (C3 = BASELINE configs[2], C4 = configs[3], K = 100)")
     ap.add_argument("--adlda-rank-local-data", action="store_true",

@@ -113,13 +113,23 @@ def run_cgs_models(
     errors = []
 
     def worker(dev, idxs):
+        # The sweeps of model i+1 run on the GPU while the host packs model i (metrics + DataFrames,
+        # about a second per model at 300 k regions): one packing thread per device, results in order.
+        from concurrent.futures import ThreadPoolExecutor
         try:
             corpus = Corpus.from_regions_by_cells(binary_matrix, device=dev)
+            pending = {}
             try:
-                for i in idxs:
-                    results[i] = _run_cgs_model_on_corpus(
-                        corpus, binary_matrix, n_topics[i], cell_names, region_names, n_iter, random_state,
-                        alpha, alpha_by_topic, eta, eta_by_topic, top_topics_coh, save_path)
+                with ThreadPoolExecutor(max_workers=1) as packer:
+                    for i in idxs:
+                        fitted, end_time, log = _fit_cgs_model_on_corpus(
+                            corpus, n_topics[i], n_iter, random_state, alpha, alpha_by_topic, eta, eta_by_topic)
+                        pending[i] = packer.submit(
+                            build_cistopic_model, fitted, binary_matrix, n_topics[i], cell_names, region_names,
+                            n_iter, random_state, alpha, alpha_by_topic, eta, eta_by_topic, top_topics_coh, end_time,
+                            save_path, log)
+                    for i, fut in pending.items():
+                        results[i] = fut.result()
             finally:
                 corpus.close()
         except BaseException as e:  # propagate to the caller like ray.get would
@@ -164,8 +174,8 @@ def run_cgs_model(
         corpus.close()
 
 
-def _run_cgs_model_on_corpus(corpus, regions_by_cells, n_topics, cell_names, region_names, n_iter, random_state,
-                             alpha, alpha_by_topic, eta, eta_by_topic, top_topics_coh, save_path):
+def _fit_cgs_model_on_corpus(corpus, n_topics, n_iter, random_state, alpha, alpha_by_topic, eta, eta_by_topic):
+    """The device part of run_cgs_model (lda_models.py:247-289): returns (fitted LDA, seconds, logger)."""
     log = _logger()
     lda_log = logging.getLogger("lda")
     lda_log.addHandler(logging.NullHandler())
@@ -186,8 +196,13 @@ def _run_cgs_model_on_corpus(corpus, regions_by_cells, n_topics, cell_names, reg
     log.info(f"Running model with {n_topics} topics")
     start_time = time.time()
     model.fit(None)
-    end_time = time.time() - start_time
+    return model, time.time() - start_time, log
 
+
+def _run_cgs_model_on_corpus(corpus, regions_by_cells, n_topics, cell_names, region_names, n_iter, random_state,
+                             alpha, alpha_by_topic, eta, eta_by_topic, top_topics_coh, save_path):
+    model, end_time, log = _fit_cgs_model_on_corpus(corpus, n_topics, n_iter, random_state, alpha, alpha_by_topic,
+                                                    eta, eta_by_topic)
     return build_cistopic_model(model, regions_by_cells, n_topics, cell_names, region_names, n_iter, random_state,
                                 alpha, alpha_by_topic, eta, eta_by_topic, top_topics_coh, end_time, save_path, log)
 
