@@ -13,7 +13,9 @@
 // so that every operand tile is a plain 2-D TMA box with the 128-byte swizzle the UMMA shared
 // memory descriptors expect.
 //
-// Kernel (impute_umma_kernel), persistent, one CTA per SM, 128 x 256 output tile:
+// Kernels: impute_umma_pair_kernel (default: CTA pairs, tcgen05.mma.cta_group::2, 256 x 256 tile per pair,
+// 3-stage 64 KB ring per CTA) and impute_umma_kernel (one CTA, 128 x 256 tile, 2-stage 96 KB ring), both
+// persistent with one CTA per SM.  Roles, single-CTA numbers:
 //   warp 0   TMA producer: per 32-wide K block four boxes (A_hi, A_lo 128 x 32; B_hi, B_lo 256 x 32)
 //            into a 2-stage shared-memory ring, completion on an mbarrier (expect_tx)
 //   warp 1   one elected thread issues 12 tcgen05.mma per K block (4 k-steps x 3 operand pairs)
@@ -21,18 +23,20 @@
 //            and, after the last K block, hands the accumulator to the epilogue
 //   warp 2   allocates / frees the 512 TMEM columns
 //   warps 4-11 epilogue (two warps per TMEM lane quarter, 128 columns each): tcgen05.ld 32 lanes x
-//            32 columns -> * scale -> truncate toward zero (cvt.rzi) -> 128-byte-swizzled 32 x 32
-//            staging tile -> one TMA store per tile (the tensor map clips the ragged edges); when
-//            n_cells is not a multiple of 4 the rows are not 16-byte aligned and the staging tile
-//            is written with 128-byte coalesced row stores instead.  Row-non-zero flags come from
-//            the same registers
-// Tiles are walked region-block fastest so that the CTAs running at the same time share one
-// 256-cell operand tile in L2 while the (small) region operand stays L2 resident.
+//            16 columns (next block in flight) -> * scale -> truncate toward zero (FP32-pipe add in
+//            round-toward-zero mode; cvt.rzi only for values outside [0, 2^23)) -> swizzled 32 x 16
+//            staging tile (two per warp) -> 16-byte coalesced stores (or one TMA store per block;
+//            4-byte stores when n_cells is not a multiple of 4 and rows are not 16-byte aligned).
+//            Row-non-zero flags come from the same registers
+// Tiles are walked in groups of 8 neighbouring cell blocks, cell block fastest inside a group, so that
+// the CTAs running at the same time share a handful of cell-operand tiles in L2 while the (small) region
+// operand stays L2 resident.
 //
 // The CUDA-core kernel below it (impute_simt_kernel) is the cross-check used by the GPU tests
 // (CGS_IMPUTE_SIMT=1); it is not a fallback: the tensor-core path handles every shape.
 #pragma once
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -166,7 +170,7 @@ constexpr int A_BYTES = BM * BK * 4;                       // 16 KB
 constexpr int B_BYTES = BN * BK * 4;                       // 32 KB
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;     // A_hi | A_lo | B_hi | B_lo = 96 KB
 constexpr int EPI_WARPS = 8;                               // two per TMEM lane quarter
-constexpr int EPI_TILE_BYTES = 32 * 32 * 4;                // one 32 x 32 staging tile (4 KB) per epilogue warp
+constexpr int EPI_TILE_BYTES = 2 * 32 * 16 * 4;            // two 32 x 16 staging tiles (2 KB each) per epilogue warp
 constexpr int EPI_BYTES = EPI_WARPS * EPI_TILE_BYTES;
 constexpr int BAR_BYTES = 128;
 constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES;
@@ -206,6 +210,7 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t sr
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read_but_one() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -240,7 +245,7 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(int m, int n) {
            | (2u << 10)              // b_format = TF32
            | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
-__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
+__device__ __forceinline__ void tmem_ld_32x32_issue(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -250,11 +255,228 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
           "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
           "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x16_issue(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
+    tmem_ld_32x32_issue(taddr, v);
+    tmem_ld_wait();
+}
+
+// Tile walk: groups of kTileGroupN neighbouring cell blocks; inside a group the region blocks advance slowest
+// and the cell blocks fastest.  The CTAs that run at the same time then (a) share a handful of cell-operand
+// tiles in L2 and (b) write kTileGroupN KB of every output row back to back -- a column-block-at-a-time walk
+// writes isolated 1 KB pieces 800 KB apart and tops out at 4.5 TB/s of the 7.5 TB/s a plain fill reaches.
+#ifndef CGS_IMPUTE_GROUP_N
+#define CGS_IMPUTE_GROUP_N 8
+#endif
+constexpr int kTileGroupN = CGS_IMPUTE_GROUP_N;
+__device__ __forceinline__ void tile_coords(int64_t t, int n_m, int n_n, int &m_idx, int &n_idx) {
+    const int64_t per_group = (int64_t)n_m * kTileGroupN;
+    const int g = (int)(t / per_group);
+    const int r = (int)(t - (int64_t)g * per_group);
+    const int gn = min(kTileGroupN, n_n - g * kTileGroupN);
+    m_idx = r / gn;
+    n_idx = g * kTileGroupN + r - m_idx * gn;
+}
+
+// ---- CTA-pair (cta_group::2) variants --------------------------------------------------------
+constexpr int STAGES2 = 3;
+constexpr int B_HALF_BYTES = (BN / 2) * BK * 4;                  // each CTA of the pair stages half of the cell tile
+constexpr int STAGE2_BYTES = 2 * A_BYTES + 2 * B_HALF_BYTES;     // 64 KB
+constexpr int SMEM2_BYTES = 1024 + STAGES2 * STAGE2_BYTES + EPI_BYTES + BAR_BYTES;
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;                   // shared::cluster address of the same offset in CTA 0
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t.reg .b32 rem;\n\t"
+        "mapa.shared::cluster.u32 rem, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [rem];\n\t}" ::"r"(bar),
+        "r"(cta)
+        : "memory");
+}
+// TMA load issued by either CTA of a pair; the bytes are accounted on CTA 0's barrier
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+            "r"(dst),
+        "l"(map), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+        "h"((uint16_t)3)
+        : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
 }
 }  // namespace imp
 
-template <bool AS_INT, bool TMA_STORE>
+// Epilogue of one 32 x 16 accumulator block held in v (lane = row): scale, convert, stage, store.
+// `reload_taddr` is the block's TMEM address (the exact-conversion path reads it again); `buf` is one of
+// the warp's two 2 KB staging tiles (32 rows x 64 bytes, 64-byte swizzle).
+// STORE: 0 = 4-byte coalesced stores (rows not 16-byte aligned), 1 = TMA store, 2 = 16-byte coalesced stores
+template <bool AS_INT, int STORE>
+__device__ __forceinline__ void impute_epi_chunk(uint32_t (&v)[16], uint32_t reload_taddr, float scale, bool &any,
+                                                 uint32_t buf, int lane, const CUtensorMap *tm_out, int col0, int row0,
+                                                 int R, int C, void *out) {
+    using namespace imp;
+    if (AS_INT) {
+        // cvt.rzi.s32.f32 runs on the special-function pipe; for 0 <= y < 2^23 (every imputed count: a
+        // probability times 10^6) truncation is an FP32-pipe add in round-toward-zero mode:
+        // y +rz 2^23 = 2^23 + trunc(y), whose low 23 bits are the integer.  Anything else (negative, huge,
+        // NaN -- visible as an unsigned bit pattern >= 0x4B000000) takes the exact cvt path.
+        uint32_t maxbits = 0, orbits = 0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const float y = __uint_as_float(v[j]) * scale;
+            maxbits = max(maxbits, __float_as_uint(y));
+            const uint32_t iv = __float_as_uint(__fadd_rz(y, 8388608.0f)) - 0x4B000000u;
+            orbits |= iv;
+            v[j] = iv;
+        }
+        if (__any_sync(0xffffffffu, maxbits >= 0x4B000000u)) {
+            tmem_ld_32x16_issue(reload_taddr, v);
+            tmem_ld_wait();
+            orbits = 0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const uint32_t iv = (uint32_t)__float2int_rz(__uint_as_float(v[j]) * scale);
+                orbits |= iv;
+                v[j] = iv;
+            }
+        }
+        any |= (orbits != 0);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const float x = __uint_as_float(v[j]);
+            const float fv = (scale != 1.0f) ? x * scale : x;
+            any |= (fv != 0.0f);
+            v[j] = __float_as_uint(fv);
+        }
+    }
+    if (STORE == 1) {
+        // the store that last used THIS staging tile (two stores ago) must have finished reading it
+        if (lane == 0) tma_store_wait_read_but_one();
+        __syncwarp();
+        // row `lane`, four 16-byte pieces, 64-byte swizzle (matches the store's tensor map)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const uint32_t addr = buf + (uint32_t)lane * 64u + (uint32_t)((c ^ ((lane >> 1) & 3)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[4 * c]), "r"(v[4 * c + 1]),
+                         "r"(v[4 * c + 2]), "r"(v[4 * c + 3])
+                         : "memory");
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) tma_store_2d(tm_out, buf, col0, row0);
+    } else if (STORE == 2) {
+        // same swizzled staging tile, read back as 16-byte pieces: a warp instruction stores 8 rows x 64 B
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const uint32_t addr = buf + (uint32_t)lane * 64u + (uint32_t)((c ^ ((lane >> 1) & 3)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[4 * c]), "r"(v[4 * c + 1]),
+                         "r"(v[4 * c + 2]), "r"(v[4 * c + 3])
+                         : "memory");
+        }
+        __syncwarp();
+        const int piece = lane & 3;
+        const int col = col0 + piece * 4;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = i * 8 + (lane >> 2);
+            const int row = row0 + r;
+            uint4 o;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w)
+                         : "r"(buf + (uint32_t)r * 64u + (uint32_t)((piece ^ ((r >> 1) & 3)) << 4)));
+            if (row < R && col < C)  // C % 4 == 0: a 16-byte piece is inside the row or outside
+                *reinterpret_cast<uint4 *>(reinterpret_cast<uint32_t *>(out) + (int64_t)row * C + col) = o;
+        }
+    } else {
+        // 32 x 16 transpose through the 2 KB staging tile (column index rotated by the row), then two rows per
+        // warp instruction: 64 contiguous bytes per row
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(buf + (uint32_t)(lane * 16 + ((j + lane) & 15)) * 4u), "r"(v[j])
+                         : "memory");
+        }
+        __syncwarp();
+        const int col = col0 + (lane & 15);
+        if (col < C) {
+#pragma unroll 8
+            for (int r2 = 0; r2 < 16; ++r2) {
+                const int r = r2 * 2 + (lane >> 4);
+                const int row = row0 + r;
+                if (row < R) {
+                    uint32_t o;
+                    asm volatile("ld.shared.b32 %0, [%1];"
+                                 : "=r"(o)
+                                 : "r"(buf + (uint32_t)(r * 16 + (((lane & 15) + r) & 15)) * 4u));
+                    reinterpret_cast<uint32_t *>(out)[(int64_t)row * C + col] = o;
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// The 32 rows x 128 columns an epilogue warp owns in a tile: eight 32 x 16 blocks.  The TMEM load of block
+// i + 1 is in flight while block i is converted, and the two staging tiles alternate so that a TMA store
+// reads one while the next block is written into the other.
+template <bool AS_INT, int STORE>
+__device__ __forceinline__ void impute_epi_tile(uint32_t taddr0, int n_blocks, float scale, bool &any, uint32_t stage_buf,
+                                                int lane, const CUtensorMap *tm_out, int col0, int row0, int R, int C,
+                                                void *out) {
+    using namespace imp;
+    uint32_t va[16], vb[16];
+    if (n_blocks > 0) tmem_ld_32x16_issue(taddr0, va);
+#pragma unroll
+    for (int ch = 0; ch < BN / 32; ++ch) {
+        if (ch < n_blocks) {  // warp-uniform
+            tmem_ld_wait();
+            const uint32_t buf = stage_buf + (uint32_t)(ch & 1) * (EPI_TILE_BYTES / 2);
+            if (ch & 1) {
+                if (ch + 1 < n_blocks) tmem_ld_32x16_issue(taddr0 + (uint32_t)(ch + 1) * 16u, va);
+                impute_epi_chunk<AS_INT, STORE>(vb, taddr0 + (uint32_t)ch * 16u, scale, any, buf, lane,
+                                                                   tm_out, col0 + ch * 16, row0, R, C, out);
+            } else {
+                if (ch + 1 < n_blocks) tmem_ld_32x16_issue(taddr0 + (uint32_t)(ch + 1) * 16u, vb);
+                impute_epi_chunk<AS_INT, STORE>(va, taddr0 + (uint32_t)ch * 16u, scale, any, buf, lane,
+                                                                   tm_out, col0 + ch * 16, row0, R, C, out);
+            }
+        }
+    }
+}
+
+template <bool AS_INT, int STORE>
 __global__ void __launch_bounds__(imp::THREADS, 1)
 impute_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
@@ -312,7 +534,9 @@ impute_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
             int stage = 0;
             uint32_t phase = 0;
             for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-                const int m0 = (int)(t % n_m) * BM, n0 = (int)(t / n_m) * BN;
+                int mi, ni;
+                tile_coords(t, n_m, n_n, mi, ni);
+                const int m0 = mi * BM, n0 = ni * BN;
                 for (int kb = 0; kb < n_kblocks; ++kb) {
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
                     const uint32_t full = bar_full + 8 * stage;
@@ -368,70 +592,18 @@ impute_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-            const int m0 = (int)(t % n_m) * BM, n0 = (int)(t / n_m) * BN;
+            int mi, ni;
+            tile_coords(t, n_m, n_n, mi, ni);
+            const int m0 = mi * BM, n0 = ni * BN;
             mbar_wait(bar_tfull + 8 * acc, acc_phase);
             tc_fence_after();
             const int row0 = m0 + q * 32;
             bool any = false;
-#pragma unroll 1
-            for (int ch = 0; ch < BN / 64; ++ch) {
-                const int col0 = n0 + half * (BN / 2) + ch * 32;
-                if (col0 >= C) break;  // warp-uniform: nothing of this tile lies further right
-                uint32_t v[32];
-                tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2) + ch * 32), v);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float x = __uint_as_float(v[j]);
-                    if (AS_INT) {
-                        const int iv = __float2int_rz(x * scale);
-                        any |= (iv != 0);
-                        v[j] = (uint32_t)iv;
-                    } else {
-                        const float fv = (scale != 1.0f) ? x * scale : x;
-                        any |= (fv != 0.0f);
-                        v[j] = __float_as_uint(fv);
-                    }
-                }
-                if (TMA_STORE) {
-                    // the previous store must have finished reading the staging tile
-                    if (lane == 0) tma_store_wait_read();
-                    __syncwarp();
-                    // row `lane`, eight 16-byte pieces, 128-byte swizzle (matches the store's tensor map)
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        const uint32_t addr = stage_buf + (uint32_t)lane * 128u + (uint32_t)((c ^ (lane & 7)) << 4);
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[4 * c]), "r"(v[4 * c + 1]),
-                                     "r"(v[4 * c + 2]), "r"(v[4 * c + 3])
-                                     : "memory");
-                    }
-                    fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) tma_store_2d(&tm_out, stage_buf, col0, row0);
-                } else {
-                    // 32 x 32 transpose through the 4 KB tile: column index rotated by the row keeps both the
-                    // row-wise writes and the column-wise reads conflict-free
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const uint32_t addr = stage_buf + (uint32_t)(lane * 32 + ((j + lane) & 31)) * 4u;
-                        asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v[j]) : "memory");
-                    }
-                    __syncwarp();
-                    const int col = col0 + lane;
-                    if (col < C) {
-#pragma unroll 8
-                        for (int r = 0; r < 32; ++r) {
-                            const int row = row0 + r;
-                            if (row < R) {
-                                uint32_t o;
-                                asm volatile("ld.shared.b32 %0, [%1];"
-                                             : "=r"(o)
-                                             : "r"(stage_buf + (uint32_t)(r * 32 + ((lane + r) & 31)) * 4u));
-                                reinterpret_cast<uint32_t *>(out)[(int64_t)row * C + col] = o;
-                            }
-                        }
-                    }
-                    __syncwarp();
-                }
+            {
+                const int colbase = n0 + half * (BN / 2);
+                const int n_blocks = colbase >= C ? 0 : min(BN / 32, (C - colbase + 15) / 16);
+                impute_epi_tile<AS_INT, STORE>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2)),
+                                                   n_blocks, scale, any, stage_buf, lane, &tm_out, colbase, row0, R, C, out);
             }
             // every lane of this warp has finished reading the accumulator
             tc_fence_before();
@@ -441,7 +613,7 @@ impute_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
             if (any && row_nonzero && row0 + lane < R) row_nonzero[row0 + lane] = 1;
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
-        if (TMA_STORE && lane == 0) tma_store_wait_all();
+        if (STORE == 1 && lane == 0) tma_store_wait_all();
     }
 
     tc_fence_before();
@@ -449,6 +621,163 @@ impute_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
+                     : "memory");
+    }
+}
+
+// CTA-pair version: two CTAs on neighbouring SMs compute one 256 x 256 tile with tcgen05.mma.cta_group::2
+// (M = 256).  Each CTA stages its own 128 regions and HALF of the 256 cells per K block (64 KB instead of
+// 96 KB, so the ring has three stages and a third less operand traffic comes out of L2); the leader CTA
+// issues the MMAs, which read both CTAs' shared memory and write each CTA's 128 rows into its own TMEM.
+template <bool AS_INT, int STORE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(imp::THREADS, 1)
+impute_umma_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                        const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                        const __grid_constant__ CUtensorMap tm_out, int32_t R, int32_t C, int32_t n_ksteps, float scale,
+                        void *__restrict__ out, uint8_t *__restrict__ row_nonzero) {
+    using namespace imp;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t *smem = smem_raw + (base - raw);
+    const uint32_t s_epi = base + STAGES2 * STAGE2_BYTES;
+    const uint32_t s_bar = s_epi + EPI_BYTES;
+    // full[3] | empty[3] | tmem_full[2] | tmem_empty[2] | TMEM base address
+    const uint32_t bar_full = s_bar, bar_empty = s_bar + 8 * STAGES2, bar_tfull = s_bar + 16 * STAGES2,
+                   bar_tempty = s_bar + 16 * STAGES2 + 16;
+    const uint32_t tmem_slot_addr = s_bar + 16 * STAGES2 + 32;
+    volatile uint32_t *tmem_slot =
+        reinterpret_cast<volatile uint32_t *>(smem + STAGES2 * STAGE2_BYTES + EPI_BYTES + 16 * STAGES2 + 32);
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();  // 0 = leader
+    const bool leader = rank == 0;
+
+    if (warp == 1 && lane == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES2; ++s) {
+            mbar_init(bar_full + 8 * s, 2);   // one arrival per CTA of the pair (the leader's carries the byte count)
+            mbar_init(bar_empty + 8 * s, 1);  // the leader's commit, multicast to both CTAs
+        }
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(bar_tfull + 8 * a, 1);
+            mbar_init(bar_tempty + 8 * a, 2 * EPI_WARPS);  // every epilogue warp of both CTAs
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot_addr),
+                     "r"((uint32_t)TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int n_m2 = (R + 2 * BM - 1) / (2 * BM);
+    const int n_n = (C + BN - 1) / BN;
+    const int64_t n_tiles = (int64_t)n_m2 * n_n;
+    const int n_kblocks = (n_ksteps + BK / UK - 1) / (BK / UK);
+    const int64_t t_first = blockIdx.x >> 1, t_step = gridDim.x >> 1;
+
+    if (warp == 0) {
+        // ================================ TMA producer (both CTAs) =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int64_t t = t_first; t < n_tiles; t += t_step) {
+                int mi, ni;
+                tile_coords(t, n_m2, n_n, mi, ni);
+                const int m0 = mi * 2 * BM + (int)rank * BM;
+                const int n0 = ni * BN + (int)rank * (BN / 2);
+                for (int kb = 0; kb < n_kblocks; ++kb) {
+                    mbar_wait(bar_empty + 8 * stage, phase ^ 1u);
+                    const uint32_t full = bar_full + 8 * stage;
+                    const uint32_t st = base + stage * STAGE2_BYTES;
+                    tma_load_2d_pair(st, &tm_a_hi, full, kb * BK, m0);
+                    tma_load_2d_pair(st + A_BYTES, &tm_a_lo, full, kb * BK, m0);
+                    tma_load_2d_pair(st + 2 * A_BYTES, &tm_b_hi, full, kb * BK, n0);
+                    tma_load_2d_pair(st + 2 * A_BYTES + B_HALF_BYTES, &tm_b_lo, full, kb * BK, n0);
+                    if (leader) mbar_expect_tx(full, 2 * STAGE2_BYTES);
+                    else mbar_arrive_cluster(full, 0);
+                    if (++stage == STAGES2) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer (leader CTA only) =================
+        if (lane == 0 && leader) {
+            constexpr uint32_t idesc = umma_idesc_tf32(2 * BM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int64_t t = t_first; t < n_tiles; t += t_step) {
+                mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < n_kblocks; ++kb) {
+                    mbar_wait(bar_full + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint32_t st = base + stage * STAGE2_BYTES;
+                    const int ks = min(BK / UK, n_ksteps - kb * (BK / UK));
+                    for (int k = 0; k < ks; ++k) {
+                        const uint32_t koff = (uint32_t)(k * UK * 4);
+                        const uint64_t a_hi = umma_desc_k_sw128(st + koff);
+                        const uint64_t a_lo = umma_desc_k_sw128(st + A_BYTES + koff);
+                        const uint64_t b_hi = umma_desc_k_sw128(st + 2 * A_BYTES + koff);
+                        const uint64_t b_lo = umma_desc_k_sw128(st + 2 * A_BYTES + B_HALF_BYTES + koff);
+                        tc_mma_tf32_pair(d_tmem, a_hi, b_hi, idesc, (kb | k) != 0 ? 1u : 0u);
+                        tc_mma_tf32_pair(d_tmem, a_lo, b_hi, idesc, 1u);
+                        tc_mma_tf32_pair(d_tmem, a_hi, b_lo, idesc, 1u);
+                    }
+                    tc_commit_pair(bar_empty + 8 * stage);
+                    if (++stage == STAGES2) { stage = 0; phase ^= 1u; }
+                }
+                tc_commit_pair(bar_tfull + 8 * acc);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ================================ epilogue (own 128 rows, all 256 columns) ======
+        const int q = warp & 3;
+        const int half = (warp - 4) >> 2;
+        const uint32_t stage_buf = s_epi + (uint32_t)(warp - 4) * EPI_TILE_BYTES;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int64_t t = t_first; t < n_tiles; t += t_step) {
+            int mi, ni;
+            tile_coords(t, n_m2, n_n, mi, ni);
+            const int m0 = mi * 2 * BM + (int)rank * BM, n0 = ni * BN;
+            mbar_wait(bar_tfull + 8 * acc, acc_phase);
+            tc_fence_after();
+            const int row0 = m0 + q * 32;
+            bool any = false;
+            {
+                const int colbase = n0 + half * (BN / 2);
+                const int n_blocks = colbase >= C ? 0 : min(BN / 32, (C - colbase + 15) / 16);
+                impute_epi_tile<AS_INT, STORE>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2)),
+                                                   n_blocks, scale, any, stage_buf, lane, &tm_out, colbase, row0, R, C, out);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(bar_tempty + 8 * acc, 0);  // the leader issues the next MMAs
+            if (any && row_nonzero && row0 + lane < R) row_nonzero[row0 + lane] = 1;
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+        if (STORE == 1 && lane == 0) tma_store_wait_all();
+    }
+
+    // both CTAs must be done with each other's shared memory and barriers before either leaves
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
                      : "memory");
     }
 }
@@ -508,55 +837,101 @@ static int impute_prepare_regions(const float *d_A, int64_t R, int32_t K, int32_
     return 0;
 }
 
-// 2-D map over the output chunk (rows x C, 4-byte elements), box = 32 x 32, 128-byte swizzle
+// 2-D map over the output chunk (rows x C, 4-byte elements), box = 32 rows x 16 columns, 64-byte swizzle
 static int make_output_map(CUtensorMap *map, void *ptr, int64_t rows, int64_t C) {
     cgs_PFN_tensorMapEncodeTiled enc;
     CGS_TRY(get_tensor_map_encoder(&enc));
     cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)C * 4};
-    cuuint32_t box[2] = {32, 32};
+    cuuint32_t box[2] = {16, 32};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_INT32, 2, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) CGS_FAIL("cuTensorMapEncodeTiled (output) failed (" + std::to_string((int)r) + ")");
     return 0;
 }
 
-template <bool AS_INT, bool TMA_STORE>
+template <bool AS_INT, int STORE>
 static int impute_umma_launch_t(const CUtensorMap &ma_hi, const CUtensorMap &ma_lo, const CUtensorMap &mb_hi,
                                 const CUtensorMap &mb_lo, const CUtensorMap &mo, int32_t R, int32_t C, int32_t n_ksteps,
                                 float scale, void *d_out, uint8_t *d_row_nonzero, int grid, cudaStream_t stream) {
-    CGS_CUDA(cudaFuncSetAttribute(impute_umma_kernel<AS_INT, TMA_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CGS_CUDA(cudaFuncSetAttribute(impute_umma_kernel<AS_INT, STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   imp::SMEM_BYTES));
-    impute_umma_kernel<AS_INT, TMA_STORE><<<grid, imp::THREADS, imp::SMEM_BYTES, stream>>>(
+    impute_umma_kernel<AS_INT, STORE><<<grid, imp::THREADS, imp::SMEM_BYTES, stream>>>(
         ma_hi, ma_lo, mb_hi, mb_lo, mo, R, C, n_ksteps, scale, d_out, d_row_nonzero);
     CGS_CUDA(cudaGetLastError());
     return 0;
 }
 
+template <bool AS_INT, int STORE>
+static int impute_umma_pair_launch_t(const CUtensorMap &ma_hi, const CUtensorMap &ma_lo, const CUtensorMap &mb_hi,
+                                     const CUtensorMap &mb_lo, const CUtensorMap &mo, int32_t R, int32_t C, int32_t n_ksteps,
+                                     float scale, void *d_out, uint8_t *d_row_nonzero, int grid, cudaStream_t stream) {
+    CGS_CUDA(cudaFuncSetAttribute(impute_umma_pair_kernel<AS_INT, STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  imp::SMEM2_BYTES));
+    impute_umma_pair_kernel<AS_INT, STORE><<<grid, imp::THREADS, imp::SMEM2_BYTES, stream>>>(
+        ma_hi, ma_lo, mb_hi, mb_lo, mo, R, C, n_ksteps, scale, d_out, d_row_nonzero);
+    CGS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// Measured on B200 (20 000 x K x 200 000, GB/s written): TMA stores 4560 / 4280 / 3970 for K = 8 / 50 / 100,
+// 16-byte coalesced stores 4960 / 4690 / 3890; neither path is the limiter.
+constexpr int kImputeDefaultStore = 2;
+
 // out = trunc(scale * A B) from the prepared operands
 static int impute_umma_launch(const float *d_a_hi, const float *d_a_lo, const float *d_b_hi, const float *d_b_lo, int32_t R,
                               int32_t K, int32_t Kp, int32_t C, float scale, int as_int32, void *d_out,
                               uint8_t *d_row_nonzero, int num_sms, cudaStream_t stream) {
+    // CTA pairs (cta_group::2) by default; CGS_IMPUTE_1CTA=1 selects the single-CTA kernel
+    const char *e1 = getenv("CGS_IMPUTE_1CTA");
+    const bool pair = !(e1 && e1[0] == '1') && num_sms >= 2;
     CUtensorMap ma_hi, ma_lo, mb_hi, mb_lo, mo;
     CGS_TRY(make_operand_map(&ma_hi, d_a_hi, R, Kp, imp::BM));
     CGS_TRY(make_operand_map(&ma_lo, d_a_lo, R, Kp, imp::BM));
-    CGS_TRY(make_operand_map(&mb_hi, d_b_hi, C, Kp, imp::BN));
-    CGS_TRY(make_operand_map(&mb_lo, d_b_lo, C, Kp, imp::BN));
-    // TMA stores need 16-byte aligned rows
-    const bool tma_store = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_out) & 15) == 0);
-    if (tma_store) CGS_TRY(make_output_map(&mo, d_out, R, C));
+    CGS_TRY(make_operand_map(&mb_hi, d_b_hi, C, Kp, pair ? imp::BN / 2 : imp::BN));
+    CGS_TRY(make_operand_map(&mb_lo, d_b_lo, C, Kp, pair ? imp::BN / 2 : imp::BN));
+    // Output path: 16-byte aligned rows allow TMA stores and 16-byte coalesced stores.  CGS_IMPUTE_STORE
+    // (tuning knob) = scalar | tma | vec overrides the default.
+    const bool aligned = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_out) & 15) == 0);
+    int store = aligned ? kImputeDefaultStore : 0;
+    if (const char *e2 = getenv("CGS_IMPUTE_STORE")) {
+        const std::string v(e2);
+        if (v == "scalar") store = 0;
+        else if (aligned && v == "tma") store = 1;
+        else if (aligned && v == "vec") store = 2;
+    }
+    if (store == 1) CGS_TRY(make_output_map(&mo, d_out, R, C));
     else mo = ma_hi;  // unused
     if (d_row_nonzero) CGS_CUDA(cudaMemsetAsync(d_row_nonzero, 0, (size_t)R, stream));
-    const int64_t tiles = ceil_div(R, imp::BM) * ceil_div(C, imp::BN);
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, num_sms));
     const int32_t n_ksteps = (K + imp::UK - 1) / imp::UK;
-    if (as_int32) {
-        if (tma_store) return impute_umma_launch_t<true, true>(ma_hi, ma_lo, mb_hi, mb_lo, mo, R, C, n_ksteps, scale, d_out, d_row_nonzero, grid, stream);
-        return impute_umma_launch_t<true, false>(ma_hi, ma_lo, mb_hi, mb_lo, mo, R, C, n_ksteps, scale, d_out, d_row_nonzero, grid, stream);
+    int64_t tiles;
+    int grid;
+    if (pair) {
+        tiles = ceil_div(R, 2 * imp::BM) * ceil_div(C, imp::BN);
+        grid = 2 * (int)std::max<int64_t>(1, std::min<int64_t>(tiles, num_sms / 2));
+    } else {
+        tiles = ceil_div(R, imp::BM) * ceil_div(C, imp::BN);
+        grid = (int)std::max<int64_t>(1, std::min<int64_t>(tiles, num_sms));
     }
-    if (tma_store) return impute_umma_launch_t<false, true>(ma_hi, ma_lo, mb_hi, mb_lo, mo, R, C, n_ksteps, scale, d_out, d_row_nonzero, grid, stream);
-    return impute_umma_launch_t<false, false>(ma_hi, ma_lo, mb_hi, mb_lo, mo, R, C, n_ksteps, scale, d_out, d_row_nonzero, grid, stream);
+#define CGS_IMPUTE_DISPATCH(AS_INT_, STORE_)                                                                               \
+    (pair ? impute_umma_pair_launch_t<AS_INT_, STORE_>(ma_hi, ma_lo, mb_hi, mb_lo, mo, R, C, n_ksteps, scale, d_out,         \
+                                                       d_row_nonzero, grid, stream)                                         \
+          : impute_umma_launch_t<AS_INT_, STORE_>(ma_hi, ma_lo, mb_hi, mb_lo, mo, R, C, n_ksteps, scale, d_out,              \
+                                                  d_row_nonzero, grid, stream))
+    if (as_int32) {
+        switch (store) {
+            case 0: return CGS_IMPUTE_DISPATCH(true, 0);
+            case 1: return CGS_IMPUTE_DISPATCH(true, 1);
+            default: return CGS_IMPUTE_DISPATCH(true, 2);
+        }
+    }
+    switch (store) {
+        case 0: return CGS_IMPUTE_DISPATCH(false, 0);
+        case 1: return CGS_IMPUTE_DISPATCH(false, 1);
+        default: return CGS_IMPUTE_DISPATCH(false, 2);
+    }
+#undef CGS_IMPUTE_DISPATCH
 }
 
 static int impute_simt_launch(const float *d_A, const float *d_B, int32_t R, int32_t K, int32_t C, float scale, int as_int32,
