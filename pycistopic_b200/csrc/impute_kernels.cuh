@@ -340,7 +340,8 @@ __device__ __forceinline__ void tc_mma_tf32_pair(uint32_t d_tmem, uint64_t a_des
 // Epilogue of one 32 x 16 accumulator block held in v (lane = row): scale, convert, stage, store.
 // `reload_taddr` is the block's TMEM address (the exact-conversion path reads it again); `buf` is one of
 // the warp's two 2 KB staging tiles (32 rows x 64 bytes, 64-byte swizzle).
-// STORE: 0 = 4-byte coalesced stores (rows not 16-byte aligned), 1 = TMA store, 2 = 16-byte coalesced stores
+// STORE: 0 = 4-byte coalesced stores (rows not 16-byte aligned), 1 = TMA store (the warp's two staging tiles
+// alternate), 2 = 16-byte coalesced stores, 4 = TMA store that always uses the same staging tile
 template <bool AS_INT, int STORE>
 __device__ __forceinline__ void impute_epi_chunk(uint32_t (&v)[16], uint32_t reload_taddr, float scale, bool &any,
                                                  uint32_t buf, int lane, const CUtensorMap *tm_out, int col0, int row0,
@@ -381,9 +382,13 @@ __device__ __forceinline__ void impute_epi_chunk(uint32_t (&v)[16], uint32_t rel
             v[j] = __float_as_uint(fv);
         }
     }
-    if (STORE == 1) {
-        // the store that last used THIS staging tile (two stores ago) must have finished reading it
-        if (lane == 0) tma_store_wait_read_but_one();
+    if (STORE == 1 || STORE == 4) {
+        // the store that last used THIS staging tile must have finished reading it: two stores ago when the
+        // tiles alternate, the previous one otherwise
+        if (lane == 0) {
+            if (STORE == 1) tma_store_wait_read_but_one();
+            else tma_store_wait_read();
+        }
         __syncwarp();
         // row `lane`, four 16-byte pieces, 64-byte swizzle (matches the store's tensor map)
 #pragma unroll
@@ -451,6 +456,8 @@ __device__ __forceinline__ void impute_epi_chunk(uint32_t (&v)[16], uint32_t rel
 // The 32 rows x 128 columns an epilogue warp owns in a tile: eight 32 x 16 blocks.  The TMEM load of block
 // i + 1 is in flight while block i is converted, and the two staging tiles alternate so that a TMA store
 // reads one while the next block is written into the other.
+// STORE as above, or 3 = even blocks through 16-byte stores (staging tile 0), odd blocks through TMA stores
+// (staging tile 1): the load/store data path and the TMA engine each carry half of the output
 template <bool AS_INT, int STORE>
 __device__ __forceinline__ void impute_epi_tile(uint32_t taddr0, int n_blocks, float scale, bool &any, uint32_t stage_buf,
                                                 int lane, const CUtensorMap *tm_out, int col0, int row0, int R, int C,
@@ -465,11 +472,11 @@ __device__ __forceinline__ void impute_epi_tile(uint32_t taddr0, int n_blocks, f
             const uint32_t buf = stage_buf + (uint32_t)(ch & 1) * (EPI_TILE_BYTES / 2);
             if (ch & 1) {
                 if (ch + 1 < n_blocks) tmem_ld_32x16_issue(taddr0 + (uint32_t)(ch + 1) * 16u, va);
-                impute_epi_chunk<AS_INT, STORE>(vb, taddr0 + (uint32_t)ch * 16u, scale, any, buf, lane,
+                impute_epi_chunk<AS_INT, (STORE == 3 ? 4 : STORE)>(vb, taddr0 + (uint32_t)ch * 16u, scale, any, buf, lane,
                                                                    tm_out, col0 + ch * 16, row0, R, C, out);
             } else {
                 if (ch + 1 < n_blocks) tmem_ld_32x16_issue(taddr0 + (uint32_t)(ch + 1) * 16u, vb);
-                impute_epi_chunk<AS_INT, STORE>(va, taddr0 + (uint32_t)ch * 16u, scale, any, buf, lane,
+                impute_epi_chunk<AS_INT, (STORE == 3 ? 2 : STORE)>(va, taddr0 + (uint32_t)ch * 16u, scale, any, buf, lane,
                                                                    tm_out, col0 + ch * 16, row0, R, C, out);
             }
         }
@@ -613,7 +620,7 @@ impute_umma_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_con
             if (any && row_nonzero && row0 + lane < R) row_nonzero[row0 + lane] = 1;
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
-        if (STORE == 1 && lane == 0) tma_store_wait_all();
+        if ((STORE == 1 || STORE == 3) && lane == 0) tma_store_wait_all();
     }
 
     tc_fence_before();
@@ -769,7 +776,7 @@ impute_umma_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __gri
             if (any && row_nonzero && row0 + lane < R) row_nonzero[row0 + lane] = 1;
             if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
-        if (STORE == 1 && lane == 0) tma_store_wait_all();
+        if ((STORE == 1 || STORE == 3) && lane == 0) tma_store_wait_all();
     }
 
     // both CTAs must be done with each other's shared memory and barriers before either leaves
@@ -892,7 +899,7 @@ static int impute_umma_launch(const float *d_a_hi, const float *d_a_lo, const fl
     CGS_TRY(make_operand_map(&mb_hi, d_b_hi, C, Kp, pair ? imp::BN / 2 : imp::BN));
     CGS_TRY(make_operand_map(&mb_lo, d_b_lo, C, Kp, pair ? imp::BN / 2 : imp::BN));
     // Output path: 16-byte aligned rows allow TMA stores and 16-byte coalesced stores.  CGS_IMPUTE_STORE
-    // (tuning knob) = scalar | tma | vec overrides the default.
+    // (tuning knob) = scalar | tma | vec | mix overrides the default.
     const bool aligned = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_out) & 15) == 0);
     int store = aligned ? kImputeDefaultStore : 0;
     if (const char *e2 = getenv("CGS_IMPUTE_STORE")) {
@@ -900,8 +907,9 @@ static int impute_umma_launch(const float *d_a_hi, const float *d_a_lo, const fl
         if (v == "scalar") store = 0;
         else if (aligned && v == "tma") store = 1;
         else if (aligned && v == "vec") store = 2;
+        else if (aligned && v == "mix") store = 3;
     }
-    if (store == 1) CGS_TRY(make_output_map(&mo, d_out, R, C));
+    if (store == 1 || store == 3) CGS_TRY(make_output_map(&mo, d_out, R, C));
     else mo = ma_hi;  // unused
     if (d_row_nonzero) CGS_CUDA(cudaMemsetAsync(d_row_nonzero, 0, (size_t)R, stream));
     const int32_t n_ksteps = (K + imp::UK - 1) / imp::UK;
@@ -923,13 +931,15 @@ static int impute_umma_launch(const float *d_a_hi, const float *d_a_lo, const fl
         switch (store) {
             case 0: return CGS_IMPUTE_DISPATCH(true, 0);
             case 1: return CGS_IMPUTE_DISPATCH(true, 1);
-            default: return CGS_IMPUTE_DISPATCH(true, 2);
+            case 2: return CGS_IMPUTE_DISPATCH(true, 2);
+            default: return CGS_IMPUTE_DISPATCH(true, 3);
         }
     }
     switch (store) {
         case 0: return CGS_IMPUTE_DISPATCH(false, 0);
         case 1: return CGS_IMPUTE_DISPATCH(false, 1);
-        default: return CGS_IMPUTE_DISPATCH(false, 2);
+        case 2: return CGS_IMPUTE_DISPATCH(false, 2);
+        default: return CGS_IMPUTE_DISPATCH(false, 3);
     }
 #undef CGS_IMPUTE_DISPATCH
 }
