@@ -333,3 +333,48 @@ def test_impute_tensor_core_kernel(R, K, C):
     np.testing.assert_allclose(out_f, simt_f, rtol=1e-5, atol=1e-12)
     simt_i, sfl_i = run(1, 1e6, True)
     assert np.abs(out_i.astype(np.int64) - simt_i.astype(np.int64)).max() <= 1
+
+
+@pytest.mark.parametrize("K", [10, 50])
+def test_full_size_c2_invariants(K):
+    """BASELINE.json configs[1] at full size (10 000 cells x 200 000 regions, 6.5e7 tokens): the oracle cannot
+    run here in seconds, so the size-independent properties are checked on the device -- after the sweeps
+    the three count tables are exactly the histograms of z (bit-exact bookkeeping under 6.5e7 concurrent
+    reductions per sweep), every total equals the token count, the log-likelihood rises from the
+    z = i mod K start, and a second chain with another seed ends within 1 % of the first."""
+    import torch
+    from pycistopic_b200 import Corpus, DeviceModel
+    from pycistopic_b200.synth import SHAPES, planted_topic_tokens
+    dev = torch.device("cuda:0")
+    D, W, dens = SHAPES["C2"]
+    cell, region = planted_topic_tokens(D, W, dens, seed=1234, device=dev)
+    cnt = torch.bincount(cell, minlength=D)
+    cell_ptr = torch.zeros(D + 1, dtype=torch.int64, device=dev)
+    cell_ptr[1:] = torch.cumsum(cnt, 0)
+    tok = region.to(torch.int32).contiguous()
+    N = tok.numel()
+    corpus = Corpus.from_device_tokens(cell_ptr.data_ptr(), tok.data_ptr(), D, W, N, keepalive=(cell_ptr, tok))
+    lls = []
+    for seed in (555, 7):
+        model = DeviceModel(corpus, K, 50.0 / K, 0.1, seed=seed)
+        model.init()
+        ll0 = model.loglikelihood()
+        model.sweep(12)
+        lls.append(model.loglikelihood())
+        assert lls[-1] > ll0
+        if seed == 555:
+            z = torch.from_numpy(model.get_z().astype(np.int64)).to(dev)
+            nzw, ndz, nz = model.counts()
+            assert int(z.min()) >= 0 and int(z.max()) < K
+            ndz_ref = torch.zeros(D * K, dtype=torch.int64, device=dev).scatter_add_(
+                0, cell * K + z, torch.ones_like(z)).view(D, K)
+            nzw_ref = torch.zeros(K * W, dtype=torch.int64, device=dev).scatter_add_(
+                0, z * W + region, torch.ones_like(z)).view(K, W)
+            assert np.array_equal(ndz_ref.cpu().numpy(), ndz)
+            assert np.array_equal(nzw_ref.cpu().numpy(), nzw)
+            assert np.array_equal(torch.bincount(z, minlength=K).cpu().numpy(), nz)
+            assert int(nz.sum()) == N and int(nzw.sum()) == N and int(ndz.sum()) == N
+            assert np.array_equal(ndz.sum(axis=1), cnt.cpu().numpy())
+        model.close()
+    assert abs(lls[0] - lls[1]) <= 0.01 * abs(lls[0])
+    corpus.close()
