@@ -403,7 +403,7 @@ int cgs_corpus_export_tokens(const cgs_corpus *c, int32_t *WS, int32_t *DS) {
 //         ~ 0.08 % per 1 % of all tokens in flight  +  0.28 % x (fraction of cells open at once),
 // while tokens of ONE cell sampled together are harmless up to ~8 % of the cell at K = 10 but not at
 // K = 40 on short cells (see cap_cell below).  So: wide CTAs, in-cell concurrency <=
-// mean_cell_tokens / 64, open cells <= D / 8, tokens in flight <= N / 128.
+// mean_cell_tokens / 16 (K <= 10) ... / 64 (K >= 40), open cells <= D / 8, tokens in flight <= N / 128.
 // At benchmark scale (D >= 10^4) none of the caps binds before the GPU is full.
 static void pick_sweep_shape(int32_t Kp, double n_tokens, double n_cells, int *tpt, int *ch, int *threads,
                              int *auto_blocks) {
@@ -415,11 +415,19 @@ static void pick_sweep_shape(int32_t Kp, double n_tokens, double n_cells, int *t
     int t = 1;
     while (t * 4 < chunks) t <<= 1;
     if (chunks >= 2 && t < 2) t = 2;
-    // K = 40 on 210-token cells: 8 tokens of a cell per step lag the trace by 0.4 % even with ONE cell
-    // open, 1-2 tokens per step by 0.1 % (profiles/r1_trace_small40_concurrency.txt)
-    const int cap_cell = (int)std::max(1.0, mean_cell / 64.0);
+    // ... and half the lanes with 5 chunks each when that covers the row (K = 33..40: 1.78-1.84 ms per sweep
+    // on C2 with 2 lanes x 5 chunks, 2.04 ms with 4 lanes x 3; 6 and 7 chunks per lane do not pay)
+    if (t >= 4 && chunks <= 5 * (t / 2)) t /= 2;
+    // In-cell concurrency: at K = 10 up to 8 % of a cell sampled together is harmless (C1), at
+    // K = 40 on 210-token cells 8 tokens per step (3.8 %) lag the trace by 0.4 % even with ONE cell open and
+    // 1-2 tokens per step by 0.1 % (profiles/r1_trace_small40_concurrency.txt): 1/16 of a cell up to
+    // K = 10, shrinking to 1/64 from K = 40.
+    const double cell_div = std::min(64.0, std::max(16.0, 1.6 * (double)Kp));
+    const int cap_cell = (int)std::max(1.0, mean_cell / cell_div);
     while (t < 32 && 32 / t > cap_cell) t <<= 1;
-    int warps = 8;
+    // 4 warps per cell measure 1-4 % faster than 8 for every multi-lane shape (more, smaller CTAs per SM);
+    // the one-lane shape (K <= 4) wants 8
+    int warps = t == 1 ? 8 : 4;
     while (warps > 1 && warps * (32 / t) > cap_cell) warps >>= 1;
     const double in_flight_per_cta = warps * (32.0 / t);
     const double by_cells = std::max(1.0, n_cells / 8.0);

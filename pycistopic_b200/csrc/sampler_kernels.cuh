@@ -267,17 +267,11 @@ __device__ __forceinline__ int sweep_step(int4 (&buf)[CH], const char *nwk_lane,
     return zn;
 }
 
-// Resident CTAs per SM the register budget is set for (measured on B200: occupancy beats the
-// few spills it costs; see profiles/).
-#ifndef CGS_SWEEP_MINB_NARROW
-#define CGS_SWEEP_MINB_NARROW 4  // CH <= 4
-#endif
-#ifndef CGS_SWEEP_MINB_WIDE
-#define CGS_SWEEP_MINB_WIDE 2  // CH >= 5
-#endif
-
+// Resident CTAs per SM the register budget is set for (measured on B200: occupancy beats the few
+// spills it costs; profiles/r1_shape_scan_*.txt): 4 x 8 warps at 64 registers up to 4 chunks per lane,
+// 3 x 8 warps at 80 registers for 5-6 chunks, 2 x 8 warps beyond.
 template <int TPT, int CH>
-__global__ void __launch_bounds__(kSweepThreads, (CH <= 4 ? CGS_SWEEP_MINB_NARROW : CGS_SWEEP_MINB_WIDE))
+__global__ void __launch_bounds__(kSweepThreads, (CH <= 4 ? 4 : CH <= 6 ? 3 : 2))
 sweep_kernel(const SweepParams p) {
     constexpr int KS = TPT * CH * 4;  // topic slots covered by one token group
     constexpr int KSB = KS * 4;

@@ -24,11 +24,13 @@ corpus = Corpus.from_device_tokens(cell_ptr.data_ptr(), tok.data_ptr(), D, W, N,
 ts = torch.cuda.Stream(); torch.cuda.set_stream(ts)
 print("lib", os.environ.get("CGS_B200_LIB", "default"), "N", N, flush=True)
 for case in args.cases.split(","):
-    K, lanes = [int(x) for x in case.split(":")]
+    parts = [int(x) for x in case.split(":")]
+    K, lanes = parts[0], parts[1]
+    warps = parts[2] if len(parts) > 2 else 8
     m = DeviceModel(corpus, K, 50.0 / K, 0.1, seed=555, stream=ts.cuda_stream)
     try:
         if lanes > 0:
-            m.set_sweep_shape(lanes, 8)
+            m.set_sweep_shape(lanes, warps)
     except Exception as e:
         print(json.dumps({"K": K, "lanes": lanes, "error": str(e)[:80]})); m.close(); continue
     m.init()
