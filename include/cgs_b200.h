@@ -185,6 +185,17 @@ int cgs_impute_plan_chunk_device(cgs_impute_plan *plan, const float *d_topic_reg
                                  void *stream);
 int cgs_impute_plan_launch_count(const cgs_impute_plan *plan, int64_t *launches);
 
+/* ---- normalize_scores (diff_features.py:511-574; inner function :540-548) ---------------------- */
+/* out = log1p( x / (colsum(x) / scale_factor) ), x = n_rows (regions) x n_cols (cells) row-major.
+ * dtype: 0 = int32 (out is float64, column sums exact in int64, as NumPy), 1 = float32 (out float32),
+ * 2 = float64 (out float64).  Host pointers; the whole matrix and its result must fit on the device. */
+int cgs_normalize_scores(int device, const void *x, int dtype, int64_t n_rows, int64_t n_cols,
+                         double scale_factor, void *out);
+/* Device-resident variant; d_colsum_scratch holds 8 * n_cols bytes and returns the per-cell totals
+ * (int64 for dtype 0, float64 otherwise). */
+int cgs_normalize_scores_device(int device, const void *d_x, int dtype, int64_t n_rows, int64_t n_cols,
+                                double scale_factor, void *d_out, void *d_colsum_scratch, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

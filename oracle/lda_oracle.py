@@ -315,3 +315,12 @@ def model_metrics(model, X, alpha_raw, eta_raw, top_topics_coh=5, loglikelihood_
     if loglikelihood_fn is not None:
         out["loglikelihood"] = loglikelihood_fn(model.nzw_, model.ndz_, alpha_raw, eta_raw)
     return out
+
+
+def normalized_scores(imputed_acc, scale_factor):
+    """CPU restatement of ``calculate_normalized_scores`` (diff_features.py:540-548): per-cell totals over
+    the regions, ``X / (totals / scale_factor)``, ``log1p``.  Pinned by tests/golden/impute.npz (norm0,
+    norm5), which the reference's own nested function produced."""
+    x = np.asarray(imputed_acc)
+    normalized = x / (np.sum(x, axis=0) / scale_factor)
+    return np.log1p(normalized, out=normalized)

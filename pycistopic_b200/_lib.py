@@ -80,6 +80,10 @@ SIGNATURES = {
     "cgs_impute_plan_chunk_device": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int32, ctypes.c_float, ctypes.c_int,
                                                     c_vp, c_vp, c_vp]),
     "cgs_impute_plan_launch_count": (ctypes.c_int, [c_vp, c_i64p]),
+    "cgs_normalize_scores": (ctypes.c_int, [ctypes.c_int, c_vp, ctypes.c_int, ctypes.c_int64, ctypes.c_int64,
+                                            ctypes.c_double, c_vp]),
+    "cgs_normalize_scores_device": (ctypes.c_int, [ctypes.c_int, c_vp, ctypes.c_int, ctypes.c_int64, ctypes.c_int64,
+                                                   ctypes.c_double, c_vp, c_vp, c_vp]),
 }
 
 

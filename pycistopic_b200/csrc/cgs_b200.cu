@@ -6,11 +6,13 @@
 #include <algorithm>
 #include <chrono>
 #include <numeric>
+#include <type_traits>
 #include <vector>
 
 #include "common.cuh"
 #include "corpus_kernels.cuh"
 #include "impute_kernels.cuh"
+#include "normalize_kernels.cuh"
 #include "sampler_kernels.cuh"
 #include "stats_kernels.cuh"
 
@@ -1125,6 +1127,54 @@ int cgs_impute_chunk(int device, const float *topic_region, const float *cell_to
     CGS_TRY(cgs_impute_plan_create(&p, device, cell_topic, 0, n_topics, n_cells, nullptr));
     int rc = cgs_impute_plan_chunk(p, topic_region, n_regions, scale, as_int32, out, row_nonzero);
     cgs_impute_plan_destroy(p);
+    return rc;
+}
+
+// ---- normalize_scores ---------------------------------------------------------------------------
+int cgs_normalize_scores_device(int device, const void *d_x, int dtype, int64_t n_rows, int64_t n_cols,
+                                double scale_factor, void *d_out, void *d_colsum_scratch, void *stream_) {
+    if (!d_x || !d_out || !d_colsum_scratch) CGS_FAIL("NULL argument");
+    if (n_rows <= 0 || n_cols <= 0) CGS_FAIL("empty matrix");
+    if (!(scale_factor != 0.0)) CGS_FAIL("scale_factor must not be zero");
+    DeviceGuard g(device);
+    if (!g.ok) CGS_FAIL("cannot select CUDA device");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    switch (dtype) {
+        case 0: return normalize_launch<int32_t, double>((const int32_t *)d_x, n_rows, n_cols, scale_factor, d_colsum_scratch,
+                                                         (double *)d_out, stream);
+        case 1: return normalize_launch<float, float>((const float *)d_x, n_rows, n_cols, scale_factor, d_colsum_scratch,
+                                                      (float *)d_out, stream);
+        case 2: return normalize_launch<double, double>((const double *)d_x, n_rows, n_cols, scale_factor, d_colsum_scratch,
+                                                        (double *)d_out, stream);
+    }
+    CGS_FAIL("dtype must be 0 (int32), 1 (float32) or 2 (float64)");
+}
+
+int cgs_normalize_scores(int device, const void *x, int dtype, int64_t n_rows, int64_t n_cols, double scale_factor,
+                         void *out) {
+    if (!x || !out) CGS_FAIL("NULL argument");
+    if (n_rows <= 0 || n_cols <= 0) CGS_FAIL("empty matrix");
+    if (dtype < 0 || dtype > 2) CGS_FAIL("dtype must be 0 (int32), 1 (float32) or 2 (float64)");
+    DeviceGuard g(device);
+    if (!g.ok) CGS_FAIL("cannot select CUDA device");
+    CGS_TRY(configure_pool(device));
+    const size_t in_elem = dtype == 2 ? 8 : 4, out_elem = dtype == 1 ? 4 : 8;
+    const size_t n = (size_t)n_rows * (size_t)n_cols;
+    uint8_t *d_x = nullptr, *d_o = nullptr, *d_s = nullptr;
+    cudaStream_t stream = nullptr;
+    CGS_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    int rc = [&]() -> int {
+        CGS_TRY(dmalloc(&d_x, n * in_elem, stream));
+        CGS_TRY(dmalloc(&d_o, n * out_elem, stream));
+        CGS_TRY(dmalloc(&d_s, (size_t)n_cols * 8, stream));
+        CGS_CUDA(cudaMemcpyAsync(d_x, x, n * in_elem, cudaMemcpyHostToDevice, stream));
+        CGS_TRY(cgs_normalize_scores_device(device, d_x, dtype, n_rows, n_cols, scale_factor, d_o, d_s, stream));
+        CGS_CUDA(cudaMemcpyAsync(out, d_o, n * out_elem, cudaMemcpyDeviceToHost, stream));
+        CGS_CUDA(cudaStreamSynchronize(stream));
+        return 0;
+    }();
+    dfree(d_x, stream); dfree(d_o, stream); dfree(d_s, stream);
+    cudaStreamDestroy(stream);
     return rc;
 }
 

@@ -128,15 +128,34 @@ def impute_accessibility(
     return imputed_acc_obj
 
 
-def calculate_normalized_scores(imputed_acc, scale_factor):
-    """diff_features.py:540-548: X / (colsum(X) / scale_factor), then log1p in place."""
-    normalized_acc = imputed_acc / (np.sum(imputed_acc, axis=0) / scale_factor)
-    return np.log1p(normalized_acc, out=normalized_acc)
+_NORM_DTYPES = {np.dtype(np.int32): (0, np.float64), np.dtype(np.float32): (1, np.float32),
+                np.dtype(np.float64): (2, np.float64)}
+
+
+def calculate_normalized_scores(imputed_acc, scale_factor, device=0):
+    """diff_features.py:540-548: ``X / (colsum(X) / scale_factor)``, then ``log1p`` -- on the GPU
+    (``cgs_normalize_scores``: one pass for the per-cell totals, one for the quotient and log1p, fp64 in the
+    reference's operation order).  int32 and float64 input give float64, float32 gives float32, as NumPy
+    does; other dtypes are converted to float64 first, which is what NumPy's true division produces."""
+    _lib.require_device()
+    x = np.asarray(imputed_acc)
+    if x.ndim != 2:
+        raise ValueError("imputed_acc must be a 2-D array (regions x cells)")
+    if x.dtype not in _NORM_DTYPES:
+        x = x.astype(np.float64)
+    x = np.ascontiguousarray(x)
+    code, out_dtype = _NORM_DTYPES[x.dtype]
+    out = np.empty(x.shape, dtype=out_dtype)
+    if x.size == 0:
+        return out
+    check(_lib.load().cgs_normalize_scores(device, x.ctypes.data_as(c_vp), code, x.shape[0], x.shape[1],
+                                           float(scale_factor), out.ctypes.data_as(c_vp)))
+    return out
 
 
 def normalize_scores(imputed_acc, scale_factor=10 ** 4):
-    """Log-normalise imputation data (diff_features.py:511-574); host NumPy, as in the
-    reference (next-row N1 in SURVEY.md section 8f moves it into the GEMM epilogue)."""
+    """Log-normalise imputation data (diff_features.py:511-574); the arithmetic runs on the GPU
+    (SURVEY.md section 8f, row N1)."""
     log = _logger()
     log.info("Normalizing imputed data")
     if isinstance(imputed_acc, CistopicImputedFeatures):

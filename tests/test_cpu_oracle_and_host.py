@@ -158,16 +158,14 @@ def test_loglikelihood_compat_matches_live_reference():
         assert pm.loglikelihood_compat(nzw, ndz, alpha, eta) == pytest.approx(f(nzw, ndz, alpha, eta), rel=1e-11, abs=1e-8)
 
 
-def test_normalize_scores_matches_reference_golden():
-    from pycistopic_b200.diff_features import CistopicImputedFeatures, normalize_scores
+def test_normalized_scores_oracle_matches_reference_golden():
+    """The oracle restatement of calculate_normalized_scores against the vectors the reference's own function
+    produced (the product path runs on the GPU: tests/test_gpu_parity.py::test_normalize_scores_*)."""
     g = np.load(os.path.join(GOLD, "impute.npz"))
     for i in (0, 5):
         out = g[f"out{i}"]
-        obj = CistopicImputedFeatures(out, [str(j) for j in range(out.shape[0])], [str(j) for j in range(out.shape[1])], "p")
-        res = normalize_scores(obj, scale_factor=10 ** 4)
-        np.testing.assert_allclose(res.mtx, g[f"norm{i}"], rtol=1e-12)
-        df = normalize_scores(pd.DataFrame(out.astype(np.float64)), scale_factor=10 ** 4)
-        np.testing.assert_allclose(df.to_numpy(), g[f"norm{i}"], rtol=1e-12)
+        np.testing.assert_allclose(lo.normalized_scores(out.astype(np.float64), 10 ** 4), g[f"norm{i}"], rtol=1e-13)
+        np.testing.assert_allclose(lo.normalized_scores(out, 10 ** 4), g[f"norm{i}"], rtol=1e-6)
 
 
 # ---- metrics: product implementation vs oracle restatement -----------------------------------------

@@ -3,6 +3,8 @@
 Integer/index work is bit-exact; the stochastic sampler is compared through the true
 log-likelihood trace and the Mimno coherence within 1 % (BASELINE.json north_star).
 """
+import os
+
 import numpy as np
 import pytest
 import scipy.sparse as sp
@@ -11,6 +13,7 @@ from oracle import lda_oracle as lo
 from pycistopic_b200.synth import make_binary_matrix
 
 pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.fixture(scope="module")
@@ -150,9 +153,10 @@ def test_supplied_z_counts_bit_exact(small, K):
     corpus.close()
 
 
-@pytest.mark.parametrize("K", [2, 7, 16, 24, 50, 100, 200, 500])
+@pytest.mark.parametrize("K", [1, 2, 7, 16, 24, 36, 50, 70, 100, 200, 300, 500, 512])
 def test_sweep_keeps_counts_consistent(small, K):
-    """After any number of sweeps the three tables are exactly the histograms of z."""
+    """After any number of sweeps the three tables are exactly the histograms of z (every kernel shape the
+    shape rule picks: 1 / 2 / 4 / 8 / 16 / 32 lanes per token, 1-5 chunks per lane, up to cgs_max_topics())."""
     from pycistopic_b200 import DeviceModel
     m, _, _ = small
     corpus, X = _corpus_pair(m)
@@ -167,8 +171,33 @@ def test_sweep_keeps_counts_consistent(small, K):
     onzw, ondz, onz = lo.counts_from_z(WS, DS, z, X.shape[0], X.shape[1], K)
     assert np.array_equal(nzw, onzw) and np.array_equal(ndz, ondz) and np.array_equal(nz, onz)
     assert nz.sum() == len(WS)
+    if K > 1:
+        assert model.loglikelihood() > ll0
+        assert not np.array_equal(z, np.arange(len(WS)) % K)
+    model.close()
+    corpus.close()
+
+
+@pytest.mark.parametrize("K,lanes,warps", [(4, 1, 8), (10, 2, 4), (30, 2, 4), (36, 2, 4), (40, 2, 8), (50, 4, 4),
+                                           (70, 4, 4), (100, 8, 4), (100, 4, 2), (300, 16, 4), (512, 32, 8)])
+def test_sweep_explicit_shapes_keep_counts_consistent(small, K, lanes, warps):
+    """The benchmark-scale kernel shapes (which the concurrency caps never pick on a corpus this small),
+    forced through cgs_model_set_sweep_shape: bookkeeping stays exact, the chain still improves."""
+    from pycistopic_b200 import DeviceModel
+    m, _, _ = small
+    corpus, X = _corpus_pair(m)
+    WS, DS = lo.matrix_to_lists(X)
+    model = DeviceModel(corpus, K, 50.0 / K, 0.1, seed=3)
+    model.set_sweep_shape(lanes, warps)
+    assert model.sweep_shape["lanes_per_token"] == lanes and model.sweep_shape["warps_per_cell"] == warps
+    model.init()
+    ll0 = model.loglikelihood()
+    model.sweep(9)
+    z = model.get_z()
+    nzw, ndz, nz = model.counts()
+    onzw, ondz, onz = lo.counts_from_z(WS, DS, z, X.shape[0], X.shape[1], K)
+    assert np.array_equal(nzw, onzw) and np.array_equal(ndz, ondz) and np.array_equal(nz, onz)
     assert model.loglikelihood() > ll0
-    assert not np.array_equal(z, np.arange(len(WS)) % K)
     model.close()
     corpus.close()
 
@@ -378,3 +407,39 @@ def test_full_size_c2_invariants(K):
         model.close()
     assert abs(lls[0] - lls[1]) <= 0.01 * abs(lls[0])
     corpus.close()
+
+
+# ---- normalize_scores -------------------------------------------------------
+def test_normalize_scores_matches_reference_golden():
+    """Product path (GPU) against the vectors the reference's own calculate_normalized_scores produced."""
+    import pandas as pd
+    from pycistopic_b200.diff_features import CistopicImputedFeatures, normalize_scores
+    g = np.load(os.path.join(ROOT, "tests", "golden", "impute.npz"))
+    for i in (0, 5):
+        out = g[f"out{i}"]
+        obj = CistopicImputedFeatures(out.astype(np.float64), [str(j) for j in range(out.shape[0])],
+                                      [str(j) for j in range(out.shape[1])], "p")
+        res = normalize_scores(obj, scale_factor=10 ** 4)
+        assert res.mtx.dtype == np.float64
+        np.testing.assert_allclose(res.mtx, g[f"norm{i}"], rtol=1e-12)
+        df = normalize_scores(pd.DataFrame(out.astype(np.float64)), scale_factor=10 ** 4)
+        np.testing.assert_allclose(df.to_numpy(), g[f"norm{i}"], rtol=1e-12)
+
+
+@pytest.mark.parametrize("dtype,rtol", [(np.int32, 1e-12), (np.float64, 1e-12), (np.float32, 2e-6)])
+@pytest.mark.parametrize("R,C", [(1, 1), (513, 257), (1500, 1000), (37, 2049)])
+def test_normalize_scores_matches_oracle(dtype, rtol, R, C):
+    """int32 (the imputed counts: exact int64 cell totals, fp64 result), fp64 and fp32 inputs, ragged sizes
+    around the 256-cell x 512-region CTA footprint, against the oracle restatement."""
+    from pycistopic_b200.diff_features import calculate_normalized_scores
+    rng = np.random.default_rng(R * 31 + C)
+    if dtype == np.int32:
+        x = rng.integers(0, 2_000_000, (R, C)).astype(np.int32)
+        x[rng.random((R, C)) < 0.3] = 0
+        x[0, :] = np.maximum(x[0, :], 1)  # every cell has a non-zero total, as imputed data has
+    else:
+        x = (rng.random((R, C)) * 1e3 + 1e-3).astype(dtype)
+    out = calculate_normalized_scores(x, 10 ** 4)
+    ref = lo.normalized_scores(x, 10 ** 4)
+    assert out.dtype == ref.dtype and out.shape == ref.shape
+    np.testing.assert_allclose(out, ref, rtol=rtol, atol=0)
