@@ -407,10 +407,9 @@ int cgs_corpus_export_tokens(const cgs_corpus *c, int32_t *WS, int32_t *DS) {
 // K = 40 on short cells (see cap_cell below).  So: wide CTAs, in-cell concurrency <=
 // mean_cell_tokens / 16 (K <= 10) ... / 64 (K >= 40), open cells <= D / 8, tokens in flight <= N / 128.
 // At benchmark scale (D >= 10^4) none of the caps binds before the GPU is full.
-static void pick_sweep_shape(int32_t Kp, double n_tokens, double n_cells, int *tpt, int *ch, int *threads,
-                             int *auto_blocks) {
-    const int chunks = Kp / 4;
-    const double mean_cell = n_tokens / std::max(1.0, n_cells);
+// Lanes per token the throughput alone asks for (a function of K only).
+static int lanes_for_topics(int32_t K) {
+    const int chunks = (K + 3) / 4;
     // fewest lanes per token with at most 4 chunks per lane, but two lanes as soon as there are two
     // chunks: one lane per token makes every row load and every count update an uncoalesced 32-address
     // access (measured on C2: K = 10 takes 0.93 ms per sweep with 2 lanes, 1.13 ms with 1)
@@ -420,6 +419,22 @@ static void pick_sweep_shape(int32_t Kp, double n_tokens, double n_cells, int *t
     // ... and half the lanes with 5 chunks each when that covers the row (K = 33..40: 1.78-1.84 ms per sweep
     // on C2 with 2 lanes x 5 chunks, 2.04 ms with 4 lanes x 3; 6 and 7 chunks per lane do not pay)
     if (t >= 4 && chunks <= 5 * (t / 2)) t /= 2;
+    return t;
+}
+
+// Row stride of n_wk / n_dk in counts: K rounded up so that the 16-byte-per-lane piece a token group loads
+// (lanes x 16 B, at most 128 B) never straddles a 32-byte sector or a 128-byte line.  Depends on K only, so
+// every rank of a sharded model uses the same layout.
+static int32_t padded_topics(int32_t K) {
+    const int piece = 4 * std::min(8, lanes_for_topics(K));  // counts per group load
+    return (K + piece - 1) / piece * piece;
+}
+
+static void pick_sweep_shape(int32_t K, int32_t Kp, double n_tokens, double n_cells, int *tpt, int *ch, int *threads,
+                             int *auto_blocks) {
+    const int chunks = (K + 3) / 4;
+    const double mean_cell = n_tokens / std::max(1.0, n_cells);
+    int t = lanes_for_topics(K);
     // In-cell concurrency: at K = 10 up to 8 % of a cell sampled together is harmless (C1), at
     // K = 40 on 210-token cells 8 tokens per step (3.8 %) lag the trace by 0.4 % even with ONE cell open and
     // 1-2 tokens per step by 0.1 % (profiles/r1_trace_small40_concurrency.txt): 1/16 of a cell up to
@@ -454,11 +469,11 @@ int cgs_model_create(cgs_model **out, cgs_corpus *corpus, int32_t n_topics, doub
     corpus->n_models++;
     int rc = [&]() -> int {
         m->K = n_topics;
-        m->Kp = (n_topics + 3) & ~3;
+        m->Kp = padded_topics(n_topics);
         m->alpha = alpha;
         m->eta = eta;
         m->seed = seed;
-        pick_sweep_shape(m->Kp, (double)corpus->n_tokens, (double)corpus->n_cells, &m->tpt, &m->ch, &m->threads,
+        pick_sweep_shape(m->K, m->Kp, (double)corpus->n_tokens, (double)corpus->n_cells, &m->tpt, &m->ch, &m->threads,
                          &m->auto_blocks);
         if (stream) {
             m->stream = (cudaStream_t)stream;
@@ -696,7 +711,7 @@ int cgs_model_set_sweep_shape(cgs_model *m, int32_t lanes_per_token, int32_t war
     if (!(t == 1 || t == 2 || t == 4 || t == 8 || t == 16 || t == 32)) CGS_FAIL("lanes_per_token must be a power of two <= 32");
     if (!(warps_per_cell == 1 || warps_per_cell == 2 || warps_per_cell == 4 || warps_per_cell == 8))
         CGS_FAIL("warps_per_cell must be 1, 2, 4 or 8");
-    const int chunks = m->Kp / 4;
+    const int chunks = (m->K + 3) / 4;
     const int ch = (chunks + t - 1) / t;
     if (ch > kMaxChunksPerLane || t * ch * 4 > kMaxTopics) CGS_FAIL("lanes_per_token too small for this n_topics");
     m->tpt = t;

@@ -291,7 +291,8 @@ sweep_kernel(const SweepParams p) {
     const int K = p.K, Kp = p.Kp;
     const float alpha = p.alpha, eta = p.eta;
     const uint32_t rowbytes = (uint32_t)Kp * 4u;
-    const int lim = ((Kp >> 2) - sub + TPT - 1) >> log2_tpt<TPT>();  // register chunks of this lane inside the row
+    // register chunks of this lane that hold topics (the row stride Kp may be padded beyond them)
+    const int lim = (((K + 3) >> 2) - sub + TPT - 1) >> log2_tpt<TPT>();
     const char *nwk_lane = reinterpret_cast<const char *>(p.n_wk) + sub * 16;
 
     int4 buf[CH];  // the n_wk row chunks of the group sampled next
