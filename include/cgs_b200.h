@@ -98,13 +98,20 @@ int cgs_model_sweep(cgs_model *m, int32_t n_sweeps);
  * longest-first, so the parts are token-balanced).  Calling it for part = 0 .. n_parts-1 is one
  * sweep; AD-LDA uses it to exchange n_wk deltas several times per sweep. */
 int cgs_model_sweep_part(cgs_model *m, int32_t part, int32_t n_parts);
+/* Diagnostics: runs ONE sweep with a device counter of the tokens actually sampled (must equal the
+ * token count: every token is resampled exactly once per sweep, as in the sequential loop). */
+int cgs_model_debug_sweep_visits(cgs_model *model, int64_t *tokens_sampled);
 /* Tuning knobs of the sweep kernel: lanes that cooperate on one token (power of two, must
- * cover n_topics with at most 16 topics per lane) and warps that share one cell.  The defaults
- * are chosen from n_topics and the mean cell size at cgs_model_create. */
+ * cover n_topics with at most 32 topics per lane) and warps that share one cell (1, 2, 4, 8, 12 or 16).
+ * The defaults are chosen from n_topics and the mean cell size at cgs_model_create. */
 int cgs_model_set_sweep_shape(cgs_model *m, int32_t lanes_per_token, int32_t warps_per_cell);
 /* Upper bound on the CTAs of the sweep kernel (0 = fill the GPU).  With 1 CTA, 32 lanes per
  * token and 1 warp per cell the sweep is an exact sequential Gibbs scan (used by the
  * stationarity test). */
+/* Number of distinct uniform draws per sweep (power of two >= 128; 0 = one independent draw per token).
+ * Default 131072: lda reuses rands[i % 131072] inside a sweep and that reuse measurably
+ * speeds up the transient of the chain, so the device sampler keeps the same reuse density. */
+int cgs_model_set_rng_period(cgs_model *m, int64_t period);
 int cgs_model_set_max_blocks(cgs_model *m, int32_t max_blocks);
 /* The topic totals n_k that a warp works with are re-synchronised often enough that at most
  * 1/divisor of a sweep is processed GPU-wide in between (default 16). */

@@ -49,7 +49,9 @@ SIGNATURES = {
     "cgs_model_get_z": (ctypes.c_int, [c_vp, c_i32p]),
     "cgs_model_sweep": (ctypes.c_int, [c_vp, ctypes.c_int32]),
     "cgs_model_sweep_part": (ctypes.c_int, [c_vp, ctypes.c_int32, ctypes.c_int32]),
+    "cgs_model_debug_sweep_visits": (ctypes.c_int, [c_vp, c_i64p]),
     "cgs_model_set_sweep_shape": (ctypes.c_int, [c_vp, ctypes.c_int32, ctypes.c_int32]),
+    "cgs_model_set_rng_period": (ctypes.c_int, [c_vp, ctypes.c_int64]),
     "cgs_model_set_max_blocks": (ctypes.c_int, [c_vp, ctypes.c_int32]),
     "cgs_model_set_nk_staleness": (ctypes.c_int, [c_vp, ctypes.c_double]),
     "cgs_model_get_sweep_shape": (ctypes.c_int, [c_vp, c_i32p, c_i32p, c_i32p]),

@@ -120,11 +120,16 @@ struct cgs_model {
     int32_t *d_work = nullptr;                      // work-queue counters, one per sweep slot
     double *d_partials = nullptr;                   // reduction scratch
     int *d_flag = nullptr;
+    unsigned long long *d_visits = nullptr;         // set only inside cgs_model_debug_sweep_visits
     int64_t launches = 0;
     int64_t sweeps = 0;
     int64_t work_slot = 0;
     int tpt = 1, ch = 1, threads = 128;
     double nk_divisor = 16.0;
+    // Distinct uniform draws per sweep.  The reference reuses 131 072 numbers cyclically inside a sweep
+    // (lda's rands[i % n_rand]), which correlates far-apart tokens and measurably speeds up the
+    // transient; the same reuse density keeps the trace on the reference's (0 = every token its own draw).
+    int64_t rng_period = 131072;
     int max_blocks = 0;   // user override, 0 = automatic
     int auto_blocks = 1 << 30;  // concurrency cap chosen by pick_sweep_shape
     int sweep_blocks = 0;
@@ -674,6 +679,7 @@ static int sweep_impl(cgs_model *m, int32_t n_sweeps, int32_t part, int32_t n_pa
     p.etaW = (float)(m->eta * (double)c->n_regions);
     p.seed_lo = (uint32_t)m->seed;
     p.seed_hi = (uint32_t)(m->seed >> 32);
+    p.rng_index_mask = m->rng_period == 0 ? ~0ull : (uint64_t)(m->rng_period / 4 - 1);
     p.token_offset = c->token_offset;
     {
         // n_k staleness budget: all warps together process at most 1/nk_divisor of a sweep
@@ -689,6 +695,7 @@ static int sweep_impl(cgs_model *m, int32_t n_sweeps, int32_t part, int32_t n_pa
     }
     p.part = part;
     p.n_parts = n_parts;
+    p.visit_counter = m->d_visits;
     for (int32_t s = 0; s < n_sweeps; ++s) {
         const int slot = (int)(m->work_slot % kWorkSlots);
         if (slot == 0) {
@@ -705,20 +712,49 @@ static int sweep_impl(cgs_model *m, int32_t n_sweeps, int32_t part, int32_t n_pa
     return 0;
 }
 
+int cgs_model_debug_sweep_visits(cgs_model *m, int64_t *tokens_sampled) {
+    if (!m || !tokens_sampled) CGS_FAIL("NULL argument");
+    DeviceGuard g(m->corpus->device);
+    unsigned long long *d = nullptr;
+    CGS_TRY(dmalloc(&d, 1, m->stream));
+    CGS_CUDA(cudaMemsetAsync(d, 0, sizeof(unsigned long long), m->stream));
+    m->d_visits = d;
+    int rc = sweep_impl(m, 1, 0, 1);
+    m->d_visits = nullptr;
+    unsigned long long h = 0;
+    if (rc == 0) {
+        cudaError_t e = cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, m->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(m->stream);
+        if (e != cudaSuccess) rc = fail(__FILE__, __LINE__, cudaGetErrorString(e));
+    }
+    dfree(d, m->stream);
+    *tokens_sampled = (int64_t)h;
+    return rc;
+}
+
 int cgs_model_set_sweep_shape(cgs_model *m, int32_t lanes_per_token, int32_t warps_per_cell) {
     if (!m) CGS_FAIL("NULL model");
     const int t = lanes_per_token;
     if (!(t == 1 || t == 2 || t == 4 || t == 8 || t == 16 || t == 32)) CGS_FAIL("lanes_per_token must be a power of two <= 32");
-    if (!(warps_per_cell == 1 || warps_per_cell == 2 || warps_per_cell == 4 || warps_per_cell == 8))
-        CGS_FAIL("warps_per_cell must be 1, 2, 4 or 8");
+    if (!(warps_per_cell == 1 || warps_per_cell == 2 || warps_per_cell == 4 || warps_per_cell == 8 ||
+          warps_per_cell == 12 || warps_per_cell == 16))
+        CGS_FAIL("warps_per_cell must be 1, 2, 4, 8, 12 or 16");
     const int chunks = (m->K + 3) / 4;
     const int ch = (chunks + t - 1) / t;
     if (ch > kMaxChunksPerLane || t * ch * 4 > kMaxTopics) CGS_FAIL("lanes_per_token too small for this n_topics");
+    if (warps_per_cell * 32 > (ch <= 4 ? 512 : ch <= 6 ? 384 : 256)) CGS_FAIL("too many warps per cell for this many chunks per lane");
     m->tpt = t;
     m->ch = ch;
     m->threads = warps_per_cell * 32;
     m->sweep_blocks = 0;
     m->auto_blocks = 1 << 30;  // an explicit shape lifts the automatic concurrency cap
+    return 0;
+}
+
+int cgs_model_set_rng_period(cgs_model *m, int64_t period) {
+    if (!m) CGS_FAIL("NULL model");
+    if (period != 0 && (period < 128 || (period & (period - 1)) != 0)) CGS_FAIL("period must be 0 or a power of two >= 128");
+    m->rng_period = period;
     return 0;
 }
 

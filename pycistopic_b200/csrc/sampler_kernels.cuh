@@ -31,7 +31,7 @@
 
 namespace cgs {
 
-constexpr int kSweepThreads = 256;  // upper bound; the launch uses 32..256
+constexpr int kSweepThreads = 512;  // upper bound (16 warps per cell); the launch uses 32..512
 constexpr int kMaxTopics = 512;     // TPT * CH * 4 slots, TPT <= 32, CH <= 8
 constexpr int kMaxChunksPerLane = 8;
 
@@ -57,6 +57,8 @@ struct SweepParams {
     int32_t part;           // this launch handles queue slots part, part + n_parts, ... (sub-sweep)
     int32_t n_parts;
     int64_t token_offset;
+    unsigned long long *visit_counter;  // diagnostics: += tokens sampled (NULL in production launches)
+    uint64_t rng_index_mask;            // Philox counter = token index & mask (see cgs_model_set_rng_period)
 };
 
 // ---- memory primitives ----------------------------------------------------------------------
@@ -267,11 +269,16 @@ __device__ __forceinline__ int sweep_step(int4 (&buf)[CH], const char *nwk_lane,
     return zn;
 }
 
-// Resident CTAs per SM the register budget is set for (measured on B200: occupancy beats the few
-// spills it costs; profiles/r1_shape_scan_*.txt): 4 x 8 warps at 64 registers up to 4 chunks per lane,
-// 3 x 8 warps at 80 registers for 5-6 chunks, 2 x 8 warps beyond.
+// Register budget (measured on B200: occupancy beats the few spills it costs; profiles/r1_shape_scan_*.txt):
+// 32 warps per SM at 64 registers up to 4 chunks per lane, 24 warps at 80 registers for 5-6 chunks, 16 warps
+// beyond.  A cell may take up to 16 warps (512 threads) for CH <= 4, 12 (384) for CH 5-6, 8 (256) beyond.
+template <int CH> struct SweepBounds {
+    static constexpr int kThreads = CH <= 4 ? 512 : CH <= 6 ? 384 : 256;
+    static constexpr int kMinBlocks = 2;
+};
+
 template <int TPT, int CH>
-__global__ void __launch_bounds__(kSweepThreads, (CH <= 4 ? 4 : CH <= 6 ? 3 : 2))
+__global__ void __launch_bounds__(SweepBounds<CH>::kThreads, SweepBounds<CH>::kMinBlocks)
 sweep_kernel(const SweepParams p) {
     constexpr int KS = TPT * CH * 4;  // topic slots covered by one token group
     constexpr int KSB = KS * 4;
@@ -332,7 +339,11 @@ sweep_kernel(const SweepParams p) {
         const int nbatch = (ntok + 31) >> 5;
         int rot = 0;
         if (nbatch > 0) {
-            uint32_t h = (uint32_t)cell * 0x9E3779B1u ^ (p.sweep * 0x85EBCA77u) ^ p.seed_lo;
+            // The start is the SAME in every sweep: a start that changes per sweep turns the systematic scan of
+            // the reference into a partly random scan, which measurably slows the transient (C1, K = 50,
+            // sequential CPU emulation, 16 seeds: -0.8 % at sweep 20 with a per-sweep start, -0.3 % with a
+            // fixed one, which is the level of independent random numbers alone).
+            uint32_t h = (uint32_t)cell * 0x9E3779B1u ^ p.seed_lo;
             h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
             rot = (int)(h % (uint32_t)nbatch);
         }
@@ -359,7 +370,7 @@ sweep_kernel(const SweepParams p) {
             const bool valid = (off + lane) < ntok;
             const int ic = valid ? off + lane : ntok - 1;
             w_j = __ldg(tok_cell + ic);
-            const uint64_t gi = gi0 + (uint64_t)off;
+            const uint64_t gi = (gi0 + (uint64_t)off) & p.rng_index_mask;
             rnd = philox4x32_10((uint32_t)gi, (uint32_t)(gi >> 32), p.sweep, 0u, p.seed_lo, p.seed_hi);
             pk_j = pack_token(rnd.x, (int)z_cell[ic], valid);
             w_c = (TPT > 1) ? __shfl_sync(FULL, w_j, 0, TPT) : w_j;
@@ -390,7 +401,7 @@ sweep_kernel(const SweepParams p) {
                 const int icn = valid_n ? off_n + lane : ntok - 1;
                 w_n = __ldg(tok_cell + icn);
                 if (bq_n == 0) {  // one Philox call per lane serves the four batches of a super-batch
-                    const uint64_t gi = gi0 + (uint64_t)off_n;
+                    const uint64_t gi = (gi0 + (uint64_t)off_n) & p.rng_index_mask;
                     rnd = philox4x32_10((uint32_t)gi, (uint32_t)(gi >> 32), p.sweep, 0u, p.seed_lo, p.seed_hi);
                 }
                 const uint32_t bits = bq_n == 0 ? rnd.x : bq_n == 1 ? rnd.y : bq_n == 2 ? rnd.z : rnd.w;
@@ -435,6 +446,10 @@ sweep_kernel(const SweepParams p) {
                 }
             }
             if ((pk_j & 0x200) == 0) z_cell[off + lane] = (uint16_t)zn_j;
+            if (p.visit_counter) {
+                const unsigned live = __ballot_sync(FULL, (pk_j & 0x200) == 0);
+                if (lane == 0) atomicAdd(p.visit_counter, (unsigned long long)__popc(live));
+            }
             sidx = sidx_n; off = off_n; bq = bq_n; more = more_n;
             w_j = w_n; pk_j = pk_n;
         }

@@ -153,6 +153,16 @@ class DeviceModel:
     def set_sweep_shape(self, lanes_per_token: int, warps_per_cell: int):
         check(_lib.load().cgs_model_set_sweep_shape(self._h, lanes_per_token, warps_per_cell))
 
+    def debug_sweep_visits(self) -> int:
+        """One sweep with a device-side count of the tokens sampled (diagnostics)."""
+        n = ctypes.c_int64()
+        check(_lib.load().cgs_model_debug_sweep_visits(self._h, ctypes.byref(n)))
+        return n.value
+
+    def set_rng_period(self, period: int):
+        """Distinct uniform draws per sweep (0 = every token its own; default 131072 as in lda)."""
+        check(_lib.load().cgs_model_set_rng_period(self._h, int(period)))
+
     def set_max_blocks(self, max_blocks: int):
         check(_lib.load().cgs_model_set_max_blocks(self._h, int(max_blocks)))
 

@@ -33,7 +33,7 @@ def gpu_traces(corpus, K, n_iter, seeds, override=None):
     return np.array(out), shape
 
 
-CASES = {"small40": ("small", 40, 60), "small100": ("small", 100, 60), "c1k10": ("C1", 10, 40), "c1k5": ("C1", 5, 40),
+CASES = {"c1k50": ("C1", 50, 40), "c1k30": ("C1", 30, 40), "small40": ("small", 40, 60), "small100": ("small", 100, 60), "c1k10": ("C1", 10, 40), "c1k5": ("C1", 5, 40),
          "c1k2": ("C1", 2, 40)}
 for case in (sys.argv[1:] or ["small40", "small100", "c1k10"]):
     override = None

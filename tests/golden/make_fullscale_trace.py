@@ -1,8 +1,9 @@
 """Oracle log-likelihood traces on a benchmark-SHAPED corpus (C2's 200 000 regions at 3 % density, 4 000 of
 its 10 000 cells: 2.6e7 tokens, cells of 6 500 tokens), so that the device sampler can be compared with the
 sequential reference at the kernel shapes and concurrency the benchmark uses -- the C1 / 300-cell corpora of the
-other parity tests never reach them.  The matrix comes from the deterministic NumPy generator (seed 1234), the
-oracle runs 4 seeds per K with refresh = 1.  Takes ~20 min on 8 cores; run in the authoring container:
+other parity tests never reach them.  The matrix comes from the torch-CPU path of the generator (seed 1234;
+reproducible for a given torch build -- the file stores checksums so that a consumer can tell), the oracle runs
+8 seeds per K with refresh = 1.  Takes ~10 min on 8 cores; run in the authoring container:
     python tests/golden/make_fullscale_trace.py
 writes tests/golden/trace_c2_4000cells.npz (mean and standard error of the trace per K; a few hundred bytes)."""
 import os
@@ -20,19 +21,28 @@ from pycistopic_b200.synth import planted_topic_tokens  # noqa: E402
 
 D, W, DENS, SEED = 4000, 200_000, 0.03, 1234
 CASES = {10: 24, 50: 24}  # K -> sweeps
-SEEDS = [555, 1, 2, 3]
+SEEDS = [555, 1, 2, 3, 4, 5, 6, 7]
+
+
+def tokens():
+    """(cell, region) int64 arrays sorted by (cell, region) and their checksums."""
+    import torch
+    cell, region = planted_topic_tokens(D, W, DENS, seed=SEED, device=torch.device("cpu"))
+    cell, region = cell.numpy(), region.numpy()
+    return cell, region, np.array([len(cell), int(cell.sum()), int(region.sum())], np.int64)
 
 
 def matrix():
-    cell, region = planted_topic_tokens(D, W, DENS, seed=SEED)
-    return sp.csr_matrix((np.ones(len(cell), np.int32), (cell, region)), shape=(D, W), dtype=np.int32)
+    cell, region, check = tokens()
+    X = sp.csr_matrix((np.ones(len(cell), np.int32), (cell, region)), shape=(D, W), dtype=np.int32)
+    return X, check
 
 
 if __name__ == "__main__":
     t = time.time()
-    X = matrix()
+    X, check = matrix()
     print(f"matrix {D} x {W}: {X.nnz} tokens ({time.time() - t:.0f} s)", flush=True)
-    out = {"D": D, "W": W, "density": DENS, "data_seed": SEED, "seeds": np.array(SEEDS), "tokens": X.nnz}
+    out = {"D": D, "W": W, "density": DENS, "data_seed": SEED, "seeds": np.array(SEEDS), "tokens": X.nnz, "checksum": check}
     for K, n_iter in CASES.items():
         def one(s):
             o = lo.OracleLDA(K, n_iter=n_iter, alpha=50.0 / K, eta=0.1, random_state=s, refresh=1).fit(X)

@@ -443,3 +443,46 @@ def test_normalize_scores_matches_oracle(dtype, rtol, R, C):
     ref = lo.normalized_scores(x, 10 ** 4)
     assert out.dtype == ref.dtype and out.shape == ref.shape
     np.testing.assert_allclose(out, ref, rtol=rtol, atol=0)
+
+
+def test_loglik_trace_benchmark_shapes():
+    """The device sampler at the kernel shapes and concurrency of the benchmark (cells of 6 500 tokens, 200 000
+    regions: 4 lanes x 4 chunks for K = 50, 2 x 2 for K = 10, hundreds of cells open) against the sequential
+    oracle's mean trace frozen in tests/golden/trace_c2_4000cells.npz (4 seeds, refresh = 1).  1 % on every
+    sweep (north star).  The matrix is regenerated with the torch-CPU generator and checked against the
+    stored checksums; another torch build that draws differently skips instead of comparing apples to pears."""
+    import torch
+    from pycistopic_b200 import Corpus, DeviceModel
+    from pycistopic_b200.synth import planted_topic_tokens
+    g = np.load(os.path.join(ROOT, "tests", "golden", "trace_c2_4000cells.npz"))
+    D, W = int(g["D"]), int(g["W"])
+    cell, region = planted_topic_tokens(D, W, float(g["density"]), seed=int(g["data_seed"]), device=torch.device("cpu"))
+    check = np.array([cell.numel(), int(cell.sum()), int(region.sum())], np.int64)
+    if not np.array_equal(check, g["checksum"]):
+        pytest.skip("the torch-CPU generator of this build draws a different matrix than the frozen oracle traces saw")
+    dev = torch.device("cuda:0")
+    cnt = torch.bincount(cell, minlength=D)
+    cell_ptr = torch.zeros(D + 1, dtype=torch.int64)
+    cell_ptr[1:] = torch.cumsum(cnt, 0)
+    cell_ptr, tok = cell_ptr.to(dev), region.to(torch.int32).to(dev)
+    corpus = Corpus.from_device_tokens(cell_ptr.data_ptr(), tok.data_ptr(), D, W, tok.numel(), keepalive=(cell_ptr, tok))
+    for K in (10, 50):
+        ref = g[f"mean_K{K}"]
+        n_iter = len(ref) - 1
+        traces = []
+        for seed in (555, 1, 2):
+            model = DeviceModel(corpus, K, 50.0 / K, 0.1, seed=seed)
+            model.init()
+            tr = []
+            for _ in range(n_iter):
+                tr.append(model.loglikelihood())
+                model.sweep(1)
+            tr.append(model.loglikelihood())
+            traces.append(tr)
+            shape = model.sweep_shape
+            model.close()
+        mean = np.mean(traces, axis=0)
+        assert mean[0] == pytest.approx(ref[0], rel=1e-10)  # identical start: z = i mod K on the identical matrix
+        rel = np.abs(mean - ref) / np.abs(ref)
+        assert rel.max() < 0.01, f"K={K} {shape}: trace deviates {rel.max():.3%} at sweep {int(rel.argmax())}"
+    corpus.close()
