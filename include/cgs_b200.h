@@ -135,6 +135,33 @@ int cgs_model_export_distributions(cgs_model *m, double *topic_word, double *doc
  * (lda_models.py:348-357 build these by transposing; the device writes them directly). */
 int cgs_model_export_frames(cgs_model *m, double *topic_region, double *cell_topic);
 
+/* ---- model-quality metrics (replaces the tmtoolkit calls of lda_models.py:291-304, :332-344 and
+ *      utils.loglikelihood, utils.py:129-160, called at lda_models.py:305) ----
+ * The reference computes them on the host from topic_word_ (K x W), doc_topic_ (D x K) and the token
+ * matrix.  Here the O(K^2 W), O(K D) and O(N) parts run on the device from the resident counts and
+ * only K x K / K x top_n sized results come back; the host finishes with O(K^3) arithmetic. */
+/* Tokens per cell (doc_lengths = X.sum(axis=1), lda_models.py:295): int64[n_cells]. */
+int cgs_corpus_export_cell_sizes(const cgs_corpus *c, int64_t *sizes);
+/* gram = topic_word @ topic_word.T, float64[K x K], from an EXACT int64 Gram of n_wk.
+ * metric_arun_2010 needs its eigenvalues (singular values of topic_word squared), metric_cao_juan_2009
+ * its cosines. */
+int cgs_model_topic_gram(cgs_model *m, double *gram);
+/* mixture[k] = sum_d nd_d * doc_topic[d, k] (float64[K]) and *length_sq = sum_d nd_d^2: Arun's
+ * cm2 = mixture / sqrt(length_sq); marginal_topic_distrib = mixture / sum(mixture). */
+int cgs_model_cell_mixture(cgs_model *m, double *mixture, double *length_sq);
+/* The top_n (<= 32) regions of every topic, most probable first: int32[K x top_n] (and their counts,
+ * may be NULL) -- tmtoolkit's argsort(topic_word, axis=1)[:, :-(top_n+1):-1] with ties (equal counts)
+ * ordered by region index descending, i.e. a stable argsort.  Fails like tmtoolkit when top_n exceeds
+ * the number of regions. */
+int cgs_model_top_regions(cgs_model *m, int32_t top_n, int32_t *top_regions, int32_t *top_counts);
+/* codf[t][a][b] = number of cells that contain both top_regions[t][a] and top_regions[t][b]
+ * (a == b: the document frequency), int32[K x top_n x top_n], from the device token list
+ * (metric_coherence_mimno_2011's df / codf, lda_models.py:297-304). */
+int cgs_model_codocument_frequencies(cgs_model *m, int32_t top_n, const int32_t *top_regions, int32_t *codf);
+/* The value utils.loglikelihood(nzw, ndz, alpha, eta) returns (bug-compatible: its loops overwrite
+ * instead of accumulating, utils.py:145, :155), called with the RAW alpha and eta (lda_models.py:305). */
+int cgs_model_loglik_compat(cgs_model *m, double alpha_raw, double eta_raw, double *ll);
+
 /* ---- AD-LDA exchange step ------------------------------------- */
 /* Device buffers a host framework may wrap (torch via __cuda_array_interface__) to run the
  * collective: 0 = n_wk (int32, W*Kp), 1 = n_wk snapshot taken at the last exchange,

@@ -61,6 +61,12 @@ SIGNATURES = {
     "cgs_model_export_counts": (ctypes.c_int, [c_vp, c_i32p, c_i32p, c_i32p]),
     "cgs_model_export_distributions": (ctypes.c_int, [c_vp, c_f64p, c_f64p]),
     "cgs_model_export_frames": (ctypes.c_int, [c_vp, c_f64p, c_f64p]),
+    "cgs_corpus_export_cell_sizes": (ctypes.c_int, [c_vp, c_i64p]),
+    "cgs_model_topic_gram": (ctypes.c_int, [c_vp, c_f64p]),
+    "cgs_model_cell_mixture": (ctypes.c_int, [c_vp, c_f64p, c_f64p]),
+    "cgs_model_top_regions": (ctypes.c_int, [c_vp, ctypes.c_int32, c_i32p, c_i32p]),
+    "cgs_model_codocument_frequencies": (ctypes.c_int, [c_vp, ctypes.c_int32, c_i32p, c_i32p]),
+    "cgs_model_loglik_compat": (ctypes.c_int, [c_vp, ctypes.c_double, ctypes.c_double, c_f64p]),
     "cgs_model_device_buffer": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.POINTER(c_vp),
                                                ctypes.POINTER(ctypes.c_size_t)]),
     "cgs_model_padded_topics": (ctypes.c_int, [c_vp, c_i32p]),

@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <numeric>
 #include <type_traits>
 #include <vector>
@@ -12,6 +13,7 @@
 #include "common.cuh"
 #include "corpus_kernels.cuh"
 #include "impute_kernels.cuh"
+#include "metrics_kernels.cuh"
 #include "normalize_kernels.cuh"
 #include "sampler_kernels.cuh"
 #include "stats_kernels.cuh"
@@ -1227,6 +1229,252 @@ int cgs_normalize_scores(int device, const void *x, int dtype, int64_t n_rows, i
     dfree(d_x, stream); dfree(d_o, stream); dfree(d_s, stream);
     cudaStreamDestroy(stream);
     return rc;
+}
+
+}  // extern "C"
+
+// ---- model-quality metrics on the device (lda_models.py:291-305, :332-344) ------------
+extern "C" {
+
+int cgs_corpus_export_cell_sizes(const cgs_corpus *c, int64_t *sizes) {
+    if (!c || !sizes) CGS_FAIL("NULL argument");
+    DeviceGuard g(c->device);
+    if (c->n_cells == 0) return 0;
+    int64_t *d_s = nullptr;
+    CGS_TRY(dmalloc(&d_s, (size_t)c->n_cells, c->stream));
+    cell_sizes_kernel<<<(unsigned)std::min<int64_t>(c->num_sms * 8, ceil_div(c->n_cells, 256)), 256, 0, c->stream>>>(
+        c->d_cell_ptr, c->n_cells, d_s);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cgs_memcpy_sync(c->stream, sizes, d_s, sizeof(int64_t) * (size_t)c->n_cells, cudaMemcpyDeviceToHost);
+    dfree(d_s, c->stream);
+    CGS_CUDA(e);
+    return 0;
+}
+
+int cgs_model_topic_gram(cgs_model *m, double *gram) {
+    if (!m || !gram) CGS_FAIL("NULL argument");
+    cgs_corpus *c = m->corpus;
+    DeviceGuard g(c->device);
+    const int64_t W = c->n_regions;
+    const int32_t K = m->K, Kp = m->Kp;
+    unsigned long long *d_g = nullptr;
+    CGS_TRY(dmalloc(&d_g, (size_t)Kp * Kp, m->stream));
+    std::vector<long long> S((size_t)Kp * Kp);
+    std::vector<int32_t> nk(Kp);
+    int rc = [&]() -> int {
+        CGS_CUDA(cudaMemsetAsync(d_g, 0, sizeof(unsigned long long) * (size_t)Kp * Kp, m->stream));
+        const int nt = Kp / 4, n_tiles = nt * (nt + 1) / 2;
+        const int gy = (int)ceil_div(n_tiles, kGramThreads);
+        const int64_t n_slabs = ceil_div(W, kGramRows);
+        const int gx = (int)std::max<int64_t>(1, std::min<int64_t>(n_slabs, std::max(1, c->num_sms * 8 / gy)));
+        const size_t smem = sizeof(int32_t) * kGramRows * (size_t)Kp;
+        topic_gram_kernel<<<dim3(gx, gy), kGramThreads, smem, m->stream>>>(m->d_nwk, W, Kp, n_tiles, d_g);
+        CGS_CUDA(cudaGetLastError());
+        m->launches += 1;
+        CGS_CUDA(cudaMemcpyAsync(S.data(), d_g, sizeof(long long) * S.size(), cudaMemcpyDeviceToHost, m->stream));
+        CGS_CUDA(cudaMemcpyAsync(nk.data(), m->d_nk, sizeof(int32_t) * (size_t)Kp, cudaMemcpyDeviceToHost, m->stream));
+        CGS_CUDA(cudaStreamSynchronize(m->stream));
+        return 0;
+    }();
+    dfree(d_g, m->stream);
+    CGS_TRY(rc);
+    // topic_word[k, w] = (n_wk[w,k] + eta) / (n_k[k] + eta W)  =>
+    // gram[i][j] = (S_ij + eta (n_i + n_j) + eta^2 W) / ((n_i + eta W)(n_j + eta W)), S exact
+    const double eta = m->eta, etaW = m->eta * (double)W;
+    for (int i = 0; i < K; ++i)
+        for (int j = 0; j < K; ++j) {
+            const long long sij = i <= j ? S[(size_t)i * Kp + j] : S[(size_t)j * Kp + i];
+            const double num = (double)sij + eta * ((double)nk[i] + (double)nk[j]) + eta * eta * (double)W;
+            gram[(size_t)i * K + j] = num / (((double)nk[i] + etaW) * ((double)nk[j] + etaW));
+        }
+    return 0;
+}
+
+int cgs_model_cell_mixture(cgs_model *m, double *mixture, double *length_sq) {
+    if (!m || !mixture || !length_sq) CGS_FAIL("NULL argument");
+    cgs_corpus *c = m->corpus;
+    DeviceGuard g(c->device);
+    const int32_t K = m->K, D = c->n_cells;
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(c->num_sms * 2, ceil_div(D, 8)));
+    double *d_p = nullptr;
+    CGS_TRY(dmalloc(&d_p, (size_t)(blocks + 1) * (K + 1), m->stream));
+    std::vector<double> h(K + 1);
+    int rc = [&]() -> int {
+        cell_mixture_kernel<<<blocks, dim3(32, 8), 0, m->stream>>>(m->d_ndk, c->d_cell_ptr, D, K, m->Kp, m->alpha, d_p);
+        double *d_out = d_p + (size_t)blocks * (K + 1);
+        column_sum_partials_kernel<<<(unsigned)ceil_div(K + 1, 128), 128, 0, m->stream>>>(d_p, blocks, K + 1, d_out);
+        CGS_CUDA(cudaGetLastError());
+        m->launches += 2;
+        CGS_CUDA(cudaMemcpyAsync(h.data(), d_out, sizeof(double) * (size_t)(K + 1), cudaMemcpyDeviceToHost, m->stream));
+        CGS_CUDA(cudaStreamSynchronize(m->stream));
+        return 0;
+    }();
+    dfree(d_p, m->stream);
+    CGS_TRY(rc);
+    std::copy(h.begin(), h.begin() + K, mixture);
+    *length_sq = h[K];
+    return 0;
+}
+
+int cgs_model_top_regions(cgs_model *m, int32_t top_n, int32_t *top_regions, int32_t *top_counts) {
+    if (!m || !top_regions) CGS_FAIL("NULL argument");
+    cgs_corpus *c = m->corpus;
+    if (top_n < 1 || top_n > 32) CGS_FAIL("top_n must be in [1, 32]");
+    if (top_n > c->n_regions)
+        CGS_FAIL("`top_n=" + std::to_string(top_n) + "` is larger than the vocabulary size of " +
+                 std::to_string(c->n_regions) + " words");
+    DeviceGuard g(c->device);
+    const int32_t K = m->K;
+    const int n_slabs = (int)ceil_div(c->n_regions, kTopSlab);
+    unsigned long long *d_cand = nullptr;
+    int32_t *d_top = nullptr;
+    CGS_TRY(dmalloc(&d_cand, (size_t)n_slabs * K * 32, m->stream));
+    int rc = dmalloc(&d_top, (size_t)2 * K * top_n, m->stream);
+    std::vector<int32_t> h((size_t)2 * K * top_n);
+    if (rc == 0) rc = [&]() -> int {
+        top_regions_slab_kernel<<<dim3(n_slabs, (unsigned)ceil_div(K, kTopWarps)), kTopWarps * 32, 0, m->stream>>>(
+            m->d_nwk, c->n_regions, K, m->Kp, d_cand);
+        top_regions_merge_kernel<<<(unsigned)ceil_div(K, kTopWarps), kTopWarps * 32, 0, m->stream>>>(
+            d_cand, n_slabs, K, top_n, d_top, d_top + (size_t)K * top_n);
+        CGS_CUDA(cudaGetLastError());
+        m->launches += 2;
+        CGS_CUDA(cudaMemcpyAsync(h.data(), d_top, sizeof(int32_t) * h.size(), cudaMemcpyDeviceToHost, m->stream));
+        CGS_CUDA(cudaStreamSynchronize(m->stream));
+        return 0;
+    }();
+    dfree(d_cand, m->stream);
+    dfree(d_top, m->stream);
+    CGS_TRY(rc);
+    std::copy(h.begin(), h.begin() + (size_t)K * top_n, top_regions);
+    if (top_counts) std::copy(h.begin() + (size_t)K * top_n, h.end(), top_counts);
+    return 0;
+}
+
+int cgs_model_codocument_frequencies(cgs_model *m, int32_t top_n, const int32_t *top_regions, int32_t *codf) {
+    if (!m || !top_regions || !codf) CGS_FAIL("NULL argument");
+    cgs_corpus *c = m->corpus;
+    if (top_n < 1 || top_n > 32) CGS_FAIL("top_n must be in [1, 32]");
+    DeviceGuard g(c->device);
+    const int32_t K = m->K, D = c->n_cells, W = c->n_regions;
+    const size_t n_ent = (size_t)K * top_n;
+    // lookup tables: bitmap over regions, sorted distinct listed regions, their (topic << 5 | rank) entries
+    std::vector<std::pair<int32_t, int32_t>> pairs(n_ent);
+    for (int t = 0; t < K; ++t)
+        for (int r = 0; r < top_n; ++r) {
+            const int32_t w = top_regions[(size_t)t * top_n + r];
+            if (w < 0 || w >= W) CGS_FAIL("top_regions holds an index outside the region axis");
+            pairs[(size_t)t * top_n + r] = {w, (t << 5) | r};
+        }
+    std::sort(pairs.begin(), pairs.end());
+    const size_t words = ((size_t)W + 31) / 32;
+    // one upload: [bitmap words][u n_ent][ent_ptr n_ent + 1][ent n_ent]
+    std::vector<int32_t> tab(words + 3 * n_ent + 1, 0);
+    int32_t *bitmap = tab.data(), *u = bitmap + words, *ent_ptr = u + n_ent, *ent = ent_ptr + n_ent + 1;
+    int32_t M = 0;
+    for (size_t i = 0; i < n_ent; ++i) {
+        const int32_t w = pairs[i].first;
+        if (i == 0 || w != pairs[i - 1].first) { u[M] = w; ent_ptr[M] = (int32_t)i; ++M; }
+        ent[i] = pairs[i].second;
+        ((uint32_t *)bitmap)[w >> 5] |= 1u << (w & 31);
+    }
+    ent_ptr[M] = (int32_t)n_ent;
+    int32_t *d_tab = nullptr, *d_codf = nullptr;
+    uint32_t *d_masks = nullptr;
+    int rc = [&]() -> int {
+        CGS_TRY(dmalloc(&d_tab, tab.size(), m->stream));
+        CGS_TRY(dmalloc(&d_codf, (size_t)K * top_n * top_n, m->stream));
+        CGS_TRY(dmalloc(&d_masks, (size_t)std::max(1, D) * K, m->stream));
+        CGS_CUDA(cudaMemcpyAsync(d_tab, tab.data(), sizeof(int32_t) * tab.size(), cudaMemcpyHostToDevice, m->stream));
+        CGS_CUDA(cudaMemsetAsync(d_codf, 0, sizeof(int32_t) * (size_t)K * top_n * top_n, m->stream));
+        if (D > 0) {
+            const int mb = (int)std::max<int64_t>(1, std::min<int64_t>(c->num_sms * 8, ceil_div(D, kMaskWarps)));
+            const size_t smem = sizeof(uint32_t) * kMaskWarps * (size_t)K;
+            cell_masks_kernel<<<mb, kMaskWarps * 32, smem, m->stream>>>(
+                c->d_cell_ptr, c->d_tok_region, D, K, (const uint32_t *)d_tab, d_tab + words, M,
+                d_tab + words + n_ent, d_tab + words + 2 * n_ent + 1, d_masks);
+            const int n_pairs = top_n * (top_n + 1) / 2;
+            const int threads = std::max(256, (n_pairs + 31) / 32 * 32);
+            const int slices = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(D, 4096), std::max(1, c->num_sms * 4 / K)));
+            pair_count_kernel<<<dim3(K, slices), threads, 0, m->stream>>>(d_masks, D, K, top_n, d_codf);
+            CGS_CUDA(cudaGetLastError());
+            m->launches += 2;
+        }
+        CGS_CUDA(cudaMemcpyAsync(codf, d_codf, sizeof(int32_t) * (size_t)K * top_n * top_n, cudaMemcpyDeviceToHost, m->stream));
+        CGS_CUDA(cudaStreamSynchronize(m->stream));
+        return 0;
+    }();
+    dfree(d_tab, m->stream);
+    dfree(d_codf, m->stream);
+    dfree(d_masks, m->stream);
+    return rc;
+}
+
+int cgs_model_loglik_compat(cgs_model *m, double alpha_raw, double eta_raw, double *ll) {
+    if (!m || !ll) CGS_FAIL("NULL argument");
+    cgs_corpus *c = m->corpus;
+    DeviceGuard g(c->device);
+    const int32_t K = m->K, Kp = m->Kp, D = c->n_cells;
+    const int64_t W = c->n_regions;
+    std::vector<int32_t> nk(Kp), row(Kp);
+    int *d_idx = nullptr;  // [0] last region of the last non-empty topic, [1] last non-empty cell
+    CGS_TRY(dmalloc(&d_idx, 2, m->stream));
+    int h_idx[2] = {-1, -1};
+    int32_t last_topic = -1, topic_count = 0;
+    int64_t cell_ptr2[2] = {0, 0};
+    int rc = [&]() -> int {
+        CGS_CUDA(cudaMemsetAsync(d_idx, 0xff, sizeof(int) * 2, m->stream));
+        CGS_CUDA(cgs_memcpy_sync(m->stream, nk.data(), m->d_nk, sizeof(int32_t) * (size_t)Kp, cudaMemcpyDeviceToHost));
+        for (int k = K - 1; k >= 0; --k)
+            if (nk[k] > 0) { last_topic = k; break; }
+        const int blocks = c->num_sms * 4;
+        if (last_topic >= 0) {
+            last_positive_row_kernel<<<blocks, 256, 0, m->stream>>>(m->d_nwk, W, Kp, last_topic, d_idx);
+            m->launches += 1;
+        }
+        if (D > 0) {
+            last_nonempty_cell_kernel<<<blocks, 256, 0, m->stream>>>(c->d_cell_ptr, D, d_idx + 1);
+            m->launches += 1;
+        }
+        CGS_CUDA(cudaGetLastError());
+        CGS_CUDA(cgs_memcpy_sync(m->stream, h_idx, d_idx, sizeof(int) * 2, cudaMemcpyDeviceToHost));
+        if (h_idx[0] >= 0)
+            CGS_CUDA(cgs_memcpy_sync(m->stream, &topic_count, m->d_nwk + (size_t)h_idx[0] * Kp + last_topic,
+                                     sizeof(int32_t), cudaMemcpyDeviceToHost));
+        if (h_idx[1] >= 0) {
+            CGS_CUDA(cgs_memcpy_sync(m->stream, row.data(), m->d_ndk + (size_t)h_idx[1] * Kp, sizeof(int32_t) * (size_t)Kp,
+                                     cudaMemcpyDeviceToHost));
+            CGS_CUDA(cgs_memcpy_sync(m->stream, cell_ptr2, c->d_cell_ptr + h_idx[1], sizeof(int64_t) * 2,
+                                     cudaMemcpyDeviceToHost));
+        }
+        return 0;
+    }();
+    dfree(d_idx, m->stream);
+    CGS_TRY(rc);
+    // utils.loglikelihood (utils.py:129-160) overwrites topic_ll / doc_ll inside its loops: what is left is the
+    // lgamma of the LAST positive entry of the last non-empty row minus the row-total terms from that row on.
+    const double etaW = eta_raw * (double)W, alphaK = alpha_raw * (double)K;
+    double topic_ll = 0.0;
+    int start = 0;
+    if (last_topic >= 0) { topic_ll = std::lgamma((double)topic_count + eta_raw); start = last_topic; }
+    for (int k = start; k < K; ++k) topic_ll -= std::lgamma(etaW + (double)nk[k]);
+    double doc_ll = 0.0;
+    int64_t dstart = 0;
+    if (h_idx[1] >= 0) {
+        int32_t last_k = -1;
+        for (int k = K - 1; k >= 0; --k)
+            if (row[k] > 0) { last_k = k; break; }
+        if (last_k < 0) CGS_FAIL("n_dk row of a non-empty cell holds no count (model not initialised?)");
+        doc_ll = std::lgamma((double)row[last_k] + alpha_raw);
+        dstart = h_idx[1];
+        doc_ll -= std::lgamma(alphaK + (double)(cell_ptr2[1] - cell_ptr2[0]));
+        ++dstart;
+    }
+    const double lg_empty = std::lgamma(alphaK);
+    for (int64_t d = dstart; d < D; ++d) doc_ll -= lg_empty;
+    const double const_prior = ((double)K * std::lgamma(alpha_raw) - std::lgamma(alphaK)) * (double)D;
+    const double const_ll = ((double)W * std::lgamma(eta_raw) - std::lgamma(etaW)) * (double)K;
+    *ll = doc_ll - const_prior + topic_ll - const_ll;
+    return 0;
 }
 
 }  // extern "C"

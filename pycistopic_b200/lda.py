@@ -100,6 +100,15 @@ class Corpus:
         check(_lib.load().cgs_corpus_export_tokens(self._h, ptr(WS, c_i32p), ptr(DS, c_i32p)))
         return WS, DS
 
+    def cell_sizes(self):
+        """Tokens per cell, int64[n_cells] (= ``X.sum(axis=1)`` of the cells x regions matrix,
+        lda_models.py:295); cached."""
+        if getattr(self, "_cell_sizes", None) is None:
+            s = np.empty(self.n_cells, np.int64)
+            check(_lib.load().cgs_corpus_export_cell_sizes(self._h, ptr(s, c_i64p)))
+            self._cell_sizes = s
+        return self._cell_sizes
+
     def close(self):
         if self._h is not None:
             check(_lib.load().cgs_corpus_destroy(self._h))
@@ -226,6 +235,54 @@ class DeviceModel:
                                                  ptr(b, c_f64p) if cell_topic else None))
         return a, b
 
+    # -- model-quality metrics (lda_models.py:291-305, :332-344) -------------------------------
+    def topic_gram(self):
+        """``topic_word_ @ topic_word_.T`` (K x K float64) from an exact integer Gram of ``n_wk``."""
+        g = np.empty((self.n_topics, self.n_topics), np.float64)
+        check(_lib.load().cgs_model_topic_gram(self._h, ptr(g, c_f64p)))
+        return g
+
+    def cell_mixture(self):
+        """(``doc_lengths @ doc_topic_`` as float64[K], ``sum(doc_lengths ** 2)``)."""
+        mix = np.empty(self.n_topics, np.float64)
+        sq = ctypes.c_double()
+        check(_lib.load().cgs_model_cell_mixture(self._h, ptr(mix, c_f64p), ctypes.byref(sq)))
+        return mix, sq.value
+
+    def top_regions(self, top_n=20, counts=False):
+        """The ``top_n`` most probable regions of every topic, most probable first (K x top_n int32);
+        equal counts are ordered by region index descending (a stable argsort read backwards)."""
+        if top_n > self.corpus.n_regions:  # tmtoolkit's check and message
+            raise ValueError("`top_n=%d` is larger than the vocabulary size of %d words" % (top_n, self.corpus.n_regions))
+        top = np.empty((self.n_topics, top_n), np.int32)
+        cnt = np.empty((self.n_topics, top_n), np.int32)
+        check(_lib.load().cgs_model_top_regions(self._h, int(top_n), ptr(top, c_i32p), ptr(cnt, c_i32p)))
+        return (top, cnt) if counts else top
+
+    def codocument_frequencies(self, top_regions):
+        """codf[t, a, b] = cells containing both ``top_regions[t, a]`` and ``top_regions[t, b]``
+        (diagonal: document frequencies), K x top_n x top_n int32."""
+        top = np.ascontiguousarray(top_regions, dtype=np.int32)
+        if top.ndim != 2 or top.shape[0] != self.n_topics:
+            raise ValueError("top_regions must be n_topics x top_n")
+        codf = np.empty((self.n_topics, top.shape[1], top.shape[1]), np.int32)
+        check(_lib.load().cgs_model_codocument_frequencies(self._h, top.shape[1], ptr(top, c_i32p),
+                                                          ptr(codf, c_i32p)))
+        return codf
+
+    def loglikelihood_compat(self, alpha_raw: float, eta_raw: float) -> float:
+        """What ``pycisTopic.utils.loglikelihood(nzw_, ndz_, alpha, eta)`` returns (utils.py:129-160)."""
+        ll = ctypes.c_double()
+        check(_lib.load().cgs_model_loglik_compat(self._h, float(alpha_raw), float(eta_raw), ctypes.byref(ll)))
+        return ll.value
+
+    def metric_ingredients(self, top_n=20):
+        """Everything ``build_cistopic_model`` needs for the metric block, computed on the device."""
+        top = self.top_regions(top_n)
+        mix, sq = self.cell_mixture()
+        return {"gram": self.topic_gram(), "cell_mixture": mix, "length_sq": sq, "top_regions": top,
+                "codf": self.codocument_frequencies(top), "top_n": top_n}
+
     # -- AD-LDA exchange -------------------------------------------------------------------
     @property
     def padded_topics(self) -> int:
@@ -282,7 +339,7 @@ class LDA:
     """
 
     def __init__(self, n_topics, n_iter=2000, alpha=0.1, eta=0.01, random_state=None, refresh=10,
-                 device=0, corpus: Corpus | None = None, lazy_exports=False):
+                 device=0, corpus: Corpus | None = None, exports="all", device_metrics=None):
         self.n_topics = n_topics
         self.n_iter = n_iter
         self.alpha = alpha
@@ -291,7 +348,14 @@ class LDA:
         self.refresh = refresh
         self.device = device
         self._corpus = corpus
-        self._lazy = lazy_exports
+        # exports: "all" = every attribute of the lda protocol; "frames" = only what CistopicLDAModel keeps
+        # (nz_, topic_region_ W x K, cell_topic_ K x D) -- run_cgs_models uses it together with
+        # device_metrics = {"alpha": raw alpha, "eta": raw eta, "top_n": 20}, which makes fit() leave the
+        # metric ingredients of lda_models.py:291-305 in ``metric_ingredients_`` (computed on the device).
+        if exports not in ("all", "frames"):
+            raise ValueError("exports must be 'all' or 'frames'")
+        self._exports = exports
+        self._device_metrics = device_metrics
         if alpha <= 0 or eta <= 0:
             raise ValueError("alpha and eta must be greater than zero")
         if random_state is None:
@@ -332,11 +396,20 @@ class LDA:
             ll = model.loglikelihood()
             logger.info("<%d> log likelihood: %.0f", self.n_iter - 1, ll)
             self.final_loglikelihood_ = ll
-            self.nzw_, self.ndz_, self.nz_ = model.counts()
-            self.components_, self.doc_topic_ = model.distributions()
-            self.topic_word_ = self.components_
+            if self._exports == "all":
+                self.nzw_, self.ndz_, self.nz_ = model.counts()
+                self.components_, self.doc_topic_ = model.distributions()
+                self.topic_word_ = self.components_
+            else:
+                self.nz_ = model.counts(nzw=False, ndz=False)[2]
             # DataFrame-ready layouts straight from the device (no host transpose)
             self.topic_region_, self.cell_topic_ = model.frames()
+            if self._device_metrics is not None:
+                dm = self._device_metrics
+                ing = model.metric_ingredients(int(dm.get("top_n", 20)))
+                ing["loglikelihood_compat"] = model.loglikelihood_compat(dm["alpha"], dm["eta"])
+                ing["doc_lengths"] = corpus.cell_sizes().astype(np.float64)
+                self.metric_ingredients_ = ing
             self.launch_count_ = model.launch_count
         finally:
             model.close()

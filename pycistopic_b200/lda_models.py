@@ -192,6 +192,8 @@ def _fit_cgs_model_on_corpus(corpus, n_topics, n_iter, random_state, alpha, alph
         refresh=n_iter,
         device=corpus.device,
         corpus=corpus,
+        exports="frames",
+        device_metrics={"alpha": alpha, "eta": eta, "top_n": 20},
     )
     log.info(f"Running model with {n_topics} topics")
     start_time = time.time()
@@ -211,12 +213,24 @@ def build_cistopic_model(model, regions_by_cells, n_topics, cell_names, region_n
                          alpha_by_topic, eta, eta_by_topic, top_topics_coh, end_time, save_path=None, log=None):
     """Metric block and DataFrame packing of lda_models.py:291-388 from a fitted LDA-protocol
     object (needs topic_word_, doc_topic_, nzw_, ndz_, nz_)."""
-    M = sparse.csr_matrix(regions_by_cells)
-    doc_lengths = np.asarray(M.sum(axis=0)).ravel().astype(float)  # tokens per cell
-    arun_2010 = _metrics.metric_arun_2010(model.topic_word_, model.doc_topic_, doc_lengths)
-    cao_juan_2009 = _metrics.metric_cao_juan_2009(model.topic_word_)
-    mimno_2011 = _metrics.metric_coherence_mimno_2011(model.topic_word_, M, top_n=20, eps=1e-12, normalize=True)
-    ll = _metrics.loglikelihood_compat(model.nzw_, model.ndz_, alpha, eta)
+    ing = getattr(model, "metric_ingredients_", None)
+    if ing is not None:
+        # Gram matrix, cell mixture, top regions and their (co-)document frequencies came from the device
+        # (cgs_model_topic_gram / _cell_mixture / _top_regions / _codocument_frequencies / _loglik_compat)
+        arun_2010 = _metrics.arun_from_gram(ing["gram"], ing["cell_mixture"], ing["length_sq"],
+                                            lambda: np.ascontiguousarray(model.topic_region_.T))
+        cao_juan_2009 = _metrics.cao_juan_from_gram(ing["gram"])
+        mimno_2011 = _metrics.mimno_from_codf(ing["codf"], eps=1e-12, normalize=True)
+        ll = ing["loglikelihood_compat"]
+        marg = _metrics.marginal_from_mixture(ing["cell_mixture"])
+    else:  # any other fitted lda-protocol object: the same formulas from its host arrays
+        M = sparse.csr_matrix(regions_by_cells)
+        doc_lengths = np.asarray(M.sum(axis=0)).ravel().astype(float)  # tokens per cell
+        arun_2010 = _metrics.metric_arun_2010(model.topic_word_, model.doc_topic_, doc_lengths)
+        cao_juan_2009 = _metrics.metric_cao_juan_2009(model.topic_word_)
+        mimno_2011 = _metrics.metric_coherence_mimno_2011(model.topic_word_, M, top_n=20, eps=1e-12, normalize=True)
+        ll = _metrics.loglikelihood_compat(model.nzw_, model.ndz_, alpha, eta)
+        marg = _metrics.marginal_topic_distrib(model.doc_topic_, doc_lengths)
 
     if len(mimno_2011) <= top_topics_coh:
         model_coh = np.mean(mimno_2011)
@@ -229,7 +243,6 @@ def build_cistopic_model(model, regions_by_cells, n_topics, cell_names, region_n
     ).transpose()
     topics = np.arange(1, n_topics + 1)
     coherence = pd.DataFrame({"Topic": topics.astype(np.float64), "Mimno_2011": np.asarray(mimno_2011, np.float64)})
-    marg = _metrics.marginal_topic_distrib(model.doc_topic_, doc_lengths)
     marg_topic = pd.DataFrame({"Topic": topics.astype(np.float64), "Marg_Topic": np.asarray(marg, np.float64)})
     topic_ass = pd.DataFrame({"Topic": topics.astype(np.int64), "Assignments": np.asarray(model.nz_, np.int64)})
     topic_names = ["Topic" + str(i) for i in range(1, n_topics + 1)]
