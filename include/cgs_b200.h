@@ -230,6 +230,26 @@ int cgs_normalize_scores(int device, const void *x, int dtype, int64_t n_rows, i
 int cgs_normalize_scores_device(int device, const void *d_x, int dtype, int64_t n_rows, int64_t n_cols,
                                 double scale_factor, void *d_out, void *d_colsum_scratch, void *stream);
 
+/* ---- differential features (diff_features.py:839-1120: markers -> get_wilcox_test_pvalues + get_log2_fc) ---- */
+/* For every row r < n_rows: scipy.stats.ranksums(fg[r], bg[r]) -- rank sum with average ranks for ties, normal
+ * approximation without tie or continuity correction -- as statistic z and two-sided pvalue, and
+ * log2fc = log2((mean(fg[r]) + 1e-12) / (mean(bg[r]) + 1e-12)); float64[n_rows] each.
+ * A group is described by a row-major matrix (row stride ld_* elements) and either a list of its columns
+ * (int32[n_*]) or NULL for columns 0 .. n_* - 1, so both call shapes of the reference are covered: two
+ * pre-subset matrices (get_wilcox_test_pvalues(fg_mat, bg_mat)) or ONE imputed matrix with two index lists
+ * (markers()); pass the same pointer and stride twice for the latter and it is uploaded once.
+ * dtype: 0 = int32, 1 = float32, 2 = float64.  Host pointers; rows are processed in device-sized rounds. */
+int cgs_ranksum_rows(int device, int dtype, int64_t n_rows,
+                     const void *fg, int64_t ld_fg, const int32_t *fg_cols, int32_t n_fg,
+                     const void *bg, int64_t ld_bg, const int32_t *bg_cols, int32_t n_bg,
+                     double *statistic, double *pvalue, double *log2fc);
+/* Device-resident variant (all pointers on `device`), asynchronous on `stream`: the consumer of an imputed
+ * chunk that never leaves the GPU (cgs_impute_plan_chunk_device -> this). */
+int cgs_ranksum_rows_device(int device, int dtype, int64_t n_rows,
+                            const void *d_fg, int64_t ld_fg, const int32_t *d_fg_cols, int32_t n_fg,
+                            const void *d_bg, int64_t ld_bg, const int32_t *d_bg_cols, int32_t n_bg,
+                            double *d_statistic, double *d_pvalue, double *d_log2fc, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

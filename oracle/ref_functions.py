@@ -8,6 +8,9 @@ imports fail), but the functions of interest are plain NumPy/``math`` code, so t
 * ``utils.subset_list`` / ``non_zero_rows``                          utils.py:113-126
 * ``calculate_imputed_accessibility`` (nested)   diff_features.py:398-492
 * ``calculate_normalized_scores`` (nested)       diff_features.py:540-548
+* ``markers`` / ``get_wilcox_test_pvalues`` / ``p_adjust_bh`` / ``get_log2_fc`` / ``mean_axis1`` /
+  ``subset_array_second_axis``                   diff_features.py:839-1120 (decorators dropped: numba.prange
+  becomes ``range``; ``np.asfarray``, removed in NumPy 2, is supplied as ``np.asarray(..., float)``)
 
 Used in THIS container to generate ``tests/golden/*.npz`` (``tests/golden/make_golden.py``);
 the GPU box has no /root/reference, so tests there read the committed fixtures.
@@ -70,3 +73,29 @@ def reference_calculate_imputed_accessibility():
 
 def reference_calculate_normalized_scores():
     return _load("diff_features.py", ["calculate_normalized_scores"])["calculate_normalized_scores"]
+
+
+class _NumpyWithAsfarray:
+    """NumPy 2 dropped ``asfarray`` (used at diff_features.py:1035); everything else is NumPy's."""
+
+    def __getattr__(self, name):
+        if name == "asfarray":
+            return lambda a: np.asarray(a, dtype=np.float64)
+        return getattr(np, name)
+
+
+def reference_diff_feature_functions():
+    """{'markers', 'get_wilcox_test_pvalues', 'p_adjust_bh', 'get_log2_fc'}: the reference's own code
+    (diff_features.py:839-1120) on top of the real ``scipy.stats.ranksums``."""
+    import sys
+    import types
+
+    import pandas as pd
+    from scipy.stats import ranksums
+
+    ns = _load("utils.py", ["get_position_index"])
+    extra = {"get_position_index": ns["get_position_index"], "ranksums": ranksums, "pd": pd, "sys": sys,
+             "logging": logging, "numba": types.SimpleNamespace(prange=range), "np": _NumpyWithAsfarray(),
+             "CistopicImputedFeatures": type("CistopicImputedFeatures", (), {})}
+    return _load("diff_features.py", ["subset_array_second_axis", "mean_axis1", "get_log2_fc", "p_adjust_bh",
+                                      "get_wilcox_test_pvalues", "markers"], extra=extra)

@@ -90,6 +90,12 @@ SIGNATURES = {
     "cgs_impute_plan_launch_count": (ctypes.c_int, [c_vp, c_i64p]),
     "cgs_normalize_scores": (ctypes.c_int, [ctypes.c_int, c_vp, ctypes.c_int, ctypes.c_int64, ctypes.c_int64,
                                             ctypes.c_double, c_vp]),
+    "cgs_ranksum_rows": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int64, c_vp, ctypes.c_int64, c_i32p,
+                                        ctypes.c_int32, c_vp, ctypes.c_int64, c_i32p, ctypes.c_int32,
+                                        c_f64p, c_f64p, c_f64p]),
+    "cgs_ranksum_rows_device": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int64, c_vp, ctypes.c_int64, c_vp,
+                                               ctypes.c_int32, c_vp, ctypes.c_int64, c_vp, ctypes.c_int32,
+                                               c_vp, c_vp, c_vp, c_vp]),
     "cgs_normalize_scores_device": (ctypes.c_int, [ctypes.c_int, c_vp, ctypes.c_int, ctypes.c_int64, ctypes.c_int64,
                                                    ctypes.c_double, c_vp, c_vp, c_vp]),
 }

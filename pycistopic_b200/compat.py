@@ -1,0 +1,55 @@
+"""Pickle interoperability with the reference package.
+
+pycisTopic pickles its models by qualified class name (``pickle.dump(model, ...)`` at
+lda_models.py:394-395 and cli/subcommand/topic_modeling.py:69-70), so a ``Topic{K}.pkl`` written here
+only loads in a pycisTopic environment -- and one written there only loads here -- if the class is
+importable as ``pycisTopic.lda_models.CistopicLDAModel``.  :func:`alias_pycistopic` arranges that.
+"""
+from __future__ import annotations
+
+import importlib
+import sys
+import types
+
+
+def alias_pycistopic(force: bool = False) -> bool:
+    """Make ``pycisTopic.lda_models`` / ``pycisTopic.diff_features`` resolve to this package's classes.
+
+    * pycisTopic is NOT importable (or ``force``): stub modules are registered in ``sys.modules`` and
+      :class:`CistopicLDAModel` / :class:`CistopicImputedFeatures` take the reference's module names, so
+      pickles written from now on carry ``pycisTopic.lda_models.CistopicLDAModel`` and reference pickles
+      load as this package's (attribute-for-attribute identical) classes.  Returns True.
+    * pycisTopic IS importable: nothing is touched (its own classes load its own pickles); use
+      :func:`to_reference_model` to hand a model to it.  Returns False.
+    """
+    from . import diff_features, lda_models
+    if not force:
+        try:
+            importlib.import_module("pycisTopic.lda_models")
+            return False
+        except Exception:
+            pass
+    root = sys.modules.get("pycisTopic")
+    if root is None or force:
+        root = types.ModuleType("pycisTopic")
+        root.__path__ = []  # a package, so that submodule imports resolve through sys.modules
+        sys.modules["pycisTopic"] = root
+    for name, mod in (("lda_models", lda_models), ("diff_features", diff_features)):
+        stub = types.ModuleType("pycisTopic." + name)
+        for attr in getattr(mod, "__all__", None) or [a for a in dir(mod) if not a.startswith("_")]:
+            setattr(stub, attr, getattr(mod, attr))
+        sys.modules["pycisTopic." + name] = stub
+        setattr(root, name, stub)
+    lda_models.CistopicLDAModel.__module__ = "pycisTopic.lda_models"
+    diff_features.CistopicImputedFeatures.__module__ = "pycisTopic.diff_features"
+    return True
+
+
+def to_reference_model(model):
+    """Re-wrap a :class:`pycistopic_b200.CistopicLDAModel` in the installed pycisTopic's own class (same seven
+    constructor arguments, lda_models.py:78-96) so that ``cistopic_obj.add_LDA_model`` / pickling use it."""
+    ref = importlib.import_module("pycisTopic.lda_models").CistopicLDAModel
+    out = ref(model.metrics, model.coherence, model.marg_topic, model.topic_ass, model.cell_topic,
+              model.topic_region, model.parameters)
+    out.cell_topic_harmony = model.cell_topic_harmony
+    return out

@@ -15,6 +15,7 @@
 #include "impute_kernels.cuh"
 #include "metrics_kernels.cuh"
 #include "normalize_kernels.cuh"
+#include "ranksum_kernels.cuh"
 #include "sampler_kernels.cuh"
 #include "stats_kernels.cuh"
 
@@ -1475,6 +1476,119 @@ int cgs_model_loglik_compat(cgs_model *m, double alpha_raw, double eta_raw, doub
     const double const_ll = ((double)W * std::lgamma(eta_raw) - std::lgamma(etaW)) * (double)K;
     *ll = doc_ll - const_prior + topic_ll - const_ll;
     return 0;
+}
+
+}  // extern "C"
+
+// ---- differential features: rank-sum test and log2 fold change per region (diff_features.py:839-1120) ----------
+namespace cgs {
+template <typename T>
+static int ranksum_launch_t(const RankSide &fg, const RankSide &bg, int64_t n_rows, double *d_stat, double *d_pval,
+                            double *d_l2fc, cudaStream_t stream, int num_sms) {
+    using K = typename RankKey<T>::type;
+    // the smaller group is sorted in shared memory, the larger one searches it
+    const bool sort_fg = fg.n <= bg.n;
+    const RankSide &sorted = sort_fg ? fg : bg, &other = sort_fg ? bg : fg;
+    const int32_t cap = (int32_t)(128 * 1024 / sizeof(K));  // values per shared-memory piece (plus 1/32 of padding)
+    int32_t piece = 2;
+    while (piece < sorted.n && piece < cap) piece <<= 1;
+    const size_t smem = ((size_t)piece + (size_t)piece / 32 + 1) * sizeof(K);
+    auto kernel = ranksum_rows_kernel<T>;
+    CGS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(136 * 1024)));
+    int per_sm = 1;
+    CGS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kRankThreads, smem));
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(n_rows, (int64_t)num_sms * std::max(1, per_sm)));
+    kernel<<<blocks, kRankThreads, smem, stream>>>(sorted, other, sort_fg ? 1 : 0, n_rows, piece, d_stat, d_pval, d_l2fc);
+    CGS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static int ranksum_launch(int dtype, const RankSide &fg, const RankSide &bg, int64_t n_rows, double *d_stat,
+                          double *d_pval, double *d_l2fc, cudaStream_t stream, int num_sms) {
+    switch (dtype) {
+        case 0: return ranksum_launch_t<int32_t>(fg, bg, n_rows, d_stat, d_pval, d_l2fc, stream, num_sms);
+        case 1: return ranksum_launch_t<float>(fg, bg, n_rows, d_stat, d_pval, d_l2fc, stream, num_sms);
+        case 2: return ranksum_launch_t<double>(fg, bg, n_rows, d_stat, d_pval, d_l2fc, stream, num_sms);
+    }
+    CGS_FAIL("dtype must be 0 (int32), 1 (float32) or 2 (float64)");
+}
+}  // namespace cgs
+
+extern "C" {
+
+int cgs_ranksum_rows_device(int device, int dtype, int64_t n_rows,
+                            const void *d_fg, int64_t ld_fg, const int32_t *d_fg_cols, int32_t n_fg,
+                            const void *d_bg, int64_t ld_bg, const int32_t *d_bg_cols, int32_t n_bg,
+                            double *d_statistic, double *d_pvalue, double *d_log2fc, void *stream) {
+    if (!d_fg || !d_bg || !d_statistic || !d_pvalue || !d_log2fc) CGS_FAIL("NULL argument");
+    if (n_fg < 1 || n_bg < 1) CGS_FAIL("foreground and background need at least one cell each");
+    if (n_rows <= 0) return 0;
+    DeviceGuard g(device);
+    if (!g.ok) CGS_FAIL("cannot select CUDA device");
+    int sms = kNumSMsFallback;
+    CGS_TRY(query_sms(device, &sms));
+    RankSide fg{d_fg, ld_fg, d_fg_cols, n_fg}, bg{d_bg, ld_bg, d_bg_cols, n_bg};
+    return ranksum_launch(dtype, fg, bg, n_rows, d_statistic, d_pvalue, d_log2fc, (cudaStream_t)stream, sms);
+}
+
+int cgs_ranksum_rows(int device, int dtype, int64_t n_rows,
+                     const void *fg, int64_t ld_fg, const int32_t *fg_cols, int32_t n_fg,
+                     const void *bg, int64_t ld_bg, const int32_t *bg_cols, int32_t n_bg,
+                     double *statistic, double *pvalue, double *log2fc) {
+    if (!fg || !bg || !statistic || !pvalue || !log2fc) CGS_FAIL("NULL argument");
+    if (dtype < 0 || dtype > 2) CGS_FAIL("dtype must be 0 (int32), 1 (float32) or 2 (float64)");
+    if (n_fg < 1 || n_bg < 1) CGS_FAIL("foreground and background need at least one cell each");
+    if (ld_fg < 1 || ld_bg < 1) CGS_FAIL("row strides must be positive");
+    if (n_rows <= 0) return 0;
+    if ((!fg_cols && n_fg > ld_fg) || (!bg_cols && n_bg > ld_bg)) CGS_FAIL("group is wider than its matrix");
+    DeviceGuard g(device);
+    if (!g.ok) CGS_FAIL("cannot select CUDA device");
+    CGS_TRY(configure_pool(device));
+    const size_t elem = dtype == 2 ? 8 : 4;
+    const bool shared_matrix = fg == bg && ld_fg == ld_bg;
+    // rows per round: about 1 GiB of matrix on the device at a time
+    const int64_t per_row = (int64_t)elem * (ld_fg + (shared_matrix ? 0 : ld_bg));
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(n_rows, ((int64_t)1 << 30) / std::max<int64_t>(1, per_row)));
+    cudaStream_t stream = nullptr;
+    CGS_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    uint8_t *d_a = nullptr, *d_b = nullptr;
+    int32_t *d_fc = nullptr, *d_bc = nullptr;
+    double *d_out = nullptr;
+    int rc = [&]() -> int {
+        CGS_TRY(dmalloc(&d_a, (size_t)chunk * ld_fg * elem, stream));
+        if (!shared_matrix) CGS_TRY(dmalloc(&d_b, (size_t)chunk * ld_bg * elem, stream));
+        CGS_TRY(dmalloc(&d_out, (size_t)chunk * 3, stream));
+        if (fg_cols) {
+            for (int32_t i = 0; i < n_fg; ++i)
+                if (fg_cols[i] < 0 || fg_cols[i] >= ld_fg) CGS_FAIL("foreground column index out of bounds");
+            CGS_TRY(dmalloc(&d_fc, (size_t)n_fg, stream));
+            CGS_CUDA(cudaMemcpyAsync(d_fc, fg_cols, sizeof(int32_t) * (size_t)n_fg, cudaMemcpyHostToDevice, stream));
+        }
+        if (bg_cols) {
+            for (int32_t i = 0; i < n_bg; ++i)
+                if (bg_cols[i] < 0 || bg_cols[i] >= ld_bg) CGS_FAIL("background column index out of bounds");
+            CGS_TRY(dmalloc(&d_bc, (size_t)n_bg, stream));
+            CGS_CUDA(cudaMemcpyAsync(d_bc, bg_cols, sizeof(int32_t) * (size_t)n_bg, cudaMemcpyHostToDevice, stream));
+        }
+        for (int64_t r0 = 0; r0 < n_rows; r0 += chunk) {
+            const int64_t nr = std::min(chunk, n_rows - r0);
+            CGS_CUDA(cudaMemcpyAsync(d_a, (const uint8_t *)fg + (size_t)r0 * ld_fg * elem, (size_t)nr * ld_fg * elem,
+                                     cudaMemcpyHostToDevice, stream));
+            if (!shared_matrix)
+                CGS_CUDA(cudaMemcpyAsync(d_b, (const uint8_t *)bg + (size_t)r0 * ld_bg * elem, (size_t)nr * ld_bg * elem,
+                                         cudaMemcpyHostToDevice, stream));
+            CGS_TRY(cgs_ranksum_rows_device(device, dtype, nr, d_a, ld_fg, d_fc, n_fg, shared_matrix ? d_a : d_b, ld_bg, d_bc,
+                                            n_bg, d_out, d_out + chunk, d_out + 2 * chunk, stream));
+            CGS_CUDA(cudaMemcpyAsync(statistic + r0, d_out, sizeof(double) * (size_t)nr, cudaMemcpyDeviceToHost, stream));
+            CGS_CUDA(cudaMemcpyAsync(pvalue + r0, d_out + chunk, sizeof(double) * (size_t)nr, cudaMemcpyDeviceToHost, stream));
+            CGS_CUDA(cudaMemcpyAsync(log2fc + r0, d_out + 2 * chunk, sizeof(double) * (size_t)nr, cudaMemcpyDeviceToHost, stream));
+            CGS_CUDA(cudaStreamSynchronize(stream));
+        }
+        return 0;
+    }();
+    dfree(d_a, stream); dfree(d_b, stream); dfree(d_out, stream); dfree(d_fc, stream); dfree(d_bc, stream);
+    cudaStreamDestroy(stream);
+    return rc;
 }
 
 }  // extern "C"

@@ -22,8 +22,27 @@ from . import _lib
 from ._lib import c_f32p, c_u8p, c_vp, check, ptr
 
 
+def get_position_index(query_list, target_list):
+    """utils.py:105-110."""
+    d = {k: idx for idx, k in enumerate(target_list)}
+    return [d[k] for k in query_list]
+
+
+def subset_list(target_list, index_list):
+    """utils.py:113-114."""
+    return list(map(target_list.__getitem__, index_list))
+
+
+def non_zero_rows(matrix):
+    """utils.py:117-126."""
+    if isinstance(matrix, scipy.sparse.csr_matrix):
+        matrix.eliminate_zeros()
+        return np.nonzero(matrix.getnnz(axis=1))[0]
+    return np.nonzero(np.count_nonzero(matrix, axis=1))[0]
+
+
 class CistopicImputedFeatures:
-    """cisTopic imputation data class (diff_features.py:26-59)."""
+    """cisTopic imputation data class (diff_features.py:26-59) with ``subset`` (:61-129)."""
 
     def __init__(self, imputed_acc, feature_names, cell_names, project):
         self.mtx = imputed_acc
@@ -34,6 +53,29 @@ class CistopicImputedFeatures:
     def __str__(self):
         return (f"CistopicImputedFeatures from project {self.project} with nCells × nFeatures = "
                 f"{len(self.cell_names)} × {len(self.feature_names)}")
+
+    def subset(self, cells=None, features=None, copy=False, split_pattern="___"):
+        """Keep the given cells and/or features, then drop all-zero features (diff_features.py:61-129)."""
+        mtx, cell_names, feature_names = self.mtx, self.cell_names, self.feature_names
+        if cells is not None:
+            try:
+                cells_index = get_position_index(cells, self.cell_names)
+            except KeyError:
+                tagged = [c.split(split_pattern)[0] if split_pattern in c else c for c in self.cell_names]
+                cells_index = get_position_index(cells, tagged)
+            mtx = mtx[:, cells_index]
+            cell_names = subset_list(cell_names, cells_index)
+        if features is not None:
+            features_index = get_position_index(features, feature_names)
+            mtx = mtx[features_index, :]
+            feature_names = subset_list(feature_names, features_index)
+        features_index = non_zero_rows(mtx)
+        if len(features_index) != mtx.shape[0]:
+            mtx = mtx[features_index, :]
+            feature_names = subset_list(feature_names, features_index)
+        if copy is True:
+            return CistopicImputedFeatures(mtx, feature_names, cell_names, self.project)
+        self.mtx, self.cell_names, self.feature_names = mtx, cell_names, feature_names
 
 
 def _logger():
@@ -169,3 +211,135 @@ def normalize_scores(imputed_acc, scale_factor=10 ** 4):
         raise TypeError("imputed_acc must be a CistopicImputedFeatures or a pandas DataFrame")
     log.info("Done!")
     return output
+
+
+# ---- differential features (diff_features.py:716-1120) -----------------------------
+_RANK_DTYPES = {np.dtype(np.int32): 0, np.dtype(np.float32): 1, np.dtype(np.float64): 2}
+
+
+def _rank_matrix(a):
+    a = np.asarray(a)
+    if a.ndim != 2:
+        raise ValueError("expected a 2-D matrix (features x cells)")
+    if a.dtype not in _RANK_DTYPES:
+        a = a.astype(np.float64)
+    return np.ascontiguousarray(a)
+
+
+def ranksum_rows(fg_mat, bg_mat=None, fg_cols=None, bg_cols=None, device=0):
+    """Per row: ``scipy.stats.ranksums`` statistic and p-value and the reference's log2 fold change, on the GPU
+    (``cgs_ranksum_rows``).  Either two matrices (features x fg cells, features x bg cells), or ONE matrix with
+    the two column-index lists.  Returns ``(statistic, pvalue, log2fc)``, float64 each."""
+    _lib.require_device()
+    fg = _rank_matrix(fg_mat)
+    bg = fg if bg_mat is None else _rank_matrix(bg_mat)
+    if fg.shape[0] != bg.shape[0]:
+        raise ValueError("Foreground matrix and background matrix have a different first dimension:"
+                         f" {fg.shape[0]} vs {bg.shape[0]}")
+    if bg is not fg and bg.dtype != fg.dtype:
+        common = np.result_type(fg.dtype, bg.dtype)
+        common = common if common in _RANK_DTYPES else np.dtype(np.float64)
+        fg, bg = np.ascontiguousarray(fg.astype(common)), np.ascontiguousarray(bg.astype(common))
+
+    def cols(c, width):
+        if c is None:
+            return None, width
+        c = np.ascontiguousarray(np.asarray(c, dtype=np.int64))
+        if c.size and (c.max() >= width or c.min() < -width):
+            bad = c.max() if c.max() >= width else c.min()
+            raise IndexError(f"index {bad} is out of bounds for axis 1 with size {width}")
+        # the statistic does not depend on the order inside a group: ascending columns make the gathers of a
+        # warp touch neighbouring addresses
+        c = np.sort(np.where(c < 0, c + width, c)).astype(np.int32)
+        return c, c.size
+
+    fc, n_fg = cols(fg_cols, fg.shape[1])
+    bc, n_bg = cols(bg_cols, bg.shape[1])
+    R = fg.shape[0]
+    stat, pval, l2fc = (np.full(R, np.nan) for _ in range(3))
+    if R == 0 or n_fg == 0 or n_bg == 0:  # scipy / numpy give NaN for an empty group
+        return stat, pval, l2fc
+    check(_lib.load().cgs_ranksum_rows(
+        device, _RANK_DTYPES[fg.dtype], R,
+        fg.ctypes.data_as(c_vp), fg.shape[1], ptr(fc, _lib.c_i32p) if fc is not None else None, n_fg,
+        bg.ctypes.data_as(c_vp), bg.shape[1], ptr(bc, _lib.c_i32p) if bc is not None else None, n_bg,
+        ptr(stat, _lib.c_f64p), ptr(pval, _lib.c_f64p), ptr(l2fc, _lib.c_f64p)))
+    return stat, pval, l2fc
+
+
+def get_wilcox_test_pvalues(fg_mat, bg_mat, device=0):
+    """Wilcoxon rank-sum p-value of every row of ``fg_mat`` against the same row of ``bg_mat``
+    (diff_features.py:968-995: ``scipy.stats.ranksums(fg_mat[i], y=bg_mat[i]).pvalue``), as a list."""
+    return ranksum_rows(fg_mat, bg_mat, device=device)[1].tolist()
+
+
+def get_log2_fc(fg_mat, bg_mat, device=0):
+    """``log2((mean(fg, axis=1) + 1e-12) / (mean(bg, axis=1) + 1e-12))`` (diff_features.py:1095-1120)."""
+    return ranksum_rows(fg_mat, bg_mat, device=device)[2]
+
+
+def p_adjust_bh(p):
+    """Benjamini-Hochberg correction (diff_features.py:1031-1041)."""
+    p = np.asarray(p, dtype=np.float64)
+    by_descend = p.argsort()[::-1]
+    by_orig = by_descend.argsort()
+    steps = float(len(p)) / np.arange(len(p), 0, -1)
+    q = np.minimum(1, np.minimum.accumulate(steps * p[by_descend]))
+    return q[by_orig]
+
+
+def markers(input_mat, barcode_group, contrast_name, adjpval_thr=0.05, log2fc_thr=1, n_cpu=1, device=0):
+    """Differential features of one contrast (diff_features.py:839-965): rank-sum p-value per feature between
+    the foreground and the background cells, Benjamini-Hochberg adjustment, log2 fold change, both thresholds,
+    sorted by ``Log2FC`` descending then ``Adjusted_pval``.  The matrix is handed to the GPU ONCE with the two
+    column lists (the reference copies out ``fg_mat`` and ``bg_mat`` first); ``n_cpu`` is ignored."""
+    log = _logger()
+    if isinstance(input_mat, pd.DataFrame):
+        mat, features, samples = input_mat.values, input_mat.index.tolist(), input_mat.columns
+    else:
+        mat, features, samples = input_mat.mtx, input_mat.feature_names, input_mat.cell_names
+    fg_cells_index = np.array(get_position_index(barcode_group[0], samples), dtype=np.int64)
+    bg_cells_index = np.array(get_position_index(barcode_group[1], samples), dtype=np.int64)
+    log.info(f"Subsetting data for {contrast_name} ({fg_cells_index.shape[0]} of {mat.shape[1]})")
+    if scipy.sparse.issparse(mat):
+        mat = mat.toarray()
+    log.info(f"Computing p-value for {contrast_name}")
+    _, wilcox_test_pvalues, log2_fc = ranksum_rows(mat, None, fg_cells_index, bg_cells_index, device=device)
+    log.info(f"Computing log2FC for {contrast_name}")
+    adj_pvalues = p_adjust_bh(wilcox_test_pvalues)
+    markers_dataframe = pd.DataFrame(
+        {"Log2FC": log2_fc, "Adjusted_pval": adj_pvalues, "Contrast": [contrast_name] * adj_pvalues.shape[0]},
+        index=features,
+    )
+    markers_dataframe = markers_dataframe.loc[markers_dataframe["Adjusted_pval"] <= adjpval_thr]
+    markers_dataframe = markers_dataframe.loc[markers_dataframe["Log2FC"] >= log2fc_thr]
+    markers_dataframe = markers_dataframe.sort_values(["Log2FC", "Adjusted_pval"], ascending=[False, True])
+    log.info(f"{contrast_name} done!")
+    return markers_dataframe
+
+
+def find_diff_features(cistopic_obj, imputed_features_obj, variable, var_features=None, contrasts=None,
+                       adjpval_thr=0.05, log2fc_thr=np.log2(1.5), split_pattern="___", n_cpu=1, device=0, **kwargs):
+    """Differential imputed features per contrast (diff_features.py:716-836): same arguments and the same
+    ``{contrast name: DataFrame}`` result; ``n_cpu`` and Ray keyword arguments are ignored."""
+    selected_cells = list(set(cistopic_obj.cell_data.index.tolist()) & set(imputed_features_obj.cell_names))
+    group_var = cistopic_obj.cell_data.loc[selected_cells, variable].dropna()
+    if contrasts is None:
+        levels = sorted(list(set(group_var.tolist())))
+        contrasts = [[[x], levels[: levels.index(x)] + levels[levels.index(x) + 1:]] for x in levels]
+        contrasts_names = levels
+    else:
+        contrasts_names = ["_".join(contrasts[i][0]) + "_VS_" + "_".join(contrasts[i][1]) for i in range(len(contrasts))]
+    barcode_groups = [
+        [group_var[group_var.isin(contrasts[i][0])].index.tolist(),
+         group_var[group_var.isin(contrasts[i][1])].index.tolist()]
+        for i in range(len(contrasts))
+    ]
+    subset_imputed_features_obj = imputed_features_obj.subset(cells=None, features=var_features, copy=True,
+                                                              split_pattern=split_pattern)
+    markers_list = [
+        markers(subset_imputed_features_obj, barcode_groups[i], contrasts_names[i], adjpval_thr=adjpval_thr,
+                log2fc_thr=log2fc_thr, n_cpu=1, device=device)
+        for i in range(len(contrasts))
+    ]
+    return {name: marker for name, marker in zip(contrasts_names, markers_list)}

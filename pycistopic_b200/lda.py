@@ -57,10 +57,19 @@ class Corpus:
         check(L.cgs_corpus_dims(self._h, ctypes.byref(d), ctypes.byref(w), ctypes.byref(n)))
         self.n_cells, self.n_regions, self.n_tokens = d.value, w.value, n.value
 
+    @staticmethod
+    def canonical_csr(binary_matrix, what="binary_matrix"):
+        """Validated ``(shape, indptr int64, indices int32)`` of a binary CSR; hand it to
+        :meth:`from_regions_by_cells` when several devices build a corpus from the same matrix."""
+        return _as_binary_csr(binary_matrix, what)
+
     @classmethod
     def from_regions_by_cells(cls, binary_matrix, device=0, cell_range=None):
         _lib.require_device()
-        (W, D), indptr, indices = _as_binary_csr(binary_matrix, "binary_matrix")
+        if isinstance(binary_matrix, tuple):  # already canonical (canonical_csr)
+            (W, D), indptr, indices = binary_matrix
+        else:
+            (W, D), indptr, indices = _as_binary_csr(binary_matrix, "binary_matrix")
         cb, ce = cell_range if cell_range is not None else (0, D)
         h = c_vp()
         check(_lib.load().cgs_corpus_from_regions_by_cells(ctypes.byref(h), device, ptr(indptr, c_i64p),

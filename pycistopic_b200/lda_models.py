@@ -104,9 +104,11 @@ def run_cgs_models(
     n_gpu = _lib.require_device()
     if devices is None:
         devices = list(range(n_gpu))
-    region_names = cistopic_obj.region_names
-    cell_names = cistopic_obj.cell_names
+    # one Index object shared by the K DataFrames of every model (pandas would rebuild it per model)
+    region_names = pd.Index(cistopic_obj.region_names)
+    cell_names = pd.Index(cistopic_obj.cell_names)
     binary_matrix = cistopic_obj.binary_matrix  # regions x cells; transposed on the device
+    canonical = Corpus.canonical_csr(binary_matrix)  # validated once, shared by every device's corpus build
     devices = devices[: max(1, min(len(devices), len(n_topics)))]
     plan = schedule_models(list(n_topics), len(devices))
     results = [None] * len(n_topics)
@@ -117,7 +119,7 @@ def run_cgs_models(
         # about a second per model at 300 k regions): one packing thread per device, results in order.
         from concurrent.futures import ThreadPoolExecutor
         try:
-            corpus = Corpus.from_regions_by_cells(binary_matrix, device=dev)
+            corpus = Corpus.from_regions_by_cells(canonical, device=dev)
             pending = {}
             try:
                 with ThreadPoolExecutor(max_workers=1) as packer:

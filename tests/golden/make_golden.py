@@ -66,6 +66,52 @@ def golden_impute():
     np.savez_compressed(os.path.join(HERE, "impute.npz"), **out)
 
 
+def golden_diff_features():
+    """markers / get_wilcox_test_pvalues / get_log2_fc / p_adjust_bh (diff_features.py:839-1120) executed from the
+    reference tree on top of the real scipy.stats.ranksums."""
+    import pandas as pd
+    ns = rf.reference_diff_feature_functions()
+    rng = np.random.default_rng(716)
+    out = {}
+    # (rows, n_fg, n_bg, dtype, kind): ties everywhere (small ints), continuous, negative values and zeros,
+    # a foreground larger than the background, a one-cell group
+    cases = [(64, 17, 40, np.int32, "ties"), (50, 33, 9, np.float32, "cont"), (40, 12, 31, np.float64, "signed"),
+             (30, 1, 25, np.int32, "ties"), (25, 60, 60, np.int32, "wide")]
+    for i, (R, n1, n2, dt, kind) in enumerate(cases):
+        if kind == "ties":
+            fg, bg = rng.integers(0, 4, (R, n1)), rng.integers(0, 5, (R, n2))
+        elif kind == "wide":
+            fg, bg = rng.integers(0, 10 ** 6, (R, n1)), rng.integers(0, 10 ** 6, (R, n2))
+            fg[:5] += 200000  # clearly shifted rows
+        elif kind == "cont":
+            fg, bg = rng.gamma(2.0, 1.0, (R, n1)), rng.gamma(2.2, 1.0, (R, n2))
+        else:
+            fg, bg = np.round(rng.normal(0, 1, (R, n1)), 1), np.round(rng.normal(0.3, 1, (R, n2)), 1)
+            fg[0, :] = 0.0
+            bg[0, :3] = -0.0
+        fg, bg = np.ascontiguousarray(fg.astype(dt)), np.ascontiguousarray(bg.astype(dt))
+        p = np.array(ns["get_wilcox_test_pvalues"](fg, bg), dtype=np.float64)
+        out[f"fg{i}"], out[f"bg{i}"], out[f"p{i}"] = fg, bg, p
+        out[f"l2fc{i}"] = np.asarray(ns["get_log2_fc"](fg, bg), dtype=np.float64)
+        out[f"padj{i}"] = ns["p_adjust_bh"](p)
+    # markers() on a DataFrame: one matrix, two barcode lists in scrambled order
+    R, C = 120, 90
+    mat = rng.integers(0, 30, (R, C)).astype(np.int32)
+    mat[:15, :30] += rng.integers(20, 60, (15, 30)).astype(np.int32)  # 15 true markers of the first 30 cells
+    cells = [f"cell{j}" for j in range(C)]
+    feats = [f"chr1:{j * 500}-{j * 500 + 500}" for j in range(R)]
+    fg_names = [cells[j] for j in rng.permutation(30)]
+    bg_names = [cells[j] for j in 30 + rng.permutation(60)[:50]]
+    df = pd.DataFrame(mat, index=feats, columns=cells)
+    res = ns["markers"](df, [fg_names, bg_names], "A_VS_B", adjpval_thr=0.05, log2fc_thr=np.log2(1.5), n_cpu=1)
+    out["m_mat"], out["m_fg"], out["m_bg"] = mat, np.array([cells.index(c) for c in fg_names]), \
+        np.array([cells.index(c) for c in bg_names])
+    out["m_index"] = np.array([feats.index(f) for f in res.index])
+    out["m_log2fc"], out["m_padj"] = res["Log2FC"].to_numpy(), res["Adjusted_pval"].to_numpy()
+    out["n"] = np.array(len(cases))
+    np.savez_compressed(os.path.join(HERE, "diff_features.npz"), **out)
+
+
 def golden_oracle_kat():
     """Known-answer vectors frozen from the CPU oracle (pins the oracle against regressions;
     parity with the real `lda` package stays UNPINNED, see oracle/lda_oracle.py)."""
@@ -108,4 +154,5 @@ if __name__ == "__main__":
     golden_loglikelihood()
     golden_impute()
     golden_oracle_kat()
+    golden_diff_features()
     print("golden fixtures written to", HERE)

@@ -5,6 +5,7 @@ import ctypes
 import os
 import pickle
 import re
+import sys
 
 import numpy as np
 import pandas as pd
@@ -276,3 +277,53 @@ def test_synthetic_shapes_and_duck_object():
     assert 0.02 < dens < 0.05
     m2, _, _ = make_binary_matrix(n_cells=50, n_regions=2000, density=0.03, n_true_topics=5, seed=2)
     assert (m != m2).nnz == 0
+
+
+def test_pickle_interop_with_reference_class_path(fitted, tmp_path):
+    """after alias_pycistopic() a saved Topic{K}.pkl names the reference's class
+    (pycisTopic.lda_models.CistopicLDAModel, lda_models.py:394-395) and loads back; run in a subprocess because
+    the alias renames the class for the whole interpreter."""
+    import subprocess
+    m, cells, regions, X, o = fitted
+    model = lda_models.build_cistopic_model(o, m, 7, cells, regions, 30, 555, 50, True, 0.1, False, 5, 1.25)
+    plain = tmp_path / "plain.pkl"
+    with open(plain, "wb") as f:
+        pickle.dump(model, f)
+    code = f"""
+import pickle, sys
+sys.path.insert(0, {ROOT!r})
+from pycistopic_b200.compat import alias_pycistopic
+assert alias_pycistopic() is True
+import pycisTopic.lda_models as ref
+from pycisTopic.lda_models import CistopicLDAModel
+m = pickle.load(open({str(plain)!r}, "rb"))
+blob = pickle.dumps(m)
+assert b"pycisTopic.lda_models" in blob and b"pycistopic_b200" not in blob
+again = pickle.loads(blob)
+assert type(again) is CistopicLDAModel and again.n_topic == 7 and again.topic_region.equals(m.topic_region)
+print("ok")
+"""
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert res.returncode == 0 and res.stdout.strip().endswith("ok"), res.stderr
+
+
+def test_diff_feature_oracle_matches_reference_golden():
+    """oracle/diff_oracle.py against tests/golden/diff_features.npz (the reference's own get_wilcox_test_pvalues /
+    get_log2_fc / p_adjust_bh, diff_features.py:968-1120, executed from the tree) and its NumPy restatement of
+    scipy.stats.ranksums against scipy itself."""
+    from oracle import diff_oracle as do
+    from pycistopic_b200 import diff_features as pdf
+    g = np.load(os.path.join(ROOT, "tests", "golden", "diff_features.npz"))
+    for i in range(int(g["n"])):
+        fg, bg = g[f"fg{i}"], g[f"bg{i}"]
+        stat, p = do.ranksums_rows(fg, bg)
+        np.testing.assert_allclose(p, g[f"p{i}"], rtol=1e-12)
+        # float32 input: the reference's mean accumulates in float32, the oracle (and the GPU) in float64
+        f32 = fg.dtype == np.float32
+        np.testing.assert_allclose(do.log2_fc(fg, bg), g[f"l2fc{i}"], rtol=1e-6 if f32 else 1e-12,
+                                   atol=2e-6 if f32 else 0, equal_nan=True)
+        np.testing.assert_allclose(do.p_adjust_bh(p), g[f"padj{i}"], rtol=1e-14)
+        np.testing.assert_allclose(pdf.p_adjust_bh(p), g[f"padj{i}"], rtol=1e-14)
+        for r in range(0, fg.shape[0], 7):
+            z, pr = do.ranksums_restated(fg[r], bg[r])
+            assert z == pytest.approx(stat[r], rel=1e-12, abs=1e-15) and pr == pytest.approx(p[r], rel=1e-12)
