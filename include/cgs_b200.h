@@ -250,6 +250,27 @@ int cgs_ranksum_rows_device(int device, int dtype, int64_t n_rows,
                             const void *d_bg, int64_t ld_bg, const int32_t *d_bg_cols, int32_t n_bg,
                             double *d_statistic, double *d_pvalue, double *d_log2fc, void *stream);
 
+/* ---- fused consumers of the imputed matrix -----------------------------
+ * impute_accessibility returns a dense regions x cells matrix (diff_features.py:434-441, :503) that normalize_scores
+ * (:511-574) and find_diff_features (:716-836) then read back.  These entry points take the two FACTORS instead
+ * (topic_region n_regions x n_topics, cell_topic n_topics x n_cells, fp32 row-major host pointers, exactly the
+ * operands of cgs_impute_chunk) and recompute the product chunk by chunk on the device, so the matrix never exists. */
+/* normalize_scores(impute_accessibility(...)): out receives log1p(x / (colsum(x) / norm_scale)) for the regions that
+ * have a non-zero imputed value, in order (float64 when as_int32 != 0, else float32; room for n_regions rows);
+ * *n_kept = number of rows written; row_nonzero (uint8[n_regions]) and column_totals (int64[n_cells] when
+ * as_int32 != 0, else float64[n_cells]) may be NULL.  Two passes over the chunks: totals, then normalisation. */
+int cgs_impute_normalized(int device, const float *topic_region, const float *cell_topic, int32_t n_regions,
+                          int32_t n_topics, int32_t n_cells, float impute_scale, int as_int32, double norm_scale,
+                          int32_t chunk_rows, void *out, uint8_t *row_nonzero, void *column_totals, int64_t *n_kept);
+/* markers() for n_contrasts contrasts in one pass: contrast k compares the cells fg_cols[fg_offsets[k] ..
+ * fg_offsets[k+1]) with bg_cols[bg_offsets[k] .. bg_offsets[k+1]); statistic / pvalue / log2fc are float64
+ * [n_contrasts x n_regions] (cgs_ranksum_rows semantics); every chunk is imputed once and read by all contrasts. */
+int cgs_impute_ranksum(int device, const float *topic_region, const float *cell_topic, int32_t n_regions,
+                       int32_t n_topics, int32_t n_cells, float impute_scale, int as_int32, int32_t chunk_rows,
+                       int32_t n_contrasts, const int32_t *fg_cols, const int64_t *fg_offsets,
+                       const int32_t *bg_cols, const int64_t *bg_offsets,
+                       double *statistic, double *pvalue, double *log2fc, uint8_t *row_nonzero);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1592,3 +1592,171 @@ int cgs_ranksum_rows(int device, int dtype, int64_t n_rows,
 }
 
 }  // extern "C"
+
+// ---- fused consumers of the imputed matrix: the product is recomputed chunk by chunk on the
+// device (a 20 000 x 200 000 chunk costs 4 ms) and consumed there, so the regions x cells matrix -- 800 GB at atlas
+// scale -- never exists, neither in HBM nor on the host.
+namespace cgs {
+struct ImputeStream {
+    cgs_impute_plan *plan = nullptr;
+    cudaStream_t stream = nullptr;
+    float *d_a = nullptr;      // R x K topic_region
+    uint8_t *d_chunk = nullptr;  // chunk_rows x C, 4 bytes per element
+    uint8_t *d_flags = nullptr;  // R
+    int32_t R = 0, K = 0, C = 0, chunk = 0;
+    float scale = 1.0f;
+    int as_int32 = 0;
+
+    int open(int device, const float *topic_region, const float *cell_topic, int32_t R_, int32_t K_, int32_t C_,
+             float scale_, int as_int32_, int32_t chunk_rows) {
+        R = R_; K = K_; C = C_; scale = scale_; as_int32 = as_int32_;
+        chunk = std::max<int32_t>(1, std::min(chunk_rows > 0 ? chunk_rows : 20000, R));
+        CGS_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        CGS_TRY(cgs_impute_plan_create(&plan, device, cell_topic, 0, K, C, stream));
+        CGS_TRY(dmalloc(&d_a, (size_t)R * K, stream));
+        CGS_TRY(dmalloc(&d_chunk, (size_t)chunk * C * 4, stream));
+        CGS_TRY(dmalloc(&d_flags, (size_t)R, stream));
+        CGS_CUDA(cudaMemcpyAsync(d_a, topic_region, sizeof(float) * (size_t)R * K, cudaMemcpyHostToDevice, stream));
+        return 0;
+    }
+    // imputes rows [r0, r0 + n) into d_chunk (and their non-zero flags into d_flags + r0)
+    int run(int32_t r0, int32_t n) {
+        return cgs_impute_plan_chunk_device(plan, d_a + (size_t)r0 * K, n, scale, as_int32, d_chunk, d_flags + r0, stream);
+    }
+    void close() {
+        dfree(d_a, stream); dfree(d_chunk, stream); dfree(d_flags, stream);
+        if (plan) cgs_impute_plan_destroy(plan);
+        if (stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); }
+    }
+};
+}  // namespace cgs
+
+extern "C" {
+
+int cgs_impute_normalized(int device, const float *topic_region, const float *cell_topic, int32_t n_regions,
+                          int32_t n_topics, int32_t n_cells, float impute_scale, int as_int32, double norm_scale,
+                          int32_t chunk_rows, void *out, uint8_t *row_nonzero, void *column_totals, int64_t *n_kept) {
+    if (!topic_region || !cell_topic || !out || !n_kept) CGS_FAIL("NULL argument");
+    if (n_regions <= 0 || n_topics <= 0 || n_cells <= 0) CGS_FAIL("empty operand");
+    if (!(norm_scale != 0.0)) CGS_FAIL("scale_factor must not be zero");
+    DeviceGuard g(device);
+    if (!g.ok) CGS_FAIL("cannot select CUDA device");
+    CGS_TRY(configure_pool(device));
+    ImputeStream is;
+    uint8_t *d_norm = nullptr, *d_tot = nullptr;
+    const size_t out_elem = as_int32 ? 8 : 4;
+    const int64_t C = n_cells;
+    std::vector<uint8_t> flags((size_t)n_regions);
+    int rc = [&]() -> int {
+        CGS_TRY(is.open(device, topic_region, cell_topic, n_regions, n_topics, n_cells, impute_scale, as_int32, chunk_rows));
+        CGS_TRY(dmalloc(&d_norm, (size_t)is.chunk * C * out_elem, is.stream));
+        CGS_TRY(dmalloc(&d_tot, (size_t)C * 8, is.stream));
+        CGS_CUDA(cudaMemsetAsync(d_tot, 0, (size_t)C * 8, is.stream));
+        // pass 1: per-cell totals over every region (all-zero regions add nothing) and the row flags
+        for (int32_t r0 = 0; r0 < n_regions; r0 += is.chunk) {
+            const int32_t n = std::min(is.chunk, n_regions - r0);
+            CGS_TRY(is.run(r0, n));
+            dim3 grid((unsigned)ceil_div(C, kNormCols), (unsigned)ceil_div(n, kNormSlab));
+            if (as_int32) colsum_kernel<int32_t><<<grid, kNormCols, 0, is.stream>>>((const int32_t *)is.d_chunk, n, C, (long long *)d_tot);
+            else colsum_kernel<float><<<grid, kNormCols, 0, is.stream>>>((const float *)is.d_chunk, n, C, (double *)d_tot);
+            CGS_CUDA(cudaGetLastError());
+        }
+        CGS_CUDA(cudaMemcpyAsync(flags.data(), is.d_flags, (size_t)n_regions, cudaMemcpyDeviceToHost, is.stream));
+        if (column_totals) CGS_CUDA(cudaMemcpyAsync(column_totals, d_tot, (size_t)C * 8, cudaMemcpyDeviceToHost, is.stream));
+        CGS_CUDA(cudaStreamSynchronize(is.stream));
+        // pass 2: recompute, normalise, and hand back only the regions that have a non-zero entry
+        int64_t kept = 0;
+        for (int32_t r0 = 0; r0 < n_regions; r0 += is.chunk) {
+            const int32_t n = std::min(is.chunk, n_regions - r0);
+            CGS_TRY(is.run(r0, n));
+            dim3 grid((unsigned)ceil_div(C, kNormCols), (unsigned)ceil_div(n, kNormSlab));
+            if (as_int32)
+                normalize_log1p_kernel<int32_t, double><<<grid, kNormCols, 0, is.stream>>>(
+                    (const int32_t *)is.d_chunk, n, C, (const long long *)d_tot, norm_scale, (double *)d_norm);
+            else
+                normalize_log1p_kernel<float, float><<<grid, kNormCols, 0, is.stream>>>(
+                    (const float *)is.d_chunk, n, C, (const double *)d_tot, norm_scale, (float *)d_norm);
+            CGS_CUDA(cudaGetLastError());
+            for (int32_t i = 0; i < n;) {  // runs of consecutive kept rows
+                if (!flags[(size_t)r0 + i]) { ++i; continue; }
+                int32_t j = i;
+                while (j < n && flags[(size_t)r0 + j]) ++j;
+                CGS_CUDA(cudaMemcpyAsync((uint8_t *)out + (size_t)kept * C * out_elem, d_norm + (size_t)i * C * out_elem,
+                                         (size_t)(j - i) * C * out_elem, cudaMemcpyDeviceToHost, is.stream));
+                kept += j - i;
+                i = j;
+            }
+            CGS_CUDA(cudaStreamSynchronize(is.stream));
+        }
+        *n_kept = kept;
+        if (row_nonzero) memcpy(row_nonzero, flags.data(), (size_t)n_regions);
+        return 0;
+    }();
+    dfree(d_norm, is.stream); dfree(d_tot, is.stream);
+    is.close();
+    return rc;
+}
+
+int cgs_impute_ranksum(int device, const float *topic_region, const float *cell_topic, int32_t n_regions,
+                       int32_t n_topics, int32_t n_cells, float impute_scale, int as_int32, int32_t chunk_rows,
+                       int32_t n_contrasts, const int32_t *fg_cols, const int64_t *fg_offsets,
+                       const int32_t *bg_cols, const int64_t *bg_offsets,
+                       double *statistic, double *pvalue, double *log2fc, uint8_t *row_nonzero) {
+    if (!topic_region || !cell_topic || !fg_cols || !fg_offsets || !bg_cols || !bg_offsets || !statistic || !pvalue || !log2fc)
+        CGS_FAIL("NULL argument");
+    if (n_regions <= 0 || n_topics <= 0 || n_cells <= 0) CGS_FAIL("empty operand");
+    if (n_contrasts < 1) CGS_FAIL("need at least one contrast");
+    for (int32_t k = 0; k < n_contrasts; ++k)
+        if (fg_offsets[k + 1] <= fg_offsets[k] || bg_offsets[k + 1] <= bg_offsets[k])
+            CGS_FAIL("foreground and background need at least one cell each");
+    const int64_t n_fg_all = fg_offsets[n_contrasts], n_bg_all = bg_offsets[n_contrasts];
+    for (int64_t i = 0; i < n_fg_all; ++i)
+        if (fg_cols[i] < 0 || fg_cols[i] >= n_cells) CGS_FAIL("foreground column index out of bounds");
+    for (int64_t i = 0; i < n_bg_all; ++i)
+        if (bg_cols[i] < 0 || bg_cols[i] >= n_cells) CGS_FAIL("background column index out of bounds");
+    DeviceGuard g(device);
+    if (!g.ok) CGS_FAIL("cannot select CUDA device");
+    CGS_TRY(configure_pool(device));
+    int sms = kNumSMsFallback;
+    CGS_TRY(query_sms(device, &sms));
+    ImputeStream is;
+    int32_t *d_fg = nullptr, *d_bg = nullptr;
+    double *d_res = nullptr;  // [3][n_contrasts][chunk]
+    int rc = [&]() -> int {
+        CGS_TRY(is.open(device, topic_region, cell_topic, n_regions, n_topics, n_cells, impute_scale, as_int32, chunk_rows));
+        CGS_TRY(dmalloc(&d_fg, (size_t)n_fg_all, is.stream));
+        CGS_TRY(dmalloc(&d_bg, (size_t)n_bg_all, is.stream));
+        CGS_TRY(dmalloc(&d_res, (size_t)3 * n_contrasts * is.chunk, is.stream));
+        CGS_CUDA(cudaMemcpyAsync(d_fg, fg_cols, sizeof(int32_t) * (size_t)n_fg_all, cudaMemcpyHostToDevice, is.stream));
+        CGS_CUDA(cudaMemcpyAsync(d_bg, bg_cols, sizeof(int32_t) * (size_t)n_bg_all, cudaMemcpyHostToDevice, is.stream));
+        const int dtype = as_int32 ? 0 : 1;
+        for (int32_t r0 = 0; r0 < n_regions; r0 += is.chunk) {
+            const int32_t n = std::min(is.chunk, n_regions - r0);
+            CGS_TRY(is.run(r0, n));  // one product per chunk, every contrast reads it from HBM / L2
+            for (int32_t k = 0; k < n_contrasts; ++k) {
+                RankSide fg{is.d_chunk, n_cells, d_fg + fg_offsets[k], (int32_t)(fg_offsets[k + 1] - fg_offsets[k])};
+                RankSide bg{is.d_chunk, n_cells, d_bg + bg_offsets[k], (int32_t)(bg_offsets[k + 1] - bg_offsets[k])};
+                double *base = d_res + (size_t)k * is.chunk;
+                const size_t plane = (size_t)n_contrasts * is.chunk;
+                CGS_TRY(ranksum_launch(dtype, fg, bg, n, base, base + plane, base + 2 * plane, is.stream, sms));
+            }
+            for (int32_t k = 0; k < n_contrasts; ++k) {
+                const double *base = d_res + (size_t)k * is.chunk;
+                const size_t plane = (size_t)n_contrasts * is.chunk, o = (size_t)k * n_regions + r0;
+                CGS_CUDA(cudaMemcpyAsync(statistic + o, base, sizeof(double) * n, cudaMemcpyDeviceToHost, is.stream));
+                CGS_CUDA(cudaMemcpyAsync(pvalue + o, base + plane, sizeof(double) * n, cudaMemcpyDeviceToHost, is.stream));
+                CGS_CUDA(cudaMemcpyAsync(log2fc + o, base + 2 * plane, sizeof(double) * n, cudaMemcpyDeviceToHost, is.stream));
+            }
+            CGS_CUDA(cudaStreamSynchronize(is.stream));
+        }
+        if (row_nonzero) {
+            CGS_CUDA(cgs_memcpy_sync(is.stream, row_nonzero, is.d_flags, (size_t)n_regions, cudaMemcpyDeviceToHost));
+        }
+        return 0;
+    }();
+    dfree(d_fg, is.stream); dfree(d_bg, is.stream); dfree(d_res, is.stream);
+    is.close();
+    return rc;
+}
+
+}  // extern "C"

@@ -78,6 +78,130 @@ class CistopicImputedFeatures:
         self.mtx, self.cell_names, self.feature_names = mtx, cell_names, feature_names
 
 
+class FactoredImputedFeatures:
+    """Imputed accessibility kept as its two factors (``impute_accessibility(..., materialize=False)``).
+
+    The reference materialises ``topic_region @ cell_topic`` as one dense regions x cells array
+    (diff_features.py:434-441, :503) -- 8 GB for 200 k regions x 10 k cells, 800 GB at atlas scale -- and
+    ``normalize_scores`` / ``find_diff_features`` read it back.  This object holds only ``topic_region``
+    (regions x topics) and ``cell_topic`` (topics x cells) in fp32; its consumers recompute the product chunk by
+    chunk on the GPU and consume it there (``cgs_impute_normalized``, ``cgs_impute_ranksum``).  ``feature_names``
+    lists, like the reference, only the regions with a non-zero imputed value (computed on first use);
+    ``to_dense()`` gives the reference's :class:`CistopicImputedFeatures`.
+    """
+
+    def __init__(self, topic_region, cell_topic, region_names, cell_names, scale_factor, chunk_size, project,
+                 device=0):
+        self.topic_region = np.ascontiguousarray(topic_region, dtype=np.float32)
+        self.cell_topic = np.ascontiguousarray(cell_topic, dtype=np.float32)
+        if self.topic_region.shape[1] != self.cell_topic.shape[0]:
+            raise ValueError(f"matmul: topic_region has {self.topic_region.shape[1]} topics, "
+                             f"cell_topic has {self.cell_topic.shape[0]}")
+        self.region_names = list(region_names)
+        self.cell_names = list(cell_names)
+        self.scale_factor = scale_factor
+        self.chunk_size = int(chunk_size)
+        self.project = project
+        self.device = device
+        self._row_nonzero = None
+
+    @property
+    def as_int32(self):
+        return isinstance(self.scale_factor, int) and self.scale_factor != 1
+
+    @property
+    def impute_scale(self):
+        return float(np.float32(self.scale_factor)) if self.as_int32 else 1.0
+
+    def __str__(self):
+        return (f"FactoredImputedFeatures from project {self.project} with nCells × nFeatures = "
+                f"{len(self.cell_names)} × {self.topic_region.shape[0]} (not materialised)")
+
+    def _operands(self):
+        R, K = self.topic_region.shape
+        return (self.device, ptr(self.topic_region, c_f32p), ptr(self.cell_topic, c_f32p), R, K, self.cell_topic.shape[1],
+                self.impute_scale, int(self.as_int32))
+
+    def ranksum(self, contrasts_cols):
+        """``[(fg column indices, bg column indices), ...]`` -> ``(statistic, pvalue, log2fc, row_nonzero)``,
+        the first three ``n_contrasts x n_regions`` float64; one imputation pass serves every contrast."""
+        _lib.require_device()
+        R, C = self.topic_region.shape[0], self.cell_topic.shape[1]
+
+        def pack(groups):
+            offs = np.zeros(len(groups) + 1, np.int64)
+            cols = []
+            for i, g in enumerate(groups):
+                g = np.asarray(g, dtype=np.int64)
+                if g.size and (g.max() >= C or g.min() < -C):
+                    raise IndexError(f"index {g.max() if g.max() >= C else g.min()} is out of bounds for axis 1 with size {C}")
+                cols.append(np.sort(np.where(g < 0, g + C, g)).astype(np.int32))
+                offs[i + 1] = offs[i] + g.size
+            return np.ascontiguousarray(np.concatenate(cols) if cols else np.zeros(0, np.int32)), offs
+
+        n = len(contrasts_cols)
+        stat, pval, l2fc = (np.full((n, R), np.nan) for _ in range(3))
+        flags = np.empty(R, np.uint8)
+        live = [i for i, (f, b) in enumerate(contrasts_cols) if len(f) and len(b)]
+        if live:
+            fg, fo = pack([contrasts_cols[i][0] for i in live])
+            bg, bo = pack([contrasts_cols[i][1] for i in live])
+            s2, p2, l2 = (np.empty((len(live), R), np.float64) for _ in range(3))
+            check(_lib.load().cgs_impute_ranksum(*self._operands(), self.chunk_size, len(live),
+                                                 ptr(fg, _lib.c_i32p), ptr(fo, _lib.c_i64p), ptr(bg, _lib.c_i32p),
+                                                 ptr(bo, _lib.c_i64p), ptr(s2, _lib.c_f64p), ptr(p2, _lib.c_f64p),
+                                                 ptr(l2, _lib.c_f64p), ptr(flags, c_u8p)))
+            stat[live], pval[live], l2fc[live] = s2, p2, l2
+            self._row_nonzero = flags.astype(bool)
+        return stat, pval, l2fc, self.row_nonzero
+
+    def normalized(self, scale_factor=10 ** 4):
+        """``normalize_scores`` of the imputed matrix without materialising it: a dense
+        :class:`CistopicImputedFeatures` (float64 for the int32 imputation, float32 otherwise)."""
+        _lib.require_device()
+        R, C = self.topic_region.shape[0], self.cell_topic.shape[1]
+        out = np.empty((R, C), np.float64 if self.as_int32 else np.float32)
+        flags = np.empty(R, np.uint8)
+        kept = ctypes.c_int64()
+        check(_lib.load().cgs_impute_normalized(*self._operands(), float(scale_factor), self.chunk_size,
+                                                out.ctypes.data_as(c_vp), ptr(flags, c_u8p), None, ctypes.byref(kept)))
+        self._row_nonzero = flags.astype(bool)
+        return CistopicImputedFeatures(out[: kept.value], self.feature_names, self.cell_names, self.project)
+
+    @property
+    def row_nonzero(self):
+        if self._row_nonzero is None:  # one imputation pass with a one-cell contrast is the cheapest way to the flags
+            self.ranksum([([0], [self.cell_topic.shape[1] - 1])])
+        return self._row_nonzero
+
+    @property
+    def feature_names(self):
+        return [n for n, k in zip(self.region_names, self.row_nonzero) if k]
+
+    def subset(self, cells=None, features=None, copy=False, split_pattern="___"):
+        """Same selection as :meth:`CistopicImputedFeatures.subset`, applied to the factors."""
+        tr, ct, regions, cell_names = self.topic_region, self.cell_topic, self.region_names, self.cell_names
+        if cells is not None:
+            try:
+                idx = get_position_index(cells, cell_names)
+            except KeyError:
+                idx = get_position_index(cells, [c.split(split_pattern)[0] if split_pattern in c else c for c in cell_names])
+            ct, cell_names = ct[:, idx], subset_list(cell_names, idx)
+        if features is not None:
+            idx = get_position_index(features, regions)
+            tr, regions = tr[idx], subset_list(regions, idx)
+        out = FactoredImputedFeatures(tr, ct, regions, cell_names, self.scale_factor, self.chunk_size, self.project,
+                                      self.device)
+        if copy is True:
+            return out
+        self.__dict__.update(out.__dict__)
+
+    def to_dense(self):
+        imputed_acc, keep = calculate_imputed_accessibility(self.topic_region, self.cell_topic, self.region_names,
+                                                            self.scale_factor, self.chunk_size, device=self.device)
+        return CistopicImputedFeatures(imputed_acc, keep, self.cell_names, self.project)
+
+
 def _logger():
     level = logging.INFO
     log_format = "%(asctime)s %(name)-12s %(levelname)-8s %(message)s"
@@ -138,8 +262,11 @@ def impute_accessibility(
     chunk_size=20000,
     project="cisTopic_Impute",
     device=0,
+    materialize=True,
 ):
-    """Impute region accessibility (diff_features.py:340-508)."""
+    """Impute region accessibility (diff_features.py:340-508).  ``materialize=False`` (extension) returns a
+    :class:`FactoredImputedFeatures` whose consumers (``normalize_scores``, ``markers``, ``find_diff_features``)
+    recompute the product on the GPU instead of reading a dense regions x cells array."""
     log = _logger()
     model = cistopic_obj.selected_model
     cell_names = cistopic_obj.cell_names
@@ -155,6 +282,9 @@ def impute_accessibility(
     cell_topic = cell_topic.to_numpy().astype(np.float32)
     topic_region = topic_region.to_numpy().astype(np.float32)
 
+    if not materialize:
+        return FactoredImputedFeatures(topic_region, cell_topic, region_names, cell_names, scale_factor, chunk_size,
+                                       project, device)
     log.info("Imputing region accessibility")
     imputed_acc, region_names_to_keep = calculate_imputed_accessibility(
         topic_region=topic_region,
@@ -200,7 +330,9 @@ def normalize_scores(imputed_acc, scale_factor=10 ** 4):
     (SURVEY.md section 8f, row N1)."""
     log = _logger()
     log.info("Normalizing imputed data")
-    if isinstance(imputed_acc, CistopicImputedFeatures):
+    if isinstance(imputed_acc, FactoredImputedFeatures):
+        output = imputed_acc.normalized(scale_factor)
+    elif isinstance(imputed_acc, CistopicImputedFeatures):
         mtx = imputed_acc.mtx.toarray() if scipy.sparse.issparse(imputed_acc.mtx) else imputed_acc.mtx
         output = CistopicImputedFeatures(calculate_normalized_scores(mtx, scale_factor), imputed_acc.feature_names,
                                          imputed_acc.cell_names, imputed_acc.project)
@@ -294,6 +426,8 @@ def markers(input_mat, barcode_group, contrast_name, adjpval_thr=0.05, log2fc_th
     sorted by ``Log2FC`` descending then ``Adjusted_pval``.  The matrix is handed to the GPU ONCE with the two
     column lists (the reference copies out ``fg_mat`` and ``bg_mat`` first); ``n_cpu`` is ignored."""
     log = _logger()
+    if isinstance(input_mat, FactoredImputedFeatures):
+        return _markers_factored(input_mat, [barcode_group], [contrast_name], adjpval_thr, log2fc_thr, log)[0]
     if isinstance(input_mat, pd.DataFrame):
         mat, features, samples = input_mat.values, input_mat.index.tolist(), input_mat.columns
     else:
@@ -307,15 +441,35 @@ def markers(input_mat, barcode_group, contrast_name, adjpval_thr=0.05, log2fc_th
     _, wilcox_test_pvalues, log2_fc = ranksum_rows(mat, None, fg_cells_index, bg_cells_index, device=device)
     log.info(f"Computing log2FC for {contrast_name}")
     adj_pvalues = p_adjust_bh(wilcox_test_pvalues)
+    markers_dataframe = _markers_frame(log2_fc, adj_pvalues, contrast_name, features, adjpval_thr, log2fc_thr)
+    log.info(f"{contrast_name} done!")
+    return markers_dataframe
+
+
+def _markers_frame(log2_fc, adj_pvalues, contrast_name, features, adjpval_thr, log2fc_thr):
+    """The DataFrame, thresholds and ordering of diff_features.py:941-963."""
     markers_dataframe = pd.DataFrame(
         {"Log2FC": log2_fc, "Adjusted_pval": adj_pvalues, "Contrast": [contrast_name] * adj_pvalues.shape[0]},
         index=features,
     )
     markers_dataframe = markers_dataframe.loc[markers_dataframe["Adjusted_pval"] <= adjpval_thr]
     markers_dataframe = markers_dataframe.loc[markers_dataframe["Log2FC"] >= log2fc_thr]
-    markers_dataframe = markers_dataframe.sort_values(["Log2FC", "Adjusted_pval"], ascending=[False, True])
-    log.info(f"{contrast_name} done!")
-    return markers_dataframe
+    return markers_dataframe.sort_values(["Log2FC", "Adjusted_pval"], ascending=[False, True])
+
+
+def _markers_factored(factored, barcode_groups, contrast_names, adjpval_thr, log2fc_thr, log):
+    """markers() of every contrast from ONE pass over the recomputed imputation chunks."""
+    samples = factored.cell_names
+    cols = [(get_position_index(g[0], samples), get_position_index(g[1], samples)) for g in barcode_groups]
+    for name, (f, _) in zip(contrast_names, cols):
+        log.info(f"Computing p-value and log2FC for {name} ({len(f)} of {len(samples)})")
+    _, pval, l2fc, keep = factored.ranksum(cols)
+    features = factored.feature_names
+    out = []
+    for k, name in enumerate(contrast_names):  # all-zero regions are not tested (impute_accessibility drops them)
+        out.append(_markers_frame(l2fc[k][keep], p_adjust_bh(pval[k][keep]), name, features, adjpval_thr, log2fc_thr))
+        log.info(f"{name} done!")
+    return out
 
 
 def find_diff_features(cistopic_obj, imputed_features_obj, variable, var_features=None, contrasts=None,
@@ -337,6 +491,10 @@ def find_diff_features(cistopic_obj, imputed_features_obj, variable, var_feature
     ]
     subset_imputed_features_obj = imputed_features_obj.subset(cells=None, features=var_features, copy=True,
                                                               split_pattern=split_pattern)
+    if isinstance(subset_imputed_features_obj, FactoredImputedFeatures):
+        markers_list = _markers_factored(subset_imputed_features_obj, barcode_groups, contrasts_names, adjpval_thr,
+                                         log2fc_thr, _logger())
+        return {name: marker for name, marker in zip(contrasts_names, markers_list)}
     markers_list = [
         markers(subset_imputed_features_obj, barcode_groups[i], contrasts_names[i], adjpval_thr=adjpval_thr,
                 log2fc_thr=log2fc_thr, n_cpu=1, device=device)

@@ -8,6 +8,7 @@ import pandas as pd
 import pytest
 
 from oracle import diff_oracle as do
+from oracle import lda_oracle as lo
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -122,3 +123,93 @@ def test_find_diff_features_one_vs_rest():
     keep = np.flatnonzero((padj <= 0.05) & (l2 >= np.log2(1.5)))
     assert sorted(res["A"].index) == sorted(feats[i] for i in keep)
     np.testing.assert_allclose(res["A"].loc[[feats[i] for i in keep], "Adjusted_pval"].to_numpy(), padj[keep], rtol=1e-10)
+
+
+# ---- fused consumers of the imputed matrix (cgs_impute_normalized / cgs_impute_ranksum) --------------------------
+def _planted_factors(R=3000, K=12, C=700, seed=9):
+    rng = np.random.default_rng(seed)
+    a = rng.dirichlet(np.full(R, 0.1), size=K).T.astype(np.float32)          # regions x topics
+    groups = np.repeat(np.arange(3), [250, 250, 200])
+    conc = np.full((3, K), 0.3)
+    conc[0, :4] = 6.0
+    conc[1, 4:8] = 6.0
+    conc[2, 8:] = 6.0
+    b = np.stack([rng.dirichlet(conc[g]) for g in groups]).T.astype(np.float32)  # topics x cells
+    a[40:55] = 0  # all-zero regions: dropped by impute_accessibility
+    cells = [f"c{j}" for j in range(C)]
+    regions = [f"chr1:{j * 500}-{j * 500 + 500}" for j in range(R)]
+    return a, b, cells, regions, np.array(["A", "B", "C"])[groups]
+
+
+class _Model:
+    def __init__(self, a, b, cells, regions):
+        topics = [f"Topic{i + 1}" for i in range(a.shape[1])]
+        self.cell_topic = pd.DataFrame(b.astype(np.float64), index=topics, columns=cells)
+        self.topic_region = pd.DataFrame(a.astype(np.float64), index=regions, columns=topics)
+
+
+class _Obj:
+    def __init__(self, a, b, cells, regions, labels):
+        self.selected_model = _Model(a, b, cells, regions)
+        self.cell_names, self.region_names = cells, regions
+        self.cell_data = pd.DataFrame({"celltype": labels}, index=cells)
+
+
+def test_factored_normalize_matches_reference_golden():
+    """normalize_scores(impute_accessibility(..., materialize=False)) == the reference's two functions chained
+    (golden vectors of calculate_imputed_accessibility + calculate_normalized_scores, diff_features.py:398-548)."""
+    from pycistopic_b200 import diff_features as pdf
+    g = np.load(os.path.join(ROOT, "tests", "golden", "impute.npz"))
+    for i in (0, 5):
+        a, b = g[f"a{i}"], g[f"b{i}"]
+        scale = int(g[f"scale{i}"]) if bool(g[f"scale_is_int{i}"]) else float(g[f"scale{i}"])
+        names = [f"r{j}" for j in range(a.shape[0])]
+        f = pdf.FactoredImputedFeatures(a, b, names, [f"c{j}" for j in range(b.shape[1])], scale, int(g[f"chunk{i}"]), "t")
+        out = pdf.normalize_scores(f, 10 ** 4)
+        assert out.feature_names == [names[j] for j in g[f"kept{i}"]]
+        # the truncated imputed value may be off by ONE where the fp32 product (3xTF32 here, sgemm there; 1e-5
+        # relative, the north-star tolerance) straddles an integer -- the reference golden then differs in those
+        # elements by one count (a handful per 10 000); everything else agrees to fp64 round-off of the totals
+        # (with scale 10^4 the counts are small, so more elements sit on an integer boundary and one count is a
+        # larger step of log1p)
+        close = np.isclose(out.mtx, g[f"norm{i}"], rtol=1e-4, atol=1e-9)
+        assert close.mean() > 0.98, close.mean()
+        # ... and it is exactly normalize_scores of this package's own (dense) imputation
+        dense = f.to_dense()
+        np.testing.assert_allclose(out.mtx, lo.normalized_scores(dense.mtx.astype(np.float64), 10 ** 4), rtol=1e-13)
+
+
+def test_factored_consumers_match_dense_path():
+    """Every consumer gives the same answer from the factors (chunks recomputed on the device, nothing
+    materialised) as from the dense matrix the reference builds."""
+    from pycistopic_b200 import diff_features as pdf
+    a, b, cells, regions, labels = _planted_factors()
+    obj = _Obj(a, b, cells, regions, labels)
+    dense = pdf.impute_accessibility(obj, scale_factor=10 ** 6, chunk_size=1000)
+    fact = pdf.impute_accessibility(obj, scale_factor=10 ** 6, chunk_size=1000, materialize=False)
+    assert isinstance(fact, pdf.FactoredImputedFeatures) and fact.feature_names == dense.feature_names
+    assert len(dense.feature_names) == len(regions) - 15
+    np.testing.assert_array_equal(fact.to_dense().mtx, dense.mtx)
+    # normalize_scores
+    nd, nf = pdf.normalize_scores(dense, 10 ** 4), pdf.normalize_scores(fact, 10 ** 4)
+    assert nf.feature_names == nd.feature_names and nf.mtx.dtype == nd.mtx.dtype == np.float64
+    np.testing.assert_allclose(nf.mtx, nd.mtx, rtol=1e-13)
+    # find_diff_features, default one-vs-rest contrasts: identical tables
+    rd = pdf.find_diff_features(obj, dense, "celltype")
+    rf = pdf.find_diff_features(obj, fact, "celltype")
+    assert list(rd) == list(rf) == ["A", "B", "C"]
+    for name in rd:
+        assert len(rd[name]) > 20
+        assert rf[name].index.tolist() == rd[name].index.tolist()
+        np.testing.assert_array_equal(rf[name]["Log2FC"].to_numpy(), rd[name]["Log2FC"].to_numpy())
+        np.testing.assert_array_equal(rf[name]["Adjusted_pval"].to_numpy(), rd[name]["Adjusted_pval"].to_numpy())
+    # a feature subset and an explicit contrast
+    var = dense.feature_names[100:900]
+    c = [[["A"], ["C"]]]
+    rd = pdf.find_diff_features(obj, dense, "celltype", var_features=var, contrasts=c)
+    rf = pdf.find_diff_features(obj, fact, "celltype", var_features=var, contrasts=c)
+    assert list(rf) == ["A_VS_C"] and rf["A_VS_C"].index.tolist() == rd["A_VS_C"].index.tolist()
+    # markers() on one contrast
+    groups = [[x for x, l in zip(cells, labels) if l == "B"], [x for x, l in zip(cells, labels) if l != "B"]]
+    md, mf = pdf.markers(dense, groups, "B"), pdf.markers(fact, groups, "B")
+    assert mf.index.tolist() == md.index.tolist() and len(md) > 5
