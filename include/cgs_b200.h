@@ -271,6 +271,28 @@ int cgs_impute_ranksum(int device, const float *topic_region, const float *cell_
                        const int32_t *bg_cols, const int64_t *bg_offsets,
                        double *statistic, double *pvalue, double *log2fc, uint8_t *row_nonzero);
 
+/* ---- count matrix from fragments ------------------------------------------------
+ * create_cistopic_object_from_fragments counts fragments in regions with `regions.join(fragments)` (pyranges) and
+ * `counts_df.groupby(["Name", "regionID"]).size().unstack()` (cistopic_class.py:868-889).  Here every fragment finds
+ * the regions it overlaps on the device and the counts come back as a regions x cells CSR (int32), the layout of
+ * CistopicObject.fragment_matrix; binarising it (sklearn binarize, cistopic_class.py:592) gives the binary_matrix
+ * cgs_corpus_from_regions_by_cells takes.
+ * Regions: n_chrom chromosomes, region_chrom_ptr[n_chrom + 1] the region range of each, region_start / region_end
+ * int32[R] sorted by start inside a chromosome (half-open, as BED).  Fragments: int32[n_fragments] chromosome id
+ * (< 0 or >= n_chrom: no regions there), start, end, cell id (< 0 or >= n_cells: barcode not kept).  A fragment
+ * counts once for every region it overlaps (fragment.start < region.end and region.start < fragment.end). */
+typedef struct cgs_fragment_counts cgs_fragment_counts;
+int cgs_fragment_counts_create(cgs_fragment_counts **out, int device, int32_t n_chrom, const int32_t *region_chrom_ptr,
+                               const int32_t *region_start, const int32_t *region_end, int64_t n_fragments,
+                               const int32_t *frag_chrom, const int32_t *frag_start, const int32_t *frag_end,
+                               const int32_t *frag_cell, int32_t n_cells);
+int cgs_fragment_counts_destroy(cgs_fragment_counts *h);
+/* nnz = stored (region, cell) pairs; n_hits = fragment-region overlaps (the sum of the counts). */
+int cgs_fragment_counts_dims(const cgs_fragment_counts *h, int32_t *n_regions, int32_t *n_cells, int64_t *nnz,
+                             int64_t *n_hits);
+/* CSR to host: indptr int64[n_regions + 1], indices int32[nnz] (cells ascending inside a region), counts int32[nnz]. */
+int cgs_fragment_counts_export(const cgs_fragment_counts *h, int64_t *indptr, int32_t *indices, int32_t *counts);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,6 +12,7 @@
 
 #include "common.cuh"
 #include "corpus_kernels.cuh"
+#include "fragment_kernels.cuh"
 #include "impute_kernels.cuh"
 #include "metrics_kernels.cuh"
 #include "normalize_kernels.cuh"
@@ -1757,6 +1758,143 @@ int cgs_impute_ranksum(int device, const float *topic_region, const float *cell_
     dfree(d_fg, is.stream); dfree(d_bg, is.stream); dfree(d_res, is.stream);
     is.close();
     return rc;
+}
+
+}  // extern "C"
+
+// ---- count matrix from fragments (cistopic_class.py:868-889) ---------------------------------
+struct cgs_fragment_counts {
+    int device = 0;
+    int32_t n_regions = 0, n_cells = 0;
+    int64_t nnz = 0, n_hits = 0;
+    cudaStream_t stream = nullptr;
+    int64_t *d_indptr = nullptr;   // R + 1
+    int32_t *d_indices = nullptr;  // nnz, cells ascending inside a region
+    int32_t *d_counts = nullptr;   // nnz
+};
+
+extern "C" {
+
+int cgs_fragment_counts_destroy(cgs_fragment_counts *h) {
+    if (!h) return 0;
+    DeviceGuard g(h->device);
+    dfree(h->d_indptr, h->stream); dfree(h->d_indices, h->stream); dfree(h->d_counts, h->stream);
+    if (h->stream) { cudaStreamSynchronize(h->stream); cudaStreamDestroy(h->stream); }
+    delete h;
+    return 0;
+}
+
+int cgs_fragment_counts_create(cgs_fragment_counts **out, int device, int32_t n_chrom, const int32_t *region_chrom_ptr,
+                               const int32_t *region_start, const int32_t *region_end, int64_t n_fragments,
+                               const int32_t *frag_chrom, const int32_t *frag_start, const int32_t *frag_end,
+                               const int32_t *frag_cell, int32_t n_cells) {
+    if (!out || !region_chrom_ptr || !region_start || !region_end) CGS_FAIL("NULL argument");
+    if (n_fragments > 0 && (!frag_chrom || !frag_start || !frag_end || !frag_cell)) CGS_FAIL("NULL argument");
+    if (n_chrom < 1 || n_cells < 1 || n_fragments < 0) CGS_FAIL("empty input");
+    const int32_t R = region_chrom_ptr[n_chrom];
+    if (region_chrom_ptr[0] != 0 || R < 1) CGS_FAIL("region_chrom_ptr must start at 0 and cover at least one region");
+    std::vector<int32_t> maxlen((size_t)n_chrom, 0);
+    for (int32_t c = 0; c < n_chrom; ++c) {
+        if (region_chrom_ptr[c + 1] < region_chrom_ptr[c]) CGS_FAIL("region_chrom_ptr must be non-decreasing");
+        for (int32_t j = region_chrom_ptr[c]; j < region_chrom_ptr[c + 1]; ++j) {
+            if (j > region_chrom_ptr[c] && region_start[j] < region_start[j - 1])
+                CGS_FAIL("regions must be sorted by start inside every chromosome");
+            if (region_end[j] < region_start[j]) CGS_FAIL("region with end < start");
+            maxlen[c] = std::max(maxlen[c], region_end[j] - region_start[j]);
+        }
+    }
+    DeviceGuard g(device);
+    if (!g.ok) CGS_FAIL("cannot select CUDA device");
+    CGS_TRY(configure_pool(device));
+    int sms = kNumSMsFallback;
+    CGS_TRY(query_sms(device, &sms));
+    cgs_fragment_counts *h = new cgs_fragment_counts();
+    *out = nullptr;
+    h->device = device; h->n_regions = R; h->n_cells = n_cells;
+    int32_t *d_rs = nullptr, *d_re = nullptr, *d_cp = nullptr, *d_ml = nullptr, *d_f = nullptr, *d_raw = nullptr;
+    unsigned long long *d_fill = nullptr, *d_nnz = nullptr;
+    int64_t *d_raw_ptr = nullptr;
+    int rc = [&]() -> int {
+        CGS_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        cudaStream_t st = h->stream;
+        const size_t F = (size_t)n_fragments;
+        CGS_TRY(dmalloc(&d_rs, (size_t)R, st)); CGS_TRY(dmalloc(&d_re, (size_t)R, st));
+        CGS_TRY(dmalloc(&d_cp, (size_t)n_chrom + 1, st)); CGS_TRY(dmalloc(&d_ml, (size_t)n_chrom, st));
+        CGS_TRY(dmalloc(&d_f, 4 * F, st));
+        CGS_TRY(dmalloc(&d_fill, (size_t)R, st)); CGS_TRY(dmalloc(&d_nnz, (size_t)R, st));
+        CGS_TRY(dmalloc(&d_raw_ptr, (size_t)R + 1, st));
+        CGS_CUDA(cudaMemcpyAsync(d_rs, region_start, sizeof(int32_t) * (size_t)R, cudaMemcpyHostToDevice, st));
+        CGS_CUDA(cudaMemcpyAsync(d_re, region_end, sizeof(int32_t) * (size_t)R, cudaMemcpyHostToDevice, st));
+        CGS_CUDA(cudaMemcpyAsync(d_cp, region_chrom_ptr, sizeof(int32_t) * ((size_t)n_chrom + 1), cudaMemcpyHostToDevice, st));
+        CGS_CUDA(cudaMemcpyAsync(d_ml, maxlen.data(), sizeof(int32_t) * (size_t)n_chrom, cudaMemcpyHostToDevice, st));
+        const int32_t *src[4] = {frag_chrom, frag_start, frag_end, frag_cell};
+        for (int k = 0; k < 4 && F > 0; ++k)
+            CGS_CUDA(cudaMemcpyAsync(d_f + k * F, src[k], sizeof(int32_t) * F, cudaMemcpyHostToDevice, st));
+        CGS_CUDA(cudaMemsetAsync(d_fill, 0, sizeof(unsigned long long) * (size_t)R, st));
+        FragRegions rg{d_rs, d_re, d_cp, d_ml, n_chrom};
+        const int blocks = sms * 8;
+        fragment_hits_kernel<false><<<blocks, 256, 0, st>>>(d_f, d_f + F, d_f + 2 * F, d_f + 3 * F, n_fragments, n_cells, rg,
+                                                            d_fill, nullptr, nullptr);
+        CGS_CUDA(cudaGetLastError());
+        exclusive_scan_i64_kernel<<<1, 1024, 0, st>>>(d_fill, d_raw_ptr, R);
+        CGS_CUDA(cudaGetLastError());
+        CGS_CUDA(cgs_memcpy_sync(st, &h->n_hits, d_raw_ptr + R, sizeof(int64_t), cudaMemcpyDeviceToHost));
+        CGS_TRY(dmalloc(&d_raw, (size_t)h->n_hits, st));
+        CGS_CUDA(cudaMemsetAsync(d_fill, 0, sizeof(unsigned long long) * (size_t)R, st));
+        fragment_hits_kernel<true><<<blocks, 256, 0, st>>>(d_f, d_f + F, d_f + 2 * F, d_f + 3 * F, n_fragments, n_cells, rg,
+                                                           d_fill, d_raw_ptr, d_raw);
+        CGS_CUDA(cudaGetLastError());
+        // per-region histogram over a shared-memory window of the cell axis
+        int max_smem = 0;
+        CGS_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+        const int32_t window = (int32_t)std::max<int64_t>(1, std::min<int64_t>(n_cells, (max_smem - 1024) / 4));
+        const size_t smem = (size_t)window * 4;
+        CGS_CUDA(cudaFuncSetAttribute(region_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CGS_CUDA(cudaFuncSetAttribute(region_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int per_sm = smem > 100 * 1024 ? 1 : (smem > 48 * 1024 ? 2 : 4);
+        const int rblocks = std::max(1, std::min(R, sms * per_sm));
+        region_rows_kernel<false><<<rblocks, 512, smem, st>>>(d_raw, d_raw_ptr, R, n_cells, window, d_nnz, nullptr, nullptr, nullptr);
+        CGS_CUDA(cudaGetLastError());
+        CGS_TRY(dmalloc(&h->d_indptr, (size_t)R + 1, st));
+        exclusive_scan_i64_kernel<<<1, 1024, 0, st>>>(d_nnz, h->d_indptr, R);
+        CGS_CUDA(cudaGetLastError());
+        CGS_CUDA(cgs_memcpy_sync(st, &h->nnz, h->d_indptr + R, sizeof(int64_t), cudaMemcpyDeviceToHost));
+        CGS_TRY(dmalloc(&h->d_indices, (size_t)h->nnz, st));
+        CGS_TRY(dmalloc(&h->d_counts, (size_t)h->nnz, st));
+        region_rows_kernel<true><<<rblocks, 512, smem, st>>>(d_raw, d_raw_ptr, R, n_cells, window, nullptr, h->d_indptr,
+                                                            h->d_indices, h->d_counts);
+        CGS_CUDA(cudaGetLastError());
+        CGS_CUDA(cudaStreamSynchronize(st));
+        return 0;
+    }();
+    dfree(d_rs, h->stream); dfree(d_re, h->stream); dfree(d_cp, h->stream); dfree(d_ml, h->stream); dfree(d_f, h->stream);
+    dfree(d_raw, h->stream); dfree(d_fill, h->stream); dfree(d_nnz, h->stream); dfree(d_raw_ptr, h->stream);
+    if (rc != 0) { cgs_fragment_counts_destroy(h); return rc; }
+    *out = h;
+    return 0;
+}
+
+int cgs_fragment_counts_dims(const cgs_fragment_counts *h, int32_t *n_regions, int32_t *n_cells, int64_t *nnz,
+                             int64_t *n_hits) {
+    if (!h) CGS_FAIL("NULL handle");
+    if (n_regions) *n_regions = h->n_regions;
+    if (n_cells) *n_cells = h->n_cells;
+    if (nnz) *nnz = h->nnz;
+    if (n_hits) *n_hits = h->n_hits;
+    return 0;
+}
+
+int cgs_fragment_counts_export(const cgs_fragment_counts *h, int64_t *indptr, int32_t *indices, int32_t *counts) {
+    if (!h) CGS_FAIL("NULL handle");
+    DeviceGuard g(h->device);
+    if (indptr)
+        CGS_CUDA(cudaMemcpyAsync(indptr, h->d_indptr, sizeof(int64_t) * ((size_t)h->n_regions + 1), cudaMemcpyDeviceToHost, h->stream));
+    if (indices && h->nnz)
+        CGS_CUDA(cudaMemcpyAsync(indices, h->d_indices, sizeof(int32_t) * (size_t)h->nnz, cudaMemcpyDeviceToHost, h->stream));
+    if (counts && h->nnz)
+        CGS_CUDA(cudaMemcpyAsync(counts, h->d_counts, sizeof(int32_t) * (size_t)h->nnz, cudaMemcpyDeviceToHost, h->stream));
+    CGS_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
 }
 
 }  // extern "C"
