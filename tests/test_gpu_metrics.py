@@ -138,8 +138,13 @@ def test_run_cgs_model_device_metrics_match_host_path(c1):
     for col in ("Arun_2010", "Cao_Juan_2009", "loglikelihood"):
         assert dev.metrics.loc["Metric", col] == pytest.approx(host.metrics.loc["Metric", col], rel=1e-9)
     np.testing.assert_allclose(dev.marg_topic["Marg_Topic"].values, host.marg_topic["Marg_Topic"].values, rtol=1e-12)
+    # coherence: identical for the same top-region lists; the host path's default argsort may order tied counts
+    # differently (NumPy leaves that unspecified), so the reference formula is evaluated on the device's lists ...
+    np.testing.assert_allclose(dev.coherence["Mimno_2011"].values,
+                               pm.metric_coherence_mimno_2011(fitted.topic_word_, m, top=ing["top_regions"]), rtol=1e-10)
+    np.testing.assert_array_equal(ing["top_regions"], pm.top_regions_stable(fitted.topic_word_, 20))
+    # ... and wherever the default argsort happens to agree, the two packed models agree as they are
     same = np.all(np.argsort(fitted.topic_word_, axis=1)[:, :-21:-1] == ing["top_regions"], axis=1)
-    assert same.sum() >= K // 2
     np.testing.assert_allclose(dev.coherence["Mimno_2011"].values[same], host.coherence["Mimno_2011"].values[same],
                                rtol=1e-10)
     np.testing.assert_array_equal(dev.topic_region.values, host.topic_region.values)
