@@ -63,7 +63,7 @@ def c1():
     return make_binary_matrix("C1")
 
 
-@pytest.mark.parametrize("K", [1, 2, 10, 50, 130])
+@pytest.mark.parametrize("K", [1, 2, 10, 50, 130, 300, 512])
 def test_metric_ingredients_after_sweeps(c1, K):
     from pycistopic_b200 import Corpus, DeviceModel
     m, _, _ = c1
