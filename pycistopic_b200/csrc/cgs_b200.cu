@@ -1493,13 +1493,19 @@ static int ranksum_launch_t(const RankSide &fg, const RankSide &bg, int64_t n_ro
     const int32_t cap = (int32_t)(128 * 1024 / sizeof(K));  // values per shared-memory piece (plus 1/32 of padding)
     int32_t piece = 2;
     while (piece < sorted.n && piece < cap) piece <<= 1;
-    const size_t smem = ((size_t)piece + (size_t)piece / 32 + 1) * sizeof(K);
+    size_t smem = ((size_t)piece + (size_t)piece / 32 + 1) * sizeof(K);
+    // integer rows of modest range are counted instead of searched (worth its fixed cost from ~2000 values on)
+    int32_t hist_bins = 0;
+    if (std::is_same<T, int32_t>::value && (int64_t)fg.n + bg.n >= 2048 && !getenv("CGS_RANKSUM_NO_HIST")) {
+        hist_bins = kRankHistBins;
+        smem = std::max(smem, (size_t)2 * hist_bins * sizeof(uint32_t));
+    }
     auto kernel = ranksum_rows_kernel<T>;
     CGS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(136 * 1024)));
     int per_sm = 1;
     CGS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kRankThreads, smem));
     const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(n_rows, (int64_t)num_sms * std::max(1, per_sm)));
-    kernel<<<blocks, kRankThreads, smem, stream>>>(sorted, other, sort_fg ? 1 : 0, n_rows, piece, d_stat, d_pval, d_l2fc);
+    kernel<<<blocks, kRankThreads, smem, stream>>>(sorted, other, sort_fg ? 1 : 0, n_rows, piece, hist_bins, d_stat, d_pval, d_l2fc);
     CGS_CUDA(cudaGetLastError());
     return 0;
 }

@@ -83,6 +83,39 @@ def test_ranksum_one_matrix_two_index_lists(dtype, R, C, n_fg, n_bg):
     np.testing.assert_allclose(l2fc2, l2fc, rtol=1e-9, atol=1e-12, equal_nan=True)  # other summation order
 
 
+def test_ranksum_counting_path_and_its_fallback():
+    """int32 rows of at least 2048 values take the shared-memory counting path when max - min < 8192 and the sort +
+    search path otherwise; the decision is per row, so one launch mixes both.  Rows at the boundary (range 8191 /
+    8192), a constant row, and rows spanning INT32_MIN..INT32_MAX must all agree with scipy, and with the launch
+    that has the counting path switched off (same integer U, so bit for bit)."""
+    import os
+    from pycistopic_b200 import diff_features as pdf
+    rng = np.random.default_rng(77)
+    R, C, n_fg = 9, 6000, 2500
+    x = rng.integers(0, 50, (R, C)).astype(np.int32)
+    x[1] = rng.integers(-4000, 4192, C); x[1, 0], x[1, 1] = -4000, 4191       # range 8191: counted
+    x[2] = rng.integers(-4000, 4193, C); x[2, 0], x[2, 1] = -4000, 4192       # range 8192: searched
+    x[3] = 7                                                                  # constant row
+    x[4] = rng.integers(-2**31, 2**31 - 1, C); x[4, 0], x[4, 1] = -2**31, 2**31 - 1
+    x[5] = rng.integers(2**31 - 9000, 2**31 - 1, C, dtype=np.int64)            # near INT32_MAX, range > 8192
+    x[6] = rng.integers(2**31 - 8000, 2**31 - 1, C, dtype=np.int64); x[6, 5] = 2**31 - 1  # near INT32_MAX, counted
+    x[7] = (rng.random(C) < 0.01) * 1000000                                    # sparse, wide
+    perm = rng.permutation(C)
+    fg_cols, bg_cols = perm[:n_fg], perm[n_fg:]
+    stat, p, l2fc = pdf.ranksum_rows(x, None, fg_cols, bg_cols)
+    ostat, op = do.ranksums_rows(x[:, fg_cols].astype(np.float64), x[:, bg_cols].astype(np.float64))
+    np.testing.assert_allclose(stat, ostat, rtol=1e-12, atol=1e-13)
+    np.testing.assert_allclose(p, op, rtol=1e-10, atol=1e-300)
+    os.environ["CGS_RANKSUM_NO_HIST"] = "1"
+    try:
+        stat2, p2, l2fc2 = pdf.ranksum_rows(x, None, fg_cols, bg_cols)
+    finally:
+        del os.environ["CGS_RANKSUM_NO_HIST"]
+    np.testing.assert_array_equal(stat2, stat)
+    np.testing.assert_array_equal(p2, p)
+    np.testing.assert_allclose(l2fc2, l2fc, rtol=1e-9, atol=1e-12, equal_nan=True)
+
+
 def test_ranksum_errors_and_empty_groups():
     from pycistopic_b200 import diff_features as pdf
     x = np.arange(12, dtype=np.int32).reshape(3, 4)
