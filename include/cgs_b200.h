@@ -230,6 +230,21 @@ int cgs_normalize_scores(int device, const void *x, int dtype, int64_t n_rows, i
 int cgs_normalize_scores_device(int device, const void *d_x, int dtype, int64_t n_rows, int64_t n_cols,
                                 double scale_factor, void *d_out, void *d_colsum_scratch, void *stream);
 
+/* ---- make_rankings (diff_features.py:274-337; the per-column closure :294-306) ---------------------------- */
+/* out[r][c] = ranking of region r within cell (column) c by DESCENDING score, 0 = highest; int32, row-major with
+ * row stride ld_out.  x is n_rows (regions) x n_cols (cells) row-major with row stride ld (elements).
+ * Ties are broken at random, as the reference does (rng.permutation, then argsort): the column is read in the order
+ * of a keyed bijection pi of [0, n_rows) -- 4-round Feistel, cycle walking, keyed by (seed, first_col + c), see
+ * csrc/rankings_kernels.cuh and oracle/rankings_oracle.py -- and sorted stably, so a column without ties gets exactly
+ * the reference's ranking and tied scores get a pseudo-random order that depends only on (seed, cell index).
+ * NaN scores rank last.  dtype: 0 = int32, 1 = float32, 2 = float64.  Host pointers; columns are processed in
+ * device-sized rounds (first_col = cell index of column 0, so a caller may split the cells itself). */
+int cgs_rank_columns(int device, int dtype, const void *x, int64_t ld, int64_t n_rows, int64_t n_cols, uint64_t seed,
+                     int64_t first_col, int32_t *out, int64_t ld_out);
+/* Device-resident variant, asynchronous on `stream` (staging comes from the device's stream-ordered pool). */
+int cgs_rank_columns_device(int device, int dtype, const void *d_x, int64_t ld, int64_t n_rows, int64_t n_cols,
+                            uint64_t seed, int64_t first_col, int32_t *d_out, int64_t ld_out, void *stream);
+
 /* ---- differential features (diff_features.py:839-1120: markers -> get_wilcox_test_pvalues + get_log2_fc) ---- */
 /* For every row r < n_rows: scipy.stats.ranksums(fg[r], bg[r]) -- rank sum with average ranks for ties, normal
  * approximation without tie or continuity correction -- as statistic z and two-sided pvalue, and

@@ -8,6 +8,7 @@ imports fail), but the functions of interest are plain NumPy/``math`` code, so t
 * ``utils.subset_list`` / ``non_zero_rows``                          utils.py:113-126
 * ``calculate_imputed_accessibility`` (nested)   diff_features.py:398-492
 * ``calculate_normalized_scores`` (nested)       diff_features.py:540-548
+* ``CistopicImputedFeatures.make_rankings`` (method, run on a stand-in object)   diff_features.py:274-337
 * ``markers`` / ``get_wilcox_test_pvalues`` / ``p_adjust_bh`` / ``get_log2_fc`` / ``mean_axis1`` /
   ``subset_array_second_axis``                   diff_features.py:839-1120 (decorators dropped: numba.prange
   becomes ``range``; ``np.asfarray``, removed in NumPy 2, is supplied as ``np.asarray(..., float)``)
@@ -99,3 +100,23 @@ def reference_diff_feature_functions():
              "CistopicImputedFeatures": type("CistopicImputedFeatures", (), {})}
     return _load("diff_features.py", ["subset_array_second_axis", "mean_axis1", "get_log2_fc", "p_adjust_bh",
                                       "get_wilcox_test_pvalues", "markers"], extra=extra)
+
+
+class _ImputedStandIn:
+    """The four attributes ``make_rankings`` touches (diff_features.py:26-59)."""
+
+    def __init__(self, imputed_acc, feature_names, cell_names, project):
+        self.mtx, self.feature_names, self.cell_names, self.project = imputed_acc, feature_names, cell_names, project
+
+
+def reference_make_rankings():
+    """``make_rankings(obj, seed)`` -> ranking matrix: the reference's own method (diff_features.py:274-337)
+    executed on a stand-in for ``CistopicImputedFeatures``."""
+    ns = _load("diff_features.py", ["make_rankings"], extra={"CistopicImputedFeatures": _ImputedStandIn})
+    method = ns["make_rankings"]
+
+    def run(mtx, seed=123):
+        obj = _ImputedStandIn(mtx, [f"r{i}" for i in range(mtx.shape[0])], [f"c{i}" for i in range(mtx.shape[1])], "ref")
+        return method(obj, seed=seed).mtx
+
+    return run

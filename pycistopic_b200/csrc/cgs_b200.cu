@@ -17,6 +17,7 @@
 #include "metrics_kernels.cuh"
 #include "normalize_kernels.cuh"
 #include "ranksum_kernels.cuh"
+#include "rankings_kernels.cuh"
 #include "sampler_kernels.cuh"
 #include "stats_kernels.cuh"
 
@@ -1229,6 +1230,107 @@ int cgs_normalize_scores(int device, const void *x, int dtype, int64_t n_rows, i
         return 0;
     }();
     dfree(d_x, stream); dfree(d_o, stream); dfree(d_s, stream);
+    cudaStreamDestroy(stream);
+    return rc;
+}
+
+
+// ---- make_rankings (diff_features.py:274-337): per-cell rankings of the imputed matrix -----------------------
+}  // extern "C"
+
+template <typename T>
+static int rank_columns_launch(const T *d_x, int64_t ld, int64_t n_rows, int64_t n_cols, uint64_t seed, int64_t first_col,
+                               int32_t *d_out, int64_t ld_out, int num_sms, cudaStream_t stream) {
+    using K = typename RankKey<T>::type;
+    auto kernel = rank_columns_kernel<T>;
+    int per_sm = 1;
+    CGS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kRkThreads, 0));
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(n_cols, (int64_t)num_sms * std::max(1, per_sm)));
+    const size_t n = (size_t)n_rows * (size_t)n_cols, scratch = (size_t)blocks * (size_t)n_rows;
+    T *d_xT = nullptr;
+    int32_t *d_rT = nullptr;
+    K *d_k0 = nullptr, *d_k1 = nullptr;
+    uint32_t *d_p0 = nullptr, *d_p1 = nullptr;
+    int rc = [&]() -> int {
+        CGS_TRY(dmalloc(&d_xT, n, stream));
+        CGS_TRY(dmalloc(&d_rT, n, stream));
+        CGS_TRY(dmalloc(&d_k0, scratch, stream));
+        CGS_TRY(dmalloc(&d_k1, scratch, stream));
+        CGS_TRY(dmalloc(&d_p0, scratch, stream));
+        CGS_TRY(dmalloc(&d_p1, scratch, stream));
+        const int64_t tiles = ceil_div(n_rows, 32) * ceil_div(n_cols, 32);
+        if (tiles > 2147483647LL) CGS_FAIL("matrix chunk too large for one launch");
+        rk_transpose_kernel<T><<<(unsigned)tiles, dim3(32, 8), 0, stream>>>(d_x, ld, n_rows, n_cols, d_xT, n_rows);
+        CGS_CUDA(cudaGetLastError());
+        RankColsParams p;
+        p.xT = d_xT; p.rT = d_rT;
+        p.keys[0] = d_k0; p.keys[1] = d_k1; p.pay[0] = d_p0; p.pay[1] = d_p1;
+        p.n_rows = (uint32_t)n_rows; p.n_cols = n_cols; p.seed = seed; p.first_col = first_col;
+        p.half_bits = rk_half_bits((uint32_t)n_rows);
+        kernel<<<blocks, kRkThreads, 0, stream>>>(p);
+        CGS_CUDA(cudaGetLastError());
+        rk_transpose_kernel<int32_t><<<(unsigned)tiles, dim3(32, 8), 0, stream>>>(d_rT, n_rows, n_cols, n_rows, d_out, ld_out);
+        CGS_CUDA(cudaGetLastError());
+        return 0;
+    }();
+    dfree(d_xT, stream); dfree(d_rT, stream); dfree(d_k0, stream); dfree(d_k1, stream); dfree(d_p0, stream); dfree(d_p1, stream);
+    return rc;
+}
+
+extern "C" {
+
+int cgs_rank_columns_device(int device, int dtype, const void *d_x, int64_t ld, int64_t n_rows, int64_t n_cols,
+                            uint64_t seed, int64_t first_col, int32_t *d_out, int64_t ld_out, void *stream_) {
+    if (!d_x || !d_out) CGS_FAIL("NULL argument");
+    if (n_rows <= 0 || n_cols <= 0) CGS_FAIL("empty matrix");
+    if (n_rows > 2147483647LL) CGS_FAIL("more than 2^31 - 1 rows");
+    if (ld < n_cols || ld_out < n_cols) CGS_FAIL("row stride smaller than the number of columns");
+    DeviceGuard g(device);
+    if (!g.ok) CGS_FAIL("cannot select CUDA device");
+    int num_sms = kNumSMsFallback;
+    CGS_TRY(query_sms(device, &num_sms));
+    cudaStream_t stream = (cudaStream_t)stream_;
+    switch (dtype) {
+        case 0: return rank_columns_launch<int32_t>((const int32_t *)d_x, ld, n_rows, n_cols, seed, first_col, d_out, ld_out, num_sms, stream);
+        case 1: return rank_columns_launch<float>((const float *)d_x, ld, n_rows, n_cols, seed, first_col, d_out, ld_out, num_sms, stream);
+        case 2: return rank_columns_launch<double>((const double *)d_x, ld, n_rows, n_cols, seed, first_col, d_out, ld_out, num_sms, stream);
+    }
+    CGS_FAIL("dtype must be 0 (int32), 1 (float32) or 2 (float64)");
+}
+
+int cgs_rank_columns(int device, int dtype, const void *x, int64_t ld, int64_t n_rows, int64_t n_cols, uint64_t seed,
+                     int64_t first_col, int32_t *out, int64_t ld_out) {
+    if (!x || !out) CGS_FAIL("NULL argument");
+    if (n_rows <= 0 || n_cols <= 0) CGS_FAIL("empty matrix");
+    if (dtype < 0 || dtype > 2) CGS_FAIL("dtype must be 0 (int32), 1 (float32) or 2 (float64)");
+    if (n_rows > 2147483647LL) CGS_FAIL("more than 2^31 - 1 rows");
+    if (ld < n_cols || ld_out < n_cols) CGS_FAIL("row stride smaller than the number of columns");
+    DeviceGuard g(device);
+    if (!g.ok) CGS_FAIL("cannot select CUDA device");
+    CGS_TRY(configure_pool(device));
+    const size_t elem = dtype == 2 ? 8 : 4;
+    // columns per round: about 2^29 values on the device at a time (2-4 GB per staging buffer)
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(n_cols, std::max<int64_t>(32, (1LL << 29) / n_rows)));
+    uint8_t *d_x = nullptr;
+    int32_t *d_o = nullptr;
+    cudaStream_t stream = nullptr;
+    CGS_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    int rc = [&]() -> int {
+        CGS_TRY(dmalloc(&d_x, (size_t)n_rows * (size_t)chunk * elem, stream));
+        CGS_TRY(dmalloc(&d_o, (size_t)n_rows * (size_t)chunk, stream));
+        for (int64_t c0 = 0; c0 < n_cols; c0 += chunk) {
+            const int64_t nc = std::min(chunk, n_cols - c0);
+            CGS_CUDA(cudaMemcpy2DAsync(d_x, (size_t)nc * elem, (const uint8_t *)x + (size_t)c0 * elem, (size_t)ld * elem,
+                                       (size_t)nc * elem, (size_t)n_rows, cudaMemcpyHostToDevice, stream));
+            CGS_TRY(cgs_rank_columns_device(device, dtype, d_x, nc, n_rows, nc, seed, first_col + c0, d_o, nc, stream));
+            CGS_CUDA(cudaMemcpy2DAsync(out + c0, (size_t)ld_out * 4, d_o, (size_t)nc * 4, (size_t)nc * 4, (size_t)n_rows,
+                                       cudaMemcpyDeviceToHost, stream));
+            CGS_CUDA(cudaStreamSynchronize(stream));
+        }
+        return 0;
+    }();
+    dfree(d_x, stream); dfree(d_o, stream);
+    cudaStreamSynchronize(stream);
     cudaStreamDestroy(stream);
     return rc;
 }

@@ -54,6 +54,27 @@ class CistopicImputedFeatures:
         return (f"CistopicImputedFeatures from project {self.project} with nCells × nFeatures = "
                 f"{len(self.cell_names)} × {len(self.feature_names)}")
 
+    def make_rankings(self, seed=123, device=0):
+        """Per-cell rankings of the regions by descending score, 0 = best, ties broken at random
+        (diff_features.py:274-337) -- on the GPU (``cgs_rank_columns``).
+
+        Returns a :class:`CistopicImputedFeatures` holding the int32 ranking matrix, like the reference.  A column
+        without ties gets the reference's ranking bit for bit; tied scores get a pseudo-random order that is a
+        pure function of ``(seed, cell index)`` (the reference's comes from NumPy's PCG64 stream and its unstable
+        argsort, which nothing outside NumPy reproduces).  Unlike the reference, whose per-column ``.toarray()``
+        (:334) only works on a SciPy sparse ``mtx``, dense arrays are accepted as well."""
+        if scipy.sparse.issparse(self.mtx):
+            mtx = self.mtx.tocsc()
+            n_rows, n_cols = mtx.shape
+            out = np.empty((n_rows, n_cols), dtype=np.int32)
+            step = max(1, min(n_cols, (1 << 28) // max(1, n_rows)))  # dense column blocks of about 1 GB
+            for c0 in range(0, n_cols, step):
+                block = mtx[:, c0:c0 + step].toarray()
+                out[:, c0:c0 + step] = rank_columns(block, seed=seed, first_col=c0, device=device)
+        else:
+            out = rank_columns(self.mtx, seed=seed, device=device)
+        return CistopicImputedFeatures(out, self.feature_names, self.cell_names, self.project)
+
     def subset(self, cells=None, features=None, copy=False, split_pattern="___"):
         """Keep the given cells and/or features, then drop all-zero features (diff_features.py:61-129)."""
         mtx, cell_names, feature_names = self.mtx, self.cell_names, self.feature_names
@@ -343,6 +364,27 @@ def normalize_scores(imputed_acc, scale_factor=10 ** 4):
         raise TypeError("imputed_acc must be a CistopicImputedFeatures or a pandas DataFrame")
     log.info("Done!")
     return output
+
+
+def rank_columns(scores, seed=123, first_col=0, device=0):
+    """Ranking of every column of ``scores`` (regions x cells) by descending value, 0 = best, ties in the order of a
+    keyed pseudo-random bijection (``cgs_rank_columns``; the closure at diff_features.py:294-306).  ``first_col`` is
+    the cell index of column 0, so a matrix ranked in column blocks gives the same result as in one call."""
+    _lib.require_device()
+    x = np.asarray(scores)
+    if x.ndim != 2:
+        raise ValueError("scores must be a 2-D array (regions x cells)")
+    if x.dtype not in _RANK_DTYPES:
+        x = x.astype(np.float64)
+    if x.strides[1] != x.itemsize or x.strides[0] < x.shape[1] * x.itemsize or x.strides[0] % x.itemsize:
+        x = np.ascontiguousarray(x)
+    out = np.empty(x.shape, dtype=np.int32)
+    if x.size == 0:
+        return out
+    check(_lib.load().cgs_rank_columns(device, _RANK_DTYPES[x.dtype], x.ctypes.data_as(c_vp), x.strides[0] // x.itemsize,
+                                       x.shape[0], x.shape[1], int(seed) & (2 ** 64 - 1), int(first_col),
+                                       out.ctypes.data_as(_lib.c_i32p), out.shape[1]))
+    return out
 
 
 # ---- differential features (diff_features.py:716-1120; SURVEY.md section 8f, row N2) -----------------------------

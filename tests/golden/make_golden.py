@@ -148,6 +148,27 @@ def golden_oracle_kat():
     np.savez_compressed(os.path.join(HERE, "oracle_kat.npz"), **out)
 
 
+def golden_rankings():
+    """make_rankings of the reference (diff_features.py:274-337, executed from the tree) on small matrices: columns
+    without ties (unique ranking), columns with ties (any valid draw), float scores."""
+    run = rf.reference_make_rankings()
+    rng = np.random.default_rng(2024)
+    R, C = 700, 6
+    x = np.empty((R, C), np.int32)
+    x[:, 0] = rng.permutation(R)                       # no ties
+    x[:, 1] = rng.permutation(R) * 3 - 500             # no ties, negative values
+    x[:, 2] = rng.integers(0, 6, R)                    # heavy ties
+    x[:, 3] = 0                                        # constant
+    x[:, 4] = (rng.random(R) < 0.1) * rng.integers(1, 1000, R)   # mostly zero
+    x[:, 5] = rng.permutation(R) + 70000               # no ties, needs three digit passes
+    xf = rng.normal(0, 1, (R, 3)).astype(np.float32)   # no ties with probability 1
+    xf[:, 2] = np.round(xf[:, 2], 1)                   # ties
+    # the reference method only accepts a SciPy sparse mtx (it calls .toarray() on every column, :334)
+    out = {"x_int": x, "rank_int": run(sp.csr_matrix(x), seed=123), "x_float": xf,
+           "rank_float": run(sp.csr_matrix(xf), seed=7)}
+    np.savez_compressed(os.path.join(HERE, "rankings.npz"), **out)
+
+
 if __name__ == "__main__":
     if not rf.available():
         sys.exit("the reference tree is not available: cannot regenerate the golden fixtures")
@@ -155,4 +176,5 @@ if __name__ == "__main__":
     golden_impute()
     golden_oracle_kat()
     golden_diff_features()
+    golden_rankings()
     print("golden fixtures written to", HERE)

@@ -327,3 +327,25 @@ def test_diff_feature_oracle_matches_reference_golden():
         for r in range(0, fg.shape[0], 7):
             z, pr = do.ranksums_restated(fg[r], bg[r])
             assert z == pytest.approx(stat[r], rel=1e-12, abs=1e-15) and pr == pytest.approx(p[r], rel=1e-12)
+
+
+def test_rankings_oracle_matches_reference_golden():
+    """oracle/rankings_oracle.py against the reference's own make_rankings (diff_features.py:274-337, executed
+    from the tree into tests/golden/rankings.npz): the NumPy restatement of the reference closure reproduces it
+    entirely (same PCG64 stream, same argsort); the restatement of the DEVICE algorithm (keyed Feistel bijection +
+    stable sort) reproduces it on every column without ties and yields the same scores at every rank elsewhere."""
+    from oracle import rankings_oracle as ro
+    g = np.load(os.path.join(ROOT, "tests", "golden", "rankings.npz"))
+    for xk, rk, seed in (("x_int", "rank_int", 123), ("x_float", "rank_float", 7)):
+        x, ref = g[xk], g[rk]
+        np.testing.assert_array_equal(ro.reference_make_rankings(x, seed=seed), ref)
+        got = ro.rank_columns(x, seed=seed)
+        for c in range(x.shape[1]):
+            assert np.array_equal(np.sort(got[:, c]), np.arange(x.shape[0]))
+            if len(np.unique(x[:, c])) == x.shape[0]:
+                np.testing.assert_array_equal(got[:, c], ref[:, c])
+            else:
+                np.testing.assert_array_equal(x[np.argsort(got[:, c]), c], x[np.argsort(ref[:, c]), c])
+    for n in (1, 2, 3, 17, 256, 257, 65536, 65537, 100_003):
+        perm = ro.permutation(n, ro.column_key(123, n))
+        assert np.array_equal(np.sort(perm), np.arange(n))
