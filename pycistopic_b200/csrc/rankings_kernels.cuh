@@ -98,7 +98,7 @@ struct RankColsParams {
 };
 
 template <typename T>
-__global__ void __launch_bounds__(kRkThreads)
+__global__ void __launch_bounds__(kRkThreads, 2)
 rank_columns_kernel(RankColsParams p) {
     using K = typename RankKey<T>::type;
     constexpr int kDigits = (int)sizeof(K);
@@ -109,8 +109,8 @@ rank_columns_kernel(RankColsParams p) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t n = p.n_rows;
-    K *kb[2] = {static_cast<K *>(p.keys[0]) + (size_t)blockIdx.x * n, static_cast<K *>(p.keys[1]) + (size_t)blockIdx.x * n};
-    uint32_t *pb[2] = {p.pay[0] + (size_t)blockIdx.x * n, p.pay[1] + (size_t)blockIdx.x * n};
+    K *const kb0 = static_cast<K *>(p.keys[0]) + (size_t)blockIdx.x * n, *const kb1 = static_cast<K *>(p.keys[1]) + (size_t)blockIdx.x * n;
+    uint32_t *const pb0 = p.pay[0] + (size_t)blockIdx.x * n, *const pb1 = p.pay[1] + (size_t)blockIdx.x * n;
 
     for (int64_t col = blockIdx.x; col < p.n_cols; col += gridDim.x) {
         const T *x = static_cast<const T *>(p.xT) + (size_t)col * n;
@@ -140,7 +140,10 @@ rank_columns_kernel(RankColsParams p) {
             continue;
         }
 
-        int src = -1, dst = 0;  // src < 0: the column itself, read through pi
+        const K *ksrc = nullptr;  // NULL: the column itself, read through pi
+        const uint32_t *psrc = nullptr;
+        K *kdst = kb0;
+        uint32_t *pdst = pb0;
         for (int d = 0; d < kDigits; ++d) {
             if (!((varying >> (8 * d)) & 0xff)) continue;
             const bool last = --passes_left == 0;
@@ -189,12 +192,12 @@ rank_columns_kernel(RankColsParams p) {
                     ok[r] = idx < n;
                     key[r] = 0; pay[r] = 0;
                     if (ok[r]) {
-                        if (src < 0) {
+                        if (!ksrc) {
                             pay[r] = rk_permute(idx, n, p.half_bits, ckey);
                             key[r] = rk_desc_key(x[pay[r]]);
                         } else {
-                            key[r] = kb[src][idx];
-                            pay[r] = pb[src][idx];
+                            key[r] = ksrc[idx];
+                            pay[r] = psrc[idx];
                         }
                     }
                 }
@@ -237,16 +240,17 @@ rank_columns_kernel(RankColsParams p) {
                         if (last) {
                             out[pay[r]] = (int32_t)dest;
                         } else {
-                            kb[dst][dest] = key[r];
-                            pb[dst][dest] = pay[r];
+                            kdst[dest] = key[r];
+                            pdst[dest] = pay[r];
                         }
                     }
                 }
                 __syncwarp();
             }
             __syncthreads();  // the pass's global writes are visible to the whole CTA
-            src = dst;
-            dst ^= 1;
+            ksrc = kdst; psrc = pdst;
+            kdst = kdst == kb0 ? kb1 : kb0;
+            pdst = pdst == pb0 ? pb1 : pb0;
         }
     }
 }
