@@ -285,6 +285,14 @@ int cgs_impute_ranksum(int device, const float *topic_region, const float *cell_
                        int32_t n_contrasts, const int32_t *fg_cols, const int64_t *fg_offsets,
                        const int32_t *bg_cols, const int64_t *bg_offsets,
                        double *statistic, double *pvalue, double *log2fc, uint8_t *row_nonzero);
+/* make_rankings(impute_accessibility(...)) (diff_features.py:274-337 on the result of :340-508): per block of cells the
+ * whole regions x block product is imputed on the device and ranked there (cgs_rank_columns_device semantics, tie
+ * order keyed by (seed, cell index)); out = int32 rankings, n_regions x n_cells row-major host memory.  The
+ * reference ranks only the regions impute_accessibility kept: pass topic_region without its all-zero rows.
+ * cell_block <= 0 picks a block of about 2^29 values. */
+int cgs_impute_rankings(int device, const float *topic_region, const float *cell_topic, int32_t n_regions,
+                        int32_t n_topics, int32_t n_cells, float impute_scale, int as_int32, uint64_t seed,
+                        int32_t cell_block, int32_t *out);
 
 /* ---- count matrix from fragments ------------------------------------------------
  * create_cistopic_object_from_fragments counts fragments in regions with `regions.join(fragments)` (pyranges) and

@@ -1868,6 +1868,52 @@ int cgs_impute_ranksum(int device, const float *topic_region, const float *cell_
     return rc;
 }
 
+
+int cgs_impute_rankings(int device, const float *topic_region, const float *cell_topic, int32_t n_regions,
+                        int32_t n_topics, int32_t n_cells, float impute_scale, int as_int32, uint64_t seed,
+                        int32_t cell_block, int32_t *out) {
+    if (!topic_region || !cell_topic || !out) CGS_FAIL("NULL argument");
+    if (n_regions <= 0 || n_topics <= 0 || n_cells <= 0) CGS_FAIL("empty operand");
+    DeviceGuard g(device);
+    if (!g.ok) CGS_FAIL("cannot select CUDA device");
+    CGS_TRY(configure_pool(device));
+    const int64_t R = n_regions, K = n_topics, C = n_cells;
+    // cells per round: the whole regions x block product (4 B per value) and its rankings live on the device
+    const int32_t block = (int32_t)std::max<int64_t>(1, std::min<int64_t>(C, cell_block > 0 ? cell_block : std::max<int64_t>(32, (1LL << 29) / R)));
+    cudaStream_t stream = nullptr;
+    CGS_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    float *d_a = nullptr;
+    uint8_t *d_prod = nullptr, *d_flags = nullptr;
+    int32_t *d_rank = nullptr;
+    cgs_impute_plan *plan = nullptr;
+    std::vector<float> cells((size_t)K * block);
+    int rc = [&]() -> int {
+        CGS_TRY(dmalloc(&d_a, (size_t)R * K, stream));
+        CGS_TRY(dmalloc(&d_prod, (size_t)R * block * 4, stream));
+        CGS_TRY(dmalloc(&d_rank, (size_t)R * block, stream));
+        CGS_TRY(dmalloc(&d_flags, (size_t)R, stream));
+        CGS_CUDA(cudaMemcpyAsync(d_a, topic_region, sizeof(float) * (size_t)R * K, cudaMemcpyHostToDevice, stream));
+        for (int64_t c0 = 0; c0 < C; c0 += block) {
+            const int32_t nc = (int32_t)std::min<int64_t>(block, C - c0);
+            for (int64_t k = 0; k < K; ++k) memcpy(cells.data() + k * nc, cell_topic + k * C + c0, sizeof(float) * (size_t)nc);
+            CGS_TRY(cgs_impute_plan_create(&plan, device, cells.data(), 0, n_topics, nc, stream));
+            CGS_TRY(cgs_impute_plan_chunk_device(plan, d_a, n_regions, impute_scale, as_int32, d_prod, d_flags, stream));
+            CGS_TRY(cgs_rank_columns_device(device, as_int32 ? 0 : 1, d_prod, nc, R, nc, seed, c0, d_rank, nc, stream));
+            CGS_CUDA(cudaMemcpy2DAsync(out + c0, (size_t)C * 4, d_rank, (size_t)nc * 4, (size_t)nc * 4, (size_t)R,
+                                       cudaMemcpyDeviceToHost, stream));
+            CGS_CUDA(cudaStreamSynchronize(stream));
+            cgs_impute_plan_destroy(plan);
+            plan = nullptr;
+        }
+        return 0;
+    }();
+    if (plan) cgs_impute_plan_destroy(plan);
+    dfree(d_a, stream); dfree(d_prod, stream); dfree(d_rank, stream); dfree(d_flags, stream);
+    cudaStreamSynchronize(stream);
+    cudaStreamDestroy(stream);
+    return rc;
+}
+
 }  // extern "C"
 
 // ---- count matrix from fragments (cistopic_class.py:868-889) ---------------------------------

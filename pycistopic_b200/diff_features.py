@@ -189,6 +189,22 @@ class FactoredImputedFeatures:
         self._row_nonzero = flags.astype(bool)
         return CistopicImputedFeatures(out[: kept.value], self.feature_names, self.cell_names, self.project)
 
+    def make_rankings(self, seed=123, cell_block=0):
+        """``make_rankings`` of the imputed matrix without materialising it (``cgs_impute_rankings``): the regions
+        ``impute_accessibility`` would keep are ranked per cell, block of cells by block of cells, on the GPU; only
+        the int32 ranking matrix comes back.  Same result as ``self.to_dense().make_rankings(seed)``."""
+        _lib.require_device()
+        keep = self.row_nonzero
+        tr = np.ascontiguousarray(self.topic_region[keep])
+        R, K = tr.shape
+        C = self.cell_topic.shape[1]
+        out = np.empty((R, C), np.int32)
+        if R and C:
+            check(_lib.load().cgs_impute_rankings(self.device, ptr(tr, c_f32p), ptr(self.cell_topic, c_f32p), R, K, C,
+                                                  self.impute_scale, int(self.as_int32), int(seed) & (2 ** 64 - 1),
+                                                  int(cell_block), ptr(out, _lib.c_i32p)))
+        return CistopicImputedFeatures(out, self.feature_names, self.cell_names, self.project)
+
     @property
     def row_nonzero(self):
         if self._row_nonzero is None:  # one imputation pass with a one-cell contrast is the cheapest way to the flags

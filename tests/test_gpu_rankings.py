@@ -112,3 +112,27 @@ def test_rank_columns_imputed_shape_properties():
     got = pdf.rank_columns(x, seed=123)
     _check_valid(x, got)
     np.testing.assert_array_equal(got[:, :2], ro.rank_columns(x[:, :2], seed=123))
+
+
+@pytest.mark.parametrize("scale", [10 ** 6, 1.0])
+def test_factored_make_rankings_equals_dense_path(scale):
+    """impute_accessibility(..., materialize=False).make_rankings() == impute_accessibility(...).make_rankings():
+    the product is recomputed per block of cells on the device (cgs_impute_rankings), all-zero regions dropped first
+    as the reference does (diff_features.py:468-486), and the tie order depends on the cell index only -- so any
+    cell blocking gives the matrix of the dense path."""
+    from pycistopic_b200 import diff_features as pdf
+    rng = np.random.default_rng(3)
+    R, C, K = 5000, 333, 12
+    tr = rng.dirichlet(np.full(R, 0.05), K).T.astype(np.float32)
+    tr[rng.random(R) < 0.2] = 0                                       # regions the row filter drops
+    ct = rng.dirichlet(np.full(K, 0.3), C).T.astype(np.float32)
+    regions, cells = [f"r{i}" for i in range(R)], [f"c{i}" for i in range(C)]
+    f = pdf.FactoredImputedFeatures(tr, ct, regions, cells, scale, 1000, "t")
+    dense = f.to_dense()
+    assert 0 < len(dense.feature_names) < R
+    want = dense.make_rankings(seed=5)
+    for block in (0, 100, 32):
+        got = f.make_rankings(seed=5, cell_block=block)
+        assert got.feature_names == dense.feature_names and got.cell_names == cells
+        np.testing.assert_array_equal(got.mtx, want.mtx)
+    _check_valid(dense.mtx, want.mtx)
