@@ -1240,20 +1240,32 @@ int cgs_normalize_scores(int device, const void *x, int dtype, int64_t n_rows, i
 
 template <typename T>
 static int rank_columns_launch(const T *d_x, int64_t ld, int64_t n_rows, int64_t n_cols, uint64_t seed, int64_t first_col,
-                               int32_t *d_out, int64_t ld_out, int num_sms, cudaStream_t stream) {
+                               int32_t *d_out, int64_t ld_out, int device, cudaStream_t stream) {
     using K = typename RankKey<T>::type;
     auto kernel = rank_columns_kernel<T>;
-    int per_sm = 1;
-    CGS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kRkThreads, 0));
-    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(n_cols, (int64_t)num_sms * std::max(1, per_sm)));
-    const size_t n = (size_t)n_rows * (size_t)n_cols, scratch = (size_t)blocks * (size_t)n_rows;
+    // clusters in flight: what the SMs can hold, but no more columns than L2 keeps resident (scores [+ rankings
+    // for 8-byte scores] + the ping-pong pairs the passes touch: one for the two passes of small integers)
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = kRkCluster; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.gridDim = dim3(kRkCluster); cfg.blockDim = dim3(kRkThreads); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+    int max_clusters = 1, l2_bytes = 0;
+    CGS_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kernel, &cfg));
+    CGS_CUDA(cudaDeviceGetAttribute(&l2_bytes, cudaDevAttrL2CacheSize, device));
+    const int64_t per_value = std::is_same<T, int32_t>::value ? 12 : std::is_same<T, float>::value ? 20 : 36;
+    int64_t n_clusters = (int64_t)(0.7 * (double)l2_bytes) / (n_rows * per_value);
+    if (const char *e = getenv("CGS_RANK_CLUSTERS")) { if (atoll(e) > 0) n_clusters = atoll(e); }  // measurement knob
+    n_clusters = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(n_clusters, std::max(1, max_clusters)), n_cols));
+    const size_t n = (size_t)n_rows * (size_t)n_cols, scratch = (size_t)n_clusters * (size_t)n_rows;
     T *d_xT = nullptr;
     int32_t *d_rT = nullptr;
     K *d_k0 = nullptr, *d_k1 = nullptr;
     uint32_t *d_p0 = nullptr, *d_p1 = nullptr;
     int rc = [&]() -> int {
         CGS_TRY(dmalloc(&d_xT, n, stream));
-        CGS_TRY(dmalloc(&d_rT, n, stream));
+        if (sizeof(T) == 8) CGS_TRY(dmalloc(&d_rT, n, stream));
         CGS_TRY(dmalloc(&d_k0, scratch, stream));
         CGS_TRY(dmalloc(&d_k1, scratch, stream));
         CGS_TRY(dmalloc(&d_p0, scratch, stream));
@@ -1267,9 +1279,10 @@ static int rank_columns_launch(const T *d_x, int64_t ld, int64_t n_rows, int64_t
         p.keys[0] = d_k0; p.keys[1] = d_k1; p.pay[0] = d_p0; p.pay[1] = d_p1;
         p.n_rows = (uint32_t)n_rows; p.n_cols = n_cols; p.seed = seed; p.first_col = first_col;
         p.half_bits = rk_half_bits((uint32_t)n_rows);
-        kernel<<<blocks, kRkThreads, 0, stream>>>(p);
-        CGS_CUDA(cudaGetLastError());
-        rk_transpose_kernel<int32_t><<<(unsigned)tiles, dim3(32, 8), 0, stream>>>(d_rT, n_rows, n_cols, n_rows, d_out, ld_out);
+        cfg.gridDim = dim3((unsigned)(n_clusters * kRkCluster));
+        CGS_CUDA(cudaLaunchKernelEx(&cfg, kernel, p));
+        const int32_t *ranks = sizeof(T) == 8 ? d_rT : reinterpret_cast<const int32_t *>(d_xT);
+        rk_transpose_kernel<int32_t><<<(unsigned)tiles, dim3(32, 8), 0, stream>>>(ranks, n_rows, n_cols, n_rows, d_out, ld_out);
         CGS_CUDA(cudaGetLastError());
         return 0;
     }();
@@ -1287,13 +1300,11 @@ int cgs_rank_columns_device(int device, int dtype, const void *d_x, int64_t ld, 
     if (ld < n_cols || ld_out < n_cols) CGS_FAIL("row stride smaller than the number of columns");
     DeviceGuard g(device);
     if (!g.ok) CGS_FAIL("cannot select CUDA device");
-    int num_sms = kNumSMsFallback;
-    CGS_TRY(query_sms(device, &num_sms));
     cudaStream_t stream = (cudaStream_t)stream_;
     switch (dtype) {
-        case 0: return rank_columns_launch<int32_t>((const int32_t *)d_x, ld, n_rows, n_cols, seed, first_col, d_out, ld_out, num_sms, stream);
-        case 1: return rank_columns_launch<float>((const float *)d_x, ld, n_rows, n_cols, seed, first_col, d_out, ld_out, num_sms, stream);
-        case 2: return rank_columns_launch<double>((const double *)d_x, ld, n_rows, n_cols, seed, first_col, d_out, ld_out, num_sms, stream);
+        case 0: return rank_columns_launch<int32_t>((const int32_t *)d_x, ld, n_rows, n_cols, seed, first_col, d_out, ld_out, device, stream);
+        case 1: return rank_columns_launch<float>((const float *)d_x, ld, n_rows, n_cols, seed, first_col, d_out, ld_out, device, stream);
+        case 2: return rank_columns_launch<double>((const double *)d_x, ld, n_rows, n_cols, seed, first_col, d_out, ld_out, device, stream);
     }
     CGS_FAIL("dtype must be 0 (int32), 1 (float32) or 2 (float64)");
 }
