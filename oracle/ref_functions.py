@@ -9,6 +9,7 @@ imports fail), but the functions of interest are plain NumPy/``math`` code, so t
 * ``calculate_imputed_accessibility`` (nested)   diff_features.py:398-492
 * ``calculate_normalized_scores`` (nested)       diff_features.py:540-548
 * ``CistopicImputedFeatures.make_rankings`` (method, run on a stand-in object)   diff_features.py:274-337
+* ``LDAMallet.corpus_to_mallet`` (method)                                          lda_models.py:472-494
 * ``markers`` / ``get_wilcox_test_pvalues`` / ``p_adjust_bh`` / ``get_log2_fc`` / ``mean_axis1`` /
   ``subset_array_second_axis``                   diff_features.py:839-1120 (decorators dropped: numba.prange
   becomes ``range``; ``np.asfarray``, removed in NumPy 2, is supplied as ``np.asarray(..., float)``)
@@ -120,3 +121,10 @@ def reference_make_rankings():
         return method(obj, seed=seed).mtx
 
     return run
+
+
+def reference_corpus_to_mallet():
+    """``corpus_to_mallet(corpus, file_like)``: the reference's own method (lda_models.py:472-494), self unused."""
+    from itertools import chain
+    method = _load("lda_models.py", ["corpus_to_mallet"], extra={"chain": chain})["corpus_to_mallet"]
+    return lambda corpus, file_like: method(None, corpus, file_like)

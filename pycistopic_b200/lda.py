@@ -348,7 +348,8 @@ class LDA:
     """
 
     def __init__(self, n_topics, n_iter=2000, alpha=0.1, eta=0.01, random_state=None, refresh=10,
-                 device=0, corpus: Corpus | None = None, exports="all", device_metrics=None):
+                 device=0, corpus: Corpus | None = None, exports="all", device_metrics=None, z_init=None,
+                 keep_assignments=False):
         self.n_topics = n_topics
         self.n_iter = n_iter
         self.alpha = alpha
@@ -365,6 +366,11 @@ class LDA:
             raise ValueError("exports must be 'all' or 'frames'")
         self._exports = exports
         self._device_metrics = device_metrics
+        # z_init: topic of every token in (cell, region) order instead of the package's ``i mod K`` start -- how a
+        # state trained elsewhere (a Mallet --output-state file, mallet_formats.py) is evaluated (n_iter = 0) or
+        # continued on the device; keep_assignments leaves the final assignments in ``z_`` (with ``WS_`` / ``DS_``)
+        self._z_init = z_init
+        self._keep_assignments = bool(keep_assignments)
         if alpha <= 0 or eta <= 0:
             raise ValueError("alpha and eta must be greater than zero")
         if random_state is None:
@@ -390,7 +396,10 @@ class LDA:
             own_corpus = True
         model = DeviceModel(corpus, self.n_topics, self.alpha, self.eta, seed=self._seed)
         try:
-            model.init()
+            if self._z_init is None:
+                model.init()
+            else:
+                model.set_z(self._z_init)
             self.loglikelihoods_ = []
             done = 0
             refresh = max(1, int(self.refresh))
@@ -419,6 +428,9 @@ class LDA:
                 ing["loglikelihood_compat"] = model.loglikelihood_compat(dm["alpha"], dm["eta"])
                 ing["doc_lengths"] = corpus.cell_sizes().astype(np.float64)
                 self.metric_ingredients_ = ing
+            if self._keep_assignments:
+                self.z_ = model.get_z()
+                self.WS_, self.DS_ = corpus.token_lists()
             self.launch_count_ = model.launch_count
         finally:
             model.close()

@@ -349,3 +349,59 @@ def test_rankings_oracle_matches_reference_golden():
     for n in (1, 2, 3, 17, 256, 257, 65536, 65537, 100_003):
         perm = ro.permutation(n, ro.column_key(123, n))
         assert np.array_equal(np.sort(perm), np.arange(n))
+
+
+def test_mallet_formats_roundtrip_and_reference_text(tmp_path):
+    """mallet_formats: corpus text identical to the reference's corpus_to_mallet
+    (lda_models.py:472-494; executed from the tree when it is there, else the documented line format), state files
+    round-trip, load_word_topics counts columns 4 / 5 as the reference does (:620-646)."""
+    import gzip
+    import io
+    import scipy.sparse as sp
+    from pycistopic_b200 import mallet_formats as mf
+    rng = np.random.default_rng(4)
+    X = (rng.random((40, 9)) < 0.25).astype(np.int32)          # regions x cells
+    X[:, 3] = 0                                                # an empty cell
+    buf = io.StringIO()
+    mf.corpus_to_mallet(sp.csr_matrix(X), buf)
+    lines = buf.getvalue().splitlines()
+    assert len(lines) == 9 and lines[3] == "3\t0\t"
+    for c, line in enumerate(lines):
+        assert line == f"{c}\t0\t" + " ".join(str(r) for r in np.flatnonzero(X[:, c]))
+    bow = [[(int(r), 1) for r in np.flatnonzero(X[:, c])] for c in range(9)]   # gensim Sparse2Corpus view (:797-803)
+    buf2 = io.StringIO()
+    mf.corpus_to_mallet(bow, buf2)
+    assert buf2.getvalue() == buf.getvalue()
+    if rf.available():
+        buf3 = io.StringIO()
+        rf.reference_corpus_to_mallet()(bow, buf3)
+        assert buf3.getvalue() == buf.getvalue()
+    # state file: write -> read -> counts
+    Xc = sp.csc_matrix(X)
+    doc = np.repeat(np.arange(9), np.diff(Xc.indptr))
+    region, K = Xc.indices, 5
+    z = rng.integers(0, K, len(region))
+    for name in ("state.gz", "state.txt"):
+        path = str(tmp_path / name)
+        mf.write_state(path, doc, region, z, np.full(K, 2.5), 0.1)
+        opener = gzip.open if name.endswith(".gz") else open
+        with opener(path, "rt") as f:
+            head = [f.readline() for _ in range(4)]
+        assert head[0] == "#doc source pos typeindex type topic\n" and head[1].startswith("#alpha : 2.5 2.5")
+        assert head[2] == "#beta : 0.1\n" and head[3] == f"{doc[0]} NA 0 0 {region[0]} {z[0]}\n"
+        st = mf.read_state(path)
+        np.testing.assert_array_equal(st["alpha"], np.full(K, 2.5))
+        assert st["beta"] == 0.1
+        np.testing.assert_array_equal(st["doc"], doc)
+        np.testing.assert_array_equal(st["region"], region)
+        np.testing.assert_array_equal(st["topic"], z)
+        wt = mf.load_word_topics(path, K, 40)
+        want = np.zeros((K, 40))
+        np.add.at(want, (z, region), 1)
+        np.testing.assert_array_equal(wt, want)
+        with pytest.raises(AssertionError, match="Mismatch between MALLET"):
+            mf.load_word_topics(path, K + 1, 40)
+    bad = tmp_path / "bad.txt"
+    bad.write_text("not a state\n")
+    with pytest.raises(ValueError, match="not a Mallet state file"):
+        mf.read_state(str(bad))
