@@ -56,7 +56,11 @@ def test_state_roundtrip_through_the_device(tmp_path):
                            device_metrics={"alpha": 50.0, "eta": eta, "top_n": 20})
     model = plm.build_cistopic_model(ev, m, K, cells, regions, 0, 555, 50.0, True, eta, False, 5, 0.0)
     host = plm.build_cistopic_model(back, m, K, cells, regions, 0, 555, 50.0, True, eta, False, 5, 0.0)
-    np.testing.assert_allclose(model.metrics.to_numpy().astype(float), host.metrics.to_numpy().astype(float), rtol=1e-9)
+    got, want = model.metrics.to_numpy().astype(float)[0], host.metrics.to_numpy().astype(float)[0]
+    np.testing.assert_allclose(got[[0, 1, 3]], want[[0, 1, 3]], rtol=1e-9)     # Arun, Cao-Juan, loglikelihood
+    # Mimno takes the top 20 regions per topic: with counts this small most of them tie, and the device and
+    # NumPy's argsort pick different members of the tie (tests/test_gpu_metrics.py covers the tie-free case exactly)
+    np.testing.assert_allclose(got[2], want[2], rtol=0.05)
     assert model.topic_ass["Assignments"].sum() == m.nnz
     # sampled further from the imported state: the chain moves on and the likelihood does not collapse
     more = mf.lda_from_state(m, path, K, alpha, eta, n_iter=20, random_state=1)
