@@ -230,6 +230,16 @@ int cgs_normalize_scores(int device, const void *x, int dtype, int64_t n_rows, i
 int cgs_normalize_scores_device(int device, const void *d_x, int dtype, int64_t n_rows, int64_t n_cols,
                                 double scale_factor, void *d_out, void *d_colsum_scratch, void *stream);
 
+/* ---- find_highly_variable_features (diff_features.py:577-714): the reduction over the matrix (:636-639) -------- */
+/* mean[r] = np.mean(x[r], dtype=float32), var[r] = np.var(x[r], dtype=float32) (population variance, two-pass, with
+ * NumPy's casts; sums accumulated in fp64, so the float32 results are correctly rounded where NumPy's pairwise
+ * float32 sums are a few ulps off).  x is n_rows (regions) x n_cols (cells) row-major with row stride ld; float32
+ * [n_rows] outputs.  dtype: 0 = int32, 1 = float32, 2 = float64.  Host pointers; rows are processed in rounds. */
+int cgs_row_mean_var(int device, int dtype, const void *x, int64_t ld, int64_t n_rows, int64_t n_cols, float *mean,
+                     float *var);
+int cgs_row_mean_var_device(int device, int dtype, const void *d_x, int64_t ld, int64_t n_rows, int64_t n_cols,
+                            float *d_mean, float *d_var, void *stream);
+
 /* ---- make_rankings (diff_features.py:274-337; the per-column closure :294-306) ---------------------------- */
 /* out[r][c] = ranking of region r within cell (column) c by DESCENDING score, 0 = highest; int32, row-major with
  * row stride ld_out.  x is n_rows (regions) x n_cols (cells) row-major with row stride ld (elements).
@@ -293,6 +303,13 @@ int cgs_impute_ranksum(int device, const float *topic_region, const float *cell_
 int cgs_impute_rankings(int device, const float *topic_region, const float *cell_topic, int32_t n_regions,
                         int32_t n_topics, int32_t n_cells, float impute_scale, int as_int32, uint64_t seed,
                         int32_t cell_block, int32_t *out);
+/* The same reduction on normalize_scores(impute_accessibility(...)) (norm_scale > 0: statistics of
+ * log1p(x / (colsum(x) / norm_scale)), float64 values for the int32 imputation, float32 otherwise) or on the imputed
+ * values themselves (norm_scale == 0), from the two factors: mean / var are float32[n_regions] over ALL regions,
+ * row_nonzero (may be NULL) tells which of them impute_accessibility keeps. */
+int cgs_impute_row_stats(int device, const float *topic_region, const float *cell_topic, int32_t n_regions,
+                         int32_t n_topics, int32_t n_cells, float impute_scale, int as_int32, double norm_scale,
+                         int32_t chunk_rows, float *mean, float *var, uint8_t *row_nonzero);
 
 /* ---- count matrix from fragments ------------------------------------------------
  * create_cistopic_object_from_fragments counts fragments in regions with `regions.join(fragments)` (pyranges) and

@@ -9,6 +9,8 @@ imports fail), but the functions of interest are plain NumPy/``math`` code, so t
 * ``calculate_imputed_accessibility`` (nested)   diff_features.py:398-492
 * ``calculate_normalized_scores`` (nested)       diff_features.py:540-548
 * ``CistopicImputedFeatures.make_rankings`` (method, run on a stand-in object)   diff_features.py:274-337
+* ``find_highly_variable_features`` (matplotlib, absent here, replaced by a no-op stand-in; plot=False)
+                                                 diff_features.py:577-714
 * ``LDAMallet.corpus_to_mallet`` (method)                                          lda_models.py:472-494
 * ``markers`` / ``get_wilcox_test_pvalues`` / ``p_adjust_bh`` / ``get_log2_fc`` / ``mean_axis1`` /
   ``subset_array_second_axis``                   diff_features.py:839-1120 (decorators dropped: numba.prange
@@ -128,3 +130,20 @@ def reference_corpus_to_mallet():
     from itertools import chain
     method = _load("lda_models.py", ["corpus_to_mallet"], extra={"chain": chain})["corpus_to_mallet"]
     return lambda corpus, file_like: method(None, corpus, file_like)
+
+
+def reference_find_highly_variable_features():
+    """The reference's own function (diff_features.py:577-714); ``plt`` / ``matplotlib`` are inert stand-ins (the
+    function calls ``plt.figure()`` even with ``plot=False``)."""
+    import sys
+    import types
+
+    import pandas as pd
+    import sklearn.utils.sparsefuncs  # noqa: F401  (the sparse branch, :633)
+    import sklearn
+
+    inert = types.SimpleNamespace(figure=lambda *a, **k: None, scatter=lambda *a, **k: None,
+                                  xlabel=lambda *a, **k: None, ylabel=lambda *a, **k: None, show=lambda *a, **k: None)
+    extra = {"pd": pd, "sys": sys, "logging": logging, "sklearn": sklearn, "plt": inert,
+             "matplotlib": types.SimpleNamespace(rcParams={}), "CistopicImputedFeatures": _ImputedStandIn}
+    return _load("diff_features.py", ["find_highly_variable_features"], extra=extra)["find_highly_variable_features"]

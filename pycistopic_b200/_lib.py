@@ -107,6 +107,13 @@ SIGNATURES = {
     "cgs_fragment_counts_destroy": (ctypes.c_int, [c_vp]),
     "cgs_fragment_counts_dims": (ctypes.c_int, [c_vp, c_i32p, c_i32p, c_i64p, c_i64p]),
     "cgs_fragment_counts_export": (ctypes.c_int, [c_vp, c_i64p, c_i32p, c_i32p]),
+    "cgs_row_mean_var": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                        c_f32p, c_f32p]),
+    "cgs_row_mean_var_device": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_vp, ctypes.c_int64, ctypes.c_int64,
+                                               ctypes.c_int64, c_vp, c_vp, c_vp]),
+    "cgs_impute_row_stats": (ctypes.c_int, [ctypes.c_int, c_f32p, c_f32p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                            ctypes.c_float, ctypes.c_int, ctypes.c_double, ctypes.c_int32, c_f32p, c_f32p,
+                                            c_u8p]),
     "cgs_impute_rankings": (ctypes.c_int, [ctypes.c_int, c_f32p, c_f32p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                            ctypes.c_float, ctypes.c_int, ctypes.c_uint64, ctypes.c_int32, c_i32p]),
     "cgs_rank_columns": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,

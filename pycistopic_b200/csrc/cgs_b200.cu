@@ -1235,6 +1235,64 @@ int cgs_normalize_scores(int device, const void *x, int dtype, int64_t n_rows, i
 }
 
 
+// ---- per-region mean / variance in front of find_highly_variable_features (diff_features.py:636-639) ----------
+int cgs_row_mean_var_device(int device, int dtype, const void *d_x, int64_t ld, int64_t n_rows, int64_t n_cols,
+                            float *d_mean, float *d_var, void *stream_) {
+    if (!d_x || !d_mean || !d_var) CGS_FAIL("NULL argument");
+    if (n_rows <= 0 || n_cols <= 0) CGS_FAIL("empty matrix");
+    if (ld < n_cols) CGS_FAIL("row stride smaller than the number of columns");
+    DeviceGuard g(device);
+    if (!g.ok) CGS_FAIL("cannot select CUDA device");
+    int sms = kNumSMsFallback;
+    CGS_TRY(query_sms(device, &sms));
+    cudaStream_t stream = (cudaStream_t)stream_;
+    switch (dtype) {
+        case 0: return row_mean_var_launch<int32_t>((const int32_t *)d_x, ld, n_rows, n_cols, d_mean, d_var, sms, stream);
+        case 1: return row_mean_var_launch<float>((const float *)d_x, ld, n_rows, n_cols, d_mean, d_var, sms, stream);
+        case 2: return row_mean_var_launch<double>((const double *)d_x, ld, n_rows, n_cols, d_mean, d_var, sms, stream);
+    }
+    CGS_FAIL("dtype must be 0 (int32), 1 (float32) or 2 (float64)");
+}
+
+int cgs_row_mean_var(int device, int dtype, const void *x, int64_t ld, int64_t n_rows, int64_t n_cols, float *mean,
+                     float *var) {
+    if (!x || !mean || !var) CGS_FAIL("NULL argument");
+    if (n_rows <= 0 || n_cols <= 0) CGS_FAIL("empty matrix");
+    if (dtype < 0 || dtype > 2) CGS_FAIL("dtype must be 0 (int32), 1 (float32) or 2 (float64)");
+    if (ld < n_cols) CGS_FAIL("row stride smaller than the number of columns");
+    DeviceGuard g(device);
+    if (!g.ok) CGS_FAIL("cannot select CUDA device");
+    CGS_TRY(configure_pool(device));
+    const size_t elem = dtype == 2 ? 8 : 4;
+    // rows per round: about 1 GB on the device, two buffers so the next upload overlaps the reduction
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(n_rows, (int64_t)((1LL << 30) / ((size_t)n_cols * elem))));
+    uint8_t *d_x[2] = {nullptr, nullptr};
+    float *d_m = nullptr, *d_v = nullptr;
+    cudaStream_t stream = nullptr;
+    CGS_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    int rc = [&]() -> int {
+        CGS_TRY(dmalloc(&d_x[0], (size_t)chunk * n_cols * elem, stream));
+        CGS_TRY(dmalloc(&d_x[1], (size_t)chunk * n_cols * elem, stream));
+        CGS_TRY(dmalloc(&d_m, (size_t)n_rows, stream));
+        CGS_TRY(dmalloc(&d_v, (size_t)n_rows, stream));
+        int which = 0;
+        for (int64_t r0 = 0; r0 < n_rows; r0 += chunk, which ^= 1) {
+            const int64_t n = std::min(chunk, n_rows - r0);
+            CGS_CUDA(cudaMemcpy2DAsync(d_x[which], (size_t)n_cols * elem, (const uint8_t *)x + (size_t)r0 * ld * elem,
+                                       (size_t)ld * elem, (size_t)n_cols * elem, (size_t)n, cudaMemcpyHostToDevice, stream));
+            CGS_TRY(cgs_row_mean_var_device(device, dtype, d_x[which], n_cols, n, n_cols, d_m + r0, d_v + r0, stream));
+        }
+        CGS_CUDA(cudaMemcpyAsync(mean, d_m, sizeof(float) * (size_t)n_rows, cudaMemcpyDeviceToHost, stream));
+        CGS_CUDA(cudaMemcpyAsync(var, d_v, sizeof(float) * (size_t)n_rows, cudaMemcpyDeviceToHost, stream));
+        CGS_CUDA(cudaStreamSynchronize(stream));
+        return 0;
+    }();
+    dfree(d_x[0], stream); dfree(d_x[1], stream); dfree(d_m, stream); dfree(d_v, stream);
+    cudaStreamSynchronize(stream);
+    cudaStreamDestroy(stream);
+    return rc;
+}
+
 // ---- make_rankings (diff_features.py:274-337): per-cell rankings of the imputed matrix -----------------------
 }  // extern "C"
 
@@ -1879,6 +1937,73 @@ int cgs_impute_ranksum(int device, const float *topic_region, const float *cell_
     return rc;
 }
 
+
+int cgs_impute_row_stats(int device, const float *topic_region, const float *cell_topic, int32_t n_regions,
+                         int32_t n_topics, int32_t n_cells, float impute_scale, int as_int32, double norm_scale,
+                         int32_t chunk_rows, float *mean, float *var, uint8_t *row_nonzero) {
+    if (!topic_region || !cell_topic || !mean || !var) CGS_FAIL("NULL argument");
+    if (n_regions <= 0 || n_topics <= 0 || n_cells <= 0) CGS_FAIL("empty operand");
+    if (norm_scale < 0.0) CGS_FAIL("scale_factor must not be negative (0 = statistics of the imputed values themselves)");
+    DeviceGuard g(device);
+    if (!g.ok) CGS_FAIL("cannot select CUDA device");
+    CGS_TRY(configure_pool(device));
+    int sms = kNumSMsFallback;
+    CGS_TRY(query_sms(device, &sms));
+    const bool normalise = norm_scale > 0.0;
+    ImputeStream is;
+    uint8_t *d_norm = nullptr, *d_tot = nullptr;
+    float *d_m = nullptr, *d_v = nullptr;
+    const size_t out_elem = as_int32 ? 8 : 4;
+    const int64_t C = n_cells;
+    int rc = [&]() -> int {
+        CGS_TRY(is.open(device, topic_region, cell_topic, n_regions, n_topics, n_cells, impute_scale, as_int32, chunk_rows));
+        CGS_TRY(dmalloc(&d_m, (size_t)n_regions, is.stream));
+        CGS_TRY(dmalloc(&d_v, (size_t)n_regions, is.stream));
+        if (normalise) {
+            CGS_TRY(dmalloc(&d_norm, (size_t)is.chunk * C * out_elem, is.stream));
+            CGS_TRY(dmalloc(&d_tot, (size_t)C * 8, is.stream));
+            CGS_CUDA(cudaMemsetAsync(d_tot, 0, (size_t)C * 8, is.stream));
+            for (int32_t r0 = 0; r0 < n_regions; r0 += is.chunk) {  // pass 1: per-cell totals
+                const int32_t n = std::min(is.chunk, n_regions - r0);
+                CGS_TRY(is.run(r0, n));
+                dim3 grid((unsigned)ceil_div(C, kNormCols), (unsigned)ceil_div(n, kNormSlab));
+                if (as_int32) colsum_kernel<int32_t><<<grid, kNormCols, 0, is.stream>>>((const int32_t *)is.d_chunk, n, C, (long long *)d_tot);
+                else colsum_kernel<float><<<grid, kNormCols, 0, is.stream>>>((const float *)is.d_chunk, n, C, (double *)d_tot);
+                CGS_CUDA(cudaGetLastError());
+            }
+        }
+        for (int32_t r0 = 0; r0 < n_regions; r0 += is.chunk) {  // (re)compute, normalise, reduce every region
+            const int32_t n = std::min(is.chunk, n_regions - r0);
+            CGS_TRY(is.run(r0, n));
+            if (normalise) {
+                dim3 grid((unsigned)ceil_div(C, kNormCols), (unsigned)ceil_div(n, kNormSlab));
+                if (as_int32) {
+                    normalize_log1p_kernel<int32_t, double><<<grid, kNormCols, 0, is.stream>>>(
+                        (const int32_t *)is.d_chunk, n, C, (const long long *)d_tot, norm_scale, (double *)d_norm);
+                    CGS_CUDA(cudaGetLastError());
+                    CGS_TRY(row_mean_var_launch<double>((const double *)d_norm, C, n, C, d_m + r0, d_v + r0, sms, is.stream));
+                } else {
+                    normalize_log1p_kernel<float, float><<<grid, kNormCols, 0, is.stream>>>(
+                        (const float *)is.d_chunk, n, C, (const double *)d_tot, norm_scale, (float *)d_norm);
+                    CGS_CUDA(cudaGetLastError());
+                    CGS_TRY(row_mean_var_launch<float>((const float *)d_norm, C, n, C, d_m + r0, d_v + r0, sms, is.stream));
+                }
+            } else if (as_int32) {
+                CGS_TRY(row_mean_var_launch<int32_t>((const int32_t *)is.d_chunk, C, n, C, d_m + r0, d_v + r0, sms, is.stream));
+            } else {
+                CGS_TRY(row_mean_var_launch<float>((const float *)is.d_chunk, C, n, C, d_m + r0, d_v + r0, sms, is.stream));
+            }
+        }
+        CGS_CUDA(cudaMemcpyAsync(mean, d_m, sizeof(float) * (size_t)n_regions, cudaMemcpyDeviceToHost, is.stream));
+        CGS_CUDA(cudaMemcpyAsync(var, d_v, sizeof(float) * (size_t)n_regions, cudaMemcpyDeviceToHost, is.stream));
+        if (row_nonzero) CGS_CUDA(cudaMemcpyAsync(row_nonzero, is.d_flags, (size_t)n_regions, cudaMemcpyDeviceToHost, is.stream));
+        CGS_CUDA(cudaStreamSynchronize(is.stream));
+        return 0;
+    }();
+    dfree(d_norm, is.stream); dfree(d_tot, is.stream); dfree(d_m, is.stream); dfree(d_v, is.stream);
+    is.close();
+    return rc;
+}
 
 int cgs_impute_rankings(int device, const float *topic_region, const float *cell_topic, int32_t n_regions,
                         int32_t n_topics, int32_t n_cells, float impute_scale, int as_int32, uint64_t seed,

@@ -189,6 +189,19 @@ class FactoredImputedFeatures:
         self._row_nonzero = flags.astype(bool)
         return CistopicImputedFeatures(out[: kept.value], self.feature_names, self.cell_names, self.project)
 
+    def row_mean_var(self, norm_scale=0):
+        """float32 per-region mean and variance over the cells (NumPy's ``mean`` / ``var`` with ``dtype=float32``) of
+        the kept regions: of the imputed values (``norm_scale = 0``) or of ``normalize_scores(self, norm_scale)``;
+        computed chunk by chunk on the device (``cgs_impute_row_stats``)."""
+        _lib.require_device()
+        R = self.topic_region.shape[0]
+        mean, var = np.empty(R, np.float32), np.empty(R, np.float32)
+        flags = np.empty(R, np.uint8)
+        check(_lib.load().cgs_impute_row_stats(*self._operands(), float(norm_scale), self.chunk_size, ptr(mean, c_f32p),
+                                               ptr(var, c_f32p), ptr(flags, c_u8p)))
+        self._row_nonzero = flags.astype(bool)
+        return mean[self._row_nonzero], var[self._row_nonzero]
+
     def make_rankings(self, seed=123, cell_block=0):
         """``make_rankings`` of the imputed matrix without materialising it (``cgs_impute_rankings``): the regions
         ``impute_accessibility`` would keep are ranked per cell, block of cells by block of cells, on the GPU; only
@@ -362,13 +375,15 @@ def calculate_normalized_scores(imputed_acc, scale_factor, device=0):
     return out
 
 
-def normalize_scores(imputed_acc, scale_factor=10 ** 4):
+def normalize_scores(imputed_acc, scale_factor=10 ** 4, materialize=True):
     """Log-normalise imputation data (diff_features.py:511-574); the arithmetic runs on the GPU
-    (SURVEY.md section 8f, row N1)."""
+    (SURVEY.md section 8f, row N1).  ``materialize=False`` (factored input only) returns a
+    :class:`FactoredNormalizedFeatures` that :func:`find_highly_variable_features` reduces on the device without the
+    normalised matrix ever existing."""
     log = _logger()
     log.info("Normalizing imputed data")
     if isinstance(imputed_acc, FactoredImputedFeatures):
-        output = imputed_acc.normalized(scale_factor)
+        output = imputed_acc.normalized(scale_factor) if materialize else FactoredNormalizedFeatures(imputed_acc, scale_factor)
     elif isinstance(imputed_acc, CistopicImputedFeatures):
         mtx = imputed_acc.mtx.toarray() if scipy.sparse.issparse(imputed_acc.mtx) else imputed_acc.mtx
         output = CistopicImputedFeatures(calculate_normalized_scores(mtx, scale_factor), imputed_acc.feature_names,
@@ -380,6 +395,132 @@ def normalize_scores(imputed_acc, scale_factor=10 ** 4):
         raise TypeError("imputed_acc must be a CistopicImputedFeatures or a pandas DataFrame")
     log.info("Done!")
     return output
+
+
+class FactoredNormalizedFeatures:
+    """``normalize_scores(impute_accessibility(..., materialize=False), scale_factor, materialize=False)``: the
+    normalised matrix as a recipe (the two factors + the scale factor).  ``to_dense()`` gives what
+    ``normalize_scores`` returns; ``row_mean_var()`` is what ``find_highly_variable_features`` needs of it."""
+
+    def __init__(self, factored, scale_factor):
+        self.factored = factored
+        self.scale_factor = scale_factor
+        self.cell_names = factored.cell_names
+        self.project = factored.project
+
+    @property
+    def feature_names(self):
+        return self.factored.feature_names
+
+    def to_dense(self):
+        return self.factored.normalized(self.scale_factor)
+
+    def row_mean_var(self):
+        return self.factored.row_mean_var(self.scale_factor)
+
+
+def row_mean_var(matrix, device=0):
+    """``(np.mean(matrix, axis=1, dtype=np.float32), np.var(matrix, axis=1, dtype=np.float32))`` on the GPU
+    (``cgs_row_mean_var``; diff_features.py:636-639)."""
+    _lib.require_device()
+    x = np.asarray(matrix)
+    if x.ndim != 2:
+        raise ValueError("matrix must be a 2-D array (regions x cells)")
+    if x.dtype not in _RANK_DTYPES:
+        x = x.astype(np.float64)
+    if x.strides[1] != x.itemsize or x.strides[0] < x.shape[1] * x.itemsize or x.strides[0] % x.itemsize:
+        x = np.ascontiguousarray(x)
+    mean, var = np.empty(x.shape[0], np.float32), np.empty(x.shape[0], np.float32)
+    if x.shape[0] == 0:
+        return mean, var
+    if x.shape[1] == 0:
+        mean[:], var[:] = np.nan, np.nan
+        return mean, var
+    check(_lib.load().cgs_row_mean_var(device, _RANK_DTYPES[x.dtype], x.ctypes.data_as(c_vp), x.strides[0] // x.itemsize,
+                                       x.shape[0], x.shape[1], ptr(mean, c_f32p), ptr(var, c_f32p)))
+    return mean, var
+
+
+def select_variable_features(mean, var, features, min_disp=0.05, min_mean=0.0125, max_disp=np.inf, max_mean=3,
+                             n_bins=20, n_top_features=None, return_frame=False):
+    """The Seurat-style selection of diff_features.py:641-699 on per-region means and variances (host work on
+    vectors of length n_regions): log dispersion, ``n_bins`` equal-width mean bins, dispersion normalised by its
+    bin's mean and standard deviation (a bin with one region: normalised dispersion 1), then either the
+    ``n_top_features`` largest or the mean / dispersion window."""
+    mean = np.array(mean, dtype=np.float32)
+    mean[mean == 0] = 1e-12
+    dispersion = np.asarray(var, dtype=np.float32) / mean
+    dispersion[dispersion == 0] = np.nan
+    with np.errstate(invalid="ignore", divide="ignore"):
+        dispersion = np.log(dispersion)
+    df = pd.DataFrame({"means": mean, "dispersions": dispersion})
+    df["mean_bin"] = pd.cut(df["means"], bins=n_bins)
+    grouped = df.groupby("mean_bin", observed=False)["dispersions"]
+    bin_mean, bin_std = grouped.mean(), grouped.std(ddof=1)
+    lonely = bin_std.isnull()                      # one region in the bin (or none)
+    bin_std[lonely.values] = bin_mean[lonely.values].values
+    bin_mean[lonely.values] = 0
+    codes = df["mean_bin"].values
+    df["dispersions_norm"] = (df["dispersions"].values - bin_mean[codes].values) / bin_std[codes].values
+    norm = df["dispersions_norm"].values.astype("float32")
+    if n_top_features is not None:
+        ranked = norm[~np.isnan(norm)]
+        ranked[::-1].sort()
+        cut = ranked[n_top_features - 1]
+        chosen = np.nan_to_num(df["dispersions_norm"].values) >= cut
+    else:
+        norm[np.isnan(norm)] = 0
+        chosen = np.logical_and.reduce((mean > min_mean, mean < max_mean, norm > min_disp, norm < max_disp))
+    df["highly_variable"] = chosen
+    selected = [features[i] for i in np.flatnonzero(chosen)]
+    return (selected, df) if return_frame else selected
+
+
+def find_highly_variable_features(input_mat, min_disp=0.05, min_mean=0.0125, max_disp=np.inf, max_mean=3, n_bins=20,
+                                  n_top_features=None, plot=True, save=None, device=0):
+    """Find highly variable features (diff_features.py:577-714).  The pass over the matrix -- per-region mean and
+    variance, :636-639 -- runs on the GPU: ``cgs_row_mean_var`` for a dense matrix / DataFrame, and straight from
+    the factors (``cgs_impute_row_stats``; the matrix never exists) for a :class:`FactoredNormalizedFeatures` or a
+    :class:`FactoredImputedFeatures`.  The selection on the two vectors is host work (:func:`select_variable_features`)."""
+    log = _logger()
+    if isinstance(input_mat, pd.DataFrame):
+        features = input_mat.index.tolist()
+        log.info("Calculating mean and variance")
+        mean, var = row_mean_var(input_mat.values, device)
+    elif isinstance(input_mat, (FactoredNormalizedFeatures, FactoredImputedFeatures)):
+        features = input_mat.feature_names
+        log.info("Calculating mean and variance")
+        mean, var = input_mat.row_mean_var()
+    else:
+        features = input_mat.feature_names
+        mat = input_mat.mtx
+        log.info("Calculating mean and variance")
+        if scipy.sparse.issparse(mat):   # sklearn.utils.sparsefuncs.mean_variance_axis in the reference (:633)
+            mat = scipy.sparse.csr_matrix(mat)
+            step = max(1, (1 << 27) // max(1, mat.shape[1]))
+            parts = [row_mean_var(mat[r0:r0 + step].toarray(), device) for r0 in range(0, mat.shape[0], step)]
+            mean, var = (np.concatenate([p[i] for p in parts]) if parts else np.empty(0, np.float32) for i in (0, 1))
+        else:
+            mean, var = row_mean_var(mat, device)
+    var_features, df = select_variable_features(mean, var, features, min_disp, min_mean, max_disp, max_mean, n_bins,
+                                                n_top_features, return_frame=True)
+    if plot:
+        try:
+            import matplotlib
+            import matplotlib.pyplot as plt
+        except ImportError:
+            log.warning("matplotlib is not installed: the mean / dispersion plot is skipped")
+        else:
+            fig = plt.figure()
+            matplotlib.rcParams["agg.path.chunksize"] = 10000
+            plt.scatter(df["means"], df["dispersions_norm"], c=df["highly_variable"], s=10, alpha=0.1)
+            plt.xlabel("Mean measurement of features")
+            plt.ylabel("Normalized dispersion of the features")
+            if save is not None:
+                fig.savefig(save)
+            plt.show()
+    log.info("Done!")
+    return var_features
 
 
 def rank_columns(scores, seed=123, first_col=0, device=0):

@@ -169,6 +169,31 @@ def golden_rankings():
     np.savez_compressed(os.path.join(HERE, "rankings.npz"), **out)
 
 
+def golden_variable_features():
+    """find_highly_variable_features of the reference (diff_features.py:577-714, executed from the tree) on a
+    normalised-imputation-shaped float64 matrix, an int32 imputed one and a float32 one: NumPy's float32 mean / var
+    per region and the selected features for the default window and for n_top_features."""
+    import pandas as pd
+    fn = rf.reference_find_highly_variable_features()
+    rng = np.random.default_rng(77)
+    R, C, K = 900, 160, 8
+    tr = rng.dirichlet(np.full(R, 0.3), K).T
+    ct = rng.dirichlet(np.full(K, 0.4), C).T
+    imputed = (tr @ ct * 1e6).astype(np.int32)
+    imputed = imputed[imputed.any(axis=1)]
+    norm64 = np.log1p(imputed / (imputed.sum(axis=0) / 10 ** 4))
+    out = {"imputed": imputed}   # norm64 = np.log1p(imputed / (imputed.sum(axis=0) / 10 ** 4)), recomputed by the tests
+    for name, mat in (("norm64", norm64), ("imputed", imputed), ("norm32", norm64.astype(np.float32))):
+        frame = pd.DataFrame(mat, index=[f"r{i}" for i in range(mat.shape[0])])
+        out[f"{name}_mean"] = np.mean(mat, axis=1, dtype=np.float32)
+        out[f"{name}_var"] = np.var(mat, axis=1, dtype=np.float32)
+        out[f"{name}_default"] = np.array(fn(frame, plot=False), dtype=str)
+        out[f"{name}_top100"] = np.array(fn(frame, n_top_features=100, plot=False), dtype=str)
+        out[f"{name}_window"] = np.array(fn(frame, min_disp=0.5, min_mean=0.05, max_mean=2.0, max_disp=3.0, n_bins=10,
+                                            plot=False), dtype=str)
+    np.savez_compressed(os.path.join(HERE, "variable_features.npz"), **out)
+
+
 if __name__ == "__main__":
     if not rf.available():
         sys.exit("the reference tree is not available: cannot regenerate the golden fixtures")
@@ -177,4 +202,5 @@ if __name__ == "__main__":
     golden_oracle_kat()
     golden_diff_features()
     golden_rankings()
+    golden_variable_features()
     print("golden fixtures written to", HERE)

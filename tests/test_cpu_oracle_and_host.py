@@ -405,3 +405,19 @@ def test_mallet_formats_roundtrip_and_reference_text(tmp_path):
     bad.write_text("not a state\n")
     with pytest.raises(ValueError, match="not a Mallet state file"):
         mf.read_state(str(bad))
+
+
+def test_variable_feature_selection_matches_reference_golden():
+    """select_variable_features (host half of find_highly_variable_features) against the reference's own function
+    (diff_features.py:577-714, run from the tree into tests/golden/variable_features.npz) on NumPy's float32 mean /
+    var: identical feature lists for the default window, n_top_features and a custom window, three dtypes."""
+    from pycistopic_b200 import diff_features as pdf
+    g = np.load(os.path.join(ROOT, "tests", "golden", "variable_features.npz"))
+    for name in ("norm64", "imputed", "norm32"):
+        mean, var = g[f"{name}_mean"], g[f"{name}_var"]
+        feats = [f"r{i}" for i in range(len(mean))]
+        assert pdf.select_variable_features(mean, var, feats) == list(g[f"{name}_default"])
+        assert pdf.select_variable_features(mean, var, feats, n_top_features=100) == list(g[f"{name}_top100"])
+        assert pdf.select_variable_features(mean, var, feats, min_disp=0.5, min_mean=0.05, max_mean=2.0, max_disp=3.0,
+                                            n_bins=10) == list(g[f"{name}_window"])
+    assert len(g["norm64_default"]) > 100 and len(g["norm64_window"]) > 20
