@@ -299,10 +299,33 @@ int cgs_impute_ranksum(int device, const float *topic_region, const float *cell_
  * whole regions x block product is imputed on the device and ranked there (cgs_rank_columns_device semantics, tie
  * order keyed by (seed, cell index)); out = int32 rankings, n_regions x n_cells row-major host memory.  The
  * reference ranks only the regions impute_accessibility kept: pass topic_region without its all-zero rows.
- * cell_block <= 0 picks a block of about 2^29 values. */
+ * cell_block <= 0 picks a block of about 2^29 values.  first_cell = global index of cell 0 of cell_topic (keys the tie
+ * order); out has row stride ld_out. */
 int cgs_impute_rankings(int device, const float *topic_region, const float *cell_topic, int32_t n_regions,
                         int32_t n_topics, int32_t n_cells, float impute_scale, int as_int32, uint64_t seed,
-                        int32_t cell_block, int32_t *out);
+                        int32_t cell_block, int64_t first_cell, int32_t *out, int64_t ld_out);
+
+/* ---- sharding the consumers over GPUs (SURVEY.md section 8e iii: regions are independent, cells couple only through
+ * the per-cell totals of normalize_scores) -----------------------------------------------------------------------
+ * Every rank / device gets a contiguous range of regions (rows of topic_region) and the whole cell_topic.
+ * cgs_impute_ranksum, cgs_impute_chunk* and cgs_impute_row_stats with norm_scale == 0 need nothing else: call them on
+ * the shard.  The normalised consumers need the per-cell totals of the WHOLE matrix: every rank computes the totals
+ * of its shard (cgs_impute_column_totals: int64[n_cells] when as_int32 != 0, else float64[n_cells]), the ranks add
+ * them up -- the one exchange step, an all-reduce of n_cells values (torch.distributed / NCCL between processes, a
+ * host sum between the threads of one process) -- and pass the sum to the _shard variants below.  make_rankings
+ * shards by CELLS instead: cgs_impute_rankings on cell_topic[:, c0:c1] with first_cell = c0 and out + c0, ld_out =
+ * total number of cells (the tie order is keyed by the global cell index). */
+int cgs_impute_column_totals(int device, const float *topic_region, const float *cell_topic, int32_t n_regions,
+                             int32_t n_topics, int32_t n_cells, float impute_scale, int as_int32, int32_t chunk_rows,
+                             void *column_totals, uint8_t *row_nonzero);
+int cgs_impute_normalized_shard(int device, const float *topic_region, const float *cell_topic, int32_t n_regions,
+                                int32_t n_topics, int32_t n_cells, float impute_scale, int as_int32, double norm_scale,
+                                int32_t chunk_rows, const void *column_totals, void *out, uint8_t *row_nonzero,
+                                int64_t *n_kept);
+int cgs_impute_row_stats_shard(int device, const float *topic_region, const float *cell_topic, int32_t n_regions,
+                               int32_t n_topics, int32_t n_cells, float impute_scale, int as_int32, double norm_scale,
+                               int32_t chunk_rows, const void *column_totals, float *mean, float *var,
+                               uint8_t *row_nonzero);
 /* The same reduction on normalize_scores(impute_accessibility(...)) (norm_scale > 0: statistics of
  * log1p(x / (colsum(x) / norm_scale)), float64 values for the int32 imputation, float32 otherwise) or on the imputed
  * values themselves (norm_scale == 0), from the two factors: mean / var are float32[n_regions] over ALL regions,

@@ -115,7 +115,16 @@ SIGNATURES = {
                                             ctypes.c_float, ctypes.c_int, ctypes.c_double, ctypes.c_int32, c_f32p, c_f32p,
                                             c_u8p]),
     "cgs_impute_rankings": (ctypes.c_int, [ctypes.c_int, c_f32p, c_f32p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
-                                           ctypes.c_float, ctypes.c_int, ctypes.c_uint64, ctypes.c_int32, c_i32p]),
+                                           ctypes.c_float, ctypes.c_int, ctypes.c_uint64, ctypes.c_int32, ctypes.c_int64,
+                                           c_vp, ctypes.c_int64]),
+    "cgs_impute_column_totals": (ctypes.c_int, [ctypes.c_int, c_f32p, c_f32p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                                ctypes.c_float, ctypes.c_int, ctypes.c_int32, c_vp, c_u8p]),
+    "cgs_impute_normalized_shard": (ctypes.c_int, [ctypes.c_int, c_f32p, c_f32p, ctypes.c_int32, ctypes.c_int32,
+                                                   ctypes.c_int32, ctypes.c_float, ctypes.c_int, ctypes.c_double,
+                                                   ctypes.c_int32, c_vp, c_vp, c_u8p, c_i64p]),
+    "cgs_impute_row_stats_shard": (ctypes.c_int, [ctypes.c_int, c_f32p, c_f32p, ctypes.c_int32, ctypes.c_int32,
+                                                  ctypes.c_int32, ctypes.c_float, ctypes.c_int, ctypes.c_double,
+                                                  ctypes.c_int32, c_vp, c_f32p, c_f32p, c_u8p]),
     "cgs_rank_columns": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                         ctypes.c_uint64, ctypes.c_int64, c_i32p, ctypes.c_int64]),
     "cgs_rank_columns_device": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_vp, ctypes.c_int64, ctypes.c_int64,

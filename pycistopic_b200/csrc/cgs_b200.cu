@@ -1811,9 +1811,14 @@ struct ImputeStream {
 
 extern "C" {
 
-int cgs_impute_normalized(int device, const float *topic_region, const float *cell_topic, int32_t n_regions,
-                          int32_t n_topics, int32_t n_cells, float impute_scale, int as_int32, double norm_scale,
-                          int32_t chunk_rows, void *out, uint8_t *row_nonzero, void *column_totals, int64_t *n_kept) {
+}  // extern "C"
+
+// totals_in != NULL: the per-cell totals of the WHOLE matrix (this call handles a shard of its regions); the first
+// pass then only recomputes the chunks for the row flags
+static int impute_normalized_impl(int device, const float *topic_region, const float *cell_topic, int32_t n_regions,
+                                  int32_t n_topics, int32_t n_cells, float impute_scale, int as_int32, double norm_scale,
+                                  int32_t chunk_rows, void *out, uint8_t *row_nonzero, void *column_totals,
+                                  const void *totals_in, int64_t *n_kept) {
     if (!topic_region || !cell_topic || !out || !n_kept) CGS_FAIL("NULL argument");
     if (n_regions <= 0 || n_topics <= 0 || n_cells <= 0) CGS_FAIL("empty operand");
     if (!(norm_scale != 0.0)) CGS_FAIL("scale_factor must not be zero");
@@ -1834,11 +1839,13 @@ int cgs_impute_normalized(int device, const float *topic_region, const float *ce
         for (int32_t r0 = 0; r0 < n_regions; r0 += is.chunk) {
             const int32_t n = std::min(is.chunk, n_regions - r0);
             CGS_TRY(is.run(r0, n));
+            if (totals_in) continue;
             dim3 grid((unsigned)ceil_div(C, kNormCols), (unsigned)ceil_div(n, kNormSlab));
             if (as_int32) colsum_kernel<int32_t><<<grid, kNormCols, 0, is.stream>>>((const int32_t *)is.d_chunk, n, C, (long long *)d_tot);
             else colsum_kernel<float><<<grid, kNormCols, 0, is.stream>>>((const float *)is.d_chunk, n, C, (double *)d_tot);
             CGS_CUDA(cudaGetLastError());
         }
+        if (totals_in) CGS_CUDA(cudaMemcpyAsync(d_tot, totals_in, (size_t)C * 8, cudaMemcpyHostToDevice, is.stream));
         CGS_CUDA(cudaMemcpyAsync(flags.data(), is.d_flags, (size_t)n_regions, cudaMemcpyDeviceToHost, is.stream));
         if (column_totals) CGS_CUDA(cudaMemcpyAsync(column_totals, d_tot, (size_t)C * 8, cudaMemcpyDeviceToHost, is.stream));
         CGS_CUDA(cudaStreamSynchronize(is.stream));
@@ -1871,6 +1878,57 @@ int cgs_impute_normalized(int device, const float *topic_region, const float *ce
         return 0;
     }();
     dfree(d_norm, is.stream); dfree(d_tot, is.stream);
+    is.close();
+    return rc;
+}
+
+extern "C" {
+
+int cgs_impute_normalized(int device, const float *topic_region, const float *cell_topic, int32_t n_regions,
+                          int32_t n_topics, int32_t n_cells, float impute_scale, int as_int32, double norm_scale,
+                          int32_t chunk_rows, void *out, uint8_t *row_nonzero, void *column_totals, int64_t *n_kept) {
+    return impute_normalized_impl(device, topic_region, cell_topic, n_regions, n_topics, n_cells, impute_scale, as_int32,
+                                  norm_scale, chunk_rows, out, row_nonzero, column_totals, nullptr, n_kept);
+}
+
+int cgs_impute_normalized_shard(int device, const float *topic_region, const float *cell_topic, int32_t n_regions,
+                                int32_t n_topics, int32_t n_cells, float impute_scale, int as_int32, double norm_scale,
+                                int32_t chunk_rows, const void *column_totals, void *out, uint8_t *row_nonzero,
+                                int64_t *n_kept) {
+    if (!column_totals) CGS_FAIL("NULL argument");
+    return impute_normalized_impl(device, topic_region, cell_topic, n_regions, n_topics, n_cells, impute_scale, as_int32,
+                                  norm_scale, chunk_rows, out, row_nonzero, nullptr, column_totals, n_kept);
+}
+
+int cgs_impute_column_totals(int device, const float *topic_region, const float *cell_topic, int32_t n_regions,
+                             int32_t n_topics, int32_t n_cells, float impute_scale, int as_int32, int32_t chunk_rows,
+                             void *column_totals, uint8_t *row_nonzero) {
+    if (!topic_region || !cell_topic || !column_totals) CGS_FAIL("NULL argument");
+    if (n_regions <= 0 || n_topics <= 0 || n_cells <= 0) CGS_FAIL("empty operand");
+    DeviceGuard g(device);
+    if (!g.ok) CGS_FAIL("cannot select CUDA device");
+    CGS_TRY(configure_pool(device));
+    ImputeStream is;
+    uint8_t *d_tot = nullptr;
+    const int64_t C = n_cells;
+    int rc = [&]() -> int {
+        CGS_TRY(is.open(device, topic_region, cell_topic, n_regions, n_topics, n_cells, impute_scale, as_int32, chunk_rows));
+        CGS_TRY(dmalloc(&d_tot, (size_t)C * 8, is.stream));
+        CGS_CUDA(cudaMemsetAsync(d_tot, 0, (size_t)C * 8, is.stream));
+        for (int32_t r0 = 0; r0 < n_regions; r0 += is.chunk) {
+            const int32_t n = std::min(is.chunk, n_regions - r0);
+            CGS_TRY(is.run(r0, n));
+            dim3 grid((unsigned)ceil_div(C, kNormCols), (unsigned)ceil_div(n, kNormSlab));
+            if (as_int32) colsum_kernel<int32_t><<<grid, kNormCols, 0, is.stream>>>((const int32_t *)is.d_chunk, n, C, (long long *)d_tot);
+            else colsum_kernel<float><<<grid, kNormCols, 0, is.stream>>>((const float *)is.d_chunk, n, C, (double *)d_tot);
+            CGS_CUDA(cudaGetLastError());
+        }
+        CGS_CUDA(cudaMemcpyAsync(column_totals, d_tot, (size_t)C * 8, cudaMemcpyDeviceToHost, is.stream));
+        if (row_nonzero) CGS_CUDA(cudaMemcpyAsync(row_nonzero, is.d_flags, (size_t)n_regions, cudaMemcpyDeviceToHost, is.stream));
+        CGS_CUDA(cudaStreamSynchronize(is.stream));
+        return 0;
+    }();
+    dfree(d_tot, is.stream);
     is.close();
     return rc;
 }
@@ -1938,9 +1996,11 @@ int cgs_impute_ranksum(int device, const float *topic_region, const float *cell_
 }
 
 
-int cgs_impute_row_stats(int device, const float *topic_region, const float *cell_topic, int32_t n_regions,
-                         int32_t n_topics, int32_t n_cells, float impute_scale, int as_int32, double norm_scale,
-                         int32_t chunk_rows, float *mean, float *var, uint8_t *row_nonzero) {
+}  // extern "C"
+
+static int impute_row_stats_impl(int device, const float *topic_region, const float *cell_topic, int32_t n_regions,
+                                 int32_t n_topics, int32_t n_cells, float impute_scale, int as_int32, double norm_scale,
+                                 int32_t chunk_rows, const void *totals_in, float *mean, float *var, uint8_t *row_nonzero) {
     if (!topic_region || !cell_topic || !mean || !var) CGS_FAIL("NULL argument");
     if (n_regions <= 0 || n_topics <= 0 || n_cells <= 0) CGS_FAIL("empty operand");
     if (norm_scale < 0.0) CGS_FAIL("scale_factor must not be negative (0 = statistics of the imputed values themselves)");
@@ -1963,7 +2023,8 @@ int cgs_impute_row_stats(int device, const float *topic_region, const float *cel
             CGS_TRY(dmalloc(&d_norm, (size_t)is.chunk * C * out_elem, is.stream));
             CGS_TRY(dmalloc(&d_tot, (size_t)C * 8, is.stream));
             CGS_CUDA(cudaMemsetAsync(d_tot, 0, (size_t)C * 8, is.stream));
-            for (int32_t r0 = 0; r0 < n_regions; r0 += is.chunk) {  // pass 1: per-cell totals
+            if (totals_in) CGS_CUDA(cudaMemcpyAsync(d_tot, totals_in, (size_t)C * 8, cudaMemcpyHostToDevice, is.stream));
+            for (int32_t r0 = 0; r0 < n_regions && !totals_in; r0 += is.chunk) {  // pass 1: per-cell totals
                 const int32_t n = std::min(is.chunk, n_regions - r0);
                 CGS_TRY(is.run(r0, n));
                 dim3 grid((unsigned)ceil_div(C, kNormCols), (unsigned)ceil_div(n, kNormSlab));
@@ -2005,11 +2066,31 @@ int cgs_impute_row_stats(int device, const float *topic_region, const float *cel
     return rc;
 }
 
+extern "C" {
+
+int cgs_impute_row_stats(int device, const float *topic_region, const float *cell_topic, int32_t n_regions,
+                         int32_t n_topics, int32_t n_cells, float impute_scale, int as_int32, double norm_scale,
+                         int32_t chunk_rows, float *mean, float *var, uint8_t *row_nonzero) {
+    return impute_row_stats_impl(device, topic_region, cell_topic, n_regions, n_topics, n_cells, impute_scale, as_int32,
+                                 norm_scale, chunk_rows, nullptr, mean, var, row_nonzero);
+}
+
+int cgs_impute_row_stats_shard(int device, const float *topic_region, const float *cell_topic, int32_t n_regions,
+                               int32_t n_topics, int32_t n_cells, float impute_scale, int as_int32, double norm_scale,
+                               int32_t chunk_rows, const void *column_totals, float *mean, float *var,
+                               uint8_t *row_nonzero) {
+    if (!column_totals) CGS_FAIL("NULL argument");
+    if (!(norm_scale > 0.0)) CGS_FAIL("scale_factor must be positive when per-cell totals are given");
+    return impute_row_stats_impl(device, topic_region, cell_topic, n_regions, n_topics, n_cells, impute_scale, as_int32,
+                                 norm_scale, chunk_rows, column_totals, mean, var, row_nonzero);
+}
+
 int cgs_impute_rankings(int device, const float *topic_region, const float *cell_topic, int32_t n_regions,
                         int32_t n_topics, int32_t n_cells, float impute_scale, int as_int32, uint64_t seed,
-                        int32_t cell_block, int32_t *out) {
+                        int32_t cell_block, int64_t first_cell, int32_t *out, int64_t ld_out) {
     if (!topic_region || !cell_topic || !out) CGS_FAIL("NULL argument");
     if (n_regions <= 0 || n_topics <= 0 || n_cells <= 0) CGS_FAIL("empty operand");
+    if (ld_out < n_cells) CGS_FAIL("row stride smaller than the number of cells");
     DeviceGuard g(device);
     if (!g.ok) CGS_FAIL("cannot select CUDA device");
     CGS_TRY(configure_pool(device));
@@ -2034,8 +2115,8 @@ int cgs_impute_rankings(int device, const float *topic_region, const float *cell
             for (int64_t k = 0; k < K; ++k) memcpy(cells.data() + k * nc, cell_topic + k * C + c0, sizeof(float) * (size_t)nc);
             CGS_TRY(cgs_impute_plan_create(&plan, device, cells.data(), 0, n_topics, nc, stream));
             CGS_TRY(cgs_impute_plan_chunk_device(plan, d_a, n_regions, impute_scale, as_int32, d_prod, d_flags, stream));
-            CGS_TRY(cgs_rank_columns_device(device, as_int32 ? 0 : 1, d_prod, nc, R, nc, seed, c0, d_rank, nc, stream));
-            CGS_CUDA(cudaMemcpy2DAsync(out + c0, (size_t)C * 4, d_rank, (size_t)nc * 4, (size_t)nc * 4, (size_t)R,
+            CGS_TRY(cgs_rank_columns_device(device, as_int32 ? 0 : 1, d_prod, nc, R, nc, seed, first_cell + c0, d_rank, nc, stream));
+            CGS_CUDA(cudaMemcpy2DAsync(out + c0, (size_t)ld_out * 4, d_rank, (size_t)nc * 4, (size_t)nc * 4, (size_t)R,
                                        cudaMemcpyDeviceToHost, stream));
             CGS_CUDA(cudaStreamSynchronize(stream));
             cgs_impute_plan_destroy(plan);

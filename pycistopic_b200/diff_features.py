@@ -22,6 +22,32 @@ from . import _lib
 from ._lib import c_f32p, c_u8p, c_vp, check, ptr
 
 
+def _as_devices(device):
+    """``device`` arguments take one CUDA ordinal or a sequence of them (regions are sharded over the sequence)."""
+    if isinstance(device, (int, np.integer)):
+        return [int(device)]
+    devices = [int(d) for d in device]
+    if not devices:
+        raise ValueError("need at least one device")
+    return devices
+
+
+def _shards(n, devices):
+    """``[(device, start, stop), ...]``: contiguous, near-equal, non-empty ranges of ``range(n)``."""
+    bounds = np.linspace(0, n, len(devices) + 1).astype(np.int64)
+    return [(d, int(a), int(b)) for d, a, b in zip(devices, bounds[:-1], bounds[1:]) if b > a]
+
+
+def _run_sharded(fn, shards):
+    """``fn(*shard)`` for every shard, one host thread per shard (the library calls release the GIL; every shard
+    drives its own device on its own stream); results in shard order."""
+    if len(shards) == 1:
+        return [fn(*shards[0])]
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(len(shards)) as pool:
+        return list(pool.map(lambda a: fn(*a), shards))
+
+
 def get_position_index(query_list, target_list):
     """utils.py:105-110."""
     d = {k: idx for idx, k in enumerate(target_list)}
@@ -123,7 +149,8 @@ class FactoredImputedFeatures:
         self.scale_factor = scale_factor
         self.chunk_size = int(chunk_size)
         self.project = project
-        self.device = device
+        self.devices = _as_devices(device)      # regions (cells for make_rankings) are sharded over them
+        self.device = self.devices[0]
         self._row_nonzero = None
 
     @property
@@ -138,10 +165,33 @@ class FactoredImputedFeatures:
         return (f"FactoredImputedFeatures from project {self.project} with nCells × nFeatures = "
                 f"{len(self.cell_names)} × {self.topic_region.shape[0]} (not materialised)")
 
-    def _operands(self):
+    def _operands(self, device=None, r0=0, r1=None):
+        """Leading ABI arguments for the regions [r0, r1) on ``device``."""
         R, K = self.topic_region.shape
-        return (self.device, ptr(self.topic_region, c_f32p), ptr(self.cell_topic, c_f32p), R, K, self.cell_topic.shape[1],
-                self.impute_scale, int(self.as_int32))
+        r1 = R if r1 is None else r1
+        a = self.topic_region[r0:r1]
+        return (self.device if device is None else device, ptr(a, c_f32p), ptr(self.cell_topic, c_f32p), r1 - r0, K,
+                self.cell_topic.shape[1], self.impute_scale, int(self.as_int32))
+
+    def _region_shards(self):
+        return _shards(self.topic_region.shape[0], self.devices)
+
+    def _column_totals(self, shards):
+        """Per-cell totals of the whole imputed matrix + row flags: every shard's partial totals (one pass over its
+        recomputed chunks), summed -- the one exchange step of the sharded normalisation (SURVEY.md 8e iii)."""
+        R, C = self.topic_region.shape[0], self.cell_topic.shape[1]
+        flags = np.empty(R, np.uint8)
+        dt = np.int64 if self.as_int32 else np.float64
+
+        def one(dev, r0, r1):
+            tot = np.empty(C, dt)
+            check(_lib.load().cgs_impute_column_totals(*self._operands(dev, r0, r1), self.chunk_size,
+                                                       tot.ctypes.data_as(c_vp), ptr(flags[r0:r1], c_u8p)))
+            return tot
+
+        totals = np.sum(_run_sharded(one, shards), axis=0, dtype=dt)
+        self._row_nonzero = flags.astype(bool)
+        return np.ascontiguousarray(totals)
 
     def ranksum(self, contrasts_cols):
         """``[(fg column indices, bg column indices), ...]`` -> ``(statistic, pvalue, log2fc, row_nonzero)``,
@@ -167,12 +217,18 @@ class FactoredImputedFeatures:
         if live:
             fg, fo = pack([contrasts_cols[i][0] for i in live])
             bg, bo = pack([contrasts_cols[i][1] for i in live])
-            s2, p2, l2 = (np.empty((len(live), R), np.float64) for _ in range(3))
-            check(_lib.load().cgs_impute_ranksum(*self._operands(), self.chunk_size, len(live),
-                                                 ptr(fg, _lib.c_i32p), ptr(fo, _lib.c_i64p), ptr(bg, _lib.c_i32p),
-                                                 ptr(bo, _lib.c_i64p), ptr(s2, _lib.c_f64p), ptr(p2, _lib.c_f64p),
-                                                 ptr(l2, _lib.c_f64p), ptr(flags, c_u8p)))
-            stat[live], pval[live], l2fc[live] = s2, p2, l2
+            def one(dev, r0, r1):  # regions are independent: a shard is a plain call on its rows
+                s2, p2, l2 = (np.empty((len(live), r1 - r0), np.float64) for _ in range(3))
+                check(_lib.load().cgs_impute_ranksum(*self._operands(dev, r0, r1), self.chunk_size, len(live),
+                                                     ptr(fg, _lib.c_i32p), ptr(fo, _lib.c_i64p), ptr(bg, _lib.c_i32p),
+                                                     ptr(bo, _lib.c_i64p), ptr(s2, _lib.c_f64p), ptr(p2, _lib.c_f64p),
+                                                     ptr(l2, _lib.c_f64p), ptr(flags[r0:r1], c_u8p)))
+                return s2, p2, l2
+
+            shards = self._region_shards()
+            for (dev, r0, r1), (s2, p2, l2) in zip(shards, _run_sharded(one, shards)):
+                for dst, src in ((stat, s2), (pval, p2), (l2fc, l2)):
+                    dst[np.ix_(live, range(r0, r1))] = src
             self._row_nonzero = flags.astype(bool)
         return stat, pval, l2fc, self.row_nonzero
 
@@ -182,12 +238,27 @@ class FactoredImputedFeatures:
         _lib.require_device()
         R, C = self.topic_region.shape[0], self.cell_topic.shape[1]
         out = np.empty((R, C), np.float64 if self.as_int32 else np.float32)
-        flags = np.empty(R, np.uint8)
-        kept = ctypes.c_int64()
-        check(_lib.load().cgs_impute_normalized(*self._operands(), float(scale_factor), self.chunk_size,
-                                                out.ctypes.data_as(c_vp), ptr(flags, c_u8p), None, ctypes.byref(kept)))
-        self._row_nonzero = flags.astype(bool)
-        return CistopicImputedFeatures(out[: kept.value], self.feature_names, self.cell_names, self.project)
+        shards = self._region_shards()
+        if len(shards) == 1:
+            flags = np.empty(R, np.uint8)
+            kept = ctypes.c_int64()
+            check(_lib.load().cgs_impute_normalized(*self._operands(), float(scale_factor), self.chunk_size,
+                                                    out.ctypes.data_as(c_vp), ptr(flags, c_u8p), None, ctypes.byref(kept)))
+            self._row_nonzero = flags.astype(bool)
+            return CistopicImputedFeatures(out[: kept.value], self.feature_names, self.cell_names, self.project)
+        totals = self._column_totals(shards)                 # sets the row flags
+        first = np.concatenate([[0], np.cumsum(self._row_nonzero)])   # kept regions before every region
+
+        def one(dev, r0, r1):
+            kept = ctypes.c_int64()
+            check(_lib.load().cgs_impute_normalized_shard(*self._operands(dev, r0, r1), float(scale_factor), self.chunk_size,
+                                                          totals.ctypes.data_as(c_vp), out[first[r0]:].ctypes.data_as(c_vp),
+                                                          None, ctypes.byref(kept)))
+            if kept.value != first[r1] - first[r0]:
+                raise RuntimeError("row filter changed between the two passes")
+
+        _run_sharded(one, shards)
+        return CistopicImputedFeatures(out[: first[-1]], self.feature_names, self.cell_names, self.project)
 
     def row_mean_var(self, norm_scale=0):
         """float32 per-region mean and variance over the cells (NumPy's ``mean`` / ``var`` with ``dtype=float32``) of
@@ -197,8 +268,20 @@ class FactoredImputedFeatures:
         R = self.topic_region.shape[0]
         mean, var = np.empty(R, np.float32), np.empty(R, np.float32)
         flags = np.empty(R, np.uint8)
-        check(_lib.load().cgs_impute_row_stats(*self._operands(), float(norm_scale), self.chunk_size, ptr(mean, c_f32p),
-                                               ptr(var, c_f32p), ptr(flags, c_u8p)))
+        shards = self._region_shards()
+        L = _lib.load()
+        if len(shards) > 1 and norm_scale:
+            totals = self._column_totals(shards)
+
+            def one(dev, r0, r1):
+                check(L.cgs_impute_row_stats_shard(*self._operands(dev, r0, r1), float(norm_scale), self.chunk_size,
+                                                   totals.ctypes.data_as(c_vp), ptr(mean[r0:r1], c_f32p),
+                                                   ptr(var[r0:r1], c_f32p), ptr(flags[r0:r1], c_u8p)))
+        else:
+            def one(dev, r0, r1):
+                check(L.cgs_impute_row_stats(*self._operands(dev, r0, r1), float(norm_scale), self.chunk_size,
+                                             ptr(mean[r0:r1], c_f32p), ptr(var[r0:r1], c_f32p), ptr(flags[r0:r1], c_u8p)))
+        _run_sharded(one, shards)
         self._row_nonzero = flags.astype(bool)
         return mean[self._row_nonzero], var[self._row_nonzero]
 
@@ -213,9 +296,13 @@ class FactoredImputedFeatures:
         C = self.cell_topic.shape[1]
         out = np.empty((R, C), np.int32)
         if R and C:
-            check(_lib.load().cgs_impute_rankings(self.device, ptr(tr, c_f32p), ptr(self.cell_topic, c_f32p), R, K, C,
-                                                  self.impute_scale, int(self.as_int32), int(seed) & (2 ** 64 - 1),
-                                                  int(cell_block), ptr(out, _lib.c_i32p)))
+            def one(dev, c0, c1):  # cells are independent; the tie order is keyed by the global cell index
+                ct = np.ascontiguousarray(self.cell_topic[:, c0:c1])
+                check(_lib.load().cgs_impute_rankings(dev, ptr(tr, c_f32p), ptr(ct, c_f32p), R, K, c1 - c0,
+                                                      self.impute_scale, int(self.as_int32), int(seed) & (2 ** 64 - 1),
+                                                      int(cell_block), c0, out[:, c0:].ctypes.data_as(c_vp), C))
+
+            _run_sharded(one, _shards(C, self.devices))
         return CistopicImputedFeatures(out, self.feature_names, self.cell_names, self.project)
 
     @property
@@ -241,14 +328,14 @@ class FactoredImputedFeatures:
             idx = get_position_index(features, regions)
             tr, regions = tr[idx], subset_list(regions, idx)
         out = FactoredImputedFeatures(tr, ct, regions, cell_names, self.scale_factor, self.chunk_size, self.project,
-                                      self.device)
+                                      self.devices)
         if copy is True:
             return out
         self.__dict__.update(out.__dict__)
 
     def to_dense(self):
         imputed_acc, keep = calculate_imputed_accessibility(self.topic_region, self.cell_topic, self.region_names,
-                                                            self.scale_factor, self.chunk_size, device=self.device)
+                                                            self.scale_factor, self.chunk_size, device=self.devices)
         return CistopicImputedFeatures(imputed_acc, keep, self.cell_names, self.project)
 
 
@@ -279,27 +366,40 @@ def calculate_imputed_accessibility(topic_region, cell_topic, region_names, scal
     region_names_to_keep = []
     output_chunk_end = 0
     scale = float(np.float32(scale_factor)) if as_int else 1.0
-    plan = c_vp()
-    check(L.cgs_impute_plan_create(ctypes.byref(plan), device, ptr(cell_topic, c_f32p), 0, K, C, None))
+    devices = _as_devices(device)
+    plans = []
     try:
-        for input_chunk_start in range(0, R, chunk_size):
-            input_chunk_end = input_chunk_start + chunk_size
-            output_chunk_start = output_chunk_end
-            if log is not None:
-                log.info(f"Impute region accessibility for regions {input_chunk_start}-{input_chunk_end}")
-            a = topic_region[input_chunk_start:input_chunk_end]
+        for dev in devices:  # one plan (cell operand prepared on that device) per GPU
+            plan = c_vp()
+            check(L.cgs_impute_plan_create(ctypes.byref(plan), dev, ptr(cell_topic, c_f32p), 0, K, C, None))
+            plans.append(plan)
+
+        def impute_chunk(plan, input_chunk_start):
+            a = topic_region[input_chunk_start:input_chunk_start + chunk_size]
             n = a.shape[0]
             chunk = np.empty((n, C), dtype=out_dtype)
             flags = np.empty(n, dtype=np.uint8)
             check(L.cgs_impute_plan_chunk(plan, ptr(a, c_f32p), n, scale, int(as_int), chunk.ctypes.data_as(c_vp),
                                           ptr(flags, c_u8p)))
-            keep = np.flatnonzero(flags)
-            names_chunk = region_names[input_chunk_start:input_chunk_end]
-            region_names_to_keep.extend([names_chunk[i] for i in keep])
-            output_chunk_end = output_chunk_start + len(keep)
-            imputed_acc[output_chunk_start:output_chunk_end, :] = chunk[keep]
+            return chunk, flags
+
+        starts = list(range(0, R, chunk_size))
+        for wave in range(0, len(starts), len(plans)):  # chunks are independent: one per device at a time, kept in order
+            batch = starts[wave:wave + len(plans)]
+            results = _run_sharded(impute_chunk, list(zip(plans, batch)))
+            for input_chunk_start, (chunk, flags) in zip(batch, results):
+                input_chunk_end = input_chunk_start + chunk_size
+                output_chunk_start = output_chunk_end
+                if log is not None:
+                    log.info(f"Impute region accessibility for regions {input_chunk_start}-{input_chunk_end}")
+                keep = np.flatnonzero(flags)
+                names_chunk = region_names[input_chunk_start:input_chunk_end]
+                region_names_to_keep.extend([names_chunk[i] for i in keep])
+                output_chunk_end = output_chunk_start + len(keep)
+                imputed_acc[output_chunk_start:output_chunk_end, :] = chunk[keep]
     finally:
-        check(L.cgs_impute_plan_destroy(plan))
+        for plan in plans:
+            check(L.cgs_impute_plan_destroy(plan))
     imputed_acc = imputed_acc[0:output_chunk_end]
     return imputed_acc, region_names_to_keep
 
@@ -613,10 +713,11 @@ def p_adjust_bh(p):
     """Benjamini-Hochberg correction (diff_features.py:1031-1041)."""
     p = np.asarray(p, dtype=np.float64)
     by_descend = p.argsort()[::-1]
-    by_orig = by_descend.argsort()
     steps = float(len(p)) / np.arange(len(p), 0, -1)
     q = np.minimum(1, np.minimum.accumulate(steps * p[by_descend]))
-    return q[by_orig]
+    out = np.empty_like(q)
+    out[by_descend] = q   # == q[by_descend.argsort()]: the inverse of a permutation, without the second sort
+    return out
 
 
 def markers(input_mat, barcode_group, contrast_name, adjpval_thr=0.05, log2fc_thr=1, n_cpu=1, device=0):
@@ -647,12 +748,17 @@ def markers(input_mat, barcode_group, contrast_name, adjpval_thr=0.05, log2fc_th
 
 def _markers_frame(log2_fc, adj_pvalues, contrast_name, features, adjpval_thr, log2fc_thr):
     """The DataFrame, thresholds and ordering of diff_features.py:941-963."""
+    # the two .loc filters of the reference, applied before the frame exists (a frame of every tested region,
+    # with an object column and a string index, costs more than the test itself on the GPU)
+    log2_fc, adj_pvalues = np.asarray(log2_fc), np.asarray(adj_pvalues)
+    with np.errstate(invalid="ignore"):
+        keep = np.flatnonzero((adj_pvalues <= adjpval_thr) & (log2_fc >= log2fc_thr))
+    contrast = pd.Series([contrast_name] * max(1, len(keep)))[: len(keep)]   # keeps the string dtype when empty
     markers_dataframe = pd.DataFrame(
-        {"Log2FC": log2_fc, "Adjusted_pval": adj_pvalues, "Contrast": [contrast_name] * adj_pvalues.shape[0]},
-        index=features,
+        {"Log2FC": log2_fc[keep], "Adjusted_pval": adj_pvalues[keep], "Contrast": contrast.to_numpy()},
+        index=pd.Index([features[i] for i in keep], dtype=pd.Index(list(features[:1]) or [""]).dtype),
     )
-    markers_dataframe = markers_dataframe.loc[markers_dataframe["Adjusted_pval"] <= adjpval_thr]
-    markers_dataframe = markers_dataframe.loc[markers_dataframe["Log2FC"] >= log2fc_thr]
+    markers_dataframe["Contrast"] = markers_dataframe["Contrast"].astype(contrast.dtype)
     return markers_dataframe.sort_values(["Log2FC", "Adjusted_pval"], ascending=[False, True])
 
 

@@ -25,11 +25,17 @@ class Obj:
     cell_data = pd.DataFrame({"celltype": names}, index=cells)
 
 import logging; logging.disable(logging.INFO)
-fact = pdf.FactoredImputedFeatures(a, b, regions, cells, 10 ** 6, 20000, "bench")
+devices = [int(d) for d in os.environ.get("CGS_DEVICES", "0").split(",")]   # regions sharded over these GPUs
+print("devices:", devices, flush=True)
+fact = pdf.FactoredImputedFeatures(a, b, regions, cells, 10 ** 6, 20000, "bench", device=devices)
 fact.ranksum([([0], [1])])  # warm-up (library load, pool)
 t = time.perf_counter(); res_f = pdf.find_diff_features(Obj(), fact, "celltype"); t_f = time.perf_counter() - t
 print(f"factored: find_diff_features {G} one-vs-rest contrasts on {R} x {C} x K={K}: {t_f:.2f} s "
       f"({G * R / t_f:.3e} region-tests/s); markers per contrast: {[len(v) for v in res_f.values()]}", flush=True)
+t = time.perf_counter(); sel = pdf.find_highly_variable_features(pdf.normalize_scores(fact, 10 ** 4, materialize=False), plot=False); t_v = time.perf_counter() - t
+print(f"factored: normalize_scores(materialize=False) -> find_highly_variable_features: {t_v:.2f} s, {len(sel)} features", flush=True)
+if os.environ.get("CGS_FUSED_ONLY"):
+    sys.exit(0)
 t = time.perf_counter(); dense = fact.to_dense(); t_i = time.perf_counter() - t
 t = time.perf_counter(); res_d = pdf.find_diff_features(Obj(), dense, "celltype"); t_d = time.perf_counter() - t
 print(f"dense:    impute_accessibility to host {t_i:.2f} s ({dense.mtx.nbytes / 1e9:.1f} GB) + find_diff_features {t_d:.2f} s", flush=True)
