@@ -421,3 +421,21 @@ def test_variable_feature_selection_matches_reference_golden():
         assert pdf.select_variable_features(mean, var, feats, min_disp=0.5, min_mean=0.05, max_mean=2.0, max_disp=3.0,
                                             n_bins=10) == list(g[f"{name}_window"])
     assert len(g["norm64_default"]) > 100 and len(g["norm64_window"]) > 20
+
+
+def test_cli_flags_mirror_the_reference():
+    """python -m pycistopic_b200 topic_modeling lda: flags, types and defaults of the reference parser
+    (cli/subcommand/topic_modeling.py:171-302); parsing only -- the run itself is a GPU test."""
+    from pycistopic_b200.__main__ import build_parser
+    p = build_parser()
+    a = p.parse_args("topic_modeling lda -i in.pkl -o out.pkl -t 2 5 10 -p 4".split())
+    assert (a.input, a.output, a.topics, a.parallel) == ("in.pkl", "out.pkl", [2, 5, 10], 4)
+    assert (a.iterations, a.alpha, a.alpha_by_topic, a.eta, a.eta_by_topic) == (500, 50, True, 0.1, False)
+    assert (a.keep_intermediate_topic_models, a.seed, a.temp_dir) == (False, 555, None)
+    a = p.parse_args("topic_modeling lda --input i --output o --topics 7 --parallel 1 --iterations 20 --alpha 10 "
+                     "--alpha_by_topic no --eta 0.5 --eta_by_topic TRUE --keep y --seed 3 --temp_dir /tmp/x".split())
+    assert (a.iterations, a.alpha, a.alpha_by_topic, a.eta, a.eta_by_topic) == (20, 10, False, 0.5, True)
+    assert (a.keep_intermediate_topic_models, a.seed, a.temp_dir) == (True, 3, "/tmp/x")
+    for bad in ("topic_modeling lda -i a -o b -t 2", "topic_modeling lda -i a -o b -p 1", "topic_modeling lda -i a -o b -t 2 -p 1 -A maybe"):
+        with pytest.raises(SystemExit):
+            p.parse_args(bad.split())

@@ -64,3 +64,39 @@ def test_config_c1_public_api(tmp_path):
         lazy = pc.find_diff_features(obj, pc.impute_accessibility(obj, materialize=False), "group")
         assert list(dars) == ["first", "other"] and len(dars["first"]) > 0
         assert lazy["first"].index.tolist() == dars["first"].index.tolist()
+
+
+def test_cli_topic_modeling_lda(tmp_path):
+    """``python -m pycistopic_b200 topic_modeling lda`` (reference cli/subcommand/topic_modeling.py:9-66): pickled object
+    in, pickled list of models out, --keep writes Topic<K>.pkl next to it; equals run_cgs_models with the same settings."""
+    import subprocess
+    import sys
+    import pycistopic_b200 as pc
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    m, cells, regions = make_binary_matrix("C1")
+    m, cells = m[:, :120].tocsr(), cells[:120]
+    obj = SyntheticCistopicObject(m, cells, regions)
+    with open(tmp_path / "obj.pkl", "wb") as f:
+        pickle.dump(obj, f)
+    out = tmp_path / "models.pkl"
+    res = subprocess.run([sys.executable, "-m", "pycistopic_b200", "topic_modeling", "lda", "-i", str(tmp_path / "obj.pkl"),
+                          "-o", str(out), "-t", "3", "6", "-p", "1", "-n", "25", "-k", "true", "-s", "7"],
+                         cwd=root, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "Number of iterations:" in res.stdout and "Writing topic modeling output" in res.stdout
+    pc.compat.alias_pycistopic()
+    with open(out, "rb") as f:
+        models = pickle.load(f)
+    want = pc.run_cgs_models(obj, n_topics=[3, 6], n_cpu=1, n_iter=25, random_state=7, alpha=50, alpha_by_topic=True,
+                             eta=0.1, eta_by_topic=False, devices=[0])
+    assert [mm.n_topic for mm in models] == [3, 6]
+    for got, ref in zip(models, want):   # two runs of a sampler with live counts: statistically, not bit-wise, equal
+        assert got.topic_region.shape == ref.topic_region.shape and got.cell_topic.shape == ref.cell_topic.shape
+        assert got.topic_region.index.equals(ref.topic_region.index) and got.cell_topic.columns.equals(ref.cell_topic.columns)
+        assert got.topic_ass["Assignments"].sum() == m.nnz
+        assert got.parameters.loc["random_state", "Parameter"] == 7 and got.parameters.loc["n_iter", "Parameter"] == 25
+        ll_got, ll_ref = got.metrics["loglikelihood"].iloc[0], ref.metrics["loglikelihood"].iloc[0]
+        assert abs(ll_got - ll_ref) <= 0.01 * abs(ll_ref)
+    for K in (3, 6):
+        with open(tmp_path / "models" / f"Topic{K}.pkl", "rb") as f:
+            assert pickle.load(f).n_topic == K
