@@ -84,7 +84,8 @@ def test_cli_topic_modeling_lda(tmp_path):
                          cwd=root, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "Number of iterations:" in res.stdout and "Writing topic modeling output" in res.stdout
-    pc.compat.alias_pycistopic()
+    from pycistopic_b200 import compat
+    compat.alias_pycistopic()
     with open(out, "rb") as f:
         models = pickle.load(f)
     want = pc.run_cgs_models(obj, n_topics=[3, 6], n_cpu=1, n_iter=25, random_state=7, alpha=50, alpha_by_topic=True,
