@@ -315,6 +315,14 @@ int cgs_impute_rankings(int device, const float *topic_region, const float *cell
  * host sum between the threads of one process) -- and pass the sum to the _shard variants below.  make_rankings
  * shards by CELLS instead: cgs_impute_rankings on cell_topic[:, c0:c1] with first_cell = c0 and out + c0, ld_out =
  * total number of cells (the tie order is keyed by the global cell index). */
+/* The imputed matrix itself (diff_features.py:443-486) for a range of regions, written straight to its final place:
+ * rows with keep[r] != 0 (all rows when keep == NULL) are copied, in order and without gaps, to out (n_cells values of
+ * 4 bytes per row: int32 when as_int32 != 0, else float32); *n_written = rows written.  The row filter of
+ * impute_accessibility (:468-486) is keep = row_nonzero of a first pass (cgs_impute_column_totals), so that the host
+ * never holds a chunk it then has to compact.  Product of chunk i + 1 overlaps the copy of chunk i. */
+int cgs_impute_rows(int device, const float *topic_region, const float *cell_topic, int32_t n_regions, int32_t n_topics,
+                    int32_t n_cells, float impute_scale, int as_int32, int32_t chunk_rows, const uint8_t *keep, void *out,
+                    int64_t *n_written);
 int cgs_impute_column_totals(int device, const float *topic_region, const float *cell_topic, int32_t n_regions,
                              int32_t n_topics, int32_t n_cells, float impute_scale, int as_int32, int32_t chunk_rows,
                              void *column_totals, uint8_t *row_nonzero);

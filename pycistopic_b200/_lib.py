@@ -117,6 +117,8 @@ SIGNATURES = {
     "cgs_impute_rankings": (ctypes.c_int, [ctypes.c_int, c_f32p, c_f32p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                            ctypes.c_float, ctypes.c_int, ctypes.c_uint64, ctypes.c_int32, ctypes.c_int64,
                                            c_vp, ctypes.c_int64]),
+    "cgs_impute_rows": (ctypes.c_int, [ctypes.c_int, c_f32p, c_f32p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                       ctypes.c_float, ctypes.c_int, ctypes.c_int32, c_u8p, c_vp, c_i64p]),
     "cgs_impute_column_totals": (ctypes.c_int, [ctypes.c_int, c_f32p, c_f32p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                                 ctypes.c_float, ctypes.c_int, ctypes.c_int32, c_vp, c_u8p]),
     "cgs_impute_normalized_shard": (ctypes.c_int, [ctypes.c_int, c_f32p, c_f32p, ctypes.c_int32, ctypes.c_int32,

@@ -1900,6 +1900,75 @@ int cgs_impute_normalized_shard(int device, const float *topic_region, const flo
                                   norm_scale, chunk_rows, out, row_nonzero, nullptr, column_totals, n_kept);
 }
 
+int cgs_impute_rows(int device, const float *topic_region, const float *cell_topic, int32_t n_regions, int32_t n_topics,
+                    int32_t n_cells, float impute_scale, int as_int32, int32_t chunk_rows, const uint8_t *keep, void *out,
+                    int64_t *n_written) {
+    if (!topic_region || !cell_topic || !out) CGS_FAIL("NULL argument");
+    if (n_regions <= 0 || n_topics <= 0 || n_cells <= 0) CGS_FAIL("empty operand");
+    DeviceGuard g(device);
+    if (!g.ok) CGS_FAIL("cannot select CUDA device");
+    CGS_TRY(configure_pool(device));
+    ImputeStream is;
+    uint8_t *d_chunk2 = nullptr;  // second product buffer: chunk i + 1 is computed while chunk i travels to the host
+    cudaEvent_t copied[2] = {nullptr, nullptr};
+    const size_t row_bytes = (size_t)n_cells * 4;
+    int64_t written = 0;
+    int rc = [&]() -> int {
+        CGS_TRY(is.open(device, topic_region, cell_topic, n_regions, n_topics, n_cells, impute_scale, as_int32, chunk_rows));
+        CGS_TRY(dmalloc(&d_chunk2, (size_t)is.chunk * row_bytes, is.stream));
+        cudaStream_t copy_stream = nullptr;
+        CGS_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+        cudaEvent_t computed[2] = {nullptr, nullptr};
+        int rc2 = [&]() -> int {
+            for (int b = 0; b < 2; ++b) {
+                CGS_CUDA(cudaEventCreateWithFlags(&computed[b], cudaEventDisableTiming));
+                CGS_CUDA(cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming));
+            }
+            uint8_t *bufs[2] = {is.d_chunk, d_chunk2};
+            auto compute = [&](int32_t r0, int b) -> int {
+                const int32_t n = std::min(is.chunk, n_regions - r0);
+                CGS_CUDA(cudaStreamWaitEvent(is.stream, copied[b], 0));  // the buffer's previous copy has left
+                CGS_TRY(cgs_impute_plan_chunk_device(is.plan, is.d_a + (size_t)r0 * n_topics, n, impute_scale, as_int32,
+                                                     bufs[b], is.d_flags + r0, is.stream));
+                CGS_CUDA(cudaEventRecord(computed[b], is.stream));
+                return 0;
+            };
+            CGS_TRY(compute(0, 0));
+            int which = 0;
+            for (int32_t r0 = 0; r0 < n_regions; r0 += is.chunk, which ^= 1) {
+                const int32_t n = std::min(is.chunk, n_regions - r0);
+                // launch the next product first: a copy to pageable host memory blocks this thread while it runs
+                if (r0 + is.chunk < n_regions) CGS_TRY(compute(r0 + is.chunk, which ^ 1));
+                CGS_CUDA(cudaStreamWaitEvent(copy_stream, computed[which], 0));
+                for (int32_t i = 0; i < n;) {  // runs of consecutive rows to keep go straight to their final place
+                    if (keep && !keep[(size_t)r0 + i]) { ++i; continue; }
+                    int32_t j = i;
+                    while (j < n && (!keep || keep[(size_t)r0 + j])) ++j;
+                    CGS_CUDA(cudaMemcpyAsync((uint8_t *)out + (size_t)written * row_bytes, bufs[which] + (size_t)i * row_bytes,
+                                             (size_t)(j - i) * row_bytes, cudaMemcpyDeviceToHost, copy_stream));
+                    written += j - i;
+                    i = j;
+                }
+                CGS_CUDA(cudaEventRecord(copied[which], copy_stream));
+            }
+            CGS_CUDA(cudaStreamSynchronize(copy_stream));
+            CGS_CUDA(cudaStreamSynchronize(is.stream));
+            return 0;
+        }();
+        cudaStreamSynchronize(copy_stream);
+        for (int b = 0; b < 2; ++b) {
+            if (computed[b]) cudaEventDestroy(computed[b]);
+            if (copied[b]) cudaEventDestroy(copied[b]);
+        }
+        cudaStreamDestroy(copy_stream);
+        return rc2;
+    }();
+    dfree(d_chunk2, is.stream);
+    is.close();
+    if (n_written) *n_written = written;
+    return rc;
+}
+
 int cgs_impute_column_totals(int device, const float *topic_region, const float *cell_topic, int32_t n_regions,
                              int32_t n_topics, int32_t n_cells, float impute_scale, int as_int32, int32_t chunk_rows,
                              void *column_totals, uint8_t *row_nonzero) {

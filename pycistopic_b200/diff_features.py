@@ -41,6 +41,8 @@ def _shards(n, devices):
 def _run_sharded(fn, shards):
     """``fn(*shard)`` for every shard, one host thread per shard (the library calls release the GIL; every shard
     drives its own device on its own stream); results in shard order."""
+    if not shards:
+        return []
     if len(shards) == 1:
         return [fn(*shards[0])]
     from concurrent.futures import ThreadPoolExecutor
@@ -363,43 +365,36 @@ def calculate_imputed_accessibility(topic_region, cell_topic, region_names, scal
     as_int = isinstance(scale_factor, int) and scale_factor != 1
     out_dtype = np.int32 if as_int else np.float32
     imputed_acc = np.empty((R, C), dtype=out_dtype)
-    region_names_to_keep = []
-    output_chunk_end = 0
     scale = float(np.float32(scale_factor)) if as_int else 1.0
-    devices = _as_devices(device)
-    plans = []
-    try:
-        for dev in devices:  # one plan (cell operand prepared on that device) per GPU
-            plan = c_vp()
-            check(L.cgs_impute_plan_create(ctypes.byref(plan), dev, ptr(cell_topic, c_f32p), 0, K, C, None))
-            plans.append(plan)
+    # Two passes over the (cheap) device product instead of the reference's chunk -> filter -> copy on the host
+    # (:443-486): the first one yields the row filter, the second one writes every kept row straight to its final
+    # place in ``imputed_acc`` (cgs_impute_rows).  Regions are sharded over ``device`` when it is a sequence.
+    shards = _shards(R, _as_devices(device))
+    flags = np.empty(R, np.uint8)
+    totals_dtype = np.int64 if as_int else np.float64
 
-        def impute_chunk(plan, input_chunk_start):
-            a = topic_region[input_chunk_start:input_chunk_start + chunk_size]
-            n = a.shape[0]
-            chunk = np.empty((n, C), dtype=out_dtype)
-            flags = np.empty(n, dtype=np.uint8)
-            check(L.cgs_impute_plan_chunk(plan, ptr(a, c_f32p), n, scale, int(as_int), chunk.ctypes.data_as(c_vp),
-                                          ptr(flags, c_u8p)))
-            return chunk, flags
+    def first_pass(dev, r0, r1):
+        tot = np.empty(C, totals_dtype)
+        check(L.cgs_impute_column_totals(dev, ptr(topic_region[r0:r1], c_f32p), ptr(cell_topic, c_f32p), r1 - r0, K, C, scale,
+                                         int(as_int), int(chunk_size), tot.ctypes.data_as(c_vp), ptr(flags[r0:r1], c_u8p)))
 
-        starts = list(range(0, R, chunk_size))
-        for wave in range(0, len(starts), len(plans)):  # chunks are independent: one per device at a time, kept in order
-            batch = starts[wave:wave + len(plans)]
-            results = _run_sharded(impute_chunk, list(zip(plans, batch)))
-            for input_chunk_start, (chunk, flags) in zip(batch, results):
-                input_chunk_end = input_chunk_start + chunk_size
-                output_chunk_start = output_chunk_end
-                if log is not None:
-                    log.info(f"Impute region accessibility for regions {input_chunk_start}-{input_chunk_end}")
-                keep = np.flatnonzero(flags)
-                names_chunk = region_names[input_chunk_start:input_chunk_end]
-                region_names_to_keep.extend([names_chunk[i] for i in keep])
-                output_chunk_end = output_chunk_start + len(keep)
-                imputed_acc[output_chunk_start:output_chunk_end, :] = chunk[keep]
-    finally:
-        for plan in plans:
-            check(L.cgs_impute_plan_destroy(plan))
+    _run_sharded(first_pass, shards)
+    first = np.concatenate([[0], np.cumsum(flags, dtype=np.int64)])   # kept regions before every region
+
+    def second_pass(dev, r0, r1):
+        if log is not None:
+            log.info(f"Impute region accessibility for regions {r0}-{r1}")
+        written = ctypes.c_int64()
+        check(L.cgs_impute_rows(dev, ptr(topic_region[r0:r1], c_f32p), ptr(cell_topic, c_f32p), r1 - r0, K, C, scale,
+                                int(as_int), int(chunk_size), ptr(flags[r0:r1], c_u8p),
+                                imputed_acc[first[r0]:].ctypes.data_as(c_vp), ctypes.byref(written)))
+        if written.value != first[r1] - first[r0]:
+            raise RuntimeError("row filter changed between the two passes")
+
+    if first[-1]:
+        _run_sharded(second_pass, shards)
+    output_chunk_end = int(first[-1])
+    region_names_to_keep = [region_names[i] for i in np.flatnonzero(flags)]
     imputed_acc = imputed_acc[0:output_chunk_end]
     return imputed_acc, region_names_to_keep
 
