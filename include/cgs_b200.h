@@ -275,6 +275,15 @@ int cgs_ranksum_rows_device(int device, int dtype, int64_t n_rows,
                             const void *d_bg, int64_t ld_bg, const int32_t *d_bg_cols, int32_t n_bg,
                             double *d_statistic, double *d_pvalue, double *d_log2fc, void *stream);
 
+/* markers() of n_contrasts contrasts on ONE host matrix (find_diff_features, diff_features.py:716-836, calls markers()
+ * once per contrast on the same imputed matrix): x (n_rows x ld, row-major, host) is uploaded once, in rounds, and
+ * every contrast tests a round while it is on the device.  Contrast k compares the columns
+ * fg_cols[fg_offsets[k] .. fg_offsets[k+1]) with bg_cols[bg_offsets[k] .. bg_offsets[k+1]); statistic / pvalue /
+ * log2fc are float64 [n_contrasts x n_rows] (cgs_ranksum_rows semantics). */
+int cgs_ranksum_contrasts(int device, int dtype, int64_t n_rows, const void *x, int64_t ld, int32_t n_contrasts,
+                          const int32_t *fg_cols, const int64_t *fg_offsets, const int32_t *bg_cols,
+                          const int64_t *bg_offsets, double *statistic, double *pvalue, double *log2fc);
+
 /* ---- fused consumers of the imputed matrix -----------------------------
  * impute_accessibility returns a dense regions x cells matrix (diff_features.py:434-441, :503) that normalize_scores
  * (:511-574) and find_diff_features (:716-836) then read back.  These entry points take the two FACTORS instead

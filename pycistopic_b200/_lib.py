@@ -96,6 +96,8 @@ SIGNATURES = {
     "cgs_ranksum_rows_device": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int64, c_vp, ctypes.c_int64, c_vp,
                                                ctypes.c_int32, c_vp, ctypes.c_int64, c_vp, ctypes.c_int32,
                                                c_vp, c_vp, c_vp, c_vp]),
+    "cgs_ranksum_contrasts": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int64, c_vp, ctypes.c_int64, ctypes.c_int32,
+                                             c_i32p, c_i64p, c_i32p, c_i64p, c_f64p, c_f64p, c_f64p]),
     "cgs_impute_normalized": (ctypes.c_int, [ctypes.c_int, c_f32p, c_f32p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                              ctypes.c_float, ctypes.c_int, ctypes.c_double, ctypes.c_int32, c_vp, c_u8p,
                                              c_vp, c_i64p]),

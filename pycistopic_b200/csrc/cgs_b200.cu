@@ -7,6 +7,7 @@
 #include <chrono>
 #include <cmath>
 #include <numeric>
+#include <thread>
 #include <type_traits>
 #include <vector>
 
@@ -1775,6 +1776,131 @@ int cgs_ranksum_rows(int device, int dtype, int64_t n_rows,
 // device (a 20 000 x 200 000 chunk costs 4 ms) and consumed there, so the regions x cells matrix -- 800 GB at atlas
 // scale -- never exists, neither in HBM nor on the host.
 namespace cgs {
+// Device -> pageable host memory at more than the few GB/s a plain cudaMemcpy gives there (its staging copy and the
+// first-touch page faults of a fresh result array run on ONE host thread): the data is DMA'd into two pinned staging
+// buffers in turn and a handful of host threads copy each buffer to its destination while the other one fills.
+// copy() is ordered after everything already enqueued on `after` (an event is taken from it); finish() drains.
+struct HostSink {
+    static constexpr size_t kStage = (size_t)64 << 20;
+    static constexpr int kThreads = 8;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    uint8_t *stage[2] = {nullptr, nullptr};
+    cudaEvent_t landed[2] = {nullptr, nullptr};
+    cudaEvent_t src_read[2] = {nullptr, nullptr};
+    cudaEvent_t ready = nullptr;
+    std::thread mover[2];
+    int next = 0;
+
+    int open(int device_) {
+        device = device_;
+        CGS_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        CGS_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+        for (int b = 0; b < 2; ++b) {
+            CGS_CUDA(cudaHostAlloc((void **)&stage[b], kStage, cudaHostAllocDefault));
+            CGS_CUDA(cudaEventCreateWithFlags(&landed[b], cudaEventDisableTiming));
+            CGS_CUDA(cudaEventCreateWithFlags(&src_read[b], cudaEventDisableTiming));
+        }
+        return 0;
+    }
+    // dst[0, bytes) = d_src[0, bytes); d_src must stay untouched until finish() or wait_sources()
+    int copy(void *dst, const void *d_src, size_t bytes, cudaStream_t after) {
+        CGS_CUDA(cudaEventRecord(ready, after));
+        CGS_CUDA(cudaStreamWaitEvent(stream, ready, 0));
+        for (size_t off = 0; off < bytes; off += kStage) {
+            const size_t n = std::min(kStage, bytes - off);
+            const int b = next;
+            next ^= 1;
+            if (mover[b].joinable()) mover[b].join();  // the buffer's previous contents have reached the host array
+            CGS_CUDA(cudaMemcpyAsync(stage[b], (const uint8_t *)d_src + off, n, cudaMemcpyDeviceToHost, stream));
+            CGS_CUDA(cudaEventRecord(landed[b], stream));
+            uint8_t *to = (uint8_t *)dst + off;
+            const uint8_t *from = stage[b];
+            cudaEvent_t ev = landed[b];
+            const int dev = device;
+            mover[b] = std::thread([=]() {
+                cudaSetDevice(dev);
+                cudaEventSynchronize(ev);
+                const size_t per = ((n + kThreads - 1) / kThreads + 4095) & ~(size_t)4095;
+                std::thread workers[kThreads];
+                int started = 0;
+                for (size_t o = 0; o < n; o += per) workers[started++] = std::thread([=]() { memcpy(to + o, from + o, std::min(per, n - o)); });
+                for (int t = 0; t < started; ++t) workers[t].join();
+            });
+        }
+        return 0;
+    }
+    // Source buffers are recycled by slot (0 / 1): mark_sources(slot) after the copies out of a buffer were issued,
+    // wait_sources(slot, s) before stream `s` overwrites that buffer (no-op until the slot was marked).
+    int mark_sources(int slot) {
+        CGS_CUDA(cudaEventRecord(src_read[slot], stream));
+        return 0;
+    }
+    int wait_sources(int slot, cudaStream_t s) {
+        CGS_CUDA(cudaStreamWaitEvent(s, src_read[slot], 0));
+        return 0;
+    }
+    void finish() {
+        for (int b = 0; b < 2; ++b)
+            if (mover[b].joinable()) mover[b].join();
+    }
+    void close() {
+        finish();
+        for (int b = 0; b < 2; ++b) {
+            if (stage[b]) cudaFreeHost(stage[b]);
+            if (landed[b]) cudaEventDestroy(landed[b]);
+            if (src_read[b]) cudaEventDestroy(src_read[b]);
+            stage[b] = nullptr; landed[b] = nullptr; src_read[b] = nullptr;
+        }
+        if (ready) cudaEventDestroy(ready);
+        if (stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); }
+        ready = nullptr; stream = nullptr;
+    }
+};
+
+// Pageable host memory -> device, the mirror image: host threads fill one pinned staging buffer while the other one
+// is DMA'd.  copy() returns when the last piece has been ENQUEUED on `stream` (the caller's stream).
+struct HostSource {
+    static constexpr size_t kStage = (size_t)64 << 20;
+    static constexpr int kThreads = 8;
+    uint8_t *stage[2] = {nullptr, nullptr};
+    cudaEvent_t sent[2] = {nullptr, nullptr};
+    int next = 0;
+
+    int open() {
+        for (int b = 0; b < 2; ++b) {
+            CGS_CUDA(cudaHostAlloc((void **)&stage[b], kStage, cudaHostAllocDefault));
+            CGS_CUDA(cudaEventCreateWithFlags(&sent[b], cudaEventDisableTiming));
+        }
+        return 0;
+    }
+    int copy(void *d_dst, const void *src, size_t bytes, cudaStream_t stream) {
+        for (size_t off = 0; off < bytes; off += kStage) {
+            const size_t n = std::min(kStage, bytes - off);
+            const int b = next;
+            next ^= 1;
+            CGS_CUDA(cudaEventSynchronize(sent[b]));  // the buffer's previous DMA has left (no-op the first time)
+            const uint8_t *from = (const uint8_t *)src + off;
+            uint8_t *to = stage[b];
+            const size_t per = ((n + kThreads - 1) / kThreads + 4095) & ~(size_t)4095;
+            std::thread workers[kThreads];
+            int started = 0;
+            for (size_t o = 0; o < n; o += per) workers[started++] = std::thread([=]() { memcpy(to + o, from + o, std::min(per, n - o)); });
+            for (int t = 0; t < started; ++t) workers[t].join();
+            CGS_CUDA(cudaMemcpyAsync((uint8_t *)d_dst + off, stage[b], n, cudaMemcpyHostToDevice, stream));
+            CGS_CUDA(cudaEventRecord(sent[b], stream));
+        }
+        return 0;
+    }
+    void close() {
+        for (int b = 0; b < 2; ++b) {
+            if (sent[b]) { cudaEventSynchronize(sent[b]); cudaEventDestroy(sent[b]); }
+            if (stage[b]) cudaFreeHost(stage[b]);
+            stage[b] = nullptr; sent[b] = nullptr;
+        }
+    }
+};
+
 struct ImputeStream {
     cgs_impute_plan *plan = nullptr;
     cudaStream_t stream = nullptr;
@@ -1826,13 +1952,16 @@ static int impute_normalized_impl(int device, const float *topic_region, const f
     if (!g.ok) CGS_FAIL("cannot select CUDA device");
     CGS_TRY(configure_pool(device));
     ImputeStream is;
-    uint8_t *d_norm = nullptr, *d_tot = nullptr;
+    uint8_t *d_norm[2] = {nullptr, nullptr}, *d_tot = nullptr;  // two normalised chunks: one computes while one leaves
+    HostSink sink;
     const size_t out_elem = as_int32 ? 8 : 4;
     const int64_t C = n_cells;
     std::vector<uint8_t> flags((size_t)n_regions);
     int rc = [&]() -> int {
         CGS_TRY(is.open(device, topic_region, cell_topic, n_regions, n_topics, n_cells, impute_scale, as_int32, chunk_rows));
-        CGS_TRY(dmalloc(&d_norm, (size_t)is.chunk * C * out_elem, is.stream));
+        CGS_TRY(sink.open(device));
+        CGS_TRY(dmalloc(&d_norm[0], (size_t)is.chunk * C * out_elem, is.stream));
+        CGS_TRY(dmalloc(&d_norm[1], (size_t)is.chunk * C * out_elem, is.stream));
         CGS_TRY(dmalloc(&d_tot, (size_t)C * 8, is.stream));
         CGS_CUDA(cudaMemsetAsync(d_tot, 0, (size_t)C * 8, is.stream));
         // pass 1: per-cell totals over every region (all-zero regions add nothing) and the row flags
@@ -1851,33 +1980,38 @@ static int impute_normalized_impl(int device, const float *topic_region, const f
         CGS_CUDA(cudaStreamSynchronize(is.stream));
         // pass 2: recompute, normalise, and hand back only the regions that have a non-zero entry
         int64_t kept = 0;
-        for (int32_t r0 = 0; r0 < n_regions; r0 += is.chunk) {
+        int which = 0;
+        for (int32_t r0 = 0; r0 < n_regions; r0 += is.chunk, which ^= 1) {
             const int32_t n = std::min(is.chunk, n_regions - r0);
             CGS_TRY(is.run(r0, n));
+            CGS_TRY(sink.wait_sources(which, is.stream));  // the chunk before the previous one has left d_norm[which]
             dim3 grid((unsigned)ceil_div(C, kNormCols), (unsigned)ceil_div(n, kNormSlab));
             if (as_int32)
                 normalize_log1p_kernel<int32_t, double><<<grid, kNormCols, 0, is.stream>>>(
-                    (const int32_t *)is.d_chunk, n, C, (const long long *)d_tot, norm_scale, (double *)d_norm);
+                    (const int32_t *)is.d_chunk, n, C, (const long long *)d_tot, norm_scale, (double *)d_norm[which]);
             else
                 normalize_log1p_kernel<float, float><<<grid, kNormCols, 0, is.stream>>>(
-                    (const float *)is.d_chunk, n, C, (const double *)d_tot, norm_scale, (float *)d_norm);
+                    (const float *)is.d_chunk, n, C, (const double *)d_tot, norm_scale, (float *)d_norm[which]);
             CGS_CUDA(cudaGetLastError());
             for (int32_t i = 0; i < n;) {  // runs of consecutive kept rows
                 if (!flags[(size_t)r0 + i]) { ++i; continue; }
                 int32_t j = i;
                 while (j < n && flags[(size_t)r0 + j]) ++j;
-                CGS_CUDA(cudaMemcpyAsync((uint8_t *)out + (size_t)kept * C * out_elem, d_norm + (size_t)i * C * out_elem,
-                                         (size_t)(j - i) * C * out_elem, cudaMemcpyDeviceToHost, is.stream));
+                CGS_TRY(sink.copy((uint8_t *)out + (size_t)kept * C * out_elem, d_norm[which] + (size_t)i * C * out_elem,
+                                  (size_t)(j - i) * C * out_elem, is.stream));
                 kept += j - i;
                 i = j;
             }
-            CGS_CUDA(cudaStreamSynchronize(is.stream));
+            CGS_TRY(sink.mark_sources(which));
         }
+        sink.finish();
+        CGS_CUDA(cudaStreamSynchronize(is.stream));
         *n_kept = kept;
         if (row_nonzero) memcpy(row_nonzero, flags.data(), (size_t)n_regions);
         return 0;
     }();
-    dfree(d_norm, is.stream); dfree(d_tot, is.stream);
+    sink.close();
+    dfree(d_norm[0], is.stream); dfree(d_norm[1], is.stream); dfree(d_tot, is.stream);
     is.close();
     return rc;
 }
@@ -1909,60 +2043,37 @@ int cgs_impute_rows(int device, const float *topic_region, const float *cell_top
     if (!g.ok) CGS_FAIL("cannot select CUDA device");
     CGS_TRY(configure_pool(device));
     ImputeStream is;
+    HostSink sink;
     uint8_t *d_chunk2 = nullptr;  // second product buffer: chunk i + 1 is computed while chunk i travels to the host
-    cudaEvent_t copied[2] = {nullptr, nullptr};
     const size_t row_bytes = (size_t)n_cells * 4;
     int64_t written = 0;
     int rc = [&]() -> int {
         CGS_TRY(is.open(device, topic_region, cell_topic, n_regions, n_topics, n_cells, impute_scale, as_int32, chunk_rows));
+        CGS_TRY(sink.open(device));
         CGS_TRY(dmalloc(&d_chunk2, (size_t)is.chunk * row_bytes, is.stream));
-        cudaStream_t copy_stream = nullptr;
-        CGS_CUDA(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
-        cudaEvent_t computed[2] = {nullptr, nullptr};
-        int rc2 = [&]() -> int {
-            for (int b = 0; b < 2; ++b) {
-                CGS_CUDA(cudaEventCreateWithFlags(&computed[b], cudaEventDisableTiming));
-                CGS_CUDA(cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming));
+        uint8_t *bufs[2] = {is.d_chunk, d_chunk2};
+        int which = 0;
+        for (int32_t r0 = 0; r0 < n_regions; r0 += is.chunk, which ^= 1) {
+            const int32_t n = std::min(is.chunk, n_regions - r0);
+            CGS_TRY(sink.wait_sources(which, is.stream));  // the chunk before the previous one has left this buffer
+            CGS_TRY(cgs_impute_plan_chunk_device(is.plan, is.d_a + (size_t)r0 * n_topics, n, impute_scale, as_int32,
+                                                 bufs[which], is.d_flags + r0, is.stream));
+            for (int32_t i = 0; i < n;) {  // runs of consecutive rows to keep go straight to their final place
+                if (keep && !keep[(size_t)r0 + i]) { ++i; continue; }
+                int32_t j = i;
+                while (j < n && (!keep || keep[(size_t)r0 + j])) ++j;
+                CGS_TRY(sink.copy((uint8_t *)out + (size_t)written * row_bytes, bufs[which] + (size_t)i * row_bytes,
+                                  (size_t)(j - i) * row_bytes, is.stream));
+                written += j - i;
+                i = j;
             }
-            uint8_t *bufs[2] = {is.d_chunk, d_chunk2};
-            auto compute = [&](int32_t r0, int b) -> int {
-                const int32_t n = std::min(is.chunk, n_regions - r0);
-                CGS_CUDA(cudaStreamWaitEvent(is.stream, copied[b], 0));  // the buffer's previous copy has left
-                CGS_TRY(cgs_impute_plan_chunk_device(is.plan, is.d_a + (size_t)r0 * n_topics, n, impute_scale, as_int32,
-                                                     bufs[b], is.d_flags + r0, is.stream));
-                CGS_CUDA(cudaEventRecord(computed[b], is.stream));
-                return 0;
-            };
-            CGS_TRY(compute(0, 0));
-            int which = 0;
-            for (int32_t r0 = 0; r0 < n_regions; r0 += is.chunk, which ^= 1) {
-                const int32_t n = std::min(is.chunk, n_regions - r0);
-                // launch the next product first: a copy to pageable host memory blocks this thread while it runs
-                if (r0 + is.chunk < n_regions) CGS_TRY(compute(r0 + is.chunk, which ^ 1));
-                CGS_CUDA(cudaStreamWaitEvent(copy_stream, computed[which], 0));
-                for (int32_t i = 0; i < n;) {  // runs of consecutive rows to keep go straight to their final place
-                    if (keep && !keep[(size_t)r0 + i]) { ++i; continue; }
-                    int32_t j = i;
-                    while (j < n && (!keep || keep[(size_t)r0 + j])) ++j;
-                    CGS_CUDA(cudaMemcpyAsync((uint8_t *)out + (size_t)written * row_bytes, bufs[which] + (size_t)i * row_bytes,
-                                             (size_t)(j - i) * row_bytes, cudaMemcpyDeviceToHost, copy_stream));
-                    written += j - i;
-                    i = j;
-                }
-                CGS_CUDA(cudaEventRecord(copied[which], copy_stream));
-            }
-            CGS_CUDA(cudaStreamSynchronize(copy_stream));
-            CGS_CUDA(cudaStreamSynchronize(is.stream));
-            return 0;
-        }();
-        cudaStreamSynchronize(copy_stream);
-        for (int b = 0; b < 2; ++b) {
-            if (computed[b]) cudaEventDestroy(computed[b]);
-            if (copied[b]) cudaEventDestroy(copied[b]);
+            CGS_TRY(sink.mark_sources(which));
         }
-        cudaStreamDestroy(copy_stream);
-        return rc2;
+        sink.finish();
+        CGS_CUDA(cudaStreamSynchronize(is.stream));
+        return 0;
     }();
+    sink.close();
     dfree(d_chunk2, is.stream);
     is.close();
     if (n_written) *n_written = written;
@@ -2064,6 +2175,98 @@ int cgs_impute_ranksum(int device, const float *topic_region, const float *cell_
     return rc;
 }
 
+
+
+int cgs_ranksum_contrasts(int device, int dtype, int64_t n_rows, const void *x, int64_t ld, int32_t n_contrasts,
+                          const int32_t *fg_cols, const int64_t *fg_offsets, const int32_t *bg_cols,
+                          const int64_t *bg_offsets, double *statistic, double *pvalue, double *log2fc) {
+    if (!x || !fg_cols || !fg_offsets || !bg_cols || !bg_offsets || !statistic || !pvalue || !log2fc) CGS_FAIL("NULL argument");
+    if (dtype < 0 || dtype > 2) CGS_FAIL("dtype must be 0 (int32), 1 (float32) or 2 (float64)");
+    if (n_contrasts < 1) CGS_FAIL("need at least one contrast");
+    if (ld < 1) CGS_FAIL("row stride must be positive");
+    if (n_rows <= 0) return 0;
+    for (int32_t k = 0; k < n_contrasts; ++k)
+        if (fg_offsets[k + 1] <= fg_offsets[k] || bg_offsets[k + 1] <= bg_offsets[k])
+            CGS_FAIL("foreground and background need at least one cell each");
+    const int64_t n_fg_all = fg_offsets[n_contrasts], n_bg_all = bg_offsets[n_contrasts];
+    for (int64_t i = 0; i < n_fg_all; ++i)
+        if (fg_cols[i] < 0 || fg_cols[i] >= ld) CGS_FAIL("foreground column index out of bounds");
+    for (int64_t i = 0; i < n_bg_all; ++i)
+        if (bg_cols[i] < 0 || bg_cols[i] >= ld) CGS_FAIL("background column index out of bounds");
+    DeviceGuard g(device);
+    if (!g.ok) CGS_FAIL("cannot select CUDA device");
+    CGS_TRY(configure_pool(device));
+    int sms = kNumSMsFallback;
+    CGS_TRY(query_sms(device, &sms));
+    const size_t elem = dtype == 2 ? 8 : 4;
+    // rows per round: about 1 GiB of matrix, two buffers: round i + 1 uploads while round i is tested
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(n_rows, ((int64_t)1 << 30) / std::max<int64_t>(1, (int64_t)elem * ld)));
+    cudaStream_t stream = nullptr, up = nullptr;
+    CGS_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    CGS_CUDA(cudaStreamCreateWithFlags(&up, cudaStreamNonBlocking));
+    HostSource source;
+    uint8_t *d_x[2] = {nullptr, nullptr};
+    int32_t *d_fg = nullptr, *d_bg = nullptr;
+    double *d_res = nullptr;  // [3][n_contrasts][chunk]
+    cudaEvent_t uploaded[2] = {nullptr, nullptr}, tested[2] = {nullptr, nullptr};
+    int rc = [&]() -> int {
+        CGS_TRY(source.open());
+        for (int b = 0; b < 2; ++b) {
+            CGS_TRY(dmalloc(&d_x[b], (size_t)chunk * ld * elem, stream));
+            CGS_CUDA(cudaEventCreateWithFlags(&uploaded[b], cudaEventDisableTiming));
+            CGS_CUDA(cudaEventCreateWithFlags(&tested[b], cudaEventDisableTiming));
+        }
+        CGS_TRY(dmalloc(&d_fg, (size_t)n_fg_all, stream));
+        CGS_TRY(dmalloc(&d_bg, (size_t)n_bg_all, stream));
+        CGS_TRY(dmalloc(&d_res, (size_t)3 * n_contrasts * chunk, stream));
+        CGS_CUDA(cudaMemcpyAsync(d_fg, fg_cols, sizeof(int32_t) * (size_t)n_fg_all, cudaMemcpyHostToDevice, stream));
+        CGS_CUDA(cudaMemcpyAsync(d_bg, bg_cols, sizeof(int32_t) * (size_t)n_bg_all, cudaMemcpyHostToDevice, stream));
+        CGS_CUDA(cudaStreamSynchronize(stream));  // the buffers exist before the upload stream touches them
+        auto upload = [&](int64_t r0, int b) -> int {
+            const int64_t nr = std::min(chunk, n_rows - r0);
+            CGS_CUDA(cudaStreamWaitEvent(up, tested[b], 0));  // the round that used this buffer is done with it
+            CGS_TRY(source.copy(d_x[b], (const uint8_t *)x + (size_t)r0 * ld * elem, (size_t)nr * ld * elem, up));
+            CGS_CUDA(cudaEventRecord(uploaded[b], up));
+            return 0;
+        };
+        CGS_TRY(upload(0, 0));
+        int which = 0;
+        const size_t plane = (size_t)n_contrasts * chunk;
+        for (int64_t r0 = 0; r0 < n_rows; r0 += chunk, which ^= 1) {
+            const int64_t nr = std::min(chunk, n_rows - r0);
+            CGS_CUDA(cudaStreamWaitEvent(stream, uploaded[which], 0));
+            for (int32_t k = 0; k < n_contrasts; ++k) {  // every contrast reads the round while it is in HBM / L2
+                RankSide fg{d_x[which], ld, d_fg + fg_offsets[k], (int32_t)(fg_offsets[k + 1] - fg_offsets[k])};
+                RankSide bg{d_x[which], ld, d_bg + bg_offsets[k], (int32_t)(bg_offsets[k + 1] - bg_offsets[k])};
+                double *base = d_res + (size_t)k * chunk;
+                CGS_TRY(ranksum_launch(dtype, fg, bg, nr, base, base + plane, base + 2 * plane, stream, sms));
+            }
+            CGS_CUDA(cudaEventRecord(tested[which], stream));
+            if (r0 + chunk < n_rows) CGS_TRY(upload(r0 + chunk, which ^ 1));  // overlaps the tests just launched
+            for (int32_t k = 0; k < n_contrasts; ++k) {
+                const double *base = d_res + (size_t)k * chunk;
+                const size_t o = (size_t)k * n_rows + r0;
+                CGS_CUDA(cudaMemcpyAsync(statistic + o, base, sizeof(double) * nr, cudaMemcpyDeviceToHost, stream));
+                CGS_CUDA(cudaMemcpyAsync(pvalue + o, base + plane, sizeof(double) * nr, cudaMemcpyDeviceToHost, stream));
+                CGS_CUDA(cudaMemcpyAsync(log2fc + o, base + 2 * plane, sizeof(double) * nr, cudaMemcpyDeviceToHost, stream));
+            }
+            CGS_CUDA(cudaStreamSynchronize(stream));  // d_res is reused by the next round
+        }
+        CGS_CUDA(cudaStreamSynchronize(up));
+        return 0;
+    }();
+    cudaStreamSynchronize(up); cudaStreamSynchronize(stream);
+    source.close();
+    for (int b = 0; b < 2; ++b) {
+        dfree(d_x[b], stream);
+        if (uploaded[b]) cudaEventDestroy(uploaded[b]);
+        if (tested[b]) cudaEventDestroy(tested[b]);
+    }
+    dfree(d_fg, stream); dfree(d_bg, stream); dfree(d_res, stream);
+    cudaStreamSynchronize(stream);
+    cudaStreamDestroy(up); cudaStreamDestroy(stream);
+    return rc;
+}
 
 }  // extern "C"
 

@@ -693,6 +693,40 @@ def ranksum_rows(fg_mat, bg_mat=None, fg_cols=None, bg_cols=None, device=0):
     return stat, pval, l2fc
 
 
+def ranksum_contrasts(matrix, contrasts_cols, device=0):
+    """``ranksum_rows(matrix, None, fg, bg)`` for every ``(fg column indices, bg column indices)`` pair, with ONE upload
+    of the matrix (``cgs_ranksum_contrasts``): ``(statistic, pvalue, log2fc)``, each ``n_contrasts x n_rows`` float64;
+    a contrast with an empty group gives NaN, as scipy / NumPy do."""
+    _lib.require_device()
+    x = _rank_matrix(matrix)
+    R, C = x.shape
+    n = len(contrasts_cols)
+    stat, pval, l2fc = (np.full((n, R), np.nan) for _ in range(3))
+
+    def pack(groups):
+        offs = np.zeros(len(groups) + 1, np.int64)
+        cols = []
+        for i, g in enumerate(groups):
+            g = np.asarray(g, dtype=np.int64)
+            if g.size and (g.max() >= C or g.min() < -C):
+                raise IndexError(f"index {g.max() if g.max() >= C else g.min()} is out of bounds for axis 1 with size {C}")
+            cols.append(np.sort(np.where(g < 0, g + C, g)).astype(np.int32))
+            offs[i + 1] = offs[i] + g.size
+        return np.ascontiguousarray(np.concatenate(cols) if cols else np.zeros(0, np.int32)), offs
+
+    live = [i for i, (f, b) in enumerate(contrasts_cols) if len(f) and len(b)]
+    if live and R:
+        fg, fo = pack([contrasts_cols[i][0] for i in live])
+        bg, bo = pack([contrasts_cols[i][1] for i in live])
+        s2, p2, l2 = (np.empty((len(live), R), np.float64) for _ in range(3))
+        check(_lib.load().cgs_ranksum_contrasts(device, _RANK_DTYPES[x.dtype], R, x.ctypes.data_as(c_vp), C, len(live),
+                                                ptr(fg, _lib.c_i32p), ptr(fo, _lib.c_i64p), ptr(bg, _lib.c_i32p),
+                                                ptr(bo, _lib.c_i64p), ptr(s2, _lib.c_f64p), ptr(p2, _lib.c_f64p),
+                                                ptr(l2, _lib.c_f64p)))
+        stat[live], pval[live], l2fc[live] = s2, p2, l2
+    return stat, pval, l2fc
+
+
 def get_wilcox_test_pvalues(fg_mat, bg_mat, device=0):
     """Wilcoxon rank-sum p-value of every row of ``fg_mat`` against the same row of ``bg_mat``
     (diff_features.py:968-995: ``scipy.stats.ranksums(fg_mat[i], y=bg_mat[i]).pvalue``), as a list."""
@@ -757,6 +791,23 @@ def _markers_frame(log2_fc, adj_pvalues, contrast_name, features, adjpval_thr, l
     return markers_dataframe.sort_values(["Log2FC", "Adjusted_pval"], ascending=[False, True])
 
 
+def _markers_dense(imputed, barcode_groups, contrast_names, adjpval_thr, log2fc_thr, log, device=0):
+    """markers() of every contrast of find_diff_features on a dense matrix with ONE upload of it (the reference, and
+    a loop over :func:`markers`, hand the whole matrix to every contrast)."""
+    mat, features, samples = imputed.mtx, imputed.feature_names, imputed.cell_names
+    if scipy.sparse.issparse(mat):
+        mat = mat.toarray()
+    cols = [(get_position_index(g[0], samples), get_position_index(g[1], samples)) for g in barcode_groups]
+    for name, (f, _) in zip(contrast_names, cols):
+        log.info(f"Computing p-value and log2FC for {name} ({len(f)} of {len(samples)})")
+    _, pval, l2fc = ranksum_contrasts(mat, cols, device=device)
+    out = []
+    for k, name in enumerate(contrast_names):
+        out.append(_markers_frame(l2fc[k], p_adjust_bh(pval[k]), name, features, adjpval_thr, log2fc_thr))
+        log.info(f"{name} done!")
+    return out
+
+
 def _markers_factored(factored, barcode_groups, contrast_names, adjpval_thr, log2fc_thr, log):
     """markers() of every contrast from ONE pass over the recomputed imputation chunks."""
     samples = factored.cell_names
@@ -795,9 +846,6 @@ def find_diff_features(cistopic_obj, imputed_features_obj, variable, var_feature
         markers_list = _markers_factored(subset_imputed_features_obj, barcode_groups, contrasts_names, adjpval_thr,
                                          log2fc_thr, _logger())
         return {name: marker for name, marker in zip(contrasts_names, markers_list)}
-    markers_list = [
-        markers(subset_imputed_features_obj, barcode_groups[i], contrasts_names[i], adjpval_thr=adjpval_thr,
-                log2fc_thr=log2fc_thr, n_cpu=1, device=device)
-        for i in range(len(contrasts))
-    ]
+    markers_list = _markers_dense(subset_imputed_features_obj, barcode_groups, contrasts_names, adjpval_thr, log2fc_thr,
+                                  _logger(), device=device)
     return {name: marker for name, marker in zip(contrasts_names, markers_list)}

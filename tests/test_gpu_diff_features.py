@@ -246,3 +246,25 @@ def test_factored_consumers_match_dense_path():
     groups = [[x for x, l in zip(cells, labels) if l == "B"], [x for x, l in zip(cells, labels) if l != "B"]]
     md, mf = pdf.markers(dense, groups, "B"), pdf.markers(fact, groups, "B")
     assert mf.index.tolist() == md.index.tolist() and len(md) > 5
+
+
+def test_ranksum_contrasts_one_upload_equals_per_contrast_calls():
+    """cgs_ranksum_contrasts (the dense find_diff_features path: one upload, every contrast on the device) gives what
+    cgs_ranksum_rows gives contrast by contrast -- also across upload rounds (the matrix below is 1.4 GB: two rounds
+    of the double-buffered upload) and for an empty group (NaN)."""
+    from pycistopic_b200 import diff_features as pdf
+    rng = np.random.default_rng(12)
+    for R, C, dtype in ((57, 300, np.float64), (900, 400_000, np.int32)):
+        x = rng.integers(0, 30, (R, C)).astype(dtype)
+        perm = rng.permutation(C)
+        contrasts = [(perm[: C // 10], perm[C // 10:]), (perm[C // 2:], perm[: C // 3]), ([], perm[:5]), (perm[:1], perm[1:3])]
+        stat, pval, l2fc = pdf.ranksum_contrasts(x, contrasts)
+        assert stat.shape == (4, R)
+        for k, (f, b) in enumerate(contrasts):
+            s1, p1, l1 = pdf.ranksum_rows(x, None, f, b)
+            np.testing.assert_array_equal(stat[k], s1)
+            np.testing.assert_array_equal(pval[k], p1)
+            np.testing.assert_array_equal(l2fc[k], l1)
+        assert np.isnan(pval[2]).all()
+    with pytest.raises(IndexError, match="out of bounds"):
+        pdf.ranksum_contrasts(x[:3, :10], [([0, 10], [1])])
