@@ -92,6 +92,195 @@ static int configure_pool(int device) {
     CGS_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
     return 0;
 }
+
+// Device -> pageable host memory at more than the few GB/s a plain cudaMemcpy gives there (its staging copy and the
+// first-touch page faults of a fresh result array run on ONE host thread): the data is DMA'd into two pinned staging
+// buffers in turn and a handful of host threads copy each buffer to its destination while the other one fills.
+// copy() is ordered after everything already enqueued on `after` (an event is taken from it); finish() drains.
+struct HostSink {
+    static constexpr size_t kStage = (size_t)64 << 20;
+    static constexpr int kThreads = 8;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    uint8_t *stage[2] = {nullptr, nullptr};
+    cudaEvent_t landed[2] = {nullptr, nullptr};
+    cudaEvent_t src_read[2] = {nullptr, nullptr};
+    cudaEvent_t ready = nullptr;
+    std::thread mover[2];
+    int next = 0;
+    size_t stage_bytes = kStage;
+
+    // total_bytes: what will travel through the sink (small transfers get small staging buffers: pinning costs time)
+    int open(int device_, size_t total_bytes = (size_t)-1) {
+        device = device_;
+        stage_bytes = std::max<size_t>((size_t)1 << 20, std::min<size_t>(kStage, (total_bytes + 4095) & ~(size_t)4095));
+        CGS_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        CGS_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+        for (int b = 0; b < 2; ++b) {
+            CGS_CUDA(cudaHostAlloc((void **)&stage[b], stage_bytes, cudaHostAllocDefault));
+            CGS_CUDA(cudaEventCreateWithFlags(&landed[b], cudaEventDisableTiming));
+            CGS_CUDA(cudaEventCreateWithFlags(&src_read[b], cudaEventDisableTiming));
+        }
+        return 0;
+    }
+    // dst[0, bytes) = d_src[0, bytes); d_src must stay untouched until finish() or wait_sources()
+    int copy(void *dst, const void *d_src, size_t bytes, cudaStream_t after) {
+        CGS_CUDA(cudaEventRecord(ready, after));
+        CGS_CUDA(cudaStreamWaitEvent(stream, ready, 0));
+        for (size_t off = 0; off < bytes; off += stage_bytes) {
+            const size_t n = std::min(stage_bytes, bytes - off);
+            const int b = next;
+            next ^= 1;
+            if (mover[b].joinable()) mover[b].join();  // the buffer's previous contents have reached the host array
+            CGS_CUDA(cudaMemcpyAsync(stage[b], (const uint8_t *)d_src + off, n, cudaMemcpyDeviceToHost, stream));
+            CGS_CUDA(cudaEventRecord(landed[b], stream));
+            uint8_t *to = (uint8_t *)dst + off;
+            const uint8_t *from = stage[b];
+            cudaEvent_t ev = landed[b];
+            const int dev = device;
+            mover[b] = std::thread([=]() {
+                cudaSetDevice(dev);
+                cudaEventSynchronize(ev);
+                const size_t per = ((n + kThreads - 1) / kThreads + 4095) & ~(size_t)4095;
+                std::thread workers[kThreads];
+                int started = 0;
+                for (size_t o = 0; o < n; o += per) workers[started++] = std::thread([=]() { memcpy(to + o, from + o, std::min(per, n - o)); });
+                for (int t = 0; t < started; ++t) workers[t].join();
+            });
+        }
+        return 0;
+    }
+    // height rows of `width` bytes, contiguous on the device, to rows `dpitch` bytes apart on the host
+    int copy2d(void *dst, size_t dpitch, const void *d_src, size_t width, size_t height, cudaStream_t after) {
+        if (dpitch == width) return copy(dst, d_src, width * height, after);
+        CGS_CUDA(cudaEventRecord(ready, after));
+        CGS_CUDA(cudaStreamWaitEvent(stream, ready, 0));
+        const size_t rows_per = std::max<size_t>(1, stage_bytes / width);
+        if (width > stage_bytes) CGS_FAIL("row wider than the staging buffer");
+        for (size_t r0 = 0; r0 < height; r0 += rows_per) {
+            const size_t nr = std::min(rows_per, height - r0);
+            const int b = next;
+            next ^= 1;
+            if (mover[b].joinable()) mover[b].join();
+            CGS_CUDA(cudaMemcpyAsync(stage[b], (const uint8_t *)d_src + r0 * width, nr * width, cudaMemcpyDeviceToHost, stream));
+            CGS_CUDA(cudaEventRecord(landed[b], stream));
+            uint8_t *to = (uint8_t *)dst + r0 * dpitch;
+            const uint8_t *from = stage[b];
+            cudaEvent_t ev = landed[b];
+            const int dev = device;
+            mover[b] = std::thread([=]() {
+                cudaSetDevice(dev);
+                cudaEventSynchronize(ev);
+                const size_t per = (nr + kThreads - 1) / kThreads;
+                std::thread workers[kThreads];
+                int started = 0;
+                for (size_t o = 0; o < nr; o += per)
+                    workers[started++] = std::thread([=]() {
+                        for (size_t r = o; r < std::min(nr, o + per); ++r) memcpy(to + r * dpitch, from + r * width, width);
+                    });
+                for (int t = 0; t < started; ++t) workers[t].join();
+            });
+        }
+        return 0;
+    }
+    // Source buffers are recycled by slot (0 / 1): mark_sources(slot) after the copies out of a buffer were issued,
+    // wait_sources(slot, s) before stream `s` overwrites that buffer (no-op until the slot was marked).
+    int mark_sources(int slot) {
+        CGS_CUDA(cudaEventRecord(src_read[slot], stream));
+        return 0;
+    }
+    int wait_sources(int slot, cudaStream_t s) {
+        CGS_CUDA(cudaStreamWaitEvent(s, src_read[slot], 0));
+        return 0;
+    }
+    void finish() {
+        for (int b = 0; b < 2; ++b)
+            if (mover[b].joinable()) mover[b].join();
+    }
+    void close() {
+        finish();
+        for (int b = 0; b < 2; ++b) {
+            if (stage[b]) cudaFreeHost(stage[b]);
+            if (landed[b]) cudaEventDestroy(landed[b]);
+            if (src_read[b]) cudaEventDestroy(src_read[b]);
+            stage[b] = nullptr; landed[b] = nullptr; src_read[b] = nullptr;
+        }
+        if (ready) cudaEventDestroy(ready);
+        if (stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); }
+        ready = nullptr; stream = nullptr;
+    }
+};
+
+// Pageable host memory -> device, the mirror image: host threads fill one pinned staging buffer while the other one
+// is DMA'd.  copy() returns when the last piece has been ENQUEUED on `stream` (the caller's stream).
+struct HostSource {
+    static constexpr size_t kStage = (size_t)64 << 20;
+    static constexpr int kThreads = 8;
+    uint8_t *stage[2] = {nullptr, nullptr};
+    cudaEvent_t sent[2] = {nullptr, nullptr};
+    int next = 0;
+    size_t stage_bytes = kStage;
+
+    int open(size_t total_bytes = (size_t)-1) {
+        stage_bytes = std::max<size_t>((size_t)1 << 20, std::min<size_t>(kStage, (total_bytes + 4095) & ~(size_t)4095));
+        for (int b = 0; b < 2; ++b) {
+            CGS_CUDA(cudaHostAlloc((void **)&stage[b], stage_bytes, cudaHostAllocDefault));
+            CGS_CUDA(cudaEventCreateWithFlags(&sent[b], cudaEventDisableTiming));
+        }
+        return 0;
+    }
+    int copy(void *d_dst, const void *src, size_t bytes, cudaStream_t stream) {
+        for (size_t off = 0; off < bytes; off += stage_bytes) {
+            const size_t n = std::min(stage_bytes, bytes - off);
+            const int b = next;
+            next ^= 1;
+            CGS_CUDA(cudaEventSynchronize(sent[b]));  // the buffer's previous DMA has left (no-op the first time)
+            const uint8_t *from = (const uint8_t *)src + off;
+            uint8_t *to = stage[b];
+            const size_t per = ((n + kThreads - 1) / kThreads + 4095) & ~(size_t)4095;
+            std::thread workers[kThreads];
+            int started = 0;
+            for (size_t o = 0; o < n; o += per) workers[started++] = std::thread([=]() { memcpy(to + o, from + o, std::min(per, n - o)); });
+            for (int t = 0; t < started; ++t) workers[t].join();
+            CGS_CUDA(cudaMemcpyAsync((uint8_t *)d_dst + off, stage[b], n, cudaMemcpyHostToDevice, stream));
+            CGS_CUDA(cudaEventRecord(sent[b], stream));
+        }
+        return 0;
+    }
+    // height rows of `width` bytes, `spitch` bytes apart on the host, to contiguous rows on the device
+    int copy2d(void *d_dst, const void *src, size_t spitch, size_t width, size_t height, cudaStream_t stream) {
+        if (spitch == width) return copy(d_dst, src, width * height, stream);
+        if (width > stage_bytes) CGS_FAIL("row wider than the staging buffer");
+        const size_t rows_per = std::max<size_t>(1, stage_bytes / width);
+        for (size_t r0 = 0; r0 < height; r0 += rows_per) {
+            const size_t nr = std::min(rows_per, height - r0);
+            const int b = next;
+            next ^= 1;
+            CGS_CUDA(cudaEventSynchronize(sent[b]));
+            const uint8_t *from = (const uint8_t *)src + r0 * spitch;
+            uint8_t *to = stage[b];
+            const size_t per = (nr + kThreads - 1) / kThreads;
+            std::thread workers[kThreads];
+            int started = 0;
+            for (size_t o = 0; o < nr; o += per)
+                workers[started++] = std::thread([=]() {
+                    for (size_t r = o; r < std::min(nr, o + per); ++r) memcpy(to + r * width, from + r * spitch, width);
+                });
+            for (int t = 0; t < started; ++t) workers[t].join();
+            CGS_CUDA(cudaMemcpyAsync((uint8_t *)d_dst + r0 * width, stage[b], nr * width, cudaMemcpyHostToDevice, stream));
+            CGS_CUDA(cudaEventRecord(sent[b], stream));
+        }
+        return 0;
+    }
+    void close() {
+        for (int b = 0; b < 2; ++b) {
+            if (sent[b]) { cudaEventSynchronize(sent[b]); cudaEventDestroy(sent[b]); }
+            if (stage[b]) cudaFreeHost(stage[b]);
+            stage[b] = nullptr; sent[b] = nullptr;
+        }
+    }
+};
+
 }  // namespace cgs
 
 using namespace cgs;
@@ -1218,18 +1407,24 @@ int cgs_normalize_scores(int device, const void *x, int dtype, int64_t n_rows, i
     const size_t in_elem = dtype == 2 ? 8 : 4, out_elem = dtype == 1 ? 4 : 8;
     const size_t n = (size_t)n_rows * (size_t)n_cols;
     uint8_t *d_x = nullptr, *d_o = nullptr, *d_s = nullptr;
+    HostSource source;
+    HostSink sink;
     cudaStream_t stream = nullptr;
     CGS_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     int rc = [&]() -> int {
         CGS_TRY(dmalloc(&d_x, n * in_elem, stream));
         CGS_TRY(dmalloc(&d_o, n * out_elem, stream));
         CGS_TRY(dmalloc(&d_s, (size_t)n_cols * 8, stream));
-        CGS_CUDA(cudaMemcpyAsync(d_x, x, n * in_elem, cudaMemcpyHostToDevice, stream));
+        CGS_TRY(source.open(n * in_elem));
+        CGS_TRY(sink.open(device, n * out_elem));
+        CGS_TRY(source.copy(d_x, x, n * in_elem, stream));
         CGS_TRY(cgs_normalize_scores_device(device, d_x, dtype, n_rows, n_cols, scale_factor, d_o, d_s, stream));
-        CGS_CUDA(cudaMemcpyAsync(out, d_o, n * out_elem, cudaMemcpyDeviceToHost, stream));
+        CGS_TRY(sink.copy(out, d_o, n * out_elem, stream));
+        sink.finish();
         CGS_CUDA(cudaStreamSynchronize(stream));
         return 0;
     }();
+    source.close(); sink.close();
     dfree(d_x, stream); dfree(d_o, stream); dfree(d_s, stream);
     cudaStreamDestroy(stream);
     return rc;
@@ -1269,9 +1464,11 @@ int cgs_row_mean_var(int device, int dtype, const void *x, int64_t ld, int64_t n
     const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(n_rows, (int64_t)((1LL << 30) / ((size_t)n_cols * elem))));
     uint8_t *d_x[2] = {nullptr, nullptr};
     float *d_m = nullptr, *d_v = nullptr;
+    HostSource source;
     cudaStream_t stream = nullptr;
     CGS_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     int rc = [&]() -> int {
+        CGS_TRY(source.open((size_t)n_rows * n_cols * elem));
         CGS_TRY(dmalloc(&d_x[0], (size_t)chunk * n_cols * elem, stream));
         CGS_TRY(dmalloc(&d_x[1], (size_t)chunk * n_cols * elem, stream));
         CGS_TRY(dmalloc(&d_m, (size_t)n_rows, stream));
@@ -1279,8 +1476,12 @@ int cgs_row_mean_var(int device, int dtype, const void *x, int64_t ld, int64_t n
         int which = 0;
         for (int64_t r0 = 0; r0 < n_rows; r0 += chunk, which ^= 1) {
             const int64_t n = std::min(chunk, n_rows - r0);
-            CGS_CUDA(cudaMemcpy2DAsync(d_x[which], (size_t)n_cols * elem, (const uint8_t *)x + (size_t)r0 * ld * elem,
-                                       (size_t)ld * elem, (size_t)n_cols * elem, (size_t)n, cudaMemcpyHostToDevice, stream));
+            if (ld == n_cols) {
+                CGS_TRY(source.copy(d_x[which], (const uint8_t *)x + (size_t)r0 * ld * elem, (size_t)n * n_cols * elem, stream));
+            } else {
+                CGS_CUDA(cudaMemcpy2DAsync(d_x[which], (size_t)n_cols * elem, (const uint8_t *)x + (size_t)r0 * ld * elem,
+                                           (size_t)ld * elem, (size_t)n_cols * elem, (size_t)n, cudaMemcpyHostToDevice, stream));
+            }
             CGS_TRY(cgs_row_mean_var_device(device, dtype, d_x[which], n_cols, n, n_cols, d_m + r0, d_v + r0, stream));
         }
         CGS_CUDA(cudaMemcpyAsync(mean, d_m, sizeof(float) * (size_t)n_rows, cudaMemcpyDeviceToHost, stream));
@@ -1288,6 +1489,8 @@ int cgs_row_mean_var(int device, int dtype, const void *x, int64_t ld, int64_t n
         CGS_CUDA(cudaStreamSynchronize(stream));
         return 0;
     }();
+    cudaStreamSynchronize(stream);
+    source.close();
     dfree(d_x[0], stream); dfree(d_x[1], stream); dfree(d_m, stream); dfree(d_v, stream);
     cudaStreamSynchronize(stream);
     cudaStreamDestroy(stream);
@@ -1383,22 +1586,28 @@ int cgs_rank_columns(int device, int dtype, const void *x, int64_t ld, int64_t n
     const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(n_cols, std::max<int64_t>(32, (1LL << 29) / n_rows)));
     uint8_t *d_x = nullptr;
     int32_t *d_o = nullptr;
+    HostSource source;
+    HostSink sink;
     cudaStream_t stream = nullptr;
     CGS_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     int rc = [&]() -> int {
+        CGS_TRY(source.open((size_t)n_rows * n_cols * elem));
+        CGS_TRY(sink.open(device, (size_t)n_rows * n_cols * 4));
         CGS_TRY(dmalloc(&d_x, (size_t)n_rows * (size_t)chunk * elem, stream));
         CGS_TRY(dmalloc(&d_o, (size_t)n_rows * (size_t)chunk, stream));
         for (int64_t c0 = 0; c0 < n_cols; c0 += chunk) {
             const int64_t nc = std::min(chunk, n_cols - c0);
-            CGS_CUDA(cudaMemcpy2DAsync(d_x, (size_t)nc * elem, (const uint8_t *)x + (size_t)c0 * elem, (size_t)ld * elem,
-                                       (size_t)nc * elem, (size_t)n_rows, cudaMemcpyHostToDevice, stream));
+            CGS_TRY(source.copy2d(d_x, (const uint8_t *)x + (size_t)c0 * elem, (size_t)ld * elem, (size_t)nc * elem,
+                                  (size_t)n_rows, stream));
             CGS_TRY(cgs_rank_columns_device(device, dtype, d_x, nc, n_rows, nc, seed, first_col + c0, d_o, nc, stream));
-            CGS_CUDA(cudaMemcpy2DAsync(out + c0, (size_t)ld_out * 4, d_o, (size_t)nc * 4, (size_t)nc * 4, (size_t)n_rows,
-                                       cudaMemcpyDeviceToHost, stream));
+            CGS_TRY(sink.copy2d(out + c0, (size_t)ld_out * 4, d_o, (size_t)nc * 4, (size_t)n_rows, stream));
+            sink.finish();
             CGS_CUDA(cudaStreamSynchronize(stream));
         }
         return 0;
     }();
+    cudaStreamSynchronize(stream);
+    source.close(); sink.close();
     dfree(d_x, stream); dfree(d_o, stream);
     cudaStreamSynchronize(stream);
     cudaStreamDestroy(stream);
@@ -1733,7 +1942,9 @@ int cgs_ranksum_rows(int device, int dtype, int64_t n_rows,
     uint8_t *d_a = nullptr, *d_b = nullptr;
     int32_t *d_fc = nullptr, *d_bc = nullptr;
     double *d_out = nullptr;
+    HostSource source;
     int rc = [&]() -> int {
+        CGS_TRY(source.open((size_t)n_rows * ld_fg * elem));
         CGS_TRY(dmalloc(&d_a, (size_t)chunk * ld_fg * elem, stream));
         if (!shared_matrix) CGS_TRY(dmalloc(&d_b, (size_t)chunk * ld_bg * elem, stream));
         CGS_TRY(dmalloc(&d_out, (size_t)chunk * 3, stream));
@@ -1751,11 +1962,9 @@ int cgs_ranksum_rows(int device, int dtype, int64_t n_rows,
         }
         for (int64_t r0 = 0; r0 < n_rows; r0 += chunk) {
             const int64_t nr = std::min(chunk, n_rows - r0);
-            CGS_CUDA(cudaMemcpyAsync(d_a, (const uint8_t *)fg + (size_t)r0 * ld_fg * elem, (size_t)nr * ld_fg * elem,
-                                     cudaMemcpyHostToDevice, stream));
+            CGS_TRY(source.copy(d_a, (const uint8_t *)fg + (size_t)r0 * ld_fg * elem, (size_t)nr * ld_fg * elem, stream));
             if (!shared_matrix)
-                CGS_CUDA(cudaMemcpyAsync(d_b, (const uint8_t *)bg + (size_t)r0 * ld_bg * elem, (size_t)nr * ld_bg * elem,
-                                         cudaMemcpyHostToDevice, stream));
+                CGS_TRY(source.copy(d_b, (const uint8_t *)bg + (size_t)r0 * ld_bg * elem, (size_t)nr * ld_bg * elem, stream));
             CGS_TRY(cgs_ranksum_rows_device(device, dtype, nr, d_a, ld_fg, d_fc, n_fg, shared_matrix ? d_a : d_b, ld_bg, d_bc,
                                             n_bg, d_out, d_out + chunk, d_out + 2 * chunk, stream));
             CGS_CUDA(cudaMemcpyAsync(statistic + r0, d_out, sizeof(double) * (size_t)nr, cudaMemcpyDeviceToHost, stream));
@@ -1765,6 +1974,8 @@ int cgs_ranksum_rows(int device, int dtype, int64_t n_rows,
         }
         return 0;
     }();
+    cudaStreamSynchronize(stream);
+    source.close();
     dfree(d_a, stream); dfree(d_b, stream); dfree(d_out, stream); dfree(d_fc, stream); dfree(d_bc, stream);
     cudaStreamDestroy(stream);
     return rc;
@@ -1776,131 +1987,6 @@ int cgs_ranksum_rows(int device, int dtype, int64_t n_rows,
 // device (a 20 000 x 200 000 chunk costs 4 ms) and consumed there, so the regions x cells matrix -- 800 GB at atlas
 // scale -- never exists, neither in HBM nor on the host.
 namespace cgs {
-// Device -> pageable host memory at more than the few GB/s a plain cudaMemcpy gives there (its staging copy and the
-// first-touch page faults of a fresh result array run on ONE host thread): the data is DMA'd into two pinned staging
-// buffers in turn and a handful of host threads copy each buffer to its destination while the other one fills.
-// copy() is ordered after everything already enqueued on `after` (an event is taken from it); finish() drains.
-struct HostSink {
-    static constexpr size_t kStage = (size_t)64 << 20;
-    static constexpr int kThreads = 8;
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    uint8_t *stage[2] = {nullptr, nullptr};
-    cudaEvent_t landed[2] = {nullptr, nullptr};
-    cudaEvent_t src_read[2] = {nullptr, nullptr};
-    cudaEvent_t ready = nullptr;
-    std::thread mover[2];
-    int next = 0;
-
-    int open(int device_) {
-        device = device_;
-        CGS_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-        CGS_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
-        for (int b = 0; b < 2; ++b) {
-            CGS_CUDA(cudaHostAlloc((void **)&stage[b], kStage, cudaHostAllocDefault));
-            CGS_CUDA(cudaEventCreateWithFlags(&landed[b], cudaEventDisableTiming));
-            CGS_CUDA(cudaEventCreateWithFlags(&src_read[b], cudaEventDisableTiming));
-        }
-        return 0;
-    }
-    // dst[0, bytes) = d_src[0, bytes); d_src must stay untouched until finish() or wait_sources()
-    int copy(void *dst, const void *d_src, size_t bytes, cudaStream_t after) {
-        CGS_CUDA(cudaEventRecord(ready, after));
-        CGS_CUDA(cudaStreamWaitEvent(stream, ready, 0));
-        for (size_t off = 0; off < bytes; off += kStage) {
-            const size_t n = std::min(kStage, bytes - off);
-            const int b = next;
-            next ^= 1;
-            if (mover[b].joinable()) mover[b].join();  // the buffer's previous contents have reached the host array
-            CGS_CUDA(cudaMemcpyAsync(stage[b], (const uint8_t *)d_src + off, n, cudaMemcpyDeviceToHost, stream));
-            CGS_CUDA(cudaEventRecord(landed[b], stream));
-            uint8_t *to = (uint8_t *)dst + off;
-            const uint8_t *from = stage[b];
-            cudaEvent_t ev = landed[b];
-            const int dev = device;
-            mover[b] = std::thread([=]() {
-                cudaSetDevice(dev);
-                cudaEventSynchronize(ev);
-                const size_t per = ((n + kThreads - 1) / kThreads + 4095) & ~(size_t)4095;
-                std::thread workers[kThreads];
-                int started = 0;
-                for (size_t o = 0; o < n; o += per) workers[started++] = std::thread([=]() { memcpy(to + o, from + o, std::min(per, n - o)); });
-                for (int t = 0; t < started; ++t) workers[t].join();
-            });
-        }
-        return 0;
-    }
-    // Source buffers are recycled by slot (0 / 1): mark_sources(slot) after the copies out of a buffer were issued,
-    // wait_sources(slot, s) before stream `s` overwrites that buffer (no-op until the slot was marked).
-    int mark_sources(int slot) {
-        CGS_CUDA(cudaEventRecord(src_read[slot], stream));
-        return 0;
-    }
-    int wait_sources(int slot, cudaStream_t s) {
-        CGS_CUDA(cudaStreamWaitEvent(s, src_read[slot], 0));
-        return 0;
-    }
-    void finish() {
-        for (int b = 0; b < 2; ++b)
-            if (mover[b].joinable()) mover[b].join();
-    }
-    void close() {
-        finish();
-        for (int b = 0; b < 2; ++b) {
-            if (stage[b]) cudaFreeHost(stage[b]);
-            if (landed[b]) cudaEventDestroy(landed[b]);
-            if (src_read[b]) cudaEventDestroy(src_read[b]);
-            stage[b] = nullptr; landed[b] = nullptr; src_read[b] = nullptr;
-        }
-        if (ready) cudaEventDestroy(ready);
-        if (stream) { cudaStreamSynchronize(stream); cudaStreamDestroy(stream); }
-        ready = nullptr; stream = nullptr;
-    }
-};
-
-// Pageable host memory -> device, the mirror image: host threads fill one pinned staging buffer while the other one
-// is DMA'd.  copy() returns when the last piece has been ENQUEUED on `stream` (the caller's stream).
-struct HostSource {
-    static constexpr size_t kStage = (size_t)64 << 20;
-    static constexpr int kThreads = 8;
-    uint8_t *stage[2] = {nullptr, nullptr};
-    cudaEvent_t sent[2] = {nullptr, nullptr};
-    int next = 0;
-
-    int open() {
-        for (int b = 0; b < 2; ++b) {
-            CGS_CUDA(cudaHostAlloc((void **)&stage[b], kStage, cudaHostAllocDefault));
-            CGS_CUDA(cudaEventCreateWithFlags(&sent[b], cudaEventDisableTiming));
-        }
-        return 0;
-    }
-    int copy(void *d_dst, const void *src, size_t bytes, cudaStream_t stream) {
-        for (size_t off = 0; off < bytes; off += kStage) {
-            const size_t n = std::min(kStage, bytes - off);
-            const int b = next;
-            next ^= 1;
-            CGS_CUDA(cudaEventSynchronize(sent[b]));  // the buffer's previous DMA has left (no-op the first time)
-            const uint8_t *from = (const uint8_t *)src + off;
-            uint8_t *to = stage[b];
-            const size_t per = ((n + kThreads - 1) / kThreads + 4095) & ~(size_t)4095;
-            std::thread workers[kThreads];
-            int started = 0;
-            for (size_t o = 0; o < n; o += per) workers[started++] = std::thread([=]() { memcpy(to + o, from + o, std::min(per, n - o)); });
-            for (int t = 0; t < started; ++t) workers[t].join();
-            CGS_CUDA(cudaMemcpyAsync((uint8_t *)d_dst + off, stage[b], n, cudaMemcpyHostToDevice, stream));
-            CGS_CUDA(cudaEventRecord(sent[b], stream));
-        }
-        return 0;
-    }
-    void close() {
-        for (int b = 0; b < 2; ++b) {
-            if (sent[b]) { cudaEventSynchronize(sent[b]); cudaEventDestroy(sent[b]); }
-            if (stage[b]) cudaFreeHost(stage[b]);
-            stage[b] = nullptr; sent[b] = nullptr;
-        }
-    }
-};
-
 struct ImputeStream {
     cgs_impute_plan *plan = nullptr;
     cudaStream_t stream = nullptr;
@@ -1959,7 +2045,7 @@ static int impute_normalized_impl(int device, const float *topic_region, const f
     std::vector<uint8_t> flags((size_t)n_regions);
     int rc = [&]() -> int {
         CGS_TRY(is.open(device, topic_region, cell_topic, n_regions, n_topics, n_cells, impute_scale, as_int32, chunk_rows));
-        CGS_TRY(sink.open(device));
+        CGS_TRY(sink.open(device, (size_t)n_regions * C * out_elem));
         CGS_TRY(dmalloc(&d_norm[0], (size_t)is.chunk * C * out_elem, is.stream));
         CGS_TRY(dmalloc(&d_norm[1], (size_t)is.chunk * C * out_elem, is.stream));
         CGS_TRY(dmalloc(&d_tot, (size_t)C * 8, is.stream));
@@ -2049,7 +2135,7 @@ int cgs_impute_rows(int device, const float *topic_region, const float *cell_top
     int64_t written = 0;
     int rc = [&]() -> int {
         CGS_TRY(is.open(device, topic_region, cell_topic, n_regions, n_topics, n_cells, impute_scale, as_int32, chunk_rows));
-        CGS_TRY(sink.open(device));
+        CGS_TRY(sink.open(device, (size_t)n_regions * row_bytes));
         CGS_TRY(dmalloc(&d_chunk2, (size_t)is.chunk * row_bytes, is.stream));
         uint8_t *bufs[2] = {is.d_chunk, d_chunk2};
         int which = 0;
@@ -2210,7 +2296,7 @@ int cgs_ranksum_contrasts(int device, int dtype, int64_t n_rows, const void *x, 
     double *d_res = nullptr;  // [3][n_contrasts][chunk]
     cudaEvent_t uploaded[2] = {nullptr, nullptr}, tested[2] = {nullptr, nullptr};
     int rc = [&]() -> int {
-        CGS_TRY(source.open());
+        CGS_TRY(source.open((size_t)n_rows * ld * elem));
         for (int b = 0; b < 2; ++b) {
             CGS_TRY(dmalloc(&d_x[b], (size_t)chunk * ld * elem, stream));
             CGS_CUDA(cudaEventCreateWithFlags(&uploaded[b], cudaEventDisableTiming));
@@ -2376,7 +2462,9 @@ int cgs_impute_rankings(int device, const float *topic_region, const float *cell
     int32_t *d_rank = nullptr;
     cgs_impute_plan *plan = nullptr;
     std::vector<float> cells((size_t)K * block);
+    HostSink sink;
     int rc = [&]() -> int {
+        CGS_TRY(sink.open(device, (size_t)R * C * 4));
         CGS_TRY(dmalloc(&d_a, (size_t)R * K, stream));
         CGS_TRY(dmalloc(&d_prod, (size_t)R * block * 4, stream));
         CGS_TRY(dmalloc(&d_rank, (size_t)R * block, stream));
@@ -2388,8 +2476,8 @@ int cgs_impute_rankings(int device, const float *topic_region, const float *cell
             CGS_TRY(cgs_impute_plan_create(&plan, device, cells.data(), 0, n_topics, nc, stream));
             CGS_TRY(cgs_impute_plan_chunk_device(plan, d_a, n_regions, impute_scale, as_int32, d_prod, d_flags, stream));
             CGS_TRY(cgs_rank_columns_device(device, as_int32 ? 0 : 1, d_prod, nc, R, nc, seed, first_cell + c0, d_rank, nc, stream));
-            CGS_CUDA(cudaMemcpy2DAsync(out + c0, (size_t)ld_out * 4, d_rank, (size_t)nc * 4, (size_t)nc * 4, (size_t)R,
-                                       cudaMemcpyDeviceToHost, stream));
+            CGS_TRY(sink.copy2d(out + c0, (size_t)ld_out * 4, d_rank, (size_t)nc * 4, (size_t)R, stream));
+            sink.finish();
             CGS_CUDA(cudaStreamSynchronize(stream));
             cgs_impute_plan_destroy(plan);
             plan = nullptr;
@@ -2397,6 +2485,8 @@ int cgs_impute_rankings(int device, const float *topic_region, const float *cell
         return 0;
     }();
     if (plan) cgs_impute_plan_destroy(plan);
+    cudaStreamSynchronize(stream);
+    sink.close();
     dfree(d_a, stream); dfree(d_prod, stream); dfree(d_rank, stream); dfree(d_flags, stream);
     cudaStreamSynchronize(stream);
     cudaStreamDestroy(stream);
