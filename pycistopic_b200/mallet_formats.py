@@ -13,7 +13,10 @@ writes before and reads after a Mallet run (src/pycisTopic/lda_models.py:472-494
   :class:`CistopicLDAModel` with the device metric block.
 * :func:`write_state` writes a fitted device model's assignments in the same format.
 
-No Mallet binary, no Java: only the formats.  The parsing is host text work; the counting runs on the device.
+No Mallet binary, no Java: only the formats.  Parsing is host text work, and ``load_word_topics`` -- a reader whose
+result is a function of the file alone, a polars group-by in the reference -- tallies the parsed columns on the host
+like the reference does; everything that involves the corpus (counts per cell and region, metrics, further sweeps)
+goes through :func:`lda_from_state`, i.e. the device.
 """
 from __future__ import annotations
 

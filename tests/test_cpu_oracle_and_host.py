@@ -439,3 +439,25 @@ def test_cli_flags_mirror_the_reference():
     for bad in ("topic_modeling lda -i a -o b -t 2", "topic_modeling lda -i a -o b -p 1", "topic_modeling lda -i a -o b -t 2 -p 1 -A maybe"):
         with pytest.raises(SystemExit):
             p.parse_args(bad.split())
+
+
+def test_region_shards_cover_the_range():
+    """Host bookkeeping of the sharded consumers (SURVEY.md 8e iii): contiguous, disjoint, non-empty ranges that
+    cover range(n) in order, one per device, fewer when there is less work than devices."""
+    from pycistopic_b200 import diff_features as pdf
+    assert pdf._as_devices(2) == [2] and pdf._as_devices((0, 1)) == [0, 1] and pdf._as_devices(np.int64(3)) == [3]
+    with pytest.raises(ValueError, match="at least one device"):
+        pdf._as_devices([])
+    for n in (0, 1, 2, 7, 100, 200_001):
+        for devices in ([0], [0, 1], [3, 2, 1, 0], list(range(8))):
+            shards = pdf._shards(n, devices)
+            assert len(shards) <= min(n, len(devices)) and (n < len(devices) or len(shards) == len(devices))
+            pos = 0
+            for dev, a, b in shards:
+                assert a == pos and b > a and dev in devices
+                pos = b
+            assert pos == n
+            sizes = [b - a for _, a, b in shards]
+            assert not sizes or max(sizes) - min(sizes) <= 1 or n < len(devices)
+    assert pdf._run_sharded(lambda d, a, b: (d, b - a), pdf._shards(10, [5, 6, 7])) == [(5, 3), (6, 3), (7, 4)]
+    assert pdf._run_sharded(lambda d, a, b: 1, []) == []
