@@ -34,6 +34,11 @@ print(f"factored: find_diff_features {G} one-vs-rest contrasts on {R} x {C} x K=
       f"({G * R / t_f:.3e} region-tests/s); markers per contrast: {[len(v) for v in res_f.values()]}", flush=True)
 t = time.perf_counter(); sel = pdf.find_highly_variable_features(pdf.normalize_scores(fact, 10 ** 4, materialize=False), plot=False); t_v = time.perf_counter() - t
 print(f"factored: normalize_scores(materialize=False) -> find_highly_variable_features: {t_v:.2f} s, {len(sel)} features", flush=True)
+t = time.perf_counter(); rk = fact.make_rankings(seed=123); t_r = time.perf_counter() - t
+print(f"factored: make_rankings, all {C} cells: {t_r:.2f} s ({rk.mtx.nbytes / 1e9:.1f} GB of int32 rankings)", flush=True)
+for c in (0, C // 2, C - 1):   # every column a permutation
+    assert np.array_equal(np.sort(rk.mtx[:, c]), np.arange(rk.mtx.shape[0]))
+del rk
 if os.environ.get("CGS_FUSED_ONLY"):
     sys.exit(0)
 t = time.perf_counter(); dense = fact.to_dense(); t_i = time.perf_counter() - t
