@@ -102,3 +102,46 @@ def test_sharded_impute_accessibility_public_api():
             assert a[k].index.tolist() == b[k].index.tolist()
     tiny = pdf.FactoredImputedFeatures(tr[:2], ct, regions[:2], cells, 10 ** 6, 700, "t", device=[0, 0, 0, 0])
     assert tiny.to_dense().mtx.shape[0] <= 2 and len(tiny.row_mean_var(10 ** 4)[0]) == len(tiny.feature_names)
+
+
+def _nccl_worker(rank, world, port, out_dir):
+    import os
+    import pickle
+    import torch
+    import torch.distributed as dist
+    from pycistopic_b200 import sharded_consumers as sc
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world)
+    tr, ct, _, _ = _factors()
+    res = sc.distributed_normalized_row_stats(tr, ct, scale_factor=10 ** 6, norm_scale=10 ** 4,
+                                              backend=sc.DeviceBackend(device=rank, chunk_size=1000))
+    with open(os.path.join(out_dir, f"r{rank}.pkl"), "wb") as f:
+        pickle.dump(res, f)
+    dist.destroy_process_group()
+
+
+def test_process_per_gpu_row_stats_over_nccl(tmp_path):
+    """One process per GPU (pycistopic_b200/sharded_consumers.py): per-rank column totals, one NCCL all_reduce of
+    n_cells values, per-rank statistics, all_gather -- equal to the single-device result on every rank."""
+    import pickle
+    import socket
+    import torch
+    import torch.multiprocessing as mp
+    from pycistopic_b200 import diff_features as pdf
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_nccl_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    tr, ct, regions, cells = _factors()
+    one = pdf.FactoredImputedFeatures(tr, ct, regions, cells, 10 ** 6, 1000, "t", device=0)
+    mean1, var1 = one.row_mean_var(10 ** 4)
+    for r in range(2):
+        with open(tmp_path / f"r{r}.pkl", "rb") as f:
+            mean, var, flags = pickle.load(f)
+        np.testing.assert_array_equal(flags, one.row_nonzero)
+        np.testing.assert_array_equal(mean[flags], mean1)
+        np.testing.assert_array_equal(var[flags], var1)
