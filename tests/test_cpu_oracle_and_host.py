@@ -461,3 +461,26 @@ def test_region_shards_cover_the_range():
             assert not sizes or max(sizes) - min(sizes) <= 1 or n < len(devices)
     assert pdf._run_sharded(lambda d, a, b: (d, b - a), pdf._shards(10, [5, 6, 7])) == [(5, 3), (6, 3), (7, 4)]
     assert pdf._run_sharded(lambda d, a, b: 1, []) == []
+
+
+def test_mallet_state_is_validated_before_the_device_is_touched(tmp_path):
+    """lda_from_state refuses a state whose tokens are not those of the matrix, or whose topics do not fit, with a
+    ValueError raised on the host (no GPU needed to get there); shuffled state lines are put back in corpus order."""
+    import scipy.sparse as sp
+    from pycistopic_b200 import mallet_formats as mf
+    rng = np.random.default_rng(6)
+    X = sp.csr_matrix((rng.random((30, 8)) < 0.3).astype(np.int32))      # regions x cells
+    Xc = sp.csc_matrix(X); Xc.sort_indices()
+    doc = np.repeat(np.arange(8), np.diff(Xc.indptr))
+    z = rng.integers(0, 4, Xc.nnz)
+    path = str(tmp_path / "s.gz")
+    mf.write_state(path, doc, Xc.indices, z, np.full(4, 1.0), 0.1)
+    other = X.tolil(copy=True); other[0, 0] = 1 - other[0, 0]
+    with pytest.raises(ValueError, match="tokens"):
+        mf.lda_from_state(sp.csr_matrix(other), path, 4, 1.0, 0.1)
+    with pytest.raises(ValueError, match="outside"):
+        mf.lda_from_state(X, path, 3, 1.0, 0.1)
+    state = mf.read_state(path)
+    state["region"] = state["region"].copy(); state["region"][0] = 29 if state["region"][0] != 29 else 28
+    with pytest.raises(ValueError, match="not those of the matrix"):
+        mf.lda_from_state(X, state, 4, 1.0, 0.1)
