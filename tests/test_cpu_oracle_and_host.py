@@ -484,3 +484,30 @@ def test_mallet_state_is_validated_before_the_device_is_touched(tmp_path):
     state["region"] = state["region"].copy(); state["region"][0] = 29 if state["region"][0] != 29 else 28
     with pytest.raises(ValueError, match="not those of the matrix"):
         mf.lda_from_state(X, state, 4, 1.0, 0.1)
+
+
+@pytest.mark.skipif(not rf.available(), reason="/root/reference not present")
+def test_variable_feature_selection_matches_live_reference():
+    """select_variable_features against the reference's function run live from the tree, on inputs that hit its
+    corner cases: all-zero regions (mean 0 -> 1e-12), constant regions (dispersion 0 -> NaN), bins holding a single
+    region (std NaN -> normalised dispersion 1), few regions, n_top_features ties."""
+    import logging
+    from pycistopic_b200 import diff_features as pdf
+    fn = rf.reference_find_highly_variable_features()
+    logging.disable(logging.INFO)
+    try:
+        rng = np.random.default_rng(31)
+        for R, C, n_bins in ((400, 60, 20), (35, 20, 20), (120, 33, 5), (7, 9, 3)):
+            mat = np.abs(rng.normal(0.3, 0.4, (R, C))) * (rng.random((R, 1)) < 0.9)
+            mat[1] = 0.7                       # constant region
+            mat[2, :] = 0; mat[2, 0] = 40.0    # an outlier mean: alone in its bin
+            frame = pd.DataFrame(mat, index=[f"r{i}" for i in range(R)])
+            mean = np.mean(mat, axis=1, dtype=np.float32)
+            var = np.var(mat, axis=1, dtype=np.float32)
+            feats = frame.index.tolist()
+            for kw in ({}, {"n_top_features": max(1, R // 5)}, {"min_disp": -0.5, "min_mean": 0.0, "max_mean": 50, "max_disp": 2.0}):
+                want = fn(frame, n_bins=n_bins, plot=False, **kw)
+                got = pdf.select_variable_features(mean, var, feats, n_bins=n_bins, **kw)
+                assert got == want, (R, C, n_bins, kw)
+    finally:
+        logging.disable(logging.NOTSET)
