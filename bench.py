@@ -49,6 +49,15 @@ def b_tok(k: int) -> float:
     return 4.0 * k + 28.0
 
 
+def hbm_peak():
+    """(GB/s, where it comes from): the driver-written measured copy bandwidth, else the recipe's fallback."""
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        with open(peaks_path) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    return 6650.0, "B200_PROFILING.md fallback (of fallback)"
+
+
 # ------------------------------------------------------------------------------------------------
 # clocks sampling (B200_PROFILING.md recipe): nvidia-smi in the background during the timed region
 # ------------------------------------------------------------------------------------------------
@@ -253,7 +262,7 @@ def run_reference(args):
 ADLDA_SHAPE, ADLDA_K = "C3", 60
 
 
-def run_adlda_leg(args, dev, rank, world, local_rank):
+def run_adlda_leg(args, dev, rank, world, local_rank, shape=None):
     import torch
     import torch.distributed as dist
 
@@ -261,7 +270,8 @@ def run_adlda_leg(args, dev, rank, world, local_rank):
     from pycistopic_b200.adlda import Exchanger, GpuShard, balanced_cell_partition
     from pycistopic_b200.synth import SHAPES, planted_topic_tokens
 
-    shape, K_adlda = args.adlda_shape, (ADLDA_K if args.adlda_shape != "C4" else 100)
+    shape = shape or args.adlda_shape
+    K_adlda = ADLDA_K if shape != "C4" else 100
     D, W, density = SHAPES[shape]
     if shape == "C4" or args.adlda_rank_local_data:
         # atlas scale: every rank draws only its own cells (equal cell counts; the budgets are i.i.d.)
@@ -294,9 +304,12 @@ def run_adlda_leg(args, dev, rank, world, local_rank):
         cp = torch.tensor(cell_ptr_h[cb:ce + 1] - t0, dtype=torch.int64, device=dev)
     torch.cuda.empty_cache()
     out = {}
-    for exchange in (["nccl", "peer"] if world > 1 else ["nccl"]):
+    modes = ["nccl", "async"] + (["peer"] if world == 2 else [])
+    n = max(3, args.steps)
+    for exchange in modes:
         corpus = Corpus.from_device_tokens(cp.data_ptr(), tok.data_ptr(), ce - cb, W, t1 - t0, device=local_rank,
                                            token_offset=t0, keepalive=(cp, tok))
+        corpus.set_global_size(D, N_total)  # concurrency caps follow the whole matrix, not the 1 / world shard
         shard = GpuShard(None, (cb, ce), t0, K_adlda, ALPHA / K_adlda, ETA, MODEL_SEED, device=local_rank,
                          exchange=exchange, corpus=corpus)
         shard.init()
@@ -305,41 +318,90 @@ def run_adlda_leg(args, dev, rank, world, local_rank):
         stream = shard.stream
 
         def sweep():
+            ex.before_sweep()
             shard.sweep_part(0, 1)
-            ex.step()
+            ex.after_sweep()
 
         for _ in range(5 + max(args.warmup, 3)):
             sweep()
+        ex.drain()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        n = max(3, args.steps)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
         e0.record(stream)
         for i in range(n):
-            ev[i][0].record(stream)
-            shard.sweep_part(0, 1)
-            ev[i][1].record(stream)
-            ex.step()
+            sweep()
+        ex.drain()  # the timed region ends with complete, identical replicas on every rank
         e1.record(stream)
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / n
-        sample_ms = statistics.mean(a.elapsed_time(b) for a, b in ev)
         if world > 1:
-            t = torch.tensor([ms, sample_ms], device=dev, dtype=torch.float64)
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms, sample_ms = float(t[0].item()), float(t[1].item())
-        ll = shard.loglik_cells()
-        out[exchange] = {"tokens_per_s": N_total / (ms * 1e-3), "ms_per_sweep": ms, "ms_sampling": sample_ms,
-                         "ms_exchange": ms - sample_ms}
+            ms = float(t[0].item())
+
+        # ---- correctness of what was just timed (parity gates run with every benchmark) ----------
+        h = shard.model.state_hash()
+        hist = torch.empty(W * shard.model.padded_topics, dtype=torch.int32, device=dev)
+        ndk_bad = shard.model.region_histogram(hist.data_ptr())
+        shard.model.sync()
+        ll_cells = shard.loglik_cells()
+        stat = torch.tensor([float(ndk_bad), ll_cells], device=dev, dtype=torch.float64)
+        hashes = [h]
+        if world > 1:
+            dist.all_reduce(hist)
+            dist.all_reduce(stat)
+            hashes = [None] * world
+            dist.all_gather_object(hashes, h)
+        bad = shard.model.verify_counts(hist.data_ptr())
+        timeouts = shard.model.exchange_timeouts() if exchange == "async" else 0
+        flags = torch.tensor([float(bad["n_wk"]), float(bad["n_k"]), float(timeouts)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(flags, op=dist.ReduceOp.MAX)
+        ll = float(stat[1].item()) + shard.loglik_regions()
+        del hist
+        checks = {
+            "replicas_identical": all(x == hashes[0] for x in hashes),
+            "sum_nwk_equals_tokens": hashes[0]["sum_nwk"] == N_total,
+            "sum_nk_equals_tokens": hashes[0]["sum_nk"] == N_total,
+            "n_dk_mismatches": int(stat[0].item()), "n_wk_mismatches_vs_histogram_of_z": int(flags[0].item()),
+            "n_k_mismatches": int(flags[1].item()), "exchange_timeouts": int(flags[2].item()),
+            "hash_nwk": f"{hashes[0]['hash_nwk']:016x}", "loglik": ll, "loglik_per_token": ll / N_total,
+        }
+        checks["ok"] = bool(checks["replicas_identical"] and checks["sum_nwk_equals_tokens"]
+                            and checks["sum_nk_equals_tokens"] and checks["n_dk_mismatches"] == 0
+                            and checks["n_wk_mismatches_vs_histogram_of_z"] == 0 and checks["n_k_mismatches"] == 0
+                            and checks["exchange_timeouts"] == 0)
+
+        # ---- sampling alone on the same shard (no exchange): what the exchange adds is ms - this -------------
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(stream)
+        for i in range(n):
+            shard.sweep_part(0, 1)
+        s1.record(stream)
+        torch.cuda.synchronize()
+        sample_ms = s0.elapsed_time(s1) / n
+        if world > 1:
+            t = torch.tensor([sample_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sample_ms = float(t[0].item())
+        out[exchange] = {"tokens_per_s": N_total / (ms * 1e-3), "ms_per_sweep": ms, "ms_sampling_alone": sample_ms,
+                         "ms_exchange_exposed": ms - sample_ms, "sweep_shape": shard.model.sweep_shape,
+                         "checks": checks}
         shard.close()
-        _ = ll
-    peak = 6544.3
+        torch.cuda.empty_cache()
+    peak = hbm_peak()[0]
     best = max(out.values(), key=lambda v: v["tokens_per_s"])
     return {"workload": f"{shape}: {D} cells x {W} regions, {N_total} tokens, one K={K_adlda} model, cells sharded "
-                        f"over {world} GPU(s), one n_wk exchange per sweep ({4 * W * ((K_adlda + 3) // 4 * 4) / 1e6:.0f} MB)",
+                        f"over {world} GPU(s), n_wk exchange ({4 * W * ((K_adlda + 3) // 4 * 4) / 1e6:.0f} MB): nccl = "
+                        "delta / all-reduce / apply after every sweep; async = fused peer-memory round kernel beside the "
+                        "next sweep",
             "scaling": "strong", "value": best["tokens_per_s"], "unit": "tokens/s", "per_exchange": out,
+            "checks_ok": all(v["checks"]["ok"] for v in out.values()),
             "frac_of_hbm_roofline_per_gpu": b_tok(K_adlda) * best["tokens_per_s"] / world / 1e9 / peak}
 
 
@@ -396,6 +458,176 @@ def run_impute_leg(args, dev, local_rank, hbm_peak):
             "ms_per_chunk": ms, "bound": "hbm (4 R C output bytes)", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
             "frac": gbs / hbm_peak, "tflops_2RCK": 2.0 * R * C * K / (ms * 1e-3) / 1e12,
             "max_abs_diff_vs_fp64_on_8_rows": max_diff, "kernel": "impute_umma_kernel (tcgen05.mma kind::tf32, 3xTF32)"}
+
+
+# ------------------------------------------------------------------------------------------------
+# Parity leg (SURVEY.md 8d "parity gates run with every benchmark"): the device sampler against the
+# oracle traces FROZEN in tests/golden/trace_c2_4000cells.npz -- a C2-shaped corpus (200 000 regions, 3 %,
+# 4 000 cells, 2.6e7 tokens; the torch-CPU generator is reproducible, the file stores its checksum), K = 10
+# and K = 50, 24 sweeps, seed-averaged on both sides; tolerance 1 % (north star).  Nothing under oracle/ runs.
+# ------------------------------------------------------------------------------------------------
+def run_parity_leg(dev, local_rank):
+    import torch
+
+    from pycistopic_b200 import Corpus, DeviceModel
+    from pycistopic_b200.synth import planted_topic_tokens
+    path = os.path.join(ROOT, "tests", "golden", "trace_c2_4000cells.npz")
+    if not os.path.exists(path):
+        return {"ok": None, "skipped": "tests/golden/trace_c2_4000cells.npz not found"}
+    t_start = time.perf_counter()
+    g = np.load(path)
+    D, W = int(g["D"]), int(g["W"])
+    cell, region = planted_topic_tokens(D, W, float(g["density"]), seed=int(g["data_seed"]), device=torch.device("cpu"))
+    check = np.array([cell.numel(), int(cell.sum()), int(region.sum())])
+    if not np.array_equal(check, g["checksum"]):
+        return {"ok": None, "skipped": "the torch CPU generator of this image does not reproduce the frozen matrix"}
+    cnt = torch.bincount(cell, minlength=D)
+    cell_ptr = torch.zeros(D + 1, dtype=torch.int64)
+    cell_ptr[1:] = torch.cumsum(cnt, 0)
+    cell_ptr, tok = cell_ptr.to(dev), region.to(torch.int32).to(dev)
+    corpus = Corpus.from_device_tokens(cell_ptr.data_ptr(), tok.data_ptr(), D, W, tok.numel(), device=local_rank,
+                                       keepalive=(cell_ptr, tok))
+    seeds = [int(x) for x in g["seeds"]]
+    out = {"workload": f"C2-shaped: {D} cells x {W} regions, {tok.numel()} tokens; device chains vs frozen oracle "
+                       f"traces (mean of {len(seeds)} seeds each), 24 sweeps, tolerance 1 %", "per_K": {}}
+    ok = True
+    for K in (10, 50):
+        ref = g[f"mean_K{K}"]
+        n_iter = len(ref) - 1
+        traces = []
+        consistent = True
+        for seed in seeds:
+            m = DeviceModel(corpus, K, ALPHA / K, ETA, seed=seed)
+            m.init()
+            tr = []
+            for _ in range(n_iter):
+                tr.append(m.loglikelihood())
+                m.sweep(1)
+            tr.append(m.loglikelihood())
+            consistent = consistent and m.verify_counts() == {"n_dk": 0, "n_wk": 0, "n_k": 0}
+            traces.append(tr)
+            m.close()
+        rel = np.abs(np.mean(traces, axis=0) - ref) / np.abs(ref)
+        this_ok = bool(rel.max() < 0.01 and abs(traces[0][0] - ref[0]) <= 1e-9 * abs(ref[0]) and consistent)
+        ok = ok and this_ok
+        out["per_K"][str(K)] = {"max_rel_dev_of_trace": float(rel.max()), "at_sweep": int(rel.argmax()),
+                                "initial_loglik_identical": bool(abs(traces[0][0] - ref[0]) <= 1e-9 * abs(ref[0])),
+                                "counts_are_histogram_of_z": bool(consistent), "ok": this_ok}
+    corpus.close()
+    out["ok"] = ok
+    out["seconds"] = round(time.perf_counter() - t_start, 1)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# The other half of BASELINE.json's metric: wall clock of the n_topics sweep through the public API on the
+# north-star target T (20 000 cells x 300 000 regions, 8 models, 500 iterations; target < 120 s on 8 x B200).
+# One process drives every GPU of the job (run_cgs_models spreads the models over `devices`).
+# ------------------------------------------------------------------------------------------------
+T_TOPICS = [5, 10, 15, 20, 25, 30, 40, 50]
+T_ITER = 500
+
+
+def run_target_leg(dev, devices):
+    import scipy.sparse as sp
+    import torch
+
+    from pycistopic_b200.lda_models import evaluate_models, run_cgs_models
+    from pycistopic_b200.synth import SHAPES, SyntheticCistopicObject, planted_topic_tokens
+    import logging
+    D, W, dens = SHAPES["T"]
+    t = time.perf_counter()
+    cell, region = planted_topic_tokens(D, W, dens, seed=DATA_SEED, device=dev)
+    cell, region = cell.cpu().numpy(), region.cpu().numpy()
+    m = sp.csr_matrix((np.ones(cell.shape[0], np.int32), (region, cell)), shape=(W, D), dtype=np.int32)
+    m.sort_indices()
+    del cell, region
+    torch.cuda.empty_cache()
+    obj = SyntheticCistopicObject(m, [f"cell_{i}" for i in range(D)], [f"chr1:{i * 500}-{i * 500 + 500}" for i in range(W)])
+    gen_s = time.perf_counter() - t
+    logging.disable(logging.INFO)
+    try:
+        t0 = time.perf_counter()
+        models = run_cgs_models(obj, n_topics=T_TOPICS, n_iter=T_ITER, random_state=MODEL_SEED, alpha=ALPHA,
+                                alpha_by_topic=True, eta=ETA, eta_by_topic=False, devices=devices)
+        wall = time.perf_counter() - t0
+        best = evaluate_models(models, return_model=True, plot=False)
+    finally:
+        logging.disable(logging.NOTSET)
+    layout_ok = all(mm.cell_topic.shape == (k, D) and mm.topic_region.shape == (W, k) and
+                    int(mm.topic_ass["Assignments"].sum()) == m.nnz for mm, k in zip(models, T_TOPICS))
+    return {"workload": f"T: run_cgs_models on {D} cells x {W} regions ({m.nnz} tokens), n_topics {T_TOPICS}, "
+                        f"{T_ITER} iterations, host CSR in -> list of CistopicLDAModel out (token lists, sweeps, metrics, "
+                        "DataFrames)", "wall_s": round(wall, 2), "target_s": 120.0, "gpus": len(devices),
+            "token_updates_per_s": m.nnz * T_ITER * len(T_TOPICS) / wall,
+            "model_fit_s": {int(mm.n_topic): round(float(mm.parameters.loc["time", "Parameter"]), 2) for mm in models},
+            "loglikelihood_true_per_token": {int(mm.n_topic): round(float(mm.loglikelihood_true) / m.nnz, 5) for mm in models},
+            "selected_n_topic": int(best.n_topic), "layout_ok": bool(layout_ok), "generate_s": round(gen_s, 1)}
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json configs[4] ("C5"): impute_accessibility on 200 000 cells x 1 000 000 regions x 100 topics.  The
+# 800 GB product never exists: every rank takes a contiguous range of regions, recomputes its chunks on the
+# tensor cores twice -- per-cell totals (the one exchange: an all-reduce of n_cells values), then per-cell scaling,
+# log1p and the per-region mean / variance (normalize_scores + find_highly_variable_features' reduction).
+# ------------------------------------------------------------------------------------------------
+C5_R, C5_K, C5_C = 1_000_000, 100, 200_000
+
+
+def run_c5_leg(args, dev, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    from pycistopic_b200.sharded_consumers import DeviceBackend, region_range
+    R, K, C = C5_R, C5_K, C5_C
+    g = torch.Generator(device=dev)
+    g.manual_seed(4321)
+    A = torch.rand(R, K, device=dev, generator=g)
+    A /= A.sum(0, keepdim=True)
+    B = torch.rand(K, C, device=dev, generator=g)
+    B /= B.sum(0, keepdim=True)
+    r0, r1 = region_range(R, rank, world)
+    A_h = np.ascontiguousarray(A[r0:r1].cpu().numpy())
+    B_h = np.ascontiguousarray(B.cpu().numpy())
+    probe_rows = torch.arange(r0, min(r1, r0 + 4), device=dev)
+    probe = (A[probe_rows].double() @ B.double()) * 1e6
+    del A, B
+    torch.cuda.empty_cache()
+    backend = DeviceBackend(device=local_rank, chunk_size=20000)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    totals, flags = backend.column_totals(A_h, B_h, 1e6, True)
+    t1 = time.perf_counter()
+    tt = torch.from_numpy(totals).to(dev)
+    if world > 1:
+        dist.all_reduce(tt)
+    totals = np.ascontiguousarray(tt.cpu().numpy())
+    t2 = time.perf_counter()
+    mean, var = backend.row_stats(A_h, B_h, 1e6, True, 1e4, totals)
+    torch.cuda.synchronize()
+    t3 = time.perf_counter()
+    times = torch.tensor([t3 - t0, t1 - t0, t2 - t1, t3 - t2], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    wall, s_tot, s_x, s_stats = [float(x) for x in times.tolist()]
+    # check on four regions of this rank against an fp64 evaluation of the same definition
+    x = torch.trunc(probe)
+    norm = torch.log1p(x / (torch.from_numpy(totals).to(dev).double() / 1e4))
+    ref_mean = norm.float().mean(dim=1).cpu().numpy()
+    rel = float(np.max(np.abs(mean[: len(ref_mean)] - ref_mean) / np.maximum(np.abs(ref_mean), 1e-30)))
+    chk = torch.tensor([rel], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(chk, op=dist.ReduceOp.MAX)
+    return {"workload": f"C5: {R} regions x {K} topics x {C} cells ({4.0 * R * C / 1e9:.0f} GB int32 product, never "
+                        f"materialised), regions sharded over {world} GPU(s), host factors in -> per-region mean / var of "
+                        "normalize_scores(impute_accessibility(...)) out; two passes over the chunks",
+            "wall_s": round(wall, 3), "s_column_totals": round(s_tot, 3), "s_exchange": round(s_x, 4),
+            "s_normalized_row_stats": round(s_stats, 3),
+            "imputed_values_per_s": 2.0 * R * C / wall, "product_TFLOPs_2RCK": 2.0 * (2.0 * R * C * K) / wall / 1e12,
+            "kept_regions_rank0": int(flags.sum()), "max_rel_diff_mean_vs_fp64_probe": float(chk.item()),
+            "ok": bool(chk.item() < 1e-3)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -479,6 +711,14 @@ def run_cuda(args):
     clock_info = clocks.stop() if rank == 0 else None
     elapsed_ms = e_start.elapsed_time(e_stop)
     launches = sum(m.launch_count for m in models) - launches0
+    # ---- the state that was just timed must be exact bookkeeping (every model, device-side recount of z) ----
+    model_checks = {}
+    for K, m in zip(my_topics, models):
+        bad = m.verify_counts()
+        h = m.state_hash()
+        model_checks[K] = {"ok": bad == {"n_dk": 0, "n_wk": 0, "n_k": 0} and h["sum_nwk"] == N and h["sum_nk"] == N,
+                           "mismatches": bad, "sum_nwk": h["sum_nwk"], "loglik_per_token": m.loglikelihood() / N,
+                           "sweeps": m.sweeps_done}
     per_model_ms = {K: statistics.mean(per_model_events[s][j][0].elapsed_time(per_model_events[s][j][1])
                                        for s in range(args.steps)) for j, K in enumerate(my_topics)}
     if world > 1:
@@ -486,20 +726,18 @@ def run_cuda(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed_ms = float(t.item())
         gathered = [None] * world
-        dist.all_gather_object(gathered, (per_model_ms, launches))
+        dist.all_gather_object(gathered, (per_model_ms, launches, model_checks))
         per_model_ms = {k: v for g in gathered for k, v in g[0].items()}
         launches = sum(g[1] for g in gathered)
+        model_checks = {k: v for g in gathered for k, v in g[2].items()}
+    checks = {"counts_are_histogram_of_z": all(v["ok"] for v in model_checks.values()),
+              "tokens": N, "per_model": {str(k): v for k, v in sorted(model_checks.items())}}
     total_tokens = float(N) * len(N_TOPICS) * args.steps
     value = total_tokens / (elapsed_ms * 1e-3)
 
     # ---- roofline of the dominant kernel: the K = 50 sweep ------------------------------------
     k_dom = max(per_model_ms, key=lambda k: per_model_ms[k])
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        with open(peaks_path) as f:
-            peak, peak_src = float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
-    else:
-        peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+    peak, peak_src = hbm_peak()
     achieved = b_tok(k_dom) * N / (per_model_ms[k_dom] * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "sweep_traffic.json")
@@ -608,12 +846,37 @@ def run_cuda(args):
     del cell_ptr, tok
     torch.cuda.empty_cache()
     torch.cuda.set_stream(torch.cuda.default_stream(dev))
+    # host-side barrier for the legs in which one rank works while the others must leave their GPUs alone
+    host_group = dist.new_group(backend="gloo") if world > 1 else None
+
+    def host_barrier():
+        if world > 1:
+            dist.barrier(group=host_group)
+
     impute = None
     if rank == 0 and not args.no_impute:
         impute = run_impute_leg(args, dev, local_rank, peak)
+    parity = None
+    if rank == 0 and not args.no_parity:
+        parity = run_parity_leg(dev, local_rank)
+    torch.cuda.synchronize()
+    host_barrier()
     adlda = None
     if not args.no_adlda:
         adlda = run_adlda_leg(args, dev, rank, world, local_rank)
+    adlda_c4 = None
+    if world >= 8 and not args.no_adlda and not args.no_c4:
+        adlda_c4 = run_adlda_leg(args, dev, rank, world, local_rank, shape="C4")
+    c5 = None
+    if not args.no_c5:
+        c5 = run_c5_leg(args, dev, rank, world, local_rank)
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    host_barrier()
+    sweep_wall_clock = None
+    if rank == 0 and not args.no_target:
+        sweep_wall_clock = run_target_leg(dev, list(range(world)))
+    host_barrier()
 
     if rank == 0:
         line = {
@@ -629,7 +892,8 @@ def run_cuda(args):
                        "l2": "inputs larger than L2: every model streams 6 B/token of tokens+topics "
                              f"({6 * N / 1e6:.0f} MB) per sweep and the step cycles through {len(my_topics)} models"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clock_info, "adlda": adlda, "impute": impute,
+            "clocks": clock_info, "checks": checks, "parity": parity, "adlda": adlda, "adlda_c4": adlda_c4,
+            "impute": impute, "impute_c5": c5, "sweep_wall_clock": sweep_wall_clock,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -649,6 +913,10 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-adlda", action="store_true")
     ap.add_argument("--no-impute", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the frozen-oracle-trace check (rank 0, ~1 min)")
+    ap.add_argument("--no-c4", action="store_true", help="skip the atlas-scale AD-LDA leg (only runs at >= 8 GPUs)")
+    ap.add_argument("--no-c5", action="store_true", help="skip the atlas-scale imputation leg")
+    ap.add_argument("--no-target", action="store_true", help="skip the n_topics-sweep wall clock on target T")
     ap.add_argument("--adlda-shape", default=ADLDA_SHAPE, choices=["C1", "C2", "C3", "C4", "T"],
                     help="matrix of the single-model AD-LDA leg (C3 = BASELINE configs[2], C4 = configs[3], K = 100)")
     ap.add_argument("--adlda-rank-local-data", action="store_true",

@@ -72,6 +72,10 @@ int cgs_corpus_dims(const cgs_corpus *c, int32_t *n_cells, int32_t *n_regions, i
 int cgs_corpus_export_tokens(const cgs_corpus *c, int32_t *WS, int32_t *DS);
 /* Global index of this shard's first token (z initialisation is i mod K over GLOBAL i). */
 int cgs_corpus_set_token_offset(cgs_corpus *c, int64_t global_token_offset);
+/* Size of the WHOLE matrix when this corpus holds one shard of its cells (AD-LDA): models created afterwards
+ * size their concurrency caps (cells open at once, tokens in flight) against the matrix the shard is sampled
+ * against, not against the shard -- otherwise a 1/8 shard would fill less than half of its GPU. */
+int cgs_corpus_set_global_size(cgs_corpus *c, int64_t n_cells_global, int64_t n_tokens_global);
 
 /* ---- model: one lda.LDA instance (lda_models.py:248-287) ----------------------------- */
 
@@ -118,6 +122,17 @@ int cgs_model_set_max_blocks(cgs_model *m, int32_t max_blocks);
 int cgs_model_set_nk_staleness(cgs_model *m, double divisor);
 int cgs_model_get_sweep_shape(const cgs_model *m, int32_t *lanes_per_token, int32_t *chunks_per_lane,
                               int32_t *warps_per_cell);
+/* Deterministic mode (the reference is bit-reproducible for a fixed random_state, lda_models.py:104; the default
+ * device schedule is not, because cells read the LIVE n_wk while other cells update it).  parts > 0: every sweep runs
+ * as `parts` sub-sweeps; each reads n_wk / n_k from a copy taken when the sub-sweep starts, one warp owns a cell, and
+ * all count updates are integer reductions (commutative) -- so the result is a pure function of (matrix, n_topics,
+ * alpha, eta, seed, parts), whatever the scheduling.  The price is staleness of up to 1/parts of a sweep (DESIGN.md
+ * section 5).  parts = 0 restores the default schedule. */
+int cgs_model_set_deterministic(cgs_model *m, int32_t parts);
+/* Arithmetic of the conditional p(k), its running sum and the inversion: 32 = float (default), 64 = double, the
+ * reference's precision (lda._lda._sample_topics).  Same schedule, random bits and integer bookkeeping
+ * either way: the A/B behind the statement that fp32 does not move the log-likelihood trace. */
+int cgs_model_set_conditional_precision(cgs_model *m, int32_t bits);
 /* Kernel launches issued by this model so far (for bench.py's gpu_launches). */
 int cgs_model_launch_count(const cgs_model *m, int64_t *count);
 /* Number of sweeps done so far. */
@@ -127,6 +142,19 @@ int cgs_model_sweeps_done(const cgs_model *m, int64_t *count);
  * `partial` selects what is summed: 0 = everything, 1 = only the cell-side terms (n_dk, nd),
  * 2 = only the region-side terms (n_wk, n_k). */
 int cgs_model_loglik(cgs_model *m, int partial, double *ll);
+
+/* ---- consistency checks on the device state (bench.py runs them after its timed regions) ---- */
+/* d_hist (DEVICE, int32[n_regions * Kp], overwritten) receives the (region, topic) histogram of this corpus' z;
+ * *ndk_mismatches = entries of n_dk that differ from the per-cell topic histogram of z (+ topics out of range). */
+int cgs_model_region_histogram(cgs_model *m, int32_t *d_hist, int64_t *ndk_mismatches);
+/* out3[0] = n_dk mismatches (as above; only when d_hist == NULL), out3[1] = entries where n_wk differs from d_hist
+ * (NULL: the local histogram of z is built first; an AD-LDA shard passes the histogram summed over all ranks),
+ * out3[2] = topics whose n_k differs from the column sum of n_wk.  All zero = the three tables are exactly the
+ * bookkeeping of z (the invariant lda._lda._sample_topics keeps). */
+int cgs_model_verify_counts(cgs_model *m, const int32_t *d_hist, int64_t *out3);
+/* out4 = { position-dependent 64-bit hash of n_wk, sum(n_wk), sum(n_k), hash of n_k }: replicas of an AD-LDA run
+ * must agree on all four and the sums must equal the global token count. */
+int cgs_model_state_hash(cgs_model *m, uint64_t *out4);
 
 /* Reference-layout exports (host pointers, any may be NULL). */
 int cgs_model_export_counts(cgs_model *m, int32_t *nzw, int32_t *ndz, int32_t *nz);
@@ -181,6 +209,36 @@ int cgs_model_snapshot(cgs_model *m);
  * the result to the local n_wk / n_k.  The caller provides the cross-rank barrier before
  * (all deltas computed) and after (all reads done). */
 int cgs_model_delta_apply_peers(cgs_model *m, void *const *peer_delta, int32_t n_ranks);
+
+/* The whole synchronous exchange step behind the ABI: delta = n_wk - snapshot, ncclAllReduce(delta, int32, sum) on
+ * the model's stream with the caller's communicator (an ncclComm_t: torch's ProcessGroupNCCL._comm_ptr(), or one
+ * made by cgs_nccl_comm_create), then cgs_model_delta_apply.  libnccl.so.2 is resolved at first use (dlopen). */
+int cgs_model_allreduce_delta(cgs_model *m, void *nccl_comm);
+/* For hosts without their own NCCL plumbing: rank 0 calls cgs_nccl_unique_id and ships the 128 bytes to the other
+ * ranks by any means; every rank then creates its communicator. */
+int cgs_nccl_unique_id(void *id_out_128_bytes);
+int cgs_nccl_comm_create(void **comm, int device, int32_t n_ranks, int32_t rank, const void *id_128_bytes);
+int cgs_nccl_comm_destroy(void *comm);
+
+/* Asynchronous exchange over peer memory, ONE fused kernel per round that runs BESIDE the sweep kernel
+ * (csrc/exchange_kernels.cuh): capture the local changes, reduce-scatter + all-gather them through loads / stores on
+ * the peers' arenas over NVLink, apply the other ranks' changes to the live n_wk with reductions.  Counts stay
+ * exact; what a rank sees of the others is at most one round old.
+ *   cgs_model_exchange_arena: the rank's arena (delta | total | flags; one cudaMalloc block, exportable with
+ *     cgs_ipc_export).  Call after cgs_model_init / set_z and before the first sweep.
+ *   cgs_model_exchange_open: peer_arena[q] = rank q's arena mapped into this process (cgs_ipc_open), own entry
+ *     ignored.  The first round turns the local counts into global ones on every rank.
+ *   cgs_model_exchange_round: enqueue one round on the model's exchange stream (highest priority); it starts when
+ *     the work enqueued on the model's stream so far is done and overlaps what is enqueued there next.  Every rank
+ *     must enqueue the same number of rounds.  n_ctas <= 0: default (64).
+ *   cgs_model_exchange_wait: the model's stream waits for the last enqueued round (before loglik / exports). */
+int cgs_model_exchange_arena(cgs_model *m, void **ptr, size_t *bytes);
+int cgs_model_exchange_open(cgs_model *m, void *const *peer_arena, int32_t n_ranks, int32_t rank);
+int cgs_model_exchange_round(cgs_model *m, int32_t n_ctas);
+int cgs_model_exchange_wait(cgs_model *m);
+/* Waits for the exchange stream; *timeouts = barrier waits that gave up after 4 s because a peer never arrived
+ * (0 = every round completed; anything else means the tables must not be used). */
+int cgs_model_exchange_status(cgs_model *m, int32_t *timeouts);
 
 /* CUDA IPC plumbing so that ranks (one process per GPU) can map each other's delta buffers:
  * export a 64-byte handle of a cgs-owned device buffer, open a peer's handle, close it. */

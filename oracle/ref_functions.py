@@ -11,6 +11,7 @@ imports fail), but the functions of interest are plain NumPy/``math`` code, so t
 * ``CistopicImputedFeatures.make_rankings`` (method, run on a stand-in object)   diff_features.py:274-337
 * ``find_highly_variable_features`` (matplotlib, absent here, replaced by a no-op stand-in; plot=False)
                                                  diff_features.py:577-714
+* ``evaluate_models`` (model selection; matplotlib replaced by an inert stand-in)   lda_models.py:1048-1270
 * ``LDAMallet.corpus_to_mallet`` (method)                                          lda_models.py:472-494
 * ``markers`` / ``get_wilcox_test_pvalues`` / ``p_adjust_bh`` / ``get_log2_fc`` / ``mean_axis1`` /
   ``subset_array_second_axis``                   diff_features.py:839-1120 (decorators dropped: numba.prange
@@ -147,3 +148,23 @@ def reference_find_highly_variable_features():
     extra = {"pd": pd, "sys": sys, "logging": logging, "sklearn": sklearn, "plt": inert,
              "matplotlib": types.SimpleNamespace(rcParams={}), "CistopicImputedFeatures": _ImputedStandIn}
     return _load("diff_features.py", ["find_highly_variable_features"], extra=extra)["find_highly_variable_features"]
+
+
+class _Inert:
+    """Accepts any attribute access and any call (stand-in for matplotlib.pyplot / matplotlib)."""
+
+    def __getattr__(self, name):
+        return _Inert()
+
+    def __call__(self, *a, **k):
+        return _Inert()
+
+
+def reference_evaluate_models():
+    """The reference's own ``evaluate_models`` (lda_models.py:1048-1270); plotting goes to an inert stand-in, so call
+    it with ``plot=False`` or ``True`` alike."""
+    import pandas as pd
+    ns = _load("utils.py", ["subset_list"])
+    extra = {"pd": pd, "plt": _Inert(), "matplotlib": _Inert(), "subset_list": ns["subset_list"],
+             "CistopicLDAModel": object}
+    return _load("lda_models.py", ["evaluate_models"], extra=extra)["evaluate_models"]

@@ -74,6 +74,21 @@ SIGNATURES = {
     "cgs_model_delta_apply": (ctypes.c_int, [c_vp]),
     "cgs_model_snapshot": (ctypes.c_int, [c_vp]),
     "cgs_model_delta_apply_peers": (ctypes.c_int, [c_vp, ctypes.POINTER(c_vp), ctypes.c_int32]),
+    "cgs_corpus_set_global_size": (ctypes.c_int, [c_vp, ctypes.c_int64, ctypes.c_int64]),
+    "cgs_model_set_deterministic": (ctypes.c_int, [c_vp, ctypes.c_int32]),
+    "cgs_model_set_conditional_precision": (ctypes.c_int, [c_vp, ctypes.c_int32]),
+    "cgs_model_region_histogram": (ctypes.c_int, [c_vp, c_vp, c_i64p]),
+    "cgs_model_verify_counts": (ctypes.c_int, [c_vp, c_vp, c_i64p]),
+    "cgs_model_state_hash": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_uint64)]),
+    "cgs_model_allreduce_delta": (ctypes.c_int, [c_vp, c_vp]),
+    "cgs_nccl_unique_id": (ctypes.c_int, [c_vp]),
+    "cgs_nccl_comm_create": (ctypes.c_int, [ctypes.POINTER(c_vp), ctypes.c_int, ctypes.c_int32, ctypes.c_int32, c_vp]),
+    "cgs_nccl_comm_destroy": (ctypes.c_int, [c_vp]),
+    "cgs_model_exchange_arena": (ctypes.c_int, [c_vp, ctypes.POINTER(c_vp), ctypes.POINTER(ctypes.c_size_t)]),
+    "cgs_model_exchange_open": (ctypes.c_int, [c_vp, ctypes.POINTER(c_vp), ctypes.c_int32, ctypes.c_int32]),
+    "cgs_model_exchange_round": (ctypes.c_int, [c_vp, ctypes.c_int32]),
+    "cgs_model_exchange_wait": (ctypes.c_int, [c_vp]),
+    "cgs_model_exchange_status": (ctypes.c_int, [c_vp, c_i32p]),
     "cgs_ipc_export": (ctypes.c_int, [c_vp, c_vp]),
     "cgs_ipc_open": (ctypes.c_int, [ctypes.c_int, c_vp, ctypes.POINTER(c_vp)]),
     "cgs_ipc_close": (ctypes.c_int, [ctypes.c_int, c_vp]),

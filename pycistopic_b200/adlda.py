@@ -13,6 +13,12 @@ of a sweep) the ranks exchange their ``n_wk`` deltas:
 * ``exchange="peer"``: every rank maps the other ranks' delta buffers (CUDA IPC) and ONE kernel
   reads them over NVLink, reduces, applies and rebuilds ``n_k``; NCCL only provides the two
   stream-ordered barriers around it.
+* ``exchange="nccl_abi"``: the same three steps as ``"nccl"`` but entirely behind the C ABI
+  (``cgs_model_allreduce_delta`` with the process group's ``ncclComm_t``), what a non-Python host calls.
+* ``exchange="async"``: the fused peer-memory round kernel (``csrc/exchange_kernels.cuh``) on a
+  high-priority stream BESIDE the sweep: the round that publishes sweep s runs while sweep s + 1
+  samples, so the exchange costs no time of its own; a rank sees the other ranks' counts one to two
+  sweeps late instead of exactly one.  ``rounds_per_sweep`` rounds are chained per sweep.
 
 The reference has no equivalent (its multi-core analogue is Mallet's per-iteration merge of
 per-thread count copies, lda_models.py:572-573).  The orchestration below is independent of the
@@ -61,9 +67,18 @@ class GpuShard:
         self.corpus = corpus
         self.model = DeviceModel(self.corpus, n_topics, alpha, eta, seed=seed, stream=self.stream.cuda_stream)
         self.exchange = exchange
+        self._seed = seed
         self._delta_t = None
         self._peers = None
         self._token = None
+
+    def set_global_size(self, n_cells, n_tokens):
+        """Must precede the model: rebuilds it so that its concurrency caps follow the whole matrix."""
+        self.corpus.set_global_size(n_cells, n_tokens)
+        m = self.model
+        from .lda import DeviceModel
+        self.model = DeviceModel(self.corpus, m.n_topics, m.alpha, m.eta, seed=self._seed, stream=self.stream.cuda_stream)
+        m.close()
 
     def init(self):
         self.model.init()
@@ -110,6 +125,41 @@ class GpuShard:
     def delta_apply_peers(self):
         self.model.delta_apply_peers(self._peers)
 
+    # -- asynchronous fused exchange (csrc/exchange_kernels.cuh) ------------------------------
+    def arena_handle(self) -> bytes:
+        import ctypes
+
+        from . import _lib
+        addr, _ = self.model.exchange_arena()
+        buf = ctypes.create_string_buffer(64)
+        _lib.check(_lib.load().cgs_ipc_export(ctypes.c_void_p(addr), buf))
+        return buf.raw
+
+    def open_arenas(self, handles, rank):
+        import ctypes
+
+        from . import _lib
+        own = self.model.exchange_arena()[0]
+        addrs = []
+        for r, h in enumerate(handles):
+            if r == rank:
+                addrs.append(own)
+            else:
+                p = ctypes.c_void_p()
+                _lib.check(_lib.load().cgs_ipc_open(self.device, ctypes.create_string_buffer(h, 64), ctypes.byref(p)))
+                addrs.append(p.value)
+        self._arenas = addrs
+        self.model.exchange_open(addrs, rank)
+
+    def exchange_round(self, n_ctas=0):
+        self.model.exchange_round(n_ctas)
+
+    def exchange_wait(self):
+        self.model.exchange_wait()
+
+    def allreduce_delta(self, comm_ptr):
+        self.model.allreduce_delta(comm_ptr)
+
     def barrier_token(self):
         if self._token is None:
             self._token = self.torch.zeros(1, dtype=self.torch.int32, device=self.torch.device("cuda", self.device))
@@ -137,14 +187,21 @@ class GpuShard:
             for a in self._peers:
                 if a != own:
                     _lib.load().cgs_ipc_close(self.device, ctypes.c_void_p(a))
+        if getattr(self, "_arenas", None) is not None:
+            self.model.sync()
+            own = self.model.exchange_arena()[0]
+            for a in self._arenas:
+                if a != own:
+                    _lib.load().cgs_ipc_close(self.device, ctypes.c_void_p(a))
         self.model.close()
         self.corpus.close()
 
 
 class Exchanger:
-    """The per-sweep n_wk exchange of one shard (see the module docstring)."""
+    """The n_wk exchange of one shard (see the module docstring).  ``fit_adlda`` calls ``before_sweep`` /
+    ``after_sweep`` around every sweep part and ``drain`` before it reads the counts."""
 
-    def __init__(self, shard, exchange="auto"):
+    def __init__(self, shard, exchange="auto", rounds_per_sweep=1, n_ctas=0):
         import torch.distributed as dist
         self.dist = dist
         self.shard = shard
@@ -153,24 +210,71 @@ class Exchanger:
         self.rank = dist.get_rank() if distributed else 0
         if exchange == "auto":
             exchange = "peer" if self.world == 2 else "nccl"
+        self.mode = exchange
+        self.rounds_per_sweep = max(1, int(rounds_per_sweep))
+        self.n_ctas = n_ctas
+        self._dirty = True  # sweeps (or the initial counts) not yet published
         self.use_peer = exchange == "peer" and self.world > 1 and hasattr(shard, "ipc_handle")
+        self.use_async = exchange == "async" and hasattr(shard, "arena_handle")
+        self.comm_ptr = None
         if self.use_peer:
             handles = [None] * self.world
             dist.all_gather_object(handles, shard.ipc_handle())
             shard.open_peers(handles, self.rank)
+        elif self.use_async:
+            handles = [shard.arena_handle()]
+            if self.world > 1:
+                handles = [None] * self.world
+                dist.all_gather_object(handles, shard.arena_handle())
+            shard.open_arenas(handles, self.rank)
+            if self.world > 1:
+                dist.barrier()  # every arena is mapped (and zeroed) before the first round touches a peer
+        elif exchange == "nccl_abi" and self.world > 1 and hasattr(shard, "allreduce_delta"):
+            backend = dist.distributed_c10d._get_default_group()._get_backend(shard.torch.device("cuda", shard.device))
+            # the communicator is created lazily by the first collective
+            dist.all_reduce(shard.barrier_token())
+            self.comm_ptr = backend._comm_ptr()
 
     def step(self):
+        """One synchronous exchange: complete (on the stream) before anything enqueued afterwards."""
         shard, dist = self.shard, self.dist
-        shard.delta_compute()
-        if self.world == 1:
-            shard.delta_apply()
-        elif self.use_peer:
-            dist.all_reduce(shard.barrier_token())   # every rank's delta is complete
-            shard.delta_apply_peers()
-            dist.all_reduce(shard.barrier_token())   # every rank has read every delta
+        if self.use_async:
+            shard.exchange_round(self.n_ctas)
+            shard.exchange_wait()
+        elif self.comm_ptr is not None:
+            shard.allreduce_delta(self.comm_ptr)
         else:
-            dist.all_reduce(shard.delta_tensor())
-            shard.delta_apply()
+            shard.delta_compute()
+            if self.world == 1:
+                shard.delta_apply()
+            elif self.use_peer:
+                dist.all_reduce(shard.barrier_token())   # every rank's delta is complete
+                shard.delta_apply_peers()
+                dist.all_reduce(shard.barrier_token())   # every rank has read every delta
+            else:
+                dist.all_reduce(shard.delta_tensor())
+                shard.delta_apply()
+        self._dirty = False
+
+    def before_sweep(self):
+        if self.use_async:
+            # publishes everything up to the previous sweep while the next one samples
+            for _ in range(self.rounds_per_sweep):
+                self.shard.exchange_round(self.n_ctas)
+            self._dirty = True
+
+    def after_sweep(self):
+        if self.use_async:
+            self._dirty = True
+        else:
+            self.step()
+
+    def drain(self):
+        """All replicas identical and complete (needed before log-likelihoods and exports)."""
+        if self.use_async and self._dirty:
+            self.step()
+        elif self.use_async:
+            self.shard.exchange_wait()
 
 
 class AdLdaResult:
@@ -178,7 +282,7 @@ class AdLdaResult:
 
 
 def fit_adlda(binary_matrix, n_topics, n_iter=150, alpha=0.1, eta=0.01, random_state=555, refresh=None,
-              sync_per_sweep=1, exchange="auto", shard_factory=None, device=None, on_sweep=None):
+              sync_per_sweep=1, exchange="auto", shard_factory=None, device=None, on_sweep=None, rounds_per_sweep=1):
     """Fit ONE model with the cells of ``binary_matrix`` (scipy CSR, regions x cells -- the
     layout of ``CistopicObject.binary_matrix``) sharded over the ranks of the default process
     group.  ``alpha`` / ``eta`` are the values the sampler uses.  Returns, on every rank, an object
@@ -189,8 +293,8 @@ def fit_adlda(binary_matrix, n_topics, n_iter=150, alpha=0.1, eta=0.01, random_s
     distributed = dist.is_available() and dist.is_initialized()
     world = dist.get_world_size() if distributed else 1
     rank = dist.get_rank() if distributed else 0
-    if exchange not in ("auto", "nccl", "peer"):
-        raise ValueError("exchange must be 'auto', 'nccl' or 'peer'")
+    if exchange not in ("auto", "nccl", "peer", "nccl_abi", "async"):
+        raise ValueError("exchange must be 'auto', 'nccl', 'nccl_abi', 'peer' or 'async'")
     if sync_per_sweep < 1:
         raise ValueError("sync_per_sweep must be >= 1")
     M = sparse.csr_matrix(binary_matrix)
@@ -210,11 +314,13 @@ def fit_adlda(binary_matrix, n_topics, n_iter=150, alpha=0.1, eta=0.01, random_s
             return GpuShard(*a, device=device, exchange=exchange)
     shard = shard_factory(M, (cb, ce), token_offset, n_topics, alpha, eta, random_state)
     try:
+        if hasattr(shard, "set_global_size"):
+            shard.set_global_size(D, int(cell_ptr[-1]))
         shard.init()
-        exchanger = Exchanger(shard, exchange)
-        exchange_step = exchanger.step
+        exchanger = Exchanger(shard, exchange, rounds_per_sweep=rounds_per_sweep)
 
         def loglik():
+            exchanger.drain()
             cells = shard.loglik_cells()
             if world > 1:
                 parts = [None] * world
@@ -222,7 +328,7 @@ def fit_adlda(binary_matrix, n_topics, n_iter=150, alpha=0.1, eta=0.01, random_s
                 cells = float(np.sum(parts))
             return cells + shard.loglik_regions()
 
-        exchange_step()  # local init counts -> global n_wk / n_k on every rank
+        exchanger.step()  # local init counts -> global n_wk / n_k on every rank
         res = AdLdaResult()
         res.loglikelihoods_ = []
         refresh = n_iter if refresh is None else max(1, int(refresh))
@@ -230,11 +336,13 @@ def fit_adlda(binary_matrix, n_topics, n_iter=150, alpha=0.1, eta=0.01, random_s
             if it % refresh == 0:
                 res.loglikelihoods_.append(loglik())
             for part in range(sync_per_sweep):
+                exchanger.before_sweep()
                 shard.sweep_part(part, sync_per_sweep)
-                exchange_step()
+                exchanger.after_sweep()
             if on_sweep is not None:
                 on_sweep(it, shard)
         res.final_loglikelihood_ = loglik()
+        exchanger.drain()
         nzw, ndz_local, nz = shard.export()
         if world > 1:
             shards = [None] * world

@@ -11,8 +11,12 @@
 #include <type_traits>
 #include <vector>
 
+#include <dlfcn.h>
+#include <nvtx3/nvToolsExt.h>
+
 #include "common.cuh"
 #include "corpus_kernels.cuh"
+#include "exchange_kernels.cuh"
 #include "fragment_kernels.cuh"
 #include "impute_kernels.cuh"
 #include "metrics_kernels.cuh"
@@ -291,6 +295,8 @@ struct cgs_corpus {
     int32_t n_cells = 0, n_regions = 0;
     int64_t n_tokens = 0;
     int64_t token_offset = 0;
+    // size of the WHOLE matrix when this corpus is one shard of it (cgs_corpus_set_global_size; 0 = not a shard)
+    int64_t global_cells = 0, global_tokens = 0;
     int64_t *d_cell_ptr = nullptr;    // D+1
     int32_t *d_tok_region = nullptr;  // N
     int32_t *d_cell_order = nullptr;  // D, longest cell first
@@ -328,6 +334,21 @@ struct cgs_model {
     int max_blocks = 0;   // user override, 0 = automatic
     int auto_blocks = 1 << 30;  // concurrency cap chosen by pick_sweep_shape
     int sweep_blocks = 0;
+    // deterministic mode (cgs_model_set_deterministic): sweeps read copies of n_wk / n_k taken at the start of
+    // each of det_parts sub-sweeps, one warp per cell
+    bool fp64 = false;  // conditional in double (A/B build, cgs_model_set_conditional_precision)
+    int det_parts = 0;
+    int32_t *d_nwk_ro = nullptr, *d_nk_ro = nullptr;
+    // asynchronous peer-memory exchange (cgs_model_exchange_*): arena = [delta | total | flags]
+    char *d_arena = nullptr;
+    size_t arena_bytes = 0;
+    ExchangePeers xpeers;
+    int x_ranks = 0, x_rank = 0;
+    uint32_t x_round = 0;
+    cudaStream_t x_stream = nullptr;
+    cudaEvent_t x_event = nullptr, x_done = nullptr;
+    bool x_pending = false;
+    int64_t x_launches = 0;
 };
 
 namespace cgs {
@@ -579,6 +600,14 @@ int cgs_corpus_set_token_offset(cgs_corpus *c, int64_t off) {
     return 0;
 }
 
+int cgs_corpus_set_global_size(cgs_corpus *c, int64_t n_cells_global, int64_t n_tokens_global) {
+    if (!c) CGS_FAIL("NULL corpus");
+    if (n_cells_global < c->n_cells || n_tokens_global < c->n_tokens) CGS_FAIL("global size smaller than the shard");
+    c->global_cells = n_cells_global;
+    c->global_tokens = n_tokens_global;
+    return 0;
+}
+
 int cgs_corpus_export_tokens(const cgs_corpus *c, int32_t *WS, int32_t *DS) {
     if (!c) CGS_FAIL("NULL corpus");
     DeviceGuard g(c->device);
@@ -673,8 +702,11 @@ int cgs_model_create(cgs_model **out, cgs_corpus *corpus, int32_t n_topics, doub
         m->alpha = alpha;
         m->eta = eta;
         m->seed = seed;
-        pick_sweep_shape(m->K, m->Kp, (double)corpus->n_tokens, (double)corpus->n_cells, &m->tpt, &m->ch, &m->threads,
-                         &m->auto_blocks);
+        // The concurrency caps compare what is in flight on THIS device with the statistics it is sampled against,
+        // i.e. with the whole matrix: a shard of an AD-LDA run passes the global sizes.
+        const double cap_tokens = (double)std::max<int64_t>(corpus->n_tokens, corpus->global_tokens);
+        const double cap_cells = (double)std::max<int64_t>(corpus->n_cells, corpus->global_cells);
+        pick_sweep_shape(m->K, m->Kp, cap_tokens, cap_cells, &m->tpt, &m->ch, &m->threads, &m->auto_blocks);
         if (stream) {
             m->stream = (cudaStream_t)stream;
         } else {
@@ -706,6 +738,11 @@ int cgs_model_destroy(cgs_model *m) {
     DeviceGuard g(m->corpus->device);
     if (m->stream) cudaStreamSynchronize(m->stream);
     dfree(m->d_z, m->stream); dfree(m->d_nwk, m->stream); dfree(m->d_ndk, m->stream); dfree(m->d_nk, m->stream);
+    if (m->x_stream) { cudaStreamSynchronize(m->x_stream); cudaStreamDestroy(m->x_stream); }
+    if (m->x_event) cudaEventDestroy(m->x_event);
+    if (m->x_done) cudaEventDestroy(m->x_done);
+    cudaFree(m->d_arena);
+    dfree(m->d_nwk_ro, m->stream); dfree(m->d_nk_ro, m->stream);
     cudaFree(m->d_snap); cudaFree(m->d_delta); dfree(m->d_work, m->stream); dfree(m->d_partials, m->stream); dfree(m->d_flag, m->stream);
     if (m->owns_stream && m->stream) cudaStreamDestroy(m->stream);
     m->corpus->n_models--;
@@ -796,32 +833,41 @@ int cgs_model_get_z(cgs_model *m, int32_t *z) {
 }  // extern "C"
 
 // ---- sweep dispatch --------------------------------------------------------------------------
-template <int TPT, int CH>
+template <int TPT, int CH, typename R>
 static int launch_sweep(cgs_model *m, const SweepParams &p, int *blocks_cache) {
     if (*blocks_cache == 0) {
         int per_sm = 0;
-        CGS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep_kernel<TPT, CH>, m->threads, 0));
+        CGS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep_kernel<TPT, CH, R>, m->threads, 0));
         if (per_sm < 1) per_sm = 1;
         *blocks_cache = m->corpus->num_sms * per_sm;
     }
     int blocks = std::max(1, std::min(*blocks_cache, m->corpus->n_cells));
     blocks = std::min(blocks, m->max_blocks > 0 ? m->max_blocks : m->auto_blocks);
-    sweep_kernel<TPT, CH><<<blocks, m->threads, 0, m->stream>>>(p);
+    sweep_kernel<TPT, CH, R><<<blocks, m->threads, 0, m->stream>>>(p);
     CGS_CUDA(cudaGetLastError());
     return 0;
 }
 
 template <int TPT>
 static int dispatch_ch(cgs_model *m, const SweepParams &p, int *bc) {
+    if (m->fp64) {  // the A/B build exists for at most 4 chunks per lane (cgs_model_set_conditional_precision re-shapes)
+        switch (m->ch) {
+            case 1: return launch_sweep<TPT, 1, double>(m, p, bc);
+            case 2: return launch_sweep<TPT, 2, double>(m, p, bc);
+            case 3: return launch_sweep<TPT, 3, double>(m, p, bc);
+            case 4: return launch_sweep<TPT, 4, double>(m, p, bc);
+        }
+        CGS_FAIL("unsupported chunk count for the fp64 conditional");
+    }
     switch (m->ch) {
-        case 1: return launch_sweep<TPT, 1>(m, p, bc);
-        case 2: return launch_sweep<TPT, 2>(m, p, bc);
-        case 3: return launch_sweep<TPT, 3>(m, p, bc);
-        case 4: return launch_sweep<TPT, 4>(m, p, bc);
-        case 5: if (TPT <= 16) return launch_sweep<(TPT <= 16 ? TPT : 16), 5>(m, p, bc); break;
-        case 6: if (TPT <= 16) return launch_sweep<(TPT <= 16 ? TPT : 16), 6>(m, p, bc); break;
-        case 7: if (TPT <= 16) return launch_sweep<(TPT <= 16 ? TPT : 16), 7>(m, p, bc); break;
-        case 8: if (TPT <= 16) return launch_sweep<(TPT <= 16 ? TPT : 16), 8>(m, p, bc); break;
+        case 1: return launch_sweep<TPT, 1, float>(m, p, bc);
+        case 2: return launch_sweep<TPT, 2, float>(m, p, bc);
+        case 3: return launch_sweep<TPT, 3, float>(m, p, bc);
+        case 4: return launch_sweep<TPT, 4, float>(m, p, bc);
+        case 5: if (TPT <= 16) return launch_sweep<(TPT <= 16 ? TPT : 16), 5, float>(m, p, bc); break;
+        case 6: if (TPT <= 16) return launch_sweep<(TPT <= 16 ? TPT : 16), 6, float>(m, p, bc); break;
+        case 7: if (TPT <= 16) return launch_sweep<(TPT <= 16 ? TPT : 16), 7, float>(m, p, bc); break;
+        case 8: if (TPT <= 16) return launch_sweep<(TPT <= 16 ? TPT : 16), 8, float>(m, p, bc); break;
     }
     CGS_FAIL("unsupported chunk count");
 }
@@ -863,8 +909,11 @@ static int sweep_impl(cgs_model *m, int32_t n_sweeps, int32_t part, int32_t n_pa
     p.tok_region = c->d_tok_region;
     p.z = m->d_z;
     p.n_wk = m->d_nwk;
+    p.n_wk_read = m->d_nwk;
+    p.nwk_write_delta = 0;
     p.n_dk = m->d_ndk;
     p.n_k = m->d_nk;
+    p.n_k_read = m->d_nk;
     p.cell_order = c->d_cell_order;
     p.n_cells = c->n_cells;
     p.K = m->K;
@@ -872,6 +921,9 @@ static int sweep_impl(cgs_model *m, int32_t n_sweeps, int32_t part, int32_t n_pa
     p.alpha = (float)m->alpha;
     p.eta = (float)m->eta;
     p.etaW = (float)(m->eta * (double)c->n_regions);
+    p.alpha64 = m->alpha;
+    p.eta64 = m->eta;
+    p.etaW64 = m->eta * (double)c->n_regions;
     p.seed_lo = (uint32_t)m->seed;
     p.seed_hi = (uint32_t)(m->seed >> 32);
     p.rng_index_mask = m->rng_period == 0 ? ~0ull : (uint64_t)(m->rng_period / 4 - 1);
@@ -891,19 +943,42 @@ static int sweep_impl(cgs_model *m, int32_t n_sweeps, int32_t part, int32_t n_pa
     p.part = part;
     p.n_parts = n_parts;
     p.visit_counter = m->d_visits;
-    for (int32_t s = 0; s < n_sweeps; ++s) {
-        const int slot = (int)(m->work_slot % kWorkSlots);
-        if (slot == 0) {
-            // a fresh bank of queue counters (stream-ordered after every launch that used the last one)
-            CGS_CUDA(cudaMemsetAsync(m->d_work, 0, sizeof(int32_t) * kWorkSlots, m->stream));
+    const bool det = m->det_parts > 0;
+    const size_t WKp = (size_t)c->n_regions * (size_t)m->Kp;
+    if (det) {
+        if (n_parts != 1) CGS_FAIL("cgs_model_sweep_part is not available in deterministic mode");
+        if (!m->d_nwk_ro) {
+            CGS_TRY(dmalloc(&m->d_nwk_ro, WKp, m->stream));
+            CGS_TRY(dmalloc(&m->d_nk_ro, (size_t)m->Kp, m->stream));
         }
-        m->work_slot += 1;
-        p.work_counter = m->d_work + slot;
-        p.sweep = (uint32_t)m->sweeps;  // all parts of one sweep share the Philox sweep index
-        CGS_TRY(dispatch_sweep(m, p));
-        m->launches += 1;
-        if (part == n_parts - 1) m->sweeps += 1;
+        p.n_wk_read = m->d_nwk_ro;
+        p.nwk_write_delta = (int64_t)((const char *)m->d_nwk - (const char *)m->d_nwk_ro);
+        p.n_k_read = m->d_nk_ro;
+        p.refresh_every = 0x7fffffff;  // the totals a cell works with are those of the copy
+        p.n_parts = m->det_parts;
     }
+    nvtxRangePushA("cgs_model_sweep");
+    for (int32_t s = 0; s < n_sweeps; ++s) {
+        for (int32_t dp = 0; dp < (det ? m->det_parts : 1); ++dp) {
+            if (det) {
+                p.part = dp;
+                CGS_CUDA(cudaMemcpyAsync(m->d_nwk_ro, m->d_nwk, WKp * 4, cudaMemcpyDeviceToDevice, m->stream));
+                CGS_CUDA(cudaMemcpyAsync(m->d_nk_ro, m->d_nk, (size_t)m->Kp * 4, cudaMemcpyDeviceToDevice, m->stream));
+            }
+            const int slot = (int)(m->work_slot % kWorkSlots);
+            if (slot == 0) {
+                // a fresh bank of queue counters (stream-ordered after every launch that used the last one)
+                CGS_CUDA(cudaMemsetAsync(m->d_work, 0, sizeof(int32_t) * kWorkSlots, m->stream));
+            }
+            m->work_slot += 1;
+            p.work_counter = m->d_work + slot;
+            p.sweep = (uint32_t)m->sweeps;  // all parts of one sweep share the Philox sweep index
+            CGS_TRY(dispatch_sweep(m, p));
+            m->launches += 1;
+        }
+        if (det || part == n_parts - 1) m->sweeps += 1;
+    }
+    nvtxRangePop();
     return 0;
 }
 
@@ -1217,6 +1292,300 @@ int cgs_ipc_close(int device, void *device_ptr) {
     DeviceGuard g(device);
     if (!g.ok) CGS_FAIL("cannot select CUDA device");
     CGS_CUDA(cudaIpcCloseMemHandle(device_ptr));
+    return 0;
+}
+
+
+// ---- precision of the conditional (A/B) ------------------------------------------------------------
+int cgs_model_set_conditional_precision(cgs_model *m, int32_t bits) {
+    if (!m) CGS_FAIL("NULL model");
+    if (bits != 32 && bits != 64) CGS_FAIL("bits must be 32 or 64");
+    m->fp64 = bits == 64;
+    m->sweep_blocks = 0;
+    if (m->fp64 && m->ch > 4) {  // the fp64 kernels are built for <= 4 chunks per lane: widen the token group
+        const int chunks = (m->K + 3) / 4;
+        while (m->tpt < 32 && (chunks + m->tpt - 1) / m->tpt > 4) m->tpt <<= 1;
+        m->ch = (chunks + m->tpt - 1) / m->tpt;
+        if (m->ch > 4) CGS_FAIL("n_topics too large for the fp64 conditional");
+    }
+    return 0;
+}
+
+// ---- deterministic mode --------------------------------------------------------------------------
+int cgs_model_set_deterministic(cgs_model *m, int32_t parts) {
+    if (!m) CGS_FAIL("NULL model");
+    if (parts < 0 || parts > 1024) CGS_FAIL("parts must be in [0, 1024]");
+    if (parts > 0 && m->det_parts == 0) {
+        m->threads = 32;  // one warp per cell: nothing a cell reads depends on another warp's timing
+        m->sweep_blocks = 0;
+        m->auto_blocks = 1 << 30;
+    } else if (parts == 0 && m->det_parts > 0) {
+        const cgs_corpus *c = m->corpus;
+        pick_sweep_shape(m->K, m->Kp, (double)std::max<int64_t>(c->n_tokens, c->global_tokens),
+                         (double)std::max<int64_t>(c->n_cells, c->global_cells), &m->tpt, &m->ch, &m->threads,
+                         &m->auto_blocks);
+        m->sweep_blocks = 0;
+    }
+    m->det_parts = parts;
+    return 0;
+}
+
+// ---- consistency checks (bench.py runs them after its timed regions) -------------------------------
+int cgs_model_region_histogram(cgs_model *m, int32_t *d_hist, int64_t *ndk_mismatches) {
+    if (!m || !d_hist) CGS_FAIL("NULL argument");
+    cgs_corpus *c = m->corpus;
+    DeviceGuard g(c->device);
+    const size_t WKp = (size_t)c->n_regions * (size_t)m->Kp;
+    unsigned long long *d_bad = nullptr;
+    CGS_TRY(dmalloc(&d_bad, 2, m->stream));
+    CGS_CUDA(cudaMemsetAsync(d_bad, 0, 2 * sizeof(unsigned long long), m->stream));
+    CGS_CUDA(cudaMemsetAsync(d_hist, 0, WKp * 4, m->stream));
+    const int blocks = std::max(1, std::min(c->n_cells, c->num_sms * 8));
+    recount_kernel<<<blocks, 256, sizeof(int) * (size_t)m->Kp, m->stream>>>(c->d_cell_ptr, c->d_tok_region, m->d_z, c->n_cells,
+                                                                           m->K, m->Kp, m->d_ndk, d_hist, d_bad);
+    CGS_CUDA(cudaGetLastError());
+    m->launches += 1;
+    unsigned long long bad[2] = {0, 0};
+    CGS_CUDA(cgs_memcpy_sync(m->stream, bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost));
+    dfree(d_bad, m->stream);
+    if (ndk_mismatches) *ndk_mismatches = (int64_t)bad[0];
+    return 0;
+}
+
+int cgs_model_verify_counts(cgs_model *m, const int32_t *d_hist, int64_t *out3) {
+    if (!m || !out3) CGS_FAIL("NULL argument");
+    cgs_corpus *c = m->corpus;
+    DeviceGuard g(c->device);
+    const size_t WKp = (size_t)c->n_regions * (size_t)m->Kp;
+    int32_t *own_hist = nullptr;
+    out3[0] = 0;
+    if (!d_hist) {
+        CGS_TRY(dmalloc(&own_hist, WKp, m->stream));
+        int rc = cgs_model_region_histogram(m, own_hist, &out3[0]);
+        if (rc != 0) { dfree(own_hist, m->stream); return rc; }
+        d_hist = own_hist;
+    }
+    unsigned long long *d_bad = nullptr;
+    long long *d_col = nullptr;
+    CGS_TRY(dmalloc(&d_bad, 2, m->stream));
+    CGS_TRY(dmalloc(&d_col, (size_t)m->Kp, m->stream));
+    CGS_CUDA(cudaMemsetAsync(d_bad, 0, 2 * sizeof(unsigned long long), m->stream));
+    CGS_CUDA(cudaMemsetAsync(d_col, 0, sizeof(long long) * (size_t)m->Kp, m->stream));
+    compare_counts_kernel<<<c->num_sms * 4, 256, sizeof(long long) * (size_t)m->Kp, m->stream>>>(
+        m->d_nwk, d_hist, (int64_t)WKp, m->Kp, d_bad, d_col);
+    CGS_CUDA(cudaGetLastError());
+    m->launches += 1;
+    unsigned long long bad[2];
+    std::vector<long long> col((size_t)m->Kp);
+    std::vector<int32_t> nk((size_t)m->Kp);
+    CGS_CUDA(cudaMemcpyAsync(bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost, m->stream));
+    CGS_CUDA(cudaMemcpyAsync(col.data(), d_col, sizeof(long long) * col.size(), cudaMemcpyDeviceToHost, m->stream));
+    CGS_CUDA(cudaMemcpyAsync(nk.data(), m->d_nk, sizeof(int32_t) * nk.size(), cudaMemcpyDeviceToHost, m->stream));
+    CGS_CUDA(cudaStreamSynchronize(m->stream));
+    dfree(d_bad, m->stream); dfree(d_col, m->stream); dfree(own_hist, m->stream);
+    out3[1] = (int64_t)bad[1];
+    out3[2] = 0;
+    for (int k = 0; k < m->Kp; ++k)
+        if (col[(size_t)k] != (long long)nk[(size_t)k]) out3[2] += 1;
+    return 0;
+}
+
+int cgs_model_state_hash(cgs_model *m, uint64_t *out4) {
+    if (!m || !out4) CGS_FAIL("NULL argument");
+    cgs_corpus *c = m->corpus;
+    DeviceGuard g(c->device);
+    unsigned long long *d_out = nullptr;
+    CGS_TRY(dmalloc(&d_out, 4, m->stream));
+    CGS_CUDA(cudaMemsetAsync(d_out, 0, 4 * sizeof(unsigned long long), m->stream));
+    state_hash_kernel<<<c->num_sms * 4, 256, 0, m->stream>>>(m->d_nwk, (int64_t)c->n_regions * m->Kp, d_out);
+    state_hash_kernel<<<1, 256, 0, m->stream>>>(m->d_nk, (int64_t)m->Kp, d_out + 2);
+    CGS_CUDA(cudaGetLastError());
+    m->launches += 2;
+    unsigned long long h[4];
+    CGS_CUDA(cgs_memcpy_sync(m->stream, h, d_out, sizeof h, cudaMemcpyDeviceToHost));
+    dfree(d_out, m->stream);
+    out4[0] = h[0]; out4[1] = h[1]; out4[2] = h[3]; out4[3] = h[2];  // hash(n_wk), sum(n_wk), sum(n_k), hash(n_k)
+    return 0;
+}
+
+// ---- asynchronous peer-memory exchange (exchange_kernels.cuh) -----------------------------------------
+static size_t arena_delta_bytes(const cgs_model *m) {
+    return (size_t)m->corpus->n_regions * (size_t)m->Kp * 4;
+}
+
+int cgs_model_exchange_arena(cgs_model *m, void **ptr, size_t *bytes) {
+    if (!m || !ptr || !bytes) CGS_FAIL("NULL argument");
+    DeviceGuard g(m->corpus->device);
+    if (!m->d_arena) {
+        const size_t wk = arena_delta_bytes(m);
+        m->arena_bytes = 2 * wk + kExchangeFlagWords * 4;
+        CGS_CUDA(cudaMalloc((void **)&m->d_arena, m->arena_bytes));
+        CGS_CUDA(cudaMemsetAsync(m->d_arena, 0, m->arena_bytes, m->stream));
+        CGS_TRY(ensure_exchange_buffers(m));  // snap (zero: the first round then publishes the local counts)
+        CGS_CUDA(cudaMemsetAsync(m->d_snap, 0, wk, m->stream));
+        CGS_CUDA(cudaStreamSynchronize(m->stream));
+    }
+    *ptr = m->d_arena;
+    *bytes = m->arena_bytes;
+    return 0;
+}
+
+int cgs_model_exchange_open(cgs_model *m, void *const *peer_arena, int32_t n_ranks, int32_t rank) {
+    if (!m || !peer_arena) CGS_FAIL("NULL argument");
+    if (n_ranks < 1 || n_ranks > kMaxExchangeRanks || rank < 0 || rank >= n_ranks) CGS_FAIL("bad n_ranks / rank");
+    DeviceGuard g(m->corpus->device);
+    void *own = nullptr;
+    size_t bytes = 0;
+    CGS_TRY(cgs_model_exchange_arena(m, &own, &bytes));
+    const size_t wk = arena_delta_bytes(m);
+    memset(&m->xpeers, 0, sizeof m->xpeers);
+    for (int q = 0; q < n_ranks; ++q) {
+        char *base = (char *)(q == rank ? own : peer_arena[q]);
+        if (!base) CGS_FAIL("NULL peer arena");
+        m->xpeers.delta[q] = (int4 *)base;
+        m->xpeers.total[q] = (int4 *)(base + wk);
+        m->xpeers.flags[q] = (uint32_t *)(base + 2 * wk);
+    }
+    m->x_ranks = n_ranks;
+    m->x_rank = rank;
+    m->x_round = 0;
+    if (!m->x_stream) {
+        int lo = 0, hi = 0;
+        CGS_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CGS_CUDA(cudaStreamCreateWithPriority(&m->x_stream, cudaStreamNonBlocking, hi));
+        CGS_CUDA(cudaEventCreateWithFlags(&m->x_event, cudaEventDisableTiming));
+        CGS_CUDA(cudaEventCreateWithFlags(&m->x_done, cudaEventDisableTiming));
+    }
+    return 0;
+}
+
+int cgs_model_exchange_round(cgs_model *m, int32_t n_ctas) {
+    if (!m) CGS_FAIL("NULL model");
+    if (m->x_ranks < 1) CGS_FAIL("cgs_model_exchange_open has not been called");
+    cgs_corpus *c = m->corpus;
+    DeviceGuard g(c->device);
+    if (n_ctas <= 0) n_ctas = 64;
+    n_ctas = std::min(n_ctas, c->num_sms);
+    ExchangeParams p;
+    p.n_wk = m->d_nwk;
+    p.snap = m->d_snap;
+    p.n_k = m->d_nk;
+    p.peers = m->xpeers;
+    p.n_ranks = m->x_ranks;
+    p.rank = m->x_rank;
+    p.n4 = (int64_t)c->n_regions * m->Kp / 4;
+    p.Kp4 = m->Kp / 4;
+    p.round = ++m->x_round;
+    nvtxRangePushA("cgs_model_exchange_round");
+    // the round starts once everything enqueued on the model's stream so far has finished, and then runs BESIDE
+    // whatever the caller enqueues there next (the next sweep)
+    CGS_CUDA(cudaEventRecord(m->x_event, m->stream));
+    CGS_CUDA(cudaStreamWaitEvent(m->x_stream, m->x_event, 0));
+    exchange_round_kernel<<<n_ctas, kExchangeThreads, sizeof(int) * (size_t)m->Kp, m->x_stream>>>(p);
+    CGS_CUDA(cudaGetLastError());
+    CGS_CUDA(cudaEventRecord(m->x_done, m->x_stream));
+    nvtxRangePop();
+    m->x_pending = true;
+    m->launches += 1;
+    m->x_launches += 1;
+    return 0;
+}
+
+int cgs_model_exchange_wait(cgs_model *m) {
+    if (!m) CGS_FAIL("NULL model");
+    DeviceGuard g(m->corpus->device);
+    if (m->x_pending) {
+        CGS_CUDA(cudaStreamWaitEvent(m->stream, m->x_done, 0));
+        m->x_pending = false;
+    }
+    return 0;
+}
+
+int cgs_model_exchange_status(cgs_model *m, int32_t *timeouts) {
+    if (!m || !timeouts) CGS_FAIL("NULL argument");
+    DeviceGuard g(m->corpus->device);
+    *timeouts = 0;
+    if (!m->d_arena) return 0;
+    if (m->x_stream) CGS_CUDA(cudaStreamSynchronize(m->x_stream));
+    uint32_t v = 0;
+    const char *flags = m->d_arena + 2 * arena_delta_bytes(m);
+    CGS_CUDA(cudaMemcpy(&v, flags + (2 * kMaxExchangeRanks + 2) * 4, 4, cudaMemcpyDeviceToHost));
+    *timeouts = (int32_t)v;
+    return 0;
+}
+
+// ---- NCCL behind the ABI (cgs_allreduce_delta) -------------------------------------------
+// The library does not link NCCL: the entry points are resolved at first use from the libnccl.so.2 the host
+// process has already loaded (torch's) or that the loader finds.  Only the few signatures used are declared.
+struct NcclId128 { char bytes[128]; };  // ncclUniqueId (passed by value to ncclCommInitRank)
+struct NcclApi {
+    void *lib = nullptr;
+    int (*GetUniqueId)(void *) = nullptr;
+    int (*CommInitRank)(void **, int, NcclId128, int) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+
+static int nccl_api() {
+    if (g_nccl.lib) return 0;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) CGS_FAIL(std::string("cannot load libnccl.so.2: ") + dlerror());
+    g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(h, "ncclCommInitRank");
+    g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(h, "ncclCommDestroy");
+    g_nccl.AllReduce = (decltype(g_nccl.AllReduce))dlsym(h, "ncclAllReduce");
+    g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(h, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllReduce || !g_nccl.GetErrorString)
+        CGS_FAIL("libnccl.so.2 lacks an expected entry point");
+    g_nccl.lib = h;
+    return 0;
+}
+#define CGS_NCCL(expr)                                                                                       \
+    do {                                                                                                     \
+        int _r = (expr);                                                                                     \
+        if (_r != 0) return ::cgs::fail(__FILE__, __LINE__, std::string(#expr) + ": " + g_nccl.GetErrorString(_r)); \
+    } while (0)
+
+int cgs_nccl_unique_id(void *id_out_128_bytes) {
+    if (!id_out_128_bytes) CGS_FAIL("NULL argument");
+    CGS_TRY(nccl_api());
+    CGS_NCCL(g_nccl.GetUniqueId(id_out_128_bytes));
+    return 0;
+}
+
+int cgs_nccl_comm_create(void **comm, int device, int32_t n_ranks, int32_t rank, const void *id_128_bytes) {
+    if (!comm || !id_128_bytes) CGS_FAIL("NULL argument");
+    CGS_TRY(nccl_api());
+    DeviceGuard g(device);
+    if (!g.ok) CGS_FAIL("cannot select CUDA device");
+    NcclId128 id;
+    memcpy(&id, id_128_bytes, sizeof id);
+    CGS_NCCL(g_nccl.CommInitRank(comm, n_ranks, id, rank));
+    return 0;
+}
+
+int cgs_nccl_comm_destroy(void *comm) {
+    if (!comm) return 0;
+    CGS_TRY(nccl_api());
+    CGS_NCCL(g_nccl.CommDestroy(comm));
+    return 0;
+}
+
+int cgs_model_allreduce_delta(cgs_model *m, void *nccl_comm) {
+    if (!m || !nccl_comm) CGS_FAIL("NULL argument");
+    CGS_TRY(nccl_api());
+    DeviceGuard g(m->corpus->device);
+    nvtxRangePushA("cgs_model_allreduce_delta");
+    CGS_TRY(cgs_model_delta_compute(m));
+    const size_t n = (size_t)m->corpus->n_regions * (size_t)m->Kp;
+    // ncclInt32 = 2, ncclSum = 0 (nccl.h); in place on the delta buffer
+    CGS_NCCL(g_nccl.AllReduce(m->d_delta, m->d_delta, n, 2, 0, nccl_comm, m->stream));
+    CGS_TRY(cgs_model_delta_apply(m));
+    nvtxRangePop();
     return 0;
 }
 

@@ -39,9 +39,13 @@ struct SweepParams {
     const int64_t *cell_ptr;
     const int32_t *tok_region;
     uint16_t *z;
-    int32_t *n_wk;
+    int32_t *n_wk;               // receives the count updates (no-return reductions)
+    const int32_t *n_wk_read;    // rows are READ from here: n_wk itself (live counts, default) or a copy taken
+                                 // at the start of the sweep part (deterministic mode, cgs_model_set_deterministic)
+    int64_t nwk_write_delta;     // (char *)n_wk - (char *)n_wk_read
     int32_t *n_dk;
     int32_t *n_k;
+    const int32_t *n_k_read;     // same for the topic totals
     const int32_t *cell_order;
     int32_t *work_counter;
     int32_t n_cells;
@@ -50,6 +54,7 @@ struct SweepParams {
     float alpha;
     float eta;
     float etaW;
+    double alpha64, eta64, etaW64;  // the same three for the fp64 A/B build
     uint32_t seed_lo;
     uint32_t seed_hi;
     uint32_t sweep;
@@ -99,10 +104,8 @@ __device__ __forceinline__ void sts_f(uint32_t a, float v) {
 __device__ __forceinline__ void sts_i(uint32_t a, int v) {
     asm volatile("st.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
-__device__ __forceinline__ int atoms_add(uint32_t a, int v) {
-    int o;
-    asm volatile("atom.shared.add.s32 %0, [%1], %2;" : "=r"(o) : "r"(a), "r"(v) : "memory");
-    return o;
+__device__ __forceinline__ void reds_add(uint32_t a, int v) {
+    asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
 }
 __device__ __forceinline__ int atoms_exch(uint32_t a, int v) {
     int o;
@@ -114,6 +117,49 @@ __device__ __forceinline__ float rcp_approx(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
+
+// ---- the arithmetic type of the conditional ------------------------------------------------------
+// float in production.  double is the A/B build the parity tests use (cgs_model_set_conditional_precision):
+// same schedule, same random bits, same integer bookkeeping -- only the arithmetic of p(k), its running sum and
+// the inversion are carried in the reference's precision (lda._lda._sample_topics works in fp64).
+template <typename R> struct Real;
+template <> struct Real<float> {
+    static __device__ __forceinline__ void lds4(uint32_t a, float (&v)[4]) {
+        const float4 t = lds_f4(a);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+    static __device__ __forceinline__ float lds(uint32_t a) { return lds_f(a); }
+    static __device__ __forceinline__ void sts(uint32_t a, float v) { sts_f(a, v); }
+    static __device__ __forceinline__ float rcp_fast(float x) { return rcp_approx(x); }
+    static __device__ __forceinline__ float rcp(float x) { return __frcp_rn(x); }
+    static __device__ __forceinline__ float inf() { return __int_as_float(0x7f800000); }
+};
+template <> struct Real<double> {
+    static __device__ __forceinline__ void lds4(uint32_t a, double (&v)[4]) {
+        asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "r"(a));
+        asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v[2]), "=d"(v[3]) : "r"(a + 16));
+    }
+    static __device__ __forceinline__ double lds(uint32_t a) {
+        double v;
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+        return v;
+    }
+    static __device__ __forceinline__ void sts(uint32_t a, double v) {
+        asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+    }
+    static __device__ __forceinline__ double rcp_fast(double x) { return 1.0 / x; }
+    static __device__ __forceinline__ double rcp(double x) { return 1.0 / x; }
+    static __device__ __forceinline__ double inf() { return __longlong_as_double(0x7ff0000000000000ll); }
+};
+
+// Shared-memory layout of a cell: f | inv | den (KS reals each), then ndk | pub (KS ints each), then the queue slot.
+template <int TPT, int CH, typename R> struct CellSmem {
+    static constexpr int KS = TPT * CH * 4;
+    static constexpr int RB = (int)sizeof(R);
+    static constexpr uint32_t F = 0, INV = KS * RB, DEN = 2 * KS * RB, NDK = 3 * KS * RB, PUB = NDK + KS * 4,
+                              SLOT = PUB + KS * 4;
+    static constexpr int WORDS = (int)(SLOT / 4) + 4;
+};
 
 template <int TPT>
 __host__ __device__ constexpr int log2_tpt() {
@@ -133,12 +179,12 @@ __device__ __forceinline__ int rot_chunk(int c, int oc) {
 
 // Number of leading entries of the non-decreasing array cum[0..N) that are <= t: bisection
 // over registers (select trees), about N + 2 log2 N instructions instead of 2.5 N.
-template <int N>
-__device__ __forceinline__ int count_le_sorted(const float (&cum)[N], float t) {
+template <int N, typename R>
+__device__ __forceinline__ int count_le_sorted(const R (&cum)[N], R t) {
     constexpr int P = N <= 4 ? 4 : N <= 8 ? 8 : N <= 16 ? 16 : 32;
-    float a[P];
+    R a[P];
 #pragma unroll
-    for (int j = 0; j < P; ++j) a[j] = j < N ? cum[j] : __int_as_float(0x7f800000);
+    for (int j = 0; j < P; ++j) a[j] = j < N ? cum[j] : Real<R>::inf();
     int cnt = 0;
 #pragma unroll
     for (int S = P / 2; S >= 1; S >>= 1) {
@@ -166,13 +212,14 @@ __device__ __forceinline__ int pack_token(uint32_t bits, int zo, bool valid) {
 // the same registers, so the loads fly while this step scans, inverts and applies.  Returns the
 // new topic of the group's token (same value in all TPT lanes of the group).  sm = shared-memory
 // window address of f; inv, den, ndk follow at multiples of KS words.
-template <int TPT, int CH>
+template <int TPT, int CH, typename R>
 __device__ __forceinline__ int sweep_step(int4 (&buf)[CH], const char *nwk_lane, uint32_t rowbytes, int lim, int w,
                                           int pk, int w_next, int pk_next, uint32_t sm, int sub, int gbase, int lane,
-                                          float alpha, float eta, int K) {
+                                          R alpha, R eta, int K, int64_t wdelta) {
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int LOG = log2_tpt<TPT>();
-    constexpr int KSB = TPT * CH * 16;  // bytes of one shared-memory array
+    using L = CellSmem<TPT, CH, R>;
+    constexpr int RB = L::RB;
     const int zo = pk & 0x1ff;
     const bool live = (pk & 0x200) == 0;
 
@@ -180,26 +227,26 @@ __device__ __forceinline__ int sweep_step(int4 (&buf)[CH], const char *nwk_lane,
     const int ochunk = zo >> 2;
     const int oc = ochunk >> LOG;
     const int hitq = (sub == (ochunk & (TPT - 1))) ? (zo & 3) : -1;
-    const float fpp = ((float)(lds_i(sm + 3 * KSB + zo * 4) - 1) + alpha) * rcp_approx(lds_f(sm + 2 * KSB + zo * 4) - 1.0f);
+    const R fpp = ((R)(lds_i(sm + L::NDK + zo * 4) - 1) + alpha) * Real<R>::rcp_fast(Real<R>::lds(sm + L::DEN + zo * RB) - (R)1);
 
     // ---- running sum of p(k) over this lane's slots ------------------------------------------
-    float cum[CH * 4];
-    float acc = 0.0f;
+    R cum[CH * 4];
+    R acc = (R)0;
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
         const int rc = rot_chunk<CH>(c, oc);
-        const float4 fv = lds_f4(sm + sub * 16 + rc * (TPT * 16));
+        R ff[4];
+        Real<R>::lds4(sm + L::F + (sub * 4 + rc * (TPT * 4)) * RB, ff);
         const int4 nv = buf[c];
-        float x[4] = {(float)nv.x + eta, (float)nv.y + eta, (float)nv.z + eta, (float)nv.w + eta};
-        float ff[4] = {fv.x, fv.y, fv.z, fv.w};
+        R x[4] = {(R)nv.x + eta, (R)nv.y + eta, (R)nv.z + eta, (R)nv.w + eta};
         if (c == 0) {
 #pragma unroll
             for (int q = 0; q < 4; ++q)
-                if (hitq == q) { x[q] -= 1.0f; ff[q] = fpp; }
+                if (hitq == q) { x[q] -= (R)1; ff[q] = fpp; }
         }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            acc = fmaf(x[q], ff[q], acc);
+            acc = fma(x[q], ff[q], acc);
             cum[c * 4 + q] = acc;
         }
     }
@@ -217,20 +264,20 @@ __device__ __forceinline__ int sweep_step(int4 (&buf)[CH], const char *nwk_lane,
     }
 
     // ---- butterfly over the TPT lanes of the token: exclusive prefix and total -----------------
-    float excl = 0.0f, total = acc;
+    R excl = (R)0, total = acc;
     if (TPT > 1) {
 #pragma unroll
         for (int off = 1; off < TPT; off <<= 1) {
-            const float t = __shfl_xor_sync(FULL, total, off);
+            const R t = __shfl_xor_sync(FULL, total, off);
             if (sub & off) excl += t;
             total += t;
         }
     }
-    const float u = (float)((uint32_t)pk >> 10) * (1.0f / 4194304.0f);
-    const float tloc = u * total - excl;  // threshold relative to this lane
+    const R u = (R)((uint32_t)pk >> 10) * (R)(1.0 / 4194304.0);
+    const R tloc = u * total - excl;  // threshold relative to this lane
     // cum[CH*4 - 1] == acc; a lane whose acc <= tloc holds no crossing
     const bool mine = !(acc <= tloc);
-    const int cnt = count_le_sorted<CH * 4>(cum, tloc);
+    const int cnt = count_le_sorted<CH * 4, R>(cum, tloc);
     const int cand = (sub + TPT * rot_chunk<CH>(cnt >> 2, oc)) * 4 + (cnt & 3);
     int zn;
     if (TPT > 1) {
@@ -245,25 +292,29 @@ __device__ __forceinline__ int sweep_step(int4 (&buf)[CH], const char *nwk_lane,
     if (zn >= K || !live) zn = zo;  // rounding guard: padded slots carry p = 0
 
     // ---- apply the move -------------------------------------------------------------------------
+    // The cell's row is updated with integer reductions (exact, commutative); the factor f[k] is then rebuilt
+    // from a FRESH read of the count, so that when several token groups of the warp (or several warps of the
+    // CTA) move into or out of the same topic in the same step every writer stores the value of the latest
+    // count it can see instead of the one its own atomic returned.
     if (zn != zo) {
-        const char *row = nwk_lane + (uint64_t)((uint32_t)w) * rowbytes;
+        const char *row = nwk_lane + (uint64_t)((uint32_t)w) * rowbytes + wdelta;
         if (TPT > 1) {
             // lane 0 of the group retires the old topic, lane 1 installs the new one
             if (sub < 2) {
                 const int k = sub ? zn : zo;
                 const int sg = sub ? 1 : -1;
                 red_add_i32((int32_t *)const_cast<char *>(row + (k * 4 - sub * 16)), sg);
-                const int old = atoms_add(sm + 3 * KSB + k * 4, sg);
-                sts_f(sm + k * 4, ((float)(old + sg) + alpha) * lds_f(sm + KSB + k * 4));
+                reds_add(sm + L::NDK + k * 4, sg);
+                Real<R>::sts(sm + L::F + k * RB, ((R)lds_i(sm + L::NDK + k * 4) + alpha) * Real<R>::lds(sm + L::INV + k * RB));
             }
         } else {
             int32_t *rowi = (int32_t *)const_cast<char *>(row);
             red_add_i32(rowi + zo, -1);
             red_add_i32(rowi + zn, 1);
-            const int o0 = atoms_add(sm + 3 * KSB + zo * 4, -1);
-            const int o1 = atoms_add(sm + 3 * KSB + zn * 4, 1);
-            sts_f(sm + zo * 4, ((float)(o0 - 1) + alpha) * lds_f(sm + KSB + zo * 4));
-            sts_f(sm + zn * 4, ((float)(o1 + 1) + alpha) * lds_f(sm + KSB + zn * 4));
+            reds_add(sm + L::NDK + zo * 4, -1);
+            reds_add(sm + L::NDK + zn * 4, 1);
+            Real<R>::sts(sm + L::F + zo * RB, ((R)lds_i(sm + L::NDK + zo * 4) + alpha) * Real<R>::lds(sm + L::INV + zo * RB));
+            Real<R>::sts(sm + L::F + zn * RB, ((R)lds_i(sm + L::NDK + zn * 4) + alpha) * Real<R>::lds(sm + L::INV + zn * RB));
         }
     }
     return zn;
@@ -272,22 +323,22 @@ __device__ __forceinline__ int sweep_step(int4 (&buf)[CH], const char *nwk_lane,
 // Register budget (measured on B200: occupancy beats the few spills it costs; profiles/r1_shape_scan_*.txt):
 // 32 warps per SM at 64 registers up to 4 chunks per lane, 24 warps at 80 registers for 5-6 chunks, 16 warps
 // beyond.  A cell may take up to 16 warps (512 threads) for CH <= 4, 12 (384) for CH 5-6, 8 (256) beyond.
-template <int CH> struct SweepBounds {
+template <int CH, typename R = float> struct SweepBounds {
     static constexpr int kThreads = CH <= 4 ? 512 : CH <= 6 ? 384 : 256;
-    static constexpr int kMinBlocks = 2;
+    static constexpr int kMinBlocks = sizeof(R) == 8 ? 1 : 2;  // the fp64 A/B build trades occupancy for registers
 };
 
-template <int TPT, int CH>
-__global__ void __launch_bounds__(SweepBounds<CH>::kThreads, SweepBounds<CH>::kMinBlocks)
+template <int TPT, int CH, typename R = float>
+__global__ void __launch_bounds__(SweepBounds<CH, R>::kThreads, SweepBounds<CH, R>::kMinBlocks)
 sweep_kernel(const SweepParams p) {
-    constexpr int KS = TPT * CH * 4;  // topic slots covered by one token group
-    constexpr int KSB = KS * 4;
+    using L = CellSmem<TPT, CH, R>;
+    constexpr int KS = L::KS;  // topic slots covered by one token group
+    constexpr int RB = L::RB;
     constexpr unsigned FULL = 0xffffffffu;
-    // f | inv | den | ndk | pub, KS words each, then the queue slot
-    __shared__ __align__(16) uint32_t smem_w[5 * KS + 4];
+    __shared__ __align__(16) uint32_t smem_w[L::WORDS];
     const uint32_t sm = smem_u32(smem_w);
-    const uint32_t s_f = sm, s_inv = sm + KSB, s_den = sm + 2 * KSB, s_ndk = sm + 3 * KSB, s_pub = sm + 4 * KSB;
-    const uint32_t s_slot = sm + 5 * KSB;
+    const uint32_t s_f = sm + L::F, s_inv = sm + L::INV, s_den = sm + L::DEN, s_ndk = sm + L::NDK, s_pub = sm + L::PUB;
+    const uint32_t s_slot = sm + L::SLOT;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -296,11 +347,12 @@ sweep_kernel(const SweepParams p) {
     const int sub = lane & (TPT - 1);
     const int gbase = lane & ~(TPT - 1);
     const int K = p.K, Kp = p.Kp;
-    const float alpha = p.alpha, eta = p.eta;
+    const R alpha = sizeof(R) == 8 ? (R)p.alpha64 : (R)p.alpha, eta = sizeof(R) == 8 ? (R)p.eta64 : (R)p.eta;
+    const R etaW = sizeof(R) == 8 ? (R)p.etaW64 : (R)p.etaW;
     const uint32_t rowbytes = (uint32_t)Kp * 4u;
     // register chunks of this lane that hold topics (the row stride Kp may be padded beyond them)
     const int lim = (((K + 3) >> 2) - sub + TPT - 1) >> log2_tpt<TPT>();
-    const char *nwk_lane = reinterpret_cast<const char *>(p.n_wk) + sub * 16;
+    const char *nwk_lane = reinterpret_cast<const char *>(p.n_wk_read) + sub * 16;
 
     int4 buf[CH];  // the n_wk row chunks of the group sampled next
 #pragma unroll
@@ -316,15 +368,15 @@ sweep_kernel(const SweepParams p) {
         int32_t *ndk_row = p.n_dk + (int64_t)cell * Kp;
 
         for (int k = tid; k < KS; k += blockDim.x) {
-            float den = 1.0f, inv = 0.0f, f = 0.0f;
+            R den = (R)1, inv = (R)0, f = (R)0;
             int nd = 0;
             if (k < K) {
-                den = (float)ld_volatile_i32(p.n_k + k) + p.etaW;
-                inv = 1.0f / den;
+                den = (R)ld_volatile_i32(p.n_k_read + k) + etaW;
+                inv = (R)1 / den;
                 nd = ndk_row[k];
-                f = ((float)nd + alpha) * inv;
+                f = ((R)nd + alpha) * inv;
             }
-            sts_f(s_den + k * 4, den); sts_f(s_inv + k * 4, inv); sts_f(s_f + k * 4, f);
+            Real<R>::sts(s_den + k * RB, den); Real<R>::sts(s_inv + k * RB, inv); Real<R>::sts(s_f + k * RB, f);
             sts_i(s_ndk + k * 4, nd); sts_i(s_pub + k * 4, nd);
         }
         __syncthreads();
@@ -415,11 +467,11 @@ sweep_kernel(const SweepParams p) {
                     const int cur = lds_i(s_ndk + k * 4);
                     const int d = cur - atoms_exch(s_pub + k * 4, cur);
                     if (d != 0) red_add_i32(p.n_k + k, d);
-                    const float den = (float)ld_volatile_i32(p.n_k + k) + p.etaW;
-                    const float inv = __frcp_rn(den);
-                    sts_f(s_den + k * 4, den);
-                    sts_f(s_inv + k * 4, inv);
-                    sts_f(s_f + k * 4, ((float)lds_i(s_ndk + k * 4) + alpha) * inv);
+                    const R den = (R)ld_volatile_i32(p.n_k_read + k) + etaW;
+                    const R inv = Real<R>::rcp(den);
+                    Real<R>::sts(s_den + k * RB, den);
+                    Real<R>::sts(s_inv + k * RB, inv);
+                    Real<R>::sts(s_f + k * RB, ((R)lds_i(s_ndk + k * 4) + alpha) * inv);
                 }
                 __syncwarp();
             }
@@ -427,8 +479,8 @@ sweep_kernel(const SweepParams p) {
             int zn_j = pk_j & 0x1ff;
             if (TPT == 1) {
                 // one token per lane: the lane's own next-batch token is the next group
-                zn_j = sweep_step<TPT, CH>(buf, nwk_lane, rowbytes, lim, w_j, pk_j, w_n, pk_n, sm, sub, gbase, lane,
-                                           alpha, eta, K);
+                zn_j = sweep_step<TPT, CH, R>(buf, nwk_lane, rowbytes, lim, w_j, pk_j, w_n, pk_n, sm, sub, gbase, lane,
+                                           alpha, eta, K, p.nwk_write_delta);
             } else {
                 constexpr int UNR = (TPT <= 8) ? TPT : 2;
 #pragma unroll UNR
@@ -438,8 +490,8 @@ sweep_kernel(const SweepParams p) {
                     const int src = last ? 0 : s + 1;
                     const int w_x = __shfl_sync(FULL, last ? w_n : w_j, src, TPT);
                     const int pk_x = __shfl_sync(FULL, last ? pk_n : pk_j, src, TPT);
-                    const int zn = sweep_step<TPT, CH>(buf, nwk_lane, rowbytes, lim, w_c, pk_c, w_x, pk_x, sm, sub,
-                                                       gbase, lane, alpha, eta, K);
+                    const int zn = sweep_step<TPT, CH, R>(buf, nwk_lane, rowbytes, lim, w_c, pk_c, w_x, pk_x, sm, sub,
+                                                       gbase, lane, alpha, eta, K, p.nwk_write_delta);
                     if (sub == s) zn_j = zn;
                     w_c = w_x;
                     pk_c = pk_x;

@@ -102,6 +102,11 @@ class Corpus:
     def set_token_offset(self, offset: int):
         check(_lib.load().cgs_corpus_set_token_offset(self._h, int(offset)))
 
+    def set_global_size(self, n_cells_global: int, n_tokens_global: int):
+        """Size of the whole matrix when this corpus is one shard of its cells (AD-LDA): models created afterwards
+        size their concurrency caps against it."""
+        check(_lib.load().cgs_corpus_set_global_size(self._h, int(n_cells_global), int(n_tokens_global)))
+
     def token_lists(self):
         """(WS, DS) exactly as ``lda.utils.matrix_to_lists`` returns them."""
         WS = np.empty(self.n_tokens, np.int32)
@@ -186,6 +191,15 @@ class DeviceModel:
 
     def set_nk_staleness(self, divisor: float):
         check(_lib.load().cgs_model_set_nk_staleness(self._h, float(divisor)))
+
+    def set_conditional_precision(self, bits: int):
+        """32 (default) or 64: arithmetic of the conditional; 64 is the A/B build in the reference's precision."""
+        check(_lib.load().cgs_model_set_conditional_precision(self._h, int(bits)))
+
+    def set_deterministic(self, parts: int):
+        """parts > 0: bit-reproducible sweeps (every sweep = ``parts`` sub-sweeps that read copies of the count
+        tables, one warp per cell); 0 = the default live-count schedule."""
+        check(_lib.load().cgs_model_set_deterministic(self._h, int(parts)))
 
     @property
     def sweep_shape(self):
@@ -292,7 +306,54 @@ class DeviceModel:
         return {"gram": self.topic_gram(), "cell_mixture": mix, "length_sq": sq, "top_regions": top,
                 "codf": self.codocument_frequencies(top), "top_n": top_n}
 
+    # -- consistency checks ----------------------------------------------------------------
+    def region_histogram(self, device_address: int) -> int:
+        """Writes the (region, topic) histogram of z to a device buffer (int32[n_regions * Kp]); returns the number
+        of n_dk entries that differ from the per-cell histogram of z."""
+        bad = ctypes.c_int64()
+        check(_lib.load().cgs_model_region_histogram(self._h, c_vp(device_address), ctypes.byref(bad)))
+        return bad.value
+
+    def verify_counts(self, histogram_address: int | None = None):
+        """{"n_dk": ..., "n_wk": ..., "n_k": ...} = entries of each table that are NOT the bookkeeping of z (all 0
+        for a consistent state).  ``histogram_address``: device histogram summed over all ranks (AD-LDA shards)."""
+        out = (ctypes.c_int64 * 3)()
+        check(_lib.load().cgs_model_verify_counts(self._h, c_vp(histogram_address) if histogram_address else None, out))
+        return {"n_dk": out[0], "n_wk": out[1], "n_k": out[2]}
+
+    def state_hash(self):
+        """{"hash_nwk", "sum_nwk", "sum_nk", "hash_nk"} of the device tables."""
+        out = (ctypes.c_uint64 * 4)()
+        check(_lib.load().cgs_model_state_hash(self._h, out))
+        return {"hash_nwk": int(out[0]), "sum_nwk": int(out[1]), "sum_nk": int(out[2]), "hash_nk": int(out[3])}
+
     # -- AD-LDA exchange -------------------------------------------------------------------
+    def allreduce_delta(self, nccl_comm: int):
+        """The synchronous exchange step behind the ABI (delta, ncclAllReduce on ``nccl_comm``, apply)."""
+        check(_lib.load().cgs_model_allreduce_delta(self._h, c_vp(nccl_comm)))
+
+    def exchange_arena(self):
+        """(address, nbytes) of this rank's arena of the asynchronous peer-memory exchange."""
+        p, n = c_vp(), ctypes.c_size_t()
+        check(_lib.load().cgs_model_exchange_arena(self._h, ctypes.byref(p), ctypes.byref(n)))
+        return p.value, n.value
+
+    def exchange_open(self, arena_addresses, rank: int):
+        arr = (c_vp * len(arena_addresses))(*[c_vp(a) for a in arena_addresses])
+        check(_lib.load().cgs_model_exchange_open(self._h, arr, len(arena_addresses), int(rank)))
+
+    def exchange_round(self, n_ctas: int = 0):
+        check(_lib.load().cgs_model_exchange_round(self._h, int(n_ctas)))
+
+    def exchange_wait(self):
+        check(_lib.load().cgs_model_exchange_wait(self._h))
+
+    def exchange_timeouts(self) -> int:
+        """Barrier waits of the exchange kernels that gave up (0 = all rounds completed)."""
+        n = ctypes.c_int32()
+        check(_lib.load().cgs_model_exchange_status(self._h, ctypes.byref(n)))
+        return n.value
+
     @property
     def padded_topics(self) -> int:
         kp = ctypes.c_int32()

@@ -258,6 +258,33 @@ def test_evaluate_models_selection():
     assert best2.n_topic == 10
 
 
+@pytest.mark.skipif(not rf.available(), reason="needs /root/reference (authoring container)")
+def test_evaluate_models_equals_the_reference_function_run_live():
+    """The mirror against the reference's OWN evaluate_models (lda_models.py:1048-1270, AST-executed from the tree,
+    matplotlib replaced by an inert stand-in): same selected model for every metric subset, min_topics_coh and
+    model order, on random metric tables."""
+    ref = rf.reference_evaluate_models()
+    rng = np.random.default_rng(1048)
+    all_metrics = ["Minmo_2011", "loglikelihood", "Cao_Juan_2009", "Arun_2010"]
+    for trial in range(60):
+        ks = sorted(rng.choice(np.arange(2, 60), size=int(rng.integers(3, 9)), replace=False).tolist())
+        models = [_fake_model(k, float(rng.uniform(1, 20)), float(rng.uniform(0.05, 0.9)), float(rng.uniform(-1, -0.1)),
+                              float(rng.uniform(-1e6, 1e6))) for k in ks]
+        models = [models[i] for i in rng.permutation(len(models))]
+        n_sel = int(rng.integers(1, 5))
+        metrics = [all_metrics[i] for i in sorted(rng.choice(4, size=n_sel, replace=False))]
+        min_coh = int(rng.choice([2, 5, 5, 10]))
+        if "Minmo_2011" in metrics and sum(k >= min_coh for k in ks) < 2:
+            continue  # rescaling a single value divides by zero in the reference too
+        want = ref(list(models), metrics=list(metrics), min_topics_coh=min_coh, plot=False)
+        got = lda_models.evaluate_models(list(models), metrics=list(metrics), min_topics_coh=min_coh, plot=False)
+        assert got.n_topic == want.n_topic, (ks, metrics, min_coh)
+        pick = int(rng.choice(ks))
+        assert lda_models.evaluate_models(list(models), select_model=pick, plot=False).n_topic == \
+            ref(list(models), select_model=pick, plot=False).n_topic == pick
+    assert ref(list(models), return_model=False, plot=False) is None
+
+
 def test_schedule_models_lpt():
     topics = [2, 5, 10, 15, 20, 25, 30, 35, 40, 45, 50]
     for n in (1, 2, 4, 8):
@@ -511,3 +538,14 @@ def test_variable_feature_selection_matches_live_reference():
                 assert got == want, (R, C, n_bins, kw)
     finally:
         logging.disable(logging.NOTSET)
+
+
+def test_pin_against_pypi_runs_or_reports_absent():
+    """oracle/pin_against_pypi.py compares the oracle with the real `lda` / `tmtoolkit` wherever they are
+    installed; here (no network) it must report them absent -- and if a later image does ship them, it must pin."""
+    from oracle import pin_against_pypi as pin
+    code, report = pin.run(verbose=False)
+    if pin.packages()[0] is None:
+        assert code == pin.EXIT_ABSENT
+    else:
+        assert code == pin.EXIT_PINNED, report

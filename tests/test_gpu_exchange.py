@@ -1,0 +1,267 @@
+"""The asynchronous peer-memory exchange (csrc/exchange_kernels.cuh), the NCCL exchange behind the ABI, the
+device-side consistency checks and the deterministic mode -- all on ONE GPU, so the driver's single-GPU box
+exercises them: the "ranks" of the exchange are R models over R cell shards on the same device, each with its
+own streams; their round kernels meet in the same cross-rank flag barriers they use over NVLink."""
+import ctypes
+import os
+import sys
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import lda_oracle as lo  # noqa: E402
+from pycistopic_b200.synth import make_binary_matrix  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def small():
+    m, _, _ = make_binary_matrix(n_cells=600, n_regions=8000, density=0.04, n_true_topics=6, seed=11)
+    return m
+
+
+def _shards(m, R, K, alpha, eta, seed=555):
+    from pycistopic_b200 import Corpus, DeviceModel
+    from pycistopic_b200.adlda import balanced_cell_partition
+    W, D = m.shape
+    per_cell = np.bincount(m.indices, minlength=D)
+    part, cell_ptr = balanced_cell_partition(per_cell, R)
+    out = []
+    for r in range(R):
+        c = Corpus.from_regions_by_cells(m, device=0, cell_range=(int(part[r]), int(part[r + 1])))
+        c.set_token_offset(int(cell_ptr[part[r]]))
+        c.set_global_size(D, int(cell_ptr[-1]))
+        out.append((c, DeviceModel(c, K, alpha, eta, seed=seed)))
+    return out, part
+
+
+def _global_histogram(shards):
+    """Sum over the shards of the (region, topic) histogram of z, as a device tensor; asserts n_dk on the way."""
+    import torch
+    c0, m0 = shards[0]
+    n = c0.n_regions * m0.padded_topics
+    total = torch.zeros(n, dtype=torch.int32, device="cuda:0")
+    tmp = torch.empty_like(total)
+    for _, mdl in shards:
+        assert mdl.region_histogram(tmp.data_ptr()) == 0
+        mdl.sync()
+        total += tmp
+    torch.cuda.synchronize()
+    return total
+
+
+@pytest.mark.parametrize("R,K", [(2, 10), (3, 50), (4, 7)])
+def test_async_exchange_virtual_ranks(small, R, K):
+    m = small
+    X = sp.csr_matrix(m.T)
+    alpha, eta = 50.0 / K, 0.1
+    shards, part = _shards(m, R, K, alpha, eta)
+    for _, mdl in shards:
+        mdl.init()
+    arenas = [mdl.exchange_arena()[0] for _, mdl in shards]
+    for r, (_, mdl) in enumerate(shards):
+        mdl.exchange_open(arenas, r)
+    # round 1: local initial counts -> the global tables on every rank
+    for _, mdl in shards:
+        mdl.exchange_round(8)
+    for _, mdl in shards:
+        mdl.exchange_wait()
+        mdl.sync()
+    WS, DS = lo.matrix_to_lists(X)
+    onzw, _, onz = lo.counts_from_z(WS, DS, np.arange(len(WS)) % K, X.shape[0], X.shape[1], K)
+    for _, mdl in shards:
+        nzw, _, nz = mdl.counts(ndz=False)
+        assert np.array_equal(nzw, onzw) and np.array_equal(nz, onz)
+    ll0 = sum(mdl.loglikelihood(1) for _, mdl in shards) + shards[0][1].loglikelihood(2)
+    assert ll0 == pytest.approx(lo.loglikelihood_true(onzw, lo.counts_from_z(WS, DS, np.arange(len(WS)) % K, X.shape[0],
+                                                                             X.shape[1], K)[1], onz, alpha, eta), rel=1e-10)
+    # sweeps with the exchange running beside them
+    for it in range(12):
+        for _, mdl in shards:
+            mdl.exchange_round(8)
+        for _, mdl in shards:
+            mdl.sweep(1)
+        if it == 5:  # a mid-run drain: consistent replicas, then carry on
+            for _, mdl in shards:
+                mdl.exchange_round(8)
+            for _, mdl in shards:
+                mdl.exchange_wait()
+                mdl.sync()
+            hashes = [mdl.state_hash() for _, mdl in shards]
+            assert all(h == hashes[0] for h in hashes), hashes
+    for _, mdl in shards:
+        mdl.exchange_round(8)
+    for _, mdl in shards:
+        mdl.exchange_wait()
+        mdl.sync()
+    assert [mdl.exchange_timeouts() for _, mdl in shards] == [0] * R
+    hashes = [mdl.state_hash() for _, mdl in shards]
+    assert all(h == hashes[0] for h in hashes), hashes
+    assert hashes[0]["sum_nwk"] == X.nnz and hashes[0]["sum_nk"] == X.nnz
+    hist = _global_histogram(shards)
+    for _, mdl in shards:
+        assert mdl.verify_counts(hist.data_ptr()) == {"n_dk": 0, "n_wk": 0, "n_k": 0}
+    ll = sum(mdl.loglikelihood(1) for _, mdl in shards) + shards[0][1].loglikelihood(2)
+    assert ll > ll0
+    for c, mdl in shards:
+        mdl.close()
+        c.close()
+
+
+def test_async_exchange_trace_follows_the_adlda_oracle(small):
+    """In production no rank waits for a round: a shard samples against counts of the other shards that are one to
+    two sweeps old (the AD-LDA oracle: exactly one).  The log-likelihood after n uninterrupted sweeps must still be
+    within 1 % of the oracle's at every checkpoint of the transient (fresh chains per checkpoint, because
+    evaluating the log-likelihood needs a drain, which would make the next sweeps fresher than production's)."""
+    m = small
+    X = sp.csr_matrix(m.T)
+    K, R = 10, 2
+    alpha, eta = 50.0 / K, 0.1
+    checkpoints = [3, 6, 10, 15, 25, 40]
+    seeds = [555, 1, 2, 3]
+    gt = np.zeros(len(checkpoints))
+    part = None
+    for seed in seeds:
+        for ci, n in enumerate(checkpoints):
+            shards, part = _shards(m, R, K, alpha, eta, seed=seed)
+            for _, mdl in shards:
+                mdl.init()
+            arenas = [mdl.exchange_arena()[0] for _, mdl in shards]
+            for r, (_, mdl) in enumerate(shards):
+                mdl.exchange_open(arenas, r)
+            for _, mdl in shards:  # the initial, synchronous round
+                mdl.exchange_round(8)
+            for _, mdl in shards:
+                mdl.exchange_wait()
+            for it in range(n):
+                for _, mdl in shards:
+                    mdl.exchange_round(8)
+                for _, mdl in shards:
+                    mdl.sweep(1)
+            for _, mdl in shards:
+                mdl.exchange_round(8)
+            for _, mdl in shards:
+                mdl.exchange_wait()
+                mdl.sync()
+            gt[ci] += sum(mdl.loglikelihood(1) for _, mdl in shards) + shards[0][1].loglikelihood(2)
+            assert [mdl.exchange_timeouts() for _, mdl in shards] == [0] * R
+            for c, mdl in shards:
+                mdl.close()
+                c.close()
+    gt /= len(seeds)
+    ot = np.zeros(len(checkpoints))
+    for seed in seeds:
+        o = lo.OracleLDA(K, n_iter=max(checkpoints), alpha=alpha, eta=eta, random_state=seed, refresh=1, n_parts=R,
+                         part_ptr=part).fit(X)
+        tr = np.array(o.loglikelihoods_ + [o.final_loglikelihood_])
+        ot += tr[checkpoints]
+    ot /= len(seeds)
+    rel = np.abs(gt - ot) / np.abs(ot)
+    assert rel.max() < 0.01, f"trace deviates {rel.max():.3%} after {checkpoints[int(rel.argmax())]} sweeps ({rel})"
+
+
+def test_nccl_exchange_behind_the_abi_single_rank(small):
+    """cgs_nccl_unique_id / cgs_nccl_comm_create / cgs_model_allreduce_delta with a one-rank communicator: the
+    all-reduce is the identity, so the tables must stay exactly the bookkeeping of z, sweep after sweep."""
+    from pycistopic_b200 import Corpus, DeviceModel, _lib
+    L = _lib.load()
+    uid = ctypes.create_string_buffer(128)
+    _lib.check(L.cgs_nccl_unique_id(uid))
+    comm = ctypes.c_void_p()
+    _lib.check(L.cgs_nccl_comm_create(ctypes.byref(comm), 0, 1, 0, uid))
+    corpus = Corpus.from_regions_by_cells(small)
+    mdl = DeviceModel(corpus, 12, 50.0 / 12, 0.1, seed=3)
+    mdl.init()
+    mdl.allreduce_delta(comm.value)
+    before = mdl.state_hash()
+    assert before["sum_nwk"] == corpus.n_tokens
+    for _ in range(3):
+        mdl.sweep(1)
+        mdl.allreduce_delta(comm.value)
+    mdl.sync()
+    assert mdl.verify_counts() == {"n_dk": 0, "n_wk": 0, "n_k": 0}
+    assert mdl.state_hash()["sum_nk"] == corpus.n_tokens
+    mdl.close()
+    corpus.close()
+    _lib.check(L.cgs_nccl_comm_destroy(comm))
+
+
+def test_verify_counts_detects_corruption(small):
+    import torch
+    from pycistopic_b200 import Corpus, DeviceModel
+    corpus = Corpus.from_regions_by_cells(small)
+    mdl = DeviceModel(corpus, 9, 5.0, 0.1, seed=1)
+    mdl.init()
+    mdl.sweep(3)
+    assert mdl.verify_counts() == {"n_dk": 0, "n_wk": 0, "n_k": 0}
+    addr, nbytes, view = mdl.device_buffer("n_wk")
+    t = torch.as_tensor(view, device="cuda:0")
+    t[5] += 1
+    torch.cuda.synchronize()
+    bad = mdl.verify_counts()
+    assert bad["n_wk"] == 1 and bad["n_k"] == 1 and bad["n_dk"] == 0
+    h1 = mdl.state_hash()
+    t[5] -= 1
+    t[6] += 1
+    torch.cuda.synchronize()
+    h2 = mdl.state_hash()
+    assert h1["sum_nwk"] == h2["sum_nwk"] and h1["hash_nwk"] != h2["hash_nwk"]
+    mdl.close()
+    corpus.close()
+
+
+@pytest.mark.parametrize("K", [5, 50])
+def test_deterministic_mode_is_bit_reproducible(small, K):
+    """Reference behaviour: a fixed random_state gives the same model (lda_models.py:104).  In deterministic
+    mode two runs must agree on every topic assignment; the default mode is only statistically reproducible."""
+    from pycistopic_b200 import Corpus, DeviceModel
+    corpus = Corpus.from_regions_by_cells(small)
+    zs = []
+    for _ in range(2):
+        mdl = DeviceModel(corpus, K, 50.0 / K, 0.1, seed=555)
+        mdl.set_deterministic(4)
+        mdl.init()
+        mdl.sweep(15)
+        assert mdl.verify_counts() == {"n_dk": 0, "n_wk": 0, "n_k": 0}
+        assert mdl.debug_sweep_visits() == corpus.n_tokens
+        zs.append(mdl.get_z())
+        mdl.close()
+    assert np.array_equal(zs[0], zs[1])
+    other = DeviceModel(corpus, K, 50.0 / K, 0.1, seed=556)
+    other.set_deterministic(4)
+    other.init()
+    other.sweep(15)
+    assert not np.array_equal(other.get_z(), zs[0])
+    other.close()
+    corpus.close()
+
+
+def test_deterministic_mode_trace_close_to_oracle(small):
+    """With 8 sub-sweeps the copies a cell reads are at most 1/8 of a sweep old: the trace stays within 1 % of the
+    sequential oracle (seed-averaged on both sides, as the other trace tests on corpora this small)."""
+    from pycistopic_b200 import Corpus, DeviceModel
+    X = sp.csr_matrix(small.T)
+    K, n_iter = 10, 40
+    alpha, eta = 50.0 / K, 0.1
+    corpus = Corpus.from_regions_by_cells(small)
+    seeds = [555, 1, 2, 3]
+    gt, ot = np.zeros(n_iter + 1), np.zeros(n_iter + 1)
+    for s in seeds:
+        mdl = DeviceModel(corpus, K, alpha, eta, seed=s)
+        mdl.set_deterministic(8)
+        mdl.init()
+        for it in range(n_iter):
+            gt[it] += mdl.loglikelihood()
+            mdl.sweep(1)
+        gt[n_iter] += mdl.loglikelihood()
+        mdl.close()
+        o = lo.OracleLDA(K, n_iter=n_iter, alpha=alpha, eta=eta, random_state=s, refresh=1).fit(X)
+        ot += np.array(o.loglikelihoods_ + [o.final_loglikelihood_])
+    rel = np.abs(gt - ot) / np.abs(ot)
+    corpus.close()
+    assert rel.max() < 0.01, f"trace deviates {rel.max():.3%} at sweep {rel.argmax()}"

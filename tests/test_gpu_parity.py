@@ -4,6 +4,7 @@ Integer/index work is bit-exact; the stochastic sampler is compared through the 
 log-likelihood trace and the Mimno coherence within 1 % (BASELINE.json north_star).
 """
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -445,14 +446,13 @@ def test_normalize_scores_matches_oracle(dtype, rtol, R, C):
     np.testing.assert_allclose(out, ref, rtol=rtol, atol=0)
 
 
-def test_loglik_trace_benchmark_shapes():
-    """The device sampler at the kernel shapes and concurrency of the benchmark (cells of 6 500 tokens, 200 000
-    regions: 4 lanes x 4 chunks for K = 50, 2 x 2 for K = 10, hundreds of cells open) against the sequential
-    oracle's mean trace frozen in tests/golden/trace_c2_4000cells.npz (4 seeds, refresh = 1).  1 % on every
-    sweep (north star).  The matrix is regenerated with the torch-CPU generator and checked against the
-    stored checksums; another torch build that draws differently skips instead of comparing apples to pears."""
+@pytest.fixture(scope="module")
+def bench_shaped():
+    """(corpus, frozen oracle traces) of the benchmark-SHAPED matrix of tests/golden/trace_c2_4000cells.npz: regenerated
+    with the torch-CPU generator and checked against the stored checksums; another torch build that draws differently
+    skips instead of comparing apples to pears."""
     import torch
-    from pycistopic_b200 import Corpus, DeviceModel
+    from pycistopic_b200 import Corpus
     from pycistopic_b200.synth import planted_topic_tokens
     g = np.load(os.path.join(ROOT, "tests", "golden", "trace_c2_4000cells.npz"))
     D, W = int(g["D"]), int(g["W"])
@@ -466,23 +466,178 @@ def test_loglik_trace_benchmark_shapes():
     cell_ptr[1:] = torch.cumsum(cnt, 0)
     cell_ptr, tok = cell_ptr.to(dev), region.to(torch.int32).to(dev)
     corpus = Corpus.from_device_tokens(cell_ptr.data_ptr(), tok.data_ptr(), D, W, tok.numel(), keepalive=(cell_ptr, tok))
+    yield corpus, g
+    corpus.close()
+
+
+def _device_traces(corpus, K, n_iter, seeds, precision=32):
+    from pycistopic_b200 import DeviceModel
+    traces, shape = [], None
+    for seed in seeds:
+        model = DeviceModel(corpus, K, 50.0 / K, 0.1, seed=int(seed))
+        if precision != 32:
+            model.set_conditional_precision(precision)
+        model.init()
+        tr = []
+        for _ in range(n_iter):
+            tr.append(model.loglikelihood())
+            model.sweep(1)
+        tr.append(model.loglikelihood())
+        traces.append(tr)
+        shape = model.sweep_shape
+        model.close()
+    return np.array(traces), shape
+
+
+def test_loglik_trace_benchmark_shapes(bench_shaped):
+    """The device sampler at the kernel shapes and concurrency of the benchmark (cells of 6 500 tokens, 200 000
+    regions: 4 lanes x 4 chunks for K = 50, 2 x 2 for K = 10, hundreds of cells open) against the sequential
+    oracle's mean trace frozen in tests/golden/trace_c2_4000cells.npz (8 seeds, refresh = 1).  1 % on every
+    sweep (north star).  The oracle's OWN single-chain spread on this corpus is asserted to be what makes the
+    seed average necessary in the smaller-corpus tests and unnecessary here (0.4 % at the plateau)."""
+    corpus, g = bench_shaped
     for K in (10, 50):
         ref = g[f"mean_K{K}"]
-        n_iter = len(ref) - 1
-        traces = []
-        for seed in (555, 1, 2):
-            model = DeviceModel(corpus, K, 50.0 / K, 0.1, seed=seed)
-            model.init()
-            tr = []
-            for _ in range(n_iter):
-                tr.append(model.loglikelihood())
-                model.sweep(1)
-            tr.append(model.loglikelihood())
-            traces.append(tr)
-            shape = model.sweep_shape
-            model.close()
-        mean = np.mean(traces, axis=0)
+        single_chain_sd = g[f"se_K{K}"] * np.sqrt(len(g["seeds"])) / np.abs(ref)
+        assert single_chain_sd.max() < 0.006
+        traces, shape = _device_traces(corpus, K, len(ref) - 1, (555, 1, 2))
+        mean = traces.mean(axis=0)
         assert mean[0] == pytest.approx(ref[0], rel=1e-10)  # identical start: z = i mod K on the identical matrix
         rel = np.abs(mean - ref) / np.abs(ref)
         assert rel.max() < 0.01, f"K={K} {shape}: trace deviates {rel.max():.3%} at sweep {int(rel.argmax())}"
+        # and every single device chain on its own
+        rel1 = np.abs(traces - ref) / np.abs(ref)
+        assert rel1.max() < 0.01, f"K={K}: a single chain deviates {rel1.max():.3%}"
+
+
+@pytest.mark.parametrize("K", [10, 50])
+def test_fp32_conditional_equals_fp64_conditional(bench_shaped, K):
+    """A/B of the one arithmetic difference from the reference: the conditional in float
+    (production) against the same kernel instantiated in double (lda._lda._sample_topics' precision) -- same
+    schedule, same random bits, same integer bookkeeping -- on the benchmark-shaped corpus, 48 seeds a side.
+    The mean traces must agree within 0.1 % wherever the statistics can resolve 0.1 % (three standard errors of the
+    difference below it: the first ~15 sweeps) and within three standard errors elsewhere; both stay within 1 % of
+    the frozen oracle trace."""
+    corpus, g = bench_shaped
+    ref = g[f"mean_K{K}"]
+    seeds = np.arange(48)
+    t32, _ = _device_traces(corpus, K, len(ref) - 1, seeds, 32)
+    t64, shape64 = _device_traces(corpus, K, len(ref) - 1, seeds, 64)
+    m32, m64 = t32.mean(axis=0), t64.mean(axis=0)
+    assert m32[0] == m64[0]
+    rel = np.abs(m32 - m64) / np.abs(m64)
+    se = np.sqrt(t32.var(axis=0, ddof=1) / len(seeds) + t64.var(axis=0, ddof=1) / len(seeds)) / np.abs(m64)
+    print(f"K={K} fp64 shape {shape64}: max |fp32 - fp64| = {rel.max():.4%} at sweep {int(rel.argmax())}; "
+          f"3 se there = {3 * se[int(rel.argmax())]:.4%}")
+    assert np.all(rel <= np.maximum(1e-3, 3 * se)), (rel, se)
+    resolvable = 3 * se < 1e-3
+    assert resolvable[:12].all() and np.all(rel[resolvable] < 1e-3)
+    assert (np.abs(m32 - ref) / np.abs(ref)).max() < 0.01 and (np.abs(m64 - ref) / np.abs(ref)).max() < 0.01
+
+
+def test_fp32_and_fp64_make_the_same_decisions_in_one_deterministic_sweep(bench_shaped):
+    """In deterministic mode a sweep is a pure function of the state, so float and double can be compared decision by
+    decision: after ONE sweep from the identical start, the assignments differ only where rounding moves the
+    inversion point across a topic boundary (a few per million) plus the tokens of the same cell that follow such
+    a flip and see a cell row changed by one (each flip begets about one more before the cell ends)."""
+    from pycistopic_b200 import DeviceModel
+    corpus, _ = bench_shaped
+    for K in (10, 50):
+        zs = []
+        for bits in (32, 64):
+            m = DeviceModel(corpus, K, 50.0 / K, 0.1, seed=555)
+            m.set_conditional_precision(bits)
+            m.set_deterministic(1)
+            m.init()
+            m.sweep(1)
+            zs.append(m.get_z())
+            m.close()
+        frac = float(np.mean(zs[0] != zs[1]))
+        print(f"K={K}: {frac:.2e} of the tokens decided differently by fp32 and fp64")
+        assert frac < 2e-3
+
+
+# ---- dense impute_accessibility against the reference's own output matrices ---------------------------
+@pytest.mark.parametrize("case", range(6))
+def test_dense_impute_matches_reference_output_matrices(case):
+    """tests/golden/impute.npz holds, for six cases, what the reference's OWN calculate_imputed_accessibility
+    (diff_features.py:398-492, AST-executed from the tree by tests/golden/make_golden.py) returned: the dense
+    matrix and the kept regions.  The device path must reproduce them: +-1 after the int32 truncation (the
+    fp32 summation order differs), 1e-5 relative for the float path (north star), and the same kept regions
+    except regions whose largest value sits on the truncation boundary (max < 2)."""
+    from pycistopic_b200.diff_features import calculate_imputed_accessibility
+    g = np.load(os.path.join(ROOT, "tests", "golden", "impute.npz"))
+    a, b = g[f"a{case}"], g[f"b{case}"]
+    scale = float(g[f"scale{case}"])
+    if bool(g[f"scale_is_int{case}"]):
+        scale = int(scale)
+    chunk = int(g[f"chunk{case}"])
+    want, want_kept = g[f"out{case}"], g[f"kept{case}"]
+    names = list(range(a.shape[0]))
+    got, got_kept = calculate_imputed_accessibility(a, b, names, scale, chunk)
+    got_kept = np.asarray(got_kept, np.int64)
+    assert got.dtype == want.dtype
+    R, C = a.shape[0], b.shape[1]
+    full_w = np.zeros((R, C), np.float64)
+    full_g = np.zeros((R, C), np.float64)
+    full_w[want_kept] = want
+    full_g[got_kept] = got
+    if want.dtype == np.int32:
+        assert np.abs(full_w - full_g).max() <= 1
+        assert (full_w != full_g).mean() < 1e-3          # boundary flips are rare
+        differing = np.setxor1d(want_kept, got_kept)
+        assert all(max(full_w[r].max(), full_g[r].max()) < 2 for r in differing)
+    else:
+        assert np.array_equal(want_kept, got_kept)
+        np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-12)
+
+
+# ---- coherence: distribution over seeds against the frozen oracle distribution --------------------------
+def _device_top5_coherence(m, K, n_iter, seeds):
+    """Model coherence (mean of the 5 best Mimno-2011 topic coherences, lda_models.py:297-328) and final
+    log-likelihood of one device chain per seed; the (co-)document frequencies come from the device."""
+    from pycistopic_b200 import LDA, Corpus
+    from pycistopic_b200 import metrics as pm
+    corpus = Corpus.from_regions_by_cells(m)
+    coh, ll = [], []
+    for s in seeds:
+        g = LDA(K, n_iter=n_iter, alpha=50.0 / K, eta=0.1, random_state=int(s), refresh=n_iter, corpus=corpus,
+                exports="frames", device_metrics={"alpha": 50.0, "eta": 0.1, "top_n": 20}).fit(None)
+        c = pm.mimno_from_codf(g.metric_ingredients_["codf"], eps=1e-12, normalize=True)
+        coh.append(np.mean(c) if len(c) <= 5 else np.mean(np.sort(c)[-5:]))
+        ll.append(g.final_loglikelihood_)
     corpus.close()
+    return np.array(coh), np.array(ll)
+
+
+@pytest.mark.parametrize("case,n_gpu_seeds", [("c1_K5", 256), ("c1_K10", 256), ("c2s_K50", 128)])
+def test_coherence_distribution_vs_frozen_oracle(case, n_gpu_seeds):
+    """North star: "final topic coherence within 1 % of the reference".  ONE chain of the sequential oracle differs
+    from another by 6 % (C1) to 12 % (C2-shaped) -- asserted below from the frozen per-seed values -- so the
+    comparison is between DISTRIBUTIONS: tests/golden/coherence_distribution.npz freezes the oracle's model
+    coherence for 128 (C1: K = 5, 10; 150 sweeps) and 96 (C2-shaped: 600 cells x 200 000 regions, K = 50, 100 sweeps)
+    seeds; the device runs 256 / 128 chains.  Gates: means within 2 % (C1; 2.7 standard errors of the difference) or
+    within max(2 %, 2.5 standard errors) (C2-shaped, where the frozen mean itself is only known to 1.25 %); spread
+    within a factor 1.5; two-sample Kolmogorov-Smirnov p > 0.001; mean final log-likelihood within 0.1 %."""
+    from scipy.stats import ks_2samp
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_coherence_distribution as mk
+    g = np.load(os.path.join(ROOT, "tests", "golden", "coherence_distribution.npz"))
+    m, check = mk.case_matrix(case)
+    assert np.array_equal(check, g[f"{case}_checksum"]), "the generator no longer reproduces the frozen matrix"
+    cfg = mk.CASES[case]
+    oc, oll = g[f"{case}_top5"], g[f"{case}_loglik"]
+    # the reason a single-chain 1 % gate is impossible: the oracle's own seed-to-seed spread
+    assert oc.std(ddof=1) / abs(oc.mean()) > 0.04
+    seeds = np.arange(1000, 1000 + n_gpu_seeds)
+    gc, gll = _device_top5_coherence(m, cfg["K"], cfg["n_iter"], seeds)
+    se = np.sqrt(oc.var(ddof=1) / len(oc) + gc.var(ddof=1) / len(gc))
+    diff = abs(gc.mean() - oc.mean())
+    gate = 0.02 * abs(oc.mean()) if case.startswith("c1") else max(0.02 * abs(oc.mean()), 2.5 * se)
+    msg = (f"{case}: device {gc.mean():.4f} +- {gc.std(ddof=1):.4f} ({len(gc)} seeds), oracle {oc.mean():.4f} +- "
+           f"{oc.std(ddof=1):.4f} ({len(oc)} seeds), diff {diff / abs(oc.mean()):.2%}, se {se / abs(oc.mean()):.2%}")
+    print(msg)
+    assert diff <= gate, msg
+    assert 1 / 1.5 < gc.std(ddof=1) / oc.std(ddof=1) < 1.5, msg
+    assert ks_2samp(gc, oc).pvalue > 1e-3, msg
+    assert gll.mean() == pytest.approx(oll.mean(), rel=1e-3), msg

@@ -1,0 +1,134 @@
+"""Property tests (hypothesis) of the size-independent invariants SURVEY.md section 4(iii) lists: count
+conservation, z round trips, equivalence of the two matrix layouts.  The CPU half exercises the oracle and
+the host logic; the half marked ``gpu`` runs the same properties through the C ABI on the device."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+from hypothesis import HealthCheck, given, settings
+from hypothesis import strategies as st
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import lda_oracle as lo  # noqa: E402
+from pycistopic_b200 import adlda, lda_models  # noqa: E402
+
+COMMON = dict(deadline=None, suppress_health_check=list(HealthCheck))
+
+
+@st.composite
+def binary_matrices(draw, max_cells=40, max_regions=120):
+    """regions x cells int32 CSR with at least one token; may hold empty cells and empty regions."""
+    D = draw(st.integers(1, max_cells))
+    W = draw(st.integers(1, max_regions))
+    density = draw(st.floats(0.01, 0.6))
+    seed = draw(st.integers(0, 2 ** 31 - 1))
+    rng = np.random.default_rng(seed)
+    dense = (rng.random((W, D)) < density).astype(np.int32)
+    if dense.sum() == 0:
+        dense[rng.integers(W), rng.integers(D)] = 1
+    return sp.csr_matrix(dense)
+
+
+# ---- CPU: the oracle and the host logic ---------------------------------------------------------------
+@settings(max_examples=40, **COMMON)
+@given(m=binary_matrices(), K=st.integers(1, 12), sweeps=st.integers(0, 4), seed=st.integers(0, 10 ** 6))
+def test_oracle_conserves_counts(m, K, sweeps, seed):
+    X = sp.csr_matrix(m.T)
+    o = lo.OracleLDA(K, n_iter=sweeps, alpha=50.0 / K, eta=0.1, random_state=seed, refresh=max(1, sweeps), keep_z=True).fit(X)
+    assert o.nz_.sum() == X.nnz and np.array_equal(o.nzw_.sum(axis=1), o.nz_)
+    assert np.array_equal(o.ndz_.sum(axis=1), np.diff(X.indptr))
+    assert np.array_equal(o.nzw_.sum(axis=0), np.asarray(X.sum(axis=0)).ravel())
+    nzw, ndz, nz = lo.counts_from_z(o.WS, o.DS, o.ZS, X.shape[0], X.shape[1], K)
+    assert np.array_equal(nzw, o.nzw_) and np.array_equal(ndz, o.ndz_) and np.array_equal(nz, o.nz_)
+    assert (o.nzw_ >= 0).all() and (o.ndz_ >= 0).all()
+
+
+@settings(max_examples=40, **COMMON)
+@given(m=binary_matrices())
+def test_oracle_token_lists_two_statements_agree(m):
+    X = sp.csr_matrix(m.T)
+    WS, DS = lo.matrix_to_lists(X)
+    WS2, DS2 = lo.matrix_to_lists_py(X)
+    assert np.array_equal(WS, WS2) and np.array_equal(DS, DS2)
+    assert np.array_equal(WS, X.indices) and np.array_equal(DS, np.repeat(np.arange(X.shape[0]), np.diff(X.indptr)))
+
+
+@settings(max_examples=60, **COMMON)
+@given(counts=st.lists(st.integers(0, 5000), min_size=1, max_size=200), parts=st.integers(1, 16))
+def test_balanced_partition_is_a_partition(counts, parts):
+    D = len(counts)
+    parts = min(parts, D)
+    ptr, cell_ptr = adlda.balanced_cell_partition(counts, parts)
+    assert ptr[0] == 0 and ptr[-1] == D and np.all(np.diff(ptr) >= 1)
+    assert np.diff(cell_ptr[ptr]).sum() == sum(counts)
+
+
+@settings(max_examples=60, **COMMON)
+@given(topics=st.lists(st.integers(1, 500), min_size=1, max_size=24), workers=st.integers(1, 16))
+def test_schedule_covers_every_model_once(topics, workers):
+    plan = lda_models.schedule_models(topics, workers)
+    assert len(plan) == workers and sorted(i for p in plan for i in p) == list(range(len(topics)))
+    loads = [sum(lda_models.model_cost(topics[i]) for i in p) for p in plan]
+    longest = max(lda_models.model_cost(k) for k in topics)
+    assert max(loads) <= sum(lda_models.model_cost(k) for k in topics) / workers + longest + 1e-9
+
+
+# ---- GPU: the same invariants through the C ABI --------------------------------------------------------
+@pytest.mark.gpu
+@settings(max_examples=25, **COMMON)
+@given(m=binary_matrices(), K=st.integers(1, 70), sweeps=st.integers(0, 3), seed=st.integers(0, 10 ** 6))
+def test_device_conserves_counts_and_round_trips_z(m, K, sweeps, seed):
+    from pycistopic_b200 import Corpus, DeviceModel
+    X = sp.csr_matrix(m.T)
+    corpus = Corpus.from_regions_by_cells(m)
+    WS, DS = corpus.token_lists()
+    oWS, oDS = lo.matrix_to_lists(X)
+    assert np.array_equal(WS, oWS) and np.array_equal(DS, oDS)
+    mdl = DeviceModel(corpus, K, 50.0 / K, 0.1, seed=seed)
+    mdl.init()
+    mdl.sweep(sweeps)
+    z = mdl.get_z()
+    assert z.min() >= 0 and z.max() < K
+    nzw, ndz, nz = mdl.counts()
+    rnzw, rndz, rnz = lo.counts_from_z(oWS, oDS, z, X.shape[0], X.shape[1], K)
+    assert np.array_equal(nzw, rnzw) and np.array_equal(ndz, rndz) and np.array_equal(nz, rnz)
+    assert mdl.verify_counts() == {"n_dk": 0, "n_wk": 0, "n_k": 0}
+    h = mdl.state_hash()
+    assert h["sum_nwk"] == X.nnz == h["sum_nk"]
+    # set_z / get_z round trip with an arbitrary assignment
+    rng = np.random.default_rng(seed)
+    z2 = rng.integers(0, K, size=len(oWS)).astype(np.int32)
+    mdl.set_z(z2)
+    assert np.array_equal(mdl.get_z(), z2)
+    nzw, ndz, nz = mdl.counts()
+    rnzw, rndz, rnz = lo.counts_from_z(oWS, oDS, z2, X.shape[0], X.shape[1], K)
+    assert np.array_equal(nzw, rnzw) and np.array_equal(ndz, rndz) and np.array_equal(nz, rnz)
+    mdl.close()
+    corpus.close()
+
+
+@pytest.mark.gpu
+@settings(max_examples=25, **COMMON)
+@given(m=binary_matrices(), shuffle_seed=st.integers(0, 10 ** 6))
+def test_device_token_list_is_layout_independent(m, shuffle_seed):
+    """regions x cells (the reference's binary_matrix, transposed on the device) and cells x regions with
+    shuffled, duplicated column indices give the same canonical token list."""
+    from pycistopic_b200 import Corpus
+    X = sp.csr_matrix(m.T)
+    a = Corpus.from_regions_by_cells(m)
+    rng = np.random.default_rng(shuffle_seed)
+    indptr, indices = X.indptr.astype(np.int64), X.indices.copy()
+    for d in range(X.shape[0]):
+        seg = indices[indptr[d]:indptr[d + 1]]
+        rng.shuffle(seg)
+    Y = sp.csr_matrix((np.ones(len(indices), np.int32), indices, indptr), shape=X.shape)
+    b = Corpus.from_cells_by_regions(Y)
+    wa, da = a.token_lists()
+    wb, db = b.token_lists()
+    assert np.array_equal(wa, wb) and np.array_equal(da, db) and a.n_tokens == X.nnz
+    a.close()
+    b.close()
