@@ -317,10 +317,15 @@ def run_adlda_leg(args, dev, rank, world, local_rank, shape=None):
         ex.step()
         stream = shard.stream
 
+        # async: one round after each half of the cell queue, so that what a rank sees of the others is half a sweep
+        # to one sweep old (one round per sweep: one to two sweeps, which lags the transient)
+        parts = args.async_parts if exchange == "async" else 1
+
         def sweep():
-            ex.before_sweep()
-            shard.sweep_part(0, 1)
-            ex.after_sweep()
+            for part in range(parts):
+                ex.before_sweep()
+                shard.sweep_part(part, parts)
+                ex.after_sweep()
 
         for _ in range(5 + max(args.warmup, 3)):
             sweep()
@@ -390,7 +395,8 @@ def run_adlda_leg(args, dev, rank, world, local_rank, shape=None):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             sample_ms = float(t[0].item())
         out[exchange] = {"tokens_per_s": N_total / (ms * 1e-3), "ms_per_sweep": ms, "ms_sampling_alone": sample_ms,
-                         "ms_exchange_exposed": ms - sample_ms, "sweep_shape": shard.model.sweep_shape,
+                         "ms_exchange_exposed": ms - sample_ms, "rounds_per_sweep": parts,
+                         "sweep_shape": shard.model.sweep_shape,
                          "checks": checks}
         shard.close()
         torch.cuda.empty_cache()
@@ -921,6 +927,7 @@ def main():
                     help="matrix of the single-model AD-LDA leg (C3 = BASELINE configs[2], C4 = configs[3], K = 100)")
     ap.add_argument("--adlda-rank-local-data", action="store_true",
                     help="every rank draws only its own cells (always on for C4)")
+    ap.add_argument("--async-parts", type=int, default=2, help="rounds (= sub-sweeps) per sweep of the async exchange")
     ap.add_argument("--adlda-only", action="store_true", help="skip the model-sweep legs (used for the C4 run)")
     args = ap.parse_args()
     # The contract is ONE JSON line on stdout.  Libraries underneath (NCCL prints its version banner

@@ -236,6 +236,10 @@ int cgs_model_exchange_arena(cgs_model *m, void **ptr, size_t *bytes);
 int cgs_model_exchange_open(cgs_model *m, void *const *peer_arena, int32_t n_ranks, int32_t rank);
 int cgs_model_exchange_round(cgs_model *m, int32_t n_ctas);
 int cgs_model_exchange_wait(cgs_model *m);
+/* Several ranks on ONE device (tests; more shards than GPUs): kernels that wait for each other must not be separate
+ * launches on one GPU, so the rounds of all n_models (<= 8) local ranks go out as ONE cooperative launch (grid =
+ * n_ctas x n_models, co-residency guaranteed); same semantics as calling cgs_model_exchange_round on each. */
+int cgs_exchange_round_local(cgs_model *const *models, int32_t n_models, int32_t n_ctas);
 /* Waits for the exchange stream; *timeouts = barrier waits that gave up after 4 s because a peer never arrived
  * (0 = every round completed; anything else means the tables must not be used). */
 int cgs_model_exchange_status(cgs_model *m, int32_t *timeouts);

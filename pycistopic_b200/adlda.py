@@ -17,8 +17,10 @@ of a sweep) the ranks exchange their ``n_wk`` deltas:
   (``cgs_model_allreduce_delta`` with the process group's ``ncclComm_t``), what a non-Python host calls.
 * ``exchange="async"``: the fused peer-memory round kernel (``csrc/exchange_kernels.cuh``) on a
   high-priority stream BESIDE the sweep: the round that publishes sweep s runs while sweep s + 1
-  samples, so the exchange costs no time of its own; a rank sees the other ranks' counts one to two
-  sweeps late instead of exactly one.  ``rounds_per_sweep`` rounds are chained per sweep.
+  samples, so the exchange costs no time of its own.  With ``sync_per_sweep=1`` a rank sees the other ranks'
+  counts one to two sweeps late (the synchronous schemes: exactly one), which lags the transient by a few per
+  cent; with ``sync_per_sweep=2`` (a round after each half of the cell queue) half a sweep to one sweep late.
+  ``rounds_per_sweep`` rounds can be chained per sweep part.
 
 The reference has no equivalent (its multi-core analogue is Mallet's per-iteration merge of
 per-thread count copies, lda_models.py:572-573).  The orchestration below is independent of the

@@ -1459,14 +1459,8 @@ int cgs_model_exchange_open(cgs_model *m, void *const *peer_arena, int32_t n_ran
     return 0;
 }
 
-int cgs_model_exchange_round(cgs_model *m, int32_t n_ctas) {
-    if (!m) CGS_FAIL("NULL model");
-    if (m->x_ranks < 1) CGS_FAIL("cgs_model_exchange_open has not been called");
+static void fill_exchange_params(cgs_model *m, ExchangeParams &p) {
     cgs_corpus *c = m->corpus;
-    DeviceGuard g(c->device);
-    if (n_ctas <= 0) n_ctas = 64;
-    n_ctas = std::min(n_ctas, c->num_sms);
-    ExchangeParams p;
     p.n_wk = m->d_nwk;
     p.snap = m->d_snap;
     p.n_k = m->d_nk;
@@ -1476,6 +1470,17 @@ int cgs_model_exchange_round(cgs_model *m, int32_t n_ctas) {
     p.n4 = (int64_t)c->n_regions * m->Kp / 4;
     p.Kp4 = m->Kp / 4;
     p.round = ++m->x_round;
+}
+
+int cgs_model_exchange_round(cgs_model *m, int32_t n_ctas) {
+    if (!m) CGS_FAIL("NULL model");
+    if (m->x_ranks < 1) CGS_FAIL("cgs_model_exchange_open has not been called");
+    cgs_corpus *c = m->corpus;
+    DeviceGuard g(c->device);
+    if (n_ctas <= 0) n_ctas = 64;
+    n_ctas = std::min(n_ctas, c->num_sms);
+    ExchangeParams p;
+    fill_exchange_params(m, p);
     nvtxRangePushA("cgs_model_exchange_round");
     // the round starts once everything enqueued on the model's stream so far has finished, and then runs BESIDE
     // whatever the caller enqueues there next (the next sweep)
@@ -1488,6 +1493,37 @@ int cgs_model_exchange_round(cgs_model *m, int32_t n_ctas) {
     m->x_pending = true;
     m->launches += 1;
     m->x_launches += 1;
+    return 0;
+}
+
+int cgs_exchange_round_local(cgs_model *const *models, int32_t n_models, int32_t n_ctas) {
+    if (!models) CGS_FAIL("NULL argument");
+    if (n_models < 1 || n_models > kMaxLocalRanks) CGS_FAIL("n_models out of range");
+    for (int i = 0; i < n_models; ++i) {
+        if (!models[i]) CGS_FAIL("NULL model");
+        if (models[i]->x_ranks < 1) CGS_FAIL("cgs_model_exchange_open has not been called");
+        if (models[i]->corpus->device != models[0]->corpus->device) CGS_FAIL("models must share one device");
+        if (models[i]->Kp != models[0]->Kp) CGS_FAIL("models must share n_topics");
+    }
+    cgs_model *lead = models[0];
+    DeviceGuard g(lead->corpus->device);
+    if (n_ctas <= 0) n_ctas = 16;
+    ExchangeParamsMulti a;
+    memset(&a, 0, sizeof a);
+    for (int i = 0; i < n_models; ++i) {
+        CGS_CUDA(cudaEventRecord(models[i]->x_event, models[i]->stream));
+        CGS_CUDA(cudaStreamWaitEvent(lead->x_stream, models[i]->x_event, 0));
+        fill_exchange_params(models[i], a.r[i]);
+    }
+    void *args[] = {&a};
+    CGS_CUDA(cudaLaunchCooperativeKernel((const void *)exchange_round_multi_kernel, dim3((unsigned)n_ctas, (unsigned)n_models),
+                                         dim3(kExchangeThreads), args, sizeof(int) * (size_t)lead->Kp, lead->x_stream));
+    for (int i = 0; i < n_models; ++i) {
+        CGS_CUDA(cudaEventRecord(models[i]->x_done, lead->x_stream));
+        models[i]->x_pending = true;
+    }
+    lead->launches += 1;
+    lead->x_launches += 1;
     return 0;
 }
 

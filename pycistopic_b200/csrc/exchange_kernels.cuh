@@ -79,14 +79,14 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
 
 // All CTAs of all ranks.  `phase` selects the flag row; the last CTA of the rank to arrive publishes the
 // round number in every peer's arena, then every CTA waits until all ranks have published.
-__device__ __forceinline__ void exchange_barrier(const ExchangeParams &p, int phase) {
+__device__ __forceinline__ void exchange_barrier(const ExchangeParams &p, int phase, unsigned n_ctas) {
     __syncthreads();
     uint32_t *mine = p.peers.flags[p.rank];
     if (threadIdx.x == 0) {
         __threadfence_system();
         uint32_t *counter = mine + 2 * kMaxExchangeRanks + phase;
         const unsigned prev = atomicAdd(counter, 1u);
-        if (prev == gridDim.x - 1) {
+        if (prev == n_ctas - 1) {
             *counter = 0;  // next use is in the next round, after both barriers of this one
             __threadfence_system();
             for (int q = 0; q < p.n_ranks; ++q)
@@ -111,13 +111,12 @@ __device__ __forceinline__ void exchange_barrier(const ExchangeParams &p, int ph
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(kExchangeThreads, 4)
-exchange_round_kernel(const ExchangeParams p) {
-    extern __shared__ int x_colsum[];  // Kp ints
+// One round of one rank, executed by n_ctas CTAs of which this is number `cta`.
+__device__ __forceinline__ void exchange_round_body(const ExchangeParams &p, unsigned cta, unsigned n_ctas, int *x_colsum) {
     const int Kp = p.Kp4 * 4;
     for (int k = threadIdx.x; k < Kp; k += blockDim.x) x_colsum[k] = 0;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const int64_t tid0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t stride = (int64_t)n_ctas * blockDim.x;
+    const int64_t tid0 = (int64_t)cta * blockDim.x + threadIdx.x;
     int4 *n_wk = reinterpret_cast<int4 *>(p.n_wk);
     int4 *snap = reinterpret_cast<int4 *>(p.snap);
     int4 *my_delta = p.peers.delta[p.rank];
@@ -141,7 +140,7 @@ exchange_round_kernel(const ExchangeParams p) {
             }
         }
     }
-    exchange_barrier(p, 0);
+    exchange_barrier(p, 0, n_ctas);
 
     // ---- phase 2: reduce the slice this rank owns, hand the sums to everybody -----------------------
     {
@@ -161,7 +160,7 @@ exchange_round_kernel(const ExchangeParams p) {
             for (int q = 0; q < R; ++q) __stcg(p.peers.total[q] + i, t);
         }
     }
-    exchange_barrier(p, 1);
+    exchange_barrier(p, 1, n_ctas);
 
     // ---- phase 3: apply what the other ranks changed ------------------------------------------------
     for (int64_t i0 = tid0; i0 < p.n4; i0 += 4 * stride) {
@@ -192,6 +191,27 @@ exchange_round_kernel(const ExchangeParams p) {
     __syncthreads();
     for (int k = threadIdx.x; k < Kp; k += blockDim.x)
         if (x_colsum[k]) red_add_global_i32(p.n_k + k, x_colsum[k]);
+}
+
+// Production: one launch per rank and round, each rank on its own GPU.
+__global__ void __launch_bounds__(kExchangeThreads, 4)
+exchange_round_kernel(const ExchangeParams p) {
+    extern __shared__ int x_colsum[];  // Kp ints
+    exchange_round_body(p, blockIdx.x, gridDim.x, x_colsum);
+}
+
+// Several ranks that share ONE GPU (tests, and a host that packs more shards than it has GPUs): kernels that wait
+// for each other must not be separate launches on one device -- nothing guarantees they run at the same time
+// (B200_PROFILING.md) -- so all ranks' rounds are ONE cooperative launch: grid = (n_ctas, n_ranks_here), row y
+// executes rank y's round; co-residency of the whole grid is what a cooperative launch guarantees.
+constexpr int kMaxLocalRanks = 8;
+struct ExchangeParamsMulti {
+    ExchangeParams r[kMaxLocalRanks];
+};
+__global__ void __launch_bounds__(kExchangeThreads, 4)
+exchange_round_multi_kernel(const ExchangeParamsMulti a) {
+    extern __shared__ int x_colsum[];
+    exchange_round_body(a.r[blockIdx.y], blockIdx.x, gridDim.x, x_colsum);
 }
 
 // ---- consistency checks ---------------------------------------------------------------------------

@@ -348,6 +348,12 @@ class DeviceModel:
     def exchange_wait(self):
         check(_lib.load().cgs_model_exchange_wait(self._h))
 
+    @staticmethod
+    def exchange_round_local(models, n_ctas: int = 0):
+        """One round of several ranks that share a device, as ONE cooperative launch."""
+        arr = (c_vp * len(models))(*[m._h for m in models])
+        check(_lib.load().cgs_exchange_round_local(arr, len(models), int(n_ctas)))
+
     def exchange_timeouts(self) -> int:
         """Barrier waits of the exchange kernels that gave up (0 = all rounds completed)."""
         n = ctypes.c_int32()

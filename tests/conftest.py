@@ -3,10 +3,6 @@ import sys
 
 import pytest
 
-# The single-GPU exchange tests run several "ranks" on one device, each with its own streams, whose round kernels
-# wait for each other: every stream needs its own hardware queue (default 8), or one rank's kernel could be queued
-# behind the kernel that waits for it.  Must be set before the CUDA context exists.
-os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:

