@@ -304,7 +304,9 @@ def run_adlda_leg(args, dev, rank, world, local_rank, shape=None):
         cp = torch.tensor(cell_ptr_h[cb:ce + 1] - t0, dtype=torch.int64, device=dev)
     torch.cuda.empty_cache()
     out = {}
-    modes = ["nccl", "async"] + (["peer"] if world == 2 else [])
+    modes = ["nccl", "fused", "async"] + (["peer"] if world == 2 else [])
+    if args.adlda_modes:
+        modes = args.adlda_modes.split(",")
     n = max(3, args.steps)
     for exchange in modes:
         corpus = Corpus.from_device_tokens(cp.data_ptr(), tok.data_ptr(), ce - cb, W, t1 - t0, device=local_rank,
@@ -360,7 +362,7 @@ def run_adlda_leg(args, dev, rank, world, local_rank, shape=None):
             hashes = [None] * world
             dist.all_gather_object(hashes, h)
         bad = shard.model.verify_counts(hist.data_ptr())
-        timeouts = shard.model.exchange_timeouts() if exchange == "async" else 0
+        timeouts = shard.model.exchange_timeouts() if exchange in ("async", "fused") else 0
         flags = torch.tensor([float(bad["n_wk"]), float(bad["n_k"]), float(timeouts)], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(flags, op=dist.ReduceOp.MAX)
@@ -404,8 +406,9 @@ def run_adlda_leg(args, dev, rank, world, local_rank, shape=None):
     best = max(out.values(), key=lambda v: v["tokens_per_s"])
     return {"workload": f"{shape}: {D} cells x {W} regions, {N_total} tokens, one K={K_adlda} model, cells sharded "
                         f"over {world} GPU(s), n_wk exchange ({4 * W * ((K_adlda + 3) // 4 * 4) / 1e6:.0f} MB): nccl = "
-                        "delta / all-reduce / apply after every sweep; async = fused peer-memory round kernel beside the "
-                        "next sweep",
+                        "delta kernel / NCCL all-reduce / apply kernel after every sweep; fused = ONE kernel after every "
+                        "sweep (delta, reduce-scatter + all-gather over peer memory, apply); async = fused peer-memory "
+                        "round kernel beside the sweep, one round per half sweep",
             "scaling": "strong", "value": best["tokens_per_s"], "unit": "tokens/s", "per_exchange": out,
             "checks_ok": all(v["checks"]["ok"] for v in out.values()),
             "frac_of_hbm_roofline_per_gpu": b_tok(K_adlda) * best["tokens_per_s"] / world / 1e9 / peak}
@@ -644,7 +647,7 @@ def run_cuda(args):
     import torch.distributed as dist
 
     from pycistopic_b200 import Corpus, DeviceModel, _lib
-    from pycistopic_b200.lda_models import schedule_models
+    from pycistopic_b200.lda_models import schedule_models, schedule_models_split
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -673,27 +676,117 @@ def run_cuda(args):
     torch.cuda.set_stream(stream)
     corpus = Corpus.from_device_tokens(cell_ptr.data_ptr(), tok.data_ptr(), D, W, N, device=local_rank,
                                        keepalive=(cell_ptr, tok))
-    plan = schedule_models(N_TOPICS, world)
-    my_topics = [N_TOPICS[i] for i in plan[rank]]
-    models = []
-    for K in my_topics:
-        m = DeviceModel(corpus, K, ALPHA / K, ETA, seed=MODEL_SEED, stream=stream.cuda_stream)
-        m.init()
-        m.sweep(BURN_IN)
-        models.append(m)
-    torch.cuda.synchronize()
-
-    def one_step(events=None):
-        for j, m in enumerate(models):
-            if events is not None:
-                events[j][0].record(stream)
-            m.sweep(1)
-            if events is not None:
-                events[j][1].record(stream)
-
     def barrier():
         if world > 1:
             dist.barrier()
+
+    # ---- plan -------------------------------------------------------------------------------------
+    # One GPU: every model whole.  Several GPUs: whole models cannot fill them evenly (the K = 50 model alone is
+    # longer than 1/8 of the step), so models are divisible: the GPUs are filled to a common level and a model that
+    # does not fit is continued on the next GPU -- its cells sharded AD-LDA style, one fused exchange kernel per sweep
+    # between the GPUs that share it (lda_models.schedule_models_split).  Costs = sweep times measured here.
+    whole_plan = schedule_models(N_TOPICS, world)
+    my_topics = [N_TOPICS[i] for i in whole_plan[rank]]  # the end-to-end leg keeps whole models
+    costs = None
+    if world > 1 and not args.no_split:
+        mine = {}
+        for i in range(rank, len(N_TOPICS), world):
+            K = N_TOPICS[i]
+            m = DeviceModel(corpus, K, ALPHA / K, ETA, seed=MODEL_SEED, stream=stream.cuda_stream)
+            m.init()
+            m.sweep(BURN_IN)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            m.sweep(4)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            mine[i] = e0.elapsed_time(e1) / 4
+            m.close()
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+        costs = [0.0] * len(N_TOPICS)
+        for g in gathered:
+            for i, v in g.items():
+                costs[i] = v
+        # what every part of a split model pays per sweep: 5 passes over its n_wk table at ~5 TB/s + two barriers
+        overhead = [5.0 * 4 * W * ((K + 3) // 4 * 4) / 5.0e12 * 1e3 + 0.03 for K in N_TOPICS]
+        plan, level = schedule_models_split(costs, world, overhead)
+    else:
+        plan, level = [[(i, 0.0, 1.0) for i in p] for p in whole_plan], None
+
+    # ---- this rank's items ---------------------------------------------------------------------------
+    tok_cum = cell_ptr  # tokens before every cell
+    items = []
+    for (i, f0, f1) in plan[rank]:
+        K = N_TOPICS[i]
+        if f0 <= 0.0 and f1 >= 1.0:
+            m = DeviceModel(corpus, K, ALPHA / K, ETA, seed=MODEL_SEED, stream=stream.cuda_stream)
+            items.append({"i": i, "K": K, "model": m, "corpus": None, "split": False, "tokens": N, "f": (0.0, 1.0)})
+            continue
+        # the cells whose cumulative token fraction lies in [f0, f1): every rank derives the same cuts
+        cuts = torch.searchsorted(tok_cum, torch.tensor([int(round(f0 * N)), int(round(f1 * N))], device=dev))
+        cb = 0 if f0 <= 0.0 else int(cuts[0].item())
+        ce = D if f1 >= 1.0 else int(cuts[1].item())
+        t0, t1 = int(cell_ptr[cb].item()), int(cell_ptr[ce].item())
+        cp = (cell_ptr[cb:ce + 1] - t0).contiguous()
+        tk = tok[t0:t1]
+        c = Corpus.from_device_tokens(cp.data_ptr(), tk.data_ptr(), ce - cb, W, t1 - t0, device=local_rank,
+                                      token_offset=t0, keepalive=(cp, tk))
+        c.set_global_size(D, N)
+        m = DeviceModel(c, K, ALPHA / K, ETA, seed=MODEL_SEED, stream=stream.cuda_stream)
+        items.append({"i": i, "K": K, "model": m, "corpus": c, "split": True, "tokens": t1 - t0, "f": (f0, f1),
+                      "cells": (cb, ce)})
+    # peers of the split models: every rank publishes the arenas of its parts, parts are ordered by their fraction
+    if world > 1:
+        mine = []
+        for it in items:
+            if it["split"]:
+                addr, _ = it["model"].exchange_arena()
+                buf = ctypes.create_string_buffer(64)
+                _lib.check(_lib.load().cgs_ipc_export(ctypes.c_void_p(addr), buf))
+                mine.append((it["i"], it["f"][0], rank, buf.raw))
+        everyone = [None] * world
+        dist.all_gather_object(everyone, mine)
+        parts = {}
+        for lst in everyone:
+            for (i, f0, r, h) in lst:
+                parts.setdefault(i, []).append((f0, r, h))
+        for it in items:
+            if not it["split"]:
+                continue
+            ordered = sorted(parts[it["i"]])
+            addrs, me = [], None
+            for j, (f0, r, h) in enumerate(ordered):
+                if r == rank and abs(f0 - it["f"][0]) < 1e-12:
+                    me = j
+                    addrs.append(it["model"].exchange_arena()[0])
+                else:
+                    ptr_ = ctypes.c_void_p()
+                    _lib.check(_lib.load().cgs_ipc_open(local_rank, ctypes.create_string_buffer(h, 64), ctypes.byref(ptr_)))
+                    addrs.append(ptr_.value)
+            it["peer_addrs"], it["part"], it["n_parts"] = addrs, me, len(ordered)
+            it["partners"] = [r for (_, r, _) in ordered]
+            it["model"].exchange_open(addrs, me)
+        barrier()  # every arena is mapped before the first exchange kernel touches a peer
+    for it in items:
+        it["model"].init()
+        if it["split"]:
+            it["model"].exchange_sync()  # local initial counts -> the global tables on every part
+
+    def one_step(events=None):
+        for j, it in enumerate(items):
+            if events is not None:
+                events[j][0].record(stream)
+            it["model"].sweep(1)
+            if events is not None:
+                events[j][1].record(stream)
+            if it["split"]:
+                it["model"].exchange_sync()
+
+    for _ in range(BURN_IN):
+        one_step()
+    torch.cuda.synchronize()
+    models = [it["model"] for it in items]
 
     for _ in range(max(args.warmup, 0)):
         one_step()
@@ -718,33 +811,78 @@ def run_cuda(args):
     elapsed_ms = e_start.elapsed_time(e_stop)
     launches = sum(m.launch_count for m in models) - launches0
     # ---- the state that was just timed must be exact bookkeeping (every model, device-side recount of z) ----
+    # whole models: recount locally.  split models: the (region, topic) histograms of the parts are summed over the
+    # ranks and every part's replica of n_wk must equal the sum; replicas must hash identically.
     model_checks = {}
-    for K, m in zip(my_topics, models):
-        bad = m.verify_counts()
-        h = m.state_hash()
-        model_checks[K] = {"ok": bad == {"n_dk": 0, "n_wk": 0, "n_k": 0} and h["sum_nwk"] == N and h["sum_nk"] == N,
-                           "mismatches": bad, "sum_nwk": h["sum_nwk"], "loglik_per_token": m.loglikelihood() / N,
-                           "sweeps": m.sweeps_done}
-    per_model_ms = {K: statistics.mean(per_model_events[s][j][0].elapsed_time(per_model_events[s][j][1])
-                                       for s in range(args.steps)) for j, K in enumerate(my_topics)}
+    split_ids = sorted({i for p in plan for (i, f0, f1) in p if not (f0 <= 0.0 and f1 >= 1.0)})
+    hists = {}
+    for i in split_ids:
+        K = N_TOPICS[i]
+        mine_it = next((it for it in items if it["i"] == i), None)
+        if mine_it is not None:
+            h = torch.empty(W * mine_it["model"].padded_topics, dtype=torch.int32, device=dev)
+            ndk_bad = mine_it["model"].region_histogram(h.data_ptr())
+            mine_it["model"].sync()
+            mine_it["ndk_bad"] = ndk_bad
+        else:
+            kp = None
+            h = None
+        # ranks without a part of this model contribute zeros of the same length
+        kp_t = torch.tensor([0 if h is None else h.numel()], device=dev, dtype=torch.int64)
+        dist.all_reduce(kp_t, op=dist.ReduceOp.MAX)
+        if h is None:
+            h = torch.zeros(int(kp_t.item()), dtype=torch.int32, device=dev)
+        dist.all_reduce(h)
+        hists[i] = h
+    item_ms = []
+    for j, it in enumerate(items):
+        m, K = it["model"], it["K"]
+        ms = statistics.mean(per_model_events[s][j][0].elapsed_time(per_model_events[s][j][1]) for s in range(args.steps))
+        item_ms.append({"K": K, "ms": ms, "tokens": it["tokens"], "split": it["split"], "fraction": list(it["f"]),
+                        "rank": rank})
+        if it["split"]:
+            bad = m.verify_counts(hists[it["i"]].data_ptr())
+            bad["n_dk"] = it["ndk_bad"]
+            h = m.state_hash()
+            key = f"{K}[{it['f'][0]:.2f},{it['f'][1]:.2f})"
+            model_checks[key] = {"ok": bad == {"n_dk": 0, "n_wk": 0, "n_k": 0} and h["sum_nwk"] == N and h["sum_nk"] == N
+                                 and m.exchange_timeouts() == 0,
+                                 "mismatches": bad, "sum_nwk": h["sum_nwk"], "hash_nwk": f"{h['hash_nwk']:016x}",
+                                 "loglik_cells_part": m.loglikelihood(1), "sweeps": m.sweeps_done, "split": True}
+        else:
+            bad = m.verify_counts()
+            h = m.state_hash()
+            model_checks[str(K)] = {"ok": bad == {"n_dk": 0, "n_wk": 0, "n_k": 0} and h["sum_nwk"] == N and h["sum_nk"] == N,
+                                    "mismatches": bad, "sum_nwk": h["sum_nwk"], "loglik_per_token": m.loglikelihood() / N,
+                                    "sweeps": m.sweeps_done}
+    hists = None
     if world > 1:
         t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed_ms = float(t.item())
         gathered = [None] * world
-        dist.all_gather_object(gathered, (per_model_ms, launches, model_checks))
-        per_model_ms = {k: v for g in gathered for k, v in g[0].items()}
+        dist.all_gather_object(gathered, (item_ms, launches, model_checks))
+        item_ms = [x for g in gathered for x in g[0]]
         launches = sum(g[1] for g in gathered)
         model_checks = {k: v for g in gathered for k, v in g[2].items()}
+    # replicas of a split model must be identical on all its parts
+    by_model = {}
+    for k, v in model_checks.items():
+        if v.get("split"):
+            by_model.setdefault(k.split("[")[0], set()).add(v["hash_nwk"])
+    replicas_ok = all(len(hs) == 1 for hs in by_model.values())
     checks = {"counts_are_histogram_of_z": all(v["ok"] for v in model_checks.values()),
+              "split_model_replicas_identical": replicas_ok if by_model else None,
               "tokens": N, "per_model": {str(k): v for k, v in sorted(model_checks.items())}}
+    per_model_ms = {x["K"]: x["ms"] for x in item_ms if not x["split"]}
     total_tokens = float(N) * len(N_TOPICS) * args.steps
     value = total_tokens / (elapsed_ms * 1e-3)
 
     # ---- roofline of the dominant kernel: the K = 50 sweep ------------------------------------
-    k_dom = max(per_model_ms, key=lambda k: per_model_ms[k])
+    dom = max(item_ms, key=lambda x: (x["ms"], x["K"]))  # the longest launch of the step
+    k_dom, n_dom, ms_dom = dom["K"], dom["tokens"], dom["ms"]
     peak, peak_src = hbm_peak()
-    achieved = b_tok(k_dom) * N / (per_model_ms[k_dom] * 1e-3) / 1e9
+    achieved = b_tok(k_dom) * n_dom / (ms_dom * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "sweep_traffic.json")
     if os.path.exists(tpath):
@@ -756,7 +894,13 @@ def run_cuda(args):
     roofline = {"bound": "hbm", "kernel": f"sweep_kernel (K={k_dom})", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_unit": "bytes per launch (ncu --set full, "
                 "profiles/sweep_traffic.json)", "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": b_tok(k_dom) * N, "ms_per_launch": per_model_ms[k_dom],
+                "algorithmic_bytes_per_launch": b_tok(k_dom) * n_dom, "ms_per_launch": ms_dom,
+                "tokens_per_launch": n_dom,
+                "per_launch": [{"K": x["K"], "rank": x["rank"], "fraction_of_cells": [round(f, 3) for f in x["fraction"]],
+                                "tokens": x["tokens"], "ms": round(x["ms"], 4),
+                                "gtok_s": round(x["tokens"] / x["ms"] / 1e6, 3),
+                                "frac": round(b_tok(x["K"]) * x["tokens"] / (x["ms"] * 1e-3) / 1e9 / peak, 4)}
+                               for x in sorted(item_ms, key=lambda x: (x["K"], x["fraction"][0]))],
                 "per_model": {str(k): {"ms": round(v, 4), "gtok_s": round(N / v / 1e6, 3),
                                        "frac": round(b_tok(k) * N / (v * 1e-3) / 1e9 / peak, 4)}
                               for k, v in sorted(per_model_ms.items())}}
@@ -844,9 +988,17 @@ def run_cuda(args):
                         "cpu": cpu_model_name(), "host_cores": os.cpu_count(), "seconds": dt}
 
     # ---- AD-LDA leg (C3, one model sharded by cells) --------------------------------------------
-    for m in models:
-        m.close()
-    models = []
+    for it in items:
+        it["model"].sync()
+    barrier()
+    for it in items:
+        for a_ in it.get("peer_addrs", []):
+            if a_ != it["model"].exchange_arena()[0]:
+                _lib.load().cgs_ipc_close(local_rank, ctypes.c_void_p(a_))
+        it["model"].close()
+        if it["corpus"] is not None:
+            it["corpus"].close()
+    items, models = [], []
     corpus.close()
     corpus._keepalive = None
     del cell_ptr, tok
@@ -892,8 +1044,14 @@ def run_cuda(args):
             "dtype": "int32 counts, fp32 conditional, u16 topics", "data": "synthetic",
             "config": {"workload": workload_text(D, W, N),
                        "n_topics": N_TOPICS, "tokens": N, "cells": D, "regions": W,
-                       "sharding": "one model per GPU, longest first" if world > 1 else "all models on one GPU",
-                       "plan": {str(r): [N_TOPICS[i] for i in plan[r]] for r in range(world)},
+                       "sharding": ("GPUs filled to a common level with measured sweep times; a model that does not fit "
+                                    "continues on the next GPU (cells sharded, one fused exchange kernel per sweep)"
+                                    if costs is not None else
+                                    "one model per GPU, longest first" if world > 1 else "all models on one GPU"),
+                       "plan": {str(r): [[N_TOPICS[i], round(f0, 3), round(f1, 3)] for (i, f0, f1) in plan[r]]
+                                for r in range(world)},
+                       "measured_sweep_ms": None if costs is None else {str(K): round(c, 4) for K, c in zip(N_TOPICS, costs)},
+                       "level_ms": level,
                        "burn_in_sweeps": BURN_IN, "e2e_sweeps_per_call": E2E_SWEEPS,
                        "l2": "inputs larger than L2: every model streams 6 B/token of tokens+topics "
                              f"({6 * N / 1e6:.0f} MB) per sweep and the step cycles through {len(my_topics)} models"},
@@ -919,6 +1077,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-adlda", action="store_true")
     ap.add_argument("--no-impute", action="store_true")
+    ap.add_argument("--n-topics", default="", help="debugging: comma-separated n_topics list instead of the C2 sweep")
+    ap.add_argument("--no-split", action="store_true", help="whole models only (round-1 schedule) at more than one GPU")
     ap.add_argument("--no-parity", action="store_true", help="skip the frozen-oracle-trace check (rank 0, ~1 min)")
     ap.add_argument("--no-c4", action="store_true", help="skip the atlas-scale AD-LDA leg (only runs at >= 8 GPUs)")
     ap.add_argument("--no-c5", action="store_true", help="skip the atlas-scale imputation leg")
@@ -927,9 +1087,13 @@ def main():
                     help="matrix of the single-model AD-LDA leg (C3 = BASELINE configs[2], C4 = configs[3], K = 100)")
     ap.add_argument("--adlda-rank-local-data", action="store_true",
                     help="every rank draws only its own cells (always on for C4)")
+    ap.add_argument("--adlda-modes", default="", help="comma-separated exchange modes of the AD-LDA legs (default: all)")
     ap.add_argument("--async-parts", type=int, default=2, help="rounds (= sub-sweeps) per sweep of the async exchange")
     ap.add_argument("--adlda-only", action="store_true", help="skip the model-sweep legs (used for the C4 run)")
     args = ap.parse_args()
+    if args.n_topics:
+        global N_TOPICS
+        N_TOPICS = [int(k) for k in args.n_topics.split(",")]
     # The contract is ONE JSON line on stdout.  Libraries underneath (NCCL prints its version banner
     # there) write to file descriptor 1 directly, so that descriptor is pointed at stderr while the
     # benchmark runs and the JSON line goes to the real stdout.

@@ -236,6 +236,13 @@ int cgs_model_exchange_arena(cgs_model *m, void **ptr, size_t *bytes);
 int cgs_model_exchange_open(cgs_model *m, void *const *peer_arena, int32_t n_ranks, int32_t rank);
 int cgs_model_exchange_round(cgs_model *m, int32_t n_ctas);
 int cgs_model_exchange_wait(cgs_model *m);
+/* The synchronous variant, for when nothing overlaps the exchange (between two sweeps): ONE kernel on the model's own
+ * stream filling the GPU -- delta = n_wk - G (G = the global table of the last exchange, kept in the arena's receive
+ * buffer), slice owners add all ranks' deltas to G and store the new G into every rank's receive buffer over NVLink,
+ * n_wk = G, n_k = its column sums.  5 table passes of local traffic instead of the 8 of delta_compute + all-reduce +
+ * delta_apply; same statistics as those.  Do not mix with cgs_model_exchange_round on one model. */
+int cgs_model_exchange_sync(cgs_model *m, int32_t n_ctas);
+int cgs_exchange_sync_local(cgs_model *const *models, int32_t n_models, int32_t n_ctas);
 /* Several ranks on ONE device (tests; more shards than GPUs): kernels that wait for each other must not be separate
  * launches on one GPU, so the rounds of all n_models (<= 8) local ranks go out as ONE cooperative launch (grid =
  * n_ctas x n_models, co-residency guaranteed); same semantics as calling cgs_model_exchange_round on each. */

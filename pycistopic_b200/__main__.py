@@ -69,7 +69,7 @@ def run_topic_modeling_lda(args):
                             devices=list(range(max(1, min(n_gpu, args.parallel)))))
     print(f'\nWriting topic modeling output to "{out}"...')
     with open(out, "wb") as fh:
-        pickle.dump(models, fh)
+        pickle.dump(compat.pickle_ready(models), fh)
     return 0
 
 

@@ -345,6 +345,7 @@ struct cgs_model {
     ExchangePeers xpeers;
     int x_ranks = 0, x_rank = 0;
     uint32_t x_round = 0;
+    int x_sync_blocks = 0;
     cudaStream_t x_stream = nullptr;
     cudaEvent_t x_event = nullptr, x_done = nullptr;
     bool x_pending = false;
@@ -777,6 +778,11 @@ static int rebuild_counts(cgs_model *m) {
     CGS_CUDA(cudaMemsetAsync(m->d_nwk, 0, sizeof(int32_t) * W * Kp, m->stream));
     CGS_CUDA(cudaMemsetAsync(m->d_ndk, 0, sizeof(int32_t) * D * Kp, m->stream));
     CGS_CUDA(cudaMemsetAsync(m->d_nk, 0, sizeof(int32_t) * Kp, m->stream));
+    if (m->d_arena) {
+        // the tables are about to hold LOCAL counts again: the exchange state restarts from "nothing published"
+        CGS_CUDA(cudaMemsetAsync(m->d_arena, 0, 2 * W * Kp * sizeof(int32_t), m->stream));
+        if (m->d_snap) CGS_CUDA(cudaMemsetAsync(m->d_snap, 0, W * Kp * sizeof(int32_t), m->stream));
+    }
     const int blocks = std::max(1, std::min(c->n_cells, c->num_sms * 8));
     count_kernel<<<blocks, 256, sizeof(int) * Kp, m->stream>>>(c->d_cell_ptr, c->d_tok_region, m->d_z, c->n_cells, m->K,
                                                               m->Kp, m->d_nwk, m->d_ndk, m->d_nk);
@@ -1012,7 +1018,8 @@ int cgs_model_set_sweep_shape(cgs_model *m, int32_t lanes_per_token, int32_t war
     const int chunks = (m->K + 3) / 4;
     const int ch = (chunks + t - 1) / t;
     if (ch > kMaxChunksPerLane || t * ch * 4 > kMaxTopics) CGS_FAIL("lanes_per_token too small for this n_topics");
-    if (warps_per_cell * 32 > (ch <= 4 ? 512 : ch <= 6 ? 384 : 256)) CGS_FAIL("too many warps per cell for this many chunks per lane");
+    if (warps_per_cell * 32 > (ch <= 2 ? 256 : ch <= 4 ? 512 : ch <= 6 ? 384 : 256))
+        CGS_FAIL("too many warps per cell for this many chunks per lane");
     m->tpt = t;
     m->ch = ch;
     m->threads = warps_per_cell * 32;
@@ -1496,7 +1503,42 @@ int cgs_model_exchange_round(cgs_model *m, int32_t n_ctas) {
     return 0;
 }
 
+int cgs_model_exchange_sync(cgs_model *m, int32_t n_ctas) {
+    if (!m) CGS_FAIL("NULL model");
+    if (m->x_ranks < 1) CGS_FAIL("cgs_model_exchange_open has not been called");
+    cgs_corpus *c = m->corpus;
+    DeviceGuard g(c->device);
+    if (m->x_sync_blocks == 0) {
+        int per_sm = 0;
+        CGS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, exchange_sync_kernel, kExchangeThreads,
+                                                                sizeof(int) * (size_t)m->Kp));
+        m->x_sync_blocks = c->num_sms * std::max(1, std::min(per_sm, 4));
+    }
+    // every CTA waits at the cross-rank barriers: the grid must be resident at once
+    n_ctas = n_ctas <= 0 ? m->x_sync_blocks : std::min(n_ctas, m->x_sync_blocks);
+    ExchangeParams p;
+    fill_exchange_params(m, p);
+    nvtxRangePushA("cgs_model_exchange_sync");
+    CGS_CUDA(cudaMemsetAsync(m->d_nk, 0, sizeof(int32_t) * (size_t)m->Kp, m->stream));
+    exchange_sync_kernel<<<n_ctas, kExchangeThreads, sizeof(int) * (size_t)m->Kp, m->stream>>>(p);
+    CGS_CUDA(cudaGetLastError());
+    nvtxRangePop();
+    m->launches += 1;
+    m->x_launches += 1;
+    return 0;
+}
+
+static int exchange_local(cgs_model *const *models, int32_t n_models, int32_t n_ctas, int sync_variant);
+
 int cgs_exchange_round_local(cgs_model *const *models, int32_t n_models, int32_t n_ctas) {
+    return exchange_local(models, n_models, n_ctas, 0);
+}
+
+int cgs_exchange_sync_local(cgs_model *const *models, int32_t n_models, int32_t n_ctas) {
+    return exchange_local(models, n_models, n_ctas, 1);
+}
+
+static int exchange_local(cgs_model *const *models, int32_t n_models, int32_t n_ctas, int sync_variant) {
     if (!models) CGS_FAIL("NULL argument");
     if (n_models < 1 || n_models > kMaxLocalRanks) CGS_FAIL("n_models out of range");
     for (int i = 0; i < n_models; ++i) {
@@ -1514,8 +1556,13 @@ int cgs_exchange_round_local(cgs_model *const *models, int32_t n_models, int32_t
         CGS_CUDA(cudaEventRecord(models[i]->x_event, models[i]->stream));
         CGS_CUDA(cudaStreamWaitEvent(lead->x_stream, models[i]->x_event, 0));
         fill_exchange_params(models[i], a.r[i]);
+        if (sync_variant) {
+            CGS_CUDA(cudaMemsetAsync(models[i]->d_nk, 0, sizeof(int32_t) * (size_t)models[i]->Kp, models[i]->stream));
+            CGS_CUDA(cudaEventRecord(models[i]->x_event, models[i]->stream));
+            CGS_CUDA(cudaStreamWaitEvent(lead->x_stream, models[i]->x_event, 0));
+        }
     }
-    void *args[] = {&a};
+    void *args[] = {&a, &sync_variant};
     CGS_CUDA(cudaLaunchCooperativeKernel((const void *)exchange_round_multi_kernel, dim3((unsigned)n_ctas, (unsigned)n_models),
                                          dim3(kExchangeThreads), args, sizeof(int) * (size_t)lead->Kp, lead->x_stream));
     for (int i = 0; i < n_models; ++i) {

@@ -193,6 +193,89 @@ __device__ __forceinline__ void exchange_round_body(const ExchangeParams &p, uns
         if (x_colsum[k]) red_add_global_i32(p.n_k + k, x_colsum[k]);
 }
 
+// ---- synchronous variant: the cheapest exchange when nothing overlaps it ---------------------------------------------
+// Between two sweeps (no sampler running) a rank needs no separate snapshot: the receive buffer `total` of the arena
+// holds G, the global table as of the last exchange (all zero before the first one), and the round is
+//   phase 1   delta = n_wk - G                                         (read 2, write 1 table)
+//   barrier
+//   phase 2   owner of a slice: G' = G + sum_q delta_q, written into EVERY rank's receive buffer over NVLink
+//   barrier
+//   phase 3   n_wk = G';  n_k = column sums of G'                        (read 1, write 1 table)
+// i.e. 5 table passes of local traffic instead of the 8 of delta_compute + all-reduce + delta_apply, and 2 (R-1)/R
+// tables over NVLink.  Statistically identical to the all-reduce scheme (every rank samples a sweep against the
+// global counts of the previous exchange plus its own live changes).
+__device__ __forceinline__ void exchange_sync_body(const ExchangeParams &p, unsigned cta, unsigned n_ctas, int *x_colsum) {
+    const int Kp = p.Kp4 * 4;
+    for (int k = threadIdx.x; k < Kp; k += blockDim.x) x_colsum[k] = 0;
+    const int64_t stride = (int64_t)n_ctas * blockDim.x;
+    const int64_t tid0 = (int64_t)cta * blockDim.x + threadIdx.x;
+    int4 *n_wk = reinterpret_cast<int4 *>(p.n_wk);
+    int4 *my_delta = p.peers.delta[p.rank];
+    int4 *my_g = p.peers.total[p.rank];
+
+    for (int64_t i0 = tid0; i0 < p.n4; i0 += 4 * stride) {
+        int4 a[4], g[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t i = i0 + u * stride;
+            if (i < p.n4) { a[u] = __ldcs(n_wk + i); g[u] = __ldcs(my_g + i); }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t i = i0 + u * stride;
+            if (i < p.n4) __stcg(my_delta + i, make_int4(a[u].x - g[u].x, a[u].y - g[u].y, a[u].z - g[u].z, a[u].w - g[u].w));
+        }
+    }
+    exchange_barrier(p, 0, n_ctas);
+    {
+        const int R = p.n_ranks;
+        const int64_t lo = p.n4 * p.rank / R, hi = p.n4 * (p.rank + 1) / R;
+        for (int64_t i = lo + tid0; i < hi; i += stride) {
+            int4 t = __ldcs(my_g + i);
+            for (int q0 = 0; q0 < R; q0 += 8) {
+                int4 v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (q0 + j < R) v[j] = ld_sys_v4(p.peers.delta[q0 + j] + i);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (q0 + j < R) { t.x += v[j].x; t.y += v[j].y; t.z += v[j].z; t.w += v[j].w; }
+            }
+            for (int q = 0; q < R; ++q) __stcg(p.peers.total[q] + i, t);
+        }
+    }
+    exchange_barrier(p, 1, n_ctas);
+    for (int64_t i0 = tid0; i0 < p.n4; i0 += 4 * stride) {
+        int4 g[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t i = i0 + u * stride;
+            if (i < p.n4) g[u] = ld_sys_v4(my_g + i);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t i = i0 + u * stride;
+            if (i >= p.n4) continue;
+            __stcg(n_wk + i, g[u]);  // stays in L2 for the sweep that follows
+            const int col = (int)(i % p.Kp4) * 4;
+            if (g[u].x) atomicAdd(&x_colsum[col + 0], g[u].x);
+            if (g[u].y) atomicAdd(&x_colsum[col + 1], g[u].y);
+            if (g[u].z) atomicAdd(&x_colsum[col + 2], g[u].z);
+            if (g[u].w) atomicAdd(&x_colsum[col + 3], g[u].w);
+        }
+    }
+    __syncthreads();
+    // n_k was zeroed by the host before the launch
+    for (int k = threadIdx.x; k < Kp; k += blockDim.x)
+        if (x_colsum[k]) red_add_global_i32(p.n_k + k, x_colsum[k]);
+}
+
+__global__ void __launch_bounds__(kExchangeThreads, 4)
+exchange_sync_kernel(const ExchangeParams p) {
+    extern __shared__ int x_colsum[];
+    exchange_sync_body(p, blockIdx.x, gridDim.x, x_colsum);
+}
+
 // Production: one launch per rank and round, each rank on its own GPU.
 __global__ void __launch_bounds__(kExchangeThreads, 4)
 exchange_round_kernel(const ExchangeParams p) {
@@ -209,9 +292,10 @@ struct ExchangeParamsMulti {
     ExchangeParams r[kMaxLocalRanks];
 };
 __global__ void __launch_bounds__(kExchangeThreads, 4)
-exchange_round_multi_kernel(const ExchangeParamsMulti a) {
+exchange_round_multi_kernel(const ExchangeParamsMulti a, int sync_variant) {
     extern __shared__ int x_colsum[];
-    exchange_round_body(a.r[blockIdx.y], blockIdx.x, gridDim.x, x_colsum);
+    if (sync_variant) exchange_sync_body(a.r[blockIdx.y], blockIdx.x, gridDim.x, x_colsum);
+    else exchange_round_body(a.r[blockIdx.y], blockIdx.x, gridDim.x, x_colsum);
 }
 
 // ---- consistency checks ---------------------------------------------------------------------------

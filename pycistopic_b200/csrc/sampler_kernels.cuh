@@ -320,12 +320,19 @@ __device__ __forceinline__ int sweep_step(int4 (&buf)[CH], const char *nwk_lane,
     return zn;
 }
 
+// Shapes whose steps are too short to hide the token stream's latency behind (see the kernel): one or two lanes
+// per token and at most three chunks per lane (K <= 24; beyond that the registers it costs spill).
+template <int TPT, int CH> constexpr bool kDeepTokenPrefetch = (TPT <= 2 && CH <= 3);
+
 // Register budget (measured on B200: occupancy beats the few spills it costs; profiles/r1_shape_scan_*.txt):
-// 32 warps per SM at 64 registers up to 4 chunks per lane, 24 warps at 80 registers for 5-6 chunks, 16 warps
-// beyond.  A cell may take up to 16 warps (512 threads) for CH <= 4, 12 (384) for CH 5-6, 8 (256) beyond.
+// 40 warps per SM at 48 registers up to 2 chunks per lane (the latency-bound shapes, K <= 16: the deeper token
+// prefetch costs 7 registers, which at the former 64-register budget took a fifth of the resident warps away --
+// profiles/r2_sweep_k2_deep_v1_ncu_summary.csv), 32 warps at 64 registers up to 4 chunks, 24 warps at 80 registers
+// for 5-6 chunks, 16 warps beyond.  A cell may take up to 8 warps (256 threads) for CH <= 2, 16 (512) for CH 3-4,
+// 12 (384) for CH 5-6, 8 (256) beyond.
 template <int CH, typename R = float> struct SweepBounds {
-    static constexpr int kThreads = CH <= 4 ? 512 : CH <= 6 ? 384 : 256;
-    static constexpr int kMinBlocks = sizeof(R) == 8 ? 1 : 2;  // the fp64 A/B build trades occupancy for registers
+    static constexpr int kThreads = CH <= 2 ? 256 : CH <= 4 ? 512 : CH <= 6 ? 384 : 256;
+    static constexpr int kMinBlocks = sizeof(R) == 8 ? 1 : CH <= 2 ? 5 : 2;  // the fp64 A/B build trades occupancy for registers
 };
 
 template <int TPT, int CH, typename R = float>
@@ -405,105 +412,244 @@ sweep_kernel(const SweepParams p) {
         uint16_t *z_cell = p.z + t0;
         const uint64_t gi0 = (uint64_t)(p.token_offset + t0) + (uint64_t)lane;
 
-        int sidx = warp;  // super-batch index in the rotated sequence
-        int off = 0;      // first token of the current batch, relative to the cell
-        int nbq = 0;      // batches in the current super-batch
-        bool more = sidx < nsuper;
-        if (more) {
-            const int b0 = sidx < nsup1 ? rot + 4 * sidx : 4 * (sidx - nsup1);
-            nbq = min(4, (sidx < nsup1 ? nbatch : rot) - b0);
-            off = b0 << 5;
-        }
-        int w_j = 0, pk_j = 0;
-        int w_c = 0, pk_c = 0x200;  // the group sampled by the next step
-        Philox4 rnd = {0u, 0u, 0u, 0u};
-        int bq = 0;  // batch inside the super-batch
-        if (more) {
-            const bool valid = (off + lane) < ntok;
-            const int ic = valid ? off + lane : ntok - 1;
-            w_j = __ldg(tok_cell + ic);
-            const uint64_t gi = (gi0 + (uint64_t)off) & p.rng_index_mask;
-            rnd = philox4x32_10((uint32_t)gi, (uint32_t)(gi >> 32), p.sweep, 0u, p.seed_lo, p.seed_hi);
-            pk_j = pack_token(rnd.x, (int)z_cell[ic], valid);
-            w_c = (TPT > 1) ? __shfl_sync(FULL, w_j, 0, TPT) : w_j;
-            pk_c = (TPT > 1) ? __shfl_sync(FULL, pk_j, 0, TPT) : pk_j;
-            const char *row = nwk_lane + (uint64_t)((uint32_t)w_c) * rowbytes;
-            const int oc = ((pk_c & 0x1ff) >> 2) >> log2_tpt<TPT>();
+        // Position of a batch in this warp's walk over the cell's rotated batch sequence.
+        struct Pos {
+            int sidx, off, bq, nbq;
+            bool more;
+        };
+        auto start_super = [&](Pos &q) {  // q.sidx is set: locate its super-batch
+            q.more = q.sidx < nsuper;
+            q.bq = 0;
+            if (q.more) {
+                const int b0 = q.sidx < nsup1 ? rot + 4 * q.sidx : 4 * (q.sidx - nsup1);
+                q.nbq = min(4, (q.sidx < nsup1 ? nbatch : rot) - b0);
+                q.off = b0 << 5;
+            }
+        };
+        auto advance = [&](Pos &q) {
+            q.off += 32;
+            q.bq += 1;
+            if (q.bq == q.nbq) {
+                q.sidx += nwarps;
+                start_super(q);
+            }
+        };
+
+        if constexpr (kDeepTokenPrefetch<TPT, CH>) {
+            // ---- K <= 16 (one or two lanes per token): a step is so short that the chain "token ids (streamed from
+            // HBM) -> row address -> row (L2) -> sample" is what a warp waits for (ncu, round 1: long-scoreboard 13.5 of
+            // 24 stall cycles per issue at K = 2).  The token ids and topics are therefore requested TWO batches ahead:
+            // they have a whole step to arrive before the step that turns them into row requests.
+            Pos pn;  // position of the batch after the current one
+            pn.sidx = warp; pn.off = 0; pn.nbq = 0;
+            start_super(pn);
+            int off = pn.off;
+            bool more = pn.more;
+            int w_j = 0, pk_j = 0;
+            int w_c = 0, pk_c = 0x200;  // the group sampled by the next step
+            Philox4 rnd = {0u, 0u, 0u, 0u};
+            int w_n = 0, z_n = 0, pkp_n = 0x200;  // next batch: region ids, topics (in flight), random bits | validity
+            if (more) {
+                const bool valid = (off + lane) < ntok;
+                const int ic = valid ? off + lane : ntok - 1;
+                w_j = __ldg(tok_cell + ic);
+                const uint64_t gi = (gi0 + (uint64_t)off) & p.rng_index_mask;
+                rnd = philox4x32_10((uint32_t)gi, (uint32_t)(gi >> 32), p.sweep, 0u, p.seed_lo, p.seed_hi);
+                pk_j = pack_token(rnd.x, (int)z_cell[ic], valid);
+                w_c = (TPT > 1) ? __shfl_sync(FULL, w_j, 0, TPT) : w_j;
+                pk_c = (TPT > 1) ? __shfl_sync(FULL, pk_j, 0, TPT) : pk_j;
+                const char *row = nwk_lane + (uint64_t)((uint32_t)w_c) * rowbytes;
+                const int oc = ((pk_c & 0x1ff) >> 2) >> log2_tpt<TPT>();
 #pragma unroll
-            for (int c = 0; c < CH; ++c) {
-                const int rc = rot_chunk<CH>(c, oc);
-                if (rc < lim) buf[c] = __ldcg(reinterpret_cast<const int4 *>(row + rc * (TPT * 16)));
-            }
-        }
-        int since_refresh = 0;
-        while (more) {
-            // ---- the batch after this one (its tokens feed the last step's prefetch) ---------------
-            int sidx_n = sidx, off_n = off + 32, bq_n = bq + 1;
-            if (bq_n == nbq) {
-                bq_n = 0;
-                sidx_n = sidx + nwarps;
-                const int b0 = sidx_n < nsup1 ? rot + 4 * sidx_n : 4 * (sidx_n - nsup1);
-                nbq = min(4, (sidx_n < nsup1 ? nbatch : rot) - b0);
-                off_n = b0 << 5;
-            }
-            const bool more_n = sidx_n < nsuper;
-            int w_n = w_j, pk_n = pk_j | 0x200;
-            if (more_n) {
-                const bool valid_n = (off_n + lane) < ntok;
-                const int icn = valid_n ? off_n + lane : ntok - 1;
-                w_n = __ldg(tok_cell + icn);
-                if (bq_n == 0) {  // one Philox call per lane serves the four batches of a super-batch
-                    const uint64_t gi = (gi0 + (uint64_t)off_n) & p.rng_index_mask;
-                    rnd = philox4x32_10((uint32_t)gi, (uint32_t)(gi >> 32), p.sweep, 0u, p.seed_lo, p.seed_hi);
+                for (int c = 0; c < CH; ++c) {
+                    const int rc = rot_chunk<CH>(c, oc);
+                    if (rc < lim) buf[c] = __ldcg(reinterpret_cast<const int4 *>(row + rc * (TPT * 16)));
                 }
-                const uint32_t bits = bq_n == 0 ? rnd.x : bq_n == 1 ? rnd.y : bq_n == 2 ? rnd.z : rnd.w;
-                pk_n = pack_token(bits, (int)z_cell[icn], valid_n);
-            }
-
-            // ---- keep the topic totals live: publish this cell's n_k deltas, re-read n_k ---------
-            if (++since_refresh > p.refresh_every) {
-                since_refresh = 1;
-                for (int k = lane; k < K; k += 32) {
-                    const int cur = lds_i(s_ndk + k * 4);
-                    const int d = cur - atoms_exch(s_pub + k * 4, cur);
-                    if (d != 0) red_add_i32(p.n_k + k, d);
-                    const R den = (R)ld_volatile_i32(p.n_k_read + k) + etaW;
-                    const R inv = Real<R>::rcp(den);
-                    Real<R>::sts(s_den + k * RB, den);
-                    Real<R>::sts(s_inv + k * RB, inv);
-                    Real<R>::sts(s_f + k * RB, ((R)lds_i(s_ndk + k * 4) + alpha) * inv);
+                advance(pn);
+                if (pn.more) {
+                    const bool valid_n = (pn.off + lane) < ntok;
+                    const int icn = valid_n ? pn.off + lane : ntok - 1;
+                    w_n = __ldg(tok_cell + icn);
+                    z_n = (int)z_cell[icn];
+                    if (pn.bq == 0) {
+                        const uint64_t gn = (gi0 + (uint64_t)pn.off) & p.rng_index_mask;
+                        rnd = philox4x32_10((uint32_t)gn, (uint32_t)(gn >> 32), p.sweep, 0u, p.seed_lo, p.seed_hi);
+                    }
+                    const uint32_t bits = pn.bq == 0 ? rnd.x : pn.bq == 1 ? rnd.y : pn.bq == 2 ? rnd.z : rnd.w;
+                    pkp_n = pack_token(bits, 0, valid_n);
                 }
-                __syncwarp();
             }
+            int since_refresh = 0;
+            while (more) {
+                // ---- two batches ahead: request region ids and topics ----------------------------------
+                const int off_n = pn.off;
+                const bool more_n = pn.more;
+                int w_nn = 0, z_nn = 0, pkp_nn = 0x200;
+                advance(pn);  // pn is now the batch after the next one
+                if (more_n && pn.more) {
+                    const bool valid_nn = (pn.off + lane) < ntok;
+                    const int icnn = valid_nn ? pn.off + lane : ntok - 1;
+                    w_nn = __ldg(tok_cell + icnn);
+                    z_nn = (int)z_cell[icnn];
+                    if (pn.bq == 0) {  // one Philox call per lane serves the four batches of a super-batch
+                        const uint64_t gn = (gi0 + (uint64_t)pn.off) & p.rng_index_mask;
+                        rnd = philox4x32_10((uint32_t)gn, (uint32_t)(gn >> 32), p.sweep, 0u, p.seed_lo, p.seed_hi);
+                    }
+                    const uint32_t bits = pn.bq == 0 ? rnd.x : pn.bq == 1 ? rnd.y : pn.bq == 2 ? rnd.z : rnd.w;
+                    pkp_nn = pack_token(bits, 0, valid_nn);
+                }
+                // the next batch's topics were requested one step ago
+                if (!more_n) { w_n = w_j; pkp_n = 0x200; z_n = 0; }
+                const int pk_n = pkp_n | z_n;
 
-            int zn_j = pk_j & 0x1ff;
-            if (TPT == 1) {
-                // one token per lane: the lane's own next-batch token is the next group
-                zn_j = sweep_step<TPT, CH, R>(buf, nwk_lane, rowbytes, lim, w_j, pk_j, w_n, pk_n, sm, sub, gbase, lane,
-                                           alpha, eta, K, p.nwk_write_delta);
-            } else {
-                constexpr int UNR = (TPT <= 8) ? TPT : 2;
+                // ---- keep the topic totals live: publish this cell's n_k deltas, re-read n_k ---------
+                if (++since_refresh > p.refresh_every) {
+                    since_refresh = 1;
+                    for (int k = lane; k < K; k += 32) {
+                        const int cur = lds_i(s_ndk + k * 4);
+                        const int d = cur - atoms_exch(s_pub + k * 4, cur);
+                        if (d != 0) red_add_i32(p.n_k + k, d);
+                        const R den = (R)ld_volatile_i32(p.n_k_read + k) + etaW;
+                        const R inv = Real<R>::rcp(den);
+                        Real<R>::sts(s_den + k * RB, den);
+                        Real<R>::sts(s_inv + k * RB, inv);
+                        Real<R>::sts(s_f + k * RB, ((R)lds_i(s_ndk + k * 4) + alpha) * inv);
+                    }
+                    __syncwarp();
+                }
+
+                int zn_j = pk_j & 0x1ff;
+                if (TPT == 1) {
+                    // one token per lane: the lane's own next-batch token is the next group
+                    zn_j = sweep_step<TPT, CH, R>(buf, nwk_lane, rowbytes, lim, w_j, pk_j, w_n, pk_n, sm, sub, gbase, lane,
+                                               alpha, eta, K, p.nwk_write_delta);
+                } else {
+                    constexpr int UNR = (TPT <= 8) ? TPT : 2;
 #pragma unroll UNR
-                for (int s = 0; s < TPT; ++s) {
-                    // the last step of a batch requests the first group of the next batch
-                    const bool last = (s + 1 >= TPT);
-                    const int src = last ? 0 : s + 1;
-                    const int w_x = __shfl_sync(FULL, last ? w_n : w_j, src, TPT);
-                    const int pk_x = __shfl_sync(FULL, last ? pk_n : pk_j, src, TPT);
-                    const int zn = sweep_step<TPT, CH, R>(buf, nwk_lane, rowbytes, lim, w_c, pk_c, w_x, pk_x, sm, sub,
-                                                       gbase, lane, alpha, eta, K, p.nwk_write_delta);
-                    if (sub == s) zn_j = zn;
-                    w_c = w_x;
-                    pk_c = pk_x;
+                    for (int s = 0; s < TPT; ++s) {
+                        // the last step of a batch requests the first group of the next batch
+                        const bool last = (s + 1 >= TPT);
+                        const int src = last ? 0 : s + 1;
+                        const int w_x = __shfl_sync(FULL, last ? w_n : w_j, src, TPT);
+                        const int pk_x = __shfl_sync(FULL, last ? pk_n : pk_j, src, TPT);
+                        const int zn = sweep_step<TPT, CH, R>(buf, nwk_lane, rowbytes, lim, w_c, pk_c, w_x, pk_x, sm, sub,
+                                                           gbase, lane, alpha, eta, K, p.nwk_write_delta);
+                        if (sub == s) zn_j = zn;
+                        w_c = w_x;
+                        pk_c = pk_x;
+                    }
+                }
+                if ((pk_j & 0x200) == 0) z_cell[off + lane] = (uint16_t)zn_j;
+                if (p.visit_counter) {
+                    const unsigned live = __ballot_sync(FULL, (pk_j & 0x200) == 0);
+                    if (lane == 0) atomicAdd(p.visit_counter, (unsigned long long)__popc(live));
+                }
+                off = off_n; more = more_n;
+                w_j = w_n; pk_j = pk_n;
+                w_n = w_nn; z_n = z_nn; pkp_n = pkp_nn;
+                if (!more_n) pn.more = false;
+            }
+        } else {
+            int sidx = warp;  // super-batch index in the rotated sequence
+            int off = 0;      // first token of the current batch, relative to the cell
+            int nbq = 0;      // batches in the current super-batch
+            bool more = sidx < nsuper;
+            if (more) {
+                const int b0 = sidx < nsup1 ? rot + 4 * sidx : 4 * (sidx - nsup1);
+                nbq = min(4, (sidx < nsup1 ? nbatch : rot) - b0);
+                off = b0 << 5;
+            }
+            int w_j = 0, pk_j = 0;
+            int w_c = 0, pk_c = 0x200;  // the group sampled by the next step
+            Philox4 rnd = {0u, 0u, 0u, 0u};
+            int bq = 0;  // batch inside the super-batch
+            if (more) {
+                const bool valid = (off + lane) < ntok;
+                const int ic = valid ? off + lane : ntok - 1;
+                w_j = __ldg(tok_cell + ic);
+                const uint64_t gi = (gi0 + (uint64_t)off) & p.rng_index_mask;
+                rnd = philox4x32_10((uint32_t)gi, (uint32_t)(gi >> 32), p.sweep, 0u, p.seed_lo, p.seed_hi);
+                pk_j = pack_token(rnd.x, (int)z_cell[ic], valid);
+                w_c = (TPT > 1) ? __shfl_sync(FULL, w_j, 0, TPT) : w_j;
+                pk_c = (TPT > 1) ? __shfl_sync(FULL, pk_j, 0, TPT) : pk_j;
+                const char *row = nwk_lane + (uint64_t)((uint32_t)w_c) * rowbytes;
+                const int oc = ((pk_c & 0x1ff) >> 2) >> log2_tpt<TPT>();
+    #pragma unroll
+                for (int c = 0; c < CH; ++c) {
+                    const int rc = rot_chunk<CH>(c, oc);
+                    if (rc < lim) buf[c] = __ldcg(reinterpret_cast<const int4 *>(row + rc * (TPT * 16)));
                 }
             }
-            if ((pk_j & 0x200) == 0) z_cell[off + lane] = (uint16_t)zn_j;
-            if (p.visit_counter) {
-                const unsigned live = __ballot_sync(FULL, (pk_j & 0x200) == 0);
-                if (lane == 0) atomicAdd(p.visit_counter, (unsigned long long)__popc(live));
+            int since_refresh = 0;
+            while (more) {
+                // ---- the batch after this one (its tokens feed the last step's prefetch) ---------------
+                int sidx_n = sidx, off_n = off + 32, bq_n = bq + 1;
+                if (bq_n == nbq) {
+                    bq_n = 0;
+                    sidx_n = sidx + nwarps;
+                    const int b0 = sidx_n < nsup1 ? rot + 4 * sidx_n : 4 * (sidx_n - nsup1);
+                    nbq = min(4, (sidx_n < nsup1 ? nbatch : rot) - b0);
+                    off_n = b0 << 5;
+                }
+                const bool more_n = sidx_n < nsuper;
+                int w_n = w_j, pk_n = pk_j | 0x200;
+                if (more_n) {
+                    const bool valid_n = (off_n + lane) < ntok;
+                    const int icn = valid_n ? off_n + lane : ntok - 1;
+                    w_n = __ldg(tok_cell + icn);
+                    if (bq_n == 0) {  // one Philox call per lane serves the four batches of a super-batch
+                        const uint64_t gi = (gi0 + (uint64_t)off_n) & p.rng_index_mask;
+                        rnd = philox4x32_10((uint32_t)gi, (uint32_t)(gi >> 32), p.sweep, 0u, p.seed_lo, p.seed_hi);
+                    }
+                    const uint32_t bits = bq_n == 0 ? rnd.x : bq_n == 1 ? rnd.y : bq_n == 2 ? rnd.z : rnd.w;
+                    pk_n = pack_token(bits, (int)z_cell[icn], valid_n);
+                }
+
+                // ---- keep the topic totals live: publish this cell's n_k deltas, re-read n_k ---------
+                if (++since_refresh > p.refresh_every) {
+                    since_refresh = 1;
+                    for (int k = lane; k < K; k += 32) {
+                        const int cur = lds_i(s_ndk + k * 4);
+                        const int d = cur - atoms_exch(s_pub + k * 4, cur);
+                        if (d != 0) red_add_i32(p.n_k + k, d);
+                        const R den = (R)ld_volatile_i32(p.n_k_read + k) + etaW;
+                        const R inv = Real<R>::rcp(den);
+                        Real<R>::sts(s_den + k * RB, den);
+                        Real<R>::sts(s_inv + k * RB, inv);
+                        Real<R>::sts(s_f + k * RB, ((R)lds_i(s_ndk + k * 4) + alpha) * inv);
+                    }
+                    __syncwarp();
+                }
+
+                int zn_j = pk_j & 0x1ff;
+                if (TPT == 1) {
+                    // one token per lane: the lane's own next-batch token is the next group
+                    zn_j = sweep_step<TPT, CH, R>(buf, nwk_lane, rowbytes, lim, w_j, pk_j, w_n, pk_n, sm, sub, gbase, lane,
+                                               alpha, eta, K, p.nwk_write_delta);
+                } else {
+                    constexpr int UNR = (TPT <= 8) ? TPT : 2;
+    #pragma unroll UNR
+                    for (int s = 0; s < TPT; ++s) {
+                        // the last step of a batch requests the first group of the next batch
+                        const bool last = (s + 1 >= TPT);
+                        const int src = last ? 0 : s + 1;
+                        const int w_x = __shfl_sync(FULL, last ? w_n : w_j, src, TPT);
+                        const int pk_x = __shfl_sync(FULL, last ? pk_n : pk_j, src, TPT);
+                        const int zn = sweep_step<TPT, CH, R>(buf, nwk_lane, rowbytes, lim, w_c, pk_c, w_x, pk_x, sm, sub,
+                                                           gbase, lane, alpha, eta, K, p.nwk_write_delta);
+                        if (sub == s) zn_j = zn;
+                        w_c = w_x;
+                        pk_c = pk_x;
+                    }
+                }
+                if ((pk_j & 0x200) == 0) z_cell[off + lane] = (uint16_t)zn_j;
+                if (p.visit_counter) {
+                    const unsigned live = __ballot_sync(FULL, (pk_j & 0x200) == 0);
+                    if (lane == 0) atomicAdd(p.visit_counter, (unsigned long long)__popc(live));
+                }
+                sidx = sidx_n; off = off_n; bq = bq_n; more = more_n;
+                w_j = w_n; pk_j = pk_n;
             }
-            sidx = sidx_n; off = off_n; bq = bq_n; more = more_n;
-            w_j = w_n; pk_j = pk_n;
         }
         __syncthreads();
         for (int k = tid; k < K; k += blockDim.x) {

@@ -348,6 +348,15 @@ class DeviceModel:
     def exchange_wait(self):
         check(_lib.load().cgs_model_exchange_wait(self._h))
 
+    def exchange_sync(self, n_ctas: int = 0):
+        """The synchronous fused exchange (one kernel on the model's stream, between two sweeps)."""
+        check(_lib.load().cgs_model_exchange_sync(self._h, int(n_ctas)))
+
+    @staticmethod
+    def exchange_sync_local(models, n_ctas: int = 0):
+        arr = (c_vp * len(models))(*[m._h for m in models])
+        check(_lib.load().cgs_exchange_sync_local(arr, len(models), int(n_ctas)))
+
     @staticmethod
     def exchange_round_local(models, n_ctas: int = 0):
         """One round of several ranks that share a device, as ONE cooperative launch."""

@@ -80,6 +80,105 @@ def schedule_models(n_topics, n_workers):
     return plan
 
 
+def sweep_cost(n_topics: int) -> float:
+    """Relative time of one sweep over a fixed corpus as measured on B200 (C2, round 2: 0.59 ms at K = 2, 0.95 at
+    10, 1.37 at 25, 2.35 at 50): the small models are latency-bound, so time grows like K + 15 rather than 4K + 28."""
+    return float(n_topics) + 15.0
+
+
+def schedule_models_split(costs, n_workers, overhead=None, min_fraction=0.2):
+    """Schedule for more workers than whole models can fill: models are DIVISIBLE (a model's cells can be sharded
+    over consecutive workers, AD-LDA: one n_wk exchange per sweep between them), so the workers are filled one
+    after the other up to a common level T (McNaughton's wrap-around rule) and a model that does not fit is
+    continued on the next worker.  ``costs[i]`` = time of one sweep of model i on one whole worker, ``overhead[i]``
+    = what every PART of a split model pays on top (its share of the exchange).  Models are taken longest first,
+    so the split ones are the big ones, where the overhead matters least.  A part is never smaller than
+    ``min_fraction`` of a model.  Returns ``(plan, T)``: ``plan[w]`` = ordered list of ``(model, f0, f1)`` -- worker w
+    samples the cells whose cumulative token fraction lies in [f0, f1) -- with the part shared with worker w - 1
+    first and the part shared with worker w + 1 last, so that neighbours meet at their common model once per step.
+    Deterministic."""
+    n = len(costs)
+    overhead = [0.0] * n if overhead is None else list(overhead)
+    order = sorted(range(n), key=lambda i: (-costs[i], i))
+
+    def fill(T, whole_first):
+        plan = [[] for _ in range(n_workers)]
+        todo = list(order)           # models not started yet, longest first
+        carry = None                 # (model, fraction already placed): continues on the next worker, first
+        for w in range(n_workers):
+            load = 0.0
+            head, middle, tail = [], [], []
+            if carry is not None:
+                i, done = carry
+                rest = (1.0 - done) * costs[i] + overhead[i]
+                if rest <= T + 1e-12:
+                    head.append((i, done, 1.0))
+                    load += rest
+                    carry = None
+                else:  # a model longer than two levels: another full worker of it
+                    frac = min(1.0 - done - min_fraction, (T - overhead[i]) / costs[i])
+                    if frac < min_fraction:
+                        return None  # the level is too low for parts of the minimum size
+                    head.append((i, done, done + frac))
+                    carry = (i, done + frac)
+                    plan[w] = head
+                    continue
+            while todo:
+                room = T - load
+                # whole_first: the longest model that fits whole goes in before anything is split (few splits);
+                # otherwise only the longest remaining model is considered (pure wrap-around: equal levels)
+                fits = next((i for i in (todo if whole_first else todo[:1]) if costs[i] <= room + 1e-12), None)
+                if fits is not None:
+                    middle.append((fits, 0.0, 1.0))
+                    load += costs[fits]
+                    todo.remove(fits)
+                    continue
+                # nothing fits whole: start the longest remaining model here and continue it on the next worker
+                i = todo[0]
+                frac = (room - overhead[i]) / costs[i]
+                if frac < min_fraction:
+                    break
+                if frac > 1.0 - min_fraction:  # never leave a sliver behind: place a little less, keep filling
+                    frac = 1.0 - min_fraction
+                tail.append((i, 0.0, frac))
+                load += frac * costs[i] + overhead[i]
+                todo.pop(0)
+                carry = (i, frac)
+                break
+            if carry is not None and tail and todo:
+                # room left after a clamped part: whole models that still fit go in the middle
+                for i in list(todo):
+                    if costs[i] <= T - load + 1e-12:
+                        middle.append((i, 0.0, 1.0))
+                        load += costs[i]
+                        todo.remove(i)
+            plan[w] = head + middle + tail
+        if todo or carry is not None:
+            return None
+        return plan
+
+    best = None
+    for whole_first in (True, False):
+        lo = sum(costs) / n_workers
+        hi = lo * 2 + max(costs) + max(overhead)
+        plan = fill(hi, whole_first)
+        if plan is None:
+            continue
+        for _ in range(40):
+            mid = 0.5 * (lo + hi)
+            trial = fill(mid, whole_first)
+            if trial is None:
+                lo = mid
+            else:
+                hi, plan = mid, trial
+        if best is None or hi < best[1] - 1e-9:
+            best = (plan, hi)
+    if best is None:  # cannot happen for sane inputs; fall back to whole models
+        whole = schedule_models([0] * n, n_workers)
+        return [[(i, 0.0, 1.0) for i in p] for p in whole], max(costs)
+    return best
+
+
 def run_cgs_models(
     cistopic_obj,
     n_topics,
@@ -178,11 +277,12 @@ def run_cgs_model(
 
 def _fit_cgs_model_on_corpus(corpus, n_topics, n_iter, random_state, alpha, alpha_by_topic, eta, eta_by_topic):
     """The device part of run_cgs_model (lda_models.py:247-289): returns (fitted LDA, seconds, logger)."""
+    # The reference silences warnings and the `lda` logger inside its Ray worker PROCESS (lda_models.py:234-238);
+    # here the fit runs in the caller's process, so neither is changed beyond this call.
     log = _logger()
     lda_log = logging.getLogger("lda")
-    lda_log.addHandler(logging.NullHandler())
-    lda_log.propagate = False
-    warnings.filterwarnings("ignore")
+    if not any(isinstance(h, logging.NullHandler) for h in lda_log.handlers):
+        lda_log.addHandler(logging.NullHandler())
 
     # hyper-parameter scaling of lda_models.py:247-282
     model = LDA(
@@ -199,7 +299,14 @@ def _fit_cgs_model_on_corpus(corpus, n_topics, n_iter, random_state, alpha, alph
     )
     log.info(f"Running model with {n_topics} topics")
     start_time = time.time()
-    model.fit(None)
+    propagate = lda_log.propagate
+    lda_log.propagate = False
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            model.fit(None)
+    finally:
+        lda_log.propagate = propagate
     return model, time.time() - start_time, log
 
 
@@ -270,10 +377,10 @@ def build_cistopic_model(model, regions_by_cells, n_topics, cell_names, region_n
     if isinstance(save_path, str):
         if log is not None:
             log.info(f"Saving model with {n_topics} topics at {save_path}")
-        if not os.path.exists(save_path):
-            os.mkdir(save_path)
+        from . import compat
+        os.makedirs(save_path, exist_ok=True)  # one packing thread per GPU may get here at the same time
         with open(os.path.join(save_path, f"Topic{n_topics}.pkl"), "wb") as f:
-            pickle.dump(out, f)
+            pickle.dump(compat.pickle_ready(out), f)
     return out
 
 

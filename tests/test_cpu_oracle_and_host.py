@@ -334,6 +334,100 @@ print("ok")
     assert res.returncode == 0 and res.stdout.strip().endswith("ok"), res.stderr
 
 
+def test_saved_models_load_in_a_plain_pycistopic_environment(fitted, tmp_path):
+    """`run_cgs_models(save_path=...)` / the CLI must write pickles a pycisTopic environment WITHOUT this
+    package can load, in both situations: (a) pycisTopic not installed where the file is written (the class is
+    pickled under the reference's qualified name), (b) pycisTopic installed there (models are re-wrapped in its own
+    class).  "pycisTopic" is a minimal stand-in package holding the reference's class layout (lda_models.py:31-96,
+    cistopic_class.py:31-51); the reader process has only that on its path.  Also: a reference cisTopic-object pickle
+    (pycisTopic.cistopic_class.CistopicObject) loads in stub mode -- what the CLI's --input needs."""
+    import subprocess
+    import textwrap
+    m, cells, regions, X, o = fitted
+    fake = tmp_path / "site"
+    (fake / "pycisTopic").mkdir(parents=True)
+    (fake / "pycisTopic" / "__init__.py").write_text("")
+    (fake / "pycisTopic" / "lda_models.py").write_text(textwrap.dedent("""
+        class CistopicLDAModel:
+            def __init__(self, metrics, coherence, marg_topic, topic_ass, cell_topic, topic_region, parameters):
+                self.metrics, self.coherence, self.marg_topic, self.topic_ass = metrics, coherence, marg_topic, topic_ass
+                self.cell_topic, self.cell_topic_harmony, self.topic_region = cell_topic, [], topic_region
+                self.parameters = parameters
+                self.n_cells, self.n_regions, self.n_topic = cell_topic.shape[1], topic_region.shape[0], cell_topic.shape[0]
+        """))
+    (fake / "pycisTopic" / "cistopic_class.py").write_text(textwrap.dedent("""
+        class CistopicObject:
+            def __init__(self, fragment_matrix, binary_matrix, cell_names, region_names, cell_data, region_data,
+                         path_to_fragments, project="cisTopic"):
+                self.fragment_matrix, self.binary_matrix = fragment_matrix, binary_matrix
+                self.cell_names, self.region_names = cell_names, region_names
+                self.cell_data, self.region_data = cell_data, region_data
+                self.path_to_fragments, self.project = path_to_fragments, project
+                self.selected_model, self.projections = None, {"cell": {}, "region": {}}
+        """))
+    reader = textwrap.dedent(f"""
+        import pickle, sys
+        sys.path.insert(0, {str(fake)!r})
+        assert not any("pycistopic_b200" in p for p in sys.modules)
+        m = pickle.load(open(sys.argv[1], "rb"))
+        m = m[0] if isinstance(m, list) else m
+        import pycisTopic.lda_models as ref
+        assert type(m) is ref.CistopicLDAModel and m.n_topic == 7 and m.topic_region.shape[1] == 7
+        assert "pycistopic_b200" not in sys.modules
+        print("ok")
+        """)
+    for mode, extra_path in (("stub", None), ("installed", str(fake))):
+        save = tmp_path / f"models_{mode}"
+        writer = textwrap.dedent(f"""
+            import pickle, sys
+            sys.path.insert(0, {ROOT!r})
+            if {extra_path!r}:
+                sys.path.insert(0, {extra_path!r})
+            from pycistopic_b200 import compat, lda_models
+            o, m, cells, regions = pickle.load(open({str(tmp_path / "fit.pkl")!r}, "rb"))
+            model = lda_models.build_cistopic_model(o, m, 7, cells, regions, 30, 555, 50, True, 0.1, False, 5, 1.25,
+                                                    save_path={str(save)!r})
+            assert compat.alias_pycistopic() is ({mode!r} == "stub")
+            with open({str(save / "list.pkl")!r}, "wb") as f:
+                pickle.dump(compat.pickle_ready([model]), f)
+            print("ok")
+            """)
+        class _Fit:
+            pass
+        keep = _Fit()
+        for a in ("topic_word_", "doc_topic_", "nzw_", "ndz_", "nz_", "final_loglikelihood_"):
+            if hasattr(o, a):
+                setattr(keep, a, getattr(o, a))
+        with open(tmp_path / "fit.pkl", "wb") as f:
+            pickle.dump(({k: v for k, v in vars(keep).items()}, m, cells, regions), f)
+        writer = writer.replace("o, m, cells, regions = pickle.load", "d, m, cells, regions = pickle.load")
+        writer = writer.replace("model = lda_models", "o = type('Fit', (), d)()\nmodel = lda_models")
+        res = subprocess.run([sys.executable, "-c", writer], capture_output=True, text=True)
+        assert res.returncode == 0 and res.stdout.strip().endswith("ok"), (mode, res.stderr)
+        for name in ("Topic7.pkl", "list.pkl"):
+            res = subprocess.run([sys.executable, "-c", reader, str(save / name)], capture_output=True, text=True)
+            assert res.returncode == 0 and res.stdout.strip().endswith("ok"), (mode, name, res.stderr)
+    # a reference cisTopic object pickle (written by the stand-in package) loads in stub mode
+    obj_pkl = tmp_path / "cistopic_obj.pkl"
+    res = subprocess.run([sys.executable, "-c", textwrap.dedent(f"""
+        import pickle, sys
+        sys.path.insert(0, {str(fake)!r})
+        from pycisTopic.cistopic_class import CistopicObject
+        pickle.dump(CistopicObject(None, None, ["c1"], ["chr1:1-2"], None, None, "f.tsv.gz"), open({str(obj_pkl)!r}, "wb"))
+        """)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    res = subprocess.run([sys.executable, "-c", textwrap.dedent(f"""
+        import pickle, sys
+        sys.path.insert(0, {ROOT!r})
+        from pycistopic_b200 import compat, fragment_matrix
+        assert compat.alias_pycistopic() is True
+        obj = pickle.load(open({str(obj_pkl)!r}, "rb"))
+        assert type(obj) is fragment_matrix.CistopicObject and obj.cell_names == ["c1"]
+        print("ok")
+        """)], capture_output=True, text=True)
+    assert res.returncode == 0 and res.stdout.strip().endswith("ok"), res.stderr
+
+
 def test_diff_feature_oracle_matches_reference_golden():
     """oracle/diff_oracle.py against tests/golden/diff_features.npz (the reference's own get_wilcox_test_pvalues /
     get_log2_fc / p_adjust_bh, diff_features.py:968-1120, executed from the tree) and its NumPy restatement of

@@ -116,6 +116,63 @@ def test_async_exchange_virtual_ranks(small, R, K):
         c.close()
 
 
+@pytest.mark.parametrize("R,K", [(2, 10), (4, 50)])
+def test_sync_fused_exchange_equals_adlda_bookkeeping(small, R, K):
+    """The synchronous fused exchange kernel (cgs_model_exchange_sync; here R ranks on one device in one cooperative
+    launch): after every exchange all replicas are identical and equal the histogram of all z, exactly like the
+    delta / all-reduce / apply scheme; the trace follows the AD-LDA oracle with the same partition within 1 %."""
+    from pycistopic_b200 import DeviceModel
+    m = small
+    X = sp.csr_matrix(m.T)
+    alpha, eta = 50.0 / K, 0.1
+    n_iter = 20
+    seeds = [555, 1, 2, 3]
+    gt = np.zeros(n_iter + 1)
+    part = None
+    for seed in seeds:
+        shards, part = _shards(m, R, K, alpha, eta, seed=seed)
+        models = [mdl for _, mdl in shards]
+        for mdl in models:
+            mdl.init()
+        arenas = [mdl.exchange_arena()[0] for mdl in models]
+        for r, mdl in enumerate(models):
+            mdl.exchange_open(arenas, r)
+
+        def exchange():
+            DeviceModel.exchange_sync_local(models, 8)
+            for mdl in models:
+                mdl.exchange_wait()
+
+        exchange()
+        for it in range(n_iter):
+            gt[it] += sum(mdl.loglikelihood(1) for mdl in models) + models[0].loglikelihood(2)
+            for mdl in models:
+                mdl.sweep(1)
+            exchange()
+            if seed == 555 and it in (0, 7, n_iter - 1):
+                for mdl in models:
+                    mdl.sync()
+                hashes = [mdl.state_hash() for mdl in models]
+                assert all(h == hashes[0] for h in hashes) and hashes[0]["sum_nwk"] == X.nnz == hashes[0]["sum_nk"]
+                hist = _global_histogram(shards)
+                for mdl in models:
+                    assert mdl.verify_counts(hist.data_ptr()) == {"n_dk": 0, "n_wk": 0, "n_k": 0}
+        gt[n_iter] += sum(mdl.loglikelihood(1) for mdl in models) + models[0].loglikelihood(2)
+        assert [mdl.exchange_timeouts() for mdl in models] == [0] * R
+        for c, mdl in shards:
+            mdl.close()
+            c.close()
+    gt /= len(seeds)
+    ot = np.zeros(n_iter + 1)
+    for seed in seeds:
+        o = lo.OracleLDA(K, n_iter=n_iter, alpha=alpha, eta=eta, random_state=seed, refresh=1, n_parts=R, part_ptr=part).fit(X)
+        ot += np.array(o.loglikelihoods_ + [o.final_loglikelihood_])
+    ot /= len(seeds)
+    assert gt[0] == pytest.approx(ot[0], rel=1e-10)
+    rel = np.abs(gt - ot) / np.abs(ot)
+    assert rel.max() < 0.01, f"trace deviates {rel.max():.3%} at sweep {rel.argmax()}"
+
+
 @pytest.mark.parametrize("parts", [1, 2])
 def test_async_exchange_trace_between_the_adlda_and_the_sequential_oracle(small, parts):
     """In production no rank waits for a round.  With one round per sweep a shard samples against counts of the
@@ -254,8 +311,11 @@ def test_deterministic_mode_is_bit_reproducible(small, K):
 
 
 def test_deterministic_mode_trace_close_to_oracle(small):
-    """With 8 sub-sweeps the copies a cell reads are at most 1/8 of a sweep old: the trace stays within 1 % of the
-    sequential oracle (seed-averaged on both sides, as the other trace tests on corpora this small)."""
+    """The copies a cell reads are up to one sub-sweep old, and all cells of a sub-sweep are sampled against the same
+    copy: measured on the benchmark-shaped corpus (scripts/det_mode_study.py, profiles/r2_det_mode_study.txt) the
+    transient lags the sequential oracle by 5-9 % with one sub-sweep per sweep, halving with every doubling (16
+    sub-sweeps: 0.5-0.9 %, 32: 0.5 %).  Here, on a 600-cell corpus with 32 sub-sweeps: within 2 % at every sweep
+    and within 0.5 % at the end (seed-averaged on both sides)."""
     from pycistopic_b200 import Corpus, DeviceModel
     X = sp.csr_matrix(small.T)
     K, n_iter = 10, 40
@@ -265,7 +325,7 @@ def test_deterministic_mode_trace_close_to_oracle(small):
     gt, ot = np.zeros(n_iter + 1), np.zeros(n_iter + 1)
     for s in seeds:
         mdl = DeviceModel(corpus, K, alpha, eta, seed=s)
-        mdl.set_deterministic(8)
+        mdl.set_deterministic(32)
         mdl.init()
         for it in range(n_iter):
             gt[it] += mdl.loglikelihood()
@@ -276,4 +336,5 @@ def test_deterministic_mode_trace_close_to_oracle(small):
         ot += np.array(o.loglikelihoods_ + [o.final_loglikelihood_])
     rel = np.abs(gt - ot) / np.abs(ot)
     corpus.close()
-    assert rel.max() < 0.01, f"trace deviates {rel.max():.3%} at sweep {rel.argmax()}"
+    print(f"deterministic mode, 32 sub-sweeps: max deviation {rel.max():.3%} at sweep {rel.argmax()}, final {rel[-1]:.3%}")
+    assert rel.max() < 0.02 and rel[-1] < 0.005, f"trace deviates {rel.max():.3%} at sweep {rel.argmax()}"

@@ -77,6 +77,40 @@ def test_schedule_covers_every_model_once(topics, workers):
     assert max(loads) <= sum(lda_models.model_cost(k) for k in topics) / workers + longest + 1e-9
 
 
+@settings(max_examples=80, **COMMON)
+@given(costs=st.lists(st.floats(0.2, 5.0), min_size=1, max_size=16), workers=st.integers(1, 12),
+       ov=st.floats(0.0, 0.3))
+def test_split_schedule_partitions_every_model(costs, workers, ov):
+    """schedule_models_split: every model's parts tile [0, 1) in order on CONSECUTIVE workers, no part is a sliver,
+    no worker exceeds the returned level, and the level is never worse than whole-model LPT."""
+    overhead = [ov] * len(costs)
+    plan, level = lda_models.schedule_models_split(costs, workers, overhead, min_fraction=0.2)
+    assert len(plan) == workers
+    where = {}
+    for w, items in enumerate(plan):
+        load = 0.0
+        for (i, f0, f1) in items:
+            assert 0.0 <= f0 < f1 <= 1.0
+            whole = f0 == 0.0 and f1 == 1.0
+            assert whole or (f1 - f0) >= 0.2 - 1e-9
+            load += (f1 - f0) * costs[i] + (0.0 if whole else overhead[i])
+            where.setdefault(i, []).append((f0, f1, w))
+        assert load <= level * (1 + 1e-6) + 1e-9
+    assert sorted(where) == list(range(len(costs)))
+    for i, parts in where.items():
+        parts.sort()
+        assert parts[0][0] == 0.0 and parts[-1][1] == 1.0
+        for a, b in zip(parts, parts[1:]):
+            assert abs(a[1] - b[0]) < 1e-12 and b[2] == a[2] + 1   # contiguous fractions on neighbouring workers
+    lpt = lda_models.schedule_models([0] * len(costs), workers)  # indices only; costs below
+    order = sorted(range(len(costs)), key=lambda i: (-costs[i], i))
+    loads = [0.0] * workers
+    for i in order:
+        j = min(range(workers), key=lambda j: (loads[j], j))
+        loads[j] += costs[i]
+    assert level <= max(loads) * (1 + 1e-6) + ov + 1e-9
+
+
 # ---- GPU: the same invariants through the C ABI --------------------------------------------------------
 @pytest.mark.gpu
 @settings(max_examples=25, **COMMON)
