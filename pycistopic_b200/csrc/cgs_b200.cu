@@ -1018,7 +1018,7 @@ int cgs_model_set_sweep_shape(cgs_model *m, int32_t lanes_per_token, int32_t war
     const int chunks = (m->K + 3) / 4;
     const int ch = (chunks + t - 1) / t;
     if (ch > kMaxChunksPerLane || t * ch * 4 > kMaxTopics) CGS_FAIL("lanes_per_token too small for this n_topics");
-    if (warps_per_cell * 32 > (ch <= 2 ? 256 : ch <= 4 ? 512 : ch <= 6 ? 384 : 256))
+    if (warps_per_cell * 32 > (ch <= 1 ? 256 : ch <= 4 ? 512 : ch <= 6 ? 384 : 256))
         CGS_FAIL("too many warps per cell for this many chunks per lane");
     m->tpt = t;
     m->ch = ch;

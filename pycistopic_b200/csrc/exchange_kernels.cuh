@@ -83,10 +83,14 @@ __device__ __forceinline__ void exchange_barrier(const ExchangeParams &p, int ph
     __syncthreads();
     uint32_t *mine = p.peers.flags[p.rank];
     if (threadIdx.x == 0) {
-        __threadfence_system();
+        // Every CTA publishes its writes at GPU scope and arrives on the rank's counter; only the LAST CTA pays for the
+        // system-scope fence, which by cumulativity covers everything the other CTAs published before they arrived
+        // (a system-scope fence in each of the ~600 CTAs cost ~0.2 ms per exchange: profiles/r2_exchange_barrier.txt).
+        __threadfence();
         uint32_t *counter = mine + 2 * kMaxExchangeRanks + phase;
         const unsigned prev = atomicAdd(counter, 1u);
         if (prev == n_ctas - 1) {
+            __threadfence();
             *counter = 0;  // next use is in the next round, after both barriers of this one
             __threadfence_system();
             for (int q = 0; q < p.n_ranks; ++q)
@@ -106,7 +110,6 @@ __device__ __forceinline__ void exchange_barrier(const ExchangeParams &p, int ph
                 break;
             }
         }
-        __threadfence_system();
     }
     __syncthreads();
 }

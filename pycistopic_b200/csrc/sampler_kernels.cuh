@@ -325,14 +325,14 @@ __device__ __forceinline__ int sweep_step(int4 (&buf)[CH], const char *nwk_lane,
 template <int TPT, int CH> constexpr bool kDeepTokenPrefetch = (TPT <= 2 && CH <= 3);
 
 // Register budget (measured on B200: occupancy beats the few spills it costs; profiles/r1_shape_scan_*.txt):
-// 40 warps per SM at 48 registers up to 2 chunks per lane (the latency-bound shapes, K <= 16: the deeper token
-// prefetch costs 7 registers, which at the former 64-register budget took a fifth of the resident warps away --
-// profiles/r2_sweep_k2_deep_v1_ncu_summary.csv), 32 warps at 64 registers up to 4 chunks, 24 warps at 80 registers
-// for 5-6 chunks, 16 warps beyond.  A cell may take up to 8 warps (256 threads) for CH <= 2, 16 (512) for CH 3-4,
-// 12 (384) for CH 5-6, 8 (256) beyond.
+// 40 warps per SM at 48 registers with one chunk per lane (K <= 8: the deeper token prefetch costs 7 registers, which
+// at the former 64-register budget took a fifth of the resident warps away -- profiles/r2_sweep_k2_deep_v1_ncu_summary.csv;
+// with two chunks per lane the 48-register budget measured 3-4 % SLOWER than 64, profiles/r2_small_k_variants.txt),
+// 32 warps at 64 registers up to 4 chunks, 24 warps at 80 registers for 5-6 chunks, 16 warps beyond.  A cell may take
+// up to 8 warps (256 threads) for CH = 1, 16 (512) for CH 2-4, 12 (384) for CH 5-6, 8 (256) beyond.
 template <int CH, typename R = float> struct SweepBounds {
-    static constexpr int kThreads = CH <= 2 ? 256 : CH <= 4 ? 512 : CH <= 6 ? 384 : 256;
-    static constexpr int kMinBlocks = sizeof(R) == 8 ? 1 : CH <= 2 ? 5 : 2;  // the fp64 A/B build trades occupancy for registers
+    static constexpr int kThreads = CH <= 1 ? 256 : CH <= 4 ? 512 : CH <= 6 ? 384 : 256;
+    static constexpr int kMinBlocks = sizeof(R) == 8 ? 1 : CH <= 1 ? 5 : 2;  // the fp64 A/B build trades occupancy for registers
 };
 
 template <int TPT, int CH, typename R = float>

@@ -425,7 +425,7 @@ class LDA:
 
     def __init__(self, n_topics, n_iter=2000, alpha=0.1, eta=0.01, random_state=None, refresh=10,
                  device=0, corpus: Corpus | None = None, exports="all", device_metrics=None, z_init=None,
-                 keep_assignments=False):
+                 keep_assignments=False, deterministic=0):
         self.n_topics = n_topics
         self.n_iter = n_iter
         self.alpha = alpha
@@ -447,6 +447,10 @@ class LDA:
         # continued on the device; keep_assignments leaves the final assignments in ``z_`` (with ``WS_`` / ``DS_``)
         self._z_init = z_init
         self._keep_assignments = bool(keep_assignments)
+        # deterministic: 0 = the default live-count schedule (statistically reproducible); n > 0 = bit-reproducible
+        # for a fixed random_state, like the `lda` package: every sweep runs as n sub-sweeps on copies of the count
+        # tables (True = 16).  Slower and slightly behind in the transient.
+        self._deterministic = 16 if deterministic is True else int(deterministic or 0)
         if alpha <= 0 or eta <= 0:
             raise ValueError("alpha and eta must be greater than zero")
         if random_state is None:
@@ -472,6 +476,8 @@ class LDA:
             own_corpus = True
         model = DeviceModel(corpus, self.n_topics, self.alpha, self.eta, seed=self._seed)
         try:
+            if self._deterministic:
+                model.set_deterministic(self._deterministic)
             if self._z_init is None:
                 model.init()
             else:

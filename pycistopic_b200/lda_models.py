@@ -197,9 +197,12 @@ def run_cgs_models(
 
     Signature and return value of the reference (lda_models.py:99-175): a list of
     :class:`CistopicLDAModel` in the order of ``n_topics``.  ``n_cpu`` and Ray keyword
-    arguments are ignored; ``devices=[...]`` (keyword-only extra) restricts the GPUs used.
+    arguments are ignored; ``devices=[...]`` (keyword-only extra) restricts the GPUs used;
+    ``deterministic=True`` (or a number of sub-sweeps) makes the result a pure function of ``random_state`` as the
+    reference's is (lda_models.py:104) -- the default schedule is only statistically reproducible.
     """
     devices = kwargs.pop("devices", None)
+    deterministic = kwargs.pop("deterministic", 0)
     n_gpu = _lib.require_device()
     if devices is None:
         devices = list(range(n_gpu))
@@ -224,7 +227,8 @@ def run_cgs_models(
                 with ThreadPoolExecutor(max_workers=1) as packer:
                     for i in idxs:
                         fitted, end_time, log = _fit_cgs_model_on_corpus(
-                            corpus, n_topics[i], n_iter, random_state, alpha, alpha_by_topic, eta, eta_by_topic)
+                            corpus, n_topics[i], n_iter, random_state, alpha, alpha_by_topic, eta, eta_by_topic,
+                            deterministic)
                         pending[i] = packer.submit(
                             build_cistopic_model, fitted, binary_matrix, n_topics[i], cell_names, region_names,
                             n_iter, random_state, alpha, alpha_by_topic, eta, eta_by_topic, top_topics_coh, end_time,
@@ -275,7 +279,8 @@ def run_cgs_model(
         corpus.close()
 
 
-def _fit_cgs_model_on_corpus(corpus, n_topics, n_iter, random_state, alpha, alpha_by_topic, eta, eta_by_topic):
+def _fit_cgs_model_on_corpus(corpus, n_topics, n_iter, random_state, alpha, alpha_by_topic, eta, eta_by_topic,
+                             deterministic=0):
     """The device part of run_cgs_model (lda_models.py:247-289): returns (fitted LDA, seconds, logger)."""
     # The reference silences warnings and the `lda` logger inside its Ray worker PROCESS (lda_models.py:234-238);
     # here the fit runs in the caller's process, so neither is changed beyond this call.
@@ -296,6 +301,7 @@ def _fit_cgs_model_on_corpus(corpus, n_topics, n_iter, random_state, alpha, alph
         corpus=corpus,
         exports="frames",
         device_metrics={"alpha": alpha, "eta": eta, "top_n": 20},
+        deterministic=deterministic,
     )
     log.info(f"Running model with {n_topics} topics")
     start_time = time.time()

@@ -103,3 +103,20 @@ def test_cli_topic_modeling_lda(tmp_path):
     for K in (3, 6):
         with open(tmp_path / "models" / f"Topic{K}.pkl", "rb") as f:
             assert pickle.load(f).n_topic == K
+
+
+def test_run_cgs_models_deterministic_is_reproducible():
+    """run_cgs_models(..., deterministic=True): two calls with the same random_state return identical models
+    (topic assignments, cell_topic, topic_region, metrics), as the reference does for a fixed random_state
+    (lda_models.py:104); a different random_state gives a different model."""
+    from pycistopic_b200 import run_cgs_models
+    from pycistopic_b200.synth import SyntheticCistopicObject, make_binary_matrix
+    m, cells, regions = make_binary_matrix(n_cells=200, n_regions=4000, density=0.05, n_true_topics=5, seed=21)
+    obj = SyntheticCistopicObject(m, cells, regions)
+    runs = [run_cgs_models(obj, n_topics=[4, 12], n_iter=20, random_state=555, deterministic=True) for _ in range(2)]
+    for a, b in zip(*runs):
+        assert a.topic_ass["Assignments"].tolist() == b.topic_ass["Assignments"].tolist()
+        assert a.cell_topic.equals(b.cell_topic) and a.topic_region.equals(b.topic_region)
+        assert a.metrics.drop(columns=[]).equals(b.metrics)
+    other = run_cgs_models(obj, n_topics=[4], n_iter=20, random_state=556, deterministic=True)[0]
+    assert not other.cell_topic.equals(runs[0][0].cell_topic)
