@@ -396,7 +396,22 @@ def run_adlda_leg(args, dev, rank, world, local_rank, shape=None):
             t = torch.tensor([sample_ms], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             sample_ms = float(t[0].item())
+        phases = shard.model.exchange_phase_times() if exchange == "fused" else None
+        # the exchange alone, back to back (nothing to publish: the pure cost of the passes and the barriers)
+        alone_ms = None
+        if exchange in ("fused", "nccl"):
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            x0, x1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            x0.record(stream)
+            for i in range(n):
+                ex.step()
+            x1.record(stream)
+            torch.cuda.synchronize()
+            alone_ms = x0.elapsed_time(x1) / n
         out[exchange] = {"tokens_per_s": N_total / (ms * 1e-3), "ms_per_sweep": ms, "ms_sampling_alone": sample_ms,
+                         "ms_exchange_alone_back_to_back": alone_ms, "fused_phase_us_rank0": phases,
                          "ms_exchange_exposed": ms - sample_ms, "rounds_per_sweep": parts,
                          "sweep_shape": shard.model.sweep_shape,
                          "checks": checks}

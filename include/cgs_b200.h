@@ -243,6 +243,9 @@ int cgs_model_exchange_wait(cgs_model *m);
  * delta_apply; same statistics as those.  Do not mix with cgs_model_exchange_round on one model. */
 int cgs_model_exchange_sync(cgs_model *m, int32_t n_ctas);
 int cgs_exchange_sync_local(cgs_model *const *models, int32_t n_models, int32_t n_ctas);
+/* Diagnostics: microseconds CTA 0 of the LAST synchronous exchange spent in { delta pass, barrier, reduce + broadcast of
+ * its slice, barrier, apply pass } (device %globaltimer). */
+int cgs_model_exchange_phase_times(cgs_model *m, double *us5);
 /* Several ranks on ONE device (tests; more shards than GPUs): kernels that wait for each other must not be separate
  * launches on one GPU, so the rounds of all n_models (<= 8) local ranks go out as ONE cooperative launch (grid =
  * n_ctas x n_models, co-residency guaranteed); same semantics as calling cgs_model_exchange_round on each. */

@@ -1597,6 +1597,18 @@ int cgs_model_exchange_status(cgs_model *m, int32_t *timeouts) {
     return 0;
 }
 
+int cgs_model_exchange_phase_times(cgs_model *m, double *us5) {
+    if (!m || !us5) CGS_FAIL("NULL argument");
+    DeviceGuard g(m->corpus->device);
+    if (!m->d_arena) CGS_FAIL("no exchange arena");
+    CGS_CUDA(cudaStreamSynchronize(m->stream));
+    unsigned long long t[6];
+    const char *flags = m->d_arena + 2 * arena_delta_bytes(m);
+    CGS_CUDA(cudaMemcpy(t, flags + kExchangeStampWord * 4, sizeof t, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 5; ++i) us5[i] = (double)(t[i + 1] - t[i]) * 1e-3;
+    return 0;
+}
+
 // ---- NCCL behind the ABI (cgs_allreduce_delta) -------------------------------------------
 // The library does not link NCCL: the entry points are resolved at first use from the libnccl.so.2 the host
 // process has already loaded (torch's) or that the loader finds.  Only the few signatures used are declared.

@@ -32,6 +32,7 @@ namespace cgs {
 
 constexpr int kMaxExchangeRanks = 16;
 constexpr int kExchangeThreads = 256;  // 256 threads x <= 64 registers: a CTA takes the room of two sweep CTAs
+constexpr int kExchangeStampWord = 64;   // 6 x uint64 phase timestamps of the last synchronous exchange (8-byte aligned)
 constexpr int kExchangeFlagWords = 256;  // per arena: [2][16] arrival flags, [2] local CTA counters, [1] timeouts
 
 struct ExchangePeers {
@@ -149,18 +150,27 @@ __device__ __forceinline__ void exchange_round_body(const ExchangeParams &p, uns
     {
         const int R = p.n_ranks;
         const int64_t lo = p.n4 * p.rank / R, hi = p.n4 * (p.rank + 1) / R;
-        for (int64_t i = lo + tid0; i < hi; i += stride) {
-            int4 t = make_int4(0, 0, 0, 0);
-            for (int q0 = 0; q0 < R; q0 += 8) {  // eight peer loads in flight per thread
-                int4 v[8];
+        for (int64_t i0 = lo + tid0; i0 < hi; i0 += 4 * stride) {  // four entries in flight per thread, one peer at a time
+            int4 t[4];
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (q0 + j < R) v[j] = ld_sys_v4(p.peers.delta[q0 + j] + i);
+            for (int u = 0; u < 4; ++u) t[u] = make_int4(0, 0, 0, 0);
+            for (int q = 0; q < R; ++q) {
+                int4 v[4];
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (q0 + j < R) { t.x += v[j].x; t.y += v[j].y; t.z += v[j].z; t.w += v[j].w; }
+                for (int u = 0; u < 4; ++u) {
+                    const int64_t i = i0 + u * stride;
+                    v[u] = i < hi ? ld_sys_v4(p.peers.delta[q] + i) : make_int4(0, 0, 0, 0);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { t[u].x += v[u].x; t[u].y += v[u].y; t[u].z += v[u].z; t[u].w += v[u].w; }
             }
-            for (int q = 0; q < R; ++q) __stcg(p.peers.total[q] + i, t);
+            for (int q = 0; q < R; ++q) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int64_t i = i0 + u * stride;
+                    if (i < hi) __stcg(p.peers.total[q] + i, t[u]);
+                }
+            }
         }
     }
     exchange_barrier(p, 1, n_ctas);
@@ -215,6 +225,10 @@ __device__ __forceinline__ void exchange_sync_body(const ExchangeParams &p, unsi
     int4 *n_wk = reinterpret_cast<int4 *>(p.n_wk);
     int4 *my_delta = p.peers.delta[p.rank];
     int4 *my_g = p.peers.total[p.rank];
+    // phase boundaries as seen by CTA 0 (nanoseconds of %globaltimer), read by cgs_model_exchange_phase_times
+    unsigned long long *stamps = reinterpret_cast<unsigned long long *>(p.peers.flags[p.rank] + kExchangeStampWord);
+    const bool stamper = cta == 0 && threadIdx.x == 0;
+    if (stamper) stamps[0] = global_timer_ns();
 
     for (int64_t i0 = tid0; i0 < p.n4; i0 += 4 * stride) {
         int4 a[4], g[4];
@@ -229,25 +243,44 @@ __device__ __forceinline__ void exchange_sync_body(const ExchangeParams &p, unsi
             if (i < p.n4) __stcg(my_delta + i, make_int4(a[u].x - g[u].x, a[u].y - g[u].y, a[u].z - g[u].z, a[u].w - g[u].w));
         }
     }
+    if (stamper) stamps[1] = global_timer_ns();
     exchange_barrier(p, 0, n_ctas);
+    if (stamper) stamps[2] = global_timer_ns();
     {
         const int R = p.n_ranks;
         const int64_t lo = p.n4 * p.rank / R, hi = p.n4 * (p.rank + 1) / R;
-        for (int64_t i = lo + tid0; i < hi; i += stride) {
-            int4 t = __ldcs(my_g + i);
-            for (int q0 = 0; q0 < R; q0 += 8) {
-                int4 v[8];
+        // Four entries per thread and iteration, one peer at a time: with a single entry per thread the loop is bound by
+        // the NVLink round trip (measured 366 GB/s per direction on 2 ranks, profiles/r2_exchange_phases.txt); four
+        // independent 16-byte loads per thread keep ~10 MB in flight per GPU, several times latency x bandwidth.
+        for (int64_t i0 = lo + tid0; i0 < hi; i0 += 4 * stride) {
+            int4 t[4];
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (q0 + j < R) v[j] = ld_sys_v4(p.peers.delta[q0 + j] + i);
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (q0 + j < R) { t.x += v[j].x; t.y += v[j].y; t.z += v[j].z; t.w += v[j].w; }
+            for (int u = 0; u < 4; ++u) {
+                const int64_t i = i0 + u * stride;
+                if (i < hi) t[u] = __ldcs(my_g + i);
             }
-            for (int q = 0; q < R; ++q) __stcg(p.peers.total[q] + i, t);
+            for (int q = 0; q < R; ++q) {
+                int4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int64_t i = i0 + u * stride;
+                    if (i < hi) v[u] = ld_sys_v4(p.peers.delta[q] + i);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) { t[u].x += v[u].x; t[u].y += v[u].y; t[u].z += v[u].z; t[u].w += v[u].w; }
+            }
+            for (int q = 0; q < R; ++q) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int64_t i = i0 + u * stride;
+                    if (i < hi) __stcg(p.peers.total[q] + i, t[u]);
+                }
+            }
         }
     }
+    if (stamper) stamps[3] = global_timer_ns();
     exchange_barrier(p, 1, n_ctas);
+    if (stamper) stamps[4] = global_timer_ns();
     for (int64_t i0 = tid0; i0 < p.n4; i0 += 4 * stride) {
         int4 g[4];
 #pragma unroll
@@ -271,6 +304,7 @@ __device__ __forceinline__ void exchange_sync_body(const ExchangeParams &p, unsi
     // n_k was zeroed by the host before the launch
     for (int k = threadIdx.x; k < Kp; k += blockDim.x)
         if (x_colsum[k]) red_add_global_i32(p.n_k + k, x_colsum[k]);
+    if (stamper) stamps[5] = global_timer_ns();
 }
 
 __global__ void __launch_bounds__(kExchangeThreads, 4)

@@ -352,6 +352,12 @@ class DeviceModel:
         """The synchronous fused exchange (one kernel on the model's stream, between two sweeps)."""
         check(_lib.load().cgs_model_exchange_sync(self._h, int(n_ctas)))
 
+    def exchange_phase_times(self):
+        """Microseconds of the last synchronous exchange per phase: delta, barrier, reduce, barrier, apply."""
+        out = (ctypes.c_double * 5)()
+        check(_lib.load().cgs_model_exchange_phase_times(self._h, out))
+        return dict(zip(("delta", "barrier_a", "reduce", "barrier_b", "apply"), [round(x, 1) for x in out]))
+
     @staticmethod
     def exchange_sync_local(models, n_ctas: int = 0):
         arr = (c_vp * len(models))(*[m._h for m in models])
