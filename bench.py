@@ -304,7 +304,7 @@ def run_adlda_leg(args, dev, rank, world, local_rank, shape=None):
         cp = torch.tensor(cell_ptr_h[cb:ce + 1] - t0, dtype=torch.int64, device=dev)
     torch.cuda.empty_cache()
     out = {}
-    modes = ["nccl", "fused", "async"] + (["peer"] if world == 2 else [])
+    modes = ["nccl", "fused", "overlap"] + (["peer"] if world == 2 else [])
     if args.adlda_modes:
         modes = args.adlda_modes.split(",")
     n = max(3, args.steps)
@@ -316,6 +316,13 @@ def run_adlda_leg(args, dev, rank, world, local_rank, shape=None):
                          exchange=exchange, corpus=corpus)
         shard.init()
         ex = Exchanger(shard, exchange)
+        if exchange == "overlap":
+            per_region = torch.bincount(tok, minlength=W).to(torch.int64)
+            if world > 1:
+                dist.all_reduce(per_region)
+            split = int(torch.searchsorted(torch.cumsum(per_region, 0), torch.tensor([N_total // 2], device=dev)).item()) + 1
+            shard.set_region_split(min(split, W))
+            del per_region
         ex.step()
         stream = shard.stream
 
@@ -325,9 +332,7 @@ def run_adlda_leg(args, dev, rank, world, local_rank, shape=None):
 
         def sweep():
             for part in range(parts):
-                ex.before_sweep()
-                shard.sweep_part(part, parts)
-                ex.after_sweep()
+                ex.sweep(part, parts)
 
         for _ in range(5 + max(args.warmup, 3)):
             sweep()
@@ -362,7 +367,7 @@ def run_adlda_leg(args, dev, rank, world, local_rank, shape=None):
             hashes = [None] * world
             dist.all_gather_object(hashes, h)
         bad = shard.model.verify_counts(hist.data_ptr())
-        timeouts = shard.model.exchange_timeouts() if exchange in ("async", "fused") else 0
+        timeouts = shard.model.exchange_timeouts() if exchange in ("async", "fused", "overlap") else 0
         flags = torch.tensor([float(bad["n_wk"]), float(bad["n_k"]), float(timeouts)], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(flags, op=dist.ReduceOp.MAX)
@@ -422,8 +427,9 @@ def run_adlda_leg(args, dev, rank, world, local_rank, shape=None):
     return {"workload": f"{shape}: {D} cells x {W} regions, {N_total} tokens, one K={K_adlda} model, cells sharded "
                         f"over {world} GPU(s), n_wk exchange ({4 * W * ((K_adlda + 3) // 4 * 4) / 1e6:.0f} MB): nccl = "
                         "delta kernel / NCCL all-reduce / apply kernel after every sweep; fused = ONE kernel after every "
-                        "sweep (delta, reduce-scatter + all-gather over peer memory, apply); async = fused peer-memory "
-                        "round kernel beside the sweep, one round per half sweep",
+                        "sweep (delta, reduce-scatter + all-gather over peer memory, apply); overlap = that exchange inside "
+                        "the sampling launches (a sweep = two half-sweeps by region index; the rows of the half that is "
+                        "not being sampled are exchanged by a few blocks of the same grid)",
             "scaling": "strong", "value": best["tokens_per_s"], "unit": "tokens/s", "per_exchange": out,
             "checks_ok": all(v["checks"]["ok"] for v in out.values()),
             "frac_of_hbm_roofline_per_gpu": b_tok(K_adlda) * best["tokens_per_s"] / world / 1e9 / peak}
@@ -696,14 +702,16 @@ def run_cuda(args):
             dist.barrier()
 
     # ---- plan -------------------------------------------------------------------------------------
-    # One GPU: every model whole.  Several GPUs: whole models cannot fill them evenly (the K = 50 model alone is
-    # longer than 1/8 of the step), so models are divisible: the GPUs are filled to a common level and a model that
-    # does not fit is continued on the next GPU -- its cells sharded AD-LDA style, one fused exchange kernel per sweep
-    # between the GPUs that share it (lda_models.schedule_models_split).  Costs = sweep times measured here.
+    # Whole models, longest first (one model per GPU at a time).  With --split the models are divisible: the GPUs are
+    # filled to a common level and a model that does not fit is continued on the next GPU -- its cells sharded AD-LDA
+    # style, one fused exchange kernel per sweep between the GPUs that share it (lda_models.schedule_models_split, costs
+    # = sweep times measured here).  Measured on 8 GPUs (profiles/r2_bench_n8_split_plan_v1.json) that is SLOWER than
+    # whole models for C2: a 20 % shard of a 10 000-cell matrix takes 40 % of the sweep (two waves of cells instead of
+    # 8.4) and every split pays ~0.35 ms of exchange on a ~2 ms step, so it is opt-in.
     whole_plan = schedule_models(N_TOPICS, world)
     my_topics = [N_TOPICS[i] for i in whole_plan[rank]]  # the end-to-end leg keeps whole models
     costs = None
-    if world > 1 and not args.no_split:
+    if world > 1 and args.split:
         mine = {}
         for i in range(rank, len(N_TOPICS), world):
             K = N_TOPICS[i]
@@ -1093,7 +1101,10 @@ def main():
     ap.add_argument("--no-adlda", action="store_true")
     ap.add_argument("--no-impute", action="store_true")
     ap.add_argument("--n-topics", default="", help="debugging: comma-separated n_topics list instead of the C2 sweep")
-    ap.add_argument("--no-split", action="store_true", help="whole models only (round-1 schedule) at more than one GPU")
+    ap.add_argument("--split", action="store_true",
+                    help="divisible-model schedule at more than one GPU (lda_models.schedule_models_split): measured SLOWER "
+                         "than whole models on C2 (230 vs 304 Gtok/s on 8 GPUs: short shards lose to wave quantisation and every "
+                         "split pays an exchange), so whole models, longest first, stay the default")
     ap.add_argument("--no-parity", action="store_true", help="skip the frozen-oracle-trace check (rank 0, ~1 min)")
     ap.add_argument("--no-c4", action="store_true", help="skip the atlas-scale AD-LDA leg (only runs at >= 8 GPUs)")
     ap.add_argument("--no-c5", action="store_true", help="skip the atlas-scale imputation leg")

@@ -242,6 +242,19 @@ int cgs_model_exchange_wait(cgs_model *m);
  * n_wk = G, n_k = its column sums.  5 table passes of local traffic instead of the 8 of delta_compute + all-reduce +
  * delta_apply; same statistics as those.  Do not mix with cgs_model_exchange_round on one model. */
 int cgs_model_exchange_sync(cgs_model *m, int32_t n_ctas);
+/* The exchange OVERLAPPED with sampling, in one launch (csrc/sampler_kernels.cuh, sweep_kernel<.., XCH = true>).
+ * Tokens are sorted by region inside a cell, so a sweep can be cut at a region index into two half-sweeps; while one
+ * half is sampled, the rows of n_wk of the OTHER half -- changed by the previous launch, untouched by this one -- go
+ * through the synchronous exchange on x_ctas blocks of the same grid (default: one per SM).  Every row is exchanged
+ * once per sweep, right after it was sampled: same statistics as cgs_model_exchange_sync after every sweep, but the
+ * NVLink round trips, the cross-rank waits and the table passes hide behind the sampling.
+ *   cgs_corpus_set_region_split: the region index that cuts the sweep (every rank the same; pick the one that halves
+ *     the tokens).  cgs_model_sweep_overlapped: n_sweeps sweeps, each two launches; the rows of the last half-sweep
+ *     stay unpublished until the next call or cgs_model_exchange_flush (call it before reading counts /
+ *     log-likelihoods).  Needs cgs_model_exchange_open and one cgs_model_exchange_sync after init. */
+int cgs_corpus_set_region_split(cgs_corpus *c, int32_t region_split);
+int cgs_model_sweep_overlapped(cgs_model *m, int32_t n_sweeps, int32_t x_ctas);
+int cgs_model_exchange_flush(cgs_model *m);
 int cgs_exchange_sync_local(cgs_model *const *models, int32_t n_models, int32_t n_ctas);
 /* Diagnostics: microseconds CTA 0 of the LAST synchronous exchange spent in { delta pass, barrier, reduce + broadcast of
  * its slice, barrier, apply pass } (device %globaltimer). */

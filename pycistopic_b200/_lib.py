@@ -89,6 +89,9 @@ SIGNATURES = {
     "cgs_model_exchange_round": (ctypes.c_int, [c_vp, ctypes.c_int32]),
     "cgs_model_exchange_wait": (ctypes.c_int, [c_vp]),
     "cgs_model_exchange_sync": (ctypes.c_int, [c_vp, ctypes.c_int32]),
+    "cgs_corpus_set_region_split": (ctypes.c_int, [c_vp, ctypes.c_int32]),
+    "cgs_model_sweep_overlapped": (ctypes.c_int, [c_vp, ctypes.c_int32, ctypes.c_int32]),
+    "cgs_model_exchange_flush": (ctypes.c_int, [c_vp]),
     "cgs_model_exchange_phase_times": (ctypes.c_int, [c_vp, c_f64p]),
     "cgs_exchange_sync_local": (ctypes.c_int, [ctypes.POINTER(c_vp), ctypes.c_int32, ctypes.c_int32]),
     "cgs_exchange_round_local": (ctypes.c_int, [ctypes.POINTER(c_vp), ctypes.c_int32, ctypes.c_int32]),

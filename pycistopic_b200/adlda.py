@@ -18,6 +18,10 @@ of a sweep) the ranks exchange their ``n_wk`` deltas:
 * ``exchange="fused"``: the synchronous fused round kernel (``cgs_model_exchange_sync``): ONE kernel between two
   sweeps does delta, reduce-scatter + all-gather through the peers' arenas over NVLink, apply and the ``n_k``
   rebuild -- 5 table passes of local traffic instead of the 8 of the NCCL path, no library call.
+* ``exchange="overlap"``: the same fused exchange INSIDE the sampling launches (``cgs_model_sweep_overlapped``):
+  a sweep is cut at a region index into two half-sweeps, and while one half is sampled the rows of ``n_wk`` of the
+  other half are exchanged by a few blocks of the same grid.  Statistically the synchronous scheme (every row is
+  exchanged once per sweep, right after it was sampled), but the exchange hides behind the sampling.
 * ``exchange="async"``: the fused peer-memory round kernel (``csrc/exchange_kernels.cuh``) on a
   high-priority stream BESIDE the sweep: the round that publishes sweep s runs while sweep s + 1
   samples, so the exchange costs no time of its own.  With ``sync_per_sweep=1`` a rank sees the other ranks'
@@ -162,6 +166,15 @@ class GpuShard:
     def exchange_sync(self, n_ctas=0):
         self.model.exchange_sync(n_ctas)
 
+    def set_region_split(self, region_split):
+        self.corpus.set_region_split(region_split)
+
+    def sweep_overlapped(self, x_ctas=0):
+        self.model.sweep_overlapped(1, x_ctas)
+
+    def exchange_flush(self):
+        self.model.exchange_flush()
+
     def exchange_wait(self):
         self.model.exchange_wait()
 
@@ -224,7 +237,8 @@ class Exchanger:
         self._dirty = True  # sweeps (or the initial counts) not yet published
         self.use_peer = exchange == "peer" and self.world > 1 and hasattr(shard, "ipc_handle")
         self.use_async = exchange == "async" and hasattr(shard, "arena_handle")
-        self.use_fused = exchange == "fused" and hasattr(shard, "arena_handle")
+        self.use_overlap = exchange == "overlap" and hasattr(shard, "arena_handle")
+        self.use_fused = (exchange == "fused" or self.use_overlap) and hasattr(shard, "arena_handle")
         self.comm_ptr = None
         if self.use_peer:
             handles = [None] * self.world
@@ -267,6 +281,18 @@ class Exchanger:
                 shard.delta_apply()
         self._dirty = False
 
+    def sweep(self, part=0, n_parts=1):
+        """One sweep part with whatever exchange belongs to it."""
+        if self.use_overlap:
+            if n_parts != 1:
+                raise ValueError("the overlapped exchange cuts the sweep itself: sync_per_sweep must be 1")
+            self.shard.sweep_overlapped(self.n_ctas)
+            self._dirty = True
+            return
+        self.before_sweep()
+        self.shard.sweep_part(part, n_parts)
+        self.after_sweep()
+
     def before_sweep(self):
         if self.use_async:
             # publishes everything up to the previous sweep while the next one samples
@@ -282,7 +308,10 @@ class Exchanger:
 
     def drain(self):
         """All replicas identical and complete (needed before log-likelihoods and exports)."""
-        if self.use_async and self._dirty:
+        if self.use_overlap:
+            self.shard.exchange_flush()
+            self._dirty = False
+        elif self.use_async and self._dirty:
             self.step()
         elif self.use_async:
             self.shard.exchange_wait()
@@ -304,8 +333,8 @@ def fit_adlda(binary_matrix, n_topics, n_iter=150, alpha=0.1, eta=0.01, random_s
     distributed = dist.is_available() and dist.is_initialized()
     world = dist.get_world_size() if distributed else 1
     rank = dist.get_rank() if distributed else 0
-    if exchange not in ("auto", "nccl", "peer", "nccl_abi", "async", "fused"):
-        raise ValueError("exchange must be 'auto', 'nccl', 'nccl_abi', 'peer', 'fused' or 'async'")
+    if exchange not in ("auto", "nccl", "peer", "nccl_abi", "async", "fused", "overlap"):
+        raise ValueError("exchange must be 'auto', 'nccl', 'nccl_abi', 'peer', 'fused', 'overlap' or 'async'")
     if sync_per_sweep < 1:
         raise ValueError("sync_per_sweep must be >= 1")
     M = sparse.csr_matrix(binary_matrix)
@@ -329,6 +358,10 @@ def fit_adlda(binary_matrix, n_topics, n_iter=150, alpha=0.1, eta=0.01, random_s
             shard.set_global_size(D, int(cell_ptr[-1]))
         shard.init()
         exchanger = Exchanger(shard, exchange, rounds_per_sweep=rounds_per_sweep)
+        if exchanger.use_overlap:
+            # the region index that halves the tokens of the WHOLE matrix (every rank computes the same one)
+            per_region = np.diff(M.indptr).astype(np.int64)
+            shard.set_region_split(int(np.searchsorted(np.cumsum(per_region), per_region.sum() / 2.0)) + 1)
 
         def loglik():
             exchanger.drain()
@@ -347,9 +380,7 @@ def fit_adlda(binary_matrix, n_topics, n_iter=150, alpha=0.1, eta=0.01, random_s
             if it % refresh == 0:
                 res.loglikelihoods_.append(loglik())
             for part in range(sync_per_sweep):
-                exchanger.before_sweep()
-                shard.sweep_part(part, sync_per_sweep)
-                exchanger.after_sweep()
+                exchanger.sweep(part, sync_per_sweep)
             if on_sweep is not None:
                 on_sweep(it, shard)
         res.final_loglikelihood_ = loglik()

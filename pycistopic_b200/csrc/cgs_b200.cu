@@ -300,6 +300,8 @@ struct cgs_corpus {
     int64_t *d_cell_ptr = nullptr;    // D+1
     int32_t *d_tok_region = nullptr;  // N
     int32_t *d_cell_order = nullptr;  // D, longest cell first
+    int64_t *d_cell_mid = nullptr;    // D: first token of every cell at or above region_split (cgs_corpus_set_region_split)
+    int32_t region_split = -1;
     bool owns_tokens = true;
     int n_models = 0;
     // Construction runs on a private non-blocking stream: pool blocks freed on one non-blocking stream are
@@ -336,6 +338,7 @@ struct cgs_model {
     int sweep_blocks = 0;
     // deterministic mode (cgs_model_set_deterministic): sweeps read copies of n_wk / n_k taken at the start of
     // each of det_parts sub-sweeps, one warp per cell
+    int sweep_half = 0, sweep_x_ctas = 0;  // set around the launches of cgs_model_sweep_overlapped
     bool fp64 = false;  // conditional in double (A/B build, cgs_model_set_conditional_precision)
     int det_parts = 0;
     int32_t *d_nwk_ro = nullptr, *d_nk_ro = nullptr;
@@ -346,6 +349,9 @@ struct cgs_model {
     int x_ranks = 0, x_rank = 0;
     uint32_t x_round = 0;
     int x_sync_blocks = 0;
+    int sweep_blocks_fused = 0;
+    ExchangeParams x_fused;      // the exchange of the current fused launch
+    int x_pending_half = 0;      // overlapped sweeps: which half of the rows was sampled and not yet exchanged
     cudaStream_t x_stream = nullptr;
     cudaEvent_t x_event = nullptr, x_done = nullptr;
     bool x_pending = false;
@@ -582,6 +588,7 @@ int cgs_corpus_destroy(cgs_corpus *c) {
         if (c->d_tok_region) dfree(c->d_tok_region, c->stream);
     }
     if (c->d_cell_order) dfree(c->d_cell_order, c->stream);
+    if (c->d_cell_mid) dfree(c->d_cell_mid, c->stream);
     if (c->stream) cudaStreamDestroy(c->stream);  // pending frees still run
     delete c;
     return 0;
@@ -598,6 +605,19 @@ int cgs_corpus_dims(const cgs_corpus *c, int32_t *n_cells, int32_t *n_regions, i
 int cgs_corpus_set_token_offset(cgs_corpus *c, int64_t off) {
     if (!c) CGS_FAIL("NULL corpus");
     c->token_offset = off;
+    return 0;
+}
+
+int cgs_corpus_set_region_split(cgs_corpus *c, int32_t region_split) {
+    if (!c) CGS_FAIL("NULL corpus");
+    if (region_split < 0 || region_split > c->n_regions) CGS_FAIL("region_split outside [0, n_regions]");
+    DeviceGuard g(c->device);
+    if (!c->d_cell_mid) CGS_TRY(dmalloc(&c->d_cell_mid, (size_t)c->n_cells, c->stream));
+    cell_split_kernel<<<(unsigned)ceil_div(c->n_cells, 256), 256, 0, c->stream>>>(c->d_cell_ptr, c->d_tok_region, c->n_cells,
+                                                                                 region_split, c->d_cell_mid);
+    CGS_CUDA(cudaGetLastError());
+    CGS_CUDA(cudaStreamSynchronize(c->stream));
+    c->region_split = region_split;
     return 0;
 }
 
@@ -799,6 +819,7 @@ int cgs_model_init(cgs_model *m) {
     CGS_CUDA(cudaGetLastError());
     m->launches += 1;
     m->sweeps = 0;
+    m->x_pending_half = 0;
     return rebuild_counts(m);
 }
 
@@ -839,17 +860,37 @@ int cgs_model_get_z(cgs_model *m, int32_t *z) {
 }  // extern "C"
 
 // ---- sweep dispatch --------------------------------------------------------------------------
+static ExchangeParams g_no_exchange;  // zero-initialised: the argument of launches that do not exchange
+
 template <int TPT, int CH, typename R>
 static int launch_sweep(cgs_model *m, const SweepParams &p, int *blocks_cache) {
-    if (*blocks_cache == 0) {
+    const bool fused = p.x_ctas > 0;
+    int *cache = fused ? &m->sweep_blocks_fused : blocks_cache;
+    if (*cache == 0) {
         int per_sm = 0;
-        CGS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep_kernel<TPT, CH, R>, m->threads, 0));
+        if (fused) {
+            if constexpr (std::is_same<R, float>::value)
+                CGS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep_kernel<TPT, CH, float, true>, m->threads, 0));
+        } else {
+            CGS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep_kernel<TPT, CH, R, false>, m->threads, 0));
+        }
         if (per_sm < 1) per_sm = 1;
-        *blocks_cache = m->corpus->num_sms * per_sm;
+        *cache = m->corpus->num_sms * per_sm;
     }
-    int blocks = std::max(1, std::min(*blocks_cache, m->corpus->n_cells));
+    int blocks = std::max(1, std::min(*cache, m->corpus->n_cells));
     blocks = std::min(blocks, m->max_blocks > 0 ? m->max_blocks : m->auto_blocks);
-    sweep_kernel<TPT, CH, R><<<blocks, m->threads, 0, m->stream>>>(p);
+    if (fused) {
+        if constexpr (std::is_same<R, float>::value) {
+            // the exchange blocks come first in the grid and must all be resident: they wait for each other and
+            // for the peers; the sampling blocks take whatever is left of the device and pull cells from the queue
+            blocks = std::max(1, std::min(blocks, *cache - p.x_ctas));
+            sweep_kernel<TPT, CH, float, true><<<blocks + p.x_ctas, m->threads, 0, m->stream>>>(p, m->x_fused);
+        } else {
+            CGS_FAIL("the fused sweep + exchange launch exists for the fp32 conditional only");
+        }
+    } else {
+        sweep_kernel<TPT, CH, R, false><<<blocks, m->threads, 0, m->stream>>>(p, g_no_exchange);
+    }
     CGS_CUDA(cudaGetLastError());
     return 0;
 }
@@ -949,6 +990,9 @@ static int sweep_impl(cgs_model *m, int32_t n_sweeps, int32_t part, int32_t n_pa
     p.part = part;
     p.n_parts = n_parts;
     p.visit_counter = m->d_visits;
+    p.cell_mid = c->d_cell_mid;
+    p.half = m->sweep_half;
+    p.x_ctas = m->sweep_x_ctas;
     const bool det = m->det_parts > 0;
     const size_t WKp = (size_t)c->n_regions * (size_t)m->Kp;
     if (det) {
@@ -1466,15 +1510,22 @@ int cgs_model_exchange_open(cgs_model *m, void *const *peer_arena, int32_t n_ran
     return 0;
 }
 
-static void fill_exchange_params(cgs_model *m, ExchangeParams &p) {
+// rows [row0, row1) of the table (row1 < 0: all rows)
+static void fill_exchange_params(cgs_model *m, ExchangeParams &p, int64_t row0 = 0, int64_t row1 = -1) {
     cgs_corpus *c = m->corpus;
-    p.n_wk = m->d_nwk;
-    p.snap = m->d_snap;
+    if (row1 < 0) row1 = c->n_regions;
+    const int64_t off = row0 * m->Kp;  // in counts; a multiple of 4
+    p.n_wk = m->d_nwk + off;
+    p.snap = m->d_snap ? m->d_snap + off : nullptr;
     p.n_k = m->d_nk;
     p.peers = m->xpeers;
+    for (int q = 0; q < m->x_ranks; ++q) {
+        p.peers.delta[q] += off / 4;
+        p.peers.total[q] += off / 4;
+    }
     p.n_ranks = m->x_ranks;
     p.rank = m->x_rank;
-    p.n4 = (int64_t)c->n_regions * m->Kp / 4;
+    p.n4 = (row1 - row0) * m->Kp / 4;
     p.Kp4 = m->Kp / 4;
     p.round = ++m->x_round;
 }
@@ -1503,8 +1554,60 @@ int cgs_model_exchange_round(cgs_model *m, int32_t n_ctas) {
     return 0;
 }
 
+static int exchange_sync_rows(cgs_model *m, int32_t n_ctas, int64_t row0, int64_t row1);
+
 int cgs_model_exchange_sync(cgs_model *m, int32_t n_ctas) {
     if (!m) CGS_FAIL("NULL model");
+    if (m->x_pending_half) CGS_FAIL("overlapped sweeps are pending: call cgs_model_exchange_flush");
+    return exchange_sync_rows(m, n_ctas, 0, -1);
+}
+
+int cgs_model_exchange_flush(cgs_model *m) {
+    if (!m) CGS_FAIL("NULL model");
+    if (!m->x_pending_half) return 0;
+    const int64_t split = m->corpus->region_split;
+    const int rc = m->x_pending_half == 1 ? exchange_sync_rows(m, 0, 0, split) : exchange_sync_rows(m, 0, split, -1);
+    if (rc == 0) m->x_pending_half = 0;
+    return rc;
+}
+
+int cgs_model_sweep_overlapped(cgs_model *m, int32_t n_sweeps, int32_t x_ctas) {
+    if (!m) CGS_FAIL("NULL model");
+    if (n_sweeps < 0) CGS_FAIL("n_sweeps < 0");
+    if (m->x_ranks < 1) CGS_FAIL("cgs_model_exchange_open has not been called");
+    cgs_corpus *c = m->corpus;
+    if (c->region_split < 0 || !c->d_cell_mid) CGS_FAIL("cgs_corpus_set_region_split has not been called");
+    if (m->det_parts > 0 || m->fp64) CGS_FAIL("overlapped sweeps need the default fp32 schedule");
+    DeviceGuard g(c->device);
+    if (x_ctas <= 0) x_ctas = c->num_sms;
+    x_ctas = std::min(x_ctas, 4 * c->num_sms);
+    const int64_t split = c->region_split, W = c->n_regions;
+    int rc = 0;
+    for (int32_t s = 0; s < n_sweeps && rc == 0; ++s) {
+        for (int half = 1; half <= 2 && rc == 0; ++half) {
+            // while this half is sampled, the rows of the other half -- sampled by the previous launch -- are exchanged
+            const bool exchange = m->x_pending_half != 0;
+            if (exchange) {
+                if (m->x_pending_half == half) { rc = fail(__FILE__, __LINE__, "overlapped sweep out of step"); break; }
+                if (m->x_pending_half == 1) fill_exchange_params(m, m->x_fused, 0, split);
+                else fill_exchange_params(m, m->x_fused, split, W);
+                m->x_launches += 1;
+            }
+            m->sweep_half = half;
+            m->sweep_x_ctas = exchange ? x_ctas : 0;
+            const int64_t before = m->sweeps;
+            rc = sweep_impl(m, 1, 0, 1);
+            m->sweeps = before;  // two half-sweeps are one sweep (same Philox sweep index)
+            m->sweep_half = 0;
+            m->sweep_x_ctas = 0;
+            m->x_pending_half = half;
+        }
+        if (rc == 0) m->sweeps += 1;
+    }
+    return rc;
+}
+
+static int exchange_sync_rows(cgs_model *m, int32_t n_ctas, int64_t row0, int64_t row1) {
     if (m->x_ranks < 1) CGS_FAIL("cgs_model_exchange_open has not been called");
     cgs_corpus *c = m->corpus;
     DeviceGuard g(c->device);
@@ -1517,9 +1620,8 @@ int cgs_model_exchange_sync(cgs_model *m, int32_t n_ctas) {
     // every CTA waits at the cross-rank barriers: the grid must be resident at once
     n_ctas = n_ctas <= 0 ? m->x_sync_blocks : std::min(n_ctas, m->x_sync_blocks);
     ExchangeParams p;
-    fill_exchange_params(m, p);
+    fill_exchange_params(m, p, row0, row1);
     nvtxRangePushA("cgs_model_exchange_sync");
-    CGS_CUDA(cudaMemsetAsync(m->d_nk, 0, sizeof(int32_t) * (size_t)m->Kp, m->stream));
     exchange_sync_kernel<<<n_ctas, kExchangeThreads, sizeof(int) * (size_t)m->Kp, m->stream>>>(p);
     CGS_CUDA(cudaGetLastError());
     nvtxRangePop();
@@ -1556,11 +1658,6 @@ static int exchange_local(cgs_model *const *models, int32_t n_models, int32_t n_
         CGS_CUDA(cudaEventRecord(models[i]->x_event, models[i]->stream));
         CGS_CUDA(cudaStreamWaitEvent(lead->x_stream, models[i]->x_event, 0));
         fill_exchange_params(models[i], a.r[i]);
-        if (sync_variant) {
-            CGS_CUDA(cudaMemsetAsync(models[i]->d_nk, 0, sizeof(int32_t) * (size_t)models[i]->Kp, models[i]->stream));
-            CGS_CUDA(cudaEventRecord(models[i]->x_event, models[i]->stream));
-            CGS_CUDA(cudaStreamWaitEvent(lead->x_stream, models[i]->x_event, 0));
-        }
     }
     void *args[] = {&a, &sync_variant};
     CGS_CUDA(cudaLaunchCooperativeKernel((const void *)exchange_round_multi_kernel, dim3((unsigned)n_ctas, (unsigned)n_models),

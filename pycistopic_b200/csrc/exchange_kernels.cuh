@@ -55,6 +55,9 @@ struct ExchangeParams {
 __device__ __forceinline__ void st_release_sys_u32(uint32_t *p, uint32_t v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ void st_relaxed_sys_u32(uint32_t *p, uint32_t v) {
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t *p) {
     uint32_t v;
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -93,9 +96,11 @@ __device__ __forceinline__ void exchange_barrier(const ExchangeParams &p, int ph
         if (prev == n_ctas - 1) {
             __threadfence();
             *counter = 0;  // next use is in the next round, after both barriers of this one
-            __threadfence_system();
-            for (int q = 0; q < p.n_ranks; ++q)
-                st_release_sys_u32(p.peers.flags[q] + phase * kMaxExchangeRanks + p.rank, p.round);
+            __threadfence_system();  // ONE system-scope fence, then the flags (a release store per peer would fence R times)
+            for (int j = 0; j < p.n_ranks; ++j) {
+                const int q = (p.rank + 1 + j) % p.n_ranks;
+                st_relaxed_sys_u32(p.peers.flags[q] + phase * kMaxExchangeRanks + p.rank, p.round);
+            }
         }
     }
     if ((int)threadIdx.x < p.n_ranks) {
@@ -154,7 +159,8 @@ __device__ __forceinline__ void exchange_round_body(const ExchangeParams &p, uns
             int4 t[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) t[u] = make_int4(0, 0, 0, 0);
-            for (int q = 0; q < R; ++q) {
+            for (int j = 0; j < R; ++j) {
+                const int q = (p.rank + 1 + j) % R;  // staggered peers
                 int4 v[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
@@ -164,7 +170,8 @@ __device__ __forceinline__ void exchange_round_body(const ExchangeParams &p, uns
 #pragma unroll
                 for (int u = 0; u < 4; ++u) { t[u].x += v[u].x; t[u].y += v[u].y; t[u].z += v[u].z; t[u].w += v[u].w; }
             }
-            for (int q = 0; q < R; ++q) {
+            for (int j = 0; j < R; ++j) {
+                const int q = (p.rank + 1 + j) % R;
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int64_t i = i0 + u * stride;
@@ -213,8 +220,9 @@ __device__ __forceinline__ void exchange_round_body(const ExchangeParams &p, uns
 //   barrier
 //   phase 2   owner of a slice: G' = G + sum_q delta_q, written into EVERY rank's receive buffer over NVLink
 //   barrier
-//   phase 3   n_wk = G';  n_k = column sums of G'                        (read 1, write 1 table)
-// i.e. 5 table passes of local traffic instead of the 8 of delta_compute + all-reduce + delta_apply, and 2 (R-1)/R
+//   phase 3   n_k += column sums of (G' - n_wk);  n_wk = G'             (read 2, write <= 1 table)
+// on any contiguous range of ROWS of the table (the pointers of ExchangeParams are offset by the host), i.e. 6 table
+// passes of local traffic instead of the 8 of delta_compute + all-reduce + delta_apply, and 2 (R-1)/R
 // tables over NVLink.  Statistically identical to the all-reduce scheme (every rank samples a sweep against the
 // global counts of the previous exchange plus its own live changes).
 __device__ __forceinline__ void exchange_sync_body(const ExchangeParams &p, unsigned cta, unsigned n_ctas, int *x_colsum) {
@@ -259,7 +267,9 @@ __device__ __forceinline__ void exchange_sync_body(const ExchangeParams &p, unsi
                 const int64_t i = i0 + u * stride;
                 if (i < hi) t[u] = __ldcs(my_g + i);
             }
-            for (int q = 0; q < R; ++q) {
+            for (int j = 0; j < R; ++j) {
+                // staggered: rank r starts with r + 1, so the R ranks pull from R different peers at any moment
+                const int q = (p.rank + 1 + j) % R;
                 int4 v[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
@@ -269,7 +279,8 @@ __device__ __forceinline__ void exchange_sync_body(const ExchangeParams &p, unsi
 #pragma unroll
                 for (int u = 0; u < 4; ++u) { t[u].x += v[u].x; t[u].y += v[u].y; t[u].z += v[u].z; t[u].w += v[u].w; }
             }
-            for (int q = 0; q < R; ++q) {
+            for (int j = 0; j < R; ++j) {
+                const int q = (p.rank + 1 + j) % R;
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int64_t i = i0 + u * stride;
@@ -281,27 +292,30 @@ __device__ __forceinline__ void exchange_sync_body(const ExchangeParams &p, unsi
     if (stamper) stamps[3] = global_timer_ns();
     exchange_barrier(p, 1, n_ctas);
     if (stamper) stamps[4] = global_timer_ns();
+    // n_k moves by the column sums of what the OTHER ranks changed (G' - n_wk): exact, and valid while a sampler that
+    // works on other rows keeps adding its own changes to n_k
     for (int64_t i0 = tid0; i0 < p.n4; i0 += 4 * stride) {
-        int4 g[4];
+        int4 g[4], o[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int64_t i = i0 + u * stride;
-            if (i < p.n4) g[u] = ld_sys_v4(my_g + i);
+            if (i < p.n4) { g[u] = ld_sys_v4(my_g + i); o[u] = __ldcg(n_wk + i); }
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int64_t i = i0 + u * stride;
             if (i >= p.n4) continue;
+            const int4 x = make_int4(g[u].x - o[u].x, g[u].y - o[u].y, g[u].z - o[u].z, g[u].w - o[u].w);
+            if ((x.x | x.y | x.z | x.w) == 0) continue;
             __stcg(n_wk + i, g[u]);  // stays in L2 for the sweep that follows
             const int col = (int)(i % p.Kp4) * 4;
-            if (g[u].x) atomicAdd(&x_colsum[col + 0], g[u].x);
-            if (g[u].y) atomicAdd(&x_colsum[col + 1], g[u].y);
-            if (g[u].z) atomicAdd(&x_colsum[col + 2], g[u].z);
-            if (g[u].w) atomicAdd(&x_colsum[col + 3], g[u].w);
+            if (x.x) atomicAdd(&x_colsum[col + 0], x.x);
+            if (x.y) atomicAdd(&x_colsum[col + 1], x.y);
+            if (x.z) atomicAdd(&x_colsum[col + 2], x.z);
+            if (x.w) atomicAdd(&x_colsum[col + 3], x.w);
         }
     }
     __syncthreads();
-    // n_k was zeroed by the host before the launch
     for (int k = threadIdx.x; k < Kp; k += blockDim.x)
         if (x_colsum[k]) red_add_global_i32(p.n_k + k, x_colsum[k]);
     if (stamper) stamps[5] = global_timer_ns();

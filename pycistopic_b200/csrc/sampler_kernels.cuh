@@ -28,6 +28,7 @@
 // batches and once per cell.
 #pragma once
 #include "common.cuh"
+#include "exchange_kernels.cuh"
 
 namespace cgs {
 
@@ -47,6 +48,9 @@ struct SweepParams {
     int32_t *n_k;
     const int32_t *n_k_read;     // same for the topic totals
     const int32_t *cell_order;
+    const int64_t *cell_mid;     // per cell: index of its first token whose region is >= the corpus' region split
+    int32_t half;                // 0 = whole cells; 1 = only tokens below the region split; 2 = only those at or above it
+    int32_t x_ctas;              // fused launches: blocks [0, x_ctas) run the n_wk exchange, the rest sample
     int32_t *work_counter;
     int32_t n_cells;
     int32_t K;
@@ -330,19 +334,35 @@ template <int TPT, int CH> constexpr bool kDeepTokenPrefetch = (TPT <= 2 && CH <
 // with two chunks per lane the 48-register budget measured 3-4 % SLOWER than 64, profiles/r2_small_k_variants.txt),
 // 32 warps at 64 registers up to 4 chunks, 24 warps at 80 registers for 5-6 chunks, 16 warps beyond.  A cell may take
 // up to 8 warps (256 threads) for CH = 1, 16 (512) for CH 2-4, 12 (384) for CH 5-6, 8 (256) beyond.
-template <int CH, typename R = float> struct SweepBounds {
+template <int CH, typename R = float, bool XCH = false> struct SweepBounds {
     static constexpr int kThreads = CH <= 1 ? 256 : CH <= 4 ? 512 : CH <= 6 ? 384 : 256;
-    static constexpr int kMinBlocks = sizeof(R) == 8 ? 1 : CH <= 1 ? 5 : 2;  // the fp64 A/B build trades occupancy for registers
+    // the fp64 A/B build trades occupancy for registers; the exchange blocks of a fused launch want 64
+    static constexpr int kMinBlocks = sizeof(R) == 8 ? 1 : (CH <= 1 && !XCH) ? 5 : (CH <= 1 ? 4 : 2);
 };
 
-template <int TPT, int CH, typename R = float>
-__global__ void __launch_bounds__(SweepBounds<CH, R>::kThreads, SweepBounds<CH, R>::kMinBlocks)
-sweep_kernel(const SweepParams p) {
+// XCH = true: the launch that overlaps the AD-LDA exchange with sampling.  Tokens are sorted by region inside a cell, so
+// a sweep can be cut at a region index w* into two half-sweeps -- first every cell's tokens below w*, then the rest --
+// and while one half is sampled, the rows of n_wk that belong to the OTHER half (changed by the previous half-sweep,
+// untouched by this one) are exchanged between the ranks: blocks [0, x_ctas) of the grid run the synchronous exchange
+// on that row range (exchange_sync_body: delta, reduce-scatter + all-gather over the peers' arenas, apply), all other
+// blocks sample.  One launch does both, so the exchange blocks are resident from the first cycle (they come first in
+// the grid) and the NVLink round trips, the cross-rank barriers and the table passes hide behind the sampling.  Every
+// row is still exchanged exactly once per sweep, right after it was sampled: the statistics are those of the
+// synchronous scheme (a rank sees the others' counts of a row as of the previous sweep).
+template <int TPT, int CH, typename R = float, bool XCH = false>
+__global__ void __launch_bounds__(SweepBounds<CH, R, XCH>::kThreads, SweepBounds<CH, R, XCH>::kMinBlocks)
+sweep_kernel(const SweepParams p, const ExchangeParams xp) {
     using L = CellSmem<TPT, CH, R>;
     constexpr int KS = L::KS;  // topic slots covered by one token group
     constexpr int RB = L::RB;
     constexpr unsigned FULL = 0xffffffffu;
     __shared__ __align__(16) uint32_t smem_w[L::WORDS];
+    if constexpr (XCH) {
+        if ((int)blockIdx.x < p.x_ctas) {
+            exchange_sync_body(xp, blockIdx.x, (unsigned)p.x_ctas, reinterpret_cast<int *>(smem_w));
+            return;
+        }
+    }
     const uint32_t sm = smem_u32(smem_w);
     const uint32_t s_f = sm + L::F, s_inv = sm + L::INV, s_den = sm + L::DEN, s_ndk = sm + L::NDK, s_pub = sm + L::PUB;
     const uint32_t s_slot = sm + L::SLOT;
@@ -371,7 +391,9 @@ sweep_kernel(const SweepParams p) {
         const int slot = lds_i(s_slot) * p.n_parts + p.part;
         if (slot >= p.n_cells) break;
         const int cell = p.cell_order[slot];
-        const int64_t t0 = p.cell_ptr[cell], t1 = p.cell_ptr[cell + 1];
+        int64_t t0 = p.cell_ptr[cell], t1 = p.cell_ptr[cell + 1];
+        if (p.half == 1) t1 = p.cell_mid[cell];
+        else if (p.half == 2) t0 = p.cell_mid[cell];
         int32_t *ndk_row = p.n_dk + (int64_t)cell * Kp;
 
         for (int k = tid; k < KS; k += blockDim.x) {
@@ -660,6 +682,20 @@ sweep_kernel(const SweepParams p) {
         }
         __syncthreads();
     }
+}
+
+// cell_mid[d] = index of the first token of cell d whose region is >= region_split (tokens are sorted by region)
+__global__ void cell_split_kernel(const int64_t *__restrict__ cell_ptr, const int32_t *__restrict__ tok_region,
+                                  int32_t n_cells, int32_t region_split, int64_t *__restrict__ cell_mid) {
+    const int32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= n_cells) return;
+    int64_t lo = cell_ptr[d], hi = cell_ptr[d + 1];
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (tok_region[mid] < region_split) lo = mid + 1;
+        else hi = mid;
+    }
+    cell_mid[d] = lo;
 }
 
 // ---- z initialisation and count rebuild ------------------------------------------------------

@@ -107,6 +107,10 @@ class Corpus:
         size their concurrency caps against it."""
         check(_lib.load().cgs_corpus_set_global_size(self._h, int(n_cells_global), int(n_tokens_global)))
 
+    def set_region_split(self, region_split: int):
+        """Region index that cuts a sweep into two half-sweeps (overlapped AD-LDA exchange)."""
+        check(_lib.load().cgs_corpus_set_region_split(self._h, int(region_split)))
+
     def token_lists(self):
         """(WS, DS) exactly as ``lda.utils.matrix_to_lists`` returns them."""
         WS = np.empty(self.n_tokens, np.int32)
@@ -351,6 +355,14 @@ class DeviceModel:
     def exchange_sync(self, n_ctas: int = 0):
         """The synchronous fused exchange (one kernel on the model's stream, between two sweeps)."""
         check(_lib.load().cgs_model_exchange_sync(self._h, int(n_ctas)))
+
+    def sweep_overlapped(self, n_sweeps: int = 1, x_ctas: int = 0):
+        """Sweeps whose n_wk exchange runs inside the sampling launches (two half-sweeps per sweep)."""
+        check(_lib.load().cgs_model_sweep_overlapped(self._h, int(n_sweeps), int(x_ctas)))
+
+    def exchange_flush(self):
+        """Publish the rows of the last half-sweep (before reading counts or log-likelihoods)."""
+        check(_lib.load().cgs_model_exchange_flush(self._h))
 
     def exchange_phase_times(self):
         """Microseconds of the last synchronous exchange per phase: delta, barrier, reduce, barrier, apply."""

@@ -57,7 +57,7 @@ def _worker(rank, world, port, out_dir, exchange, sync_per_sweep, K, n_iter):
 
 
 @pytest.mark.skipif(_n_gpus() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("exchange,sync_per_sweep", [("nccl", 1), ("peer", 1), ("peer", 4), ("nccl_abi", 1), ("fused", 1),
+@pytest.mark.parametrize("exchange,sync_per_sweep", [("nccl", 1), ("peer", 1), ("peer", 4), ("nccl_abi", 1), ("fused", 1), ("overlap", 1),
                                                      ("async", 2), ("async", 4)])
 def test_adlda_two_gpus(exchange, sync_per_sweep):
     import torch.multiprocessing as mp

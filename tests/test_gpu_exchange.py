@@ -338,3 +338,39 @@ def test_deterministic_mode_trace_close_to_oracle(small):
     corpus.close()
     print(f"deterministic mode, 32 sub-sweeps: max deviation {rel.max():.3%} at sweep {rel.argmax()}, final {rel[-1]:.3%}")
     assert rel.max() < 0.02 and rel[-1] < 0.005, f"trace deviates {rel.max():.3%} at sweep {rel.argmax()}"
+
+
+@pytest.mark.parametrize("K", [3, 10, 50])
+def test_overlapped_sweeps_single_rank_mechanics(small, K):
+    """cgs_model_sweep_overlapped with one rank (the exchange blocks of the fused launch then reduce over a single
+    arena): two half-sweeps by region index visit every token exactly once per sweep, the tables stay the exact
+    bookkeeping of z through the in-launch exchange of the other half's rows, and the chain behaves like the plain one
+    (log-likelihood within 1 % of the plain schedule's after the same number of sweeps, seed-averaged)."""
+    from pycistopic_b200 import Corpus, DeviceModel
+    corpus = Corpus.from_regions_by_cells(small)
+    per_region = np.diff(small.indptr)
+    split = int(np.searchsorted(np.cumsum(per_region), per_region.sum() / 2.0)) + 1
+    corpus.set_region_split(split)
+    lls = {"plain": [], "overlapped": []}
+    for seed in (1, 2, 3, 4):
+        for mode in lls:
+            mdl = DeviceModel(corpus, K, 50.0 / K, 0.1, seed=seed)
+            mdl.init()
+            if mode == "overlapped":
+                mdl.exchange_open([mdl.exchange_arena()[0]], 0)
+                mdl.exchange_sync()
+                before = mdl.state_hash()
+                assert before["sum_nwk"] == corpus.n_tokens == before["sum_nk"]
+                mdl.sweep_overlapped(25, 8)
+                mdl.exchange_flush()
+                mdl.sync()
+                assert mdl.exchange_timeouts() == 0
+                assert mdl.sweeps_done == 25
+            else:
+                mdl.sweep(25)
+            assert mdl.verify_counts() == {"n_dk": 0, "n_wk": 0, "n_k": 0}
+            lls[mode].append(mdl.loglikelihood())
+            mdl.close()
+    a, b = np.mean(lls["plain"]), np.mean(lls["overlapped"])
+    assert abs(a - b) / abs(a) < 0.01, lls
+    corpus.close()
