@@ -315,7 +315,7 @@ def run_adlda_leg(args, dev, rank, world, local_rank, shape=None):
         shard = GpuShard(None, (cb, ce), t0, K_adlda, ALPHA / K_adlda, ETA, MODEL_SEED, device=local_rank,
                          exchange=exchange, corpus=corpus)
         shard.init()
-        ex = Exchanger(shard, exchange)
+        ex = Exchanger(shard, exchange, n_ctas=args.overlap_ctas if exchange == "overlap" else 0)
         if exchange == "overlap":
             per_region = torch.bincount(tok, minlength=W).to(torch.int64)
             if world > 1:
@@ -1114,6 +1114,7 @@ def main():
     ap.add_argument("--adlda-rank-local-data", action="store_true",
                     help="every rank draws only its own cells (always on for C4)")
     ap.add_argument("--adlda-modes", default="", help="comma-separated exchange modes of the AD-LDA legs (default: all)")
+    ap.add_argument("--overlap-ctas", type=int, default=0, help="exchange blocks of the fused launches (0 = one per two SMs)")
     ap.add_argument("--async-parts", type=int, default=2, help="rounds (= sub-sweeps) per sweep of the async exchange")
     ap.add_argument("--adlda-only", action="store_true", help="skip the model-sweep legs (used for the C4 run)")
     args = ap.parse_args()

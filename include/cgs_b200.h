@@ -245,7 +245,7 @@ int cgs_model_exchange_sync(cgs_model *m, int32_t n_ctas);
 /* The exchange OVERLAPPED with sampling, in one launch (csrc/sampler_kernels.cuh, sweep_kernel<.., XCH = true>).
  * Tokens are sorted by region inside a cell, so a sweep can be cut at a region index into two half-sweeps; while one
  * half is sampled, the rows of n_wk of the OTHER half -- changed by the previous launch, untouched by this one -- go
- * through the synchronous exchange on x_ctas blocks of the same grid (default: one per SM).  Every row is exchanged
+ * through the synchronous exchange on x_ctas blocks of the same grid (default: one per two SMs).  Every row is exchanged
  * once per sweep, right after it was sampled: same statistics as cgs_model_exchange_sync after every sweep, but the
  * NVLink round trips, the cross-rank waits and the table passes hide behind the sampling.
  *   cgs_corpus_set_region_split: the region index that cuts the sweep (every rank the same; pick the one that halves
