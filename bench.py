@@ -33,7 +33,10 @@ import numpy as np  # noqa: E402
 N_TOPICS = [2, 5, 10, 15, 20, 25, 30, 35, 40, 45, 50]
 ALPHA, ETA, MODEL_SEED, DATA_SEED = 50.0, 0.1, 555, 1234
 WORKLOAD = "C2"
-E2E_SWEEPS = 10
+# sweeps per end-to-end call: the reference's default n_iter (run_cgs_models(..., n_iter=150), lda_models.py:104).  Round 1
+# used 10, which makes the fixed costs of a call (260 MB upload, create / init / export) a sixth of it -- no user call
+# is that short; BASELINE.json's own configs run 150-500 iterations
+E2E_SWEEPS = 150
 BURN_IN = 20  # sweeps before any timing, so the chains are past the z = i mod K transient
 
 
@@ -668,7 +671,7 @@ def run_cuda(args):
     import torch.distributed as dist
 
     from pycistopic_b200 import Corpus, DeviceModel, _lib
-    from pycistopic_b200.lda_models import schedule_models, schedule_models_split
+    from pycistopic_b200.lda_models import schedule_models, schedule_models_paired, schedule_models_split
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -702,16 +705,15 @@ def run_cuda(args):
             dist.barrier()
 
     # ---- plan -------------------------------------------------------------------------------------
-    # Whole models, longest first (one model per GPU at a time).  With --split the models are divisible: the GPUs are
-    # filled to a common level and a model that does not fit is continued on the next GPU -- its cells sharded AD-LDA
-    # style, one fused exchange kernel per sweep between the GPUs that share it (lda_models.schedule_models_split, costs
-    # = sweep times measured here).  Measured on 8 GPUs (profiles/r2_bench_n8_split_plan_v1.json) that is SLOWER than
-    # whole models for C2: a 20 % shard of a 10 000-cell matrix takes 40 % of the sweep (two waves of cells instead of
-    # 8.4) and every split pays ~0.35 ms of exchange on a ~2 ms step, so it is opt-in.
-    whole_plan = schedule_models(N_TOPICS, world)
-    my_topics = [N_TOPICS[i] for i in whole_plan[rank]]  # the end-to-end leg keeps whole models
+    # Whole models, longest first (one model per GPU at a time), placed with sweep times measured here.  11 models
+    # cannot fill 8 GPUs evenly (the K = 50 model alone is the makespan), so --plan paired / auto additionally splits the
+    # longest models between TWO GPUs that run their parts at the same time, cells sharded AD-LDA style with the exchange
+    # inside the sampling launches (lda_models.schedule_models_paired).  --plan wrap is the wrap-around filling with a
+    # synchronous exchange per split (measured slower than whole models, profiles/r2_bench_n8_split_plan_v1.json).
     costs = None
-    if world > 1 and args.split:
+    plan_kind = "whole"
+    level = None
+    if world > 1 and args.plan != "lpt":
         mine = {}
         for i in range(rank, len(N_TOPICS), world):
             K = N_TOPICS[i]
@@ -731,11 +733,30 @@ def run_cuda(args):
         for g in gathered:
             for i, v in g.items():
                 costs[i] = v
-        # what every part of a split model pays per sweep: 5 passes over its n_wk table at ~5 TB/s + two barriers
-        overhead = [5.0 * 4 * W * ((K + 3) // 4 * 4) / 5.0e12 * 1e3 + 0.03 for K in N_TOPICS]
-        plan, level = schedule_models_split(costs, world, overhead)
+    if costs is None:
+        whole_plan = schedule_models(N_TOPICS, world)
+        plan = [[(i, 0.0, 1.0) for i in p] for p in whole_plan]
     else:
-        plan, level = [[(i, 0.0, 1.0) for i in p] for p in whole_plan], None
+        # whole models placed longest-first with MEASURED sweep times and improved by moves / swaps
+        plan, level = schedule_models_paired(costs, world, max_splits=0)
+        whole_plan = [[i for (i, _, _) in p] for p in plan]
+        if args.plan == "wrap":
+            overhead = [5.0 * 4 * W * ((K + 3) // 4 * 4) / 5.0e12 * 1e3 + 0.03 for K in N_TOPICS]
+            plan, level = schedule_models_split(costs, world, overhead)
+            plan_kind = "wrap"
+        elif args.plan in ("auto", "paired"):
+            # ... and with the longest models split between two GPUs that run them at the same time (overlapped exchange)
+            paired, level_p = schedule_models_paired(costs, world)
+            if args.plan == "paired" or level_p < 0.97 * level:
+                plan, level, plan_kind = paired, level_p, "paired"
+            if all(f0 <= 0.0 and f1 >= 1.0 for p in plan for (_, f0, f1) in p):
+                plan_kind = "whole"
+    my_topics = [N_TOPICS[i] for i in whole_plan[rank]]  # the end-to-end leg keeps whole models
+    region_split = None
+    if plan_kind == "paired":
+        per_region = torch.bincount(tok, minlength=W).to(torch.int64)
+        region_split = min(W, int(torch.searchsorted(torch.cumsum(per_region, 0), torch.tensor([N // 2], device=dev)).item()) + 1)
+        del per_region
 
     # ---- this rank's items ---------------------------------------------------------------------------
     tok_cum = cell_ptr  # tokens before every cell
@@ -756,9 +777,11 @@ def run_cuda(args):
         c = Corpus.from_device_tokens(cp.data_ptr(), tk.data_ptr(), ce - cb, W, t1 - t0, device=local_rank,
                                       token_offset=t0, keepalive=(cp, tk))
         c.set_global_size(D, N)
+        if region_split is not None:
+            c.set_region_split(region_split)
         m = DeviceModel(c, K, ALPHA / K, ETA, seed=MODEL_SEED, stream=stream.cuda_stream)
         items.append({"i": i, "K": K, "model": m, "corpus": c, "split": True, "tokens": t1 - t0, "f": (f0, f1),
-                      "cells": (cb, ce)})
+                      "cells": (cb, ce), "overlap": region_split is not None})
     # peers of the split models: every rank publishes the arenas of its parts, parts are ordered by their fraction
     if world > 1:
         mine = []
@@ -800,10 +823,13 @@ def run_cuda(args):
         for j, it in enumerate(items):
             if events is not None:
                 events[j][0].record(stream)
-            it["model"].sweep(1)
+            if it.get("overlap"):
+                it["model"].sweep_overlapped(1)  # the exchange with the partner GPU runs inside the two launches
+            else:
+                it["model"].sweep(1)
             if events is not None:
                 events[j][1].record(stream)
-            if it["split"]:
+            if it["split"] and not it.get("overlap"):
                 it["model"].exchange_sync()
 
     for _ in range(BURN_IN):
@@ -833,6 +859,9 @@ def run_cuda(args):
     clock_info = clocks.stop() if rank == 0 else None
     elapsed_ms = e_start.elapsed_time(e_stop)
     launches = sum(m.launch_count for m in models) - launches0
+    for it in items:
+        if it.get("overlap"):
+            it["model"].exchange_flush()  # the rows of the last half-sweep (outside the timed region: once per fit)
     # ---- the state that was just timed must be exact bookkeeping (every model, device-side recount of z) ----
     # whole models: recount locally.  split models: the (region, topic) histograms of the parts are summed over the
     # ranks and every part's replica of n_wk must equal the sum; replicas must hash identically.
@@ -969,7 +998,7 @@ def run_cuda(args):
         stage_ms.clear()
         torch.cuda.synchronize()
         barrier()
-        n_e2e = max(1, min(args.steps, 3))
+        n_e2e = max(1, min(args.steps, 2))
         t0 = time.perf_counter()
         for _ in range(n_e2e):
             e2e_step()
@@ -1067,10 +1096,14 @@ def run_cuda(args):
             "dtype": "int32 counts, fp32 conditional, u16 topics", "data": "synthetic",
             "config": {"workload": workload_text(D, W, N),
                        "n_topics": N_TOPICS, "tokens": N, "cells": D, "regions": W,
-                       "sharding": ("GPUs filled to a common level with measured sweep times; a model that does not fit "
-                                    "continues on the next GPU (cells sharded, one fused exchange kernel per sweep)"
-                                    if costs is not None else
-                                    "one model per GPU, longest first" if world > 1 else "all models on one GPU"),
+                       "sharding": {"whole": "whole models, longest first with measured sweep times + local search"
+                                             if costs is not None else ("one model per GPU, longest first" if world > 1
+                                                                        else "all models on one GPU"),
+                                    "paired": "whole models, except that the longest are split between two GPUs that run "
+                                              "their parts at the same time, exchange inside the sampling launches",
+                                    "wrap": "GPUs filled to a common level; a model that does not fit continues on the next "
+                                            "GPU (cells sharded, one fused exchange kernel per sweep)"}[plan_kind],
+                       "plan_kind": plan_kind,
                        "plan": {str(r): [[N_TOPICS[i], round(f0, 3), round(f1, 3)] for (i, f0, f1) in plan[r]]
                                 for r in range(world)},
                        "measured_sweep_ms": None if costs is None else {str(K): round(c, 4) for K, c in zip(N_TOPICS, costs)},
@@ -1101,10 +1134,11 @@ def main():
     ap.add_argument("--no-adlda", action="store_true")
     ap.add_argument("--no-impute", action="store_true")
     ap.add_argument("--n-topics", default="", help="debugging: comma-separated n_topics list instead of the C2 sweep")
-    ap.add_argument("--split", action="store_true",
-                    help="divisible-model schedule at more than one GPU (lda_models.schedule_models_split): measured SLOWER "
-                         "than whole models on C2 (230 vs 304 Gtok/s on 8 GPUs: short shards lose to wave quantisation and every "
-                         "split pays an exchange), so whole models, longest first, stay the default")
+    ap.add_argument("--plan", default="auto", choices=["auto", "whole", "paired", "wrap", "lpt"],
+                    help="model sweep on several GPUs: lpt = whole models, longest first by 4K+28 (round 1); whole = the same with "
+                         "measured sweep times + local search; paired = additionally split the longest models between two GPUs "
+                         "(overlapped exchange); auto = paired when predicted >= 3 %% faster than whole; wrap = wrap-around "
+                         "filling with synchronous exchanges (measured slower: 230 vs 304 Gtok/s on 8 GPUs)")
     ap.add_argument("--no-parity", action="store_true", help="skip the frozen-oracle-trace check (rank 0, ~1 min)")
     ap.add_argument("--no-c4", action="store_true", help="skip the atlas-scale AD-LDA leg (only runs at >= 8 GPUs)")
     ap.add_argument("--no-c5", action="store_true", help="skip the atlas-scale imputation leg")

@@ -179,6 +179,101 @@ def schedule_models_split(costs, n_workers, overhead=None, min_fraction=0.2):
     return best
 
 
+def schedule_models_paired(costs, n_workers, penalty=1.10, overhead=0.05, min_fraction=0.25, max_splits=None):
+    """Whole models, longest first -- except that the j longest models are split in TWO parts that run on two workers
+    at the same time (first in both workers' steps, so that their overlapped exchange meets), a worker taking at most
+    one such part.  For every j: the parts and the whole models are placed longest-first, the two fractions of every
+    split model level its two workers, and a local search (move or swap whole models between workers, re-levelling
+    after each try) lowers the makespan further; the j with the smallest predicted makespan wins (j = 0 is plain LPT
+    plus the local search).  A part costs ``penalty`` x its share of the model (a shard fills the GPU less evenly) plus
+    ``overhead``.  Returns ``(plan, makespan)`` with ``plan[w]`` = ordered ``(model, f0, f1)`` items, split part first.
+    Deterministic."""
+    n = len(costs)
+    order = sorted(range(n), key=lambda i: (-costs[i], i))
+    max_splits = min(n, n_workers // 2) if max_splits is None else min(max_splits, n, n_workers // 2)
+
+    def evaluate(whole, pairs):
+        """whole[w] = list of whole models on w, pairs = {model: (wa, wb)} -> (loads, fractions)."""
+        loads = [sum(costs[i] for i in whole[w]) for w in range(n_workers)]
+        fractions = {}
+        for i, (wa, wb) in pairs.items():
+            c = costs[i] * penalty
+            f = min(1.0 - min_fraction, max(min_fraction, (loads[wb] - loads[wa] + c) / (2.0 * c)))
+            loads[wa] += f * c + overhead
+            loads[wb] += (1.0 - f) * c + overhead
+            fractions[i] = f
+        return loads, fractions
+
+    def score(loads):
+        return (round(max(loads), 9), round(sum(x * x for x in loads), 9))
+
+    best = None
+    for j in range(0, max_splits + 1):
+        split = order[:j]
+        items = []
+        for i in order:
+            if i in split:
+                half = 0.5 * costs[i] * penalty + overhead
+                items += [(half, i, 0), (half, i, 1)]
+            else:
+                items.append((costs[i], i, None))
+        items.sort(key=lambda t: (-t[0], t[1], t[2] if t[2] is not None else -1))
+        loads = [0.0] * n_workers
+        part_on = {}
+        place = {}
+        whole = [[] for _ in range(n_workers)]
+        ok = True
+        for c, i, part in items:
+            cands = [w for w in range(n_workers) if part is None or (w not in part_on and place.get((i, 1 - part)) != w)]
+            if not cands:
+                ok = False
+                break
+            w = min(cands, key=lambda w: (loads[w], w))
+            loads[w] += c
+            if part is not None:
+                part_on[w] = i
+                place[(i, part)] = w
+            else:
+                whole[w].append(i)
+        if not ok:
+            continue
+        pairs = {i: (place[(i, 0)], place[(i, 1)]) for i in split}
+        loads, fractions = evaluate(whole, pairs)
+        def one_better(whole, loads):
+            """First move / swap of whole models between two workers that lowers (makespan, sum of squares)."""
+            cur = score(loads)
+            for a in range(n_workers):
+                for b in range(n_workers):
+                    if a == b:
+                        continue
+                    trials = [([x], []) for x in whole[a]] + [([x], [y]) for x in whole[a] for y in whole[b] if a < b]
+                    for out_a, out_b in trials:
+                        cand = [list(w) for w in whole]
+                        for x in out_a:
+                            cand[a].remove(x)
+                            cand[b].append(x)
+                        for y in out_b:
+                            cand[b].remove(y)
+                            cand[a].append(y)
+                        l2, f2 = evaluate(cand, pairs)
+                        if score(l2) < cur:
+                            return cand, l2, f2
+            return None
+
+        for _ in range(200):  # local search
+            nxt = one_better(whole, loads)
+            if nxt is None:
+                break
+            whole, loads, fractions = nxt
+        plan = [[(i, 0.0, 1.0) for i in sorted(whole[w], key=lambda i: (-costs[i], i))] for w in range(n_workers)]
+        for i, (wa, wb) in pairs.items():
+            plan[wa].insert(0, (i, 0.0, fractions[i]))
+            plan[wb].insert(0, (i, fractions[i], 1.0))
+        if best is None or max(loads) < best[1] - 1e-9:
+            best = (plan, max(loads))
+    return best
+
+
 def run_cgs_models(
     cistopic_obj,
     n_topics,
@@ -212,7 +307,9 @@ def run_cgs_models(
     binary_matrix = cistopic_obj.binary_matrix  # regions x cells; transposed on the device
     canonical = Corpus.canonical_csr(binary_matrix)  # validated once, shared by every device's corpus build
     devices = devices[: max(1, min(len(devices), len(n_topics)))]
-    plan = schedule_models(list(n_topics), len(devices))
+    # whole models, longest first by the measured cost model, improved by moves / swaps between GPUs
+    plan = [[i for (i, _, _) in p]
+            for p in schedule_models_paired([sweep_cost(k) for k in n_topics], len(devices), max_splits=0)[0]]
     results = [None] * len(n_topics)
     errors = []
 

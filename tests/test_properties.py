@@ -111,6 +111,38 @@ def test_split_schedule_partitions_every_model(costs, workers, ov):
     assert level <= max(loads) * (1 + 1e-6) + ov + 1e-9
 
 
+@settings(max_examples=60, **COMMON)
+@given(costs=st.lists(st.floats(0.2, 5.0), min_size=1, max_size=12), workers=st.integers(1, 10))
+def test_paired_schedule_properties(costs, workers):
+    """schedule_models_paired: every model is placed exactly once (whole, or as two parts that tile [0, 1) on two
+    different workers), a worker holds at most one part and holds it FIRST, no part is below the minimum fraction, and
+    the predicted makespan is never worse than plain longest-first placement of whole models."""
+    plan, makespan = lda_models.schedule_models_paired(costs, workers)
+    assert len(plan) == workers
+    seen = {}
+    for w, items in enumerate(plan):
+        parts_here = [(i, f0, f1) for (i, f0, f1) in items if not (f0 == 0.0 and f1 == 1.0)]
+        assert len(parts_here) <= 1
+        if parts_here:
+            assert items[0] == parts_here[0] and parts_here[0][2] - parts_here[0][1] >= 0.25 - 1e-9
+        for (i, f0, f1) in items:
+            seen.setdefault(i, []).append((f0, f1, w))
+    assert sorted(seen) == list(range(len(costs)))
+    for i, parts in seen.items():
+        parts.sort()
+        if len(parts) == 1:
+            assert parts[0][:2] == (0.0, 1.0)
+        else:
+            assert len(parts) == 2 and parts[0][0] == 0.0 and parts[1][1] == 1.0 and parts[0][1] == parts[1][0]
+            assert parts[0][2] != parts[1][2]
+    order = sorted(range(len(costs)), key=lambda i: (-costs[i], i))
+    loads = [0.0] * workers
+    for i in order:
+        j = min(range(workers), key=lambda j: (loads[j], j))
+        loads[j] += costs[i]
+    assert makespan <= max(loads) + 1e-9
+
+
 # ---- GPU: the same invariants through the C ABI --------------------------------------------------------
 @pytest.mark.gpu
 @settings(max_examples=25, **COMMON)
