@@ -683,6 +683,46 @@ def run_cuda(args):
     dev = torch.device("cuda", local_rank)
     _lib.require_device()
 
+    # ---- preflight: can the ranks map each other's device memory (CUDA IPC)?  The fused / overlapped exchanges and the
+    # paired plan need it; without it the bench falls back to whole models and the NCCL exchange instead of failing.
+    args.ipc_ok = True
+    if world > 1:
+        ok, raw, why = 1, b"", ""
+        try:
+            probe = ctypes.c_void_p()
+            _lib.check(_lib.load().cgs_device_malloc(local_rank, 1 << 20, ctypes.byref(probe)))
+            buf = ctypes.create_string_buffer(64)
+            _lib.check(_lib.load().cgs_ipc_export(probe, buf))
+            raw = buf.raw
+        except Exception as e:  # noqa: BLE001
+            ok, why = 0, str(e)
+        handles = [None] * world
+        dist.all_gather_object(handles, raw)  # every rank takes part, whatever happened above
+        if ok and all(len(h) == 64 for h in handles):
+            try:
+                peer = ctypes.c_void_p()
+                _lib.check(_lib.load().cgs_ipc_open(local_rank, ctypes.create_string_buffer(handles[(rank + 1) % world], 64),
+                                                    ctypes.byref(peer)))
+                torch.cuda.synchronize()
+                _lib.check(_lib.load().cgs_ipc_close(local_rank, peer))
+            except Exception as e:  # noqa: BLE001
+                ok, why = 0, str(e)
+        else:
+            ok = 0
+        if not ok:
+            print(f"[bench] rank {rank}: CUDA IPC preflight failed ({why}); NCCL exchange and whole models only", file=sys.stderr)
+        t = torch.tensor([ok], device=dev, dtype=torch.int32)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)  # (also: every rank is done with its neighbour's probe)
+        args.ipc_ok = bool(t.item())
+        try:
+            _lib.load().cgs_device_free(local_rank, probe)
+        except Exception:  # noqa: BLE001
+            pass
+        if not args.ipc_ok:
+            args.plan = "whole" if args.plan in ("auto", "paired", "wrap") else args.plan
+            if not args.adlda_modes:
+                args.adlda_modes = "nccl"
+
     if args.adlda_only:
         adlda = run_adlda_leg(args, dev, rank, world, local_rank)
         if rank == 0:
@@ -746,7 +786,8 @@ def run_cuda(args):
             plan_kind = "wrap"
         elif args.plan in ("auto", "paired"):
             # ... and with the longest models split between two GPUs that run them at the same time (overlapped exchange)
-            paired, level_p = schedule_models_paired(costs, world)
+            paired, level_p = schedule_models_paired(costs, world, penalty=args.split_penalty, equal_parts=args.equal_parts,
+                                                     max_splits=args.max_splits if args.max_splits >= 0 else None)
             if args.plan == "paired" or level_p < 0.97 * level:
                 plan, level, plan_kind = paired, level_p, "paired"
             if all(f0 <= 0.0 and f1 >= 1.0 for p in plan for (_, f0, f1) in p):
@@ -1139,6 +1180,9 @@ def main():
                          "measured sweep times + local search; paired = additionally split the longest models between two GPUs "
                          "(overlapped exchange); auto = paired when predicted >= 3 %% faster than whole; wrap = wrap-around "
                          "filling with synchronous exchanges (measured slower: 230 vs 304 Gtok/s on 8 GPUs)")
+    ap.add_argument("--split-penalty", type=float, default=1.10)
+    ap.add_argument("--equal-parts", action="store_true")
+    ap.add_argument("--max-splits", type=int, default=-1)
     ap.add_argument("--no-parity", action="store_true", help="skip the frozen-oracle-trace check (rank 0, ~1 min)")
     ap.add_argument("--no-c4", action="store_true", help="skip the atlas-scale AD-LDA leg (only runs at >= 8 GPUs)")
     ap.add_argument("--no-c5", action="store_true", help="skip the atlas-scale imputation leg")

@@ -272,6 +272,10 @@ int cgs_model_exchange_status(cgs_model *m, int32_t *timeouts);
 int cgs_ipc_export(void *device_ptr, void *handle_out_64_bytes);
 int cgs_ipc_open(int device, const void *handle_64_bytes, void **device_ptr);
 int cgs_ipc_close(int device, void *device_ptr);
+/* Plain cudaMalloc / cudaFree on `device`: IPC-exportable scratch for a host that wants to probe whether its ranks can map
+ * each other's memory before it commits to the peer-memory exchanges. */
+int cgs_device_malloc(int device, size_t bytes, void **device_ptr);
+int cgs_device_free(int device, void *device_ptr);
 
 /* ---- imputation (replaces the fp32 chunk product of diff_features.py:443-464) --------- */
 /* out[r, c] = trunc_int32( (sum_k topic_region[r, k] * cell_topic[k, c]) * scale ) when

@@ -99,6 +99,8 @@ SIGNATURES = {
     "cgs_ipc_export": (ctypes.c_int, [c_vp, c_vp]),
     "cgs_ipc_open": (ctypes.c_int, [ctypes.c_int, c_vp, ctypes.POINTER(c_vp)]),
     "cgs_ipc_close": (ctypes.c_int, [ctypes.c_int, c_vp]),
+    "cgs_device_malloc": (ctypes.c_int, [ctypes.c_int, ctypes.c_size_t, ctypes.POINTER(c_vp)]),
+    "cgs_device_free": (ctypes.c_int, [ctypes.c_int, c_vp]),
     "cgs_impute_chunk": (ctypes.c_int, [ctypes.c_int, c_f32p, c_f32p, ctypes.c_int32, ctypes.c_int32,
                                         ctypes.c_int32, ctypes.c_float, ctypes.c_int, c_vp, c_u8p]),
     "cgs_impute_chunk_device": (ctypes.c_int, [ctypes.c_int, c_vp, c_vp, ctypes.c_int32, ctypes.c_int32,

@@ -1338,6 +1338,22 @@ int cgs_ipc_open(int device, const void *handle_64_bytes, void **device_ptr) {
     return 0;
 }
 
+int cgs_device_malloc(int device, size_t bytes, void **device_ptr) {
+    if (!device_ptr || bytes == 0) CGS_FAIL("bad argument");
+    DeviceGuard g(device);
+    if (!g.ok) CGS_FAIL("cannot select CUDA device");
+    CGS_CUDA(cudaMalloc(device_ptr, bytes));
+    return 0;
+}
+
+int cgs_device_free(int device, void *device_ptr) {
+    if (!device_ptr) return 0;
+    DeviceGuard g(device);
+    if (!g.ok) CGS_FAIL("cannot select CUDA device");
+    CGS_CUDA(cudaFree(device_ptr));
+    return 0;
+}
+
 int cgs_ipc_close(int device, void *device_ptr) {
     if (!device_ptr) return 0;
     DeviceGuard g(device);

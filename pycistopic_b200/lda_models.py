@@ -179,7 +179,8 @@ def schedule_models_split(costs, n_workers, overhead=None, min_fraction=0.2):
     return best
 
 
-def schedule_models_paired(costs, n_workers, penalty=1.10, overhead=0.05, min_fraction=0.25, max_splits=None):
+def schedule_models_paired(costs, n_workers, penalty=1.10, overhead=0.05, min_fraction=0.25, max_splits=None,
+                           equal_parts=False):
     """Whole models, longest first -- except that the j longest models are split in TWO parts that run on two workers
     at the same time (first in both workers' steps, so that their overlapped exchange meets), a worker taking at most
     one such part.  For every j: the parts and the whole models are placed longest-first, the two fractions of every
@@ -199,6 +200,8 @@ def schedule_models_paired(costs, n_workers, penalty=1.10, overhead=0.05, min_fr
         for i, (wa, wb) in pairs.items():
             c = costs[i] * penalty
             f = min(1.0 - min_fraction, max(min_fraction, (loads[wb] - loads[wa] + c) / (2.0 * c)))
+            if equal_parts:
+                f = 0.5  # the two parts then take the same time, so the partners' fused launches meet without waiting
             loads[wa] += f * c + overhead
             loads[wb] += (1.0 - f) * c + overhead
             fractions[i] = f
