@@ -453,6 +453,95 @@ __device__ __forceinline__ void impute_epi_chunk(uint32_t (&v)[16], uint32_t rel
     }
 }
 
+// STORE = 5 ("wide"): the same epilogue in 32 x 32 blocks.  tcgen05.ld.32x32b.x32 leaves every lane 32 consecutive
+// columns of its row -- a full 128-byte line -- so after the staging tile (32 rows x 128 bytes, 16-byte pieces
+// XOR-swizzled by the row, conflict-free both ways) a warp instruction stores FOUR complete lines where the 32 x 16
+// blocks store eight half lines: half the wavefronts through the L1 / LSU data path per byte written, which is the unit
+// round 1's ncu showed busiest in this epilogue (77 % at K = 8).  One 4 KB staging tile per warp; the TMEM load of
+// block i + 1 is in flight while block i is converted and stored.
+template <bool AS_INT>
+__device__ __forceinline__ void impute_epi_chunk_wide(uint32_t (&v)[32], uint32_t reload_taddr, float scale, bool &any,
+                                                      uint32_t buf, int lane, int col0, int row0, int R, int C, void *out) {
+    using namespace imp;
+    if (AS_INT) {
+        uint32_t maxbits = 0, orbits = 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const float y = __uint_as_float(v[j]) * scale;
+            maxbits = max(maxbits, __float_as_uint(y));
+            const uint32_t iv = __float_as_uint(__fadd_rz(y, 8388608.0f)) - 0x4B000000u;
+            orbits |= iv;
+            v[j] = iv;
+        }
+        if (__any_sync(0xffffffffu, maxbits >= 0x4B000000u)) {  // negative, huge or NaN somewhere: the exact conversion
+            tmem_ld_32x32(reload_taddr, v);
+            orbits = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const uint32_t iv = (uint32_t)__float2int_rz(__uint_as_float(v[j]) * scale);
+                orbits |= iv;
+                v[j] = iv;
+            }
+        }
+        any |= (orbits != 0);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const float x = __uint_as_float(v[j]);
+            const float fv = (scale != 1.0f) ? x * scale : x;
+            any |= (fv != 0.0f);
+            v[j] = __float_as_uint(fv);
+        }
+    }
+    __syncwarp();  // the previous block's reads of the staging tile are done
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const uint32_t addr = buf + (uint32_t)lane * 128u + (uint32_t)((c ^ (lane & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[4 * c]), "r"(v[4 * c + 1]),
+                     "r"(v[4 * c + 2]), "r"(v[4 * c + 3])
+                     : "memory");
+    }
+    __syncwarp();
+    const int piece = lane & 7;
+    const int col = col0 + piece * 4;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = i * 4 + (lane >> 3);
+        const int row = row0 + r;
+        uint4 o;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(o.x), "=r"(o.y), "=r"(o.z), "=r"(o.w)
+                     : "r"(buf + (uint32_t)r * 128u + (uint32_t)((piece ^ (r & 7)) << 4)));
+        if (row < R && col < C)  // C % 4 == 0: a 16-byte piece is inside the row or outside
+            *reinterpret_cast<uint4 *>(reinterpret_cast<uint32_t *>(out) + (int64_t)row * C + col) = o;
+    }
+}
+
+template <bool AS_INT>
+__device__ __forceinline__ void impute_epi_tile_wide(uint32_t taddr0, int n_blocks16, float scale, bool &any,
+                                                     uint32_t stage_buf, int lane, int col0, int row0, int R, int C,
+                                                     void *out) {
+    using namespace imp;
+    const int n_blocks = (n_blocks16 + 1) >> 1;  // 32-column blocks (columns past C are masked piece by piece)
+    uint32_t va[32], vb[32];
+    if (n_blocks > 0) tmem_ld_32x32_issue(taddr0, va);
+#pragma unroll
+    for (int ch = 0; ch < BN / 64; ++ch) {
+        if (ch < n_blocks) {  // warp-uniform
+            tmem_ld_wait();
+            if (ch & 1) {
+                if (ch + 1 < n_blocks) tmem_ld_32x32_issue(taddr0 + (uint32_t)(ch + 1) * 32u, va);
+                impute_epi_chunk_wide<AS_INT>(vb, taddr0 + (uint32_t)ch * 32u, scale, any, stage_buf, lane, col0 + ch * 32,
+                                              row0, R, C, out);
+            } else {
+                if (ch + 1 < n_blocks) tmem_ld_32x32_issue(taddr0 + (uint32_t)(ch + 1) * 32u, vb);
+                impute_epi_chunk_wide<AS_INT>(va, taddr0 + (uint32_t)ch * 32u, scale, any, stage_buf, lane, col0 + ch * 32,
+                                              row0, R, C, out);
+            }
+        }
+    }
+}
+
 // The 32 rows x 128 columns an epilogue warp owns in a tile: eight 32 x 16 blocks.  The TMEM load of block
 // i + 1 is in flight while block i is converted, and the two staging tiles alternate so that a TMA store
 // reads one while the next block is written into the other.
@@ -463,6 +552,10 @@ __device__ __forceinline__ void impute_epi_tile(uint32_t taddr0, int n_blocks, f
                                                 int lane, const CUtensorMap *tm_out, int col0, int row0, int R, int C,
                                                 void *out) {
     using namespace imp;
+    if constexpr (STORE == 5) {
+        impute_epi_tile_wide<AS_INT>(taddr0, n_blocks, scale, any, stage_buf, lane, col0, row0, R, C, out);
+        return;
+    }
     uint32_t va[16], vb[16];
     if (n_blocks > 0) tmem_ld_32x16_issue(taddr0, va);
 #pragma unroll
@@ -908,6 +1001,7 @@ static int impute_umma_launch(const float *d_a_hi, const float *d_a_lo, const fl
         else if (aligned && v == "tma") store = 1;
         else if (aligned && v == "vec") store = 2;
         else if (aligned && v == "mix") store = 3;
+        else if (aligned && v == "wide") store = 5;
     }
     if (store == 1 || store == 3) CGS_TRY(make_output_map(&mo, d_out, R, C));
     else mo = ma_hi;  // unused
@@ -932,6 +1026,7 @@ static int impute_umma_launch(const float *d_a_hi, const float *d_a_lo, const fl
             case 0: return CGS_IMPUTE_DISPATCH(true, 0);
             case 1: return CGS_IMPUTE_DISPATCH(true, 1);
             case 2: return CGS_IMPUTE_DISPATCH(true, 2);
+            case 5: return CGS_IMPUTE_DISPATCH(true, 5);
             default: return CGS_IMPUTE_DISPATCH(true, 3);
         }
     }
@@ -939,6 +1034,7 @@ static int impute_umma_launch(const float *d_a_hi, const float *d_a_lo, const fl
         case 0: return CGS_IMPUTE_DISPATCH(false, 0);
         case 1: return CGS_IMPUTE_DISPATCH(false, 1);
         case 2: return CGS_IMPUTE_DISPATCH(false, 2);
+        case 5: return CGS_IMPUTE_DISPATCH(false, 5);
         default: return CGS_IMPUTE_DISPATCH(false, 3);
     }
 #undef CGS_IMPUTE_DISPATCH
