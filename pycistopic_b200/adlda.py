@@ -7,9 +7,9 @@ of a sweep) the ranks exchange their ``n_wk`` deltas:
 
 * ``exchange="nccl"``: ``delta = n_wk - snapshot`` (kernel) -> ``all_reduce(delta)`` (NCCL over
   NVLink) -> ``n_wk = snapshot + delta; snapshot = n_wk; n_k = colsum`` (one kernel);
-* ``exchange="auto"`` (default): the peer kernel on 2 ranks, NCCL from 3 ranks up (measured on B200,
-  120 MB of deltas: 2 ranks 0.28 ms peer vs 0.41 ms NCCL; 8 ranks 1.44 ms peer vs 0.52 ms NCCL, where
-  the NVSwitch reduces in the network).
+* ``exchange="auto"`` (default): ``"overlap"`` (``"fused"`` when ``sync_per_sweep > 1``) -- measured on 8 B200s,
+  C3 / K = 60 (128 MB table): 0.02 ms of the exchange exposed per sweep against 0.48 (fused), 0.55 (NCCL) and
+  1.44 ms (round 1's peer kernel).
 * ``exchange="peer"``: every rank maps the other ranks' delta buffers (CUDA IPC) and ONE kernel
   reads them over NVLink, reduces, applies and rebuilds ``n_k``; NCCL only provides the two
   stream-ordered barriers around it.
@@ -352,6 +352,10 @@ def fit_adlda(binary_matrix, n_topics, n_iter=150, alpha=0.1, eta=0.01, random_s
 
         def shard_factory(*a):
             return GpuShard(*a, device=device, exchange=exchange)
+    if exchange == "auto" and world > 1:
+        # the exchange inside the sampling launches when the sweep is not cut into parts, the fused kernel otherwise
+        # (both need the ranks to map each other's memory; a CPU stand-in shard falls through to the plain all-reduce)
+        exchange = "overlap" if sync_per_sweep == 1 else "fused"
     shard = shard_factory(M, (cb, ce), token_offset, n_topics, alpha, eta, random_state)
     try:
         if hasattr(shard, "set_global_size"):

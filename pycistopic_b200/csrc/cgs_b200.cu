@@ -41,6 +41,12 @@ struct DeviceGuard {
     }
 };
 
+// NVTX range for the lifetime of a scope (sweeps, exchanges, exports, log-likelihood show up by name in a timeline)
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+
 // Device buffers come from the device's stream-ordered pool (cudaMallocAsync): creating and
 // destroying models inside a topic sweep then costs microseconds instead of the device-wide
 // synchronisation of cudaMalloc / cudaFree.  `stream` is the stream that first uses the buffer
@@ -1007,7 +1013,7 @@ static int sweep_impl(cgs_model *m, int32_t n_sweeps, int32_t part, int32_t n_pa
         p.refresh_every = 0x7fffffff;  // the totals a cell works with are those of the copy
         p.n_parts = m->det_parts;
     }
-    nvtxRangePushA("cgs_model_sweep");
+    NvtxRange nvtx("cgs_model_sweep");
     for (int32_t s = 0; s < n_sweeps; ++s) {
         for (int32_t dp = 0; dp < (det ? m->det_parts : 1); ++dp) {
             if (det) {
@@ -1028,7 +1034,6 @@ static int sweep_impl(cgs_model *m, int32_t n_sweeps, int32_t part, int32_t n_pa
         }
         if (det || part == n_parts - 1) m->sweeps += 1;
     }
-    nvtxRangePop();
     return 0;
 }
 
@@ -1118,6 +1123,7 @@ int cgs_model_sweeps_done(const cgs_model *m, int64_t *count) {
 int cgs_model_loglik(cgs_model *m, int partial, double *ll) {
     if (!m || !ll) CGS_FAIL("NULL argument");
     if (partial < 0 || partial > 2) CGS_FAIL("partial must be 0, 1 or 2");
+    NvtxRange nvtx("cgs_model_loglik");
     cgs_corpus *c = m->corpus;
     DeviceGuard g(c->device);
     const int64_t W = c->n_regions, D = c->n_cells;
@@ -1151,6 +1157,7 @@ int cgs_model_loglik(cgs_model *m, int partial, double *ll) {
 // ---- exports ----------------------------------------------------------------------------------
 int cgs_model_export_counts(cgs_model *m, int32_t *nzw, int32_t *ndz, int32_t *nz) {
     if (!m) CGS_FAIL("NULL model");
+    NvtxRange nvtx("cgs_model_export_counts");
     cgs_corpus *c = m->corpus;
     DeviceGuard g(c->device);
     const int64_t W = c->n_regions, D = c->n_cells;
@@ -1184,6 +1191,7 @@ int cgs_model_export_counts(cgs_model *m, int32_t *nzw, int32_t *ndz, int32_t *n
 }
 
 static int export_dist(cgs_model *m, double *topic_side, int topic_transposed, double *cell_side, int cell_transposed) {
+    NvtxRange nvtx("cgs_model_export_distributions");
     cgs_corpus *c = m->corpus;
     const int64_t W = c->n_regions, D = c->n_cells;
     const int32_t K = m->K, Kp = m->Kp;
@@ -1555,7 +1563,7 @@ int cgs_model_exchange_round(cgs_model *m, int32_t n_ctas) {
     n_ctas = std::min(n_ctas, c->num_sms);
     ExchangeParams p;
     fill_exchange_params(m, p);
-    nvtxRangePushA("cgs_model_exchange_round");
+    NvtxRange nvtx("cgs_model_exchange_round");
     // the round starts once everything enqueued on the model's stream so far has finished, and then runs BESIDE
     // whatever the caller enqueues there next (the next sweep)
     CGS_CUDA(cudaEventRecord(m->x_event, m->stream));
@@ -1563,7 +1571,6 @@ int cgs_model_exchange_round(cgs_model *m, int32_t n_ctas) {
     exchange_round_kernel<<<n_ctas, kExchangeThreads, sizeof(int) * (size_t)m->Kp, m->x_stream>>>(p);
     CGS_CUDA(cudaGetLastError());
     CGS_CUDA(cudaEventRecord(m->x_done, m->x_stream));
-    nvtxRangePop();
     m->x_pending = true;
     m->launches += 1;
     m->x_launches += 1;
@@ -1640,10 +1647,9 @@ static int exchange_sync_rows(cgs_model *m, int32_t n_ctas, int64_t row0, int64_
     n_ctas = n_ctas <= 0 ? m->x_sync_blocks : std::min(n_ctas, m->x_sync_blocks);
     ExchangeParams p;
     fill_exchange_params(m, p, row0, row1);
-    nvtxRangePushA("cgs_model_exchange_sync");
+    NvtxRange nvtx("cgs_model_exchange_sync");
     exchange_sync_kernel<<<n_ctas, kExchangeThreads, sizeof(int) * (size_t)m->Kp, m->stream>>>(p);
     CGS_CUDA(cudaGetLastError());
-    nvtxRangePop();
     m->launches += 1;
     m->x_launches += 1;
     return 0;
@@ -1790,13 +1796,12 @@ int cgs_model_allreduce_delta(cgs_model *m, void *nccl_comm) {
     if (!m || !nccl_comm) CGS_FAIL("NULL argument");
     CGS_TRY(nccl_api());
     DeviceGuard g(m->corpus->device);
-    nvtxRangePushA("cgs_model_allreduce_delta");
+    NvtxRange nvtx("cgs_model_allreduce_delta");
     CGS_TRY(cgs_model_delta_compute(m));
     const size_t n = (size_t)m->corpus->n_regions * (size_t)m->Kp;
     // ncclInt32 = 2, ncclSum = 0 (nccl.h); in place on the delta buffer
     CGS_NCCL(g_nccl.AllReduce(m->d_delta, m->d_delta, n, 2, 0, nccl_comm, m->stream));
     CGS_TRY(cgs_model_delta_apply(m));
-    nvtxRangePop();
     return 0;
 }
 

@@ -503,6 +503,9 @@ class LDA:
             self.loglikelihoods_ = []
             done = 0
             refresh = max(1, int(self.refresh))
+            import time as _time
+            model.sync()
+            t_fit = _time.perf_counter()
             while done < self.n_iter:
                 if done % refresh == 0:
                     ll = model.loglikelihood()
@@ -514,6 +517,11 @@ class LDA:
             ll = model.loglikelihood()
             logger.info("<%d> log likelihood: %.0f", self.n_iter - 1, ll)
             self.final_loglikelihood_ = ll
+            # sampling rate of this fit (the log-likelihood evaluations included), for the "lda" logger and bench
+            dt = max(_time.perf_counter() - t_fit, 1e-9)
+            self.tokens_per_second_ = corpus.n_tokens * self.n_iter / dt
+            logger.info("%d sweeps over %d tokens in %.3f s: %.2f Gtok/s per sweep", self.n_iter, corpus.n_tokens, dt,
+                        self.tokens_per_second_ / 1e9)
             if self._exports == "all":
                 self.nzw_, self.ndz_, self.nz_ = model.counts()
                 self.components_, self.doc_topic_ = model.distributions()

@@ -294,9 +294,13 @@ def test_loglik_trace_larger_k(small):
             g = LDA(K, n_iter=60, alpha=50.0 / K, eta=0.1, random_state=s, refresh=5).fit(X)
             ot.append(o.loglikelihoods_ + [o.final_loglikelihood_])
             gt.append(g.loglikelihoods_ + [g.final_loglikelihood_])
+        # why the average: on a corpus this small ONE chain of the sequential oracle differs from another by more than
+        # the tolerance allows for (asserted, so that the averaging is shown to be needed rather than convenient)
+        oracle_spread = (np.std(ot, axis=0, ddof=1) / np.abs(np.mean(ot, axis=0))).max()
+        assert oracle_spread > 0.003, oracle_spread
         ot, gt = np.mean(ot, axis=0), np.mean(gt, axis=0)
         rel = np.abs(gt - ot) / np.abs(ot)
-        assert rel.max() < 0.01, f"K={K}: trace deviates {rel.max():.3%}"
+        assert rel.max() < 0.01, f"K={K}: trace deviates {rel.max():.3%} (oracle chain-to-chain spread {oracle_spread:.3%})"
 
 
 # ---- imputation -----------------------------------------------------------------------------------
