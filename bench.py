@@ -270,7 +270,8 @@ def run_adlda_leg(args, dev, rank, world, local_rank, shape=None):
     import torch.distributed as dist
 
     from pycistopic_b200 import Corpus
-    from pycistopic_b200.adlda import Exchanger, GpuShard, balanced_cell_partition
+    from pycistopic_b200.adlda import (Exchanger, GpuShard, balanced_cell_partition, balanced_region_blocks,
+                                       region_blocks_for_table)
     from pycistopic_b200.synth import SHAPES, planted_topic_tokens
 
     shape = shape or args.adlda_shape
@@ -319,12 +320,13 @@ def run_adlda_leg(args, dev, rank, world, local_rank, shape=None):
                          exchange=exchange, corpus=corpus)
         shard.init()
         ex = Exchanger(shard, exchange, n_ctas=args.overlap_ctas if exchange == "overlap" else 0)
+        n_region_blocks = None
         if exchange == "overlap":
             per_region = torch.bincount(tok, minlength=W).to(torch.int64)
             if world > 1:
                 dist.all_reduce(per_region)
-            split = int(torch.searchsorted(torch.cumsum(per_region, 0), torch.tensor([N_total // 2], device=dev)).item()) + 1
-            shard.set_region_split(min(split, W))
+            n_region_blocks = args.region_blocks or region_blocks_for_table(W, shard.model.padded_topics)
+            shard.set_region_blocks(balanced_region_blocks(per_region.cpu().numpy(), n_region_blocks))
             del per_region
         ex.step()
         stream = shard.stream
@@ -421,6 +423,7 @@ def run_adlda_leg(args, dev, rank, world, local_rank, shape=None):
         out[exchange] = {"tokens_per_s": N_total / (ms * 1e-3), "ms_per_sweep": ms, "ms_sampling_alone": sample_ms,
                          "ms_exchange_alone_back_to_back": alone_ms, "fused_phase_us_rank0": phases,
                          "ms_exchange_exposed": ms - sample_ms, "rounds_per_sweep": parts,
+                         "region_blocks": n_region_blocks,
                          "sweep_shape": shard.model.sweep_shape,
                          "checks": checks}
         shard.close()
@@ -1192,6 +1195,8 @@ def main():
     ap.add_argument("--adlda-rank-local-data", action="store_true",
                     help="every rank draws only its own cells (always on for C4)")
     ap.add_argument("--adlda-modes", default="", help="comma-separated exchange modes of the AD-LDA legs (default: all)")
+    ap.add_argument("--region-blocks", type=int, default=0,
+                    help="region blocks of the overlapped sweeps (0 = two, or enough for a block's rows to fit the L2)")
     ap.add_argument("--overlap-ctas", type=int, default=0, help="exchange blocks of the fused launches (0 = one per two SMs)")
     ap.add_argument("--async-parts", type=int, default=2, help="rounds (= sub-sweeps) per sweep of the async exchange")
     ap.add_argument("--adlda-only", action="store_true", help="skip the model-sweep legs (used for the C4 run)")

@@ -253,6 +253,13 @@ int cgs_model_exchange_sync(cgs_model *m, int32_t n_ctas);
  *     stay unpublished until the next call or cgs_model_exchange_flush (call it before reading counts /
  *     log-likelihoods).  Needs cgs_model_exchange_open and one cgs_model_exchange_sync after init. */
 int cgs_corpus_set_region_split(cgs_corpus *c, int32_t region_split);
+/* The general form: n_blocks region blocks, block b = regions [bounds[b], bounds[b + 1]) (bounds[0] = 0, bounds[n_blocks] =
+ * n_regions; every rank the same).  A sweep is then n_blocks launches, each over one block of every cell, and while block b
+ * is sampled the rows of block b - 1 are exchanged.  More blocks than two pay when the table does not fit the L2 (C4: 400 MB
+ * per rank): a launch then only gathers rows of its own block, which does.  cgs_model_sweep_blocked is the same block-wise
+ * sweep without any exchange (one GPU, or between stand-alone exchanges). */
+int cgs_corpus_set_region_blocks(cgs_corpus *c, int32_t n_blocks, const int32_t *bounds);
+int cgs_model_sweep_blocked(cgs_model *m, int32_t n_sweeps);
 int cgs_model_sweep_overlapped(cgs_model *m, int32_t n_sweeps, int32_t x_ctas);
 int cgs_model_exchange_flush(cgs_model *m);
 int cgs_exchange_sync_local(cgs_model *const *models, int32_t n_models, int32_t n_ctas);

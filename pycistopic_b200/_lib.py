@@ -90,6 +90,8 @@ SIGNATURES = {
     "cgs_model_exchange_wait": (ctypes.c_int, [c_vp]),
     "cgs_model_exchange_sync": (ctypes.c_int, [c_vp, ctypes.c_int32]),
     "cgs_corpus_set_region_split": (ctypes.c_int, [c_vp, ctypes.c_int32]),
+    "cgs_corpus_set_region_blocks": (ctypes.c_int, [c_vp, ctypes.c_int32, c_i32p]),
+    "cgs_model_sweep_blocked": (ctypes.c_int, [c_vp, ctypes.c_int32]),
     "cgs_model_sweep_overlapped": (ctypes.c_int, [c_vp, ctypes.c_int32, ctypes.c_int32]),
     "cgs_model_exchange_flush": (ctypes.c_int, [c_vp]),
     "cgs_model_exchange_phase_times": (ctypes.c_int, [c_vp, c_f64p]),

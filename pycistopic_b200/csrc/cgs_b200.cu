@@ -306,8 +306,10 @@ struct cgs_corpus {
     int64_t *d_cell_ptr = nullptr;    // D+1
     int32_t *d_tok_region = nullptr;  // N
     int32_t *d_cell_order = nullptr;  // D, longest cell first
-    int64_t *d_cell_mid = nullptr;    // D: first token of every cell at or above region_split (cgs_corpus_set_region_split)
-    int32_t region_split = -1;
+    // region blocks (cgs_corpus_set_region_blocks): block b = regions [block_bounds[b], block_bounds[b + 1]);
+    // d_cell_split[(b - 1) * D + d] = first token of cell d at or above block_bounds[b], b = 1 .. n_blocks - 1
+    int64_t *d_cell_split = nullptr;
+    std::vector<int32_t> block_bounds;
     bool owns_tokens = true;
     int n_models = 0;
     // Construction runs on a private non-blocking stream: pool blocks freed on one non-blocking stream are
@@ -344,7 +346,7 @@ struct cgs_model {
     int sweep_blocks = 0;
     // deterministic mode (cgs_model_set_deterministic): sweeps read copies of n_wk / n_k taken at the start of
     // each of det_parts sub-sweeps, one warp per cell
-    int sweep_half = 0, sweep_x_ctas = 0;  // set around the launches of cgs_model_sweep_overlapped
+    int sweep_block = -1, sweep_x_ctas = 0;  // set around the launches of cgs_model_sweep_overlapped / _blocked
     bool fp64 = false;  // conditional in double (A/B build, cgs_model_set_conditional_precision)
     int det_parts = 0;
     int32_t *d_nwk_ro = nullptr, *d_nk_ro = nullptr;
@@ -357,7 +359,7 @@ struct cgs_model {
     int x_sync_blocks = 0;
     int sweep_blocks_fused = 0;
     ExchangeParams x_fused;      // the exchange of the current fused launch
-    int x_pending_half = 0;      // overlapped sweeps: which half of the rows was sampled and not yet exchanged
+    int x_pending_block = -1;    // overlapped sweeps: the region block that was sampled and not yet exchanged
     cudaStream_t x_stream = nullptr;
     cudaEvent_t x_event = nullptr, x_done = nullptr;
     bool x_pending = false;
@@ -594,7 +596,7 @@ int cgs_corpus_destroy(cgs_corpus *c) {
         if (c->d_tok_region) dfree(c->d_tok_region, c->stream);
     }
     if (c->d_cell_order) dfree(c->d_cell_order, c->stream);
-    if (c->d_cell_mid) dfree(c->d_cell_mid, c->stream);
+    if (c->d_cell_split) dfree(c->d_cell_split, c->stream);
     if (c->stream) cudaStreamDestroy(c->stream);  // pending frees still run
     delete c;
     return 0;
@@ -614,17 +616,32 @@ int cgs_corpus_set_token_offset(cgs_corpus *c, int64_t off) {
     return 0;
 }
 
+int cgs_corpus_set_region_blocks(cgs_corpus *c, int32_t n_blocks, const int32_t *bounds) {
+    if (!c || !bounds) CGS_FAIL("NULL argument");
+    if (n_blocks < 1 || n_blocks > 64) CGS_FAIL("n_blocks must be in [1, 64]");
+    if (bounds[0] != 0 || bounds[n_blocks] != c->n_regions) CGS_FAIL("bounds must start at 0 and end at n_regions");
+    for (int b = 0; b < n_blocks; ++b)
+        if (bounds[b + 1] < bounds[b]) CGS_FAIL("bounds must not decrease");
+    DeviceGuard g(c->device);
+    if (c->d_cell_split) { dfree(c->d_cell_split, c->stream); c->d_cell_split = nullptr; }
+    if (n_blocks > 1) {
+        CGS_TRY(dmalloc(&c->d_cell_split, (size_t)(n_blocks - 1) * (size_t)c->n_cells, c->stream));
+        for (int b = 1; b < n_blocks; ++b) {
+            cell_split_kernel<<<(unsigned)ceil_div(c->n_cells, 256), 256, 0, c->stream>>>(
+                c->d_cell_ptr, c->d_tok_region, c->n_cells, bounds[b], c->d_cell_split + (size_t)(b - 1) * c->n_cells);
+            CGS_CUDA(cudaGetLastError());
+        }
+    }
+    CGS_CUDA(cudaStreamSynchronize(c->stream));
+    c->block_bounds.assign(bounds, bounds + n_blocks + 1);
+    return 0;
+}
+
 int cgs_corpus_set_region_split(cgs_corpus *c, int32_t region_split) {
     if (!c) CGS_FAIL("NULL corpus");
     if (region_split < 0 || region_split > c->n_regions) CGS_FAIL("region_split outside [0, n_regions]");
-    DeviceGuard g(c->device);
-    if (!c->d_cell_mid) CGS_TRY(dmalloc(&c->d_cell_mid, (size_t)c->n_cells, c->stream));
-    cell_split_kernel<<<(unsigned)ceil_div(c->n_cells, 256), 256, 0, c->stream>>>(c->d_cell_ptr, c->d_tok_region, c->n_cells,
-                                                                                 region_split, c->d_cell_mid);
-    CGS_CUDA(cudaGetLastError());
-    CGS_CUDA(cudaStreamSynchronize(c->stream));
-    c->region_split = region_split;
-    return 0;
+    const int32_t bounds[3] = {0, region_split, c->n_regions};
+    return cgs_corpus_set_region_blocks(c, 2, bounds);
 }
 
 int cgs_corpus_set_global_size(cgs_corpus *c, int64_t n_cells_global, int64_t n_tokens_global) {
@@ -825,7 +842,7 @@ int cgs_model_init(cgs_model *m) {
     CGS_CUDA(cudaGetLastError());
     m->launches += 1;
     m->sweeps = 0;
-    m->x_pending_half = 0;
+    m->x_pending_block = -1;
     return rebuild_counts(m);
 }
 
@@ -996,8 +1013,13 @@ static int sweep_impl(cgs_model *m, int32_t n_sweeps, int32_t part, int32_t n_pa
     p.part = part;
     p.n_parts = n_parts;
     p.visit_counter = m->d_visits;
-    p.cell_mid = c->d_cell_mid;
-    p.half = m->sweep_half;
+    p.cell_lo = c->d_cell_ptr;
+    p.cell_hi = c->d_cell_ptr + 1;
+    if (m->sweep_block >= 0) {  // one region block of every cell
+        const int nb = (int)c->block_bounds.size() - 1, b = m->sweep_block;
+        if (b > 0) p.cell_lo = c->d_cell_split + (size_t)(b - 1) * c->n_cells;
+        if (b < nb - 1) p.cell_hi = c->d_cell_split + (size_t)b * c->n_cells;
+    }
     p.x_ctas = m->sweep_x_ctas;
     const bool det = m->det_parts > 0;
     const size_t WKp = (size_t)c->n_regions * (size_t)m->Kp;
@@ -1581,17 +1603,61 @@ static int exchange_sync_rows(cgs_model *m, int32_t n_ctas, int64_t row0, int64_
 
 int cgs_model_exchange_sync(cgs_model *m, int32_t n_ctas) {
     if (!m) CGS_FAIL("NULL model");
-    if (m->x_pending_half) CGS_FAIL("overlapped sweeps are pending: call cgs_model_exchange_flush");
+    if (m->x_pending_block >= 0) CGS_FAIL("overlapped sweeps are pending: call cgs_model_exchange_flush");
     return exchange_sync_rows(m, n_ctas, 0, -1);
 }
 
 int cgs_model_exchange_flush(cgs_model *m) {
     if (!m) CGS_FAIL("NULL model");
-    if (!m->x_pending_half) return 0;
-    const int64_t split = m->corpus->region_split;
-    const int rc = m->x_pending_half == 1 ? exchange_sync_rows(m, 0, 0, split) : exchange_sync_rows(m, 0, split, -1);
-    if (rc == 0) m->x_pending_half = 0;
+    if (m->x_pending_block < 0) return 0;
+    const std::vector<int32_t> &bb = m->corpus->block_bounds;
+    const int rc = exchange_sync_rows(m, 0, bb[(size_t)m->x_pending_block], bb[(size_t)m->x_pending_block + 1]);
+    if (rc == 0) m->x_pending_block = -1;
     return rc;
+}
+
+// One sweep = one launch per region block.  exchange: while block b is sampled, the rows of the block sampled by the
+// previous launch are exchanged inside the same launch.
+static int sweep_region_blocks(cgs_model *m, int32_t n_sweeps, bool exchange, int32_t x_ctas) {
+    cgs_corpus *c = m->corpus;
+    const int nb = (int)c->block_bounds.size() - 1;
+    if (nb < 1) CGS_FAIL("cgs_corpus_set_region_blocks / _split has not been called");
+    if (m->det_parts > 0) CGS_FAIL("region-blocked sweeps are not available in deterministic mode");
+    if (exchange && m->fp64) CGS_FAIL("overlapped sweeps need the fp32 conditional");
+    DeviceGuard g(c->device);
+    int rc = 0;
+    for (int32_t s = 0; s < n_sweeps && rc == 0; ++s) {
+        for (int b = 0; b < nb && rc == 0; ++b) {
+            const bool fused = exchange && m->x_pending_block >= 0;
+            if (fused) {
+                const int pb = m->x_pending_block;
+                if (pb == b && nb > 1) { rc = fail(__FILE__, __LINE__, "overlapped sweep out of step"); break; }
+                if (pb == b) {  // a single block: nothing can overlap, exchange first
+                    rc = cgs_model_exchange_flush(m);
+                    if (rc != 0) break;
+                } else {
+                    fill_exchange_params(m, m->x_fused, c->block_bounds[(size_t)pb], c->block_bounds[(size_t)pb + 1]);
+                    m->x_launches += 1;
+                }
+            }
+            m->sweep_block = b;
+            m->sweep_x_ctas = (fused && m->x_pending_block >= 0) ? x_ctas : 0;
+            const int64_t before = m->sweeps;
+            rc = sweep_impl(m, 1, 0, 1);
+            m->sweeps = before;  // the blocks of one sweep share the Philox sweep index
+            m->sweep_block = -1;
+            m->sweep_x_ctas = 0;
+            if (exchange) m->x_pending_block = b;
+        }
+        if (rc == 0) m->sweeps += 1;
+    }
+    return rc;
+}
+
+int cgs_model_sweep_blocked(cgs_model *m, int32_t n_sweeps) {
+    if (!m) CGS_FAIL("NULL model");
+    if (n_sweeps < 0) CGS_FAIL("n_sweeps < 0");
+    return sweep_region_blocks(m, n_sweeps, false, 0);
 }
 
 int cgs_model_sweep_overlapped(cgs_model *m, int32_t n_sweeps, int32_t x_ctas) {
@@ -1599,38 +1665,12 @@ int cgs_model_sweep_overlapped(cgs_model *m, int32_t n_sweeps, int32_t x_ctas) {
     if (n_sweeps < 0) CGS_FAIL("n_sweeps < 0");
     if (m->x_ranks < 1) CGS_FAIL("cgs_model_exchange_open has not been called");
     cgs_corpus *c = m->corpus;
-    if (c->region_split < 0 || !c->d_cell_mid) CGS_FAIL("cgs_corpus_set_region_split has not been called");
-    if (m->det_parts > 0 || m->fp64) CGS_FAIL("overlapped sweeps need the default fp32 schedule");
-    DeviceGuard g(c->device);
     // measured on 8 ranks (C3, K = 60, 128 MB table; profiles/r2_adlda_c3_n8_overlap.txt): 74 exchange blocks leave 0.02 ms
     // of the exchange exposed, 148 leave 0.10 ms, 296 leave 0.25 ms -- the blocks only have to finish before the
-    // half-sweep does, and every one of them takes a sampling block's place
+    // block sweep does, and every one of them takes a sampling block's place
     if (x_ctas <= 0) x_ctas = std::max(1, c->num_sms / 2);
     x_ctas = std::min(x_ctas, 4 * c->num_sms);
-    const int64_t split = c->region_split, W = c->n_regions;
-    int rc = 0;
-    for (int32_t s = 0; s < n_sweeps && rc == 0; ++s) {
-        for (int half = 1; half <= 2 && rc == 0; ++half) {
-            // while this half is sampled, the rows of the other half -- sampled by the previous launch -- are exchanged
-            const bool exchange = m->x_pending_half != 0;
-            if (exchange) {
-                if (m->x_pending_half == half) { rc = fail(__FILE__, __LINE__, "overlapped sweep out of step"); break; }
-                if (m->x_pending_half == 1) fill_exchange_params(m, m->x_fused, 0, split);
-                else fill_exchange_params(m, m->x_fused, split, W);
-                m->x_launches += 1;
-            }
-            m->sweep_half = half;
-            m->sweep_x_ctas = exchange ? x_ctas : 0;
-            const int64_t before = m->sweeps;
-            rc = sweep_impl(m, 1, 0, 1);
-            m->sweeps = before;  // two half-sweeps are one sweep (same Philox sweep index)
-            m->sweep_half = 0;
-            m->sweep_x_ctas = 0;
-            m->x_pending_half = half;
-        }
-        if (rc == 0) m->sweeps += 1;
-    }
-    return rc;
+    return sweep_region_blocks(m, n_sweeps, true, x_ctas);
 }
 
 static int exchange_sync_rows(cgs_model *m, int32_t n_ctas, int64_t row0, int64_t row1) {

@@ -48,8 +48,8 @@ struct SweepParams {
     int32_t *n_k;
     const int32_t *n_k_read;     // same for the topic totals
     const int32_t *cell_order;
-    const int64_t *cell_mid;     // per cell: index of its first token whose region is >= the corpus' region split
-    int32_t half;                // 0 = whole cells; 1 = only tokens below the region split; 2 = only those at or above it
+    const int64_t *cell_lo;      // per cell: first and one-past-last token this launch samples -- cell_ptr and
+    const int64_t *cell_hi;      // cell_ptr + 1 for whole cells, or the bounds of one REGION BLOCK of every cell
     int32_t x_ctas;              // fused launches: blocks [0, x_ctas) run the n_wk exchange, the rest sample
     int32_t *work_counter;
     int32_t n_cells;
@@ -341,9 +341,9 @@ template <int CH, typename R = float, bool XCH = false> struct SweepBounds {
 };
 
 // XCH = true: the launch that overlaps the AD-LDA exchange with sampling.  Tokens are sorted by region inside a cell, so
-// a sweep can be cut at a region index w* into two half-sweeps -- first every cell's tokens below w*, then the rest --
-// and while one half is sampled, the rows of n_wk that belong to the OTHER half (changed by the previous half-sweep,
-// untouched by this one) are exchanged between the ranks: blocks [0, x_ctas) of the grid run the synchronous exchange
+// a sweep can be cut at region indices into B region-block sweeps -- first every cell's tokens of block 0, then of block
+// 1, ... -- and while one block is sampled, the rows of n_wk that belong to the PREVIOUS block (just changed, untouched by
+// this launch) are exchanged between the ranks: blocks [0, x_ctas) of the grid run the synchronous exchange
 // on that row range (exchange_sync_body: delta, reduce-scatter + all-gather over the peers' arenas, apply), all other
 // blocks sample.  One launch does both, so the exchange blocks are resident from the first cycle (they come first in
 // the grid) and the NVLink round trips, the cross-rank barriers and the table passes hide behind the sampling.  Every
@@ -391,9 +391,7 @@ sweep_kernel(const SweepParams p, const ExchangeParams xp) {
         const int slot = lds_i(s_slot) * p.n_parts + p.part;
         if (slot >= p.n_cells) break;
         const int cell = p.cell_order[slot];
-        int64_t t0 = p.cell_ptr[cell], t1 = p.cell_ptr[cell + 1];
-        if (p.half == 1) t1 = p.cell_mid[cell];
-        else if (p.half == 2) t0 = p.cell_mid[cell];
+        const int64_t t0 = p.cell_lo[cell], t1 = p.cell_hi[cell];
         int32_t *ndk_row = p.n_dk + (int64_t)cell * Kp;
 
         for (int k = tid; k < KS; k += blockDim.x) {
@@ -687,6 +685,7 @@ sweep_kernel(const SweepParams p, const ExchangeParams xp) {
 // cell_mid[d] = index of the first token of cell d whose region is >= region_split (tokens are sorted by region)
 __global__ void cell_split_kernel(const int64_t *__restrict__ cell_ptr, const int32_t *__restrict__ tok_region,
                                   int32_t n_cells, int32_t region_split, int64_t *__restrict__ cell_mid) {
+    // (one launch per block boundary of cgs_corpus_set_region_blocks)
     const int32_t d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= n_cells) return;
     int64_t lo = cell_ptr[d], hi = cell_ptr[d + 1];

@@ -111,6 +111,12 @@ class Corpus:
         """Region index that cuts a sweep into two half-sweeps (overlapped AD-LDA exchange)."""
         check(_lib.load().cgs_corpus_set_region_split(self._h, int(region_split)))
 
+    def set_region_blocks(self, bounds):
+        """Region blocks [bounds[b], bounds[b + 1]) that cut a sweep into one launch per block (bounds[0] = 0,
+        bounds[-1] = n_regions)."""
+        b = np.ascontiguousarray(bounds, dtype=np.int32)
+        check(_lib.load().cgs_corpus_set_region_blocks(self._h, len(b) - 1, ptr(b, c_i32p)))
+
     def token_lists(self):
         """(WS, DS) exactly as ``lda.utils.matrix_to_lists`` returns them."""
         WS = np.empty(self.n_tokens, np.int32)
@@ -359,6 +365,10 @@ class DeviceModel:
     def sweep_overlapped(self, n_sweeps: int = 1, x_ctas: int = 0):
         """Sweeps whose n_wk exchange runs inside the sampling launches (two half-sweeps per sweep)."""
         check(_lib.load().cgs_model_sweep_overlapped(self._h, int(n_sweeps), int(x_ctas)))
+
+    def sweep_blocked(self, n_sweeps: int = 1):
+        """Sweeps as one launch per region block, no exchange (keeps the gathered slice of n_wk L2-sized)."""
+        check(_lib.load().cgs_model_sweep_blocked(self._h, int(n_sweeps)))
 
     def exchange_flush(self):
         """Publish the rows of the last half-sweep (before reading counts or log-likelihoods)."""

@@ -340,18 +340,20 @@ def test_deterministic_mode_trace_close_to_oracle(small):
     assert rel.max() < 0.02 and rel[-1] < 0.005, f"trace deviates {rel.max():.3%} at sweep {rel.argmax()}"
 
 
-@pytest.mark.parametrize("K", [3, 10, 50])
-def test_overlapped_sweeps_single_rank_mechanics(small, K):
+@pytest.mark.parametrize("K,n_blocks", [(3, 2), (10, 3), (50, 2), (50, 5)])
+def test_overlapped_sweeps_single_rank_mechanics(small, K, n_blocks):
     """cgs_model_sweep_overlapped with one rank (the exchange blocks of the fused launch then reduce over a single
-    arena): two half-sweeps by region index visit every token exactly once per sweep, the tables stay the exact
-    bookkeeping of z through the in-launch exchange of the other half's rows, and the chain behaves like the plain one
-    (log-likelihood within 1 % of the plain schedule's after the same number of sweeps, seed-averaged)."""
+    arena) and cgs_model_sweep_blocked (no exchange): a sweep as one launch per REGION BLOCK visits every token
+    exactly once, the tables stay the exact bookkeeping of z through the in-launch exchange of the previous block's
+    rows, and the chain behaves like the plain one (log-likelihood within 1 % of the plain schedule's after the same
+    number of sweeps, seed-averaged)."""
     from pycistopic_b200 import Corpus, DeviceModel
+    from pycistopic_b200.adlda import balanced_region_blocks
     corpus = Corpus.from_regions_by_cells(small)
-    per_region = np.diff(small.indptr)
-    split = int(np.searchsorted(np.cumsum(per_region), per_region.sum() / 2.0)) + 1
-    corpus.set_region_split(split)
-    lls = {"plain": [], "overlapped": []}
+    bounds = balanced_region_blocks(np.diff(small.indptr), n_blocks)
+    assert bounds[0] == 0 and bounds[-1] == small.shape[0] and len(bounds) == n_blocks + 1 and np.all(np.diff(bounds) > 0)
+    corpus.set_region_blocks(bounds)
+    lls = {"plain": [], "overlapped": [], "blocked": []}
     for seed in (1, 2, 3, 4):
         for mode in lls:
             mdl = DeviceModel(corpus, K, 50.0 / K, 0.1, seed=seed)
@@ -366,11 +368,15 @@ def test_overlapped_sweeps_single_rank_mechanics(small, K):
                 mdl.sync()
                 assert mdl.exchange_timeouts() == 0
                 assert mdl.sweeps_done == 25
+            elif mode == "blocked":
+                mdl.sweep_blocked(25)
+                assert mdl.sweeps_done == 25
             else:
                 mdl.sweep(25)
             assert mdl.verify_counts() == {"n_dk": 0, "n_wk": 0, "n_k": 0}
             lls[mode].append(mdl.loglikelihood())
             mdl.close()
-    a, b = np.mean(lls["plain"]), np.mean(lls["overlapped"])
-    assert abs(a - b) / abs(a) < 0.01, lls
+    a = np.mean(lls["plain"])
+    for mode in ("overlapped", "blocked"):
+        assert abs(a - np.mean(lls[mode])) / abs(a) < 0.01, lls
     corpus.close()
