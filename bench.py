@@ -1196,7 +1196,7 @@ def main():
                     help="every rank draws only its own cells (always on for C4)")
     ap.add_argument("--adlda-modes", default="", help="comma-separated exchange modes of the AD-LDA legs (default: all)")
     ap.add_argument("--region-blocks", type=int, default=0,
-                    help="region blocks of the overlapped sweeps (0 = two, or enough for a block's rows to fit the L2)")
+                    help="region blocks of the overlapped sweeps (0 = two, the measured best)")
     ap.add_argument("--overlap-ctas", type=int, default=0, help="exchange blocks of the fused launches (0 = one per two SMs)")
     ap.add_argument("--async-parts", type=int, default=2, help="rounds (= sub-sweeps) per sweep of the async exchange")
     ap.add_argument("--adlda-only", action="store_true", help="skip the model-sweep legs (used for the C4 run)")

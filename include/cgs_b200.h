@@ -255,9 +255,9 @@ int cgs_model_exchange_sync(cgs_model *m, int32_t n_ctas);
 int cgs_corpus_set_region_split(cgs_corpus *c, int32_t region_split);
 /* The general form: n_blocks region blocks, block b = regions [bounds[b], bounds[b + 1]) (bounds[0] = 0, bounds[n_blocks] =
  * n_regions; every rank the same).  A sweep is then n_blocks launches, each over one block of every cell, and while block b
- * is sampled the rows of block b - 1 are exchanged.  More blocks than two pay when the table does not fit the L2 (C4: 400 MB
- * per rank): a launch then only gathers rows of its own block, which does.  cgs_model_sweep_blocked is the same block-wise
- * sweep without any exchange (one GPU, or between stand-alone exchanges). */
+ * is sampled the rows of block b - 1 are exchanged.  Two blocks are what the overlap needs and the measured best (L2-sized
+ * slices of a 512 MB table did not pay: the sweep is issue / LSU bound, profiles/r2_region_blocks.txt).
+ * cgs_model_sweep_blocked is the same block-wise sweep without any exchange. */
 int cgs_corpus_set_region_blocks(cgs_corpus *c, int32_t n_blocks, const int32_t *bounds);
 int cgs_model_sweep_blocked(cgs_model *m, int32_t n_sweeps);
 int cgs_model_sweep_overlapped(cgs_model *m, int32_t n_sweeps, int32_t x_ctas);

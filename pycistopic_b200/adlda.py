@@ -67,11 +67,12 @@ def balanced_region_blocks(tokens_per_region, n_blocks):
     return np.maximum.accumulate(bounds).astype(np.int32)
 
 
-def region_blocks_for_table(n_regions, padded_topics, l2_bytes=126 << 20):
-    """How many region blocks an overlapped sweep uses: two, or as many as it takes for one block's rows of n_wk to
-    fit in 60 % of the L2 (measured on C4, K = 100, 400 MB per rank: the block launches gather from L2)."""
-    table = 4.0 * n_regions * padded_topics
-    return int(max(2, np.ceil(table / (0.6 * l2_bytes))))
+def region_blocks_for_table(n_regions, padded_topics):
+    """How many region blocks an overlapped sweep uses: two -- what the overlap needs.  More blocks would keep the slice
+    of n_wk a launch gathers from inside the L2 (C4, K = 100: 512 MB per rank), but the sweep is bound by issue slots and
+    the load/store path, not by DRAM: measured on a C4 shard 18.8 / 18.6 / 18.8 / 19.1 / 19.5 ms per sweep for 1 / 2 / 4 /
+    6 / 8 blocks (profiles/r2_region_blocks.txt)."""
+    return 2
 
 
 class GpuShard:
