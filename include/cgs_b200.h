@@ -124,9 +124,10 @@ int cgs_model_get_sweep_shape(const cgs_model *m, int32_t *lanes_per_token, int3
                               int32_t *warps_per_cell);
 /* Deterministic mode (the reference is bit-reproducible for a fixed random_state, lda_models.py:104; the default
  * device schedule is not, because cells read the LIVE n_wk while other cells update it).  parts > 0: every sweep runs
- * as `parts` sub-sweeps; each reads n_wk / n_k from a copy taken when the sub-sweep starts, one warp owns a cell, and
- * all count updates are integer reductions (commutative) -- so the result is a pure function of (matrix, n_topics,
- * alpha, eta, seed, parts), whatever the scheduling.  The price is staleness of up to 1/parts of a sweep (DESIGN.md
+ * as `parts` sub-sweeps; each reads n_wk / n_k from a copy taken when the sub-sweep starts, the warps of a cell work in
+ * rounds on private copies of the cell's row that are merged with integer atomics between two barriers, and all count
+ * updates are integer reductions (commutative) -- so the result is a pure function of (matrix, n_topics, alpha, eta,
+ * seed, parts, sweep shape), whatever the scheduling.  The price is staleness of up to 1/parts of a sweep (DESIGN.md
  * section 5).  parts = 0 restores the default schedule. */
 int cgs_model_set_deterministic(cgs_model *m, int32_t parts);
 /* Arithmetic of the conditional p(k), its running sum and the inversion: 32 = float (default), 64 = double, the

@@ -358,6 +358,7 @@ struct cgs_model {
     uint32_t x_round = 0;
     int x_sync_blocks = 0;
     int sweep_blocks_fused = 0;
+    int sweep_blocks_det = 0;
     ExchangeParams x_fused;      // the exchange of the current fused launch
     int x_pending_block = -1;    // overlapped sweeps: the region block that was sampled and not yet exchanged
     cudaStream_t x_stream = nullptr;
@@ -942,6 +943,46 @@ static int dispatch_ch(cgs_model *m, const SweepParams &p, int *bc) {
     CGS_FAIL("unsupported chunk count");
 }
 
+template <int TPT, int CH>
+static int launch_sweep_det(cgs_model *m, const SweepParams &p) {
+    using L = CellSmem<TPT, CH, float>;
+    const int nwarps = m->threads / 32;
+    const size_t smem = (size_t)nwarps * L::WORDS * 4 + 2 * (size_t)L::KS * 4 + 16;
+    if (m->sweep_blocks_det == 0) {
+        CGS_CUDA(cudaFuncSetAttribute(sweep_det_kernel<TPT, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        CGS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep_det_kernel<TPT, CH>, m->threads, smem));
+        m->sweep_blocks_det = m->corpus->num_sms * std::max(1, per_sm);
+    }
+    const int blocks = std::max(1, std::min(m->sweep_blocks_det, m->corpus->n_cells));
+    sweep_det_kernel<TPT, CH><<<blocks, m->threads, smem, m->stream>>>(p);
+    CGS_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <int TPT>
+static int dispatch_det_ch(cgs_model *m, const SweepParams &p) {
+    switch (m->ch) {
+        case 1: return launch_sweep_det<TPT, 1>(m, p);
+        case 2: return launch_sweep_det<TPT, 2>(m, p);
+        case 3: return launch_sweep_det<TPT, 3>(m, p);
+        case 4: return launch_sweep_det<TPT, 4>(m, p);
+    }
+    CGS_FAIL("unsupported chunk count for the deterministic sweep");
+}
+
+static int dispatch_sweep_det(cgs_model *m, const SweepParams &p) {
+    switch (m->tpt) {
+        case 1: return dispatch_det_ch<1>(m, p);
+        case 2: return dispatch_det_ch<2>(m, p);
+        case 4: return dispatch_det_ch<4>(m, p);
+        case 8: return dispatch_det_ch<8>(m, p);
+        case 16: return dispatch_det_ch<16>(m, p);
+        case 32: return dispatch_det_ch<32>(m, p);
+    }
+    CGS_FAIL("unsupported lanes-per-token");
+}
+
 static int dispatch_sweep(cgs_model *m, const SweepParams &p) {
     int *bc = &m->sweep_blocks;
     switch (m->tpt) {
@@ -1051,7 +1092,8 @@ static int sweep_impl(cgs_model *m, int32_t n_sweeps, int32_t part, int32_t n_pa
             m->work_slot += 1;
             p.work_counter = m->d_work + slot;
             p.sweep = (uint32_t)m->sweeps;  // all parts of one sweep share the Philox sweep index
-            CGS_TRY(dispatch_sweep(m, p));
+            if (det) CGS_TRY(dispatch_sweep_det(m, p));
+            else CGS_TRY(dispatch_sweep(m, p));
             m->launches += 1;
         }
         if (det || part == n_parts - 1) m->sweeps += 1;
@@ -1399,6 +1441,7 @@ int cgs_model_set_conditional_precision(cgs_model *m, int32_t bits) {
     if (bits != 32 && bits != 64) CGS_FAIL("bits must be 32 or 64");
     m->fp64 = bits == 64;
     m->sweep_blocks = 0;
+    if (m->fp64 && m->det_parts > 0) CGS_FAIL("the deterministic sweep exists for the fp32 conditional");
     if (m->fp64 && m->ch > 4) {  // the fp64 kernels are built for <= 4 chunks per lane: widen the token group
         const int chunks = (m->K + 3) / 4;
         while (m->tpt < 32 && (chunks + m->tpt - 1) / m->tpt > 4) m->tpt <<= 1;
@@ -1412,17 +1455,15 @@ int cgs_model_set_conditional_precision(cgs_model *m, int32_t bits) {
 int cgs_model_set_deterministic(cgs_model *m, int32_t parts) {
     if (!m) CGS_FAIL("NULL model");
     if (parts < 0 || parts > 1024) CGS_FAIL("parts must be in [0, 1024]");
-    if (parts > 0 && m->det_parts == 0) {
-        m->threads = 32;  // one warp per cell: nothing a cell reads depends on another warp's timing
-        m->sweep_blocks = 0;
-        m->auto_blocks = 1 << 30;
-    } else if (parts == 0 && m->det_parts > 0) {
-        const cgs_corpus *c = m->corpus;
-        pick_sweep_shape(m->K, m->Kp, (double)std::max<int64_t>(c->n_tokens, c->global_tokens),
-                         (double)std::max<int64_t>(c->n_cells, c->global_cells), &m->tpt, &m->ch, &m->threads,
-                         &m->auto_blocks);
+    if (parts > 0 && m->fp64) CGS_FAIL("the deterministic sweep exists for the fp32 conditional");
+    if (parts > 0 && m->ch > 4) {  // the deterministic kernels are built for <= 4 chunks per lane: widen the token group
+        const int chunks = (m->K + 3) / 4;
+        while (m->tpt < 32 && (chunks + m->tpt - 1) / m->tpt > 4) m->tpt <<= 1;
+        m->ch = (chunks + m->tpt - 1) / m->tpt;
+        if (m->ch > 4) CGS_FAIL("n_topics too large for the deterministic sweep");
         m->sweep_blocks = 0;
     }
+    m->sweep_blocks_det = 0;
     m->det_parts = parts;
     return 0;
 }

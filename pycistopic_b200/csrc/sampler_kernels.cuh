@@ -682,6 +682,158 @@ sweep_kernel(const SweepParams p, const ExchangeParams xp) {
     }
 }
 
+// ---- deterministic sweep (cgs_model_set_deterministic) --------------------------------------------------------------
+// Same sampling step as sweep_kernel (sweep_step), arranged so that NOTHING a warp reads depends on another warp's or
+// another CTA's timing:
+//   * n_wk rows and n_k come from copies taken when the sub-sweep starts (p.n_wk_read / p.n_k_read); updates go to the live
+//     tables as integer reductions, which commute;
+//   * a cell is owned by one CTA and worked on in ROUNDS: in a round every warp samples one batch of 32 tokens against its
+//     PRIVATE copy of the cell row (counts and f, refreshed from the cell's shared row when the round starts; the warp sees
+//     its own moves at once, exactly as in the default kernel), then the warps add what they changed to the shared row
+//     with integer atomics; two barriers per round.  What a warp sees of the others is one round old -- the same order of
+//     in-cell staleness as the default kernel's steps in flight, but at points fixed by the data, not by the scheduler.
+// Hence z after a sweep is a pure function of (z before, tables before, seed), for any grid size or scheduling order.
+template <int TPT, int CH>
+__global__ void __launch_bounds__(SweepBounds<CH, float, true>::kThreads, 2)
+sweep_det_kernel(const SweepParams p) {
+    using L = CellSmem<TPT, CH, float>;
+    constexpr int KS = L::KS;
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int kMaxWarps = SweepBounds<CH, float, true>::kThreads / 32;
+    constexpr uint32_t REGION = (uint32_t)L::WORDS * 4u;  // one private copy of the cell layout per warp
+    extern __shared__ __align__(16) uint32_t det_smem[];   // [nwarps] private regions, then shared ndk[KS], first[KS], slot
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = __shfl_sync(FULL, tid >> 5, 0);
+    const int nwarps = blockDim.x >> 5;
+    const uint32_t sm0 = smem_u32(det_smem);
+    const uint32_t sm = sm0 + (uint32_t)warp * REGION;                 // this warp's private region
+    const uint32_t s_shared = sm0 + (uint32_t)nwarps * REGION;         // the cell's row, authoritative between rounds
+    const uint32_t s_first = s_shared + KS * 4;                        // the row as loaded (for the n_k update)
+    const uint32_t s_slot = s_first + KS * 4;
+    (void)kMaxWarps;
+    const int sub = lane & (TPT - 1);
+    const int gbase = lane & ~(TPT - 1);
+    const int K = p.K, Kp = p.Kp;
+    const float alpha = p.alpha, eta = p.eta;
+    const uint32_t rowbytes = (uint32_t)Kp * 4u;
+    const int lim = (((K + 3) >> 2) - sub + TPT - 1) >> log2_tpt<TPT>();
+    const char *nwk_lane = reinterpret_cast<const char *>(p.n_wk_read) + sub * 16;
+    int4 buf[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) buf[c] = make_int4(0, 0, 0, 0);
+
+    for (;;) {
+        if (tid == 0) sts_i(s_slot, atomicAdd(p.work_counter, 1));
+        __syncthreads();
+        const int slot = lds_i(s_slot) * p.n_parts + p.part;
+        if (slot >= p.n_cells) break;
+        const int cell = p.cell_order[slot];
+        const int64_t t0 = p.cell_lo[cell], t1 = p.cell_hi[cell];
+        int32_t *ndk_row = p.n_dk + (int64_t)cell * Kp;
+        for (int k = tid; k < KS; k += blockDim.x) {
+            const int nd = k < K ? ndk_row[k] : 0;
+            sts_i(s_shared + k * 4, nd);
+            sts_i(s_first + k * 4, nd);
+        }
+        // the totals are those of the copy for the whole cell: every warp keeps them in its own region
+        for (int k = lane; k < KS; k += 32) {
+            float den = 1.0f, inv = 0.0f;
+            if (k < K) {
+                den = (float)p.n_k_read[k] + p.etaW;
+                inv = 1.0f / den;
+            }
+            sts_f(sm + L::DEN + k * 4, den);
+            sts_f(sm + L::INV + k * 4, inv);
+        }
+        __syncthreads();
+
+        const int ntok = (int)(t1 - t0);
+        const int nbatch = (ntok + 31) >> 5;
+        int rot = 0;
+        if (nbatch > 0) {
+            uint32_t h = (uint32_t)cell * 0x9E3779B1u ^ p.seed_lo;
+            h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
+            rot = (int)(h % (uint32_t)nbatch);
+        }
+        const int32_t *tok_cell = p.tok_region + t0;
+        uint16_t *z_cell = p.z + t0;
+        const uint64_t gi0 = (uint64_t)(p.token_offset + t0) + (uint64_t)lane;
+        const int rounds = (nbatch + nwarps - 1) / nwarps;
+        for (int r = 0; r < rounds; ++r) {
+            // ---- refresh the private copy of the cell row --------------------------------------------------
+            for (int k = lane; k < KS; k += 32) {
+                const int nd = lds_i(s_shared + k * 4);
+                sts_i(sm + L::NDK + k * 4, nd);
+                sts_i(sm + L::PUB + k * 4, nd);
+                sts_f(sm + L::F + k * 4, k < K ? ((float)nd + alpha) * lds_f(sm + L::INV + k * 4) : 0.0f);
+            }
+            __syncwarp();
+            const int b = r * nwarps + warp;  // this warp's batch of the round, in the cell's rotated order
+            if (b < nbatch) {
+                int bb = b + rot;
+                if (bb >= nbatch) bb -= nbatch;
+                const int off = bb << 5;
+                const bool valid = (off + lane) < ntok;
+                const int ic = valid ? off + lane : ntok - 1;
+                const int w_j = __ldg(tok_cell + ic);
+                const uint64_t gi = (gi0 + (uint64_t)off) & p.rng_index_mask;
+                const Philox4 rnd = philox4x32_10((uint32_t)gi, (uint32_t)(gi >> 32), p.sweep, 1u, p.seed_lo, p.seed_hi);
+                const int pk_j = pack_token(rnd.x, (int)z_cell[ic], valid);
+                int w_c = (TPT > 1) ? __shfl_sync(FULL, w_j, 0, TPT) : w_j;
+                int pk_c = (TPT > 1) ? __shfl_sync(FULL, pk_j, 0, TPT) : pk_j;
+                {
+                    const char *row = nwk_lane + (uint64_t)((uint32_t)w_c) * rowbytes;
+                    const int oc = ((pk_c & 0x1ff) >> 2) >> log2_tpt<TPT>();
+#pragma unroll
+                    for (int c = 0; c < CH; ++c) {
+                        const int rc = rot_chunk<CH>(c, oc);
+                        if (rc < lim) buf[c] = __ldcg(reinterpret_cast<const int4 *>(row + rc * (TPT * 16)));
+                    }
+                }
+                int zn_j = pk_j & 0x1ff;
+                if (TPT == 1) {
+                    zn_j = sweep_step<TPT, CH, float>(buf, nwk_lane, rowbytes, lim, w_j, pk_j, w_j, pk_j | 0x200, sm, sub, gbase,
+                                                      lane, alpha, eta, K, p.nwk_write_delta);
+                } else {
+                    constexpr int UNR = (TPT <= 8) ? TPT : 2;
+#pragma unroll UNR
+                    for (int s = 0; s < TPT; ++s) {
+                        const bool last = (s + 1 >= TPT);
+                        const int src = last ? 0 : s + 1;
+                        const int w_x = __shfl_sync(FULL, w_j, src, TPT);
+                        int pk_x = __shfl_sync(FULL, pk_j, src, TPT);
+                        if (last) pk_x |= 0x200;  // nothing to prefetch across the round barrier
+                        const int zn = sweep_step<TPT, CH, float>(buf, nwk_lane, rowbytes, lim, w_c, pk_c, w_x, pk_x, sm, sub,
+                                                                  gbase, lane, alpha, eta, K, p.nwk_write_delta);
+                        if (sub == s) zn_j = zn;
+                        w_c = w_x;
+                        pk_c = pk_x;
+                    }
+                }
+                if (valid) z_cell[off + lane] = (uint16_t)zn_j;
+                if (p.visit_counter) {
+                    const unsigned live = __ballot_sync(FULL, valid);
+                    if (lane == 0) atomicAdd(p.visit_counter, (unsigned long long)__popc(live));
+                }
+            }
+            __syncthreads();  // every warp has taken its copy of the shared row before anyone changes it ...
+            for (int k = lane; k < K; k += 32) {
+                const int d = lds_i(sm + L::NDK + k * 4) - lds_i(sm + L::PUB + k * 4);
+                if (d != 0) reds_add(s_shared + k * 4, d);
+            }
+            __syncthreads();  // ... and every change is in before the next round copies it
+        }
+        for (int k = tid; k < K; k += blockDim.x) {
+            const int cur = lds_i(s_shared + k * 4);
+            ndk_row[k] = cur;
+            const int d = cur - lds_i(s_first + k * 4);
+            if (d != 0) red_add_i32(p.n_k + k, d);
+        }
+        __syncthreads();
+    }
+}
+
 // cell_mid[d] = index of the first token of cell d whose region is >= region_split (tokens are sorted by region)
 __global__ void cell_split_kernel(const int64_t *__restrict__ cell_ptr, const int32_t *__restrict__ tok_region,
                                   int32_t n_cells, int32_t region_split, int64_t *__restrict__ cell_mid) {
