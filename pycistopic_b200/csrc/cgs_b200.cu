@@ -943,30 +943,39 @@ static int dispatch_ch(cgs_model *m, const SweepParams &p, int *bc) {
     CGS_FAIL("unsupported chunk count");
 }
 
-template <int TPT, int CH>
+template <int TPT, int CH, typename R>
 static int launch_sweep_det(cgs_model *m, const SweepParams &p) {
-    using L = CellSmem<TPT, CH, float>;
+    using L = CellSmem<TPT, CH, R>;
     const int nwarps = m->threads / 32;
     const size_t smem = (size_t)nwarps * L::WORDS * 4 + 2 * (size_t)L::KS * 4 + 16;
     if (m->sweep_blocks_det == 0) {
-        CGS_CUDA(cudaFuncSetAttribute(sweep_det_kernel<TPT, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CGS_CUDA(cudaFuncSetAttribute(sweep_det_kernel<TPT, CH, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
-        CGS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep_det_kernel<TPT, CH>, m->threads, smem));
+        CGS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep_det_kernel<TPT, CH, R>, m->threads, smem));
         m->sweep_blocks_det = m->corpus->num_sms * std::max(1, per_sm);
     }
     const int blocks = std::max(1, std::min(m->sweep_blocks_det, m->corpus->n_cells));
-    sweep_det_kernel<TPT, CH><<<blocks, m->threads, smem, m->stream>>>(p);
+    sweep_det_kernel<TPT, CH, R><<<blocks, m->threads, smem, m->stream>>>(p);
     CGS_CUDA(cudaGetLastError());
     return 0;
 }
 
 template <int TPT>
 static int dispatch_det_ch(cgs_model *m, const SweepParams &p) {
-    switch (m->ch) {
-        case 1: return launch_sweep_det<TPT, 1>(m, p);
-        case 2: return launch_sweep_det<TPT, 2>(m, p);
-        case 3: return launch_sweep_det<TPT, 3>(m, p);
-        case 4: return launch_sweep_det<TPT, 4>(m, p);
+    if (m->fp64) {
+        switch (m->ch) {
+            case 1: return launch_sweep_det<TPT, 1, double>(m, p);
+            case 2: return launch_sweep_det<TPT, 2, double>(m, p);
+            case 3: return launch_sweep_det<TPT, 3, double>(m, p);
+            case 4: return launch_sweep_det<TPT, 4, double>(m, p);
+        }
+    } else {
+        switch (m->ch) {
+            case 1: return launch_sweep_det<TPT, 1, float>(m, p);
+            case 2: return launch_sweep_det<TPT, 2, float>(m, p);
+            case 3: return launch_sweep_det<TPT, 3, float>(m, p);
+            case 4: return launch_sweep_det<TPT, 4, float>(m, p);
+        }
     }
     CGS_FAIL("unsupported chunk count for the deterministic sweep");
 }
@@ -1441,7 +1450,7 @@ int cgs_model_set_conditional_precision(cgs_model *m, int32_t bits) {
     if (bits != 32 && bits != 64) CGS_FAIL("bits must be 32 or 64");
     m->fp64 = bits == 64;
     m->sweep_blocks = 0;
-    if (m->fp64 && m->det_parts > 0) CGS_FAIL("the deterministic sweep exists for the fp32 conditional");
+    m->sweep_blocks_det = 0;
     if (m->fp64 && m->ch > 4) {  // the fp64 kernels are built for <= 4 chunks per lane: widen the token group
         const int chunks = (m->K + 3) / 4;
         while (m->tpt < 32 && (chunks + m->tpt - 1) / m->tpt > 4) m->tpt <<= 1;
@@ -1455,7 +1464,6 @@ int cgs_model_set_conditional_precision(cgs_model *m, int32_t bits) {
 int cgs_model_set_deterministic(cgs_model *m, int32_t parts) {
     if (!m) CGS_FAIL("NULL model");
     if (parts < 0 || parts > 1024) CGS_FAIL("parts must be in [0, 1024]");
-    if (parts > 0 && m->fp64) CGS_FAIL("the deterministic sweep exists for the fp32 conditional");
     if (parts > 0 && m->ch > 4) {  // the deterministic kernels are built for <= 4 chunks per lane: widen the token group
         const int chunks = (m->K + 3) / 4;
         while (m->tpt < 32 && (chunks + m->tpt - 1) / m->tpt > 4) m->tpt <<= 1;

@@ -693,10 +693,11 @@ sweep_kernel(const SweepParams p, const ExchangeParams xp) {
 //     with integer atomics; two barriers per round.  What a warp sees of the others is one round old -- the same order of
 //     in-cell staleness as the default kernel's steps in flight, but at points fixed by the data, not by the scheduler.
 // Hence z after a sweep is a pure function of (z before, tables before, seed), for any grid size or scheduling order.
-template <int TPT, int CH>
-__global__ void __launch_bounds__(SweepBounds<CH, float, true>::kThreads, 2)
+template <int TPT, int CH, typename R = float>
+__global__ void __launch_bounds__(SweepBounds<CH, float, true>::kThreads, sizeof(R) == 8 ? 1 : 2)
 sweep_det_kernel(const SweepParams p) {
-    using L = CellSmem<TPT, CH, float>;
+    using L = CellSmem<TPT, CH, R>;
+    constexpr int RB = L::RB;
     constexpr int KS = L::KS;
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int kMaxWarps = SweepBounds<CH, float, true>::kThreads / 32;
@@ -715,7 +716,8 @@ sweep_det_kernel(const SweepParams p) {
     const int sub = lane & (TPT - 1);
     const int gbase = lane & ~(TPT - 1);
     const int K = p.K, Kp = p.Kp;
-    const float alpha = p.alpha, eta = p.eta;
+    const R alpha = sizeof(R) == 8 ? (R)p.alpha64 : (R)p.alpha, eta = sizeof(R) == 8 ? (R)p.eta64 : (R)p.eta;
+    const R etaW = sizeof(R) == 8 ? (R)p.etaW64 : (R)p.etaW;
     const uint32_t rowbytes = (uint32_t)Kp * 4u;
     const int lim = (((K + 3) >> 2) - sub + TPT - 1) >> log2_tpt<TPT>();
     const char *nwk_lane = reinterpret_cast<const char *>(p.n_wk_read) + sub * 16;
@@ -738,13 +740,13 @@ sweep_det_kernel(const SweepParams p) {
         }
         // the totals are those of the copy for the whole cell: every warp keeps them in its own region
         for (int k = lane; k < KS; k += 32) {
-            float den = 1.0f, inv = 0.0f;
+            R den = (R)1, inv = (R)0;
             if (k < K) {
-                den = (float)p.n_k_read[k] + p.etaW;
-                inv = 1.0f / den;
+                den = (R)p.n_k_read[k] + etaW;
+                inv = (R)1 / den;
             }
-            sts_f(sm + L::DEN + k * 4, den);
-            sts_f(sm + L::INV + k * 4, inv);
+            Real<R>::sts(sm + L::DEN + k * RB, den);
+            Real<R>::sts(sm + L::INV + k * RB, inv);
         }
         __syncthreads();
 
@@ -766,7 +768,7 @@ sweep_det_kernel(const SweepParams p) {
                 const int nd = lds_i(s_shared + k * 4);
                 sts_i(sm + L::NDK + k * 4, nd);
                 sts_i(sm + L::PUB + k * 4, nd);
-                sts_f(sm + L::F + k * 4, k < K ? ((float)nd + alpha) * lds_f(sm + L::INV + k * 4) : 0.0f);
+                Real<R>::sts(sm + L::F + k * RB, k < K ? ((R)nd + alpha) * Real<R>::lds(sm + L::INV + k * RB) : (R)0);
             }
             __syncwarp();
             const int b = r * nwarps + warp;  // this warp's batch of the round, in the cell's rotated order
@@ -793,7 +795,7 @@ sweep_det_kernel(const SweepParams p) {
                 }
                 int zn_j = pk_j & 0x1ff;
                 if (TPT == 1) {
-                    zn_j = sweep_step<TPT, CH, float>(buf, nwk_lane, rowbytes, lim, w_j, pk_j, w_j, pk_j | 0x200, sm, sub, gbase,
+                    zn_j = sweep_step<TPT, CH, R>(buf, nwk_lane, rowbytes, lim, w_j, pk_j, w_j, pk_j | 0x200, sm, sub, gbase,
                                                       lane, alpha, eta, K, p.nwk_write_delta);
                 } else {
                     constexpr int UNR = (TPT <= 8) ? TPT : 2;
@@ -804,7 +806,7 @@ sweep_det_kernel(const SweepParams p) {
                         const int w_x = __shfl_sync(FULL, w_j, src, TPT);
                         int pk_x = __shfl_sync(FULL, pk_j, src, TPT);
                         if (last) pk_x |= 0x200;  // nothing to prefetch across the round barrier
-                        const int zn = sweep_step<TPT, CH, float>(buf, nwk_lane, rowbytes, lim, w_c, pk_c, w_x, pk_x, sm, sub,
+                        const int zn = sweep_step<TPT, CH, R>(buf, nwk_lane, rowbytes, lim, w_c, pk_c, w_x, pk_x, sm, sub,
                                                                   gbase, lane, alpha, eta, K, p.nwk_write_delta);
                         if (sub == s) zn_j = zn;
                         w_c = w_x;
