@@ -426,6 +426,9 @@ def run_adlda_leg(args, dev, rank, world, local_rank, shape=None):
                          "region_blocks": n_region_blocks,
                          "sweep_shape": shard.model.sweep_shape,
                          "checks": checks}
+        shard.close_peers()
+        if world > 1:
+            dist.barrier()  # nobody frees a buffer that another rank still has mapped
         shard.close()
         torch.cuda.empty_cache()
     peak = hbm_peak()[0]
@@ -1091,6 +1094,8 @@ def run_cuda(args):
         for a_ in it.get("peer_addrs", []):
             if a_ != it["model"].exchange_arena()[0]:
                 _lib.load().cgs_ipc_close(local_rank, ctypes.c_void_p(a_))
+    barrier()  # nobody frees an arena that another rank still has mapped
+    for it in items:
         it["model"].close()
         if it["corpus"] is not None:
             it["corpus"].close()

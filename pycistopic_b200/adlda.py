@@ -220,21 +220,28 @@ class GpuShard:
     def sync(self):
         self.model.sync()
 
-    def close(self):
+    def close_peers(self):
+        """Unmap the other ranks' buffers.  Every rank must have done this before any rank frees its own buffers
+        (callers put a barrier between close_peers() and close())."""
         import ctypes
 
         from . import _lib
+        self.model.sync()
         if self._peers is not None:
             own = self.model.device_buffer("delta")[0]
             for a in self._peers:
                 if a != own:
                     _lib.load().cgs_ipc_close(self.device, ctypes.c_void_p(a))
+            self._peers = None
         if getattr(self, "_arenas", None) is not None:
-            self.model.sync()
             own = self.model.exchange_arena()[0]
             for a in self._arenas:
                 if a != own:
                     _lib.load().cgs_ipc_close(self.device, ctypes.c_void_p(a))
+            self._arenas = None
+
+    def close(self):
+        self.close_peers()
         self.model.close()
         self.corpus.close()
 
@@ -423,6 +430,9 @@ def fit_adlda(binary_matrix, n_topics, n_iter=150, alpha=0.1, eta=0.01, random_s
         nd = tokens_per_cell.astype(np.float64)
         res.doc_topic_ = (ndz + alpha) / (nd[:, None] + alpha * n_topics)
         res.part_ptr_ = part_ptr
+        if world > 1 and hasattr(shard, "close_peers"):
+            shard.close_peers()
+            dist.barrier()  # nobody frees a buffer that another rank still has mapped
         return res
     finally:
         shard.close()
