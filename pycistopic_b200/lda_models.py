@@ -179,12 +179,13 @@ def schedule_models_split(costs, n_workers, overhead=None, min_fraction=0.2):
     return best
 
 
-def schedule_models_paired(costs, n_workers, penalty=1.10, overhead=0.05, min_fraction=0.25, max_splits=None,
-                           equal_parts=False):
+def schedule_models_paired(costs, n_workers, penalty=1.07, overhead=0.05, min_fraction=0.25, max_splits=None,
+                           equal_parts=True):
     """Whole models, longest first -- except that the j longest models are split in TWO parts that run on two workers
     at the same time (first in both workers' steps, so that their overlapped exchange meets), a worker taking at most
-    one such part.  For every j: the parts and the whole models are placed longest-first, the two fractions of every
-    split model level its two workers, and a local search (move or swap whole models between workers, re-levelling
+    one such part.  For every j: the parts and the whole models are placed longest-first, a split model is cut in equal
+    halves (``equal_parts``: the partners' launches then take the same time and never wait for each other -- measured
+    better than fractions that level the two workers, which is what ``equal_parts=False`` does), and a local search (move or swap whole models between workers, re-levelling
     after each try) lowers the makespan further; the j with the smallest predicted makespan wins (j = 0 is plain LPT
     plus the local search).  A part costs ``penalty`` x its share of the model (a shard fills the GPU less evenly) plus
     ``overhead``.  Returns ``(plan, makespan)`` with ``plan[w]`` = ordered ``(model, f0, f1)`` items, split part first.
