@@ -616,13 +616,14 @@ def _device_top5_coherence(m, K, n_iter, seeds):
     return np.array(coh), np.array(ll)
 
 
-@pytest.mark.parametrize("case,n_gpu_seeds", [("c1_K5", 256), ("c1_K10", 256), ("c2s_K50", 128)])
+@pytest.mark.parametrize("case,n_gpu_seeds", [("c1_K5", 256), ("c1_K10", 512), ("c2s_K50", 128)])
 def test_coherence_distribution_vs_frozen_oracle(case, n_gpu_seeds):
     """North star: "final topic coherence within 1 % of the reference".  ONE chain of the sequential oracle differs
     from another by 6 % (C1) to 12 % (C2-shaped) -- asserted below from the frozen per-seed values -- so the
     comparison is between DISTRIBUTIONS: tests/golden/coherence_distribution.npz freezes the oracle's model
     coherence for 128 (C1: K = 5, 10; 150 sweeps) and 96 (C2-shaped: 600 cells x 200 000 regions, K = 50, 100 sweeps)
-    seeds; the device runs 256 / 128 chains.  Gates: means within 2 % (C1; 2.7 standard errors of the difference) or
+    seeds; the device runs 256 / 512 / 128 chains (512 where the measured offset, 1.2-1.6 % at C1 / K = 10, leaves the
+    least room under the gate).  Gates: means within 2 % (C1; 2.7 standard errors of the difference) or
     within max(2 %, 2.5 standard errors) (C2-shaped, where the frozen mean itself is only known to 1.25 %); spread
     within a factor 1.5; two-sample Kolmogorov-Smirnov p > 0.001; mean final log-likelihood within 0.3 %."""
     from scipy.stats import ks_2samp

@@ -68,6 +68,22 @@ def test_balanced_partition_is_a_partition(counts, parts):
 
 
 @settings(max_examples=60, **COMMON)
+@given(counts=st.lists(st.integers(0, 3000), min_size=1, max_size=300), blocks=st.integers(1, 12))
+def test_balanced_region_blocks_cover_the_regions(counts, blocks):
+    """adlda.balanced_region_blocks: bounds start at 0, end at n_regions, never decrease, and no block holds more than
+    its share of the tokens plus one region's worth."""
+    if sum(counts) == 0:
+        counts = counts[:-1] + [1]
+    bounds = adlda.balanced_region_blocks(counts, blocks)
+    W = len(counts)
+    assert bounds[0] == 0 and bounds[-1] == W and np.all(np.diff(bounds) >= 0) and len(bounds) == min(blocks, W) + 1
+    cum = np.concatenate([[0], np.cumsum(counts)])
+    per_block = np.diff(cum[bounds])
+    assert per_block.sum() == sum(counts)
+    assert per_block.max() <= sum(counts) / (len(bounds) - 1) + 2 * max(counts) + 1e-9
+
+
+@settings(max_examples=60, **COMMON)
 @given(topics=st.lists(st.integers(1, 500), min_size=1, max_size=24), workers=st.integers(1, 16))
 def test_schedule_covers_every_model_once(topics, workers):
     plan = lda_models.schedule_models(topics, workers)
