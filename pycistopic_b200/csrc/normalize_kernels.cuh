@@ -55,8 +55,16 @@ __global__ void __launch_bounds__(kNormCols) normalize_log1p_kernel(const T *__r
     const double d = (double)colsum[c] / scale;  // np.sum(X, axis=0) / scale_factor
     const int64_t r0 = (int64_t)blockIdx.y * kNormSlab;
     const int64_t r1 = r0 + kNormSlab < R ? r0 + kNormSlab : R;
+    // A zero numerator sends the fp64 division down its slow path (a subroutine of ~100 instructions), and a truncated
+    // imputation is mostly zeros: log1p(0 / d) is that same zero exactly for d > 0, so those values skip both.
+    const bool d_pos = d > 0.0;
     for (int64_t r = r0; r < r1; ++r) {
-        const double q = (double)x[r * C + c] / d;
+        const T v = x[r * C + c];
+        if (v == T(0) && d_pos) {
+            out[r * C + c] = (OUT)v;  // keeps the sign of a floating-point zero, as log1p(-0 / d) does
+            continue;
+        }
+        const double q = (double)v / d;
         out[r * C + c] = (OUT)log1p(q);
     }
 }
