@@ -213,7 +213,8 @@ int cgs_model_delta_apply_peers(cgs_model *m, void *const *peer_delta, int32_t n
 
 /* The whole synchronous exchange step behind the ABI: delta = n_wk - snapshot, ncclAllReduce(delta, int32, sum) on
  * the model's stream with the caller's communicator (an ncclComm_t: torch's ProcessGroupNCCL._comm_ptr(), or one
- * made by cgs_nccl_comm_create), then cgs_model_delta_apply.  libnccl.so.2 is resolved at first use (dlopen). */
+ * made by cgs_nccl_comm_create), then cgs_model_delta_apply.  libnccl.so.2 is resolved at first use (dlopen): the copy
+ * the process has already loaded, else the file $CGS_NCCL_LIBRARY names, else the loader's default. */
 int cgs_model_allreduce_delta(cgs_model *m, void *nccl_comm);
 /* For hosts without their own NCCL plumbing: rank 0 calls cgs_nccl_unique_id and ships the 128 bytes to the other
  * ranks by any means; every rank then creates its communicator. */
@@ -252,7 +253,11 @@ int cgs_model_exchange_sync(cgs_model *m, int32_t n_ctas);
  *   cgs_corpus_set_region_split: the region index that cuts the sweep (every rank the same; pick the one that halves
  *     the tokens).  cgs_model_sweep_overlapped: n_sweeps sweeps, each two launches; the rows of the last half-sweep
  *     stay unpublished until the next call or cgs_model_exchange_flush (call it before reading counts /
- *     log-likelihoods).  Needs cgs_model_exchange_open and one cgs_model_exchange_sync after init. */
+ *     log-likelihoods).  Needs cgs_model_exchange_open and one cgs_model_exchange_sync after init.
+ *   The exchange blocks of all ranks wait for each other, so they must be resident at once: x_ctas is clamped to what the
+ *   sweep kernel can keep resident beside one sampling block, and nothing else may occupy the GPU while the launch
+ *   starts (other work on the device delays the exchange; after 4 s a wait gives up and cgs_model_exchange_status
+ *   reports the timeout). */
 int cgs_corpus_set_region_split(cgs_corpus *c, int32_t region_split);
 /* The general form: n_blocks region blocks, block b = regions [bounds[b], bounds[b + 1]) (bounds[0] = 0, bounds[n_blocks] =
  * n_regions; every rank the same).  A sweep is then n_blocks launches, each over one block of every cell, and while block b

@@ -168,6 +168,25 @@ class CgsError(RuntimeError):
     """Raised when a C-ABI call returns a non-zero code; carries cgs_last_error()."""
 
 
+def _point_at_bundled_nccl():
+    """cgs_nccl_* resolve NCCL at first use (csrc/cgs_b200.cu, nccl_api): the copy the process has already loaded, else
+    ``$CGS_NCCL_LIBRARY``, else whatever the loader finds as libnccl.so.2.  In a Python process that has not imported torch
+    yet the last one would be the SYSTEM library, and a later ``import torch`` would then be bound to it by soname instead
+    of the (newer) one its wheel ships -- and fail.  So name the wheel's copy; nothing is loaded here."""
+    if os.environ.get("CGS_NCCL_LIBRARY"):
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia")
+        for loc in (spec.submodule_search_locations if spec else []):
+            cand = os.path.join(loc, "nccl", "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["CGS_NCCL_LIBRARY"] = cand
+                return
+    except Exception:  # no such wheel: the loader's default applies
+        pass
+
+
 def load() -> ctypes.CDLL:
     """Load (building first if the sources are newer) the CUDA library.  Fails loudly."""
     global _lib
@@ -179,6 +198,7 @@ def load() -> ctypes.CDLL:
             pass
         else:
             _build.build()
+    _point_at_bundled_nccl()
     try:
         L = ctypes.CDLL(path)
     except OSError as e:  # pragma: no cover

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <mutex>
 #include <numeric>
 #include <thread>
 #include <type_traits>
@@ -907,8 +908,13 @@ static int launch_sweep(cgs_model *m, const SweepParams &p, int *blocks_cache) {
         if constexpr (std::is_same<R, float>::value) {
             // the exchange blocks come first in the grid and must all be resident: they wait for each other and
             // for the peers; the sampling blocks take whatever is left of the device and pull cells from the queue
-            blocks = std::max(1, std::min(blocks, *cache - p.x_ctas));
-            sweep_kernel<TPT, CH, float, true><<<blocks + p.x_ctas, m->threads, 0, m->stream>>>(p, m->x_fused);
+            // (a request for more exchange blocks than fit beside one sampling block would leave some of them waiting
+            // for an SM while the resident ones wait for them at the barrier: clamp it to what this kernel can hold)
+            SweepParams q = p;
+            q.x_ctas = std::min(p.x_ctas, *cache - 1);
+            if (q.x_ctas < 1) CGS_FAIL("the device cannot hold an exchange block beside a sampling block");
+            blocks = std::max(1, std::min(blocks, *cache - q.x_ctas));
+            sweep_kernel<TPT, CH, float, true><<<blocks + q.x_ctas, m->threads, 0, m->stream>>>(q, m->x_fused);
         } else {
             CGS_FAIL("the fused sweep + exchange launch exists for the fp32 conditional only");
         }
@@ -1483,17 +1489,21 @@ int cgs_model_region_histogram(cgs_model *m, int32_t *d_hist, int64_t *ndk_misma
     DeviceGuard g(c->device);
     const size_t WKp = (size_t)c->n_regions * (size_t)m->Kp;
     unsigned long long *d_bad = nullptr;
-    CGS_TRY(dmalloc(&d_bad, 2, m->stream));
-    CGS_CUDA(cudaMemsetAsync(d_bad, 0, 2 * sizeof(unsigned long long), m->stream));
-    CGS_CUDA(cudaMemsetAsync(d_hist, 0, WKp * 4, m->stream));
-    const int blocks = std::max(1, std::min(c->n_cells, c->num_sms * 8));
-    recount_kernel<<<blocks, 256, sizeof(int) * (size_t)m->Kp, m->stream>>>(c->d_cell_ptr, c->d_tok_region, m->d_z, c->n_cells,
-                                                                           m->K, m->Kp, m->d_ndk, d_hist, d_bad);
-    CGS_CUDA(cudaGetLastError());
-    m->launches += 1;
     unsigned long long bad[2] = {0, 0};
-    CGS_CUDA(cgs_memcpy_sync(m->stream, bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost));
+    CGS_TRY(dmalloc(&d_bad, 2, m->stream));
+    const int rc = [&]() -> int {
+        CGS_CUDA(cudaMemsetAsync(d_bad, 0, 2 * sizeof(unsigned long long), m->stream));
+        CGS_CUDA(cudaMemsetAsync(d_hist, 0, WKp * 4, m->stream));
+        const int blocks = std::max(1, std::min(c->n_cells, c->num_sms * 8));
+        recount_kernel<<<blocks, 256, sizeof(int) * (size_t)m->Kp, m->stream>>>(c->d_cell_ptr, c->d_tok_region, m->d_z, c->n_cells,
+                                                                               m->K, m->Kp, m->d_ndk, d_hist, d_bad);
+        CGS_CUDA(cudaGetLastError());
+        m->launches += 1;
+        CGS_CUDA(cgs_memcpy_sync(m->stream, bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost));
+        return 0;
+    }();
     dfree(d_bad, m->stream);
+    if (rc != 0) return rc;
     if (ndk_mismatches) *ndk_mismatches = (int64_t)bad[0];
     return 0;
 }
@@ -1513,22 +1523,26 @@ int cgs_model_verify_counts(cgs_model *m, const int32_t *d_hist, int64_t *out3) 
     }
     unsigned long long *d_bad = nullptr;
     long long *d_col = nullptr;
-    CGS_TRY(dmalloc(&d_bad, 2, m->stream));
-    CGS_TRY(dmalloc(&d_col, (size_t)m->Kp, m->stream));
-    CGS_CUDA(cudaMemsetAsync(d_bad, 0, 2 * sizeof(unsigned long long), m->stream));
-    CGS_CUDA(cudaMemsetAsync(d_col, 0, sizeof(long long) * (size_t)m->Kp, m->stream));
-    compare_counts_kernel<<<c->num_sms * 4, 256, sizeof(long long) * (size_t)m->Kp, m->stream>>>(
-        m->d_nwk, d_hist, (int64_t)WKp, m->Kp, d_bad, d_col);
-    CGS_CUDA(cudaGetLastError());
-    m->launches += 1;
-    unsigned long long bad[2];
+    unsigned long long bad[2] = {0, 0};
     std::vector<long long> col((size_t)m->Kp);
     std::vector<int32_t> nk((size_t)m->Kp);
-    CGS_CUDA(cudaMemcpyAsync(bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost, m->stream));
-    CGS_CUDA(cudaMemcpyAsync(col.data(), d_col, sizeof(long long) * col.size(), cudaMemcpyDeviceToHost, m->stream));
-    CGS_CUDA(cudaMemcpyAsync(nk.data(), m->d_nk, sizeof(int32_t) * nk.size(), cudaMemcpyDeviceToHost, m->stream));
-    CGS_CUDA(cudaStreamSynchronize(m->stream));
+    const int rc = [&]() -> int {
+        CGS_TRY(dmalloc(&d_bad, 2, m->stream));
+        CGS_TRY(dmalloc(&d_col, (size_t)m->Kp, m->stream));
+        CGS_CUDA(cudaMemsetAsync(d_bad, 0, 2 * sizeof(unsigned long long), m->stream));
+        CGS_CUDA(cudaMemsetAsync(d_col, 0, sizeof(long long) * (size_t)m->Kp, m->stream));
+        compare_counts_kernel<<<c->num_sms * 4, 256, sizeof(long long) * (size_t)m->Kp, m->stream>>>(
+            m->d_nwk, d_hist, (int64_t)WKp, m->Kp, d_bad, d_col);
+        CGS_CUDA(cudaGetLastError());
+        m->launches += 1;
+        CGS_CUDA(cudaMemcpyAsync(bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost, m->stream));
+        CGS_CUDA(cudaMemcpyAsync(col.data(), d_col, sizeof(long long) * col.size(), cudaMemcpyDeviceToHost, m->stream));
+        CGS_CUDA(cudaMemcpyAsync(nk.data(), m->d_nk, sizeof(int32_t) * nk.size(), cudaMemcpyDeviceToHost, m->stream));
+        CGS_CUDA(cudaStreamSynchronize(m->stream));
+        return 0;
+    }();
     dfree(d_bad, m->stream); dfree(d_col, m->stream); dfree(own_hist, m->stream);
+    if (rc != 0) return rc;
     out3[1] = (int64_t)bad[1];
     out3[2] = 0;
     for (int k = 0; k < m->Kp; ++k)
@@ -1542,14 +1556,18 @@ int cgs_model_state_hash(cgs_model *m, uint64_t *out4) {
     DeviceGuard g(c->device);
     unsigned long long *d_out = nullptr;
     CGS_TRY(dmalloc(&d_out, 4, m->stream));
-    CGS_CUDA(cudaMemsetAsync(d_out, 0, 4 * sizeof(unsigned long long), m->stream));
-    state_hash_kernel<<<c->num_sms * 4, 256, 0, m->stream>>>(m->d_nwk, (int64_t)c->n_regions * m->Kp, d_out);
-    state_hash_kernel<<<1, 256, 0, m->stream>>>(m->d_nk, (int64_t)m->Kp, d_out + 2);
-    CGS_CUDA(cudaGetLastError());
-    m->launches += 2;
-    unsigned long long h[4];
-    CGS_CUDA(cgs_memcpy_sync(m->stream, h, d_out, sizeof h, cudaMemcpyDeviceToHost));
+    unsigned long long h[4] = {0, 0, 0, 0};
+    const int rc = [&]() -> int {
+        CGS_CUDA(cudaMemsetAsync(d_out, 0, 4 * sizeof(unsigned long long), m->stream));
+        state_hash_kernel<<<c->num_sms * 4, 256, 0, m->stream>>>(m->d_nwk, (int64_t)c->n_regions * m->Kp, d_out);
+        state_hash_kernel<<<1, 256, 0, m->stream>>>(m->d_nk, (int64_t)m->Kp, d_out + 2);
+        CGS_CUDA(cudaGetLastError());
+        m->launches += 2;
+        CGS_CUDA(cgs_memcpy_sync(m->stream, h, d_out, sizeof h, cudaMemcpyDeviceToHost));
+        return 0;
+    }();
     dfree(d_out, m->stream);
+    if (rc != 0) return rc;
     out4[0] = h[0]; out4[1] = h[1]; out4[2] = h[3]; out4[3] = h[2];  // hash(n_wk), sum(n_wk), sum(n_k), hash(n_k)
     return 0;
 }
@@ -1834,9 +1852,16 @@ struct NcclApi {
 };
 static NcclApi g_nccl;
 
+static std::mutex g_nccl_mutex;
+
 static int nccl_api() {
+    std::lock_guard<std::mutex> lock(g_nccl_mutex);  // shards driven by several host threads resolve it once
     if (g_nccl.lib) return 0;
+    // the copy this process already uses, else the one the host names (pycistopic_b200/_lib.py points CGS_NCCL_LIBRARY at
+    // the NCCL wheel torch will load, so that a later `import torch` meets its own library), else the loader's choice
     void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+    const char *named = getenv("CGS_NCCL_LIBRARY");
+    if (!h && named && named[0]) h = dlopen(named, RTLD_NOW | RTLD_GLOBAL);
     if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
     if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
     if (!h) CGS_FAIL(std::string("cannot load libnccl.so.2: ") + dlerror());

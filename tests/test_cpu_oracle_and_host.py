@@ -643,3 +643,29 @@ def test_pin_against_pypi_runs_or_reports_absent():
         assert code == pin.EXIT_ABSENT
     else:
         assert code == pin.EXIT_PINNED, report
+
+
+def test_lazy_nccl_resolution_does_not_break_a_later_torch_import():
+    """cgs_nccl_* dlopen NCCL at first use.  In a process that has not imported torch yet the loader's default is the
+    SYSTEM libnccl.so.2; torch would then be bound to it by soname and fail on the symbols only its own (newer) wheel
+    has.  _lib.load() therefore names the wheel's copy in CGS_NCCL_LIBRARY: the id call must load that file and
+    `import torch` must still work afterwards (fresh interpreter; ncclGetUniqueId needs no GPU)."""
+    import subprocess
+    code = (
+        "import ctypes, os, sys\n"
+        f"sys.path.insert(0, {ROOT!r})\n"
+        "from pycistopic_b200 import _lib\n"
+        "L = _lib.load()\n"
+        "assert 'torch' not in sys.modules\n"
+        "uid = ctypes.create_string_buffer(128)\n"
+        "assert L.cgs_nccl_unique_id(uid) == 0, L.cgs_last_error()\n"
+        "assert any(uid.raw)\n"
+        "loaded = sorted(set(l.split()[-1] for l in open('/proc/self/maps') if 'libnccl' in l))\n"
+        "named = os.environ.get('CGS_NCCL_LIBRARY')\n"
+        "assert named is None or loaded == [os.path.realpath(named)] or loaded == [named], (named, loaded)\n"
+        "import torch\n"
+        "print('ok', loaded)\n"
+    )
+    env = {k: v for k, v in os.environ.items() if k != "CGS_NCCL_LIBRARY"}
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout + r.stderr

@@ -380,3 +380,30 @@ def test_overlapped_sweeps_single_rank_mechanics(small, K, n_blocks):
     for mode in ("overlapped", "blocked"):
         assert abs(a - np.mean(lls[mode])) / abs(a) < 0.01, lls
     corpus.close()
+
+
+@pytest.mark.parametrize("K", [10, 50])
+def test_overlapped_sweep_clamps_the_exchange_blocks_to_what_is_resident(small, K):
+    """The exchange blocks of the fused launch wait for each other, so all of them must be resident at once: a request
+    for more blocks than the sweep kernel can keep on the device (here: the ABI's upper limit, four per SM, which the
+    two-chunk kernels cannot hold) must be clamped, not left to run into the 4 s barrier timeout."""
+    import time
+
+    from pycistopic_b200 import Corpus, DeviceModel
+    from pycistopic_b200.adlda import balanced_region_blocks
+    corpus = Corpus.from_regions_by_cells(small)
+    corpus.set_region_blocks(balanced_region_blocks(np.diff(small.indptr), 2))
+    mdl = DeviceModel(corpus, K, 50.0 / K, 0.1, seed=9)
+    mdl.init()
+    mdl.exchange_open([mdl.exchange_arena()[0]], 0)
+    mdl.exchange_sync()
+    mdl.sync()
+    t0 = time.perf_counter()
+    mdl.sweep_overlapped(5, 10 ** 6)
+    mdl.exchange_flush()
+    mdl.sync()
+    assert time.perf_counter() - t0 < 2.0
+    assert mdl.exchange_timeouts() == 0
+    assert mdl.verify_counts() == {"n_dk": 0, "n_wk": 0, "n_k": 0}
+    mdl.close()
+    corpus.close()
