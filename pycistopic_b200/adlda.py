@@ -257,8 +257,8 @@ class Exchanger:
         distributed = dist.is_available() and dist.is_initialized()
         self.world = dist.get_world_size() if distributed else 1
         self.rank = dist.get_rank() if distributed else 0
-        if exchange == "auto":
-            exchange = "peer" if self.world == 2 else "nccl"
+        if exchange == "auto":  # as fit_adlda resolves it when the sweep is not cut into parts
+            exchange = "overlap" if self.world > 1 and hasattr(shard, "arena_handle") else "nccl"
         self.mode = exchange
         self.rounds_per_sweep = max(1, int(rounds_per_sweep))
         self.n_ctas = n_ctas
