@@ -475,6 +475,31 @@ int cgs_fragment_counts_dims(const cgs_fragment_counts *h, int32_t *n_regions, i
 /* CSR to host: indptr int64[n_regions + 1], indices int32[nnz] (cells ascending inside a region), counts int32[nnz]. */
 int cgs_fragment_counts_export(const cgs_fragment_counts *h, int64_t *indptr, int32_t *indices, int32_t *counts);
 
+/* ---- fragments / regions BED files (host code, no device needed) -------------------
+ * The reader in front of cgs_fragment_counts_*: replaces read_fragments_to_pyranges (fragments.py:21-165, called at
+ * cistopic_class.py:814-817) and pyranges.read_bed (cistopic_class.py:835, :578) for the columns the path reads.
+ * Plain or gzip / bgzip text.  Blank lines and lines starting with '#' BEFORE the first record are skipped and the first
+ * record sets the column count (fragments.py:67-85); fewer than min_columns (4 for fragments, 3 for regions) fails with
+ * the reference's message (:87-91).  Columns: 1 Chromosome and 4 Name (barcode) as dictionary codes -- the dictionaries
+ * SORTED, as the categories of a pandas "category" column are; 2 Start and 3 End as int32; 5 Score as int32 when every
+ * value is an integer.  Later columns are ignored; a record with another column count, or a Start / End that is not a
+ * 32-bit integer, is an error naming the line.  n_threads <= 0: all host cores. */
+typedef struct cgs_bed_table cgs_bed_table;
+int cgs_bed_read(cgs_bed_table **out, const char *path, int32_t min_columns, int32_t n_threads);
+int cgs_bed_destroy(cgs_bed_table *t);
+/* score_state: 0 = no fifth column, 1 = int32 scores, 2 = a fifth column that is not all integers (exported as 0).
+ * *_chars = total bytes of the dictionary strings.  Any output may be NULL. */
+int cgs_bed_dims(const cgs_bed_table *t, int64_t *n_rows, int32_t *n_columns, int32_t *n_chromosomes,
+                 int64_t *chromosome_chars, int32_t *n_names, int64_t *name_chars, int32_t *score_state);
+/* Columns int32[n_rows] in file order; dictionaries as concatenated UTF-8 bytes + int64[n + 1] offsets.  Any output may
+ * be NULL (name / score must be NULL when the table has no such column). */
+int cgs_bed_export(const cgs_bed_table *t, int32_t *chromosome, int32_t *start, int32_t *end, int32_t *name, int32_t *score,
+                   char *chromosome_chars, int64_t *chromosome_offsets, char *name_chars, int64_t *name_offsets);
+/* collapse_duplicates (utils.py:284-293, applied at cistopic_class.py:819-829 when the file has no Score column): records
+ * equal in (Chromosome, Start, End, Name) become one record, Score = how many there were; the first of each group keeps
+ * its place. */
+int cgs_bed_collapse_duplicates(cgs_bed_table *t, int32_t n_threads, int64_t *n_removed);
+
 #ifdef __cplusplus
 }
 #endif

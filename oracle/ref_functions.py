@@ -168,3 +168,74 @@ def reference_evaluate_models():
     extra = {"pd": pd, "plt": _Inert(), "matplotlib": _Inert(), "subset_list": ns["subset_list"],
              "CistopicLDAModel": object}
     return _load("lda_models.py", ["evaluate_models"], extra=extra)["evaluate_models"]
+
+
+# ---- the count-matrix front end -------------------------------------------------------------------
+class _PyRangesStandIn:
+    """pyranges is absent: ``PyRanges(df)`` only has to hand the DataFrame back as ``.df``."""
+
+    def __init__(self, df):
+        self.df = df
+
+
+def reference_read_fragments_to_pyranges():
+    """fragments.py:21-165 with its "pandas" and "pyarrow" engines (both installed here; polars is not).  Returns a
+    function ``(path, engine) -> DataFrame``."""
+    import gzip
+    import types
+
+    import pandas as pd
+    import pyarrow as pa
+    import pyarrow.csv  # noqa: F401  (the reference reaches it as pa.csv)
+    ns = _load("utils.py", ["normalise_filepath"], extra={"os": os})
+    ns = _load("fragments.py", ["read_fragments_to_pyranges"],
+               extra={"normalise_filepath": ns["normalise_filepath"], "gzip": gzip, "pd": pd, "pa": pa, "pl": None,
+                      "pr": types.SimpleNamespace(PyRanges=_PyRangesStandIn), "Literal": typing.Literal})
+    fn = ns["read_fragments_to_pyranges"]
+    return lambda path, engine="pandas": fn(path, engine=engine).df
+
+
+def reference_collapse_duplicates():
+    """utils.py:284-293."""
+    import pandas as pd
+    return _load("utils.py", ["collapse_duplicates"], extra={"pd": pd})["collapse_duplicates"]
+
+
+def reference_prepare_tag_cells():
+    """utils.py:205-223."""
+    import re
+    return _load("utils.py", ["prepare_tag_cells"], extra={"re": re})["prepare_tag_cells"]
+
+
+class _ObjectStandIn:
+    """Records what ``create_cistopic_object`` hands to ``CistopicObject`` (cistopic_class.py:643-652)."""
+
+    def __init__(self, fragment_matrix, binary_matrix, cell_names, region_names, cell_data, region_data,
+                 path_to_fragments, project="cisTopic"):
+        self.fragment_matrix, self.binary_matrix = fragment_matrix, binary_matrix
+        self.cell_names, self.region_names = cell_names, region_names
+        self.cell_data, self.region_data = cell_data, region_data
+        self.path_to_fragments, self.project = path_to_fragments, project
+
+
+def reference_create_cistopic_object(region_names_to_coordinates):
+    """cistopic_class.py:508-655 without a blacklist (that step is pyranges).  ``region_names_to_coordinates`` of the
+    reference is polars code (utils.py:60-102): the caller supplies an equivalent."""
+    import sys
+
+    import pandas as pd
+    import sklearn.preprocessing as sp
+    u = _load("utils.py", ["subset_list", "non_zero_rows"])
+    ns = _load("cistopic_class.py", ["create_cistopic_object"],
+               extra={"pd": pd, "sp": sp, "sys": sys, "logging": logging, "CistopicObject": _ObjectStandIn,
+                      "subset_list": u["subset_list"], "non_zero_rows": u["non_zero_rows"],
+                      "region_names_to_coordinates": region_names_to_coordinates})
+    return ns["create_cistopic_object"]
+
+
+def reference_add_cell_data():
+    """``CistopicObject.add_cell_data`` (cistopic_class.py:88-142) as a function of (object, cell_data, split_pattern)."""
+    import pandas as pd
+    ns = _load("cistopic_class.py", ["add_cell_data"],
+               extra={"pd": pd, "prepare_tag_cells": reference_prepare_tag_cells()})
+    return ns["add_cell_data"]

@@ -19,7 +19,7 @@ NVCC_FLAGS = [
 def _sources():
     out = [os.path.join(_HERE, "..", "include", "cgs_b200.h")]
     for f in sorted(os.listdir(CSRC)):
-        if f.endswith((".cu", ".cuh", ".h")):
+        if f.endswith((".cu", ".cuh", ".h", ".cpp")):
             out.append(os.path.join(CSRC, f))
     return out
 
@@ -46,7 +46,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
             if not force and not needs_build():  # another rank built it while this one waited
                 return LIB_PATH
             tmp = f"{LIB_PATH}.tmp{os.getpid()}"
-            cmd = [nvcc, *NVCC_FLAGS, "-o", tmp, os.path.join(CSRC, "cgs_b200.cu"), "-lcuda"]
+            cmd = [nvcc, *NVCC_FLAGS, "-o", tmp, os.path.join(CSRC, "cgs_b200.cu"), os.path.join(CSRC, "bed_reader.cpp"),
+                   "-lcuda", "-lz"]  # bed_reader.cpp: host-only file reader (zlib for .gz)
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
             res = subprocess.run(cmd, capture_output=True, text=True)

@@ -135,6 +135,12 @@ SIGNATURES = {
     "cgs_fragment_counts_destroy": (ctypes.c_int, [c_vp]),
     "cgs_fragment_counts_dims": (ctypes.c_int, [c_vp, c_i32p, c_i32p, c_i64p, c_i64p]),
     "cgs_fragment_counts_export": (ctypes.c_int, [c_vp, c_i64p, c_i32p, c_i32p]),
+    "cgs_bed_read": (ctypes.c_int, [ctypes.POINTER(c_vp), ctypes.c_char_p, ctypes.c_int32, ctypes.c_int32]),
+    "cgs_bed_destroy": (ctypes.c_int, [c_vp]),
+    "cgs_bed_dims": (ctypes.c_int, [c_vp, c_i64p, c_i32p, c_i32p, c_i64p, c_i32p, c_i64p, c_i32p]),
+    "cgs_bed_export": (ctypes.c_int, [c_vp, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p, ctypes.c_char_p, c_i64p,
+                                      ctypes.c_char_p, c_i64p]),
+    "cgs_bed_collapse_duplicates": (ctypes.c_int, [c_vp, ctypes.c_int32, c_i64p]),
     "cgs_row_mean_var": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_vp, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
                                         c_f32p, c_f32p]),
     "cgs_row_mean_var_device": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, c_vp, ctypes.c_int64, ctypes.c_int64,

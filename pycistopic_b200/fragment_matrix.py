@@ -8,12 +8,18 @@ which binarises it (:592).  Here the overlap join and the counting run on the GP
 ``fragment_kernels.cuh``) and come back as a regions x cells CSR; the binarisation, the all-zero filters and
 the per-cell / per-region statistics follow the reference line by line on that sparse matrix.
 
-File parsing (pyranges / polars readers of the reference) is not rebuilt: fragments and regions are pandas
-DataFrames with the BED column names pyranges uses (``Chromosome``, ``Start``, ``End``, and ``Name`` = barcode).
+File parsing: ``read_fragments_from_file`` / ``read_bed`` stand where the reference calls
+``read_fragments_to_pyranges`` (fragments.py:21-165, at cistopic_class.py:814-817) and ``pyranges.read_bed`` (:835, :578):
+a native multi-threaded reader (``cgs_bed_*``, csrc/bed_reader.cpp; plain, gzip or bgzip text) that hands back the
+columns dictionary-coded, so the strings of a 10^8-line fragments file never become Python objects.  Fragments and
+regions may also be given as pandas DataFrames with the BED column names pyranges uses (``Chromosome``, ``Start``,
+``End``, and ``Name`` = barcode).
 """
 from __future__ import annotations
 
 import ctypes
+import os
+import re
 
 import numpy as np
 import pandas as pd
@@ -34,6 +40,127 @@ def _codes_in(values: pd.Series, categories: pd.Index) -> np.ndarray:
     return np.ascontiguousarray(categories.get_indexer(values).astype(np.int32))
 
 
+def _strings(chars: bytes, offsets: np.ndarray) -> list[str]:
+    return [chars[offsets[i]:offsets[i + 1]].decode("utf-8", "replace") for i in range(len(offsets) - 1)]
+
+
+def read_bed_table(path, min_columns=3, n_threads=0, collapse_duplicates=False) -> dict:
+    """One BED-like text file (plain / gzip / bgzip) through ``cgs_bed_read``.  Returns a dict with ``n_columns`` (of the
+    file), int32 arrays ``chromosome`` (codes), ``start``, ``end``, ``name`` (codes, 4+ columns) and ``score`` (5+ columns
+    of integers, or after ``collapse_duplicates``), the SORTED dictionaries ``chromosomes`` / ``names`` and
+    ``score_is_integer``.  ``collapse_duplicates``: utils.py:284-293 on a file WITHOUT a Score column (the condition of
+    cistopic_class.py:819); ``duplicates_removed`` tells how many records went."""
+    path = os.path.expanduser(os.fspath(path))  # utils.normalise_filepath
+    L = _lib.load()
+    h = c_vp()
+    check(L.cgs_bed_read(ctypes.byref(h), path.encode(), int(min_columns), int(n_threads)))
+    try:
+        n_rows, n_cols, n_chrom, n_names, state = (ctypes.c_int64(), ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32(),
+                                                   ctypes.c_int32())
+        chrom_chars, name_chars = ctypes.c_int64(), ctypes.c_int64()
+        removed = ctypes.c_int64(0)
+        check(L.cgs_bed_dims(h, None, ctypes.byref(n_cols), None, None, None, None, ctypes.byref(state)))
+        collapsed = bool(collapse_duplicates) and n_cols.value == 4
+        if collapsed:
+            check(L.cgs_bed_collapse_duplicates(h, int(n_threads), ctypes.byref(removed)))
+        check(L.cgs_bed_dims(h, ctypes.byref(n_rows), ctypes.byref(n_cols), ctypes.byref(n_chrom), ctypes.byref(chrom_chars),
+                             ctypes.byref(n_names), ctypes.byref(name_chars), ctypes.byref(state)))
+        n = n_rows.value
+        out = {"n_columns": n_cols.value, "duplicates_removed": removed.value if collapsed else None,
+               "chromosome": np.empty(n, np.int32), "start": np.empty(n, np.int32), "end": np.empty(n, np.int32)}
+        has_name, has_score = n_cols.value >= 4, state.value != 0
+        if has_name:
+            out["name"] = np.empty(n, np.int32)
+        if has_score:
+            out["score"] = np.empty(n, np.int32)
+        out["score_is_integer"] = state.value == 1
+        cbuf = ctypes.create_string_buffer(max(1, chrom_chars.value))
+        coff = np.empty(n_chrom.value + 1, np.int64)
+        nbuf = ctypes.create_string_buffer(max(1, name_chars.value))
+        noff = np.empty(n_names.value + 1, np.int64)
+        check(L.cgs_bed_export(h, ptr(out["chromosome"], c_i32p), ptr(out["start"], c_i32p), ptr(out["end"], c_i32p),
+                               ptr(out["name"], c_i32p) if has_name else None,
+                               ptr(out["score"], c_i32p) if has_score else None,
+                               cbuf, ptr(coff, c_i64p), nbuf if has_name else None, ptr(noff, c_i64p) if has_name else None))
+        out["chromosomes"] = _strings(cbuf.raw, coff)
+        out["names"] = _strings(nbuf.raw, noff) if has_name else []
+        return out
+    finally:
+        check(L.cgs_bed_destroy(h))
+
+
+def _table_to_frame(t: dict) -> pd.DataFrame:
+    df = pd.DataFrame({
+        "Chromosome": pd.Categorical.from_codes(t["chromosome"], categories=pd.Index(t["chromosomes"], dtype=object)),
+        "Start": t["start"], "End": t["end"]})
+    if "name" in t:
+        df["Name"] = pd.Categorical.from_codes(t["name"], categories=pd.Index(t["names"], dtype=object))
+    if "score" in t:
+        df["Score"] = t["score"]
+    return df
+
+
+def read_fragments_from_file(path_to_fragments, n_threads=0, collapse_duplicates=False) -> pd.DataFrame:
+    """The DataFrame behind ``read_fragments_to_pyranges(path).df`` (fragments.py:21-165) for the columns the count
+    matrix reads: ``Chromosome`` and ``Name`` categorical, ``Start`` / ``End`` int32, ``Score`` int32 when the file has
+    a fifth column.  Fewer than four columns raise the reference's ValueError."""
+    try:
+        t = read_bed_table(path_to_fragments, 4, n_threads, collapse_duplicates)
+    except _lib.CgsError as e:
+        if "needs to have at least" in str(e):
+            raise ValueError(re.sub(r" \[[^\]]*\]$", "", str(e))) from None
+        raise
+    return _table_to_frame(t)
+
+
+def read_bed(path_to_regions, n_threads=0) -> pd.DataFrame:
+    """``pyranges.read_bed(path)[["Chromosome", "Start", "End"]]`` as a DataFrame, records in file order
+    (cistopic_class.py:835-836, :578)."""
+    return _table_to_frame(read_bed_table(path_to_regions, 3, n_threads))[["Chromosome", "Start", "End"]]
+
+
+def regions_outside_blacklist(regions: pd.DataFrame, blacklist: pd.DataFrame) -> np.ndarray:
+    """Boolean mask of ``regions.overlap(blacklist, invert=True)`` (cistopic_class.py:575-579): a region goes when it
+    shares at least one base with a blacklisted interval of its chromosome (half-open intervals)."""
+    keep = np.ones(len(regions), bool)
+    r_chrom = regions["Chromosome"].astype(str).to_numpy()
+    r_start, r_end = regions["Start"].to_numpy().astype(np.int64), regions["End"].to_numpy().astype(np.int64)
+    b_chrom = blacklist["Chromosome"].astype(str).to_numpy()
+    for chrom in pd.unique(b_chrom):
+        rows = np.flatnonzero(r_chrom == chrom)
+        if len(rows) == 0:
+            continue
+        sel = b_chrom == chrom
+        bs, be = blacklist["Start"].to_numpy()[sel].astype(np.int64), blacklist["End"].to_numpy()[sel].astype(np.int64)
+        order = np.argsort(bs, kind="stable")
+        bs, be = bs[order], np.maximum.accumulate(be[order])  # furthest end among the intervals starting at or before
+        # intervals with start < region end: the first j of them; one overlaps iff the furthest of their ends > region start
+        j = np.searchsorted(bs, r_end[rows], side="left")
+        hit = (j > 0) & (be[np.maximum(j, 1) - 1] > r_start[rows])
+        keep[rows[hit]] = False
+    return keep
+
+
+def _device_counts(device, n_chrom, chrom_ptr, s_start, s_end, f_chrom, f_start, f_end, f_cell, n_cells):
+    """The device step: CSR (indptr int64, indices int32, counts int32) of the sorted regions x cells counts."""
+    _lib.require_device()
+    L = _lib.load()
+    h = c_vp()
+    check(L.cgs_fragment_counts_create(ctypes.byref(h), device, n_chrom, ptr(chrom_ptr, c_i32p), ptr(s_start, c_i32p),
+                                       ptr(s_end, c_i32p), len(f_cell), ptr(f_chrom, c_i32p),
+                                       ptr(f_start, c_i32p), ptr(f_end, c_i32p), ptr(f_cell, c_i32p), n_cells))
+    try:
+        nnz = ctypes.c_int64()
+        check(L.cgs_fragment_counts_dims(h, None, None, ctypes.byref(nnz), None))
+        indptr = np.empty(len(s_start) + 1, np.int64)
+        indices = np.empty(nnz.value, np.int32)
+        data = np.empty(nnz.value, np.int32)
+        check(L.cgs_fragment_counts_export(h, ptr(indptr, c_i64p), ptr(indices, c_i32p), ptr(data, c_i32p)))
+    finally:
+        check(L.cgs_fragment_counts_destroy(h))
+    return indptr, indices, data
+
+
 def count_fragments_in_regions(fragments: pd.DataFrame, regions: pd.DataFrame, valid_bc=None, device=0, timings=None):
     """Fragments-in-regions counts as a sparse matrix.
 
@@ -45,7 +172,6 @@ def count_fragments_in_regions(fragments: pd.DataFrame, regions: pd.DataFrame, v
     """
     import time
     t0 = time.perf_counter()
-    _lib.require_device()
     chrom = pd.Categorical(regions["Chromosome"].astype(str))
     r_chrom = chrom.codes.astype(np.int32)
     r_start = regions["Start"].to_numpy().astype(np.int32)
@@ -72,22 +198,9 @@ def count_fragments_in_regions(fragments: pd.DataFrame, regions: pd.DataFrame, v
     f_end = np.ascontiguousarray(fragments["End"].to_numpy().astype(np.int32))
     n_cells = max(1, len(cell_categories))
 
-    L = _lib.load()
-    h = c_vp()
     t1 = time.perf_counter()
-    check(L.cgs_fragment_counts_create(ctypes.byref(h), device, n_chrom, ptr(chrom_ptr, c_i32p), ptr(s_start, c_i32p),
-                                       ptr(s_end, c_i32p), len(f_cell), ptr(f_chrom, c_i32p),
-                                       ptr(f_start, c_i32p), ptr(f_end, c_i32p), ptr(f_cell, c_i32p), n_cells))
-    try:
-        nnz = ctypes.c_int64()
-        check(L.cgs_fragment_counts_dims(h, None, None, ctypes.byref(nnz), None))
-        R = len(order)
-        indptr = np.empty(R + 1, np.int64)
-        indices = np.empty(nnz.value, np.int32)
-        data = np.empty(nnz.value, np.int32)
-        check(L.cgs_fragment_counts_export(h, ptr(indptr, c_i64p), ptr(indices, c_i32p), ptr(data, c_i32p)))
-    finally:
-        check(L.cgs_fragment_counts_destroy(h))
+    R = len(order)
+    indptr, indices, data = _device_counts(device, n_chrom, chrom_ptr, s_start, s_end, f_chrom, f_start, f_end, f_cell, n_cells)
     t2 = time.perf_counter()
     m = sparse.csr_matrix((data, indices, indptr), shape=(R, n_cells))
     inv = np.empty(R, np.int64)
@@ -125,11 +238,54 @@ class CistopicObject:
     def __str__(self):
         return f"CistopicObject from project {self.project} with n_cells × n_regions = {len(self.cell_names)} × {len(self.region_names)}"
 
+    def add_cell_data(self, cell_data: pd.DataFrame, split_pattern: str = "___"):
+        """cistopic_class.py:88-142: join metadata indexed by cell name -- or by the bare barcode, when the object's
+        names carry the ``___project`` tag and the metadata's do not -- onto ``cell_data``; columns that exist are
+        overwritten, cells absent from the metadata get NaN."""
+        obj_cell_data = self.cell_data.copy()
+        obj_cell_names = list(self.cell_names)
+        by_barcode = False
+        present = set(obj_cell_names) & set(cell_data.index)
+        if len(present) < len(obj_cell_names):
+            bare = prepare_tag_cells(obj_cell_names, split_pattern)
+            if len(set(bare) & set(cell_data.index)) < len(present):
+                print("Warning: Some cells in this CistopicObject are not present in this cell_data. Values will be "
+                      "filled with Nan\n")
+            else:
+                by_barcode = True
+        common = [c for c in obj_cell_data.columns if c in set(cell_data.columns)]
+        if common:
+            print(f"Columns {common} will be overwritten")
+            obj_cell_data = obj_cell_data.loc[:, [c for c in obj_cell_data.columns if c not in set(common)]]
+        if by_barcode:
+            bare = prepare_tag_cells(obj_cell_names, split_pattern)
+            obj_cell_data.index = bare
+            cell_data = cell_data.loc[[b for b in dict.fromkeys(bare) if b in set(cell_data.index)],]
+            new_cell_data = pd.concat([obj_cell_data, cell_data], axis=1, sort=False).loc[bare]
+            new_cell_data.index = obj_cell_names
+        else:
+            cell_data = cell_data.loc[[c for c in obj_cell_names if c in present],]
+            new_cell_data = pd.concat([obj_cell_data, cell_data], axis=1, sort=False)
+        self.cell_data = new_cell_data.loc[obj_cell_names]
+
     def add_LDA_model(self, model):
         model.region_topic = model.topic_region  # the reference's spelling at cistopic_class.py:502
         model.cell_topic = model.cell_topic.loc[:, self.cell_names]
         model.topic_region = model.topic_region.loc[self.region_names]
         self.selected_model = model
+
+
+def prepare_tag_cells(cell_names, split_pattern="___"):
+    """utils.py:205-223: the barcode in front of the sample tag."""
+    if split_pattern == "-":
+        out = []
+        for x in cell_names:
+            m = re.findall(r"^[ACGT]*-[0-9]+-", x)
+            y = m[0].rstrip("-") if m else x
+            m2 = re.findall(r"^\w*-[0-9]*", y)
+            out.append(m2[0].rstrip("-") if m2 and y == x else y)
+        return out
+    return [x.split(split_pattern)[0] for x in cell_names]
 
 
 def region_names_to_coordinates(region_names):
@@ -141,10 +297,13 @@ def region_names_to_coordinates(region_names):
     return df
 
 
-def create_cistopic_object(fragment_matrix, cell_names=None, region_names=None, min_frag=1, min_cell=1, is_acc=1,
-                           path_to_fragments=None, project="cisTopic", tag_cells=True, split_pattern="___"):
-    """``create_cistopic_object`` (cistopic_class.py:508-655) without the blacklist step: binarise at ``is_acc``,
-    drop all-zero regions, per-cell and per-region statistics, ``min_frag`` / ``min_cell`` filters."""
+def create_cistopic_object(fragment_matrix, cell_names=None, region_names=None, path_to_blacklist=None, min_frag=1,
+                           min_cell=1, is_acc=1, path_to_fragments=None, project="cisTopic", tag_cells=True,
+                           split_pattern="___"):
+    """``create_cistopic_object`` (cistopic_class.py:508-655): blacklisted regions out (``path_to_blacklist``: a BED
+    file, or a DataFrame of intervals), binarise at ``is_acc``, drop all-zero regions, per-cell and per-region statistics,
+    ``min_frag`` / ``min_cell`` filters.  The regions keep their input order (the reference's blacklist step returns them
+    grouped by chromosome, a pyranges habit)."""
     if isinstance(fragment_matrix, pd.DataFrame):
         region_names = list(fragment_matrix.index)
         cell_names = list(fragment_matrix.columns.values)
@@ -153,6 +312,11 @@ def create_cistopic_object(fragment_matrix, cell_names=None, region_names=None, 
     cell_names, region_names = list(cell_names), list(region_names)
     if tag_cells:
         cell_names = [c + split_pattern + project for c in cell_names]
+    if path_to_blacklist is not None:
+        blacklist = path_to_blacklist if isinstance(path_to_blacklist, pd.DataFrame) else read_bed(path_to_blacklist)
+        keep = np.flatnonzero(regions_outside_blacklist(region_names_to_coordinates(region_names), blacklist))
+        fragment_matrix = fragment_matrix[keep,]
+        region_names = [region_names[i] for i in keep]
     # sklearn.preprocessing.binarize(X, threshold=is_acc - 1): 1 where the count exceeds the threshold
     binary_matrix = fragment_matrix.copy()
     binary_matrix.data = (binary_matrix.data > is_acc - 1).astype(np.int32)
@@ -193,12 +357,77 @@ def create_cistopic_object(fragment_matrix, cell_names=None, region_names=None, 
                           cell_data, region_data, path_to_fragments or {}, project)
 
 
-def create_cistopic_object_from_fragments(fragments, regions, valid_bc=None, min_frag=1, min_cell=1, is_acc=1,
-                                          project="cisTopic", split_pattern="___", device=0, **_ignored):
-    """The counting half of the reference function (cistopic_class.py:700-935) on the GPU.  ``fragments`` and
-    ``regions`` are DataFrames (``Chromosome``, ``Start``, ``End``; fragments also ``Name``) instead of file
-    paths; ``valid_bc`` selects barcodes (:855-857); ``n_cpu``, ``partition`` and blacklist / metrics arguments
-    of the reference are accepted and ignored."""
-    m, region_names, cell_names = count_fragments_in_regions(fragments, regions, valid_bc, device)
-    return create_cistopic_object(m, cell_names, region_names, min_frag=min_frag, min_cell=min_cell, is_acc=is_acc,
-                                  project=project, split_pattern=split_pattern)
+def _collapse_duplicates_frame(fragments: pd.DataFrame) -> pd.DataFrame:
+    """utils.py:284-293 on a DataFrame: one record per (Chromosome, Start, End, Name), ``Score`` = how many there were."""
+    keys = ["Chromosome", "Start", "End", "Name"]
+    out = fragments.groupby(keys, sort=False, observed=True).size().reset_index(name="Score")
+    out["Score"] = out["Score"].astype(np.int32)
+    return out
+
+
+def create_cistopic_object_from_fragments(path_to_fragments, path_to_regions, path_to_blacklist=None, metrics=None,
+                                          valid_bc=None, n_cpu=1, min_frag=1, min_cell=1, is_acc=1,
+                                          check_for_duplicates=True, project="cisTopic", partition=5, fragments_df=None,
+                                          split_pattern="___", use_polars=True, device=0):
+    """``create_cistopic_object_from_fragments`` (cistopic_class.py:738-935), same arguments in the same order.
+
+    ``path_to_fragments`` / ``path_to_regions`` are BED files (plain, gzip, bgzip) read by the native reader, or -- as
+    ``fragments_df`` of the reference -- DataFrames with ``Chromosome``, ``Start``, ``End`` (and ``Name``).  Without a
+    ``Score`` column duplicated fragments are collapsed when ``check_for_duplicates`` (:819-831; in the reader for a
+    file).  ``metrics`` (CellRanger ``singlecell.csv`` path or DataFrame, :844-853) and ``valid_bc`` (:854-856) select
+    barcodes; without ``metrics`` the number of fragments of every barcode becomes ``Unique_nr_frag`` (:857-866, :934).
+    The overlap join and the counting (:868-889) run on the GPU; ``n_cpu`` sets the reader's threads; ``partition`` and
+    ``use_polars`` (the reference's fallback for its dense intermediate, :896-929, and its reader switch) are accepted
+    and not needed."""
+    source = path_to_fragments if isinstance(path_to_fragments, (str, os.PathLike)) else None
+    if isinstance(path_to_fragments, pd.DataFrame) and fragments_df is None:
+        fragments_df = path_to_fragments
+    if hasattr(fragments_df, "df") and not isinstance(fragments_df, pd.DataFrame):
+        fragments_df = fragments_df.df  # a PyRanges
+    if isinstance(fragments_df, pd.DataFrame):
+        fragments = fragments_df
+        if "Score" not in fragments.columns:
+            fragments = _collapse_duplicates_frame(fragments) if check_for_duplicates else fragments.assign(Score=1)
+    else:
+        if source is None:
+            raise ValueError("path_to_fragments must be a file name when fragments_df is not given")
+        threads = 0 if n_cpu is None or n_cpu <= 1 else int(n_cpu)  # the reference's default n_cpu = 1 is about pyranges
+        fragments = read_fragments_from_file(source, threads, collapse_duplicates=check_for_duplicates)
+        if "Score" not in fragments.columns:
+            fragments["Score"] = np.int32(1)
+    regions = path_to_regions if isinstance(path_to_regions, pd.DataFrame) else read_bed(path_to_regions)
+    regions = regions[["Chromosome", "Start", "End"]]
+
+    if metrics is not None:
+        if isinstance(metrics, (str, os.PathLike)):
+            metrics = pd.read_csv(metrics)
+        if "is__cell_barcode" in metrics.columns:
+            metrics = metrics[metrics.is__cell_barcode == 1]
+            metrics.index = metrics.barcode
+            metrics = metrics.iloc[:, 2:]
+        fragments = fragments[fragments.Name.isin(set(metrics.index))]
+    if isinstance(valid_bc, list):
+        fragments = fragments[fragments.Name.isin(set(valid_bc))]
+    if metrics is None:
+        name = fragments["Name"]
+        if not isinstance(name.dtype, pd.CategoricalDtype):
+            name = name.astype("category")
+        per_barcode = np.bincount(name.cat.codes.to_numpy()[name.cat.codes.to_numpy() >= 0],
+                                  minlength=len(name.cat.categories))
+        used = np.flatnonzero(per_barcode)
+        barcodes = [str(b) for b in name.cat.categories[used]]
+        FPB_DF = pd.DataFrame({"Unique_nr_frag": per_barcode[used]}, index=barcodes)
+
+    # the filters above already removed every other barcode: the cells come out sorted, as without valid_bc
+    m, region_names, cell_names = count_fragments_in_regions(fragments, regions, None, device)
+    obj = create_cistopic_object(m, cell_names, region_names, path_to_blacklist=path_to_blacklist, min_frag=min_frag,
+                                 min_cell=min_cell, is_acc=is_acc, path_to_fragments={project: source}, project=project,
+                                 split_pattern=split_pattern)
+    if metrics is not None:
+        metrics = metrics.copy()
+        metrics["barcode"] = metrics.index.tolist()
+        obj.add_cell_data(metrics, split_pattern)
+    else:
+        FPB_DF["barcode"] = FPB_DF.index.tolist()
+        obj.add_cell_data(FPB_DF, split_pattern)
+    return obj
