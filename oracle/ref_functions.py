@@ -239,3 +239,48 @@ def reference_add_cell_data():
     ns = _load("cistopic_class.py", ["add_cell_data"],
                extra={"pd": pd, "prepare_tag_cells": reference_prepare_tag_cells()})
     return ns["add_cell_data"]
+
+
+# ---- run_cgs_model itself (A2 / A14): hyper-parameter scaling, metric block, DataFrame packing ----------------------
+def reference_run_cgs_model(lda_class, metric_functions):
+    """``run_cgs_model`` (lda_models.py:178-396, the Ray decorator dropped) and ``CistopicLDAModel`` (:31-96) executed
+    from the tree.  The two third-party packages it calls are absent and are stood in for: ``lda.LDA`` by ``lda_class``
+    (the oracle's restatement, or a recorder) and the four ``tmtoolkit`` functions by ``metric_functions`` -- a dict
+    ``metric_arun_2010`` / ``metric_cao_juan_2009`` / ``metric_coherence_mimno_2011`` / ``marginal_topic_distrib``.
+    Everything else -- the scaling of alpha / eta, which arguments reach the metrics and ``utils.loglikelihood``, the
+    seven DataFrames, the pickle -- is the reference's own code.  Returns ``(run_cgs_model, CistopicLDAModel)``."""
+    import pickle
+    import sys
+    import time
+    import types
+    import warnings
+    from itertools import chain
+
+    import pandas as pd
+    path = os.path.join(REFERENCE_ROOT, "src", "pycisTopic", "lda_models.py")
+    with open(path) as f:
+        tree = ast.parse(f.read())
+    cls = next(n for n in ast.walk(tree) if isinstance(n, ast.ClassDef) and n.name == "CistopicLDAModel")
+    for node in ast.walk(cls):
+        if isinstance(node, ast.FunctionDef):
+            node.returns = None
+            for a in node.args.args + node.args.kwonlyargs:
+                a.annotation = None
+    tm = types.SimpleNamespace(
+        topicmod=types.SimpleNamespace(
+            evaluate=types.SimpleNamespace(**{k: metric_functions[k] for k in (
+                "metric_arun_2010", "metric_cao_juan_2009", "metric_coherence_mimno_2011")}),
+            model_stats=types.SimpleNamespace(marginal_topic_distrib=metric_functions["marginal_topic_distrib"])))
+    extra = {"pd": pd, "sys": sys, "time": time, "os": os, "pickle": pickle, "warnings": warnings, "logging": logging,
+             "chain": chain, "lda": types.SimpleNamespace(LDA=lda_class), "tmtoolkit": tm,
+             "loglikelihood": reference_loglikelihood()}
+    # the class must be importable for the reference's pickle.dump (:394-395): give it a module of its own
+    home = types.ModuleType("oracle._reference_lda_models")
+    sys.modules[home.__name__] = home
+    extra["__name__"] = home.__name__
+    mod = ast.Module(body=[cls], type_ignores=[])
+    ast.fix_missing_locations(mod)
+    exec(compile(mod, path, "exec"), extra)
+    home.CistopicLDAModel = extra["CistopicLDAModel"]
+    ns = _load("lda_models.py", ["run_cgs_model"], extra=extra)
+    return ns["run_cgs_model"], ns["CistopicLDAModel"]

@@ -228,6 +228,58 @@ def test_model_packing_layout(fitted, tmp_path):
     assert obj.selected_model is model
 
 
+@pytest.mark.skipif(not rf.available(), reason="/root/reference is not here")
+def test_run_cgs_model_equals_the_reference_function_run_live(tmp_path, monkeypatch):
+    """A2 / A14: the reference's ``run_cgs_model`` (lda_models.py:178-396) executed from the tree -- ``lda.LDA`` stood
+    in for by the oracle, the four tmtoolkit functions by their restatements -- against the mirror on the same fitted
+    model: the seven DataFrames (values, dtypes, index and column names) and the model's attributes are identical, and
+    alpha / eta reach the sampler scaled the same way in all four ``*_by_topic`` combinations."""
+    made = []
+
+    class Recorder(lo.OracleLDA):
+        def __init__(self, **kw):
+            made.append(dict(kw))
+            super().__init__(**kw)
+            made[-1]["fitted"] = self
+
+    # tmtoolkit hands back a (K, 1) matrix for the np.matrix document lengths the reference passes (lda_models.py:337-341)
+    fns = dict(metric_arun_2010=lo.metric_arun_2010, metric_cao_juan_2009=lo.metric_cao_juan_2009,
+               metric_coherence_mimno_2011=lo.metric_coherence_mimno_2011,
+               marginal_topic_distrib=lambda dt, dl: np.asmatrix(lo.marginal_topic_distrib(dt, dl)).T)
+    ref_run, ref_class = rf.reference_run_cgs_model(Recorder, fns)
+    m, cells, regions = make_binary_matrix(n_cells=60, n_regions=400, density=0.08, n_true_topics=3, seed=3)
+    X = sp.csr_matrix(m.T)
+    frames = ["metrics", "coherence", "marg_topic", "topic_ass", "cell_topic", "topic_region", "parameters"]
+    for K, top, a_by, e_by in [(7, 5, True, False), (3, 5, True, True), (6, 2, False, False), (5, 5, False, True)]:
+        ref = ref_run(X, K, cells, regions, n_iter=12, random_state=555, alpha=50, alpha_by_topic=a_by, eta=0.1,
+                      eta_by_topic=e_by, top_topics_coh=top, save_path=str(tmp_path / "ref"))
+        fitted = made[-1].pop("fitted")
+        got = lda_models.build_cistopic_model(fitted, m, K, cells, regions, 12, 555, 50, a_by, 0.1, e_by, top,
+                                              ref.parameters.loc["time", "Parameter"], save_path=str(tmp_path / "got"))
+        for name in frames:
+            pd.testing.assert_frame_equal(getattr(got, name), getattr(ref, name), check_exact=False, rtol=1e-12)
+        assert (got.n_cells, got.n_regions, got.n_topic) == (ref.n_cells, ref.n_regions, ref.n_topic) == (60, len(regions), K)
+        assert str(got) == str(ref) and got.cell_topic_harmony == ref.cell_topic_harmony == []
+        assert sorted(os.listdir(tmp_path / "ref")) == sorted(os.listdir(tmp_path / "got"))
+        # what the mirror hands to ITS sampler (the device LDA, recorded instead of run)
+        seen = {}
+
+        class DeviceLDA:
+            def __init__(self, **kw):
+                seen.update(kw)
+
+            def fit(self, X):
+                return self
+
+        monkeypatch.setattr(lda_models, "LDA", DeviceLDA)
+        import types
+        lda_models._fit_cgs_model_on_corpus(types.SimpleNamespace(device=0), K, 12, 555, 50, a_by, 0.1, e_by)
+        for key in ("n_topics", "n_iter", "random_state", "alpha", "eta", "refresh"):
+            assert seen[key] == made[-1][key], key
+        assert seen["device_metrics"]["alpha"] == 50 and seen["device_metrics"]["eta"] == 0.1  # RAW values (:305)
+    assert [f for f in os.listdir(tmp_path / "ref")] and isinstance(ref, ref_class)
+
+
 def _fake_model(k, arun, cao, mimno, ll):
     metrics = pd.DataFrame([arun, cao, mimno, ll], index=["Arun_2010", "Cao_Juan_2009", "Mimno_2011", "loglikelihood"],
                            columns=["Metric"]).transpose()
