@@ -18,6 +18,9 @@
 #include <cstring>
 #include <functional>
 #include <memory>
+#include <mutex>
+#include <new>
+#include <exception>
 #include <future>
 #include <string>
 #include <string_view>
@@ -169,11 +172,29 @@ void parse_piece(const char *b, const char *e, int32_t n_columns, Worker *w, Pie
     }
 }
 
+// fn(0) .. fn(n - 1) side by side; the first exception of any of them is rethrown here once all have ended
 void run_parallel(int n, const std::function<void(int)> &fn) {
     std::vector<std::thread> th;
-    for (int i = 1; i < n; ++i) th.emplace_back(fn, i);
-    fn(0);
+    std::exception_ptr first;
+    std::mutex mu;
+    auto guarded = [&](int i) {
+        try {
+            fn(i);
+        } catch (...) {
+            std::lock_guard<std::mutex> lock(mu);
+            if (!first) first = std::current_exception();
+        }
+    };
+    for (int i = 1; i < n; ++i) {
+        try {
+            th.emplace_back(guarded, i);
+        } catch (...) {  // no thread to be had: that share is done here
+            guarded(i);
+        }
+    }
+    guarded(0);
     for (auto &t : th) t.join();
+    if (first) std::rethrow_exception(first);
 }
 
 // ---- the file as a stream of text ------------------------------------------------------------------------------
@@ -477,9 +498,17 @@ void flatten(cgs_bed_table *t) {
 
 }  // namespace
 
-extern "C" {
+// C++ exceptions (allocation failure, no thread to be had) end at the ABI as an error code
+#define CGS_BED_GUARD(call)                                                            \
+    try {                                                                              \
+        return call;                                                                   \
+    } catch (const std::bad_alloc &) {                                                 \
+        CGS_FAIL("out of host memory");                                                \
+    } catch (const std::exception &e) {                                                \
+        CGS_FAIL(std::string("unexpected failure: ") + e.what());                      \
+    }
 
-int cgs_bed_read(cgs_bed_table **out, const char *path, int32_t min_columns, int32_t n_threads) {
+static int bed_read(cgs_bed_table **out, const char *path, int32_t min_columns, int32_t n_threads) {
     if (!out || !path) CGS_FAIL("NULL argument");
     if (min_columns < 3 || min_columns > 5) CGS_FAIL("min_columns must be 3, 4 or 5");
     *out = nullptr;
@@ -662,6 +691,12 @@ int cgs_bed_read(cgs_bed_table **out, const char *path, int32_t min_columns, int
     return 0;
 }
 
+extern "C" {
+
+int cgs_bed_read(cgs_bed_table **out, const char *path, int32_t min_columns, int32_t n_threads) {
+    CGS_BED_GUARD(bed_read(out, path, min_columns, n_threads))
+}
+
 int cgs_bed_destroy(cgs_bed_table *t) {
     delete t;
     return 0;
@@ -696,8 +731,8 @@ static void export_strings(const std::vector<std::string> &v, char *chars, int64
     if (offsets) offsets[v.size()] = o;
 }
 
-int cgs_bed_export(const cgs_bed_table *t, int32_t *chromosome, int32_t *start, int32_t *end, int32_t *name, int32_t *score,
-                   char *chromosome_chars, int64_t *chromosome_offsets, char *name_chars, int64_t *name_offsets) {
+static int bed_export(const cgs_bed_table *t, int32_t *chromosome, int32_t *start, int32_t *end, int32_t *name, int32_t *score,
+                      char *chromosome_chars, int64_t *chromosome_offsets, char *name_chars, int64_t *name_offsets) {
     if (!t) CGS_FAIL("NULL table");
     if (name && t->n_columns < 4) CGS_FAIL("the file has no Name column");
     if (score && t->score_state == 0) CGS_FAIL("the table has no Score column");
@@ -722,10 +757,16 @@ int cgs_bed_export(const cgs_bed_table *t, int32_t *chromosome, int32_t *start, 
     return 0;
 }
 
+int cgs_bed_export(const cgs_bed_table *t, int32_t *chromosome, int32_t *start, int32_t *end, int32_t *name, int32_t *score,
+                   char *chromosome_chars, int64_t *chromosome_offsets, char *name_chars, int64_t *name_offsets) {
+    CGS_BED_GUARD(bed_export(t, chromosome, start, end, name, score, chromosome_chars, chromosome_offsets, name_chars,
+                             name_offsets))
+}
+
 // utils.py:284-293 collapse_duplicates: records equal in (Chromosome, Start, End, Name) become one record whose Score is
 // their number.  The first record of every group stays where it is (the reference returns the groups sorted; the order of
 // the records does not reach the count matrix).
-int cgs_bed_collapse_duplicates(cgs_bed_table *t, int32_t n_threads, int64_t *n_removed) {
+static int bed_collapse_duplicates(cgs_bed_table *t, int32_t n_threads, int64_t *n_removed) {
     if (!t) CGS_FAIL("NULL table");
     if (t->n_columns < 4) CGS_FAIL("collapsing duplicates needs the Name column");
     flatten(t);
@@ -790,6 +831,10 @@ int cgs_bed_collapse_duplicates(cgs_bed_table *t, int32_t n_threads, int64_t *n_
     t->score_state = 1;
     if (n_removed) *n_removed = (int64_t)(n - o);
     return 0;
+}
+
+int cgs_bed_collapse_duplicates(cgs_bed_table *t, int32_t n_threads, int64_t *n_removed) {
+    CGS_BED_GUARD(bed_collapse_duplicates(t, n_threads, n_removed))
 }
 
 }  // extern "C"
