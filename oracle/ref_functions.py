@@ -233,6 +233,19 @@ def reference_create_cistopic_object(region_names_to_coordinates):
     return ns["create_cistopic_object"]
 
 
+def reference_create_cistopic_object_from_matrix_file(region_names_to_coordinates):
+    """cistopic_class.py:656-735 on top of the reference's own ``create_cistopic_object``; the stand-in object gets the
+    reference's ``add_cell_data``."""
+    import sys
+
+    import pandas as pd
+    _ObjectStandIn.add_cell_data = reference_add_cell_data()
+    ns = _load("cistopic_class.py", ["create_cistopic_object_from_matrix_file"],
+               extra={"pd": pd, "sys": sys, "logging": logging,
+                      "create_cistopic_object": reference_create_cistopic_object(region_names_to_coordinates)})
+    return ns["create_cistopic_object_from_matrix_file"]
+
+
 def reference_add_cell_data():
     """``CistopicObject.add_cell_data`` (cistopic_class.py:88-142) as a function of (object, cell_data, split_pattern)."""
     import pandas as pd

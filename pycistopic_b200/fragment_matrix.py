@@ -29,6 +29,11 @@ from . import _lib
 from ._lib import c_i32p, c_i64p, c_vp, check, ptr
 
 
+def _log():
+    import logging
+    return logging.getLogger("cisTopic")
+
+
 def _codes_in(values: pd.Series, categories: pd.Index) -> np.ndarray:
     """int32 position of every value in ``categories`` (-1 when absent).  A categorical column (how fragment
     files are read) is recoded through its few categories instead of its millions of values."""
@@ -355,6 +360,27 @@ def create_cistopic_object(fragment_matrix, cell_names=None, region_names=None, 
         region_names = region_data.index.to_list()
     return CistopicObject(sparse.csr_matrix(fragment_matrix), sparse.csr_matrix(binary_matrix), cell_names, region_names,
                           cell_data, region_data, path_to_fragments or {}, project)
+
+
+def create_cistopic_object_from_matrix_file(fragment_matrix_file, path_to_blacklist=None, compression=None, min_frag=1,
+                                            min_cell=1, is_acc=1, path_to_fragments=None, sample_id=None,
+                                            project="cisTopic", split_pattern="___"):
+    """``create_cistopic_object_from_matrix_file`` (cistopic_class.py:656-735): a tab-separated count matrix read as the
+    reference reads it (``pd.read_csv(sep="\\t", header=0)``): a header of cell names and records that start with the
+    region name, one field more than the header, which pandas then takes as the row names."""
+    if compression is not None:
+        fragment_matrix = pd.read_csv(fragment_matrix_file, sep="\t", header=0, compression=compression)
+    else:
+        fragment_matrix = pd.read_csv(fragment_matrix_file, sep="\t", header=0)
+    obj = create_cistopic_object(fragment_matrix, path_to_blacklist=path_to_blacklist, min_frag=min_frag, min_cell=min_cell,
+                                 is_acc=is_acc, path_to_fragments=path_to_fragments, project=project,
+                                 split_pattern=split_pattern)
+    if sample_id is not None:
+        if isinstance(path_to_fragments, dict):
+            obj.add_cell_data(sample_id, split_pattern)
+        else:
+            _log().error("Provide path_to_fragments with keys matching levels in sample_id!")
+    return obj
 
 
 def _collapse_duplicates_frame(fragments: pd.DataFrame) -> pd.DataFrame:

@@ -302,6 +302,28 @@ def test_create_cistopic_object_equals_the_reference_function(kw):
     assert got2.cell_names == ref.cell_names and (got2.binary_matrix != ref.binary_matrix).nnz == 0
 
 
+@needs_reference
+def test_object_from_matrix_file_equals_the_reference_function(tmp_path):
+    ref_create = rf.reference_create_cistopic_object_from_matrix_file(fm.region_names_to_coordinates)
+    m, cells, regions = _count_matrix(13)
+    frame = pd.DataFrame(m.toarray(), index=regions, columns=cells)
+    plain, packed = str(tmp_path / "matrix.tsv"), str(tmp_path / "matrix.tsv.gz")
+    # the format the reference expects: a header of cell names only, so that pandas takes the first field of every
+    # record -- the region -- as the row name
+    frame.to_csv(plain, sep="\t", index_label=False)
+    frame.to_csv(packed, sep="\t", index_label=False, compression="gzip")
+    sample = pd.DataFrame({"sample_id": "run7", "batch": np.arange(len(cells))}, index=[c + "___mx" for c in cells])
+    for path, kw in ((plain, {}), (packed, {"compression": "gzip"}),
+                     (plain, {"is_acc": 2, "sample_id": sample, "path_to_fragments": {"mx": "f.tsv.gz"}})):
+        ref = ref_create(path, project="mx", **{k: (v.copy() if isinstance(v, pd.DataFrame) else v) for k, v in kw.items()})
+        got = fm.create_cistopic_object_from_matrix_file(path, project="mx", **kw)
+        assert got.cell_names == ref.cell_names and got.region_names == ref.region_names
+        assert (got.binary_matrix != ref.binary_matrix).nnz == 0 and (got.fragment_matrix != ref.fragment_matrix).nnz == 0
+        pd.testing.assert_frame_equal(got.cell_data.sort_index(axis=1), ref.cell_data.sort_index(axis=1))
+        pd.testing.assert_frame_equal(got.region_data, ref.region_data, check_names=False)
+        assert got.path_to_fragments == ref.path_to_fragments
+
+
 def test_create_cistopic_object_min_frag_min_cell():
     """cistopic_class.py:617-638: cells with fewer than min_frag fragments go first; the region statistics, and with
     them the min_cell filter, are taken over the cells that are left."""
