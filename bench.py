@@ -1115,29 +1115,42 @@ def run_cuda(args):
         if world > 1:
             dist.barrier(group=host_group)
 
+    def extra_leg(fn, *a, one_rank=False, **kw):
+        """The legs behind the headline are extra keys of the line: where a failure cannot leave other ranks waiting
+        in a collective (one process, or a leg that rank 0 runs alone) it is reported under the leg's key instead of
+        costing the headline its line; a leg with collectives on several ranks fails the run, as before."""
+        if world > 1 and not one_rank:
+            return fn(*a, **kw)
+        try:
+            return fn(*a, **kw)
+        except Exception as e:  # noqa: BLE001 -- reported, not hidden
+            import traceback
+            traceback.print_exc(file=sys.stderr)
+            return {"ok": False, "error": f"{type(e).__name__}: {e}"[:500]}
+
     impute = None
     if rank == 0 and not args.no_impute:
-        impute = run_impute_leg(args, dev, local_rank, peak)
+        impute = extra_leg(run_impute_leg, args, dev, local_rank, peak, one_rank=True)
     parity = None
     if rank == 0 and not args.no_parity:
-        parity = run_parity_leg(dev, local_rank)
+        parity = extra_leg(run_parity_leg, dev, local_rank, one_rank=True)
     torch.cuda.synchronize()
     host_barrier()
     adlda = None
     if not args.no_adlda:
-        adlda = run_adlda_leg(args, dev, rank, world, local_rank)
+        adlda = extra_leg(run_adlda_leg, args, dev, rank, world, local_rank)
     adlda_c4 = None
     if world >= 8 and not args.no_adlda and not args.no_c4:
-        adlda_c4 = run_adlda_leg(args, dev, rank, world, local_rank, shape="C4")
+        adlda_c4 = extra_leg(run_adlda_leg, args, dev, rank, world, local_rank, shape="C4")
     c5 = None
     if not args.no_c5:
-        c5 = run_c5_leg(args, dev, rank, world, local_rank)
+        c5 = extra_leg(run_c5_leg, args, dev, rank, world, local_rank)
     torch.cuda.synchronize()
     torch.cuda.empty_cache()
     host_barrier()
     sweep_wall_clock = None
     if rank == 0 and not args.no_target:
-        sweep_wall_clock = run_target_leg(dev, list(range(world)))
+        sweep_wall_clock = extra_leg(run_target_leg, dev, list(range(world)), one_rank=True)
     host_barrier()
 
     if rank == 0:
