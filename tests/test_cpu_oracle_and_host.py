@@ -34,6 +34,18 @@ def test_abi_exports_every_declared_symbol():
     assert L.cgs_version() >= 100 and L.cgs_max_topics() == 512
 
 
+def test_abi_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: the header compiles as C99 (no C++ types, no torch types in the signatures)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "use_header.c"
+    src.write_text('#include "cgs_b200.h"\nint main(void) { return cgs_version() == 0; }\n')
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-fsyntax-only",
+                    "-I", os.path.join(ROOT, "include"), str(src)], check=True, capture_output=True)
+
+
 def test_no_cpu_fallback_without_device():
     n = ctypes.c_int(0)
     rc = _lib.load().cgs_device_count(ctypes.byref(n))
