@@ -155,6 +155,80 @@ def test_paired_schedule_properties(costs, workers):
 
 
 # ---- GPU: the same invariants through the C ABI --------------------------------------------------------
+# ---- CPU: the fragments / BED reader (host code behind the C ABI) ----------------------------------------
+_FIELD = st.text(alphabet=st.characters(min_codepoint=33, max_codepoint=126), min_size=1, max_size=12)
+
+
+@st.composite
+def bed_files(draw):
+    """Records of a BED-like file with its layout choices: 3 to 6 columns, '\n' or '\r\n', blank lines between
+    records, '#' / blank header lines, with or without a last line end."""
+    n_cols = draw(st.integers(3, 6))
+    n = draw(st.integers(1, 60))
+    chroms = draw(st.lists(_FIELD.filter(lambda f: not f.startswith("#")), min_size=1, max_size=4, unique=True))
+    names = draw(st.lists(_FIELD, min_size=1, max_size=6, unique=True))
+    rows = []
+    for _ in range(n):
+        row = [draw(st.sampled_from(chroms)), draw(st.integers(-5, 2 ** 31 - 1)), draw(st.integers(0, 2 ** 31 - 1))]
+        if n_cols >= 4:
+            row.append(draw(st.sampled_from(names)))
+        if n_cols >= 5:
+            row.append(draw(st.integers(-3, 1000)))
+        if n_cols >= 6:
+            row.append(draw(st.sampled_from(["+", "-", "."])))
+        rows.append(row)
+    eol = draw(st.sampled_from(["\n", "\r\n"]))
+    header = "".join(draw(st.lists(st.sampled_from(["# comment" + eol, eol, "#" + eol, "  " + eol]), max_size=3)))
+    body = []
+    for row in rows:
+        body.append("\t".join(str(v) for v in row))
+        body.extend([""] * draw(st.integers(0, 1) if n < 20 else st.just(0)))  # blank lines between records
+    while body and body[-1] == "":
+        body.pop()
+    text = header + eol.join(body) + (eol if draw(st.booleans()) else "")
+    return rows, n_cols, text
+
+
+@settings(max_examples=60, **COMMON)
+@given(case=bed_files(), block=st.sampled_from([16, 23, 64, 257, 1 << 20]), threads=st.integers(1, 5),
+       packing=st.sampled_from(["plain", "gzip", "bgzf"]))
+def test_bed_reader_returns_the_records_of_the_file(case, block, threads, packing, tmp_path_factory):
+    import gzip
+
+    from pycistopic_b200 import fragment_matrix as fm
+    from test_cpu_fragment_files import _bgzf
+    rows, n_cols, text = case
+    raw = text.encode()
+    if packing == "gzip":
+        raw = gzip.compress(raw)
+    elif packing == "bgzf":
+        raw = _bgzf(raw, block=37)
+    path = str(tmp_path_factory.mktemp("bed") / "records.bed")
+    with open(path, "wb") as f:
+        f.write(raw)
+    os.environ["CGS_BED_BLOCK_BYTES"] = str(block)
+    try:
+        t = fm.read_bed_table(path, 3, n_threads=threads)
+    finally:
+        del os.environ["CGS_BED_BLOCK_BYTES"]
+    assert t["n_columns"] == n_cols and len(t["start"]) == len(rows)
+    assert t["chromosomes"] == sorted({r[0] for r in rows}) and [t["chromosomes"][c] for c in t["chromosome"]] == [r[0] for r in rows]
+    assert t["start"].tolist() == [r[1] for r in rows] and t["end"].tolist() == [r[2] for r in rows]
+    if n_cols >= 4:
+        assert t["names"] == sorted({r[3] for r in rows}) and [t["names"][c] for c in t["name"]] == [r[3] for r in rows]
+    if n_cols >= 5:
+        assert t["score_is_integer"] and t["score"].tolist() == [r[4] for r in rows]
+    if n_cols == 4:  # duplicates collapse to their first record, Score = multiplicity (utils.py:284-293)
+        c = fm.read_bed_table(path, 4, n_threads=threads, collapse_duplicates=True)
+        seen = {}
+        for r in rows:
+            seen[tuple(r)] = seen.get(tuple(r), 0) + 1
+        got = [(c["chromosomes"][a], s, e, c["names"][b]) for a, s, e, b in zip(c["chromosome"], c["start"].tolist(),
+                                                                                c["end"].tolist(), c["name"])]
+        assert got == list(seen) and c["score"].tolist() == list(seen.values())
+        assert c["duplicates_removed"] == len(rows) - len(seen)
+
+
 @pytest.mark.gpu
 @settings(max_examples=25, **COMMON)
 @given(m=binary_matrices(), K=st.integers(1, 70), sweeps=st.integers(0, 3), seed=st.integers(0, 10 ** 6))
