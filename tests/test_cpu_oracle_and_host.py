@@ -46,6 +46,42 @@ def test_abi_header_is_plain_c(tmp_path):
                     "-I", os.path.join(ROOT, "include"), str(src)], check=True, capture_output=True)
 
 
+def build_c_host_example(workdir):
+    """gcc examples/host_example.c against the in-tree library; returns the binary (None without gcc)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        return None
+    _lib.load()  # builds the library first if the sources are newer
+    exe = os.path.join(str(workdir), "host_example")
+    lib_dir = os.path.join(ROOT, "pycistopic_b200")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "host_example.c"), "-L", lib_dir, "-lcgs_b200",
+                    f"-Wl,-rpath,{lib_dir}", "-lm", "-o", exe], check=True, capture_output=True)
+    return exe
+
+
+def test_c_host_example_builds_and_runs_its_host_part(tmp_path):
+    """A host without Python links the C ABI (examples/host_example.c): the file reader runs anywhere; without a GPU
+    the program says that the sampler has no CPU path and stops."""
+    import subprocess
+    exe = build_c_host_example(tmp_path)
+    if exe is None:
+        pytest.skip("no gcc")
+    frag = tmp_path / "f.tsv"
+    frag.write_text("chr1\t1\t5\tA\nchr1\t1\t5\tA\nchr2\t3\t9\tB\n")
+    res = subprocess.run([exe, str(frag)], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "3 records, 4 columns, 2 chromosomes, 2 barcodes" in res.stdout and "1 duplicate records collapsed" in res.stdout
+    n = ctypes.c_int(0)
+    if _lib.load().cgs_device_count(ctypes.byref(n)) != 0 or n.value < 1:
+        assert "no CUDA device" in res.stdout
+    else:
+        assert res.stdout.rstrip().endswith("OK")
+    bad = subprocess.run([exe, str(tmp_path / "absent.tsv")], capture_output=True, text=True, timeout=600)
+    assert bad.returncode == 1 and "cannot open" in bad.stderr
+
+
 def test_no_cpu_fallback_without_device():
     n = ctypes.c_int(0)
     rc = _lib.load().cgs_device_count(ctypes.byref(n))

@@ -37,3 +37,23 @@ def test_fragment_files_to_models(tmp_path):
     obj.add_LDA_model(models[0])
     assert obj.selected_model.cell_topic.shape == (4, len(obj.cell_names))
     assert int(models[0].topic_ass["Assignments"].sum()) == obj.binary_matrix.nnz
+
+
+def test_c_host_example_on_the_device(tmp_path):
+    """examples/host_example.c: a C host drives corpus -> model -> sweeps -> exports through the ABI and checks the
+    bookkeeping invariants itself; its initial log-likelihood is the oracle's for the same matrix (z = i mod K)."""
+    import re
+    import subprocess
+
+    from test_cpu_oracle_and_host import build_c_host_example
+    exe = build_c_host_example(tmp_path)
+    if exe is None:
+        pytest.skip("no gcc")
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and res.stdout.rstrip().endswith("OK"), res.stdout + res.stderr
+    m = re.search(r"(\d+) tokens, K = 4: log-likelihood (-?[\d.]+) -> (-?[\d.]+) after 150 sweeps", res.stdout)
+    assert m and int(m.group(1)) == 22432
+    # oracle/lda_oracle.OracleLDA on the matrix the program generates (xorshift64, seed in the source): -213918.78 at
+    # z = i mod K; after 150 sweeps eight seeds of the sequential chain end between -171 758 and -171 983
+    assert float(m.group(2)) == pytest.approx(-213918.78, abs=0.2)
+    assert float(m.group(3)) == pytest.approx(-171870.0, rel=0.01)  # the 1 % of north_star
