@@ -75,3 +75,40 @@ for path in (plain, gz, bgz):
 os.remove(plain)
 os.remove(gz)
 os.remove(bgz)
+
+# ---- duplicates: a four-column file (no Score), a third of the records repeated --------------------------------------
+# the reference collapses them per chromosome with utils.collapse_duplicates (np.lexsort over an object array,
+# cistopic_class.py:819-829); here: cgs_bed_collapse_duplicates inside the reader
+n4 = min(n, 3_000_000)
+dup = df.iloc[:n4, :4]
+dup = pd.concat([dup, dup.iloc[rng.integers(0, n4, n4 // 3)]], ignore_index=True)
+four = os.path.join(out, "bench_fragments4.tsv")
+dup.to_csv(four, sep="\t", header=False, index=False)
+size4, n_all = os.path.getsize(four), len(dup)
+n = n_all
+print(f"{n_all} records without Score, {n4 // 3} of them duplicates, {size4 / 1e6:.0f} MB plain")
+got = timed("plain cgs_bed_read + cgs_bed_collapse_duplicates", lambda: fm.read_bed_table(four, 4, collapse_duplicates=True), size4)
+
+
+def reference_way():
+    import pyarrow as pa
+    import pyarrow.csv
+    f = pa.csv.read_csv(four, read_options=pa.csv.ReadOptions(use_threads=True, column_names=names[:4]),
+                        parse_options=pa.csv.ParseOptions(delimiter="\t", quote_char=False),
+                        convert_options=pa.csv.ConvertOptions(column_types={
+                            "Chromosome": pa.dictionary(pa.int32(), pa.string()), "Start": pa.int32(), "End": pa.int32(),
+                            "Name": pa.dictionary(pa.int32(), pa.string())})).to_pandas()
+
+    def collapse(d):  # utils.py:284-293, verbatim arithmetic
+        a = d.values
+        sidx = np.lexsort(a[:, :4].T)
+        b = a[sidx, :4]
+        m = np.concatenate(([True], (b[1:] != b[:-1]).any(1), [True]))
+        return pd.DataFrame(np.column_stack((b[m[:-1], :4], np.diff(np.flatnonzero(m) + 1))),
+                            columns=["Chromosome", "Start", "End", "Name", "Score"])
+    return pd.concat([collapse(f[f.Chromosome == x]) for x in f.Chromosome.cat.categories.values])
+
+
+ref = timed("plain reference: pyarrow engine + collapse_duplicates", reference_way, size4)
+assert len(ref) == len(got["start"]) and int(ref["Score"].sum()) == int(got["score"].sum()) == n_all
+os.remove(four)
