@@ -297,3 +297,31 @@ def reference_run_cgs_model(lda_class, metric_functions):
     home.CistopicLDAModel = extra["CistopicLDAModel"]
     ns = _load("lda_models.py", ["run_cgs_model"], extra=extra)
     return ns["run_cgs_model"], ns["CistopicLDAModel"]
+
+
+class _RayStandIn:
+    """Ray is absent: tasks run where they are submitted (``f.remote(...)`` is the call, ``ray.get`` hands the list
+    back); ``init`` records what it was given (``n_cpu`` and the forwarded keyword arguments, lda_models.py:154)."""
+
+    def __init__(self):
+        self.init_calls, self.shutdowns = [], 0
+
+    def init(self, **kw):
+        self.init_calls.append(kw)
+
+    def get(self, results):
+        return results
+
+    def shutdown(self):
+        self.shutdowns += 1
+
+
+def reference_run_cgs_models(lda_class, metric_functions):
+    """``run_cgs_models`` (lda_models.py:99-175) on top of the reference's own ``run_cgs_model``; returns
+    ``(run_cgs_models, ray_stand_in)``."""
+    import types
+    run_one, _ = reference_run_cgs_model(lda_class, metric_functions)
+    ray = _RayStandIn()
+    ns = _load("lda_models.py", ["run_cgs_models"],
+               extra={"ray": ray, "run_cgs_model": types.SimpleNamespace(remote=run_one)})
+    return ns["run_cgs_models"], ray

@@ -328,6 +328,62 @@ def test_run_cgs_model_equals_the_reference_function_run_live(tmp_path, monkeypa
     assert [f for f in os.listdir(tmp_path / "ref")] and isinstance(ref, ref_class)
 
 
+@pytest.mark.skipif(not rf.available(), reason="/root/reference is not here")
+def test_run_cgs_models_equals_the_reference_function_run_live(tmp_path, monkeypatch):
+    """A1: the reference's ``run_cgs_models`` (lda_models.py:99-175; Ray stood in for by direct calls, ``lda.LDA`` by
+    the oracle) against the mirror's orchestration -- the device replaced, for this test only, by the same oracle
+    behind the two classes the orchestration talks to -- on two fake GPUs: same models in the order of ``n_topics``,
+    the same matrix orientation reaching the sampler, the same files under ``save_path``."""
+    fns = dict(metric_arun_2010=lo.metric_arun_2010, metric_cao_juan_2009=lo.metric_cao_juan_2009,
+               metric_coherence_mimno_2011=lo.metric_coherence_mimno_2011,
+               marginal_topic_distrib=lambda dt, dl: np.asmatrix(lo.marginal_topic_distrib(dt, dl)).T)
+    ref_run, ray = rf.reference_run_cgs_models(lambda **kw: lo.OracleLDA(**kw), fns)
+    m, cells, regions = make_binary_matrix(n_cells=50, n_regions=300, density=0.1, n_true_topics=3, seed=5)
+    obj = SyntheticCistopicObject(m, cells, regions)
+    topics = [6, 2, 9, 4]  # not sorted: the result keeps this order
+    kw = dict(n_iter=8, random_state=555, alpha=50, alpha_by_topic=True, eta=0.1, eta_by_topic=False, top_topics_coh=3)
+    ref = ref_run(obj, topics, n_cpu=3, save_path=str(tmp_path / "ref"), _temp_dir="/tmp/ray", **kw)
+    assert ray.init_calls == [{"num_cpus": 3, "_temp_dir": "/tmp/ray"}] and ray.shutdowns == 1
+
+    class HostCorpus:  # what lda_models asks of a Corpus
+        def __init__(self, regions_by_cells, device):
+            self.X, self.device = sp.csr_matrix(sp.csr_matrix(regions_by_cells).T), device
+
+        @staticmethod
+        def canonical_csr(matrix):
+            return sp.csr_matrix(matrix)
+
+        @classmethod
+        def from_regions_by_cells(cls, canonical, device=0):
+            return cls(canonical, device)
+
+        def close(self):
+            pass
+
+    class HostLDA:  # what lda_models asks of the device LDA
+        def __init__(self, n_topics, n_iter, random_state, alpha, eta, refresh, corpus=None, **_device_only):
+            self.inner, self.corpus = lo.OracleLDA(n_topics, n_iter, alpha, eta, random_state, refresh), corpus
+
+        def fit(self, X):
+            assert X is None  # the corpus is already on the "device"
+            o = self.inner.fit(self.corpus.X)
+            for name in ("topic_word_", "doc_topic_", "nzw_", "ndz_", "nz_", "final_loglikelihood_"):
+                setattr(self, name, getattr(o, name))
+            return self
+
+    monkeypatch.setattr(lda_models, "Corpus", HostCorpus)
+    monkeypatch.setattr(lda_models, "LDA", HostLDA)
+    monkeypatch.setattr(lda_models._lib, "require_device", lambda: 2)
+    got = lda_models.run_cgs_models(obj, topics, n_cpu=3, save_path=str(tmp_path / "got"), _temp_dir="/tmp/ray", **kw)
+    assert [g.n_topic for g in got] == [r.n_topic for r in ref] == topics
+    for g, r in zip(got, ref):
+        for name in ("metrics", "coherence", "marg_topic", "topic_ass", "cell_topic", "topic_region"):
+            pd.testing.assert_frame_equal(getattr(g, name), getattr(r, name), check_exact=False, rtol=1e-9)
+        pd.testing.assert_frame_equal(g.parameters.drop("time"), r.parameters.drop("time"))
+        assert (g.n_cells, g.n_regions) == (r.n_cells, r.n_regions) == (50, len(regions))
+    assert sorted(os.listdir(tmp_path / "got")) == sorted(os.listdir(tmp_path / "ref")) == sorted(f"Topic{k}.pkl" for k in topics)
+
+
 def _fake_model(k, arun, cao, mimno, ll):
     metrics = pd.DataFrame([arun, cao, mimno, ll], index=["Arun_2010", "Cao_Juan_2009", "Mimno_2011", "loglikelihood"],
                            columns=["Metric"]).transpose()
