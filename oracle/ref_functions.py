@@ -325,3 +325,32 @@ def reference_run_cgs_models(lda_class, metric_functions):
     ns = _load("lda_models.py", ["run_cgs_models"],
                extra={"ray": ray, "run_cgs_model": types.SimpleNamespace(remote=run_one)})
     return ns["run_cgs_models"], ray
+
+
+def reference_imputed_features_class():
+    """``CistopicImputedFeatures`` (diff_features.py:26-337: constructor, ``subset``, ``merge``, ``make_rankings``) and the
+    outer ``impute_accessibility`` (:340-508) executed from the tree; returns ``(class, impute_accessibility)``."""
+    import sys
+
+    import pandas as pd
+    path = os.path.join(REFERENCE_ROOT, "src", "pycisTopic", "diff_features.py")
+    with open(path) as f:
+        tree = ast.parse(f.read())
+    cls = next(n for n in ast.walk(tree) if isinstance(n, ast.ClassDef) and n.name == "CistopicImputedFeatures")
+    for node in ast.walk(cls):
+        if isinstance(node, ast.FunctionDef):
+            node.returns = None
+            for a in node.args.args + node.args.kwonlyargs:
+                a.annotation = None
+    u = _load("utils.py", ["subset_list", "non_zero_rows", "get_position_index"])
+    extra = {"pd": pd, "sys": sys, "logging": logging, "prepare_tag_cells": reference_prepare_tag_cells(),
+             "subset_list": u["subset_list"], "non_zero_rows": u["non_zero_rows"],
+             "get_position_index": u["get_position_index"], "__name__": "oracle._reference_diff_features"}
+    ns = {"math": math, "np": np, "sparse": sparse, "typing": typing}
+    ns.update(extra)
+    mod = ast.Module(body=[cls], type_ignores=[])
+    ast.fix_missing_locations(mod)
+    exec(compile(mod, path, "exec"), ns)
+    extra["CistopicImputedFeatures"] = ns["CistopicImputedFeatures"]
+    fn = _load("diff_features.py", ["impute_accessibility"], extra=extra)["impute_accessibility"]
+    return ns["CistopicImputedFeatures"], fn

@@ -134,6 +134,39 @@ class CistopicImputedFeatures:
         self.mtx, self.cell_names, self.feature_names = mtx, cell_names, feature_names
 
 
+    def merge(self, cistopic_imputed_features_list, project="cisTopic_impute_merge", copy=False):
+        """Append the cells of other :class:`CistopicImputedFeatures` (diff_features.py:131-272): features present in
+        both keep their values side by side, a feature missing on one side gets zeros there.  Rows come out as
+        [common, only in the objects so far, only in the added one]; the reference orders the common block by a Python
+        ``set`` (arbitrary), here it keeps the order of the object merged into.  As in the reference a merge that had to
+        add zero rows returns float64 (``np.zeros`` joins the stack)."""
+        mtx, feature_names, cell_names = self.mtx, list(self.feature_names), list(self.cell_names)
+        for other in cistopic_imputed_features_list:
+            add_mtx, add_features = other.mtx, list(other.feature_names)
+            cell_names = cell_names + list(other.cell_names)
+            in_cur, in_add = set(feature_names), set(add_features)
+            common = [f for f in feature_names if f in in_add]
+            sparse_in = scipy.sparse.issparse(mtx)
+            hstack = (lambda blocks: scipy.sparse.hstack(blocks, format="csr")) if sparse_in else np.hstack
+            vstack = (lambda blocks: scipy.sparse.vstack(blocks, format="csr")) if sparse_in else np.vstack
+            mtx_common = hstack([mtx[get_position_index(common, feature_names),],
+                                 add_mtx[get_position_index(common, add_features),]])
+            if in_cur != in_add:
+                only_cur = sorted(in_cur - in_add)  # np.setdiff1d: sorted
+                only_add = sorted(in_add - in_cur)
+                diff_1 = hstack([mtx[get_position_index(only_cur, feature_names),],
+                                 np.zeros((len(only_cur), add_mtx.shape[1]))])
+                diff_2 = hstack([np.zeros((len(only_add), mtx.shape[1])),
+                                 add_mtx[get_position_index(only_add, add_features),]])
+                mtx = vstack([mtx_common, diff_1, diff_2])
+                feature_names = common + only_cur + only_add
+            else:
+                mtx, feature_names = mtx_common, common
+        if copy is True:
+            return CistopicImputedFeatures(mtx, feature_names, cell_names, project)
+        self.mtx, self.cell_names, self.feature_names, self.project = mtx, cell_names, feature_names, project
+
+
 class FactoredImputedFeatures:
     """Imputed accessibility kept as its two factors (``impute_accessibility(..., materialize=False)``).
 

@@ -384,6 +384,68 @@ def test_run_cgs_models_equals_the_reference_function_run_live(tmp_path, monkeyp
     assert sorted(os.listdir(tmp_path / "got")) == sorted(os.listdir(tmp_path / "ref")) == sorted(f"Topic{k}.pkl" for k in topics)
 
 
+@pytest.mark.skipif(not rf.available(), reason="/root/reference is not here")
+def test_imputed_features_class_equals_the_reference_class_run_live(monkeypatch):
+    """A16's host side: ``impute_accessibility`` (diff_features.py:340-508: cell / region selection, dtypes, the
+    result class) and the ``subset`` / ``merge`` methods of ``CistopicImputedFeatures`` (:61-272), the reference's
+    code executed from the tree against the mirror.  The product itself -- the device's part, compared with the
+    reference's matrices in the GPU tests -- is the reference's nested function on both sides here."""
+    from pycistopic_b200 import diff_features as df
+    ref_class, ref_impute = rf.reference_imputed_features_class()
+    ref_product = rf.reference_calculate_imputed_accessibility()
+    monkeypatch.setattr(df, "calculate_imputed_accessibility",
+                        lambda topic_region, cell_topic, region_names, scale_factor, chunk_size, device=0, log=None:
+                        ref_product(topic_region, cell_topic, region_names, scale_factor, chunk_size))
+    rng = np.random.default_rng(31)
+    R, C, K = 90, 25, 4
+    regions, cells = [f"chr1:{100 * i}-{100 * i + 50}" for i in range(R)], [f"c{j}___s" for j in range(C)]
+    tr = rng.dirichlet(np.full(R, 0.05), K).T  # sparse-ish topics: some regions impute to zero and are dropped
+    ct = rng.dirichlet(np.full(K, 0.5), C).T
+    model = lda_models.CistopicLDAModel(None, None, None, None, pd.DataFrame(ct, index=[f"Topic{k + 1}" for k in range(K)], columns=cells),
+                                        pd.DataFrame(tr, index=regions, columns=[f"Topic{k + 1}" for k in range(K)]), None)
+    obj = SyntheticCistopicObject(sp.csr_matrix((R, C), dtype=np.int32), cells, regions)
+    obj.selected_model = model
+    for kw in (dict(), dict(scale_factor=1), dict(selected_cells=cells[3:15], selected_regions=regions[10:70][::-1], chunk_size=17)):
+        a, b = df.impute_accessibility(obj, project="p", **kw), ref_impute(obj, project="p", **kw)
+        assert a.mtx.dtype == b.mtx.dtype and np.array_equal(a.mtx, b.mtx)
+        if not kw:  # the int32 path truncates: regions that impute to zero everywhere are dropped
+            assert a.mtx.dtype == np.int32 and a.mtx.shape[0] < len(regions)
+        assert list(a.feature_names) == list(b.feature_names) and list(a.cell_names) == list(b.cell_names)
+        assert a.project == b.project and str(a) == str(b)
+
+    def pair(features, cell_list, seed, sparse_mtx=False):
+        m = np.random.default_rng(seed).integers(0, 3, (len(features), len(cell_list))).astype(np.int32)
+        m = sp.csr_matrix(m) if sparse_mtx else m
+        return (df.CistopicImputedFeatures(m.copy(), list(features), list(cell_list), "p"),
+                ref_class(m.copy(), list(features), list(cell_list), "p"))
+
+    # subset: by tagged names, by bare barcodes, by features; all-zero features go
+    for cells_arg, feats_arg in ((cells[2:9], None), ([c.split("___")[0] for c in cells[5:12]], regions[0:40:3]), (None, regions[50:60])):
+        a, b = pair(regions, cells, 1)
+        a2, b2 = a.subset(cells=cells_arg, features=feats_arg, copy=True), b.subset(cells=cells_arg, features=feats_arg, copy=True)
+        assert np.array_equal(a2.mtx, b2.mtx) and a2.feature_names == b2.feature_names and a2.cell_names == b2.cell_names
+        a.subset(cells=cells_arg, features=feats_arg)
+        b.subset(cells=cells_arg, features=feats_arg)
+        assert np.array_equal(a.mtx, b.mtx) and a.feature_names == b.feature_names and a.cell_names == b.cell_names
+    # merge: overlapping, disjoint and identical feature sets; dense and sparse; several objects at once
+    def same_up_to_row_order(a, b):
+        assert a.cell_names == b.cell_names and sorted(a.feature_names) == sorted(b.feature_names) and a.project == b.project
+        am, bm = (x.toarray() if sp.issparse(x) else np.asarray(x) for x in (a.mtx, b.mtx))
+        assert a.mtx.dtype == b.mtx.dtype and sp.issparse(a.mtx) == sp.issparse(b.mtx)
+        order = [b.feature_names.index(f) for f in a.feature_names]
+        assert np.array_equal(am, bm[order])
+
+    for sparse_mtx in (False, True):
+        for sets in ((regions[:40], regions[20:60]), (regions[:20], regions[20:30]), (regions[:30], regions[:30][::-1]),
+                     (regions[:40], regions[30:50], regions[45:80])):
+            mine, theirs = zip(*[pair(f, [f"s{i}_{c}" for c in cells[:4 + i]], 10 + i, sparse_mtx) for i, f in enumerate(sets)])
+            merged_a = mine[0].merge(list(mine[1:]), project="m", copy=True)
+            merged_b = theirs[0].merge(list(theirs[1:]), project="m", copy=True)
+            same_up_to_row_order(merged_a, merged_b)
+            mine[0].merge(list(mine[1:]), project="m")
+            same_up_to_row_order(mine[0], merged_b)
+
+
 def _fake_model(k, arun, cao, mimno, ll):
     metrics = pd.DataFrame([arun, cao, mimno, ll], index=["Arun_2010", "Cao_Juan_2009", "Mimno_2011", "loglikelihood"],
                            columns=["Metric"]).transpose()
