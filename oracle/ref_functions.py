@@ -354,3 +354,22 @@ def reference_imputed_features_class():
     extra["CistopicImputedFeatures"] = ns["CistopicImputedFeatures"]
     fn = _load("diff_features.py", ["impute_accessibility"], extra=extra)["impute_accessibility"]
     return ns["CistopicImputedFeatures"], fn
+
+
+def reference_find_diff_features():
+    """``find_diff_features`` (diff_features.py:716-836) with the reference's own ``markers`` chain beneath it (on the real
+    ``scipy.stats.ranksums``) and its own ``CistopicImputedFeatures``; Ray is not reached for ``n_cpu=1`` and is the
+    direct-call stand-in otherwise.  Returns ``(find_diff_features, CistopicImputedFeatures, helper functions)``."""
+    import sys
+    import types
+
+    import pandas as pd
+    from scipy.stats import ranksums
+    cls, _ = reference_imputed_features_class()
+    u = _load("utils.py", ["get_position_index"])
+    extra = {"get_position_index": u["get_position_index"], "ranksums": ranksums, "pd": pd, "sys": sys,
+             "logging": logging, "numba": types.SimpleNamespace(prange=range), "np": _NumpyWithAsfarray(),
+             "CistopicImputedFeatures": cls, "ray": _RayStandIn()}
+    ns = _load("diff_features.py", ["subset_array_second_axis", "mean_axis1", "get_log2_fc", "p_adjust_bh",
+                                    "get_wilcox_test_pvalues", "markers", "find_diff_features"], extra=extra)
+    return ns["find_diff_features"], cls, ns

@@ -446,6 +446,47 @@ def test_imputed_features_class_equals_the_reference_class_run_live(monkeypatch)
             same_up_to_row_order(mine[0], merged_b)
 
 
+@pytest.mark.skipif(not rf.available(), reason="/root/reference is not here")
+def test_find_diff_features_equals_the_reference_function_run_live(monkeypatch):
+    """N2's host side: ``find_diff_features`` (diff_features.py:716-836: contrasts from a cell_data column or given,
+    their names, the barcode groups, ``var_features``, BH adjustment, thresholds, ordering of the tables) -- the
+    reference's function with its own ``markers`` beneath it against the mirror, whose device step (rank sums and
+    log2FC of every contrast, compared with SciPy in the GPU tests) is the reference's arithmetic here."""
+    from pycistopic_b200 import diff_features as df
+    ref_find, ref_class, ref_ns = rf.reference_find_diff_features()
+
+    def host_contrasts(matrix, contrasts_cols, device=0):
+        n, R = len(contrasts_cols), matrix.shape[0]
+        stat, pval, l2fc = (np.full((n, R), np.nan) for _ in range(3))
+        for i, (f, b) in enumerate(contrasts_cols):
+            fg, bg = np.asarray(matrix)[:, f], np.asarray(matrix)[:, b]
+            pval[i] = ref_ns["get_wilcox_test_pvalues"](fg, bg)
+            l2fc[i] = ref_ns["get_log2_fc"](fg.astype(np.float64), bg.astype(np.float64))
+        return stat, pval, l2fc
+
+    monkeypatch.setattr(df, "ranksum_contrasts", host_contrasts)
+    rng = np.random.default_rng(41)
+    R, C = 120, 60
+    cells, regions = [f"c{j}___s" for j in range(C)], [f"chr2:{10 * i}-{10 * i + 5}" for i in range(R)]
+    kind = np.array(["A", "B", "C"])[np.arange(C) % 3]
+    mtx = rng.poisson(3.0, (R, C)).astype(np.float64)
+    for t, letter in enumerate("ABC"):  # planted signal: a block of regions per cell type
+        mtx[40 * t:40 * t + 15, kind == letter] *= 4
+    cell_data = pd.DataFrame({"celltype": kind, "other": 1}, index=cells)
+    cell_data.loc[cells[7], "celltype"] = np.nan  # a cell without a label is left out (dropna, :762)
+    obj = SyntheticCistopicObject(sp.csr_matrix((R, C), dtype=np.int32), cells, regions)
+    obj.cell_data = cell_data
+    cases = [dict(), dict(var_features=regions[5:100:2]), dict(contrasts=[[["A"], ["B"]], [["A", "B"], ["C"]]], adjpval_thr=0.2,
+                                                             log2fc_thr=0.5)]
+    for kw in cases:
+        got = df.find_diff_features(obj, df.CistopicImputedFeatures(mtx.copy(), list(regions), list(cells), "p"), "celltype", **kw)
+        want = ref_find(obj, ref_class(mtx.copy(), list(regions), list(cells), "p"), "celltype", **kw)
+        assert list(got) == list(want) and len(got) in (2, 3)
+        for name in want:
+            assert len(want[name]) >= 3
+            pd.testing.assert_frame_equal(got[name], want[name], check_exact=False, rtol=1e-12)
+
+
 def _fake_model(k, arun, cao, mimno, ll):
     metrics = pd.DataFrame([arun, cao, mimno, ll], index=["Arun_2010", "Cao_Juan_2009", "Mimno_2011", "loglikelihood"],
                            columns=["Metric"]).transpose()
