@@ -110,8 +110,8 @@ int cgs_model_debug_sweep_visits(cgs_model *model, int64_t *tokens_sampled);
  * The defaults are chosen from n_topics and the mean cell size at cgs_model_create. */
 int cgs_model_set_sweep_shape(cgs_model *m, int32_t lanes_per_token, int32_t warps_per_cell);
 /* Upper bound on the CTAs of the sweep kernel (0 = fill the GPU).  With 1 CTA, 32 lanes per
- * token and 1 warp per cell the sweep is an exact sequential Gibbs scan (used by the
- * stationarity test). */
+ * token and 1 warp per cell the cells are sampled one after the other, one token at a time (the
+ * concurrency studies of scripts/trace_check.py use it as their sequential end). */
 /* Number of distinct uniform draws per sweep (power of two >= 128; 0 = one independent draw per token).
  * Default 131072: lda reuses rands[i % 131072] inside a sweep and that reuse measurably
  * speeds up the transient of the chain, so the device sampler keeps the same reuse density. */
