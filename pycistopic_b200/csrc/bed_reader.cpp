@@ -4,9 +4,11 @@
 // column count from the first record, Chromosome and Name as dictionary-coded strings, Start / End as int32)
 // and pyranges.read_bed at cistopic_class.py:835,578; cgs_bed_collapse_duplicates is utils.py:284-293.
 //
-// No device work here: a block of the (gzip-)stream is inflated by the calling thread while the previous block is
-// tokenised by a pool of worker threads; every worker codes the strings it meets against its own dictionary and the
-// dictionaries are merged (sorted, as a pandas "category" column is) once the file has been read.
+// No device work here: the calling thread reads the next block of text -- plain files directly, BGZF (bgzip) files
+// with their members inflated side by side on all threads, any other gzip file through zlib's sequential reader --
+// while a pool of worker threads tokenises the previous block; every worker codes the strings it meets against its
+// own dictionary and the dictionaries are merged (sorted, as a pandas "category" column is) once the file has been
+// read.  The arrays a worker fills become chunks of the table as they are; the export copies the chunks side by side.
 #include "../../include/cgs_b200.h"
 
 #include <zlib.h>
@@ -371,6 +373,10 @@ struct Source {
                 }
                 const unsigned char *t = raw.data() + p + ms - 4;
                 size_t isize = (size_t)t[0] | ((size_t)t[1] << 8) | ((size_t)t[2] << 16) | ((size_t)t[3] << 24);
+                if (isize > 65536) {  // the format's limit; a damaged trailer must not size a buffer
+                    *err = "BGZF member claims more than 64 KiB of text";
+                    return -1;
+                }
                 if (got + out + isize > n) {
                     first_too_big = batch.empty();
                     break;
