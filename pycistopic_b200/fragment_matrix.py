@@ -127,23 +127,42 @@ def read_bed(path_to_regions, n_threads=0) -> pd.DataFrame:
 def regions_outside_blacklist(regions: pd.DataFrame, blacklist: pd.DataFrame) -> np.ndarray:
     """Boolean mask of ``regions.overlap(blacklist, invert=True)`` (cistopic_class.py:575-579): a region goes when it
     shares at least one base with a blacklisted interval of its chromosome (half-open intervals)."""
-    keep = np.ones(len(regions), bool)
+    return ~_overlaps_any(regions["Chromosome"].astype(str).to_numpy(), regions["Start"].to_numpy(),
+                          regions["End"].to_numpy(), blacklist)
+
+
+def _overlaps_any(chrom, start, end, regions: pd.DataFrame) -> np.ndarray:
+    """For every interval (chrom names, starts, ends): does it share a base with at least one of ``regions``?"""
+    hit = np.zeros(len(start), bool)
+    chrom = np.asarray(chrom)
     r_chrom = regions["Chromosome"].astype(str).to_numpy()
-    r_start, r_end = regions["Start"].to_numpy().astype(np.int64), regions["End"].to_numpy().astype(np.int64)
-    b_chrom = blacklist["Chromosome"].astype(str).to_numpy()
-    for chrom in pd.unique(b_chrom):
-        rows = np.flatnonzero(r_chrom == chrom)
+    for name in pd.unique(r_chrom):
+        rows = np.flatnonzero(chrom == name)
         if len(rows) == 0:
             continue
-        sel = b_chrom == chrom
-        bs, be = blacklist["Start"].to_numpy()[sel].astype(np.int64), blacklist["End"].to_numpy()[sel].astype(np.int64)
-        order = np.argsort(bs, kind="stable")
-        bs, be = bs[order], np.maximum.accumulate(be[order])  # furthest end among the intervals starting at or before
-        # intervals with start < region end: the first j of them; one overlaps iff the furthest of their ends > region start
-        j = np.searchsorted(bs, r_end[rows], side="left")
-        hit = (j > 0) & (be[np.maximum(j, 1) - 1] > r_start[rows])
-        keep[rows[hit]] = False
-    return keep
+        sel = r_chrom == name
+        rs = regions["Start"].to_numpy()[sel].astype(np.int64)
+        re_ = regions["End"].to_numpy()[sel].astype(np.int64)
+        order = np.argsort(rs, kind="stable")
+        rs, far = rs[order], np.maximum.accumulate(re_[order])  # furthest end among the regions starting at or before
+        j = np.searchsorted(rs, np.asarray(end)[rows], side="left")  # regions that start before the interval ends
+        hit[rows] = (j > 0) & (far[np.maximum(j, 1) - 1] > np.asarray(start)[rows])
+    return hit
+
+
+def get_fragments_in_peaks(fragments: pd.DataFrame, regions: pd.DataFrame) -> pd.DataFrame:
+    """``get_fragments_in_peaks`` (fragments.py:945-1021) on pandas frames: per barcode, over the fragments that overlap
+    at least one region (each such fragment once, ``how="first"``), ``total_fragments_in_peaks_count`` = sum of
+    ``Score`` and ``unique_fragments_in_peaks_count`` = their number; barcodes in the order they first appear among
+    those fragments (``group_by(maintain_order=True)``).  Host NumPy (a sorted-interval search per chromosome)."""
+    inside = _overlaps_any(fragments["Chromosome"].astype(str).to_numpy(), fragments["Start"].to_numpy(),
+                           fragments["End"].to_numpy(), regions)
+    sub = fragments.loc[inside, ["Name", "Score"]]
+    codes, barcodes = pd.factorize(sub["Name"].astype(str), sort=False)
+    return pd.DataFrame({"CB": barcodes,
+                         "total_fragments_in_peaks_count": np.bincount(codes, weights=sub["Score"].to_numpy(),
+                                                                       minlength=len(barcodes)).astype(np.int64),
+                         "unique_fragments_in_peaks_count": np.bincount(codes, minlength=len(barcodes)).astype(np.int64)})
 
 
 def _device_counts(device, n_chrom, chrom_ptr, s_start, s_end, f_chrom, f_start, f_end, f_cell, n_cells):

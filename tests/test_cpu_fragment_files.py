@@ -273,6 +273,25 @@ def test_blacklist_mask_equals_brute_force():
     assert 0 < keep.sum() < n and keep[regions.Chromosome == "chr3"].all()
 
 
+def test_fragments_in_peaks_equals_brute_force():
+    """fragments.py:945-1021: per barcode, the fragments that overlap at least one region -- how many, and their scores."""
+    frags = _fragments(14, n=3000, n_cells=20)
+    rng = np.random.default_rng(14)
+    regions = pd.DataFrame({"Chromosome": rng.choice(["chr1", "chr2", "chrX", "chr7"], 80), "Start": rng.integers(0, 200000, 80)})
+    regions["End"] = regions["Start"] + rng.integers(50, 4000, 80)  # overlapping regions: a fragment still counts once
+    got = fm.get_fragments_in_peaks(frags, regions)
+    inside = np.zeros(len(frags), bool)
+    for i, f in enumerate(frags.itertuples(index=False)):
+        r = regions[regions.Chromosome == f.Chromosome]
+        inside[i] = ((r.Start < f.End) & (f.Start < r.End)).any()
+    sub = frags[inside]
+    want = sub.groupby("Name", sort=False).agg(total=("Score", "sum"), unique=("Score", "size")).reset_index()
+    assert 0 < inside.sum() < len(frags)
+    assert got["CB"].tolist() == want["Name"].tolist()  # order of first appearance
+    np.testing.assert_array_equal(got["total_fragments_in_peaks_count"], want["total"])
+    np.testing.assert_array_equal(got["unique_fragments_in_peaks_count"], want["unique"])
+
+
 def _count_matrix(seed=7, n_regions=120, n_cells=30):
     rng = np.random.default_rng(seed)
     m = sp.random(n_regions, n_cells, density=0.2, random_state=seed, format="csr", dtype=np.float64)
