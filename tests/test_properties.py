@@ -229,6 +229,25 @@ def test_bed_reader_returns_the_records_of_the_file(case, block, threads, packin
         assert c["duplicates_removed"] == len(rows) - len(seen)
 
 
+_INTERVAL = st.tuples(st.sampled_from(["chr1", "chr2", "chrX"]), st.integers(0, 60), st.integers(0, 12))
+
+
+@settings(max_examples=150, **COMMON)
+@given(a=st.lists(_INTERVAL, min_size=1, max_size=25), b=st.lists(_INTERVAL, min_size=0, max_size=25))
+def test_interval_overlap_search_equals_all_pairs(a, b):
+    """The sorted-interval search behind the blacklist filter and get_fragments_in_peaks: half-open intervals, touching
+    ends do not overlap, nested and duplicated intervals, chromosomes present on one side only."""
+    import pandas as pd
+
+    from pycistopic_b200 import fragment_matrix as fm
+    frame = lambda rows: pd.DataFrame({"Chromosome": [r[0] for r in rows], "Start": [r[1] for r in rows],  # noqa: E731
+                                       "End": [r[1] + r[2] + 1 for r in rows]}).astype({"Start": np.int64, "End": np.int64})
+    A, B = frame(a), frame(b)
+    want = np.array([any(c == c2 and s < e2 and s2 < e for c2, s2, e2 in B.itertuples(index=False))
+                     for c, s, e in A.itertuples(index=False)], dtype=bool)
+    np.testing.assert_array_equal(fm.regions_outside_blacklist(A, B), ~want)
+
+
 @pytest.mark.gpu
 @settings(max_examples=25, **COMMON)
 @given(m=binary_matrices(), K=st.integers(1, 70), sweeps=st.integers(0, 3), seed=st.integers(0, 10 ** 6))
