@@ -26,10 +26,10 @@ for line in sass.splitlines():
     total[cur] += 1 if re.search(r"^\s+/\*[0-9a-f]{4}\*/", line) else 0
     for mm in pat.findall(line):
         counts[cur][mm] += 1
-want = sys.argv[1:] or ["sweep_kernel<4, 4, float>", "sweep_kernel<1, 1, float>", "sweep_kernel<2, 2, float>", "sweep_kernel<4, 4, double>",
-                        "exchange_round_kernel", "exchange_sync_kernel", "exchange_round_multi_kernel", "delta_apply_kernel",
-                        "impute_umma_pair_kernel", "impute_umma_kernel", "rank_columns_kernel", "ranksum_rows_kernel", "count_kernel",
-                        "recount_kernel", "topic_gram_kernel"]
+want = sys.argv[1:] or ["sweep_kernel<4, 4, float, false>", "sweep_kernel<4, 4, float, true>", "sweep_kernel<4, 4, double, false>",
+                        "sweep_kernel<1, 1, float, false>", "sweep_det_kernel<4, 4", "exchange_round_kernel", "exchange_sync_kernel",
+                        "delta_apply_kernel", "impute_umma_pair_kernel<true, 5>", "impute_umma_pair_kernel<true, 2>",
+                        "rank_columns_kernel<int>", "ranksum_rows_kernel<int>", "count_kernel", "recount_kernel", "topic_gram_kernel"]
 for name, c in counts.items():
     short = name.replace("cgs::", "").replace("void ", "")
     if not any(w in short for w in want):
