@@ -1116,17 +1116,7 @@ def run_cuda(args):
             dist.barrier(group=host_group)
 
     def extra_leg(fn, *a, one_rank=False, **kw):
-        """The legs behind the headline are extra keys of the line: where a failure cannot leave other ranks waiting
-        in a collective (one process, or a leg that rank 0 runs alone) it is reported under the leg's key instead of
-        costing the headline its line; a leg with collectives on several ranks fails the run, as before."""
-        if world > 1 and not one_rank:
-            return fn(*a, **kw)
-        try:
-            return fn(*a, **kw)
-        except Exception as e:  # noqa: BLE001 -- reported, not hidden
-            import traceback
-            traceback.print_exc(file=sys.stderr)
-            return {"ok": False, "error": f"{type(e).__name__}: {e}"[:500]}
+        return run_extra_leg(world, one_rank, fn, *a, **kw)
 
     impute = None
     if rank == 0 and not args.no_impute:
@@ -1185,6 +1175,20 @@ def run_cuda(args):
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def run_extra_leg(world, one_rank, fn, *a, **kw):
+    """The legs behind the headline are extra keys of the line: where a failure cannot leave other ranks waiting in a
+    collective (one process, or a leg that rank 0 runs alone) it is reported under the leg's key instead of costing
+    the headline its line; a leg with collectives on several ranks fails the run, as before."""
+    if world > 1 and not one_rank:
+        return fn(*a, **kw)
+    try:
+        return fn(*a, **kw)
+    except Exception as e:  # noqa: BLE001 -- reported, not hidden
+        import traceback
+        traceback.print_exc(file=sys.stderr)
+        return {"ok": False, "error": f"{type(e).__name__}: {e}"[:500]}
 
 
 def main():

@@ -928,3 +928,22 @@ def test_lazy_nccl_resolution_does_not_break_a_later_torch_import():
     env = {k: v for k, v in os.environ.items() if k != "CGS_NCCL_LIBRARY"}
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0 and r.stdout.startswith("ok"), r.stdout + r.stderr
+
+
+def test_bench_extra_leg_reports_failures_where_no_rank_is_left_waiting():
+    """bench.py: a failing extra leg is reported under its key in one process or when rank 0 runs it alone; a leg
+    with collectives on several ranks still fails the run."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_for_test", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+
+    def boom(what):
+        raise ValueError("bad " + what)
+
+    assert bench.run_extra_leg(1, False, lambda x, y=1: {"v": x + y}, 2, y=3) == {"v": 5}
+    assert bench.run_extra_leg(1, False, boom, "leg") == {"ok": False, "error": "ValueError: bad leg"}
+    assert bench.run_extra_leg(8, True, boom, "solo")["ok"] is False
+    with pytest.raises(ValueError):
+        bench.run_extra_leg(8, False, boom, "collective")
+
