@@ -904,6 +904,20 @@ def test_pin_against_pypi_runs_or_reports_absent():
         assert code == pin.EXIT_PINNED, report
 
 
+def test_pin_against_pyranges_runs_or_reports_absent():
+    """oracle/pin_against_pyranges.py: the interval join / blacklist / read_bed half of the count-matrix oracle against
+    the real pyranges wherever it is installed; here it must report it absent (and must not write a pin file)."""
+    from oracle import pin_against_pyranges as pin
+    try:
+        import pyranges  # noqa: F401
+        present = True
+    except Exception:
+        present = False
+    code, report = pin.run(verbose=False)
+    assert code == (pin.EXIT_PINNED if present else pin.EXIT_ABSENT), report
+    assert present or not os.path.exists(os.path.join(GOLD, "pyranges_pin.json"))
+
+
 def test_lazy_nccl_resolution_does_not_break_a_later_torch_import():
     """cgs_nccl_* dlopen NCCL at first use.  In a process that has not imported torch yet the loader's default is the
     SYSTEM libnccl.so.2; torch would then be bound to it by soname and fail on the symbols only its own (newer) wheel
