@@ -5,7 +5,8 @@ half-open intervals, one output row per (region, fragment) pair with region.Star
 fragment.Start < region.End on the same chromosome -- followed, verbatim, by the reference's pandas counting
 (``groupby(["Name", "regionID"], sort=False, observed=True).size().unstack(level="Name", fill_value=0)``).
 pyranges is not installed here, so the join itself is a plain NumPy all-pairs test per chromosome
-(**parity unpinned** for the join; the pandas half is the reference's own expression).
+(**parity unpinned** for the join -- oracle/pin_against_pyranges.py pins it wherever pyranges installs; the pandas
+half is the reference's own expression).
 """
 from __future__ import annotations
 
